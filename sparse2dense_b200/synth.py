@@ -1,0 +1,87 @@
+"""Seeded synthetic spinning-LiDAR scenes (Waymo-shaped).
+
+The reference trains/evaluates on Waymo sweeps loaded as ``[N,5]`` float32 rows
+``x, y, z, tanh(intensity), elongation`` (det3d/datasets/pipelines/loading.py:61-70).
+There is no dataset on the build or GPU boxes, so every test and the benchmark use
+this generator instead.  It is host-side numpy only: it
+produces the *input* of the hot path and is never timed.
+
+Scene model: a 64-beam sensor 2 m above a flat ground plane, a ring of vertical
+cylinders that occlude rays, a far "wall" for rays that hit nothing, two returns
+for a fraction of the rays.  The ray budget is tuned so that about 180 k points
+fall inside the Waymo detection range ``[-75.2,-75.2,-2, 75.2,75.2,4]``.
+"""
+import numpy as np
+
+WAYMO_RANGE = (-75.2, -75.2, -2.0, 75.2, 75.2, 4.0)
+WAYMO_VOXEL = (0.1, 0.1, 0.15)
+WAYMO_MAX_POINTS = 5
+WAYMO_MAX_VOXELS = 150000
+
+
+def lidar_scene(seed, n_beams=64, n_azimuth=2680, n_cylinders=120, second_return=0.10,
+                sensor_height=2.0, shuffle=False):
+    """Return one cloud ``float32 [N,5]``; deterministic in ``seed``."""
+    rng = np.random.default_rng(seed)
+    elev = np.deg2rad(np.linspace(-17.6, 2.4, n_beams))
+    az = np.linspace(0.0, 2.0 * np.pi, n_azimuth, endpoint=False)
+    az = az[None, :] + rng.uniform(0.0, 1e-3, size=(n_beams, 1))
+    el = np.broadcast_to(elev[:, None], az.shape)
+    dx, dy, dz = np.cos(el) * np.cos(az), np.cos(el) * np.sin(az), np.sin(el)
+
+    # ground hit (z = 0 plane, sensor at z = sensor_height)
+    with np.errstate(divide="ignore", invalid="ignore"):
+        t_ground = np.where(dz < -1e-6, -sensor_height / dz, np.inf)
+    # rays that hit nothing return from a far surface
+    t_far = rng.uniform(30.0, 80.0, size=az.shape)
+    t = np.minimum(t_ground, np.where(np.isfinite(t_ground), np.inf, t_far))
+    t = np.where(np.isfinite(t), t, t_far)
+
+    # vertical cylinders (cars / poles / trunks)
+    cx = rng.uniform(-70.0, 70.0, n_cylinders)
+    cy = rng.uniform(-70.0, 70.0, n_cylinders)
+    cr = rng.uniform(0.5, 3.0, n_cylinders)
+    ch = rng.uniform(1.0, 3.5, n_cylinders)
+    hxy = np.sqrt(dx * dx + dy * dy)
+    ux, uy = dx / hxy, dy / hxy
+    for k in range(n_cylinders):
+        if cx[k] * cx[k] + cy[k] * cy[k] < (cr[k] + 3.0) ** 2:
+            continue                                    # keep the ego footprint free
+        b = ux * cx[k] + uy * cy[k]
+        disc = b * b - (cx[k] * cx[k] + cy[k] * cy[k] - cr[k] * cr[k])
+        s = b - np.sqrt(np.maximum(disc, 0.0))          # horizontal distance to entry
+        tt = s / hxy
+        zhit = sensor_height + tt * dz
+        hit = (disc > 0) & (s > 0) & (zhit >= 0.0) & (zhit <= ch[k]) & (tt < t)
+        t = np.where(hit, tt, t)
+
+    t = t * (1.0 + rng.normal(0.0, 0.002, size=t.shape))
+    pts = np.stack([t * dx, t * dy, sensor_height + t * dz], axis=-1).reshape(-1, 3)
+
+    # second returns: a little behind the first one along the same ray
+    m2 = rng.uniform(size=t.shape) < second_return
+    t2 = t[m2] + rng.uniform(0.3, 2.5, size=int(m2.sum()))
+    p2 = np.stack([t2 * dx[m2], t2 * dy[m2], sensor_height + t2 * dz[m2]], axis=-1)
+    pts = np.concatenate([pts, p2], axis=0)
+
+    feats = rng.uniform(0.0, 1.0, size=(pts.shape[0], 2))
+    out = np.concatenate([pts, feats], axis=1).astype(np.float32)
+    if shuffle:
+        rng.shuffle(out, axis=0)
+    return np.ascontiguousarray(out)
+
+
+def lidar_batch(cfg, batch, **kw):
+    """Scenes ``seed = 1000*cfg + scene_idx``."""
+    return [lidar_scene(1000 * cfg + i, **kw) for i in range(batch)]
+
+
+def small_scene(seed, n_beams=16, n_azimuth=1250):
+    """cfg-1 sized cloud (20 k rays)."""
+    return lidar_scene(seed, n_beams=n_beams, n_azimuth=n_azimuth, n_cylinders=30, second_return=0.0)
+
+
+def in_range_mask(points, pc_range=WAYMO_RANGE):
+    lo = np.asarray(pc_range[:3], np.float32)
+    hi = np.asarray(pc_range[3:], np.float32)
+    return np.all((points[:, :3] >= lo) & (points[:, :3] < hi), axis=1)
