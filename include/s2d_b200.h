@@ -1,0 +1,155 @@
+/*
+ * s2d_b200.h -- C ABI of libs2d_b200.so, the B200 (sm_100a) implementation of the
+ * Sparse2Dense / CenterPoint hot path:  voxelize -> sparse 3-D conv backbone -> BEV.
+ *
+ * The reference has no C/FFI boundary of its own on this path: the
+ * arithmetic sits behind three Python operator APIs.  Each entry point below names the
+ * reference interface it replaces (paths relative to the reference checkout).
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer unless the name ends in _host; the caller (PyTorch in
+ *     this repo) owns every allocation, including workspaces sized by the *_workspace_bytes
+ *     queries;
+ *   - every call is asynchronous on the cudaStream_t passed as `stream` (void* here so the
+ *     header needs no CUDA include) and never synchronises the device;
+ *   - return value: 0 on success, negative on error (never exit()/abort(), unlike
+ *     det3d/ops/iou3d_nms/src/iou3d_nms.cpp:14-25); s2d_last_error() gives the text of the
+ *     last failure on the calling thread;
+ *   - sparse tensors are (features f32 [N,C] row-major, coors i32 [N,4] = (batch,z,y,x));
+ *   - rulebook tables are "k-major": tbl[k * tbl_stride + out_row] = in_row or -1, with k the
+ *     row-major kernel offset (kz,ky,kx), exactly the offset order of spconv's
+ *     weight[kD,kH,kW,Cin,Cout].
+ */
+#ifndef S2D_B200_H_
+#define S2D_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define S2D_OK 0
+#define S2D_ERR_INVALID (-1)   /* bad argument                    */
+#define S2D_ERR_CUDA (-2)      /* a CUDA runtime call failed      */
+#define S2D_ERR_WORKSPACE (-3) /* workspace or capacity too small */
+#define S2D_ERR_UNSUPPORTED (-4)
+
+#define S2D_MAX_BATCH 64
+
+int s2d_version(void);
+const char* s2d_last_error(void);
+/* kernels launched by this library in this process so far (bench.py reports the per-run delta) */
+unsigned long long s2d_kernel_launches(void);
+
+/* ---------------------------------------------------------------------------------------
+ * Voxelizer.  Replaces points_to_voxel(points, voxel_size, coors_range, max_points,
+ * reverse_index=True, max_voxels) -- det3d/ops/point_cloud/point_cloud_ops.py:112-184
+ * (kernel :7-55), as called by VoxelGenerator.generate (det3d/core/input/voxel_generator.py:
+ * 19-30) -- for a whole batch at once, plus the batch-index column that collate_kitti
+ * prepends (det3d/torchie/parallel/collate.py:137-144) and, optionally, the reader
+ * VoxelFeatureExtractorV3.forward (det3d/models/readers/voxel_encoder.py:17-24).
+ *
+ * Semantics are bit-exact with the reference's serial loop: per scene, voxel ids follow the
+ * order of first appearance of a voxel in the point list; a voxel keeps its first
+ * max_points points in point order; once max_voxels voxels exist, points that would open a
+ * new voxel are dropped while existing voxels keep filling.
+ *
+ *   points               f32 [n_points, F], scenes concatenated
+ *   scene_offsets_host   HOST i32 [batch+1], scene b owns points [off[b], off[b+1])
+ *   range_host, vsize_host   HOST f32 [6] (xmin,ymin,zmin,xmax,ymax,zmax), [3] (x,y,z)
+ *   voxels      (nullable) f32 [batch*max_voxels, max_points, F], rows past the total untouched
+ *   coors                i32 [batch*max_voxels, 4] (b,z,y,x)
+ *   num_points           i32 [batch*max_voxels]
+ *   mean        (nullable) f32 [batch*max_voxels, mean_channels]: sum of the kept points /
+ *                        num_points over the first mean_channels features
+ *   voxel_offsets        i32 [batch+1]: exclusive prefix of the per-scene voxel counts;
+ *                        voxel_offsets[batch] is the total number of rows written
+ * ------------------------------------------------------------------------------------- */
+size_t s2d_voxelize_workspace_bytes(int n_points, int batch, int max_points, int max_voxels);
+int s2d_voxelize(const float* points, const int* scene_offsets_host, int n_points, int batch, int F,
+                 const float* range_host, const float* vsize_host, int max_points, int max_voxels,
+                 float* voxels, int* coors, int* num_points, float* mean, int mean_channels,
+                 int* voxel_offsets, void* workspace, size_t workspace_bytes, void* stream);
+
+/* VoxelFeatureExtractorV3.forward alone (voxel_encoder.py:17-24) for voxels produced elsewhere. */
+int s2d_voxel_mean(const float* voxels, const int* num_points, int n_voxels, int max_points, int F,
+                   int channels, float* out, void* stream);
+
+/* ---------------------------------------------------------------------------------------
+ * Coordinate index of one sparse tensor: an occupancy bitmap over batch*D*H*W with a
+ * per-word popcount prefix (and, when the rows are not in ascending flattened order, a
+ * rank -> row permutation).  It is what spconv keeps as its grid/hash inside
+ * indice_dict (spconv.SparseConvTensor.indice_dict, used at scn.py:105-152).
+ *
+ *   index memory = s2d_grid_index_bytes(batch, shape, n_rows_capacity), owned by the caller.
+ *   s2d_grid_index_build: rows may be in any order and must be unique.
+ * ------------------------------------------------------------------------------------- */
+size_t s2d_grid_index_bytes(int batch, const int* shape_host, int n_rows_capacity);
+/* n_rows_dev (nullable): when given, the row count is read from device memory at run time and
+ * n_rows is only the launch bound / capacity -- lets the voxelizer feed the index without a
+ * host round trip. */
+int s2d_grid_index_build(const int* coors, int n_rows, const int* n_rows_dev, int batch,
+                         const int* shape_host, void* index, size_t index_bytes, void* stream);
+
+/* SubMConv3d rulebook (spconv.SubMConv3d, scn.py:16-39,105): output set == input set, same
+ * row order.  tbl i32 [K, tbl_stride], K = prod(ksize); neighbour of row i under offset k is
+ * the active voxel at x_i + (k - ksize/2)*dilation.  n_pairs (nullable): device u64, += the
+ * number of (in,out) pairs. */
+int s2d_rulebook_subm(const int* coors, int n_rows, int batch, const int* shape_host,
+                      const int* ksize_host, const int* dilation_host, const void* index, int* tbl,
+                      int tbl_stride, unsigned long long* n_pairs, void* stream);
+
+/* SparseConv3d (spconv.SparseConv3d, scn.py:116-118,126-128,136-138,147-149), in two steps so
+ * that the coordinate phase of a whole backbone can run without a host synchronisation:
+ *
+ * 1. s2d_sparse_out_coords: output site o is active iff x = o*s - p + k*d for an active input
+ *    x and some offset k.  Writes out_coors i32 [out_capacity,4] in ascending flattened
+ *    (b,z,y,x) order, the true count to *n_out (device; may exceed out_capacity, the caller
+ *    checks) and builds index_out = the coordinate index of the output tensor
+ *    (s2d_grid_index_bytes(batch, shape_out, out_capacity)), which serves the next layers.
+ *    n_in_dev: as n_rows_dev above.
+ * 2. s2d_rulebook_sparse: tbl[k][o] = input row at o*s - p + k*d or -1, looked up in index_in
+ *    (the index of the INPUT tensor). */
+int s2d_conv_out_shape(const int* shape_in_host, const int* ksize_host, const int* stride_host,
+                       const int* pad_host, const int* dilation_host, int* shape_out_host);
+int s2d_sparse_out_coords(const int* coors_in, int n_in, const int* n_in_dev, int batch,
+                          const int* shape_in_host, const int* ksize_host, const int* stride_host,
+                          const int* pad_host, const int* dilation_host, void* index_out,
+                          size_t index_out_bytes, int* out_coors, int out_capacity, int* n_out,
+                          void* stream);
+int s2d_rulebook_sparse(const int* out_coors, int n_out, int batch, const int* shape_in_host,
+                        const int* ksize_host, const int* stride_host, const int* pad_host,
+                        const int* dilation_host, const void* index_in, int* tbl, int tbl_stride,
+                        unsigned long long* n_pairs, void* stream);
+
+/* ---------------------------------------------------------------------------------------
+ * Sparse convolution forward, output-stationary gather-GEMM with fused epilogue.  Replaces
+ * spconv's per-offset gather -> mm -> scatter-add and the BatchNorm1d / ReLU / residual
+ * modules applied to .features (scn.py:69-85,104-152):
+ *
+ *   out[o,:] = act( (sum_k in[tbl[k][o],:] @ W[k]) * scale + shift (+ residual[o,:]) )
+ *
+ *   W f32 [K, Cin, Cout] (spconv layout [kD,kH,kW,Cin,Cout] flattened)
+ *   scale, shift (nullable, both or neither) f32 [Cout] -- eval-mode BN folded by the host,
+ *   or bias via shift with scale == NULL meaning 1
+ *   residual (nullable) f32 [n_out, Cout]; relu != 0 applies max(0, .)
+ *   precision: S2D_PRECISION_FP32 (SIMT FFMA) or S2D_PRECISION_TF32 (tcgen05, fp32 accumulate)
+ * ------------------------------------------------------------------------------------- */
+#define S2D_PRECISION_FP32 0
+#define S2D_PRECISION_TF32 1
+#define S2D_PRECISION_TF32X3 2
+int s2d_spconv_fwd(const float* in, int n_in, const float* W, const int* tbl, int tbl_stride,
+                   int n_out, int Cin, int Cout, int K, const float* scale, const float* shift,
+                   const float* residual, int relu, float* out, int precision, void* stream);
+
+/* SparseConvTensor.dense() + view(N, C*D, H, W) (scn.py:173-176): bev f32 [batch, C*D, H, W],
+ * bev[b, c*D + z, y, x] = feat[row, c].  The kernel zero-fills bev itself. */
+int s2d_dense_bev(const float* feat, const int* coors, int n_rows, int C, int batch, int D, int H, int W,
+                  float* bev, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* S2D_B200_H_ */

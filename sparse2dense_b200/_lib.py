@@ -1,0 +1,77 @@
+"""ctypes binding of ``libs2d_b200.so`` (the C ABI in ``include/s2d_b200.h``).
+
+The library is the product: there is no CPU or PyTorch fallback.  A missing or unloadable
+library raises at first use, and every non-zero status becomes a ``RuntimeError`` carrying
+``s2d_last_error()``.
+"""
+import ctypes
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libs2d_b200.so")
+
+_c_int_p = ctypes.POINTER(ctypes.c_int)
+_c_float_p = ctypes.POINTER(ctypes.c_float)
+_vp = ctypes.c_void_p
+_i = ctypes.c_int
+_sz = ctypes.c_size_t
+
+# name -> (restype, argtypes); must list every symbol include/s2d_b200.h declares
+SIGNATURES = {
+    "s2d_version": (_i, []),
+    "s2d_last_error": (ctypes.c_char_p, []),
+    "s2d_kernel_launches": (ctypes.c_ulonglong, []),
+    "s2d_voxelize_workspace_bytes": (_sz, [_i, _i, _i, _i]),
+    "s2d_voxelize": (_i, [_vp, _c_int_p, _i, _i, _i, _c_float_p, _c_float_p, _i, _i, _vp, _vp, _vp, _vp, _i, _vp,
+                          _vp, _sz, _vp]),
+    "s2d_voxel_mean": (_i, [_vp, _vp, _i, _i, _i, _i, _vp, _vp]),
+    "s2d_grid_index_bytes": (_sz, [_i, _c_int_p, _i]),
+    "s2d_grid_index_build": (_i, [_vp, _i, _vp, _i, _c_int_p, _vp, _sz, _vp]),
+    "s2d_rulebook_subm": (_i, [_vp, _i, _i, _c_int_p, _c_int_p, _c_int_p, _vp, _vp, _i, _vp, _vp]),
+    "s2d_conv_out_shape": (_i, [_c_int_p, _c_int_p, _c_int_p, _c_int_p, _c_int_p, _c_int_p]),
+    "s2d_sparse_out_coords": (_i, [_vp, _i, _vp, _i, _c_int_p, _c_int_p, _c_int_p, _c_int_p, _c_int_p, _vp, _sz,
+                                   _vp, _i, _vp, _vp]),
+    "s2d_rulebook_sparse": (_i, [_vp, _i, _i, _c_int_p, _c_int_p, _c_int_p, _c_int_p, _c_int_p, _vp, _vp, _i, _vp,
+                                 _vp]),
+    "s2d_spconv_fwd": (_i, [_vp, _i, _vp, _vp, _i, _i, _i, _i, _i, _vp, _vp, _vp, _i, _vp, _i, _vp]),
+    "s2d_dense_bev": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _i, _vp, _vp]),
+}
+
+_lib = None
+
+
+class S2DError(RuntimeError):
+    pass
+
+
+def load():
+    """Load (once) and return the ctypes handle; raises if the CUDA library was not built."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise S2DError(
+                f"{LIB_PATH} not found: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+                "(or `make -C sparse2dense_b200/csrc`).  There is no CPU fallback.")
+        lib = ctypes.CDLL(LIB_PATH)
+        for name, (res, args) in SIGNATURES.items():
+            fn = getattr(lib, name)          # AttributeError if the .so lacks a declared symbol
+            fn.restype = res
+            fn.argtypes = args
+        _lib = lib
+    return _lib
+
+
+def check(status, what=""):
+    if status != 0:
+        msg = load().s2d_last_error().decode("utf-8", "replace")
+        raise S2DError(f"{what or 's2d call'} failed with status {status}: {msg}")
+
+
+def ints(values):
+    values = [int(v) for v in values]
+    return (ctypes.c_int * len(values))(*values)
+
+
+def floats(values):
+    values = [float(v) for v in values]
+    return (ctypes.c_float * len(values))(*values)

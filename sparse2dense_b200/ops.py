@@ -1,0 +1,291 @@
+"""Tensor-level wrappers over the C ABI (``include/s2d_b200.h``).
+
+PyTorch is plumbing here: it owns device memory and the CUDA stream; every arithmetic step is
+one call into ``libs2d_b200.so``.  All functions require CUDA tensors and raise otherwise --
+there is no CPU path.
+"""
+import numpy as np
+import torch
+
+from . import _lib
+
+PRECISION_FP32 = 0
+PRECISION_TF32 = 1
+PRECISION_TF32X3 = 2
+
+
+# When set to a list, spconv_fwd appends (key, start_event, end_event) per launch so that bench.py can
+# time the dominant kernel live on its own stream (profiling aid; off by default).
+KERNEL_EVENTS = None
+
+
+def _stream():
+    return torch.cuda.current_stream().cuda_stream
+
+
+def kernel_launches():
+    """Kernels launched by libs2d_b200.so in this process so far."""
+    return int(_lib.load().s2d_kernel_launches())
+
+
+def _ptr(t):
+    return None if t is None else t.data_ptr()
+
+
+def _need_cuda(*tensors):
+    for t in tensors:
+        if t is not None and not t.is_cuda:
+            raise _lib.S2DError("sparse2dense_b200 ops need CUDA tensors (no CPU fallback)")
+
+
+def _triple(v):
+    if isinstance(v, (int, np.integer)):
+        return (int(v),) * 3
+    v = tuple(int(a) for a in v)
+    assert len(v) == 3, v
+    return v
+
+
+# ------------------------------------------------------------------------------------------
+# voxelizer
+# ------------------------------------------------------------------------------------------
+class VoxelBatch:
+    """Device-side result of :func:`voxelize` with capacity-sized buffers and a lazy host count."""
+
+    def __init__(self, voxels, coors, num_points, mean, voxel_offsets, batch):
+        self._voxels, self._coors, self._num_points, self._mean = voxels, coors, num_points, mean
+        self.voxel_offsets = voxel_offsets          # device i32 [batch+1]
+        self.batch = batch
+        self._offsets_host = None
+
+    @property
+    def n_dev(self):
+        return self.voxel_offsets[self.batch:]
+
+    def offsets_host(self):
+        if self._offsets_host is None:
+            self._offsets_host = self.voxel_offsets.cpu().tolist()   # the one host sync
+        return self._offsets_host
+
+    @property
+    def n(self):
+        return self.offsets_host()[-1]
+
+    @property
+    def capacity(self):
+        return self._coors.shape[0]
+
+    @property
+    def coors_buffer(self):
+        return self._coors
+
+    @property
+    def mean_buffer(self):
+        return self._mean
+
+    @property
+    def voxels(self):
+        return None if self._voxels is None else self._voxels[: self.n]
+
+    @property
+    def coors(self):
+        return self._coors[: self.n]
+
+    @property
+    def num_points(self):
+        return self._num_points[: self.n]
+
+    @property
+    def mean(self):
+        return None if self._mean is None else self._mean[: self.n]
+
+
+def voxelize(points, scene_offsets, voxel_size, coors_range, max_points, max_voxels, want_voxels=True,
+             mean_channels=None):
+    """Batched GPU voxelizer (C ABI ``s2d_voxelize``; reference point_cloud_ops.py:112-184).
+
+    points: cuda f32 [N,F] (scenes concatenated); scene_offsets: host ints [B+1].
+    """
+    _need_cuda(points)
+    lib = _lib.load()
+    assert points.dtype == torch.float32 and points.dim() == 2
+    points = points.contiguous()
+    n, f = points.shape
+    batch = len(scene_offsets) - 1
+    dev = points.device
+    cap = min(batch * max_voxels, max(n, 1))
+    voxels = torch.empty((cap, max_points, f), dtype=torch.float32, device=dev) if want_voxels else None
+    coors = torch.empty((cap, 4), dtype=torch.int32, device=dev)
+    num = torch.empty((cap,), dtype=torch.int32, device=dev)
+    mean = torch.empty((cap, mean_channels), dtype=torch.float32, device=dev) if mean_channels else None
+    offs = torch.empty((batch + 1,), dtype=torch.int32, device=dev)
+    ws_bytes = lib.s2d_voxelize_workspace_bytes(n, batch, max_points, max_voxels)
+    ws = torch.empty((ws_bytes,), dtype=torch.uint8, device=dev)
+    _lib.check(lib.s2d_voxelize(_ptr(points), _lib.ints(scene_offsets), n, batch, f, _lib.floats(coors_range),
+                                _lib.floats(voxel_size), max_points, max_voxels, _ptr(voxels), _ptr(coors),
+                                _ptr(num), _ptr(mean), mean_channels or 0, _ptr(offs), _ptr(ws), ws_bytes,
+                                _stream()), "s2d_voxelize")
+    return VoxelBatch(voxels, coors, num, mean, offs, batch)
+
+
+def voxel_mean(voxels, num_points, channels=None):
+    """VoxelFeatureExtractorV3.forward (voxel_encoder.py:17-24)."""
+    _need_cuda(voxels, num_points)
+    m, p, f = voxels.shape
+    c = f if channels is None else channels
+    out = torch.empty((m, c), dtype=torch.float32, device=voxels.device)
+    _lib.check(_lib.load().s2d_voxel_mean(_ptr(voxels.contiguous()), _ptr(num_points.int().contiguous()), m, p, f, c,
+                                          _ptr(out), _stream()), "s2d_voxel_mean")
+    return out
+
+
+# ------------------------------------------------------------------------------------------
+# coordinate index + rulebooks
+# ------------------------------------------------------------------------------------------
+class GridIndex:
+    """Occupancy bitmap + popcount prefix (+ rank->row permutation) of one sparse tensor."""
+
+    def __init__(self, batch, shape, capacity, device):
+        self.batch, self.shape, self.capacity = int(batch), _triple(shape), int(capacity)
+        self.nbytes = _lib.load().s2d_grid_index_bytes(self.batch, _lib.ints(self.shape), self.capacity)
+        self.buf = torch.empty((self.nbytes,), dtype=torch.uint8, device=device)
+
+
+def build_grid_index(coors, batch, shape, n=None, n_dev=None):
+    _need_cuda(coors)
+    assert coors.dtype == torch.int32 and coors.is_contiguous() and coors.shape[1] == 4
+    n = coors.shape[0] if n is None else n
+    idx = GridIndex(batch, shape, n, coors.device)
+    _lib.check(_lib.load().s2d_grid_index_build(_ptr(coors), n, _ptr(n_dev), idx.batch, _lib.ints(idx.shape),
+                                                _ptr(idx.buf), idx.nbytes, _stream()), "s2d_grid_index_build")
+    return idx
+
+
+def rulebook_subm(coors, index, ksize=3, dilation=1, count_pairs=False):
+    """-> tbl i32 [K, n] (k-major), and the pair count tensor (device u64 as int64) if requested."""
+    _need_cuda(coors)
+    n = coors.shape[0]
+    ks, dl = _triple(ksize), _triple(dilation)
+    k = ks[0] * ks[1] * ks[2]
+    tbl = torch.empty((k, max(n, 1)), dtype=torch.int32, device=coors.device)
+    pairs = torch.zeros((1,), dtype=torch.int64, device=coors.device) if count_pairs else None
+    _lib.check(_lib.load().s2d_rulebook_subm(_ptr(coors), n, index.batch, _lib.ints(index.shape), _lib.ints(ks),
+                                             _lib.ints(dl), _ptr(index.buf), _ptr(tbl), tbl.shape[1], _ptr(pairs),
+                                             _stream()), "s2d_rulebook_subm")
+    return (tbl, pairs) if count_pairs else tbl
+
+
+def conv_out_shape(shape, ksize, stride, pad, dilation=1):
+    out = (_lib.ctypes.c_int * 3)()
+    _lib.check(_lib.load().s2d_conv_out_shape(_lib.ints(_triple(shape)), _lib.ints(_triple(ksize)),
+                                              _lib.ints(_triple(stride)), _lib.ints(_triple(pad)),
+                                              _lib.ints(_triple(dilation)), out), "s2d_conv_out_shape")
+    return tuple(out)
+
+
+def out_capacity_bound(n_in, batch, shape_out, ksize, stride):
+    """Upper bound of the number of output sites of a strided conv over n_in active inputs."""
+    per_input = 1
+    for k, s in zip(_triple(ksize), _triple(stride)):
+        per_input *= -(-k // s)
+    return int(min(n_in * per_input, batch * shape_out[0] * shape_out[1] * shape_out[2]))
+
+
+class SparseCoords:
+    """Output coordinate set of a strided conv: capacity buffers, device count, lazy host count."""
+
+    def __init__(self, coors_buf, n_dev, index, shape):
+        self.coors_buffer, self.n_dev, self.index, self.shape = coors_buf, n_dev, index, shape
+        self._n = None
+
+    @property
+    def n(self):
+        if self._n is None:
+            self._n = int(self.n_dev.item())
+            if self._n > self.coors_buffer.shape[0]:
+                raise _lib.S2DError(f"sparse conv produced {self._n} outputs > capacity {self.coors_buffer.shape[0]}")
+        return self._n
+
+    def set_n(self, n):
+        self._n = int(n)
+        if self._n > self.coors_buffer.shape[0]:
+            raise _lib.S2DError(f"sparse conv produced {self._n} outputs > capacity {self.coors_buffer.shape[0]}")
+
+    @property
+    def coors(self):
+        return self.coors_buffer[: self.n]
+
+
+def sparse_out_coords(coors_in, n_in, batch, shape_in, ksize, stride, pad, dilation=1, n_in_dev=None):
+    """Phase 1 of SparseConv3d: output coordinates (ascending) + their index; no host sync."""
+    _need_cuda(coors_in)
+    ks, st, pd, dl = _triple(ksize), _triple(stride), _triple(pad), _triple(dilation)
+    shape_out = conv_out_shape(shape_in, ks, st, pd, dl)
+    cap = max(out_capacity_bound(n_in, batch, shape_out, ks, st), 1)
+    dev = coors_in.device
+    index = GridIndex(batch, shape_out, cap, dev)
+    out_coors = torch.empty((cap, 4), dtype=torch.int32, device=dev)
+    n_out = torch.zeros((1,), dtype=torch.int32, device=dev)
+    _lib.check(_lib.load().s2d_sparse_out_coords(_ptr(coors_in), n_in, _ptr(n_in_dev), batch,
+                                                 _lib.ints(_triple(shape_in)), _lib.ints(ks), _lib.ints(st),
+                                                 _lib.ints(pd), _lib.ints(dl), _ptr(index.buf), index.nbytes,
+                                                 _ptr(out_coors), cap, _ptr(n_out), _stream()),
+               "s2d_sparse_out_coords")
+    return SparseCoords(out_coors, n_out, index, shape_out)
+
+
+def rulebook_sparse(out_coors, index_in, ksize, stride, pad, dilation=1, count_pairs=False):
+    """Phase 2 of SparseConv3d: gather table i32 [K, n_out]."""
+    _need_cuda(out_coors)
+    n_out = out_coors.shape[0]
+    ks, st, pd, dl = _triple(ksize), _triple(stride), _triple(pad), _triple(dilation)
+    k = ks[0] * ks[1] * ks[2]
+    tbl = torch.empty((k, max(n_out, 1)), dtype=torch.int32, device=out_coors.device)
+    pairs = torch.zeros((1,), dtype=torch.int64, device=out_coors.device) if count_pairs else None
+    _lib.check(_lib.load().s2d_rulebook_sparse(_ptr(out_coors), n_out, index_in.batch, _lib.ints(index_in.shape),
+                                               _lib.ints(ks), _lib.ints(st), _lib.ints(pd), _lib.ints(dl),
+                                               _ptr(index_in.buf), _ptr(tbl), tbl.shape[1], _ptr(pairs), _stream()),
+               "s2d_rulebook_sparse")
+    return (tbl, pairs) if count_pairs else tbl
+
+
+# ------------------------------------------------------------------------------------------
+# convolution + densify
+# ------------------------------------------------------------------------------------------
+def spconv_fwd(feats, weight, tbl, n_out, scale=None, shift=None, residual=None, relu=False,
+               precision=PRECISION_FP32, out=None):
+    """out[o] = act((sum_k feats[tbl[k][o]] @ W[k]) * scale + shift (+ residual[o])).
+
+    weight: [kD,kH,kW,Cin,Cout] (spconv layout) or [K,Cin,Cout], fp32 contiguous.
+    """
+    _need_cuda(feats, weight, tbl)
+    assert feats.dtype == torch.float32 and feats.is_contiguous() and weight.is_contiguous()
+    cin, cout = weight.shape[-2], weight.shape[-1]
+    k = weight.numel() // (cin * cout)
+    assert feats.shape[1] == cin and tbl.shape[0] == k and tbl.dtype == torch.int32
+    if out is None:
+        out = torch.empty((n_out, cout), dtype=torch.float32, device=feats.device)
+    for t in (scale, shift, residual):
+        assert t is None or (t.dtype == torch.float32 and t.is_contiguous())
+    ev = None
+    if KERNEL_EVENTS is not None:
+        ev = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
+        ev[0].record()
+    _lib.check(_lib.load().s2d_spconv_fwd(_ptr(feats), feats.shape[0], _ptr(weight), _ptr(tbl), tbl.stride(0), n_out,
+                                          cin, cout, k, _ptr(scale), _ptr(shift), _ptr(residual), int(bool(relu)),
+                                          _ptr(out), int(precision), _stream()), "s2d_spconv_fwd")
+    if ev is not None:
+        ev[1].record()
+        KERNEL_EVENTS.append(((cin, cout, k, residual is not None, feats.shape[0], n_out, int(precision)), ev[0], ev[1]))
+    return out
+
+
+def dense_bev(feats, coors, batch, spatial_shape):
+    """SparseConvTensor.dense() + view(N, C*D, H, W) (scn.py:173-176) -> [B, C*D, H, W]."""
+    _need_cuda(feats, coors)
+    d, h, w = _triple(spatial_shape)
+    n, c = feats.shape
+    bev = torch.empty((batch, c * d, h, w), dtype=torch.float32, device=feats.device)
+    _lib.check(_lib.load().s2d_dense_bev(_ptr(feats.contiguous()), _ptr(coors.contiguous()), n, c, batch, d, h, w,
+                                         _ptr(bev), _stream()), "s2d_dense_bev")
+    return bev

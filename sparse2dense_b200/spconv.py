@@ -1,0 +1,270 @@
+"""Host-side mirror of the spconv v1.x Python API that the reference backbone is written against.
+
+Names, constructor arguments, attributes and state-dict layout follow spconv @ 7342772 as the
+reference uses it (det3d/models/backbones/scn.py:2,8,16-39,42-85,104-152,159-176;
+det3d/models/detectors/voxelnet.py:203-215), so reference-style model code keeps working:
+
+    SparseConvTensor(features, indices, spatial_shape, batch_size)  .features .indices
+        .spatial_shape .batch_size .indice_dict .dense()
+    SubMConv3d / SparseConv3d(in, out, kernel_size, stride=1, padding=0, dilation=1, groups=1,
+        bias=True, indice_key=None)      weight: Parameter[kD,kH,kW,Cin,Cout]
+    SparseSequential(*modules), SparseModule
+
+Underneath, every step is one call into libs2d_b200.so (output-stationary gather-GEMM with a
+fused BatchNorm/ReLU/residual epilogue) -- see include/s2d_b200.h.  Forward only in this
+version; there is no CPU implementation.
+"""
+import math
+from collections import OrderedDict
+
+import numpy as np
+import torch
+from torch import nn
+
+from . import ops
+
+
+class SparseModule(nn.Module):
+    """Marker base class: modules that consume / produce SparseConvTensor (scn.py:42)."""
+
+
+class _Indice:
+    """What spconv keeps per ``indice_key``: the rulebook and the output coordinate set."""
+
+    def __init__(self, tbl, out_indices, out_index, out_shape, n_pairs=None):
+        self.tbl, self.out_indices, self.out_index, self.out_shape, self.n_pairs = (
+            tbl, out_indices, out_index, out_shape, n_pairs)
+
+
+class SparseConvTensor:
+    def __init__(self, features, indices, spatial_shape, batch_size, grid=None):
+        self.features = features
+        self.indices = indices
+        self.spatial_shape = tuple(int(v) for v in np.asarray(spatial_shape).tolist())
+        self.batch_size = int(batch_size)
+        self.indice_dict = {}
+        self.grid = grid
+        self._index = None            # ops.GridIndex of this tensor's coordinate set
+        self._planned = {}            # id(module) -> ops.SparseCoords precomputed by plan_coords()
+
+    @property
+    def spatial_size(self):
+        return int(np.prod(self.spatial_shape))
+
+    def find_indice_pair(self, key):
+        if key is None:
+            return None
+        return self.indice_dict.get(key)
+
+    def index(self):
+        if self._index is None:
+            self._index = ops.build_grid_index(self.indices, self.batch_size, self.spatial_shape)
+        return self._index
+
+    def _like(self, features, indices=None, spatial_shape=None, index=None):
+        out = SparseConvTensor(features, self.indices if indices is None else indices,
+                               self.spatial_shape if spatial_shape is None else spatial_shape, self.batch_size)
+        out.indice_dict = self.indice_dict
+        out._planned = self._planned
+        out._index = index if indices is not None else self._index
+        return out
+
+    def dense(self, channels_first=True):
+        """[B, C, D, H, W] like spconv (zeros scattered with the active rows, then permuted)."""
+        d, h, w = self.spatial_shape
+        bev = ops.dense_bev(self.features, self.indices, self.batch_size, self.spatial_shape)
+        out = bev.view(self.batch_size, self.features.shape[1], d, h, w)
+        return out if channels_first else out.permute(0, 2, 3, 4, 1).contiguous()
+
+
+def _fold_bn(bn, bias, cout, device):
+    """eval-mode BatchNorm1d (+ conv bias) -> per-channel (scale, shift)."""
+    if bn is None:
+        if bias is None:
+            return None, None
+        return None, bias.detach().float().contiguous()
+    inv = torch.rsqrt(bn.running_var.float() + bn.eps)
+    gamma = bn.weight.float() if bn.weight is not None else torch.ones(cout, device=device)
+    beta = bn.bias.float() if bn.bias is not None else torch.zeros(cout, device=device)
+    scale = gamma * inv
+    shift = beta - bn.running_mean.float() * scale
+    if bias is not None:
+        shift = shift + bias.float() * scale
+    return scale.detach().contiguous(), shift.detach().contiguous()
+
+
+class SparseConvolution(SparseModule):
+    def __init__(self, ndim, in_channels, out_channels, kernel_size=3, stride=1, padding=0, dilation=1, groups=1,
+                 bias=True, subm=False, indice_key=None):
+        super().__init__()
+        assert ndim == 3 and groups == 1
+        self.ndim = ndim
+        self.in_channels, self.out_channels = in_channels, out_channels
+        self.kernel_size = ops._triple(kernel_size)
+        self.stride = ops._triple(stride)
+        self.padding = ops._triple(padding)
+        self.dilation = ops._triple(dilation)
+        self.groups = groups
+        self.subm = subm
+        self.indice_key = indice_key
+        self.precision = ops.PRECISION_FP32
+        self.weight = nn.Parameter(torch.empty(*self.kernel_size, in_channels, out_channels))
+        if bias:
+            self.bias = nn.Parameter(torch.empty(out_channels))
+        else:
+            self.register_parameter("bias", None)
+        self.reset_parameters()
+
+    def reset_parameters(self):
+        nn.init.kaiming_uniform_(self.weight, a=math.sqrt(5))
+        if self.bias is not None:
+            fan_in, _ = nn.init._calculate_fan_in_and_fan_out(self.weight)
+            bound = 1 / math.sqrt(fan_in)
+            nn.init.uniform_(self.bias, -bound, bound)
+
+    def extra_repr(self):
+        return (f"{self.in_channels}, {self.out_channels}, kernel_size={self.kernel_size}, stride={self.stride}, "
+                f"padding={self.padding}, subm={self.subm}, indice_key={self.indice_key}")
+
+    # -- rulebook ---------------------------------------------------------------------------
+    def _indice(self, x):
+        cached = x.find_indice_pair(self.indice_key)
+        if cached is not None:
+            return cached
+        if self.subm:
+            index = x.index()
+            tbl = ops.rulebook_subm(x.indices, index, self.kernel_size, self.dilation)
+            ind = _Indice(tbl, x.indices, index, x.spatial_shape)
+        else:
+            coords = x._planned.get(id(self))
+            if coords is None:
+                coords = ops.sparse_out_coords(x.indices, x.indices.shape[0], x.batch_size, x.spatial_shape,
+                                               self.kernel_size, self.stride, self.padding, self.dilation)
+            out_indices = coords.coors          # host count read here unless plan_coords() already did
+            tbl = ops.rulebook_sparse(out_indices, x.index(), self.kernel_size, self.stride, self.padding,
+                                      self.dilation)
+            ind = _Indice(tbl, out_indices, coords.index, coords.shape)
+        if self.indice_key is not None:
+            x.indice_dict[self.indice_key] = ind
+        return ind
+
+    # -- forward ----------------------------------------------------------------------------
+    def fused_forward(self, x, bn=None, relu=False, residual=None):
+        """conv (+ eval BatchNorm1d) (+ residual) (+ ReLU) in one kernel launch."""
+        assert isinstance(x, SparseConvTensor)
+        ind = self._indice(x)
+        scale, shift = _fold_bn(bn, self.bias, self.out_channels, x.features.device)
+        n_out = ind.out_indices.shape[0]
+        feats = ops.spconv_fwd(x.features.contiguous(), self.weight.detach(), ind.tbl, n_out, scale, shift,
+                               None if residual is None else residual.contiguous(), relu, self.precision)
+        if self.subm:
+            return x._like(feats)
+        return x._like(feats, ind.out_indices, ind.out_shape, ind.out_index)
+
+    def forward(self, x):
+        return self.fused_forward(x)
+
+
+class SubMConv3d(SparseConvolution):
+    """Submanifold conv: output set == input set; `padding`/`stride` are ignored as in spconv
+    (scn.py:16-26 passes padding=1, scn.py:105 passes nothing; both mean a centred kernel)."""
+
+    def __init__(self, in_channels, out_channels, kernel_size, stride=1, padding=0, dilation=1, groups=1, bias=True,
+                 indice_key=None):
+        super().__init__(3, in_channels, out_channels, kernel_size, stride, padding, dilation, groups, bias, True,
+                         indice_key)
+
+
+class SparseConv3d(SparseConvolution):
+    def __init__(self, in_channels, out_channels, kernel_size, stride=1, padding=0, dilation=1, groups=1, bias=True,
+                 indice_key=None):
+        super().__init__(3, in_channels, out_channels, kernel_size, stride, padding, dilation, groups, bias, False,
+                         indice_key)
+
+
+def _is_eval_bn(m):
+    return isinstance(m, nn.BatchNorm1d) and not m.training and m.track_running_stats
+
+
+class SparseSequential(SparseModule):
+    """spconv.SparseSequential: sparse modules get the tensor, others are applied to ``.features``.
+
+    In eval mode a ``conv -> BatchNorm1d -> ReLU`` run is executed as ONE fused kernel; the
+    result is identical up to fp32 rounding of the folded affine.
+    """
+
+    def __init__(self, *args, **kwargs):
+        super().__init__()
+        if len(args) == 1 and isinstance(args[0], OrderedDict):
+            for key, module in args[0].items():
+                self.add_module(key, module)
+        else:
+            for idx, module in enumerate(args):
+                self.add_module(str(idx), module)
+        for name, module in kwargs.items():
+            if name in self._modules:
+                raise ValueError("name exists.")
+            self.add_module(name, module)
+
+    def __getitem__(self, idx):
+        if not (-len(self) <= idx < len(self)):
+            raise IndexError("index {} is out of range".format(idx))
+        if idx < 0:
+            idx += len(self)
+        return list(self._modules.values())[idx]
+
+    def __len__(self):
+        return len(self._modules)
+
+    def add(self, module, name=None):
+        if name is None:
+            name = str(len(self._modules))
+            if name in self._modules:
+                raise KeyError("name exists")
+        self.add_module(name, module)
+
+    def forward(self, input):
+        mods = list(self._modules.values())
+        i = 0
+        while i < len(mods):
+            m = mods[i]
+            if isinstance(m, SparseConvolution) and isinstance(input, SparseConvTensor):
+                bn = mods[i + 1] if i + 1 < len(mods) and _is_eval_bn(mods[i + 1]) else None
+                relu = bn is not None and i + 2 < len(mods) and isinstance(mods[i + 2], nn.ReLU)
+                input = m.fused_forward(input, bn=bn, relu=relu)
+                i += 1 + (bn is not None) + int(relu)
+            elif isinstance(m, SparseModule):
+                input = m(input)
+                i += 1
+            else:
+                if isinstance(input, SparseConvTensor):
+                    if input.indices.shape[0] != 0:
+                        input.features = m(input.features)
+                else:
+                    input = m(input)
+                i += 1
+        return input
+
+
+def plan_coords(x, modules):
+    """Run the coordinate phase of every strided conv in ``modules`` (in forward order) without a
+    host round trip, then read all output counts in ONE device->host copy.
+
+    Coordinates do not depend on features, so the whole chain voxels -> conv2.0 -> conv3.0 -> ...
+    can be resolved before the first feature kernel runs.  Results are parked on the tensor and
+    picked up by ``SparseConv3d`` when it executes.
+    """
+    convs = [m for m in modules if isinstance(m, SparseConvolution) and not m.subm]
+    coors, n, n_dev, shape = x.indices, x.indices.shape[0], None, x.spatial_shape
+    planned = []
+    for m in convs:
+        sc = ops.sparse_out_coords(coors, n, x.batch_size, shape, m.kernel_size, m.stride, m.padding, m.dilation,
+                                   n_in_dev=n_dev)
+        planned.append(sc)
+        coors, n, n_dev, shape = sc.coors_buffer, sc.coors_buffer.shape[0], sc.n_dev, sc.shape
+    if planned:
+        counts = torch.cat([sc.n_dev for sc in planned]).cpu().tolist()       # the one sync
+        for m, sc, c in zip(convs, planned, counts):
+            sc.set_n(c)
+            x._planned[id(m)] = sc
+    return planned

@@ -85,3 +85,36 @@ def in_range_mask(points, pc_range=WAYMO_RANGE):
     lo = np.asarray(pc_range[:3], np.float32)
     hi = np.asarray(pc_range[3:], np.float32)
     return np.all((points[:, :3] >= lo) & (points[:, :3] < hi), axis=1)
+
+
+def backbone_state(seed=0, num_input_features=5):
+    """Seeded random weights for SpMiddleResNetFHD in the reference's state-dict format
+    (det3d/models/backbones/scn.py:104-152; spconv weight layout [kD,kH,kW,Cin,Cout]) with
+    non-trivial BatchNorm running statistics so that BN folding is exercised.
+    There is no checkpoint on the build or GPU boxes."""
+    rng = np.random.default_rng(seed)
+    state = {}
+
+    def conv(name, ks, cin, cout, bias):
+        fan = cin * int(np.prod(ks))
+        state[name + ".weight"] = (rng.normal(size=(*ks, cin, cout)) * np.sqrt(2.0 / fan)).astype(np.float32)
+        if bias:
+            state[name + ".bias"] = rng.uniform(-0.1, 0.1, cout).astype(np.float32)
+
+    def bn(name, c):
+        state[name + ".weight"] = rng.uniform(0.5, 1.5, c).astype(np.float32)
+        state[name + ".bias"] = rng.normal(0, 0.1, c).astype(np.float32)
+        state[name + ".running_mean"] = rng.normal(0, 0.1, c).astype(np.float32)
+        state[name + ".running_var"] = rng.uniform(0.5, 1.5, c).astype(np.float32)
+
+    def block(name, c):
+        conv(name + ".conv1", (3, 3, 3), c, c, True); bn(name + ".bn1", c)
+        conv(name + ".conv2", (3, 3, 3), c, c, True); bn(name + ".bn2", c)
+
+    conv("conv_input.0", (3, 3, 3), num_input_features, 16, False); bn("conv_input.1", 16)
+    block("conv1.0", 16); block("conv1.1", 16)
+    for name, cin, cout in (("conv2", 16, 32), ("conv3", 32, 64), ("conv4", 64, 128)):
+        conv(name + ".0", (3, 3, 3), cin, cout, False); bn(name + ".1", cout)
+        block(name + ".3", cout); block(name + ".4", cout)
+    conv("extra_conv.0", (3, 1, 1), 128, 128, False); bn("extra_conv.1", 128)
+    return state
