@@ -34,6 +34,9 @@ SIGNATURES = {
     "s2d_rulebook_sparse": (_i, [_vp, _i, _i, _c_int_p, _c_int_p, _c_int_p, _c_int_p, _c_int_p, _vp, _vp, _i, _vp,
                                  _vp]),
     "s2d_spconv_fwd": (_i, [_vp, _i, _vp, _vp, _i, _i, _i, _i, _i, _vp, _vp, _vp, _i, _vp, _i, _vp]),
+    "s2d_spconv_tf32_supported": (_i, [_i, _i]),
+    "s2d_spconv_packed_bytes": (_sz, [_i, _i, _i]),
+    "s2d_spconv_pack_weights": (_i, [_vp, _i, _i, _i, _vp, _vp]),
     "s2d_dense_bev": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _i, _vp, _vp]),
 }
 

@@ -110,11 +110,14 @@ class SpMiddleResNetFHD(nn.Module):
             nn.ReLU(),
         )
 
-    def set_precision(self, precision, min_channels=32):
-        """Choose the arithmetic of the sparse convs (ops.PRECISION_*) for layers with Cin >= min_channels."""
+    def set_precision(self, precision):
+        """Choose the arithmetic of the sparse convs: ops.PRECISION_FP32 (CUDA cores), PRECISION_TF32X3
+        (tcgen05, split TF32, ~fp32 accuracy) or PRECISION_TF32 (tcgen05 single pass).  Layers whose
+        shape has no tensor-core kernel (Cin < 32) stay on the fp32 kernel."""
         for m in self.modules():
             if isinstance(m, spconv.SparseConvolution):
-                m.precision = precision if m.in_channels >= min_channels else ops.PRECISION_FP32
+                ok = precision != ops.PRECISION_FP32 and ops.tf32_supported(m.in_channels, m.out_channels)
+                m.precision = precision if ok else ops.PRECISION_FP32
 
     def forward(self, voxel_features, coors, batch_size, input_shape, index=None):
         sparse_shape = np.array(input_shape[::-1]) + [1, 0, 0]          # scn.py:159 (depth 41, not 40)

@@ -253,7 +253,7 @@ def rulebook_sparse(out_coors, index_in, ksize, stride, pad, dilation=1, count_p
 # convolution + densify
 # ------------------------------------------------------------------------------------------
 def spconv_fwd(feats, weight, tbl, n_out, scale=None, shift=None, residual=None, relu=False,
-               precision=PRECISION_FP32, out=None):
+               precision=PRECISION_FP32, out=None, packed=None):
     """out[o] = act((sum_k feats[tbl[k][o]] @ W[k]) * scale + shift (+ residual[o])).
 
     weight: [kD,kH,kW,Cin,Cout] (spconv layout) or [K,Cin,Cout], fp32 contiguous.
@@ -267,17 +267,40 @@ def spconv_fwd(feats, weight, tbl, n_out, scale=None, shift=None, residual=None,
         out = torch.empty((n_out, cout), dtype=torch.float32, device=feats.device)
     for t in (scale, shift, residual):
         assert t is None or (t.dtype == torch.float32 and t.is_contiguous())
+    w_arg = weight
+    if precision != PRECISION_FP32:
+        w_arg = packed if packed is not None else pack_weights_tf32(weight)
     ev = None
     if KERNEL_EVENTS is not None:
         ev = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
         ev[0].record()
-    _lib.check(_lib.load().s2d_spconv_fwd(_ptr(feats), feats.shape[0], _ptr(weight), _ptr(tbl), tbl.stride(0), n_out,
+    _lib.check(_lib.load().s2d_spconv_fwd(_ptr(feats), feats.shape[0], _ptr(w_arg), _ptr(tbl), tbl.stride(0), n_out,
                                           cin, cout, k, _ptr(scale), _ptr(shift), _ptr(residual), int(bool(relu)),
                                           _ptr(out), int(precision), _stream()), "s2d_spconv_fwd")
     if ev is not None:
         ev[1].record()
         KERNEL_EVENTS.append(((cin, cout, k, residual is not None, feats.shape[0], n_out, int(precision)), ev[0], ev[1]))
     return out
+
+
+def tf32_supported(cin, cout):
+    return bool(_lib.load().s2d_spconv_tf32_supported(int(cin), int(cout)))
+
+
+def pack_weights_tf32(weight):
+    """Weights [kD,kH,kW,Cin,Cout] -> the pre-split (TF32 hi/lo), pre-swizzled shared-memory image the
+    tcgen05 kernel bulk-copies per (offset, 32-channel chunk).  Done once per layer."""
+    _need_cuda(weight)
+    weight = weight.detach().contiguous().float()
+    cin, cout = weight.shape[-2], weight.shape[-1]
+    k = weight.numel() // (cin * cout)
+    nbytes = _lib.load().s2d_spconv_packed_bytes(k, cin, cout)
+    if nbytes == 0:
+        raise _lib.S2DError(f"no tcgen05 packing for Cin={cin} Cout={cout}")
+    packed = torch.empty((nbytes // 4,), dtype=torch.float32, device=weight.device)
+    _lib.check(_lib.load().s2d_spconv_pack_weights(_ptr(weight), k, cin, cout, _ptr(packed), _stream()),
+               "s2d_spconv_pack_weights")
+    return packed
 
 
 def dense_bev(feats, coors, batch, spatial_shape):

@@ -108,6 +108,7 @@ class SparseConvolution(SparseModule):
         self.subm = subm
         self.indice_key = indice_key
         self.precision = ops.PRECISION_FP32
+        self._packed = None           # (key, tensor): tcgen05 weight image, rebuilt when the weight changes
         self.weight = nn.Parameter(torch.empty(*self.kernel_size, in_channels, out_channels))
         if bias:
             self.bias = nn.Parameter(torch.empty(out_channels))
@@ -155,14 +156,22 @@ class SparseConvolution(SparseModule):
         ind = self._indice(x)
         scale, shift = _fold_bn(bn, self.bias, self.out_channels, x.features.device)
         n_out = ind.out_indices.shape[0]
+        packed = self._packed_weights() if self.precision != ops.PRECISION_FP32 else None
         feats = ops.spconv_fwd(x.features.contiguous(), self.weight.detach(), ind.tbl, n_out, scale, shift,
-                               None if residual is None else residual.contiguous(), relu, self.precision)
+                               None if residual is None else residual.contiguous(), relu, self.precision,
+                               packed=packed)
         if self.subm:
             return x._like(feats)
         return x._like(feats, ind.out_indices, ind.out_shape, ind.out_index)
 
     def forward(self, x):
         return self.fused_forward(x)
+
+    def _packed_weights(self):
+        key = (self.weight.data_ptr(), self.weight._version, str(self.weight.device))
+        if self._packed is None or self._packed[0] != key:
+            self._packed = (key, ops.pack_weights_tf32(self.weight))
+        return self._packed[1]
 
 
 class SubMConv3d(SparseConvolution):

@@ -1,0 +1,111 @@
+"""GPU parity of the tcgen05 (TF32) sparse conv kernels through the C ABI vs the fp64-accumulating oracle.
+
+Tolerances (relative to the output scale, north_star bar = 1e-3):
+  TF32X3 (split hi/lo, 3 MMAs): 2e-5  -- this is the mode the backbone uses to meet the bar
+  TF32   (single pass)        : 3e-3 per layer (documented as a fast, reduced-precision mode)
+"""
+import numpy as np
+import pytest
+import torch
+
+from oracle import backbone as OB
+from oracle import ref_ops as R
+from sparse2dense_b200 import ops, registry, synth
+
+pytestmark = pytest.mark.gpu
+SHAPES = [(32, 32), (32, 64), (64, 64), (64, 128), (128, 128)]
+
+
+def rel_err(a, b):
+    return float(np.abs(a - b).max() / max(np.abs(b).max(), 1e-30))
+
+
+def make_case(cin, cout, n, seed, ks=(3, 3, 3)):
+    rng = np.random.default_rng(seed)
+    shape, batch = (9, 40, 40), 2
+    lin = rng.permutation(rng.choice(batch * 9 * 1600, n, replace=False))
+    coors = np.stack([lin // 14400, (lin // 1600) % 9, (lin // 40) % 40, lin % 40], 1).astype(np.int32)
+    feats = rng.normal(size=(n, cin)).astype(np.float32)
+    w = (rng.normal(size=(*ks, cin, cout)) / np.sqrt(np.prod(ks) * cin)).astype(np.float32)
+    return shape, batch, coors, feats, w
+
+
+@pytest.mark.parametrize("cin,cout", SHAPES)
+@pytest.mark.parametrize("precision,tol", [(ops.PRECISION_TF32X3, 2e-5), (ops.PRECISION_TF32, 3e-3)])
+@pytest.mark.parametrize("fused", [False, True])
+def test_tc_subm_vs_oracle(cin, cout, precision, tol, fused):
+    assert ops.tf32_supported(cin, cout)
+    n = 3001                                                  # ragged: 23 full tiles + 57 rows
+    shape, batch, coors, feats, w = make_case(cin, cout, n, cin * 7 + cout)
+    rt, _ = R.rulebook_subm(coors, shape, 3)
+    c = torch.from_numpy(coors).cuda()
+    tbl = ops.rulebook_subm(c, ops.build_grid_index(c, batch, shape), 3)
+    ref = R.spconv_fwd(feats, w, rt, wide=True)
+    kw = {}
+    if fused:
+        rng = np.random.default_rng(1)
+        scale = rng.uniform(0.5, 1.5, cout).astype(np.float32)
+        shift = rng.normal(0, 0.2, cout).astype(np.float32)
+        res = rng.normal(size=(n, cout)).astype(np.float32)
+        ref = R.bn_act(ref, scale, shift, res, True)
+        kw = dict(scale=torch.from_numpy(scale).cuda(), shift=torch.from_numpy(shift).cuda(),
+                  residual=torch.from_numpy(res).cuda(), relu=True)
+    out = ops.spconv_fwd(torch.from_numpy(feats).cuda(), torch.from_numpy(w).cuda(), tbl, n, precision=precision, **kw)
+    torch.cuda.synchronize()
+    assert rel_err(out.cpu().numpy(), ref) < tol
+
+
+def test_tc_strided_and_k3_vs_oracle():
+    for (cin, cout, ks, st, pd) in [(32, 64, 3, 2, 1), (64, 128, 3, 2, (0, 1, 1)), (128, 128, (3, 1, 1), (2, 1, 1), 0)]:
+        kst = (ks,) * 3 if isinstance(ks, int) else ks
+        shape, batch, coors, feats, w = make_case(cin, cout, 2500, 5, kst)
+        oc, rt, oshape, _ = R.rulebook_sparse(coors, shape, ks, st, pd)
+        c = torch.from_numpy(coors).cuda()
+        idx = ops.build_grid_index(c, batch, shape)
+        sc = ops.sparse_out_coords(c, len(coors), batch, shape, ks, st, pd)
+        tbl = ops.rulebook_sparse(sc.coors, idx, ks, st, pd)
+        np.testing.assert_array_equal(tbl.cpu().numpy(), rt)
+        ref = R.spconv_fwd(feats, w, rt, wide=True)
+        out = ops.spconv_fwd(torch.from_numpy(feats).cuda(), torch.from_numpy(w).cuda(), tbl, len(oc),
+                             precision=ops.PRECISION_TF32X3)
+        assert rel_err(out.cpu().numpy(), ref) < 2e-5, (cin, cout)
+
+
+def test_tc_matches_fp32_kernel_and_is_deterministic():
+    shape, batch, coors, feats, w = make_case(64, 64, 4096, 9)
+    c = torch.from_numpy(coors).cuda()
+    tbl = ops.rulebook_subm(c, ops.build_grid_index(c, batch, shape), 3)
+    f, wt = torch.from_numpy(feats).cuda(), torch.from_numpy(w).cuda()
+    a = ops.spconv_fwd(f, wt, tbl, 4096, precision=ops.PRECISION_TF32X3)
+    b = ops.spconv_fwd(f, wt, tbl, 4096, precision=ops.PRECISION_TF32X3)
+    s = ops.spconv_fwd(f, wt, tbl, 4096, precision=ops.PRECISION_FP32)
+    assert torch.equal(a, b)
+    assert rel_err(a.cpu().numpy(), s.cpu().numpy()) < 2e-5
+
+
+def test_backbone_tf32x3_full_size_scene_vs_oracle():
+    """The shipped configuration: tcgen05 split-TF32 for Cin >= 32, fp32 CUDA cores below; 1e-3 bar."""
+    state = OB.random_state(1)
+    bb = registry.build_backbone(dict(type="SpMiddleResNetFHD", num_input_features=5, ds_factor=8))
+    bb.load_state_dict({k: torch.from_numpy(v) for k, v in state.items()}, strict=False)
+    bb = bb.cuda().eval()
+    bb.set_precision(ops.PRECISION_TF32X3)
+    assert bb.conv4[3].conv1.precision == ops.PRECISION_TF32X3 and bb.conv1[0].conv1.precision == ops.PRECISION_FP32
+    cloud = synth.lidar_scene(1000)
+    vb = ops.voxelize(torch.from_numpy(cloud).cuda(), [0, len(cloud)], synth.WAYMO_VOXEL, synth.WAYMO_RANGE, 5, 150000,
+                      want_voxels=False, mean_channels=5)
+    with torch.no_grad():
+        bev, multi = bb(vb.mean, vb.coors, 1, [1504, 1504, 40])
+    ref_bev, ref_multi = OB.backbone_forward(state, vb.mean.cpu().numpy(), vb.coors.cpu().numpy(), 1,
+                                             (1504, 1504, 40), wide=True)
+    for name in ("conv1", "conv2", "conv3", "conv4"):
+        assert rel_err(multi[name].features.cpu().numpy(), ref_multi[name][0]) < 1e-3, name
+    err = rel_err(bev.cpu().numpy(), ref_bev)
+    print("tf32x3 backbone rel err", err)
+    assert err < 1e-3
+    bb.set_precision(ops.PRECISION_TF32)
+    with torch.no_grad():
+        bev1, _ = bb(vb.mean, vb.coors, 1, [1504, 1504, 40])
+    err1 = rel_err(bev1.cpu().numpy(), ref_bev)
+    print("tf32 (single pass) backbone rel err", err1)
+    assert err1 < 2e-2
