@@ -1,0 +1,30 @@
+#!/usr/bin/env python
+"""Compact summary of an `ncu --set full` report: ncu_summary.py REPORT.ncu-rep  (runs `ncu -i ... --page raw --csv`)."""
+import csv
+import io
+import subprocess
+import sys
+
+WANT = ["gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum",
+        "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed", "lts__throughput.avg.pct_of_peak_sustained_elapsed",
+        "lts__t_sector_hit_rate.pct", "l1tex__throughput.avg.pct_of_peak_sustained_elapsed",
+        "sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_elapsed",
+        "sm__throughput.avg.pct_of_peak_sustained_elapsed", "sm__warps_active.avg.pct_of_peak_sustained_active",
+        "launch__registers_per_thread", "launch__grid_size", "launch__block_size",
+        "launch__shared_mem_per_block_dynamic", "smsp__inst_executed.sum", "sm__cycles_elapsed.max"]
+
+
+def main():
+    raw = subprocess.run(["ncu", "-i", sys.argv[1], "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    rows = list(csv.reader(io.StringIO(raw)))
+    hdr, units = rows[0], rows[1]
+    col = {h: i for i, h in enumerate(hdr)}
+    for r in rows[2:]:
+        print(r[col["Kernel Name"]][:80], "grid", r[col.get("launch__grid_size", 0)])
+        for w in WANT:
+            if w in col:
+                print(f"    {w:70s} {r[col[w]]:>16s} {units[col[w]]}")
+
+
+if __name__ == "__main__":
+    main()
