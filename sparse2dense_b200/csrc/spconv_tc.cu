@@ -3,25 +3,25 @@
 //
 //   out[o,:] = act( (sum_k in[tbl[k][o],:] @ W[k]) * scale + shift (+ residual[o,:]) )
 //
-// One CTA owns BM = 128 output rows and all Cout channels; the accumulator D[128 x Cout] lives in
-// TMEM for the whole tile.  The contraction runs over (kernel offset k) x (32-channel chunk c):
+// One CTA owns T = 4 tiles of BM = 128 output rows and all Cout channels; the T accumulators D[128 x Cout]
+// live in TMEM (T*Cout <= 512 columns) for the whole CTA.  The contraction runs over
+// (kernel offset k) x (32-channel chunk c) x (tile t); the weight tile of (k,c) is fetched ONCE per CTA and
+// reused by the T tiles, which divides the L2->SM weight traffic (the dominant stream at Cout=128) by T.
 //
-//   warps 0-3  A producers: gather the 128 neighbour rows of offset k (LDG.128, 8 lanes per 128 B
-//              row), split every value into TF32 hi + lo parts (cvt.rna) and store them into the
-//              128B-swizzled K-major UMMA layout (STS.128, conflict free); fence.proxy.async +
-//              mbarrier arrive.  After the main loop the same warps run the epilogue
+//   warps 0-7  A producers: gather the neighbour rows of (k, t) (LDG.128, 8 lanes per 128 B row, three
+//              steps of loads in flight per warp), split every value into TF32 hi + lo parts (cvt.rna) and
+//              store them into the 128B-swizzled K-major UMMA layout (STS.128, conflict free);
+//              fence.proxy.async + mbarrier arrive.  After the main loop the same warps run the epilogue
 //              (tcgen05.ld -> BN affine / residual / ReLU -> global).
-//   warp 4     B loader: one cp.async.bulk per step copies the pre-swizzled, pre-split weight tile
-//              (hi + lo, packed once per layer by s2d_spconv_pack_weights) and completes its bytes
-//              on the stage's mbarrier; also owns the TMEM allocation.
-//   warp 5     MMA issuer: one thread issues tcgen05.mma.kind::tf32 (M=128, N=Cout, K=8) x 4 per
-//              step -- three per K-slice in the split-precision mode:  Ahi*Bhi + Alo*Bhi + Ahi*Blo --
-//              and tcgen05.commit releases the stage / publishes the accumulator.
+//   warp 8     loader: neighbour-table slices of offset k+2 (coalesced copy into a 4-slot ring) and one
+//              cp.async.bulk per (k,c) for the pre-swizzled, pre-split weight tile (hi + lo, packed once
+//              per layer by s2d_spconv_pack_weights), completing on the slot's mbarrier; owns TMEM alloc.
+//   warp 9     MMA issuer: one thread issues tcgen05.mma.kind::tf32 (M=128, N=Cout, K=8) x 4 per step --
+//              three per K-slice in the split-precision mode:  Alo*Bhi + Ahi*Blo + Ahi*Bhi -- and
+//              tcgen05.commit releases the rings / publishes the accumulators.
 //
 // Precision modes: TF32X3 (error-compensated, ~fp32 accuracy: this is what meets the 1e-3 parity
-// bar through 21 layers) and TF32 (single pass, ~5e-4 relative error per layer).
-//
-// Offsets k for which no row of the tile has a neighbour are skipped by all three roles.
+// bar through 21 layers) and TF32 (single pass).
 #include "common.cuh"
 
 namespace s2d {
@@ -104,6 +104,20 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
       : "memory");
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "elect.sync _|p, 0xffffffff;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(pred));
+  return pred != 0;
+}
+// TF32 keeps 10 explicit mantissa bits: drop (truncate) or round-to-nearest (ties away) the low 13 bits
+__device__ __forceinline__ float tf32_trunc(float x) { return __uint_as_float(__float_as_uint(x) & 0xffffe000u); }
+__device__ __forceinline__ float tf32_round(float x) {
+  return __uint_as_float((__float_as_uint(x) + 0x1000u) & 0xffffe000u);
+}
 __device__ __forceinline__ float tf32_rna(float x) {
   uint32_t r;
   asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
@@ -130,207 +144,304 @@ __host__ __device__ __forceinline__ uint32_t sw128_chunk_offset(int r, int c16) 
 // ---------------------------------------------------------------------------------------------
 // kernel
 // ---------------------------------------------------------------------------------------------
+constexpr int kProducerWarps = 8;
+constexpr int kLoaderWarp = 8;
+constexpr int kMmaWarp = 9;
+constexpr int kTcThreads = 320;
+constexpr int kNbrSlots = 4;
+constexpr int kPrefetch = 3;   // A steps whose global loads are in flight per producer warp
+
 template <int CIN, int COUT, int PASSES>
 struct TcCfg {
   static constexpr int NCHUNK = CIN / kBK;
   static constexpr int NPART = PASSES == 3 ? 2 : 1;
-  static constexpr int A_TILE = kBM * kBK * 4;   // 16 KB
-  static constexpr int B_TILE = COUT * kBK * 4;  // 4 / 8 / 16 KB
-  static constexpr int STAGE_BYTES = NPART * (A_TILE + B_TILE);
-  static constexpr int NBR_BYTES = kTcMaxK * kBM * 4;
-  static constexpr int BUDGET = 232448 - 1280;   // 227 KB opt-in limit minus barriers/alignment slack
-  static constexpr int STAGES_RAW = (BUDGET - NBR_BYTES) / STAGE_BYTES;
-  static constexpr int STAGES = STAGES_RAW > 6 ? 6 : STAGES_RAW;
-  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + NBR_BYTES + 256 + 1024;  // + barriers + alignment slack
-  static constexpr int TMEM_COLS = COUT < 32 ? 32 : COUT;
+  static constexpr int T = 4;                          // 128-row tiles per CTA sharing every weight tile
+  static constexpr int ROWS = T * kBM;
+  static constexpr int A_TILE = kBM * kBK * 4;         // 16 KB
+  static constexpr int B_TILE = COUT * kBK * 4;        // 4 / 8 / 16 KB
+  static constexpr int A_STAGE = NPART * A_TILE;
+  static constexpr int B_STAGE = NPART * B_TILE;
+  static constexpr int SB = (B_STAGE >= 32 * 1024) ? 2 : 4;   // weight-tile ring (deeper when tiles are small)
+  static constexpr int NBR_BYTES = kNbrSlots * ROWS * 4;
+  static constexpr int BUDGET = 232448 - 2048;         // 227 KB opt-in limit minus barriers/alignment slack
+  static constexpr int SA_RAW = (BUDGET - NBR_BYTES - SB * B_STAGE) / A_STAGE;
+  static constexpr int SA = SA_RAW > 8 ? 8 : SA_RAW;   // gathered-tile ring
+  static constexpr int SMEM_BYTES = SA * A_STAGE + SB * B_STAGE + NBR_BYTES + 1024 + 1024;
+  static constexpr int TMEM_COLS = T * COUT;
+  static constexpr int BATCH = (SA >= 8) ? 4 : 2;      // steps per producer fence; needs SA >= 2*BATCH to overlap
   static_assert(CIN % kBK == 0, "Cin must be a multiple of 32");
-  static_assert(COUT % 16 == 0 && COUT >= 16 && COUT <= 256, "UMMA N constraint for M=128");
-  static_assert((COUT & (COUT - 1)) == 0, "TMEM allocation needs a power of two");
-  static_assert(STAGES >= 2, "not enough shared memory for a pipeline");
+  static_assert(COUT % 16 == 0 && COUT >= 32 && COUT <= 128, "UMMA N constraint for M=128 / TMEM budget");
+  static_assert((TMEM_COLS & (TMEM_COLS - 1)) == 0 && TMEM_COLS <= 512, "TMEM allocation: power of two <= 512");
+  static_assert(SA >= 2 * BATCH && T % BATCH == 0, "gathered-tile ring must hold two producer batches");
 };
 
+// One CTA = T row tiles.  Loop nest: kernel offset k > channel chunk c > tile t; the weight tile of (k,c) is
+// loaded once and feeds T MMAs groups (one per tile accumulator), so L2->SM weight traffic drops by T.
 template <int CIN, int COUT, int PASSES>
-__global__ void __launch_bounds__(192, 1)
+__global__ void __launch_bounds__(kTcThreads, 1)
 spconv_tc_kernel(const float* __restrict__ in, const float* __restrict__ packed, const int* __restrict__ tbl,
                  int tbl_stride, int n_out, int K, const float* __restrict__ scale, const float* __restrict__ shift,
                  const float* __restrict__ residual, int relu, float* __restrict__ out) {
   using Cfg = TcCfg<CIN, COUT, PASSES>;
-  constexpr int STAGES = Cfg::STAGES, NCHUNK = Cfg::NCHUNK, NPART = Cfg::NPART;
-  constexpr int A_TILE = Cfg::A_TILE, B_TILE = Cfg::B_TILE;
+  constexpr int SA = Cfg::SA, SB = Cfg::SB, NCHUNK = Cfg::NCHUNK, T = Cfg::T;
+  constexpr int A_TILE = Cfg::A_TILE, B_TILE = Cfg::B_TILE, A_STAGE = Cfg::A_STAGE, B_STAGE = Cfg::B_STAGE;
+  constexpr int STEPS_PER_K = NCHUNK * T;
 
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint8_t* stage_base = smem;                                          // STAGES x [A_hi | A_lo | B_hi | B_lo]
-  int* s_nbr = reinterpret_cast<int*>(smem + STAGES * Cfg::STAGE_BYTES);   // [K][128]
+  uint8_t* a_ring = smem;                                   // SA x [A_hi | A_lo]
+  uint8_t* b_ring = a_ring + SA * A_STAGE;                  // SB x [B_hi | B_lo]
+  int* s_nbr = reinterpret_cast<int*>(b_ring + SB * B_STAGE);   // kNbrSlots x [T*128]
   uint64_t* bars = reinterpret_cast<uint64_t*>(reinterpret_cast<uint8_t*>(s_nbr) + Cfg::NBR_BYTES);
-  // bars[0..STAGES) full, [STAGES..2*STAGES) empty, [2*STAGES] accumulator ready
-  uint32_t* s_misc = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 1);  // [0] tmem base, [1] kmask
+  uint64_t* bar_a_full = bars;
+  uint64_t* bar_a_empty = bar_a_full + SA;
+  uint64_t* bar_b_full = bar_a_empty + SA;
+  uint64_t* bar_b_empty = bar_b_full + SB;
+  uint64_t* bar_n_full = bar_b_empty + SB;
+  uint64_t* bar_n_empty = bar_n_full + kNbrSlots;
+  uint64_t* bar_accum = bar_n_empty + kNbrSlots;
+  uint32_t* s_tmem = reinterpret_cast<uint32_t*>(bar_accum + 1);
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int tile0 = blockIdx.x * kBM;
-  const uint32_t full0 = smem_u32(bars), empty0 = smem_u32(bars + STAGES), accum_bar = smem_u32(bars + 2 * STAGES);
+  const int tile0 = blockIdx.x * Cfg::ROWS;
+  const int nsteps = K * STEPS_PER_K;
 
-  if (tid == 0) s_misc[1] = 0;
-  if (warp == 5 && lane == 0) {
-    for (int s = 0; s < STAGES; ++s) {
-      mbar_init(full0 + 8 * s, 128 + 1);  // 128 A-producer arrives + the B loader's arrive.expect_tx
-      mbar_init(empty0 + 8 * s, 1);       // one tcgen05.commit
+  if (warp == kMmaWarp && lane == 0) {
+    for (int s = 0; s < SA; ++s) {
+      mbar_init(smem_u32(bar_a_full + s), kProducerWarps);        // one arrival per producer warp
+      mbar_init(smem_u32(bar_a_empty + s), 1);                    // one tcgen05.commit
     }
-    mbar_init(accum_bar, 1);
+    for (int s = 0; s < SB; ++s) {
+      mbar_init(smem_u32(bar_b_full + s), 1);                     // arrive.expect_tx of the loader
+      mbar_init(smem_u32(bar_b_empty + s), 1);
+    }
+    for (int s = 0; s < kNbrSlots; ++s) {
+      mbar_init(smem_u32(bar_n_full + s), 32);                    // every loader lane arrives
+      mbar_init(smem_u32(bar_n_empty + s), kProducerWarps);
+    }
+    mbar_init(smem_u32(bar_accum), 1);
     fence_barrier_init();
   }
-  if (warp == 4) tmem_alloc(smem_u32(s_misc), Cfg::TMEM_COLS);
-  __syncthreads();
-  for (int idx = tid; idx < K * kBM; idx += 192) {
-    const int k = idx >> 7, r = idx & 127;
-    const int row = tile0 + r;
-    const int j = row < n_out ? __ldg(tbl + (size_t)k * tbl_stride + row) : -1;
-    s_nbr[idx] = j;
-    if (j >= 0) atomicOr(&s_misc[1], 1u << k);
-  }
+  if (warp == kLoaderWarp) tmem_alloc(smem_u32(s_tmem), Cfg::TMEM_COLS);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  const uint32_t tmem_base = s_misc[0];
-  const uint32_t kmask = s_misc[1];
+  const uint32_t tmem_base = *s_tmem;
 
-  if (warp < 4) {
-    // ===================== A producers =====================
-    const int c16 = tid & 7;      // 16 B chunk inside the 128 B row
-    const int r0 = tid >> 3;      // 16 rows per pass, 8 passes
-    int it = 0;
-    for (int k = 0; k < K; ++k) {
-      if (!((kmask >> k) & 1)) continue;
-      const int* nbr = s_nbr + k * kBM;
-#pragma unroll 1
-      for (int c = 0; c < NCHUNK; ++c, ++it) {
-        const int stage = it % STAGES;
-        const uint32_t phase = (it / STAGES) & 1;
-        float4 v[8];
+  if (warp < kProducerWarps) {
+    // ===================== A producers (8 warps x 16 rows) =====================
+    const int c16 = lane & 7;                    // 16 B chunk inside the 128 B row
+    const int rbase = warp * 16 + (lane >> 3);   // rows rbase + 4*i, i = 0..3
+    const float4* in4 = reinterpret_cast<const float4*>(in);
+    const uint32_t bar_a_full0 = smem_u32(bar_a_full), bar_a_empty0 = smem_u32(bar_a_empty);
+    const uint32_t bar_n_full0 = smem_u32(bar_n_full), bar_n_empty0 = smem_u32(bar_n_empty);
+    // swizzled byte offsets of this lane's four 16 B chunks inside a tile (constant over the whole kernel)
+    uint32_t soff[4];
 #pragma unroll
-        for (int p = 0; p < 8; ++p) {
-          const int j = nbr[p * 16 + r0];
-          v[p] = make_float4(0.f, 0.f, 0.f, 0.f);
-          if (j >= 0) v[p] = __ldg(reinterpret_cast<const float4*>(in + (size_t)j * CIN + c * kBK) + c16);
+    for (int i = 0; i < 4; ++i) soff[i] = sw128_chunk_offset(rbase + 4 * i, c16);
+
+    // Steps are produced in batches of BATCH: the loads of batch n+1 are issued before batch n is converted
+    // and stored, and there is ONE fence.proxy.async per batch.  (The fence also waits for the thread's
+    // outstanding global loads, so a fence per step would serialise the gather on the memory latency.)
+    constexpr int BATCH = Cfg::BATCH;
+    // load stream position (k, c, t) and store stream position (stage, phase): plain counters, no divisions
+    int lk = 0, lc = 0, lt = 0;
+    int sstage = 0;
+    uint32_t sphase = 1;                         // first pass over the ring: slots are free
+    auto load_batch = [&](float4 (&v)[BATCH][4]) {
+#pragma unroll
+      for (int b = 0; b < BATCH; ++b) {
+        const int slot = lk & (kNbrSlots - 1);
+        if ((lc | lt) == 0) mbar_wait(bar_n_full0 + 8 * slot, (lk / kNbrSlots) & 1);
+        const int* nbr = s_nbr + slot * Cfg::ROWS + lt * kBM + rbase;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const int j = nbr[4 * i];
+          v[b][i] = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (j >= 0) v[b][i] = __ldg(in4 + ((size_t)j * (CIN / 4) + lc * (kBK / 4) + c16));
         }
-        mbar_wait(empty0 + 8 * stage, phase ^ 1);
-        uint8_t* a_hi = stage_base + (size_t)stage * Cfg::STAGE_BYTES;
+        if (++lt == T) {
+          lt = 0;
+          if (++lc == NCHUNK) {
+            lc = 0;
+            __syncwarp();                        // every lane has read this k's indices
+            if (lane == 0) mbar_arrive(bar_n_empty0 + 8 * slot);
+            ++lk;
+          }
+        }
+      }
+    };
+    auto store_batch = [&](const float4 (&v)[BATCH][4]) {
+      const int stage0 = sstage;
 #pragma unroll
-        for (int p = 0; p < 8; ++p) {
-          const int r = p * 16 + r0;
-          const uint32_t off = sw128_chunk_offset(r, c16);
+      for (int b = 0; b < BATCH; ++b) {
+        mbar_wait(bar_a_empty0 + 8 * sstage, sphase);
+        uint8_t* a_hi = a_ring + (size_t)sstage * A_STAGE;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
           float4 hi;
-          hi.x = tf32_rna(v[p].x); hi.y = tf32_rna(v[p].y); hi.z = tf32_rna(v[p].z); hi.w = tf32_rna(v[p].w);
-          *reinterpret_cast<float4*>(a_hi + off) = hi;
           if constexpr (PASSES == 3) {
+            // split x = hi + lo exactly: hi keeps the 10 TF32 mantissa bits (truncation), lo the remainder
+            hi.x = tf32_trunc(v[b][i].x); hi.y = tf32_trunc(v[b][i].y);
+            hi.z = tf32_trunc(v[b][i].z); hi.w = tf32_trunc(v[b][i].w);
             float4 lo;
-            lo.x = v[p].x - hi.x; lo.y = v[p].y - hi.y; lo.z = v[p].z - hi.z; lo.w = v[p].w - hi.w;
-            *reinterpret_cast<float4*>(a_hi + A_TILE + off) = lo;
+            lo.x = v[b][i].x - hi.x; lo.y = v[b][i].y - hi.y; lo.z = v[b][i].z - hi.z; lo.w = v[b][i].w - hi.w;
+            *reinterpret_cast<float4*>(a_hi + A_TILE + soff[i]) = lo;
+          } else {
+            hi.x = tf32_round(v[b][i].x); hi.y = tf32_round(v[b][i].y);
+            hi.z = tf32_round(v[b][i].z); hi.w = tf32_round(v[b][i].w);
           }
+          *reinterpret_cast<float4*>(a_hi + soff[i]) = hi;
         }
-        fence_proxy_async();               // generic-proxy stores -> visible to the tensor core (async proxy)
-        mbar_arrive(full0 + 8 * stage);
+        if (++sstage == SA) { sstage = 0; sphase ^= 1; }
       }
+      fence_proxy_async();                 // generic-proxy stores -> visible to the tensor core (async proxy)
+      __syncwarp();
+      if (lane == 0) {                     // one arrival per producer warp and stage
+        int st = stage0;
+#pragma unroll
+        for (int b = 0; b < BATCH; ++b) {
+          mbar_arrive(bar_a_full0 + 8 * st);
+          if (++st == SA) st = 0;
+        }
+      }
+    };
+
+    const int nbatches = nsteps / BATCH;         // nsteps = K * NCHUNK * T is a multiple of T = 4 >= BATCH
+    float4 bufA[BATCH][4], bufB[BATCH][4];
+    if (nbatches > 0) load_batch(bufA);
+    for (int nb = 0; nb < nbatches; nb += 2) {
+      if (nb + 1 < nbatches) load_batch(bufB);
+      store_batch(bufA);
+      if (nb + 2 < nbatches) load_batch(bufA);
+      if (nb + 1 < nbatches) store_batch(bufB);
     }
-    // ===================== epilogue =====================
-    const int row = tile0 + tid;           // TMEM lane == tile row; warp w may touch lanes [32w, 32w+32)
-    if (kmask != 0) {
-      mbar_wait(accum_bar, 0);
-      tc_fence_after();
-    }
+
+    // ===================== epilogue (same 8 warps) =====================
+    // TMEM lane == row inside a tile; warp w may touch lanes [32*(w%4), +32).  Warps 0-3 take the even tiles,
+    // warps 4-7 the odd ones.
+    mbar_wait(smem_u32(bar_accum), 0);
+    tc_fence_after();
+    const int g = warp & 3;
 #pragma unroll 1
-    for (int c0 = 0; c0 < COUT; c0 += 32) {
-      uint32_t acc[32];
-      if (kmask != 0) {
-        tmem_ld32(tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)c0, acc);
-      } else {
+    for (int t = warp >> 2; t < T; t += 2) {
+      const int row = tile0 + t * kBM + g * 32 + lane;
+#pragma unroll 1
+      for (int c0 = 0; c0 < COUT; c0 += 32) {
+        uint32_t acc[32];
+        tmem_ld32(tmem_base + ((uint32_t)(g * 32) << 16) + (uint32_t)(t * COUT + c0), acc);
+        if (row < n_out) {
+          float* dst = out + (size_t)row * COUT + c0;
+          const float* res = residual ? residual + (size_t)row * COUT + c0 : nullptr;
 #pragma unroll
-        for (int i = 0; i < 32; ++i) acc[i] = 0u;
-      }
-      if (row < n_out) {
-        float* dst = out + (size_t)row * COUT + c0;
-        const float* res = residual ? residual + (size_t)row * COUT + c0 : nullptr;
-#pragma unroll
-        for (int q = 0; q < 8; ++q) {
-          float4 y;
-          y.x = __uint_as_float(acc[4 * q + 0]); y.y = __uint_as_float(acc[4 * q + 1]);
-          y.z = __uint_as_float(acc[4 * q + 2]); y.w = __uint_as_float(acc[4 * q + 3]);
-          if (scale) {
-            const float4 sc = __ldg(reinterpret_cast<const float4*>(scale + c0) + q);
-            y.x *= sc.x; y.y *= sc.y; y.z *= sc.z; y.w *= sc.w;
+          for (int q = 0; q < 8; ++q) {
+            float4 y;
+            y.x = __uint_as_float(acc[4 * q + 0]); y.y = __uint_as_float(acc[4 * q + 1]);
+            y.z = __uint_as_float(acc[4 * q + 2]); y.w = __uint_as_float(acc[4 * q + 3]);
+            if (scale) {
+              const float4 sc = __ldg(reinterpret_cast<const float4*>(scale + c0) + q);
+              y.x *= sc.x; y.y *= sc.y; y.z *= sc.z; y.w *= sc.w;
+            }
+            if (shift) {
+              const float4 sh = __ldg(reinterpret_cast<const float4*>(shift + c0) + q);
+              y.x += sh.x; y.y += sh.y; y.z += sh.z; y.w += sh.w;
+            }
+            if (res) {
+              const float4 rr = __ldg(reinterpret_cast<const float4*>(res) + q);
+              y.x += rr.x; y.y += rr.y; y.z += rr.z; y.w += rr.w;
+            }
+            if (relu) {
+              y.x = fmaxf(y.x, 0.f); y.y = fmaxf(y.y, 0.f); y.z = fmaxf(y.z, 0.f); y.w = fmaxf(y.w, 0.f);
+            }
+            reinterpret_cast<float4*>(dst)[q] = y;
           }
-          if (shift) {
-            const float4 sh = __ldg(reinterpret_cast<const float4*>(shift + c0) + q);
-            y.x += sh.x; y.y += sh.y; y.z += sh.z; y.w += sh.w;
-          }
-          if (res) {
-            const float4 rr = __ldg(reinterpret_cast<const float4*>(res) + q);
-            y.x += rr.x; y.y += rr.y; y.z += rr.z; y.w += rr.w;
-          }
-          if (relu) {
-            y.x = fmaxf(y.x, 0.f); y.y = fmaxf(y.y, 0.f); y.z = fmaxf(y.z, 0.f); y.w = fmaxf(y.w, 0.f);
-          }
-          reinterpret_cast<float4*>(dst)[q] = y;
         }
       }
     }
-  } else if (warp == 4) {
-    // ===================== B loader =====================
-    if (lane == 0) {
-      int it = 0;
-      for (int k = 0; k < K; ++k) {
-        if (!((kmask >> k) & 1)) continue;
-        for (int c = 0; c < NCHUNK; ++c, ++it) {
-          const int stage = it % STAGES;
-          const uint32_t phase = (it / STAGES) & 1;
-          mbar_wait(empty0 + 8 * stage, phase ^ 1);
-          const uint32_t bar = full0 + 8 * stage;
-          mbar_arrive_expect_tx(bar, NPART * B_TILE);
-          const float* src = packed + (size_t)(k * NCHUNK + c) * 2 * (B_TILE / 4);
-          bulk_copy_g2s(smem_u32(stage_base + (size_t)stage * Cfg::STAGE_BYTES + NPART * A_TILE), src, NPART * B_TILE,
+  } else if (warp == kLoaderWarp) {
+    // ===================== loader: neighbour-table slices (all lanes) + weight tiles (lane 0) =====================
+    auto load_nbr = [&](int k) {
+      const int slot = k % kNbrSlots;
+      mbar_wait(smem_u32(bar_n_empty + slot), ((k / kNbrSlots) & 1) ^ 1);
+      int* dst = s_nbr + slot * Cfg::ROWS;
+      const int* src = tbl + (size_t)k * tbl_stride + tile0;
+      int v[Cfg::ROWS / 32];
+#pragma unroll
+      for (int i = 0; i < Cfg::ROWS / 32; ++i)     // all loads in flight before the first store
+        v[i] = (tile0 + lane + 32 * i < n_out) ? __ldg(src + lane + 32 * i) : -1;
+#pragma unroll
+      for (int i = 0; i < Cfg::ROWS / 32; ++i) dst[lane + 32 * i] = v[i];
+      mbar_arrive(smem_u32(bar_n_full + slot));
+    };
+    if (0 < K) load_nbr(0);
+    if (1 < K) load_nbr(1);
+    for (int k = 0; k < K; ++k) {
+      if (k + 2 < K) load_nbr(k + 2);
+      if (lane == 0) {
+        for (int c = 0; c < NCHUNK; ++c) {
+          const int bstep = k * NCHUNK + c;
+          const int bs = bstep % SB;
+          mbar_wait(smem_u32(bar_b_empty + bs), ((bstep / SB) & 1) ^ 1);
+          const uint32_t bar = smem_u32(bar_b_full + bs);
+          mbar_arrive_expect_tx(bar, B_STAGE);
+          bulk_copy_g2s(smem_u32(b_ring + (size_t)bs * B_STAGE), packed + (size_t)bstep * 2 * (B_TILE / 4), B_STAGE,
                         bar);
         }
       }
+      __syncwarp();
     }
   } else {
     // ===================== MMA issuer =====================
-    if (lane == 0) {
-      constexpr uint32_t idesc = make_idesc_tf32(kBM, COUT);
-      int it = 0;
-      for (int k = 0; k < K; ++k) {
-        if (!((kmask >> k) & 1)) continue;
-        for (int c = 0; c < NCHUNK; ++c, ++it) {
-          const int stage = it % STAGES;
-          const uint32_t phase = (it / STAGES) & 1;
-          mbar_wait(full0 + 8 * stage, phase);
-          tc_fence_after();
-          const uint32_t a_hi = smem_u32(stage_base + (size_t)stage * Cfg::STAGE_BYTES);
-          const uint32_t b_hi = a_hi + NPART * A_TILE;
+    // The whole warp runs the (warp-uniform) loop so that descriptors and addresses stay in uniform
+    // registers; one elected lane issues the tcgen05 instructions.
+    constexpr uint32_t idesc = make_idesc_tf32(kBM, COUT);
+    // constant high word of the SW128 K-major descriptor: SBO = 1024 B, version 1, layout SWIZZLE_128B
+    constexpr uint32_t desc_hi = 64u | (1u << 14) | (2u << 29);
+    const uint32_t a_lo0 = ((smem_u32(a_ring) >> 4) & 0x3FFF) | (1u << 16);
+    const uint32_t b_lo0 = ((smem_u32(b_ring) >> 4) & 0x3FFF) | (1u << 16);
+    const uint32_t bar_a_full0 = smem_u32(bar_a_full), bar_a_empty0 = smem_u32(bar_a_empty);
+    const uint32_t bar_b_full0 = smem_u32(bar_b_full), bar_b_empty0 = smem_u32(bar_b_empty);
+    int stage = 0, bs = 0, t = 0;
+    uint32_t a_phase = 0, b_phase = 0, first = 1;
+    for (int s = 0; s < nsteps; ++s) {
+      if (t == 0) mbar_wait(bar_b_full0 + 8 * bs, b_phase);
+      mbar_wait(bar_a_full0 + 8 * stage, a_phase);
+      tc_fence_after();
+      if (elect_one()) {
+        const uint32_t a_lo = a_lo0 + (uint32_t)stage * (A_STAGE >> 4);
+        const uint32_t b_lo = b_lo0 + (uint32_t)bs * (B_STAGE >> 4);
+        const uint32_t d = tmem_base + (uint32_t)(t * COUT);
 #pragma unroll
-          for (int s = 0; s < kBK / 8; ++s) {   // UMMA K = 8 for TF32: 32 B steps inside the swizzled row
-            const uint64_t da_hi = make_desc_sw128(a_hi + 32 * s);
-            const uint64_t db_hi = make_desc_sw128(b_hi + 32 * s);
-            if constexpr (PASSES == 3) {
-              const uint64_t da_lo = make_desc_sw128(a_hi + A_TILE + 32 * s);
-              const uint64_t db_lo = make_desc_sw128(b_hi + B_TILE + 32 * s);
-              umma_tf32(tmem_base, da_lo, db_hi, idesc, (it | s) != 0);   // small terms first
-              umma_tf32(tmem_base, da_hi, db_lo, idesc, 1);
-              umma_tf32(tmem_base, da_hi, db_hi, idesc, 1);
-            } else {
-              umma_tf32(tmem_base, da_hi, db_hi, idesc, (it | s) != 0);
-            }
+        for (int q = 0; q < kBK / 8; ++q) {   // UMMA K = 8 for TF32: 32 B (= 2 x 16 B) steps inside the swizzled row
+          const uint64_t da_hi = ((uint64_t)desc_hi << 32) | (a_lo + 2 * q);
+          const uint64_t db_hi = ((uint64_t)desc_hi << 32) | (b_lo + 2 * q);
+          if constexpr (PASSES == 3) {
+            const uint64_t da_lo = ((uint64_t)desc_hi << 32) | (a_lo + (A_TILE >> 4) + 2 * q);
+            const uint64_t db_lo = ((uint64_t)desc_hi << 32) | (b_lo + (B_TILE >> 4) + 2 * q);
+            umma_tf32(d, da_lo, db_hi, idesc, q == 0 ? (first ^ 1u) : 1u);   // small terms first
+            umma_tf32(d, da_hi, db_lo, idesc, 1);
+            umma_tf32(d, da_hi, db_hi, idesc, 1);
+          } else {
+            umma_tf32(d, da_hi, db_hi, idesc, q == 0 ? (first ^ 1u) : 1u);
           }
-          umma_commit(empty0 + 8 * stage);   // stage reusable once these MMAs have read it
         }
+        umma_commit(bar_a_empty0 + 8 * stage);                  // gathered tile reusable once read
+        if (t == T - 1) umma_commit(bar_b_empty0 + 8 * bs);     // weight tile reusable
+        if (s == nsteps - 1) umma_commit(smem_u32(bar_accum));  // all accumulators complete
       }
-      if (it > 0) umma_commit(accum_bar);      // accumulator complete
+      __syncwarp();
+      if (++stage == SA) { stage = 0; a_phase ^= 1; }
+      if (++t == T) {
+        t = 0;
+        first = 0;                                              // every tile has seen its first (k=0,c=0) MMA
+        if (++bs == SB) { bs = 0; b_phase ^= 1; }
+      }
     }
   }
-  __syncwarp();
 
   tc_fence_before();
   __syncthreads();
-  if (warp == 4) tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
+  if (warp == kLoaderWarp) tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -368,7 +479,7 @@ static int launch_tc(const float* in, const float* packed, const int* tbl, int t
                                   Cfg::SMEM_BYTES));
     configured = true;
   }
-  spconv_tc_kernel<CIN, COUT, PASSES><<<div_up(n_out, kBM), 192, Cfg::SMEM_BYTES, st>>>(
+  spconv_tc_kernel<CIN, COUT, PASSES><<<div_up(n_out, Cfg::ROWS), kTcThreads, Cfg::SMEM_BYTES, st>>>(
       in, packed, tbl, tbl_stride, n_out, K, scale, shift, residual, relu, out);
   S2D_LAUNCH_CHECK();
   count_launches(1);
