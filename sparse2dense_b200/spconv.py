@@ -154,7 +154,7 @@ class SparseConvolution(SparseModule):
         """conv (+ eval BatchNorm1d) (+ residual) (+ ReLU) in one kernel launch."""
         assert isinstance(x, SparseConvTensor)
         ind = self._indice(x)
-        scale, shift = _fold_bn(bn, self.bias, self.out_channels, x.features.device)
+        scale, shift = self._folded(bn, x.features.device)
         n_out = ind.out_indices.shape[0]
         packed = self._packed_weights() if self.precision != ops.PRECISION_FP32 else None
         feats = ops.spconv_fwd(x.features.contiguous(), self.weight.detach(), ind.tbl, n_out, scale, shift,
@@ -166,6 +166,16 @@ class SparseConvolution(SparseModule):
 
     def forward(self, x):
         return self.fused_forward(x)
+
+    def _folded(self, bn, device):
+        """(scale, shift) of the eval-mode BatchNorm (+ conv bias), cached until a parameter changes."""
+        tensors = [self.bias] if bn is None else [self.bias, bn.weight, bn.bias, bn.running_mean, bn.running_var]
+        key = (id(bn), str(device)) + tuple((t.data_ptr(), t._version) if t is not None else None for t in tensors)
+        cache = self.__dict__.get("_fold_cache")
+        if cache is None or cache[0] != key:
+            cache = (key,) + _fold_bn(bn, self.bias, self.out_channels, device)
+            self.__dict__["_fold_cache"] = cache
+        return cache[1], cache[2]
 
     def _packed_weights(self):
         key = (self.weight.data_ptr(), self.weight._version, str(self.weight.device))
