@@ -91,6 +91,26 @@ __device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t desc_a, uint
       "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
       : "memory");
 }
+// D[tmem] (+)= A[tmem] * B[smem]  (TS mode: the A operand is read from tensor memory, lane = row, column = k)
+__device__ __forceinline__ void umma_tf32_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t desc_b, uint32_t idesc,
+                                             uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t}" ::"r"(tmem_d),
+      "r"(tmem_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// 16 lanes x 32 columns: reg 4n+e -> (lane l/4, column 8n + 2(l%4) + e), reg 4n+2+e -> lane l/4 + 8 (probed on B200)
+__device__ __forceinline__ void tmem_st_16x256b_x4(uint32_t taddr, const uint32_t (&v)[16]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.16x256b.x4.b32 [%0], "
+      "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};" ::"r"(taddr),
+      "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]), "r"(v[8]), "r"(v[9]),
+      "r"(v[10]), "r"(v[11]), "r"(v[12]), "r"(v[13]), "r"(v[14]), "r"(v[15])
+      : "memory");
+}
+__device__ __forceinline__ void tmem_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
   asm volatile(
       "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
@@ -149,34 +169,39 @@ constexpr int kLoaderWarp = 8;
 constexpr int kMmaWarp = 9;
 constexpr int kTcThreads = 320;
 constexpr int kNbrSlots = 4;
-constexpr int kPrefetch = 3;   // A steps whose global loads are in flight per producer warp
+
+// A tile element (row m, channel ch of the 32-channel chunk) lives in TMEM lane m, column a_col(ch).  The
+// permutation makes the 8 columns a thread owns in a tcgen05.st.16x256b.x4 fragment
+// (columns 8n + 2j + e, j = lane % 4) equal to 8 CONTIGUOUS channels [8j, 8j+8) of its row, so the gather is
+// two LDG.128 per row.  The weight tiles are packed with the same K permutation (pack_weights_kernel).
+__host__ __device__ constexpr int a_col_of_channel(int ch) { return 8 * ((ch % 8) / 2) + 2 * (ch / 8) + (ch % 2); }
 
 template <int CIN, int COUT, int PASSES>
 struct TcCfg {
   static constexpr int NCHUNK = CIN / kBK;
   static constexpr int NPART = PASSES == 3 ? 2 : 1;
-  static constexpr int T = 4;                          // 128-row tiles per CTA sharing every weight tile
+  static constexpr int T = COUT >= 128 ? 2 : 4;        // 128-row tiles per CTA sharing every weight tile
   static constexpr int ROWS = T * kBM;
-  static constexpr int A_TILE = kBM * kBK * 4;         // 16 KB
   static constexpr int B_TILE = COUT * kBK * 4;        // 4 / 8 / 16 KB
-  static constexpr int A_STAGE = NPART * A_TILE;
   static constexpr int B_STAGE = NPART * B_TILE;
-  static constexpr int SB = (B_STAGE >= 32 * 1024) ? 2 : 4;   // weight-tile ring (deeper when tiles are small)
+  static constexpr int SB = 4;                         // weight-tile ring (shared memory)
+  static constexpr int ACC_COLS = T * COUT;            // TMEM: accumulators ...
+  static constexpr int A_COLS = NPART * kBK;           // ... and one gathered A stage (hi | lo), 32 columns each
+  static constexpr int SA_RAW = (512 - ACC_COLS) / A_COLS;
+  static constexpr int SA = SA_RAW > 8 ? 8 : SA_RAW;   // gathered-tile ring (TMEM)
+  static constexpr int TMEM_COLS = 512;
   static constexpr int NBR_BYTES = kNbrSlots * ROWS * 4;
-  static constexpr int BUDGET = 232448 - 2048;         // 227 KB opt-in limit minus barriers/alignment slack
-  static constexpr int SA_RAW = (BUDGET - NBR_BYTES - SB * B_STAGE) / A_STAGE;
-  static constexpr int SA = SA_RAW > 8 ? 8 : SA_RAW;   // gathered-tile ring
-  static constexpr int SMEM_BYTES = SA * A_STAGE + SB * B_STAGE + NBR_BYTES + 1024 + 1024;
-  static constexpr int TMEM_COLS = T * COUT;
-  static constexpr int BATCH = (SA >= 8) ? 4 : 2;      // steps per producer fence; needs SA >= 2*BATCH to overlap
+  static constexpr int SMEM_BYTES = SB * B_STAGE + NBR_BYTES + 1024 + 1024;
   static_assert(CIN % kBK == 0, "Cin must be a multiple of 32");
   static_assert(COUT % 16 == 0 && COUT >= 32 && COUT <= 128, "UMMA N constraint for M=128 / TMEM budget");
-  static_assert((TMEM_COLS & (TMEM_COLS - 1)) == 0 && TMEM_COLS <= 512, "TMEM allocation: power of two <= 512");
+  static constexpr int BATCH = 1;                      // steps per producer hand-off (2 measured slower except 128->128 TF32)
   static_assert(SA >= 2 * BATCH && T % BATCH == 0, "gathered-tile ring must hold two producer batches");
 };
 
 // One CTA = T row tiles.  Loop nest: kernel offset k > channel chunk c > tile t; the weight tile of (k,c) is
-// loaded once and feeds T MMAs groups (one per tile accumulator), so L2->SM weight traffic drops by T.
+// loaded once and feeds T MMA groups (one per tile accumulator).  The gathered A operand never touches
+// shared memory: the producer warps write it straight into TMEM (tcgen05.st) and the MMAs run in TS mode,
+// so shared-memory bandwidth only carries the small weight slices.
 template <int CIN, int COUT, int PASSES>
 __global__ void __launch_bounds__(kTcThreads, 1)
 spconv_tc_kernel(const float* __restrict__ in, const float* __restrict__ packed, const int* __restrict__ tbl,
@@ -184,13 +209,11 @@ spconv_tc_kernel(const float* __restrict__ in, const float* __restrict__ packed,
                  const float* __restrict__ residual, int relu, float* __restrict__ out) {
   using Cfg = TcCfg<CIN, COUT, PASSES>;
   constexpr int SA = Cfg::SA, SB = Cfg::SB, NCHUNK = Cfg::NCHUNK, T = Cfg::T;
-  constexpr int A_TILE = Cfg::A_TILE, B_TILE = Cfg::B_TILE, A_STAGE = Cfg::A_STAGE, B_STAGE = Cfg::B_STAGE;
-  constexpr int STEPS_PER_K = NCHUNK * T;
+  constexpr int B_TILE = Cfg::B_TILE, B_STAGE = Cfg::B_STAGE, A_COLS = Cfg::A_COLS;
 
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint8_t* a_ring = smem;                                   // SA x [A_hi | A_lo]
-  uint8_t* b_ring = a_ring + SA * A_STAGE;                  // SB x [B_hi | B_lo]
+  uint8_t* b_ring = smem;                                       // SB x [B_hi | B_lo]
   int* s_nbr = reinterpret_cast<int*>(b_ring + SB * B_STAGE);   // kNbrSlots x [T*128]
   uint64_t* bars = reinterpret_cast<uint64_t*>(reinterpret_cast<uint8_t*>(s_nbr) + Cfg::NBR_BYTES);
   uint64_t* bar_a_full = bars;
@@ -204,7 +227,7 @@ spconv_tc_kernel(const float* __restrict__ in, const float* __restrict__ packed,
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int tile0 = blockIdx.x * Cfg::ROWS;
-  const int nsteps = K * STEPS_PER_K;
+  const int nsteps = K * NCHUNK * T;
 
   if (warp == kMmaWarp && lane == 0) {
     for (int s = 0; s < SA; ++s) {
@@ -227,38 +250,42 @@ spconv_tc_kernel(const float* __restrict__ in, const float* __restrict__ packed,
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *s_tmem;
+  const uint32_t tmem_a0 = tmem_base + Cfg::ACC_COLS;            // first column of the A ring
 
   if (warp < kProducerWarps) {
     // ===================== A producers (8 warps x 16 rows) =====================
-    const int c16 = lane & 7;                    // 16 B chunk inside the 128 B row
-    const int rbase = warp * 16 + (lane >> 3);   // rows rbase + 4*i, i = 0..3
+    // warp w owns TMEM lanes (= tile rows) [32*(w%4) + 16*(w/4), +16); lane l: rows rA = base + l/4 and rA + 8,
+    // channels [8*(l%4), +8) of the chunk (see a_col_of_channel).
+    const int row16 = 32 * (warp & 3) + 16 * (warp >> 2);
+    const int rA = row16 + (lane >> 2);
+    const int j4 = (lane & 3) * 2;               // float4 index of this lane's 8 channels inside the chunk
     const float4* in4 = reinterpret_cast<const float4*>(in);
     const uint32_t bar_a_full0 = smem_u32(bar_a_full), bar_a_empty0 = smem_u32(bar_a_empty);
     const uint32_t bar_n_full0 = smem_u32(bar_n_full), bar_n_empty0 = smem_u32(bar_n_empty);
-    // swizzled byte offsets of this lane's four 16 B chunks inside a tile (constant over the whole kernel)
-    uint32_t soff[4];
-#pragma unroll
-    for (int i = 0; i < 4; ++i) soff[i] = sw128_chunk_offset(rbase + 4 * i, c16);
+    const uint32_t tmem_mine = tmem_a0 + ((uint32_t)row16 << 16);
 
-    // Steps are produced in batches of BATCH: the loads of batch n+1 are issued before batch n is converted
-    // and stored, and there is ONE fence.proxy.async per batch.  (The fence also waits for the thread's
-    // outstanding global loads, so a fence per step would serialise the gather on the memory latency.)
+    // Steps are produced in batches of BATCH: one empty-wait / tcgen05.wait::st / fence / arrive sequence per
+    // batch amortises the fixed latencies of the hand-off; the loads of the next batch are already in flight.
     constexpr int BATCH = Cfg::BATCH;
-    // load stream position (k, c, t) and store stream position (stage, phase): plain counters, no divisions
-    int lk = 0, lc = 0, lt = 0;
-    int sstage = 0;
+    int lk = 0, lc = 0, lt = 0;                  // load stream position (k, c, t)
+    int sstage = 0;                              // store stream position
     uint32_t sphase = 1;                         // first pass over the ring: slots are free
+    // v[b][0..1] = row rA channels 8j..8j+7, v[b][2..3] = row rA+8
     auto load_batch = [&](float4 (&v)[BATCH][4]) {
 #pragma unroll
       for (int b = 0; b < BATCH; ++b) {
         const int slot = lk & (kNbrSlots - 1);
         if ((lc | lt) == 0) mbar_wait(bar_n_full0 + 8 * slot, (lk / kNbrSlots) & 1);
-        const int* nbr = s_nbr + slot * Cfg::ROWS + lt * kBM + rbase;
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          const int j = nbr[4 * i];
-          v[b][i] = make_float4(0.f, 0.f, 0.f, 0.f);
-          if (j >= 0) v[b][i] = __ldg(in4 + ((size_t)j * (CIN / 4) + lc * (kBK / 4) + c16));
+        const int* nbr = s_nbr + slot * Cfg::ROWS + lt * kBM + rA;
+        const int ja = nbr[0], jb = nbr[8];
+        v[b][0] = v[b][1] = v[b][2] = v[b][3] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (ja >= 0) {
+          const float4* p = in4 + ((size_t)ja * (CIN / 4) + lc * (kBK / 4) + j4);
+          v[b][0] = __ldg(p); v[b][1] = __ldg(p + 1);
+        }
+        if (jb >= 0) {
+          const float4* p = in4 + ((size_t)jb * (CIN / 4) + lc * (kBK / 4) + j4);
+          v[b][2] = __ldg(p); v[b][3] = __ldg(p + 1);
         }
         if (++lt == T) {
           lt = 0;
@@ -276,29 +303,40 @@ spconv_tc_kernel(const float* __restrict__ in, const float* __restrict__ packed,
 #pragma unroll
       for (int b = 0; b < BATCH; ++b) {
         mbar_wait(bar_a_empty0 + 8 * sstage, sphase);
-        uint8_t* a_hi = a_ring + (size_t)sstage * A_STAGE;
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          float4 hi;
-          if constexpr (PASSES == 3) {
-            // split x = hi + lo exactly: hi keeps the 10 TF32 mantissa bits (truncation), lo the remainder
-            hi.x = tf32_trunc(v[b][i].x); hi.y = tf32_trunc(v[b][i].y);
-            hi.z = tf32_trunc(v[b][i].z); hi.w = tf32_trunc(v[b][i].w);
-            float4 lo;
-            lo.x = v[b][i].x - hi.x; lo.y = v[b][i].y - hi.y; lo.z = v[b][i].z - hi.z; lo.w = v[b][i].w - hi.w;
-            *reinterpret_cast<float4*>(a_hi + A_TILE + soff[i]) = lo;
-          } else {
-            hi.x = tf32_round(v[b][i].x); hi.y = tf32_round(v[b][i].y);
-            hi.z = tf32_round(v[b][i].z); hi.w = tf32_round(v[b][i].w);
-          }
-          *reinterpret_cast<float4*>(a_hi + soff[i]) = hi;
-        }
+        if (b == BATCH - 1) tc_fence_after();
         if (++sstage == SA) { sstage = 0; sphase ^= 1; }
       }
-      fence_proxy_async();                 // generic-proxy stores -> visible to the tensor core (async proxy)
+      int st = stage0;
+#pragma unroll
+      for (int b = 0; b < BATCH; ++b) {
+        // fragment order of tcgen05.st.16x256b.x4: reg 4n+e = row rA, column 8n+2j+e; reg 4n+2+e = row rA+8
+        const float xa[8] = {v[b][0].x, v[b][0].y, v[b][0].z, v[b][0].w, v[b][1].x, v[b][1].y, v[b][1].z, v[b][1].w};
+        const float xb[8] = {v[b][2].x, v[b][2].y, v[b][2].z, v[b][2].w, v[b][3].x, v[b][3].y, v[b][3].z, v[b][3].w};
+        uint32_t hi[16], lo[16];
+#pragma unroll
+        for (int n = 0; n < 4; ++n)
+#pragma unroll
+          for (int e = 0; e < 2; ++e) {
+            const float a = xa[2 * n + e], c = xb[2 * n + e];
+            if constexpr (PASSES == 3) {
+              const float ah = tf32_trunc(a), ch = tf32_trunc(c);   // x = hi + lo exactly
+              hi[4 * n + e] = __float_as_uint(ah);      lo[4 * n + e] = __float_as_uint(a - ah);
+              hi[4 * n + 2 + e] = __float_as_uint(ch);  lo[4 * n + 2 + e] = __float_as_uint(c - ch);
+            } else {
+              hi[4 * n + e] = __float_as_uint(tf32_round(a));
+              hi[4 * n + 2 + e] = __float_as_uint(tf32_round(c));
+            }
+          }
+        const uint32_t dst = tmem_mine + (uint32_t)(st * A_COLS);
+        tmem_st_16x256b_x4(dst, hi);
+        if constexpr (PASSES == 3) tmem_st_16x256b_x4(dst + kBK, lo);
+        if (++st == SA) st = 0;
+      }
+      tmem_wait_st();
+      tc_fence_before();
       __syncwarp();
-      if (lane == 0) {                     // one arrival per producer warp and stage
-        int st = stage0;
+      if (lane == 0) {                           // one arrival per producer warp and stage
+        st = stage0;
 #pragma unroll
         for (int b = 0; b < BATCH; ++b) {
           mbar_arrive(bar_a_full0 + 8 * st);
@@ -307,7 +345,7 @@ spconv_tc_kernel(const float* __restrict__ in, const float* __restrict__ packed,
       }
     };
 
-    const int nbatches = nsteps / BATCH;         // nsteps = K * NCHUNK * T is a multiple of T = 4 >= BATCH
+    const int nbatches = nsteps / BATCH;         // nsteps = K * NCHUNK * T is a multiple of T >= BATCH
     float4 bufA[BATCH][4], bufB[BATCH][4];
     if (nbatches > 0) load_batch(bufA);
     for (int nb = 0; nb < nbatches; nb += 2) {
@@ -393,11 +431,10 @@ spconv_tc_kernel(const float* __restrict__ in, const float* __restrict__ packed,
   } else {
     // ===================== MMA issuer =====================
     // The whole warp runs the (warp-uniform) loop so that descriptors and addresses stay in uniform
-    // registers; one elected lane issues the tcgen05 instructions.
+    // registers; one elected lane issues the tcgen05 instructions.  A comes from TMEM (TS mode).
     constexpr uint32_t idesc = make_idesc_tf32(kBM, COUT);
     // constant high word of the SW128 K-major descriptor: SBO = 1024 B, version 1, layout SWIZZLE_128B
     constexpr uint32_t desc_hi = 64u | (1u << 14) | (2u << 29);
-    const uint32_t a_lo0 = ((smem_u32(a_ring) >> 4) & 0x3FFF) | (1u << 16);
     const uint32_t b_lo0 = ((smem_u32(b_ring) >> 4) & 0x3FFF) | (1u << 16);
     const uint32_t bar_a_full0 = smem_u32(bar_a_full), bar_a_empty0 = smem_u32(bar_a_empty);
     const uint32_t bar_b_full0 = smem_u32(bar_b_full), bar_b_empty0 = smem_u32(bar_b_empty);
@@ -408,21 +445,19 @@ spconv_tc_kernel(const float* __restrict__ in, const float* __restrict__ packed,
       mbar_wait(bar_a_full0 + 8 * stage, a_phase);
       tc_fence_after();
       if (elect_one()) {
-        const uint32_t a_lo = a_lo0 + (uint32_t)stage * (A_STAGE >> 4);
+        const uint32_t a_hi = tmem_a0 + (uint32_t)(stage * A_COLS);
         const uint32_t b_lo = b_lo0 + (uint32_t)bs * (B_STAGE >> 4);
         const uint32_t d = tmem_base + (uint32_t)(t * COUT);
 #pragma unroll
-        for (int q = 0; q < kBK / 8; ++q) {   // UMMA K = 8 for TF32: 32 B (= 2 x 16 B) steps inside the swizzled row
-          const uint64_t da_hi = ((uint64_t)desc_hi << 32) | (a_lo + 2 * q);
+        for (int q = 0; q < kBK / 8; ++q) {   // UMMA K = 8 for TF32: 8 TMEM columns of A, 32 B of every B row
           const uint64_t db_hi = ((uint64_t)desc_hi << 32) | (b_lo + 2 * q);
           if constexpr (PASSES == 3) {
-            const uint64_t da_lo = ((uint64_t)desc_hi << 32) | (a_lo + (A_TILE >> 4) + 2 * q);
             const uint64_t db_lo = ((uint64_t)desc_hi << 32) | (b_lo + (B_TILE >> 4) + 2 * q);
-            umma_tf32(d, da_lo, db_hi, idesc, q == 0 ? (first ^ 1u) : 1u);   // small terms first
-            umma_tf32(d, da_hi, db_lo, idesc, 1);
-            umma_tf32(d, da_hi, db_hi, idesc, 1);
+            umma_tf32_ts(d, a_hi + kBK + 8 * q, db_hi, idesc, q == 0 ? (first ^ 1u) : 1u);   // small terms first
+            umma_tf32_ts(d, a_hi + 8 * q, db_lo, idesc, 1);
+            umma_tf32_ts(d, a_hi + 8 * q, db_hi, idesc, 1);
           } else {
-            umma_tf32(d, da_hi, db_hi, idesc, q == 0 ? (first ^ 1u) : 1u);
+            umma_tf32_ts(d, a_hi + 8 * q, db_hi, idesc, q == 0 ? (first ^ 1u) : 1u);
           }
         }
         umma_commit(bar_a_empty0 + 8 * stage);                  // gathered tile reusable once read
@@ -463,7 +498,8 @@ __global__ void __launch_bounds__(256) pack_weights_kernel(const float* __restri
   const int nchunk = Cin / kBK;
   const size_t tile = (size_t)Cout * kBK;                       // floats per tile
   const size_t base = (size_t)(k * nchunk + c) * 2 * tile;
-  const size_t pos = (sw128_chunk_offset(n, kk >> 2) >> 2) + (kk & 3);
+  const int col = a_col_of_channel(kk);                         // K position the MMA sees (matches the TMEM A layout)
+  const size_t pos = (sw128_chunk_offset(n, col >> 2) >> 2) + (col & 3);
   packed[base + pos] = hi;
   packed[base + tile + pos] = lo;
 }
