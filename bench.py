@@ -41,6 +41,18 @@ def peaks():
     return dict(hbm=6650.0, bf16=1590.0, bf16_sustained=1400.0, source="fallback")
 
 
+def ncu_traffic(kernel_key):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernel, from the committed
+    `ncu --set full` capture (profiles/ncu_traffic.json names the report it was read from)."""
+    path = os.path.join(ROOT, "profiles", "ncu_traffic.json")
+    if not os.path.exists(path):
+        return None
+    with open(path) as f:
+        table = json.load(f)
+    ent = table.get(kernel_key)
+    return None if ent is None else ent["dram_bytes_per_launch"]
+
+
 def config_dict(args, extra=None):
     cfg = {"workload": WORKLOAD, "batch_per_gpu": args.batch, "points_in_range": "~180k/scene",
            "voxel_size": [0.1, 0.1, 0.15], "max_voxels": 150000, "weights": "seeded random (synth.backbone_state(0))",
@@ -153,7 +165,7 @@ class ClockSampler:
 def run_gpu(args):
     import torch
     import torch.distributed as dist
-    from sparse2dense_b200 import ops, synth
+    from sparse2dense_b200 import ops, sharding, synth
     from sparse2dense_b200.hotpath import VoxelBackbonePath, concat_clouds
 
     if not torch.cuda.is_available():
@@ -169,7 +181,7 @@ def run_gpu(args):
     precision = {"fp32": ops.PRECISION_FP32, "tf32": ops.PRECISION_TF32, "tf32x3": ops.PRECISION_TF32X3}[args.precision]
     path = VoxelBackbonePath(state=synth.backbone_state(0), precision=precision, device=dev)
     # weak scaling: every rank owns its own batch of scenes (seeds differ per rank); no data-path collective
-    clouds = [synth.lidar_scene(1000 * 1 + rank * args.batch + i) for i in range(args.batch)]
+    clouds = [synth.lidar_scene(seed) for seed in sharding.scene_seeds(1, args.batch, rank)]
     pts_host, offs = concat_clouds(clouds, pin=True)
     pts_dev = pts_host.to(dev)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
@@ -223,10 +235,8 @@ def run_gpu(args):
     e2e_wall = time.perf_counter() - t0
     e2e_ms = sum(a.elapsed_time(b) for a, b in e2e_evs)
 
-    t = torch.tensor([dev_ms, e2e_ms], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    dev_ms, e2e_ms = t.tolist()
+    dev_ms, e2e_ms = sharding.max_over_ranks([dev_ms, e2e_ms], device=dev)     # slowest rank sets the time
+    (launches,) = sharding.sum_over_ranks([launches], device=dev)
 
     # ---- per-kernel accounting for the roofline object (rank 0) ------------------------------
     if rank == 0:
@@ -264,7 +274,8 @@ def run_gpu(args):
         else:
             tf32_peak = pk_peaks["bf16"] / 2.0
             roof = {"bound": "tensor", "achieved": tfl, "peak": tf32_peak, "unit": "TFLOP/s", "frac": tfl / tf32_peak,
-                    "traffic": None, "kernel": f"spconv_tc_kernel<{cin},{cout}> (K={K})",
+                    "traffic": ncu_traffic(f"spconv_tc_kernel<{cin},{cout},{3 if prec == ops.PRECISION_TF32X3 else 1}>"),
+                    "algorithmic_bytes": bytes_launch, "kernel": f"spconv_tc_kernel<{cin},{cout}> (K={K})",
                     "launches_per_step": dom_n / args.steps, "avg_launch_ms": avg_ms,
                     "share_of_step": dom_ms / dev_ms if world == 1 else None,
                     "peak_source": pk_peaks["source"] + " bf16 burst / 2 (TF32 runs at half the bf16 rate)",
