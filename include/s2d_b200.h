@@ -150,6 +150,73 @@ int s2d_spconv_fwd(const float* in, int n_in, const float* W, const int* tbl, in
                    int n_out, int Cin, int Cout, int K, const float* scale, const float* shift,
                    const float* residual, int relu, float* out, int precision, void* stream);
 
+/* ---------------------------------------------------------------------------------------
+ * General gather-GEMM convolution (the same kernels as s2d_spconv_fwd with every knob exposed).
+ * It also serves the DENSE 2-D convolutions of the S2D neck / RPN / CenterHead
+ * (det3d/models/necks/rpn.py:186-259,300-337; det3d/models/bbox_heads/center_head.py:209-244):
+ * a BEV map in NHWC is a "sparse" tensor with every site active, rows = (b,y,x), and a
+ * Conv2d / ConvTranspose2d is a gather-GEMM over a regular-grid neighbour table
+ * (s2d_grid2d_table).  Replaces torch.nn.Conv2d/ConvTranspose2d + BatchNorm2d + GELU/ReLU
+ * (+ residual add, + torch.cat through out_ld / channel-offset pointers).
+ *
+ *   out[r(o), :] = post( act( (sum_k in[tbl[k][o], :] @ W[k]) * scale + shift  [+ res] ) [+ res] )
+ *
+ *   in_ld / out_ld / res_ld : row strides in floats (multiples of 4); pointers may already be
+ *                             offset to a channel slice of a wider buffer
+ *   out_rows (nullable)     : r(o) = out_rows[o] (row remap, e.g. sub-pixel transposed conv)
+ *   act                     : S2D_ACT_NONE / RELU / GELU (exact erf form, torch.nn.GELU default)
+ *   res_after_act           : 0: residual added before the activation (ResNet), 1: after it
+ *   weights                 : raw [K,Cin,Cout] for S2D_PRECISION_FP32, packed image otherwise
+ * ------------------------------------------------------------------------------------- */
+#define S2D_ACT_NONE 0
+#define S2D_ACT_RELU 1
+#define S2D_ACT_GELU 2
+typedef struct s2d_conv_params {
+  const float* in;
+  const float* weights;
+  const int* tbl;
+  const float* scale;
+  const float* shift;
+  const float* residual;
+  float* out;
+  const int* out_rows;
+  int in_ld, out_ld, res_ld;
+  int tbl_stride, K;
+  int n_in, n_out, Cin, Cout;
+  int act, res_after_act, precision;
+} s2d_conv_params;
+int s2d_conv_fwd(const s2d_conv_params* params, void* stream);
+
+/* Regular-grid neighbour tables for dense 2-D convolutions over NHWC rows (row = (b*H + y)*W + x).
+ *   s2d_grid2d_table       : Conv2d(kh x kw, stride, pad): tbl i32 [kh*kw, B*Ho*Wo], -1 outside the map
+ *                            (zero padding; nn.ZeroPad2d(1)+Conv2d(3) of rpn.py:128-131 is pad = 1)
+ *   s2d_grid2d_tconv_table : ConvTranspose2d(stride 2) with (k,pad) = (4,1) or (2,0) as four sub-pixel
+ *                            convolutions (rpn.py:224-238,84-92): class (py,px) owns outputs (2y+py, 2x+px);
+ *                            tbl i32 [(kh/2)*(kw/2), B*H*W] over the INPUT grid, taps ky = ((py+pad)&1) + 2a,
+ *                            out_rows i32 [B*H*W] = output row of each input-grid site for s2d_conv_fwd. */
+int s2d_grid2d_table(int B, int H, int W, int kh, int kw, int stride, int pad, int* tbl, int tbl_stride,
+                     void* stream);
+int s2d_grid2d_tconv_table(int B, int H, int W, int kh, int kw, int pad, int py, int px, int* tbl,
+                           int tbl_stride, int* out_rows, void* stream);
+
+/* Layout changes at the module boundary: torch NCHW [B,C,HW] <-> rows [B*HW, ld] (channel fastest). */
+int s2d_nchw_to_nhwc(const float* in, int B, int C, int HW, float* out, int out_ld, void* stream);
+int s2d_nhwc_to_nchw(const float* in, int in_ld, int B, int C, int HW, float* out, void* stream);
+
+/* ConvNeXt pieces of the S2D module (rpn.py:204-222): depthwise k x k conv (weight [C,k,k], bias [C]
+ * nullable) and nn.LayerNorm([C,H,W], eps) over all C*H*W elements of a sample with affine
+ * parameters stored [C,H,W]; data in NHWC rows. */
+int s2d_dwconv2d(const float* in, const float* weight, const float* bias, int B, int H, int W, int C, int k,
+                 int pad, float* out, void* stream);
+size_t s2d_layernorm_workspace_bytes(int B);
+int s2d_layernorm_chw(const float* in, const float* gamma, const float* beta, int B, int C, int HW, float eps,
+                      float* out, void* workspace, size_t workspace_bytes, void* stream);
+
+/* SparseConvTensor.dense() + view(N, C*D, H, W) (scn.py:173-176) written directly as NHWC rows
+ * out f32 [B*H*W, out_ld], out[(b,y,x)][c*D + z] = feat[row, c]; zero-fills out itself. */
+int s2d_dense_bev_nhwc(const float* feat, const int* coors, int n_rows, int C, int batch, int D, int H, int W,
+                       float* out, int out_ld, void* stream);
+
 /* SparseConvTensor.dense() + view(N, C*D, H, W) (scn.py:173-176): bev f32 [batch, C*D, H, W],
  * bev[b, c*D + z, y, x] = feat[row, c].  The kernel zero-fills bev itself. */
 int s2d_dense_bev(const float* feat, const int* coors, int n_rows, int C, int batch, int D, int H, int W,

@@ -37,8 +37,27 @@ SIGNATURES = {
     "s2d_spconv_tf32_supported": (_i, [_i, _i]),
     "s2d_spconv_packed_bytes": (_sz, [_i, _i, _i]),
     "s2d_spconv_pack_weights": (_i, [_vp, _i, _i, _i, _vp, _vp]),
+    "s2d_conv_fwd": (_i, [_vp, _vp]),
+    "s2d_grid2d_table": (_i, [_i, _i, _i, _i, _i, _i, _i, _vp, _i, _vp]),
+    "s2d_grid2d_tconv_table": (_i, [_i, _i, _i, _i, _i, _i, _i, _i, _vp, _i, _vp, _vp]),
+    "s2d_nchw_to_nhwc": (_i, [_vp, _i, _i, _i, _vp, _i, _vp]),
+    "s2d_nhwc_to_nchw": (_i, [_vp, _i, _i, _i, _i, _vp, _vp]),
+    "s2d_dwconv2d": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _vp, _vp]),
+    "s2d_layernorm_workspace_bytes": (_sz, [_i]),
+    "s2d_layernorm_chw": (_i, [_vp, _vp, _vp, _i, _i, _i, ctypes.c_float, _vp, _vp, _sz, _vp]),
+    "s2d_dense_bev_nhwc": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _i, _vp, _i, _vp]),
     "s2d_dense_bev": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _i, _vp, _vp]),
 }
+
+
+
+class ConvParams(ctypes.Structure):
+    """struct s2d_conv_params (include/s2d_b200.h)."""
+    _fields_ = [("in_", _vp), ("weights", _vp), ("tbl", _vp), ("scale", _vp), ("shift", _vp), ("residual", _vp),
+                ("out", _vp), ("out_rows", _vp), ("in_ld", _i), ("out_ld", _i), ("res_ld", _i), ("tbl_stride", _i),
+                ("K", _i), ("n_in", _i), ("n_out", _i), ("Cin", _i), ("Cout", _i), ("act", _i),
+                ("res_after_act", _i), ("precision", _i)]
+
 
 _lib = None
 

@@ -1,0 +1,136 @@
+"""CenterPoint head, forward part (det3d/models/bbox_heads/center_head.py:65-110 ``SepHead``, :167-244
+``CenterHead.__init__/forward``).  Same constructor arguments and state-dict keys
+(``shared_conv.0.weight``, ``tasks.0.hm.3.bias`` …).  The shared 3x3 conv and the five 64->64 branch convs
+(fused into one 64->320 launch) run on the tcgen05 gather-GEMM; the tiny output convs (Cout <= 3) on the fp32
+kernel.  ``loss`` / ``predict`` are not built yet."""
+import copy
+import logging
+
+import torch
+from torch import nn
+
+from . import ops
+from .dense import ACT_NONE, ACT_RELU, DenseOps, conv_rows, conv_table, fold_bn, to_nchw, to_rows
+from .registry import HEADS
+
+
+class SepHead(nn.Module):
+    def __init__(self, in_channels, heads, head_conv=64, final_kernel=1, bn=False, init_bias=-2.19, **kwargs):
+        super(SepHead, self).__init__(**kwargs)
+        self.heads = heads
+        for head in self.heads:
+            classes, num_conv = self.heads[head]
+            mods = []
+            for _ in range(num_conv - 1):
+                mods.append(nn.Conv2d(in_channels, head_conv, kernel_size=final_kernel, stride=1,
+                                      padding=final_kernel // 2, bias=True))
+                if bn:
+                    mods.append(nn.BatchNorm2d(head_conv))
+                mods.append(nn.ReLU())
+            mods.append(nn.Conv2d(head_conv, classes, kernel_size=final_kernel, stride=1, padding=final_kernel // 2,
+                                  bias=True))
+            fc = nn.Sequential(*mods)
+            if "hm" in head:
+                fc[-1].bias.data.fill_(init_bias)
+            else:
+                for m in fc.modules():
+                    if isinstance(m, nn.Conv2d):
+                        nn.init.kaiming_normal_(m.weight, mode="fan_out", nonlinearity="relu")
+                        if m.bias is not None:
+                            nn.init.constant_(m.bias, 0)
+            self.__setattr__(head, fc)
+
+
+@HEADS.register_module
+class CenterHead(nn.Module):
+    def __init__(self, in_channels=[128, ], tasks=[], dataset="nuscenes", weight=0.25, code_weights=[],
+                 common_heads=dict(), logger=None, init_bias=-2.19, share_conv_channel=64, num_hm_conv=2,
+                 dcn_head=False):
+        super(CenterHead, self).__init__()
+        if dcn_head:
+            raise NotImplementedError("dcn_head=True is not used by the Waymo configs and is out of scope")
+        num_classes = [len(t["class_names"]) for t in tasks]
+        self.class_names = [t["class_names"] for t in tasks]
+        self.code_weights = code_weights
+        self.weight = weight
+        self.dataset = dataset
+        self.in_channels = in_channels
+        self.num_classes = num_classes
+        self.box_n_dim = 9 if "vel" in common_heads else 7
+        self.use_direction_classifier = False
+        self.logger = logger or logging.getLogger("CenterHead")
+        self.shared_conv = nn.Sequential(
+            nn.Conv2d(in_channels, share_conv_channel, kernel_size=3, padding=1, bias=True),
+            nn.BatchNorm2d(share_conv_channel), nn.ReLU(inplace=True))
+        self.tasks = nn.ModuleList()
+        for num_cls in num_classes:
+            heads = copy.deepcopy(common_heads)
+            heads.update(dict(hm=(num_cls, num_hm_conv)))
+            self.tasks.append(SepHead(share_conv_channel, heads, bn=True, init_bias=init_bias, final_kernel=3))
+        self._dense = DenseOps()
+
+    def set_precision(self, precision):
+        self._dense = DenseOps(precision)
+
+    def forward_rows(self, x, B, H, W):
+        """x rows [B*H*W, C] -> list (per task) of dict head -> rows [B*H*W, classes]."""
+        if self.training:
+            raise NotImplementedError("CenterHead is forward/eval only in this version (call .eval())")
+        D = self._dense
+        s, _, _ = D.conv("shared_conv.0", x, B, H, W, self.shared_conv[0], self.shared_conv[1], ACT_RELU)
+        tbl, _, _ = conv_table(x.device, B, H, W, 3, 1, 1)
+        n = B * H * W
+        ret = []
+        for ti, task in enumerate(self.tasks):
+            names = list(task.heads)
+            two_conv = all(task.heads[h][1] == 2 for h in names)
+            out = {}
+            if two_conv:
+                # the first conv of every branch reads the same 64-channel map: one 64 -> 64*len(heads) launch
+                firsts = [getattr(task, h)[0] for h in names]
+                bns = [getattr(task, h)[1] for h in names]
+
+                def build():
+                    w = torch.cat([c.weight.detach().float() for c in firsts], 0)               # [320,64,3,3]
+                    kio = w.permute(2, 3, 1, 0).reshape(9, w.shape[1], w.shape[0]).contiguous()
+                    packed = ops.pack_weights_tf32(kio) if (D.precision != ops.PRECISION_FP32 and
+                                                            ops.tf32_supported(kio.shape[1], kio.shape[2])) else None
+                    sc, sh = zip(*[fold_bn(b, c.bias, c.weight.shape[0], c.weight.device) for c, b in zip(firsts, bns)])
+                    return kio, packed, torch.cat(sc).contiguous(), torch.cat(sh).contiguous()
+                src = [c.weight for c in firsts] + [c.bias for c in firsts] + \
+                      [t for b in bns for t in (b.weight, b.bias, b.running_mean, b.running_var)]
+                kio, packed, sc, sh = D.cache.get(("heads", ti, D.precision), src, build)
+                mid = conv_rows(s, kio, tbl, n, sc, sh, ACT_RELU, precision=D.precision, packed=packed)
+                hc = firsts[0].weight.shape[0]
+                for hi, h in enumerate(names):
+                    last = getattr(task, h)[-1]
+                    kio_l = D.cache.get(("last", ti, h), [last.weight],
+                                        lambda last=last: last.weight.detach().float().permute(2, 3, 1, 0).reshape(
+                                            9, last.weight.shape[1], last.weight.shape[0]).contiguous())
+                    out[h] = conv_rows(mid[:, hi * hc:(hi + 1) * hc], kio_l, tbl, n, None,
+                                       last.bias.detach().float().contiguous(), ACT_NONE,
+                                       precision=ops.PRECISION_FP32)
+            else:
+                for h in names:
+                    y = s
+                    mods = list(getattr(task, h))
+                    j = 0
+                    while j < len(mods):
+                        m = mods[j]
+                        if isinstance(m, nn.Conv2d):
+                            bn = mods[j + 1] if j + 1 < len(mods) and isinstance(mods[j + 1], nn.BatchNorm2d) else None
+                            k = j + 1 + int(bn is not None)
+                            relu = k < len(mods) and isinstance(mods[k], nn.ReLU)
+                            y, _, _ = D.conv(f"tasks.{ti}.{h}.{j}", y, B, H, W, m, bn, ACT_RELU if relu else ACT_NONE)
+                            j = k + int(relu)
+                        else:
+                            j += 1
+                    out[h] = y
+            ret.append(out)
+        return ret
+
+    def forward(self, x, *kwargs):
+        """x NCHW [B,C,H,W] -> list of dicts of NCHW maps, like center_head.py:236-244."""
+        B, _, H, W = x.shape
+        rows = self.forward_rows(to_rows(x), B, H, W)
+        return [{h: to_nchw(v, B, H, W) for h, v in d.items()} for d in rows]

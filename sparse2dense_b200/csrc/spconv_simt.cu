@@ -142,89 +142,99 @@ __global__ void __launch_bounds__(256) spconv_simt_kernel(const float* __restric
   }
 }
 
-// Any (Cin, Cout): one thread per (row, cout).  Correctness path for shapes outside the backbone's.
-__global__ void __launch_bounds__(256) spconv_generic_kernel(const float* __restrict__ in, const float* __restrict__ W,
-                                                             const int* __restrict__ tbl, int tbl_stride, int n_out,
-                                                             int Cin, int Cout, int K, const float* __restrict__ scale,
-                                                             const float* __restrict__ shift,
-                                                             const float* __restrict__ residual, int relu,
-                                                             float* __restrict__ out) {
+// Any shape / stride / activation: one thread per (row, cout).  Correctness path for shapes outside the
+// tuned kernels (and the tiny CenterHead output convs, Cout <= 3).
+__global__ void __launch_bounds__(256) conv_generic_kernel(const __grid_constant__ s2d_conv_params P) {
   const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (idx >= (long long)n_out * Cout) return;
-  const int row = (int)(idx / Cout), co = (int)(idx - (long long)row * Cout);
+  if (idx >= (long long)P.n_out * P.Cout) return;
+  const int row = (int)(idx / P.Cout), co = (int)(idx - (long long)row * P.Cout);
   float acc = 0.f;
-  for (int k = 0; k < K; ++k) {
-    const int j = __ldg(tbl + (size_t)k * tbl_stride + row);
+  for (int k = 0; k < P.K; ++k) {
+    const int j = __ldg(P.tbl + (size_t)k * P.tbl_stride + row);
     if (j < 0) continue;
-    const float* x = in + (size_t)j * Cin;
-    const float* w = W + (size_t)k * Cin * Cout + co;
-    for (int ci = 0; ci < Cin; ++ci) acc = fmaf(__ldg(x + ci), __ldg(w + (size_t)ci * Cout), acc);
+    const float* x = P.in + (size_t)j * P.in_ld;
+    const float* w = P.weights + (size_t)k * P.Cin * P.Cout + co;
+    for (int ci = 0; ci < P.Cin; ++ci) acc = fmaf(__ldg(x + ci), __ldg(w + (size_t)ci * P.Cout), acc);
   }
-  float y = fmaf(acc, scale ? scale[co] : 1.f, shift ? shift[co] : 0.f);
-  if (residual) y += residual[idx];
-  if (relu) y = fmaxf(y, 0.f);
-  out[idx] = y;
+  float y = fmaf(acc, P.scale ? P.scale[co] : 1.f, P.shift ? P.shift[co] : 0.f);
+  const int orow = P.out_rows ? P.out_rows[row] : row;
+  const float r = P.residual ? P.residual[(size_t)orow * P.res_ld + co] : 0.f;
+  if (!P.res_after_act) y += r;
+  if (P.act == S2D_ACT_RELU) y = fmaxf(y, 0.f);
+  if (P.act == S2D_ACT_GELU) y = 0.5f * y * (1.f + erff(y * 0.70710678118654752440f));
+  if (P.res_after_act) y += r;
+  P.out[(size_t)orow * P.out_ld + co] = y;
 }
 
 template <int CIN, int COUT>
-static int launch_simt(const float* in, const float* W, const int* tbl, int tbl_stride, int n_out, int K,
-                       const float* scale, const float* shift, const float* residual, int relu, float* out,
-                       cudaStream_t st) {
+static int launch_simt(const s2d_conv_params& p, cudaStream_t st) {
   using Cfg = SimtCfg<CIN, COUT>;
-  spconv_simt_kernel<CIN, COUT><<<div_up(n_out, Cfg::TM), Cfg::THREADS, 0, st>>>(in, W, tbl, tbl_stride, n_out, K,
-                                                                                scale, shift, residual, relu, out);
+  spconv_simt_kernel<CIN, COUT><<<div_up(p.n_out, Cfg::TM), Cfg::THREADS, 0, st>>>(
+      p.in, p.weights, p.tbl, p.tbl_stride, p.n_out, p.K, p.scale, p.shift, p.residual, p.act == S2D_ACT_RELU, p.out);
   S2D_LAUNCH_CHECK();
   count_launches(1);
   return S2D_OK;
 }
 
-int spconv_fwd_fp32(const float* in, const float* W, const int* tbl, int tbl_stride, int n_out, int Cin, int Cout,
-                    int K, const float* scale, const float* shift, const float* residual, int relu, float* out,
-                    cudaStream_t st) {
+static int conv_fwd_fp32(const s2d_conv_params& p, cudaStream_t st) {
+  const bool plain = p.in_ld == p.Cin && p.out_ld == p.Cout && (!p.residual || p.res_ld == p.Cout) && !p.out_rows &&
+                     !p.res_after_act && (p.act == S2D_ACT_NONE || p.act == S2D_ACT_RELU);
+  if (plain) {
 #define S2D_SIMT_CASE(ci, co) \
-  if (Cin == ci && Cout == co) return launch_simt<ci, co>(in, W, tbl, tbl_stride, n_out, K, scale, shift, residual, relu, out, st)
-  S2D_SIMT_CASE(5, 16);
-  S2D_SIMT_CASE(16, 16);
-  S2D_SIMT_CASE(16, 32);
-  S2D_SIMT_CASE(32, 32);
-  S2D_SIMT_CASE(32, 64);
-  S2D_SIMT_CASE(64, 64);
-  S2D_SIMT_CASE(64, 128);
-  S2D_SIMT_CASE(128, 128);
+  if (p.Cin == ci && p.Cout == co) return launch_simt<ci, co>(p, st)
+    S2D_SIMT_CASE(5, 16);
+    S2D_SIMT_CASE(16, 16);
+    S2D_SIMT_CASE(16, 32);
+    S2D_SIMT_CASE(32, 32);
+    S2D_SIMT_CASE(32, 64);
+    S2D_SIMT_CASE(64, 64);
+    S2D_SIMT_CASE(64, 128);
+    S2D_SIMT_CASE(128, 128);
 #undef S2D_SIMT_CASE
-  spconv_generic_kernel<<<div_up((long long)n_out * Cout, 256), 256, 0, st>>>(in, W, tbl, tbl_stride, n_out, Cin, Cout,
-                                                                              K, scale, shift, residual, relu, out);
+  }
+  conv_generic_kernel<<<div_up((long long)p.n_out * p.Cout, 256), 256, 0, st>>>(p);
   S2D_LAUNCH_CHECK();
   count_launches(1);
   return S2D_OK;
 }
 
-int spconv_fwd_tf32(const float* in, int n_in, const float* W, const int* tbl, int tbl_stride, int n_out, int Cin,
-                    int Cout, int K, const float* scale, const float* shift, const float* residual, int relu,
-                    float* out, int passes, cudaStream_t st);  // spconv_tc.cu
+int conv_fwd_tf32(const s2d_conv_params& p, cudaStream_t st);  // spconv_tc.cu
 
 }  // namespace s2d
 
 using namespace s2d;
 
+extern "C" int s2d_conv_fwd(const s2d_conv_params* params, void* stream) {
+  S2D_REQUIRE(params, "s2d_conv_fwd: null params");
+  const s2d_conv_params& p = *params;
+  S2D_REQUIRE(p.n_in >= 0 && p.n_out >= 0 && p.Cin >= 1 && p.Cout >= 1, "s2d_conv_fwd: bad sizes");
+  S2D_REQUIRE(p.K >= 1 && p.K <= kMaxK, "s2d_conv_fwd: K=%d outside [1,%d]", p.K, kMaxK);
+  S2D_REQUIRE(p.tbl_stride >= p.n_out, "s2d_conv_fwd: tbl_stride %d < n_out %d", p.tbl_stride, p.n_out);
+  S2D_REQUIRE(p.in_ld >= p.Cin && p.out_ld >= p.Cout && (!p.residual || p.res_ld >= p.Cout),
+              "s2d_conv_fwd: row stride smaller than the channel count");
+  S2D_REQUIRE(p.act >= S2D_ACT_NONE && p.act <= S2D_ACT_GELU, "s2d_conv_fwd: unknown activation %d", p.act);
+  if (p.n_out == 0) return S2D_OK;
+  S2D_REQUIRE(p.in && p.weights && p.tbl && p.out, "s2d_conv_fwd: null argument");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  switch (p.precision) {
+    case S2D_PRECISION_FP32:
+      return conv_fwd_fp32(p, st);
+    case S2D_PRECISION_TF32:
+    case S2D_PRECISION_TF32X3:
+      return conv_fwd_tf32(p, st);
+    default:
+      set_error("s2d_conv_fwd: unknown precision %d", p.precision);
+      return S2D_ERR_INVALID;
+  }
+}
+
 extern "C" int s2d_spconv_fwd(const float* in, int n_in, const float* W, const int* tbl, int tbl_stride, int n_out,
                               int Cin, int Cout, int K, const float* scale, const float* shift,
                               const float* residual, int relu, float* out, int precision, void* stream) {
-  S2D_REQUIRE(n_in >= 0 && n_out >= 0 && Cin >= 1 && Cout >= 1, "s2d_spconv_fwd: bad sizes");
-  S2D_REQUIRE(K >= 1 && K <= kMaxK, "s2d_spconv_fwd: K=%d outside [1,%d]", K, kMaxK);
-  S2D_REQUIRE(tbl_stride >= n_out, "s2d_spconv_fwd: tbl_stride %d < n_out %d", tbl_stride, n_out);
-  if (n_out == 0) return S2D_OK;
-  S2D_REQUIRE(in && W && tbl && out, "s2d_spconv_fwd: null argument");
-  cudaStream_t st = static_cast<cudaStream_t>(stream);
-  switch (precision) {
-    case S2D_PRECISION_FP32:
-      return spconv_fwd_fp32(in, W, tbl, tbl_stride, n_out, Cin, Cout, K, scale, shift, residual, relu, out, st);
-    case S2D_PRECISION_TF32:
-    case S2D_PRECISION_TF32X3:
-      return spconv_fwd_tf32(in, n_in, W, tbl, tbl_stride, n_out, Cin, Cout, K, scale, shift, residual, relu, out,
-                             precision == S2D_PRECISION_TF32X3 ? 3 : 1, st);
-    default:
-      set_error("s2d_spconv_fwd: unknown precision %d", precision);
-      return S2D_ERR_INVALID;
-  }
+  s2d_conv_params p;
+  p.in = in; p.weights = W; p.tbl = tbl; p.scale = scale; p.shift = shift; p.residual = residual; p.out = out;
+  p.out_rows = nullptr; p.in_ld = Cin; p.out_ld = Cout; p.res_ld = Cout; p.tbl_stride = tbl_stride; p.K = K;
+  p.n_in = n_in; p.n_out = n_out; p.Cin = Cin; p.Cout = Cout; p.act = relu ? S2D_ACT_RELU : S2D_ACT_NONE;
+  p.res_after_act = 0; p.precision = precision;
+  return s2d_conv_fwd(&p, stream);
 }

@@ -176,9 +176,8 @@ constexpr int kNbrSlots = 4;
 // two LDG.128 per row.  The weight tiles are packed with the same K permutation (pack_weights_kernel).
 __host__ __device__ constexpr int a_col_of_channel(int ch) { return 8 * ((ch % 8) / 2) + 2 * (ch / 8) + (ch % 2); }
 
-template <int CIN, int COUT, int PASSES>
+template <int COUT, int PASSES>
 struct TcCfg {
-  static constexpr int NCHUNK = CIN / kBK;
   static constexpr int NPART = PASSES == 3 ? 2 : 1;
   static constexpr int T = COUT >= 128 ? 2 : 4;        // 128-row tiles per CTA sharing every weight tile
   static constexpr int ROWS = T * kBM;
@@ -192,7 +191,6 @@ struct TcCfg {
   static constexpr int TMEM_COLS = 512;
   static constexpr int NBR_BYTES = kNbrSlots * ROWS * 4;
   static constexpr int SMEM_BYTES = SB * B_STAGE + NBR_BYTES + 1024 + 1024;
-  static_assert(CIN % kBK == 0, "Cin must be a multiple of 32");
   static_assert(COUT % 16 == 0 && COUT >= 32 && COUT <= 128, "UMMA N constraint for M=128 / TMEM budget");
   static constexpr int BATCH = 1;                      // steps per producer hand-off (2 measured slower except 128->128 TF32)
   static_assert(SA >= 2 * BATCH && T % BATCH == 0, "gathered-tile ring must hold two producer batches");
@@ -202,14 +200,39 @@ struct TcCfg {
 // loaded once and feeds T MMA groups (one per tile accumulator).  The gathered A operand never touches
 // shared memory: the producer warps write it straight into TMEM (tcgen05.st) and the MMAs run in TS mode,
 // so shared-memory bandwidth only carries the small weight slices.
-template <int CIN, int COUT, int PASSES>
-__global__ void __launch_bounds__(kTcThreads, 1)
-spconv_tc_kernel(const float* __restrict__ in, const float* __restrict__ packed, const int* __restrict__ tbl,
-                 int tbl_stride, int n_out, int K, const float* __restrict__ scale, const float* __restrict__ shift,
-                 const float* __restrict__ residual, int relu, float* __restrict__ out) {
-  using Cfg = TcCfg<CIN, COUT, PASSES>;
-  constexpr int SA = Cfg::SA, SB = Cfg::SB, NCHUNK = Cfg::NCHUNK, T = Cfg::T;
+// Arguments of one launch.  Rows may be strided (in_ld / out_ld / res_ld, in floats) so that layers can read
+// from and write into channel slices of wider buffers (concatenations); blockIdx.y selects a block of COUT
+// output channels (weights are packed per block); out_rows optionally remaps output rows (sub-pixel
+// transposed convolutions).
+struct ConvArgs {
+  const float* in;
+  const float* packed;
+  const int* tbl;
+  const float* scale;
+  const float* shift;
+  const float* residual;
+  float* out;
+  const int* out_rows;
+  int in_ld, out_ld, res_ld, tbl_stride, n_out, K, nchunk, act, res_after_act;
+};
+
+__device__ __forceinline__ float apply_act(float y, int act) {
+  if (act == S2D_ACT_RELU) return fmaxf(y, 0.f);
+  if (act == S2D_ACT_GELU) return 0.5f * y * (1.f + erff(y * 0.70710678118654752440f));   // exact GELU (torch default)
+  return y;
+}
+
+template <int COUT, int PASSES>
+__global__ void __launch_bounds__(kTcThreads, 1) spconv_tc_kernel(const __grid_constant__ ConvArgs A) {
+  using Cfg = TcCfg<COUT, PASSES>;
+  constexpr int SA = Cfg::SA, SB = Cfg::SB, T = Cfg::T;
   constexpr int B_TILE = Cfg::B_TILE, B_STAGE = Cfg::B_STAGE, A_COLS = Cfg::A_COLS;
+  const int NCHUNK = A.nchunk, K = A.K, n_out = A.n_out;
+  const size_t blk_tiles = (size_t)blockIdx.y * K * NCHUNK;            // weight tiles before this channel block
+  const float* __restrict__ packed = A.packed + blk_tiles * 2 * (B_TILE / 4);
+  const int* __restrict__ tbl = A.tbl;
+  const int tbl_stride = A.tbl_stride;
+  const int cblk = blockIdx.y * COUT;                                  // first output channel of this block
 
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -259,7 +282,8 @@ spconv_tc_kernel(const float* __restrict__ in, const float* __restrict__ packed,
     const int row16 = 32 * (warp & 3) + 16 * (warp >> 2);
     const int rA = row16 + (lane >> 2);
     const int j4 = (lane & 3) * 2;               // float4 index of this lane's 8 channels inside the chunk
-    const float4* in4 = reinterpret_cast<const float4*>(in);
+    const float4* in4 = reinterpret_cast<const float4*>(A.in);
+    const int in_ld4 = A.in_ld >> 2;
     const uint32_t bar_a_full0 = smem_u32(bar_a_full), bar_a_empty0 = smem_u32(bar_a_empty);
     const uint32_t bar_n_full0 = smem_u32(bar_n_full), bar_n_empty0 = smem_u32(bar_n_empty);
     const uint32_t tmem_mine = tmem_a0 + ((uint32_t)row16 << 16);
@@ -280,11 +304,11 @@ spconv_tc_kernel(const float* __restrict__ in, const float* __restrict__ packed,
         const int ja = nbr[0], jb = nbr[8];
         v[b][0] = v[b][1] = v[b][2] = v[b][3] = make_float4(0.f, 0.f, 0.f, 0.f);
         if (ja >= 0) {
-          const float4* p = in4 + ((size_t)ja * (CIN / 4) + lc * (kBK / 4) + j4);
+          const float4* p = in4 + ((size_t)ja * in_ld4 + lc * (kBK / 4) + j4);
           v[b][0] = __ldg(p); v[b][1] = __ldg(p + 1);
         }
         if (jb >= 0) {
-          const float4* p = in4 + ((size_t)jb * (CIN / 4) + lc * (kBK / 4) + j4);
+          const float4* p = in4 + ((size_t)jb * in_ld4 + lc * (kBK / 4) + j4);
           v[b][2] = __ldg(p); v[b][3] = __ldg(p + 1);
         }
         if (++lt == T) {
@@ -361,16 +385,20 @@ spconv_tc_kernel(const float* __restrict__ in, const float* __restrict__ packed,
     mbar_wait(smem_u32(bar_accum), 0);
     tc_fence_after();
     const int g = warp & 3;
+    const float* __restrict__ scale = A.scale ? A.scale + cblk : nullptr;
+    const float* __restrict__ shift = A.shift ? A.shift + cblk : nullptr;
+    const int act = A.act, res_after = A.res_after_act;
 #pragma unroll 1
     for (int t = warp >> 2; t < T; t += 2) {
       const int row = tile0 + t * kBM + g * 32 + lane;
+      const int orow = (row < n_out && A.out_rows) ? __ldg(A.out_rows + row) : row;
 #pragma unroll 1
       for (int c0 = 0; c0 < COUT; c0 += 32) {
         uint32_t acc[32];
         tmem_ld32(tmem_base + ((uint32_t)(g * 32) << 16) + (uint32_t)(t * COUT + c0), acc);
         if (row < n_out) {
-          float* dst = out + (size_t)row * COUT + c0;
-          const float* res = residual ? residual + (size_t)row * COUT + c0 : nullptr;
+          float* dst = A.out + (size_t)orow * A.out_ld + cblk + c0;
+          const float* res = A.residual ? A.residual + (size_t)orow * A.res_ld + cblk + c0 : nullptr;
 #pragma unroll
           for (int q = 0; q < 8; ++q) {
             float4 y;
@@ -384,13 +412,11 @@ spconv_tc_kernel(const float* __restrict__ in, const float* __restrict__ packed,
               const float4 sh = __ldg(reinterpret_cast<const float4*>(shift + c0) + q);
               y.x += sh.x; y.y += sh.y; y.z += sh.z; y.w += sh.w;
             }
-            if (res) {
-              const float4 rr = __ldg(reinterpret_cast<const float4*>(res) + q);
-              y.x += rr.x; y.y += rr.y; y.z += rr.z; y.w += rr.w;
-            }
-            if (relu) {
-              y.x = fmaxf(y.x, 0.f); y.y = fmaxf(y.y, 0.f); y.z = fmaxf(y.z, 0.f); y.w = fmaxf(y.w, 0.f);
-            }
+            float4 rr = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (res) rr = __ldg(reinterpret_cast<const float4*>(res) + q);
+            if (!res_after) { y.x += rr.x; y.y += rr.y; y.z += rr.z; y.w += rr.w; }
+            y.x = apply_act(y.x, act); y.y = apply_act(y.y, act); y.z = apply_act(y.z, act); y.w = apply_act(y.w, act);
+            if (res_after) { y.x += rr.x; y.y += rr.y; y.z += rr.z; y.w += rr.w; }
             reinterpret_cast<float4*>(dst)[q] = y;
           }
         }
@@ -480,15 +506,16 @@ spconv_tc_kernel(const float* __restrict__ in, const float* __restrict__ packed,
 }
 
 // ---------------------------------------------------------------------------------------------
-// weight packing: W [K, Cin, Cout] -> per (k, chunk): [hi tile | lo tile], each Cout rows x 32 fp32 in the
-// exact shared-memory image the kernel's B descriptor expects (K-major, 128B swizzle), TF32-rounded.
+// weight packing: W [K, Cin, Cout] -> per (cout block, k, chunk): [hi tile | lo tile], each CB rows x 32 fp32 in
+// the exact shared-memory image the kernel's B descriptor expects (K-major, 128B swizzle, K permuted like
+// the TMEM A layout), TF32-rounded.
 // ---------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) pack_weights_kernel(const float* __restrict__ W, int K, int Cin, int Cout,
-                                                           float* __restrict__ packed) {
+                                                           int CB, float* __restrict__ packed) {
   const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   const long long total = (long long)K * Cin * Cout;
   if (idx >= total) return;
-  const int n = (int)(idx % Cout);
+  const int co = (int)(idx % Cout);
   const int ci = (int)((idx / Cout) % Cin);
   const int k = (int)(idx / ((long long)Cout * Cin));
   const float w = W[idx];
@@ -496,57 +523,53 @@ __global__ void __launch_bounds__(256) pack_weights_kernel(const float* __restri
   const float lo = tf32_rna(w - hi);
   const int c = ci / kBK, kk = ci % kBK;
   const int nchunk = Cin / kBK;
-  const size_t tile = (size_t)Cout * kBK;                       // floats per tile
-  const size_t base = (size_t)(k * nchunk + c) * 2 * tile;
+  const int blk = co / CB, n = co % CB;
+  const size_t tile = (size_t)CB * kBK;                         // floats per tile
+  const size_t base = ((size_t)(blk * K + k) * nchunk + c) * 2 * tile;
   const int col = a_col_of_channel(kk);                         // K position the MMA sees (matches the TMEM A layout)
   const size_t pos = (sw128_chunk_offset(n, col >> 2) >> 2) + (col & 3);
   packed[base + pos] = hi;
   packed[base + tile + pos] = lo;
 }
 
-template <int CIN, int COUT, int PASSES>
-static int launch_tc(const float* in, const float* packed, const int* tbl, int tbl_stride, int n_out, int K,
-                     const float* scale, const float* shift, const float* residual, int relu, float* out,
-                     cudaStream_t st) {
-  using Cfg = TcCfg<CIN, COUT, PASSES>;
+static int cout_block(int Cout) { return Cout % 128 == 0 ? 128 : (Cout % 64 == 0 ? 64 : (Cout % 32 == 0 ? 32 : 0)); }
+
+static bool tc_supported(int Cin, int Cout) { return Cin >= kBK && Cin % kBK == 0 && cout_block(Cout) != 0; }
+
+template <int COUT, int PASSES>
+static int launch_tc(const ConvArgs& a, int Cout, cudaStream_t st) {
+  using Cfg = TcCfg<COUT, PASSES>;
   static bool configured = false;
   if (!configured) {
-    S2D_CUDA(cudaFuncSetAttribute(spconv_tc_kernel<CIN, COUT, PASSES>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    S2D_CUDA(cudaFuncSetAttribute(spconv_tc_kernel<COUT, PASSES>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                   Cfg::SMEM_BYTES));
     configured = true;
   }
-  spconv_tc_kernel<CIN, COUT, PASSES><<<div_up(n_out, Cfg::ROWS), kTcThreads, Cfg::SMEM_BYTES, st>>>(
-      in, packed, tbl, tbl_stride, n_out, K, scale, shift, residual, relu, out);
+  const dim3 grid(div_up(a.n_out, Cfg::ROWS), Cout / COUT);
+  spconv_tc_kernel<COUT, PASSES><<<grid, kTcThreads, Cfg::SMEM_BYTES, st>>>(a);
   S2D_LAUNCH_CHECK();
   count_launches(1);
   return S2D_OK;
 }
 
-static bool tc_supported(int Cin, int Cout) {
-  return (Cin == 32 && (Cout == 32 || Cout == 64)) || (Cin == 64 && (Cout == 64 || Cout == 128)) ||
-         (Cin == 128 && Cout == 128);
-}
-
-int spconv_fwd_tf32(const float* in, int n_in, const float* packed, const int* tbl, int tbl_stride, int n_out,
-                    int Cin, int Cout, int K, const float* scale, const float* shift, const float* residual, int relu,
-                    float* out, int passes, cudaStream_t st) {
-  (void)n_in;
-  if (!tc_supported(Cin, Cout)) {
-    set_error("s2d_spconv_fwd: no tcgen05 kernel for Cin=%d Cout=%d (supported: 32->32/64, 64->64/128, 128->128)", Cin,
-              Cout);
+int conv_fwd_tf32(const s2d_conv_params& p, cudaStream_t st) {
+  if (!tc_supported(p.Cin, p.Cout)) {
+    set_error("s2d_conv_fwd: no tcgen05 kernel for Cin=%d Cout=%d (need Cin %% 32 == 0 and Cout %% 32 == 0)", p.Cin,
+              p.Cout);
     return S2D_ERR_UNSUPPORTED;
   }
-#define S2D_TC_CASE(ci, co)                                                                                           \
-  if (Cin == ci && Cout == co)                                                                                        \
-    return passes == 3 ? launch_tc<ci, co, 3>(in, packed, tbl, tbl_stride, n_out, K, scale, shift, residual, relu, out, st) \
-                       : launch_tc<ci, co, 1>(in, packed, tbl, tbl_stride, n_out, K, scale, shift, residual, relu, out, st)
-  S2D_TC_CASE(32, 32);
-  S2D_TC_CASE(32, 64);
-  S2D_TC_CASE(64, 64);
-  S2D_TC_CASE(64, 128);
-  S2D_TC_CASE(128, 128);
-#undef S2D_TC_CASE
-  return S2D_ERR_UNSUPPORTED;
+  S2D_REQUIRE(p.in_ld % 4 == 0 && p.out_ld % 4 == 0 && (!p.residual || p.res_ld % 4 == 0),
+              "s2d_conv_fwd: row strides must be multiples of 4 floats");
+  ConvArgs a;
+  a.in = p.in; a.packed = p.weights; a.tbl = p.tbl; a.scale = p.scale; a.shift = p.shift; a.residual = p.residual;
+  a.out = p.out; a.out_rows = p.out_rows; a.in_ld = p.in_ld; a.out_ld = p.out_ld; a.res_ld = p.res_ld;
+  a.tbl_stride = p.tbl_stride; a.n_out = p.n_out; a.K = p.K; a.nchunk = p.Cin / kBK; a.act = p.act;
+  a.res_after_act = p.res_after_act;
+  const int cb = cout_block(p.Cout);
+  const bool x3 = p.precision == S2D_PRECISION_TF32X3;
+  if (cb == 128) return x3 ? launch_tc<128, 3>(a, p.Cout, st) : launch_tc<128, 1>(a, p.Cout, st);
+  if (cb == 64) return x3 ? launch_tc<64, 3>(a, p.Cout, st) : launch_tc<64, 1>(a, p.Cout, st);
+  return x3 ? launch_tc<32, 3>(a, p.Cout, st) : launch_tc<32, 1>(a, p.Cout, st);
 }
 
 }  // namespace s2d
@@ -556,7 +579,7 @@ using namespace s2d;
 extern "C" int s2d_spconv_tf32_supported(int Cin, int Cout) { return tc_supported(Cin, Cout) ? 1 : 0; }
 
 extern "C" size_t s2d_spconv_packed_bytes(int K, int Cin, int Cout) {
-  if (K < 1 || Cin < 1 || Cout < 1 || Cin % kBK) return 0;
+  if (K < 1 || !tc_supported(Cin, Cout)) return 0;
   return (size_t)K * Cin * Cout * 2 * sizeof(float);
 }
 
@@ -564,7 +587,7 @@ extern "C" int s2d_spconv_pack_weights(const float* W, int K, int Cin, int Cout,
   S2D_REQUIRE(W && packed && K >= 1 && K <= kTcMaxK, "s2d_spconv_pack_weights: bad argument");
   S2D_REQUIRE(tc_supported(Cin, Cout), "s2d_spconv_pack_weights: unsupported shape Cin=%d Cout=%d", Cin, Cout);
   pack_weights_kernel<<<div_up((long long)K * Cin * Cout, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
-      W, K, Cin, Cout, packed);
+      W, K, Cin, Cout, cout_block(Cout), packed);
   S2D_LAUNCH_CHECK();
   count_launches(1);
   return S2D_OK;

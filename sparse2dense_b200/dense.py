@@ -1,0 +1,227 @@
+"""Dense BEV stage on NHWC rows.
+
+A BEV map ``[B,C,H,W]`` is stored as rows ``[B*H*W, C]`` (row = (b*H + y)*W + x, channel fastest).  In that
+layout ``Conv2d`` / ``ConvTranspose2d`` are the same gather-GEMM as the sparse convolution, driven by a
+regular-grid neighbour table, so they run on the tcgen05 kernel with BatchNorm / bias / GELU / ReLU /
+residual fused in the epilogue and ``torch.cat`` replaced by writing into channel slices of a wider buffer.
+
+Replaces the ``torch.nn`` (cuDNN) modules of det3d/models/necks/rpn.py:186-259,300-337 and
+det3d/models/bbox_heads/center_head.py:209-244.  Everything here is a thin wrapper over
+``s2d_conv_fwd`` / ``s2d_grid2d_*`` / ``s2d_dwconv2d`` / ``s2d_layernorm_chw`` (include/s2d_b200.h).
+"""
+import ctypes
+
+import torch
+
+from . import _lib, ops
+
+ACT_NONE, ACT_RELU, ACT_GELU = 0, 1, 2
+
+_TABLES = {}          # (device, kind, B, H, W, ...) -> tensors; regular-grid tables depend on the shape only
+
+
+def _stream():
+    return torch.cuda.current_stream().cuda_stream
+
+
+def conv_table(device, B, H, W, k, stride, pad):
+    """-> (tbl i32 [k*k, B*Ho*Wo], Ho, Wo) for Conv2d(k, stride, pad) on a [B,H,W] grid (cached)."""
+    key = (str(device), "conv", B, H, W, k, stride, pad)
+    hit = _TABLES.get(key)
+    if hit is None:
+        Ho, Wo = (H + 2 * pad - k) // stride + 1, (W + 2 * pad - k) // stride + 1
+        n = B * Ho * Wo
+        tbl = torch.empty((k * k, n), dtype=torch.int32, device=device)
+        _lib.check(_lib.load().s2d_grid2d_table(B, H, W, k, k, stride, pad, tbl.data_ptr(), n, _stream()),
+                   "s2d_grid2d_table")
+        hit = _TABLES[key] = (tbl, Ho, Wo)
+    return hit
+
+
+def tconv_tables(device, B, H, W, k, pad):
+    """Four sub-pixel classes of ConvTranspose2d(k, stride 2, pad): list of (py, px, tbl, out_rows) (cached)."""
+    key = (str(device), "tconv", B, H, W, k, pad)
+    hit = _TABLES.get(key)
+    if hit is None:
+        n = B * H * W
+        hit = []
+        for py in (0, 1):
+            for px in (0, 1):
+                tbl = torch.empty(((k // 2) ** 2, n), dtype=torch.int32, device=device)
+                rows = torch.empty((n,), dtype=torch.int32, device=device)
+                _lib.check(_lib.load().s2d_grid2d_tconv_table(B, H, W, k, k, pad, py, px, tbl.data_ptr(), n,
+                                                              rows.data_ptr(), _stream()), "s2d_grid2d_tconv_table")
+                hit.append((py, px, tbl, rows))
+        _TABLES[key] = hit
+    return hit
+
+
+def to_rows(x_nchw, out=None):
+    """torch NCHW -> rows [B*H*W, C] (or into `out`, a 2-D view with stride(1) == 1)."""
+    B, C, H, W = x_nchw.shape
+    x_nchw = x_nchw.contiguous().float()
+    if out is None:
+        out = torch.empty((B * H * W, C), dtype=torch.float32, device=x_nchw.device)
+    _lib.check(_lib.load().s2d_nchw_to_nhwc(x_nchw.data_ptr(), B, C, H * W, out.data_ptr(), out.stride(0), _stream()),
+               "s2d_nchw_to_nhwc")
+    return out
+
+
+def to_nchw(rows, B, H, W):
+    C = rows.shape[1]
+    out = torch.empty((B, C, H, W), dtype=torch.float32, device=rows.device)
+    _lib.check(_lib.load().s2d_nhwc_to_nchw(rows.data_ptr(), rows.stride(0), B, C, H * W, out.data_ptr(), _stream()),
+               "s2d_nhwc_to_nchw")
+    return out
+
+
+def fold_bn(bn, bias, cout, device):
+    """eval-mode BatchNorm2d (+ conv bias) -> (scale, shift); bn None -> (None, bias)."""
+    if bn is None:
+        return None, (None if bias is None else bias.detach().float().contiguous())
+    inv = torch.rsqrt(bn.running_var.float() + bn.eps)
+    gamma = bn.weight.float() if bn.weight is not None else torch.ones(cout, device=device)
+    beta = bn.bias.float() if bn.bias is not None else torch.zeros(cout, device=device)
+    scale = gamma * inv
+    shift = beta - bn.running_mean.float() * scale
+    if bias is not None:
+        shift = shift + bias.float() * scale
+    return scale.detach().contiguous(), shift.detach().contiguous()
+
+
+def conv_rows(x, weight_kio, tbl, n_out, scale=None, shift=None, act=ACT_NONE, residual=None, res_after_act=False,
+              out=None, out_rows=None, precision=ops.PRECISION_TF32X3, packed=None):
+    """One gather-GEMM launch.  x / out / residual: 2-D views with stride(1) == 1; weight_kio: [K,Cin,Cout]."""
+    K, cin, cout = weight_kio.shape
+    assert x.stride(1) == 1 and x.shape[1] == cin and tbl.shape[0] == K
+    if out is None:
+        out = torch.empty((n_out if out_rows is None else int(out_rows.numel()), cout), dtype=torch.float32,
+                          device=x.device)
+    assert out.stride(1) == 1 and out.shape[1] == cout
+    use_tc = precision != ops.PRECISION_FP32 and ops.tf32_supported(cin, cout)
+    w = weight_kio
+    if use_tc:
+        w = packed if packed is not None else ops.pack_weights_tf32(weight_kio)
+    p = _lib.ConvParams()
+    p.in_, p.weights, p.tbl = x.data_ptr(), w.data_ptr(), tbl.data_ptr()
+    p.scale = None if scale is None else scale.data_ptr()
+    p.shift = None if shift is None else shift.data_ptr()
+    p.residual = None if residual is None else residual.data_ptr()
+    p.out = out.data_ptr()
+    p.out_rows = None if out_rows is None else out_rows.data_ptr()
+    p.in_ld, p.out_ld = x.stride(0), out.stride(0)
+    p.res_ld = 0 if residual is None else residual.stride(0)
+    p.tbl_stride, p.K = tbl.stride(0), K
+    p.n_in, p.n_out, p.Cin, p.Cout = x.shape[0], n_out, cin, cout
+    p.act, p.res_after_act = act, int(bool(res_after_act))
+    p.precision = precision if use_tc else ops.PRECISION_FP32
+    ev = None
+    if ops.KERNEL_EVENTS is not None:
+        ev = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
+        ev[0].record()
+    _lib.check(_lib.load().s2d_conv_fwd(ctypes.byref(p), _stream()), "s2d_conv_fwd")
+    if ev is not None:
+        ev[1].record()
+        ops.KERNEL_EVENTS.append(((cin, cout, K, residual is not None, x.shape[0], n_out, int(p.precision)), ev[0], ev[1]))
+    return out
+
+
+class ParamCache:
+    """Per-module cache of derived tensors (k-major / packed weights, folded BN), rebuilt when a source
+    parameter changes (data_ptr / version / device)."""
+
+    def __init__(self):
+        self._store = {}
+
+    def get(self, name, sources, build):
+        key = tuple(None if t is None else (t.data_ptr(), t._version, str(t.device)) for t in sources)
+        hit = self._store.get(name)
+        if hit is None or hit[0] != key:
+            hit = (key, build())
+            self._store[name] = hit
+        return hit[1]
+
+
+def _bn_sources(bn):
+    return [] if bn is None else [bn.weight, bn.bias, bn.running_mean, bn.running_var]
+
+
+class DenseOps:
+    """Executes torch ``Conv2d`` / ``ConvTranspose2d`` (+BN +activation) modules on NHWC rows."""
+
+    def __init__(self, precision=ops.PRECISION_TF32X3):
+        self.precision = precision
+        self.cache = ParamCache()
+
+    # -- parameter preparation -------------------------------------------------------------
+    def _conv_weights(self, name, conv, transposed_class=None):
+        def build():
+            w = conv.weight.detach().float()
+            if transposed_class is None:                      # Conv2d [Cout,Cin,kh,kw] -> [K,Cin,Cout]
+                kio = w.permute(2, 3, 1, 0).reshape(-1, w.shape[1], w.shape[0]).contiguous()
+            else:                                             # ConvTranspose2d [Cin,Cout,kh,kw], taps of one class
+                py, px, pad = transposed_class
+                kh, kw = w.shape[2], w.shape[3]
+                ky0, kx0 = (py + pad) & 1, (px + pad) & 1
+                taps = [w[:, :, ky0 + 2 * a, kx0 + 2 * c] for a in range(kh // 2) for c in range(kw // 2)]
+                kio = torch.stack(taps, 0).contiguous()       # [K, Cin, Cout]
+            packed = None
+            if self.precision != ops.PRECISION_FP32 and ops.tf32_supported(kio.shape[1], kio.shape[2]):
+                packed = ops.pack_weights_tf32(kio)
+            return kio, packed
+        return self.cache.get(("w", name, transposed_class, self.precision), [conv.weight], build)
+
+    def _affine(self, name, conv, bn):
+        return self.cache.get(("bn", name), [conv.bias] + _bn_sources(bn),
+                              lambda: fold_bn(bn, conv.bias, conv.weight.shape[0] if not isinstance(
+                                  conv, torch.nn.ConvTranspose2d) else conv.weight.shape[1], conv.weight.device))
+
+    # -- layers ----------------------------------------------------------------------------
+    def conv(self, name, x, B, H, W, conv, bn=None, act=ACT_NONE, residual=None, res_after_act=False, out=None,
+             pad=None):
+        """Conv2d on rows; returns (out_rows_tensor, Ho, Wo)."""
+        k, s = conv.kernel_size[0], conv.stride[0]
+        pad = conv.padding[0] if pad is None else pad
+        tbl, Ho, Wo = conv_table(x.device, B, H, W, k, s, pad)
+        kio, packed = self._conv_weights(name, conv)
+        scale, shift = self._affine(name, conv, bn)
+        y = conv_rows(x, kio, tbl, B * Ho * Wo, scale, shift, act, residual, res_after_act, out, None,
+                      self.precision, packed)
+        return y, Ho, Wo
+
+    def tconv(self, name, x, B, H, W, conv, bn=None, act=ACT_NONE, out=None):
+        """ConvTranspose2d(stride 2) on rows as four sub-pixel convolutions; returns (out, 2H, 2W)."""
+        k, pad = conv.kernel_size[0], conv.padding[0]
+        assert conv.stride[0] == 2 and (k, pad) in ((4, 1), (2, 0))
+        cout = conv.weight.shape[1]
+        if out is None:
+            out = torch.empty((B * 4 * H * W, cout), dtype=torch.float32, device=x.device)
+        scale, shift = self._affine(name, conv, bn)
+        for py, px, tbl, rows in tconv_tables(x.device, B, H, W, k, pad):
+            kio, packed = self._conv_weights(name, conv, (py, px, pad))
+            conv_rows(x, kio, tbl, B * H * W, scale, shift, act, None, False, out, rows, self.precision, packed)
+        return out, 2 * H, 2 * W
+
+    def dwconv(self, x, B, H, W, conv):
+        C, k = conv.weight.shape[0], conv.kernel_size[0]
+        assert conv.groups == C and x.is_contiguous()
+        out = torch.empty_like(x)
+        w = conv.weight.detach().float().contiguous()
+        b = None if conv.bias is None else conv.bias.detach().float().contiguous()
+        _lib.check(_lib.load().s2d_dwconv2d(x.data_ptr(), w.data_ptr(), None if b is None else b.data_ptr(), B, H, W, C,
+                                            k, conv.padding[0], out.data_ptr(), _stream()), "s2d_dwconv2d")
+        return out
+
+    def layernorm(self, x, B, H, W, ln):
+        C = x.shape[1]
+        assert tuple(ln.normalized_shape) == (C, H, W) and x.is_contiguous()
+        out = torch.empty_like(x)
+        lib = _lib.load()
+        nbytes = lib.s2d_layernorm_workspace_bytes(B)
+        ws = torch.empty((nbytes,), dtype=torch.uint8, device=x.device)
+        g = None if ln.weight is None else ln.weight.detach().float().contiguous()
+        b = None if ln.bias is None else ln.bias.detach().float().contiguous()
+        _lib.check(lib.s2d_layernorm_chw(x.data_ptr(), None if g is None else g.data_ptr(),
+                                         None if b is None else b.data_ptr(), B, C, H * W, float(ln.eps),
+                                         out.data_ptr(), ws.data_ptr(), nbytes, _stream()), "s2d_layernorm_chw")
+        return out

@@ -312,3 +312,15 @@ def dense_bev(feats, coors, batch, spatial_shape):
     _lib.check(_lib.load().s2d_dense_bev(_ptr(feats.contiguous()), _ptr(coors.contiguous()), n, c, batch, d, h, w,
                                          _ptr(bev), _stream()), "s2d_dense_bev")
     return bev
+
+
+def dense_bev_rows(feats, coors, batch, spatial_shape, out=None):
+    """dense() + view(N, C*D, H, W) written directly as NHWC rows [B*H*W, C*D] (channel = c*D + z)."""
+    _need_cuda(feats, coors)
+    d, h, w = _triple(spatial_shape)
+    n, c = feats.shape
+    if out is None:
+        out = torch.empty((batch * h * w, c * d), dtype=torch.float32, device=feats.device)
+    _lib.check(_lib.load().s2d_dense_bev_nhwc(_ptr(feats.contiguous()), _ptr(coors.contiguous()), n, c, batch, d, h, w,
+                                              _ptr(out), out.stride(0), _stream()), "s2d_dense_bev_nhwc")
+    return out

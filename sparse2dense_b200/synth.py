@@ -118,3 +118,31 @@ def backbone_state(seed=0, num_input_features=5):
         block(name + ".3", cout); block(name + ".4", cout)
     conv("extra_conv.0", (3, 1, 1), 128, 128, False); bn("extra_conv.1", 128)
     return state
+
+
+def random_module_state(module, seed):
+    """Seeded, torch-RNG-independent random state dict for any nn.Module of this package (reference key names):
+    conv / linear weights ~ N(0, 2/fan_in), biases small, BatchNorm / LayerNorm affine around 1 with non-trivial
+    running statistics.  Used for the dense neck / head where no checkpoint is available."""
+    rng = np.random.default_rng(seed)
+    out = {}
+    for key, t in sorted(module.state_dict().items()):
+        shape = tuple(t.shape)
+        name = key.rsplit(".", 1)[-1]
+        if name == "num_batches_tracked":
+            continue
+        if name == "running_mean":
+            v = rng.normal(0, 0.1, shape)
+        elif name == "running_var":
+            v = rng.uniform(0.5, 1.5, shape)
+        elif name == "weight" and len(shape) >= 2 and not (len(shape) == 3 and "convnext" in key and ".1." in key):
+            fan_in = int(np.prod(shape[1:])) if len(shape) > 2 else shape[1]
+            if len(shape) == 4 and "decoder" in key and shape[2] == 4:
+                fan_in = shape[0] * 4                       # ConvTranspose2d [Cin,Cout,4,4]: 4 taps reach an output
+            v = rng.normal(0, np.sqrt(2.0 / max(fan_in, 1)), shape)
+        elif name == "weight":
+            v = rng.uniform(0.5, 1.5, shape)                # norm scale
+        else:
+            v = rng.normal(0, 0.05, shape)                  # biases
+        out[key] = v.astype(np.float32)
+    return out

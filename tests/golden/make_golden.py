@@ -133,6 +133,96 @@ def make_spconv_goldens():
         print(f"spconv_{name}: N_in={n} N_out={len(oc)} out_shape={oshape}")
 
 
+def reference_dense_modules():
+    """Import the reference's own S2D_RPN / CenterHead through the namespace shim of SURVEY.md App. G."""
+    import logging
+    import types
+    R = REF
+
+    def pkg(name, path):
+        m = types.ModuleType(name); m.__path__ = [path]; sys.modules[name] = m; return m
+
+    def stub(name, **kw):
+        m = types.ModuleType(name); m.__dict__.update(kw); sys.modules[name] = m; return m
+    for n, p_ in [("det3d", "det3d"), ("det3d.models", "det3d/models"), ("det3d.torchie", "det3d/torchie"),
+                  ("det3d.models.necks", "det3d/models/necks"), ("det3d.models.bbox_heads", "det3d/models/bbox_heads"),
+                  ("det3d.models.readers", "det3d/models/readers"), ("det3d.models.losses", "det3d/models/losses"),
+                  ("det3d.torchie.cnn", "det3d/torchie/cnn"), ("det3d.utils", "det3d/utils")]:
+        pkg(n, f"{R}/{p_}")
+    stub("det3d.torchie.trainer", load_checkpoint=lambda *a, **k: None)
+    import det3d.torchie.cnn.weight_init as wi
+    sys.modules["det3d.torchie.cnn"].__dict__.update({k: getattr(wi, k) for k in dir(wi) if k.endswith("_init")})
+    sys.modules["det3d.torchie"].is_str = lambda x: isinstance(x, str)
+    import det3d.utils.registry as reg
+    sys.modules["det3d.utils"].Registry, sys.modules["det3d.utils"].build_from_cfg = reg.Registry, reg.build_from_cfg
+    stub("det3d.utils.dist")
+    sys.modules["det3d.utils.dist"].dist_common = stub("det3d.utils.dist.dist_common", get_world_size=lambda: 1)
+    stub("det3d.core", box_torch_ops=types.SimpleNamespace())
+    stub("det3d.core.utils")
+    stub("det3d.core.utils.circle_nms_jit", circle_nms=None)
+    stub("det3d.core.utils.center_utils", _transpose_and_gather_feat=None)
+    import det3d.models.registry  # noqa: F401
+    import det3d.models.utils  # noqa: F401
+    import det3d.models.necks.rpn as rpn
+    import det3d.models.bbox_heads.center_head as ch
+    return rpn, ch, logging.getLogger("ref")
+
+
+NECK_CFG = dict(layer_nums=[5, 5], ds_layer_strides=[1, 2], ds_num_filters=[128, 256], us_layer_strides=[1, 2],
+                us_num_filters=[256, 256], num_input_features=256)
+HEAD_CFG = dict(in_channels=512, tasks=[dict(num_class=3, class_names=["VEHICLE", "PEDESTRIAN", "CYCLIST"])],
+                dataset="waymo", weight=2, code_weights=[1.0] * 8,
+                common_heads={"reg": (2, 2), "height": (1, 2), "dim": (3, 2), "rot": (2, 2)})
+
+
+def bev_input(seed, batch=1, occupancy=0.25):
+    """Sparse-looking BEV map like the backbone's dense() output: ~25 % occupied cells, ReLU-positive values."""
+    rng = np.random.default_rng(seed)
+    occ = rng.uniform(size=(batch, 1, 188, 188)) < occupancy
+    x = np.abs(rng.normal(0, 1.0, size=(batch, 256, 188, 188))) * occ
+    return x.astype(np.float32)
+
+
+def make_neck_head_goldens():
+    import logging
+    import torch
+    from oracle import neck_head as NH
+    from sparse2dense_b200 import registry
+    rpn, ch, logger = reference_dense_modules()
+    torch.manual_seed(0)
+    ours_neck = registry.build_neck(dict(type="S2D_RPN", logger=logging.getLogger("x"), **NECK_CFG))
+    ours_head = registry.build_head(dict(type="CenterHead", **HEAD_CFG))
+    ns, hs = synth.random_module_state(ours_neck, 11), synth.random_module_state(ours_head, 12)
+    ref_neck = rpn.S2D_RPN(logger=logger, **NECK_CFG).eval()
+    ref_head = ch.CenterHead(logger=logger, **HEAD_CFG).eval()
+    for ref, st in ((ref_neck, ns), (ref_head, hs)):
+        res = ref.load_state_dict({k: torch.from_numpy(v) for k, v in st.items()}, strict=False)
+        assert not res.unexpected_keys, res.unexpected_keys
+        assert all(k.endswith("num_batches_tracked") for k in res.missing_keys), res.missing_keys
+    x = torch.from_numpy(bev_input(21))
+    with torch.no_grad():
+        rx, _, _, _, _, rfa, rfb = ref_neck(x)
+        rh = ref_head(rx)[0]
+        ox, ofa, ofb = NH.s2d_rpn_forward(ns, x)
+        oh = NH.center_head_forward(hs, ox)[0]
+    rng = np.random.default_rng(5)
+    out = {}
+    for name, r, o in [("x", rx, ox), ("F_S_a", rfa, ofa), ("F_S_b", rfb, ofb)] + [(h, rh[h], oh[h]) for h in rh]:
+        r, o = r.numpy(), o.numpy()
+        err = np.abs(r - o).max() / np.abs(r).max()
+        print(f"neck/head {name}: shape {r.shape} max|ref| {np.abs(r).max():.3f} oracle-vs-reference rel err {err:.2e}")
+        assert err < 1e-5, name
+        idx = rng.choice(r.size, size=min(4000, r.size), replace=False)
+        out[name + "_idx"] = idx.astype(np.int64)
+        out[name + "_val"] = r.reshape(-1)[idx]
+        out[name + "_absmax"] = np.float32(np.abs(r).max())
+    np.savez_compressed(os.path.join(HERE, "neck_head_s2d.npz"), neck_seed=11, head_seed=12, input_seed=21, **out)
+
+
 if __name__ == "__main__":
+    if len(sys.argv) > 1 and sys.argv[1] == "dense":
+        make_neck_head_goldens()
+        sys.exit(0)
     make_voxel_goldens()
     make_spconv_goldens()
+    make_neck_head_goldens()
