@@ -119,7 +119,9 @@ class SpMiddleResNetFHD(nn.Module):
                 ok = precision != ops.PRECISION_FP32 and ops.tf32_supported(m.in_channels, m.out_channels)
                 m.precision = precision if ok else ops.PRECISION_FP32
 
-    def forward(self, voxel_features, coors, batch_size, input_shape, index=None):
+    def forward(self, voxel_features, coors, batch_size, input_shape, index=None, as_rows=False):
+        """scn.py:156-185.  ``as_rows=True`` returns the BEV map as NHWC rows ``[B*H*W, C*D]`` (what the dense
+        stage of this package consumes) instead of the reference's NCHW ``[B, C*D, H, W]``."""
         sparse_shape = np.array(input_shape[::-1]) + [1, 0, 0]          # scn.py:159 (depth 41, not 40)
         coors = coors.int().contiguous()
         ret = spconv.SparseConvTensor(voxel_features, coors, sparse_shape, batch_size)
@@ -134,9 +136,12 @@ class SpMiddleResNetFHD(nn.Module):
         x_conv4 = self.conv4(x_conv3)
         ret = self.extra_conv(x_conv4)
 
-        ret = ret.dense()
-        N, C, D, H, W = ret.shape
-        ret = ret.view(N, C * D, H, W)
+        if as_rows:
+            ret = ops.dense_bev_rows(ret.features, ret.indices, batch_size, ret.spatial_shape)
+        else:
+            ret = ret.dense()
+            N, C, D, H, W = ret.shape
+            ret = ret.view(N, C * D, H, W)
 
         multi_scale_voxel_features = {
             "conv1": x_conv1,

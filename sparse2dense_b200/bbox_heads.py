@@ -102,14 +102,30 @@ class CenterHead(nn.Module):
                 kio, packed, sc, sh = D.cache.get(("heads", ti, D.precision), src, build)
                 mid = conv_rows(s, kio, tbl, n, sc, sh, ACT_RELU, precision=D.precision, packed=packed)
                 hc = firsts[0].weight.shape[0]
-                for hi, h in enumerate(names):
-                    last = getattr(task, h)[-1]
-                    kio_l = D.cache.get(("last", ti, h), [last.weight],
-                                        lambda last=last: last.weight.detach().float().permute(2, 3, 1, 0).reshape(
-                                            9, last.weight.shape[1], last.weight.shape[0]).contiguous())
-                    out[h] = conv_rows(mid[:, hi * hc:(hi + 1) * hc], kio_l, tbl, n, None,
-                                       last.bias.detach().float().contiguous(), ACT_NONE,
-                                       precision=ops.PRECISION_FP32)
+                # the five output convs (Cout 2/1/3/2/3) as ONE block-diagonal 320 -> 32 launch on the tensor cores
+                lasts = [getattr(task, h)[-1] for h in names]
+                classes = [c.weight.shape[0] for c in lasts]
+                cpad = -(-sum(classes) // 32) * 32
+
+                def build_last():
+                    kio = torch.zeros((9, hc * len(names), cpad), dtype=torch.float32, device=s.device)
+                    bias = torch.zeros((cpad,), dtype=torch.float32, device=s.device)
+                    off = 0
+                    for hi, c in enumerate(lasts):
+                        w = c.weight.detach().float().permute(2, 3, 1, 0).reshape(9, hc, c.weight.shape[0])
+                        kio[:, hi * hc:(hi + 1) * hc, off:off + c.weight.shape[0]] = w
+                        bias[off:off + c.weight.shape[0]] = c.bias.detach().float()
+                        off += c.weight.shape[0]
+                    packed = ops.pack_weights_tf32(kio) if (D.precision != ops.PRECISION_FP32 and
+                                                            ops.tf32_supported(kio.shape[1], kio.shape[2])) else None
+                    return kio, packed, bias
+                kio_l, packed_l, bias_l = D.cache.get(("lasts", ti, D.precision),
+                                                      [c.weight for c in lasts] + [c.bias for c in lasts], build_last)
+                y = conv_rows(mid, kio_l, tbl, n, None, bias_l, ACT_NONE, precision=D.precision, packed=packed_l)
+                off = 0
+                for h, c in zip(names, classes):
+                    out[h] = y[:, off:off + c]
+                    off += c
             else:
                 for h in names:
                     y = s

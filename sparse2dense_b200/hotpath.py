@@ -56,3 +56,41 @@ def concat_clouds(clouds, pin=True):
     if pin and torch.cuda.is_available():
         cat = cat.pin_memory()
     return cat, offs
+
+
+class FullForwardPath(VoxelBackbonePath):
+    """points -> voxelize -> reader -> SpMiddleResNetFHD -> S2D_RPN -> CenterHead maps (BASELINE configs[2] up to
+    the head outputs; decode + NMS + second stage are not built yet).  The dense stage runs on NHWC rows end to
+    end: the backbone densifies straight into rows, the head outputs are transposed to NCHW at the very end."""
+
+    NECK_CFG = dict(type="S2D_RPN", layer_nums=[5, 5], ds_layer_strides=[1, 2], ds_num_filters=[128, 256],
+                    us_layer_strides=[1, 2], us_num_filters=[256, 256], num_input_features=256)
+    HEAD_CFG = dict(type="CenterHead", in_channels=512,
+                    tasks=[dict(num_class=3, class_names=["VEHICLE", "PEDESTRIAN", "CYCLIST"])], dataset="waymo",
+                    weight=2, code_weights=[1.0] * 8,
+                    common_heads={"reg": (2, 2), "height": (1, 2), "dim": (3, 2), "rot": (2, 2)})
+
+    def __init__(self, state=None, neck_state=None, head_state=None, precision=ops.PRECISION_TF32X3, device="cuda"):
+        super().__init__(state=state, precision=precision, device=device)
+        import logging
+        self.neck = registry.build_neck(dict(logger=logging.getLogger("RPN"), **self.NECK_CFG))
+        self.head = registry.build_head(dict(**self.HEAD_CFG))
+        if neck_state is not None:
+            self.neck.load_state_dict({k: torch.as_tensor(v) for k, v in neck_state.items()}, strict=False)
+        if head_state is not None:
+            self.head.load_state_dict({k: torch.as_tensor(v) for k, v in head_state.items()}, strict=False)
+        self.neck.to(self.device).eval().set_precision(precision)
+        self.head.to(self.device).eval().set_precision(precision)
+
+    @torch.no_grad()
+    def forward_points(self, points, scene_offsets):
+        from .dense import to_nchw
+        batch = len(scene_offsets) - 1
+        vb = self.generator.generate_batch(points, scene_offsets, want_voxels=False,
+                                           mean_channels=self.num_input_features)
+        n = vb.n
+        rows, _ = self.backbone(vb.mean_buffer[:n], vb.coors_buffer[:n], batch, self.grid, as_rows=True)
+        H = W = 188
+        ups, (Hu, Wu), F_S_a, F_S_b = self.neck.forward_rows(rows, batch, H, W)
+        preds = self.head.forward_rows(ups, batch, Hu, Wu)
+        return [{h: to_nchw(v, batch, Hu, Wu) for h, v in d.items()} for d in preds]
