@@ -111,7 +111,7 @@ def run_reference(args):
                                    "backbone (spconv-CPU is not installable here)"},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
-    print(json.dumps(line), flush=True)
+    emit_line(line)
 
 
 # ---------------------------------------------------------------------------------------------
@@ -309,7 +309,7 @@ def run_gpu(args):
             "gpu_launches": int(launches), "wall_ms_per_step": 1e3 * wall / args.steps,
             "roofline": roof, "cpu_baseline": cpu, "kernel_ms_per_step": per_group,
         }
-        print(json.dumps(line), flush=True)
+        emit_line(line)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
@@ -349,7 +349,29 @@ def count_pairs_for(path, pts_dev, offs, shape_key):
     return int(pairs.item())
 
 
+_REAL_STDOUT = None
+
+
+def quiet_stdout():
+    """Send everything libraries print on fd 1 (e.g. NCCL's version banner) to stderr; the JSON line is the only
+    thing written to the real stdout (emit_line)."""
+    global _REAL_STDOUT
+    if _REAL_STDOUT is None:
+        sys.stdout.flush()
+        _REAL_STDOUT = os.dup(1)
+        os.dup2(2, 1)
+
+
+def emit_line(obj):
+    data = (json.dumps(obj) + "\n").encode()
+    if _REAL_STDOUT is None:
+        sys.stdout.write(data.decode()); sys.stdout.flush()
+    else:
+        os.write(_REAL_STDOUT, data)
+
+
 def main():
+    quiet_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=10)
