@@ -178,7 +178,7 @@ def run_gpu(args):
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     dev = torch.device("cuda", local)
 
-    precision = {"fp32": ops.PRECISION_FP32, "tf32": ops.PRECISION_TF32, "tf32x3": ops.PRECISION_TF32X3}[args.precision]
+    precision = ops.PRECISION_NAMES[args.precision]
     path = VoxelBackbonePath(state=synth.backbone_state(0), precision=precision, device=dev)
     # weak scaling: every rank owns its own batch of scenes (seeds differ per rank); no data-path collective
     clouds = [synth.lidar_scene(seed) for seed in sharding.scene_seeds(1, args.batch, rank)]
@@ -273,16 +273,22 @@ def run_gpu(args):
                                   "frac": tfl / FP32_SIMT_PEAK_TFLOPS}}
         else:
             tf32_peak = pk_peaks["bf16"] / 2.0
+            if prec == ops.PRECISION_AUTO:                     # what the library resolves AUTO to for this shape
+                prec = ops.PRECISION_TF32_BF16C if cout % 128 == 0 else ops.PRECISION_TF32X3
+            passes = {ops.PRECISION_TF32: 1, ops.PRECISION_TF32_BF16C: 2, ops.PRECISION_TF32X3: 3}[prec]
+            mode_note = {1: "", 2: "; per K-slice one TF32 MMA + BF16 correction MMAs costing one more TF32 pass "
+                                   "(TF32 + BF16-correction mode, fp32-level accuracy)",
+                         3: " and 3 MMAs per K-slice in the error-compensated TF32x3 mode"}[passes]
             roof = {"bound": "tensor", "achieved": tfl, "peak": tf32_peak, "unit": "TFLOP/s", "frac": tfl / tf32_peak,
-                    "traffic": ncu_traffic(f"spconv_tc_kernel<{cin},{cout},{3 if prec == ops.PRECISION_TF32X3 else 1}>"),
+                    "traffic": ncu_traffic(f"spconv_tc_kernel<{cout},{passes}> Cin={cin}"),
                     "algorithmic_bytes": bytes_launch, "kernel": f"spconv_tc_kernel<{cin},{cout}> (K={K})",
                     "launches_per_step": dom_n / args.steps, "avg_launch_ms": avg_ms,
                     "share_of_step": dom_ms / dev_ms if world == 1 else None,
                     "peak_source": pk_peaks["source"] + " bf16 burst / 2 (TF32 runs at half the bf16 rate)",
                     "note": "achieved = algorithmic flops 2*P*Cin*Cout (real neighbour pairs only); the kernel "
                             "executes dense 128-row tiles (zero rows for missing neighbours)"
-                            + (" and 3 MMAs per K-slice in the error-compensated TF32x3 mode" if prec == ops.PRECISION_TF32X3 else ""),
-                    "executed_tflops": tfl * (n_out * K / max(pairs, 1)) * (3 if prec == ops.PRECISION_TF32X3 else 1),
+                            + mode_note,
+                    "executed_tflops_tf32_equiv": tfl * (n_out * K / max(pairs, 1)) * passes,
                     "hbm": {"achieved_gbs": gbs, "frac": gbs / pk_peaks["hbm"]}}
         per_group = {f"{k[0]}->{k[1]} K={k[2]}{' +res' if k[3] else ''}": round(g["ms"] / args.steps, 4)
                      for k, g in sorted(groups.items())}
@@ -378,7 +384,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--batch", type=int, default=4, help="scenes per GPU per step")
-    ap.add_argument("--precision", default=os.environ.get("S2D_PRECISION", "tf32x3"), choices=["fp32", "tf32", "tf32x3"])
+    ap.add_argument("--precision", default=os.environ.get("S2D_PRECISION", "auto"), choices=["fp32", "tf32", "tf32x3", "tf32_bf16c", "auto"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     if args.impl == "reference":

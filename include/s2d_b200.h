@@ -135,17 +135,23 @@ int s2d_rulebook_sparse(const int* out_coors, int n_out, int batch, const int* s
  *   scale, shift (nullable, both or neither) f32 [Cout] -- eval-mode BN folded by the host,
  *   or bias via shift with scale == NULL meaning 1
  *   residual (nullable) f32 [n_out, Cout]; relu != 0 applies max(0, .)
- *   precision: S2D_PRECISION_FP32 (SIMT FFMA) or S2D_PRECISION_TF32[X3] (tcgen05, fp32 accumulate).
- *              For the TF32 modes W must be the PACKED image produced by s2d_spconv_pack_weights
- *              (once per layer), not the raw tensor: TF32X3 = error-compensated split
- *              (hi*hi + lo*hi + hi*lo, ~fp32 accuracy), TF32 = single pass.
+ *   precision: S2D_PRECISION_FP32 (SIMT FFMA) or a tcgen05 mode (fp32 accumulate in TMEM).
+ *              For the tcgen05 modes W must be the PACKED image produced by s2d_spconv_pack_weights
+ *              FOR THAT PRECISION (once per layer), not the raw tensor:
+ *                TF32X3     = error-compensated split (hi*hi + lo*hi + hi*lo in TF32, ~fp32 accuracy),
+ *                TF32_BF16C = hi*hi in TF32 + the two correction terms as one BF16 contraction
+ *                             (same accuracy class, 2/3 of the tensor time; TF32 and TF32X3 share an image),
+ *                TF32       = single pass.
+ *              Shapes: Cin == 16 or Cin % 32 == 0; Cout % 16 == 0 (s2d_spconv_tf32_supported).
  * ------------------------------------------------------------------------------------- */
 #define S2D_PRECISION_FP32 0
 #define S2D_PRECISION_TF32 1
 #define S2D_PRECISION_TF32X3 2
+#define S2D_PRECISION_TF32_BF16C 3
+#define S2D_PRECISION_AUTO 4 /* TF32_BF16C where the layer is tensor bound (Cout % 128 == 0), TF32X3 elsewhere */
 int s2d_spconv_tf32_supported(int Cin, int Cout);
 size_t s2d_spconv_packed_bytes(int K, int Cin, int Cout);
-int s2d_spconv_pack_weights(const float* W, int K, int Cin, int Cout, float* packed, void* stream);
+int s2d_spconv_pack_weights(const float* W, int K, int Cin, int Cout, int precision, float* packed, void* stream);
 int s2d_spconv_fwd(const float* in, int n_in, const float* W, const int* tbl, int tbl_stride,
                    int n_out, int Cin, int Cout, int K, const float* scale, const float* shift,
                    const float* residual, int relu, float* out, int precision, void* stream);

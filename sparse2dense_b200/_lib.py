@@ -36,7 +36,7 @@ SIGNATURES = {
     "s2d_spconv_fwd": (_i, [_vp, _i, _vp, _vp, _i, _i, _i, _i, _i, _vp, _vp, _vp, _i, _vp, _i, _vp]),
     "s2d_spconv_tf32_supported": (_i, [_i, _i]),
     "s2d_spconv_packed_bytes": (_sz, [_i, _i, _i]),
-    "s2d_spconv_pack_weights": (_i, [_vp, _i, _i, _i, _vp, _vp]),
+    "s2d_spconv_pack_weights": (_i, [_vp, _i, _i, _i, _i, _vp, _vp]),
     "s2d_conv_fwd": (_i, [_vp, _vp]),
     "s2d_grid2d_table": (_i, [_i, _i, _i, _i, _i, _i, _i, _vp, _i, _vp]),
     "s2d_grid2d_tconv_table": (_i, [_i, _i, _i, _i, _i, _i, _i, _i, _vp, _i, _vp, _vp]),

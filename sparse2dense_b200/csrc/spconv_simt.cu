@@ -221,6 +221,8 @@ extern "C" int s2d_conv_fwd(const s2d_conv_params* params, void* stream) {
       return conv_fwd_fp32(p, st);
     case S2D_PRECISION_TF32:
     case S2D_PRECISION_TF32X3:
+    case S2D_PRECISION_TF32_BF16C:
+    case S2D_PRECISION_AUTO:
       return conv_fwd_tf32(p, st);
     default:
       set_error("s2d_conv_fwd: unknown precision %d", p.precision);

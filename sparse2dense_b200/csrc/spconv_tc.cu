@@ -22,6 +22,8 @@
 //
 // Precision modes: TF32X3 (error-compensated, ~fp32 accuracy: this is what meets the 1e-3 parity
 // bar through 21 layers) and TF32 (single pass).
+#include <cuda_bf16.h>
+
 #include "common.cuh"
 
 namespace s2d {
@@ -48,18 +50,23 @@ __device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t byt
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
 }
 // Bounded wait: a protocol bug traps (reported as a CUDA error) instead of hanging the GPU.
-__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
-  uint32_t done = 0;
-  for (uint32_t spin = 0; !done; ++spin) {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-        "selp.u32 %0, 1, 0, p;\n\t}"
-        : "=r"(done)
-        : "r"(bar), "r"(parity)
-        : "memory");
+__device__ __forceinline__ uint32_t mbar_try_wait(uint32_t bar, uint32_t parity) {
+  uint32_t done;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(done)
+      : "r"(bar), "r"(parity)
+      : "memory");
+  return done;
+}
+__device__ __noinline__ void mbar_wait_slow(uint32_t bar, uint32_t parity) {
+  for (uint32_t spin = 0; !mbar_try_wait(bar, parity); ++spin)
     if (spin > (1u << 22)) __trap();
-  }
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  if (!mbar_try_wait(bar, parity)) mbar_wait_slow(bar, parity);   // the common case is one instruction + branch
 }
 __device__ __forceinline__ void bulk_copy_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
@@ -101,6 +108,22 @@ __device__ __forceinline__ void umma_tf32_ts(uint32_t tmem_d, uint32_t tmem_a, u
       "r"(tmem_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
       : "memory");
 }
+// D[tmem] (+)= A[tmem] * B[smem], BF16 inputs (two per 32-bit TMEM column, low half = lower k), fp32 accumulate
+__device__ __forceinline__ void umma_bf16_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t desc_b, uint32_t idesc,
+                                             uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}" ::"r"(tmem_d),
+      "r"(tmem_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// {lo, hi} -> one 32-bit word of two BF16 values (lo in bits [0,16)), TRUNCATED: one PRMT on the ALU pipe
+// instead of a conversion-pipe cvt (16 of those per lane and step made the producers conversion-bound).  The
+// operands packed here are the 2^-12-sized correction terms, so truncation (2^-8 relative) costs ~2^-20.
+__device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
+  return __byte_perm(__float_as_uint(lo), __float_as_uint(hi), 0x7632);
+}
 // 16 lanes x 32 columns: reg 4n+e -> (lane l/4, column 8n + 2(l%4) + e), reg 4n+2+e -> lane l/4 + 8 (probed on B200)
 __device__ __forceinline__ void tmem_st_16x256b_x4(uint32_t taddr, const uint32_t (&v)[16]) {
   asm volatile(
@@ -123,6 +146,38 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
       : "r"(taddr)
       : "memory");
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&v)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+        "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+      : "r"(taddr)
+      : "memory");
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+template <int N>
+__device__ __forceinline__ void tmem_ld(uint32_t taddr, uint32_t (&v)[N]) {
+  static_assert(N == 16 || N == 32, "accumulator columns per load");
+  if constexpr (N == 32) tmem_ld32(taddr, v); else tmem_ld16(taddr, v);
+}
+// 16 B global -> shared copy that bypasses registers; src_bytes = 0 writes zeros (missing neighbour)
+__device__ __forceinline__ void cp_async16_zfill(uint32_t dst, const void* src, uint32_t src_bytes) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(src_bytes) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+__device__ __forceinline__ int lds32(uint32_t addr) {
+  int v;
+  asm volatile("ld.shared.b32 %0, [%1];" : "=r"(v) : "r"(addr));
+  return v;
+}
+__device__ __forceinline__ float4 lds128(uint32_t addr) {
+  float4 v;
+  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
+  return v;
 }
 __device__ __forceinline__ bool elect_one() {
   uint32_t pred;
@@ -156,6 +211,11 @@ __host__ __device__ constexpr uint32_t make_idesc_tf32(int M, int N) {
   return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
 }
 
+// kind::f16 with BF16 inputs: c_format F32 (1<<4), a/b format BF16 (1<<7, 1<<10)
+__host__ __device__ constexpr uint32_t make_idesc_bf16(int M, int N) {
+  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+
 // byte offset of the 16 B chunk `c16` (0..7) of row `r` inside a [rows x 32 fp32] SW128 tile
 __host__ __device__ __forceinline__ uint32_t sw128_chunk_offset(int r, int c16) {
   return (uint32_t)r * 128u + (uint32_t)((c16 ^ (r & 7)) << 4);
@@ -164,46 +224,70 @@ __host__ __device__ __forceinline__ uint32_t sw128_chunk_offset(int r, int c16) 
 // ---------------------------------------------------------------------------------------------
 // kernel
 // ---------------------------------------------------------------------------------------------
-constexpr int kProducerWarps = 8;
-constexpr int kLoaderWarp = 8;
-constexpr int kMmaWarp = 9;
-constexpr int kTcThreads = 320;
+constexpr int kGroups = 2;                 // producer groups: group g gathers / converts the steps s = g (mod kGroups)
+constexpr int kGroupWarps = 8;             // 8 warps x 16 rows = one 128-row step
+constexpr int kProducerWarps = kGroups * kGroupWarps;
+constexpr int kLoaderWarp = kProducerWarps;
+constexpr int kMmaWarp0 = kProducerWarps + 1;   // first MMA warp; MMA warp m issues the MMAs of row tile t = m
+constexpr int kMmaWarps = 4;                     // = max T: a single issuing thread cannot keep the tensor pipe fed
+constexpr int kTcThreads = 32 * (kProducerWarps + 1 + kMmaWarps);
 constexpr int kNbrSlots = 4;
+constexpr int kMaxKps = 2;   // kernel offsets folded into one 32-channel contraction step (Cin = 16: two)
 
 // A tile element (row m, channel ch of the 32-channel chunk) lives in TMEM lane m, column a_col(ch).  The
 // permutation makes the 8 columns a thread owns in a tcgen05.st.16x256b.x4 fragment
 // (columns 8n + 2j + e, j = lane % 4) equal to 8 CONTIGUOUS channels [8j, 8j+8) of its row, so the gather is
 // two LDG.128 per row.  The weight tiles are packed with the same K permutation (pack_weights_kernel).
 __host__ __device__ constexpr int a_col_of_channel(int ch) { return 8 * ((ch % 8) / 2) + 2 * (ch / 8) + (ch % 2); }
+// Same idea for the BF16 correction operand: two values per 32-bit column, 16 columns per 32 channels; the
+// thread's 4 columns {2j, 2j+1, 8+2j, 8+2j+1} hold channels 8j..8j+7 at k positions 4j..4j+3, 16+4j..16+4j+3.
+__host__ __device__ constexpr int bf16_kpos_of_channel(int ch) { return 16 * ((ch % 8) / 4) + 4 * (ch / 8) + (ch % 4); }
 
+// PASSES: 1 = single TF32 pass; 3 = split TF32 (Alo*Bhi + Ahi*Blo + Ahi*Bhi, three TF32 MMAs per K slice);
+//         2 = TF32 main term + BF16 correction terms: Ahi*Bhi in TF32, and [Alo | A] x [B ; Blo] as ONE BF16
+//             contraction of twice the depth (BF16 runs at twice the TF32 rate, so the corrections cost one TF32
+//             pass instead of two).  The correction terms are 2^-11 of the result, so their own BF16 rounding
+//             (2^-9 relative) leaves an error of ~2^-20 per product: fp32-level accuracy at 2/3 of the tensor time.
 template <int COUT, int PASSES>
 struct TcCfg {
-  static constexpr int NPART = PASSES == 3 ? 2 : 1;
+  static constexpr int NPART = PASSES == 1 ? 1 : 2;
   static constexpr int T = COUT >= 128 ? 2 : 4;        // 128-row tiles per CTA sharing every weight tile
   static constexpr int ROWS = T * kBM;
-  static constexpr int B_TILE = COUT * kBK * 4;        // 4 / 8 / 16 KB
+  static constexpr int B_TILE = COUT * kBK * 4;        // 2 / 4 / 8 / 16 KB (COUT rows x 128 B)
   static constexpr int B_STAGE = NPART * B_TILE;
-  static constexpr int SB = 4;                         // weight-tile ring (shared memory)
-  static constexpr int ACC_COLS = T * COUT;            // TMEM: accumulators ...
-  static constexpr int A_COLS = NPART * kBK;           // ... and one gathered A stage (hi | lo), 32 columns each
+  static constexpr int SB = COUT >= 128 ? 3 : 4;       // weight-tile ring (shared memory)
+  static constexpr int ACC_STRIDE = COUT < 32 ? 32 : COUT;   // accumulators of different tiles (issued by different
+                                                       // threads) never share a 32-column TMEM granule
+  static constexpr int ACC_COLS = T * ACC_STRIDE;      // TMEM: accumulators ...
+  static constexpr int A_COLS = NPART * kBK;           // ... and one gathered A stage: 32 TF32 columns (+ 32 more)
   static constexpr int SA_RAW = (512 - ACC_COLS) / A_COLS;
   static constexpr int SA = SA_RAW > 8 ? 8 : SA_RAW;   // gathered-tile ring (TMEM)
   static constexpr int TMEM_COLS = 512;
-  static constexpr int NBR_BYTES = kNbrSlots * ROWS * 4;
-  static constexpr int SMEM_BYTES = SB * B_STAGE + NBR_BYTES + 1024 + 1024;
-  static_assert(COUT % 16 == 0 && COUT >= 32 && COUT <= 128, "UMMA N constraint for M=128 / TMEM budget");
-  static constexpr int BATCH = 1;                      // steps per producer hand-off (2 measured slower except 128->128 TF32)
-  static_assert(SA >= 2 * BATCH && T % BATCH == 0, "gathered-tile ring must hold two producer batches");
+  static constexpr int DEPTH = COUT >= 128 ? 3 : 4;    // gathered steps in flight per producer warp (cp.async ring)
+  static constexpr int A_WARP_STAGE = 16 * 128;        // 16 rows x 128 B per producer warp and step
+  static constexpr int A_RING_BYTES = kProducerWarps * DEPTH * A_WARP_STAGE;
+  static constexpr int EPC = COUT < 32 ? COUT : 32;    // accumulator columns per epilogue tcgen05.ld
+  static constexpr int NBR_BYTES = kNbrSlots * kMaxKps * ROWS * 4;
+  static constexpr int SMEM_BYTES = SB * B_STAGE + A_RING_BYTES + NBR_BYTES + 1024 + 1024;
+  static_assert(SMEM_BYTES <= 227 * 1024, "shared memory budget");
+  static_assert(COUT % 16 == 0 && COUT >= 16 && COUT <= 128, "UMMA N constraint for M=128 / TMEM budget");
+  static_assert(SA >= 2 && SA >= kGroups, "gathered-tile ring too small");
+  static_assert(T % kGroups == 0, "every producer group must touch every offset step");
 };
 
-// One CTA = T row tiles.  Loop nest: kernel offset k > channel chunk c > tile t; the weight tile of (k,c) is
-// loaded once and feeds T MMA groups (one per tile accumulator).  The gathered A operand never touches
-// shared memory: the producer warps write it straight into TMEM (tcgen05.st) and the MMAs run in TS mode,
-// so shared-memory bandwidth only carries the small weight slices.
 // Arguments of one launch.  Rows may be strided (in_ld / out_ld / res_ld, in floats) so that layers can read
 // from and write into channel slices of wider buffers (concatenations); blockIdx.y selects a block of COUT
 // output channels (weights are packed per block); out_rows optionally remaps output rows (sub-pixel
-// transposed convolutions).
+// transposed convolutions).  A contraction step covers 32 input channels: one 32-channel chunk of one kernel
+// offset (kps = 1, nchunk = Cin/32) or the 16 channels of two consecutive offsets (kps = 2, Cin = 16).
+// Ablation switches (tools/ablate_spconv.py) exist only in builds with -DS2D_TC_ABLATE; they cost instructions in
+// the producer loop, which is issue bound.
+#ifdef S2D_TC_ABLATE
+#define S2D_DBG(args, bit) ((args).dbg & (bit))
+#else
+#define S2D_DBG(args, bit) 0
+#endif
+
 struct ConvArgs {
   const float* in;
   const float* packed;
@@ -213,7 +297,8 @@ struct ConvArgs {
   const float* residual;
   float* out;
   const int* out_rows;
-  int in_ld, out_ld, res_ld, tbl_stride, n_out, K, nchunk, act, res_after_act;
+  int in_ld, out_ld, res_ld, tbl_stride, n_out, K, nchunk, kps, ksteps, act, res_after_act;
+  int dbg;   // ablation switches for tools/ablate_spconv.py (0 in production): 1 no gather, 2 no TMEM store, 4 no MMA
 };
 
 __device__ __forceinline__ float apply_act(float y, int act) {
@@ -222,13 +307,17 @@ __device__ __forceinline__ float apply_act(float y, int act) {
   return y;
 }
 
+// One CTA = T row tiles.  Loop nest: offset step kk > channel chunk c > tile t; the weight tile of (kk,c) is
+// loaded once and feeds T MMA groups (one per tile accumulator).  The gathered A operand never touches
+// shared memory: the producer warps write it straight into TMEM (tcgen05.st) and the MMAs run in TS mode,
+// so shared-memory bandwidth only carries the small weight slices.
 template <int COUT, int PASSES>
 __global__ void __launch_bounds__(kTcThreads, 1) spconv_tc_kernel(const __grid_constant__ ConvArgs A) {
   using Cfg = TcCfg<COUT, PASSES>;
   constexpr int SA = Cfg::SA, SB = Cfg::SB, T = Cfg::T;
   constexpr int B_TILE = Cfg::B_TILE, B_STAGE = Cfg::B_STAGE, A_COLS = Cfg::A_COLS;
-  const int NCHUNK = A.nchunk, K = A.K, n_out = A.n_out;
-  const size_t blk_tiles = (size_t)blockIdx.y * K * NCHUNK;            // weight tiles before this channel block
+  const int NCHUNK = A.nchunk, K = A.K, KS = A.ksteps, kps = A.kps, n_out = A.n_out;
+  const size_t blk_tiles = (size_t)blockIdx.y * KS * NCHUNK;           // weight tiles before this channel block
   const float* __restrict__ packed = A.packed + blk_tiles * 2 * (B_TILE / 4);
   const int* __restrict__ tbl = A.tbl;
   const int tbl_stride = A.tbl_stride;
@@ -236,8 +325,9 @@ __global__ void __launch_bounds__(kTcThreads, 1) spconv_tc_kernel(const __grid_c
 
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint8_t* b_ring = smem;                                       // SB x [B_hi | B_lo]
-  int* s_nbr = reinterpret_cast<int*>(b_ring + SB * B_STAGE);   // kNbrSlots x [T*128]
+  uint8_t* b_ring = smem;                                       // SB x [B_hi | B_lo or B_bf16]
+  uint8_t* a_ring = b_ring + SB * B_STAGE;                      // 8 warps x DEPTH x [16 rows x 128 B], 128B-swizzled
+  int* s_nbr = reinterpret_cast<int*>(a_ring + Cfg::A_RING_BYTES);   // kNbrSlots x kMaxKps x [T*128]
   uint64_t* bars = reinterpret_cast<uint64_t*>(reinterpret_cast<uint8_t*>(s_nbr) + Cfg::NBR_BYTES);
   uint64_t* bar_a_full = bars;
   uint64_t* bar_a_empty = bar_a_full + SA;
@@ -250,22 +340,22 @@ __global__ void __launch_bounds__(kTcThreads, 1) spconv_tc_kernel(const __grid_c
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int tile0 = blockIdx.x * Cfg::ROWS;
-  const int nsteps = K * NCHUNK * T;
+  const int nsteps = KS * NCHUNK * T;
 
-  if (warp == kMmaWarp && lane == 0) {
+  if (warp == kMmaWarp0 && lane == 0) {
     for (int s = 0; s < SA; ++s) {
-      mbar_init(smem_u32(bar_a_full + s), kProducerWarps);        // one arrival per producer warp
+      mbar_init(smem_u32(bar_a_full + s), kGroupWarps);           // one arrival per producer warp of the step's group
       mbar_init(smem_u32(bar_a_empty + s), 1);                    // one tcgen05.commit
     }
     for (int s = 0; s < SB; ++s) {
       mbar_init(smem_u32(bar_b_full + s), 1);                     // arrive.expect_tx of the loader
-      mbar_init(smem_u32(bar_b_empty + s), 1);
+      mbar_init(smem_u32(bar_b_empty + s), T);                    // one tcgen05.commit per row tile
     }
     for (int s = 0; s < kNbrSlots; ++s) {
       mbar_init(smem_u32(bar_n_full + s), 32);                    // every loader lane arrives
       mbar_init(smem_u32(bar_n_empty + s), kProducerWarps);
     }
-    mbar_init(smem_u32(bar_accum), 1);
+    mbar_init(smem_u32(bar_accum), T);
     fence_barrier_init();
   }
   if (warp == kLoaderWarp) tmem_alloc(smem_u32(s_tmem), Cfg::TMEM_COLS);
@@ -278,129 +368,169 @@ __global__ void __launch_bounds__(kTcThreads, 1) spconv_tc_kernel(const __grid_c
   if (warp < kProducerWarps) {
     // ===================== A producers (8 warps x 16 rows) =====================
     // warp w owns TMEM lanes (= tile rows) [32*(w%4) + 16*(w/4), +16); lane l: rows rA = base + l/4 and rA + 8,
-    // channels [8*(l%4), +8) of the chunk (see a_col_of_channel).
-    const int row16 = 32 * (warp & 3) + 16 * (warp >> 2);
-    const int rA = row16 + (lane >> 2);
-    const int j4 = (lane & 3) * 2;               // float4 index of this lane's 8 channels inside the chunk
-    const float4* in4 = reinterpret_cast<const float4*>(A.in);
-    const int in_ld4 = A.in_ld >> 2;
+    // channels [8*(l%4), +8) of the step's 32 contraction channels (see a_col_of_channel).
+    const int grp = warp / kGroupWarps, gw = warp % kGroupWarps;
+    const int row16 = 32 * (gw & 3) + 16 * (gw >> 2);
+    const int rl = lane >> 2;                                // fragment rows rl and rl + 8 of the warp's 16
+    const int j = lane & 3;
+    const int o = lane >> 3, c = lane & 7;                   // gather: lane = (row octet, 16 B chunk of the row)
+    const int sub = kps == 2 ? (c >> 2) : 0;                 // which of the step's offsets this lane gathers
+    const int c4 = kps == 2 ? (c & 3) : c;                   // float4 index inside the source row chunk
     const uint32_t bar_a_full0 = smem_u32(bar_a_full), bar_a_empty0 = smem_u32(bar_a_empty);
     const uint32_t bar_n_full0 = smem_u32(bar_n_full), bar_n_empty0 = smem_u32(bar_n_empty);
     const uint32_t tmem_mine = tmem_a0 + ((uint32_t)row16 << 16);
+    const int* nbr_mine = s_nbr + sub * Cfg::ROWS + row16 + o;
+    constexpr int DEPTH = Cfg::DEPTH;
+    const uint32_t ring0 = smem_u32(a_ring) + (uint32_t)warp * (DEPTH * Cfg::A_WARP_STAGE);
+    // gather destination of this lane inside a stage (row 4i + o, chunk c, 128B swizzle) and fragment sources
+    const uint32_t g_off = (uint32_t)o * 128u + (uint32_t)((c ^ o) << 4);          // + i*512 ; (4i+o)&7 = o ^ 4*(i&1)
+    const uint32_t f_off0 = (uint32_t)rl * 128u + (uint32_t)(((2 * j) ^ rl) << 4);
+    const uint32_t f_off1 = (uint32_t)rl * 128u + (uint32_t)(((2 * j + 1) ^ rl) << 4);
 
-    // Steps are produced in batches of BATCH: one empty-wait / tcgen05.wait::st / fence / arrive sequence per
-    // batch amortises the fixed latencies of the hand-off; the loads of the next batch are already in flight.
-    constexpr int BATCH = Cfg::BATCH;
-    int lk = 0, lc = 0, lt = 0;                  // load stream position (k, c, t)
-    int sstage = 0;                              // store stream position
-    uint32_t sphase = 1;                         // first pass over the ring: slots are free
-    // v[b][0..1] = row rA channels 8j..8j+7, v[b][2..3] = row rA+8
-    auto load_batch = [&](float4 (&v)[BATCH][4]) {
+    // The gather runs DEPTH steps ahead of the conversion: every lane copies 16 B pieces of the neighbour rows
+    // straight into the warp's shared-memory ring with cp.async (a missing neighbour is a zero-fill), so the
+    // number of rows in flight is bounded by the ring, not by registers or scoreboards.  A warp gathers exactly
+    // the 16 rows it later converts, so only warp-level synchronisation is needed.
+    // This warp's steps are s = grp, grp + kGroups, ...; step s = (lk * NCHUNK + lc) * T + lt.
+    int lk = 0, lc = 0, lt = grp;                // gather stream position (offset step, chunk, tile); kGroups <= T
+    int lk_ready = -1;                           // last offset step whose neighbour slice this warp has waited for
+    int gstage = 0, cstage = 0;                  // ring positions of the gather / convert streams
+    int sstage = grp;                            // TMEM ring position of step s: s % SA
+    uint32_t sphase = 1;                         // first pass over the TMEM ring: slots are free
+    // byte offsets are 32 bit (the host checks n_in * in_ld * 4 < 4 GiB); neighbour indices are read with ld.shared
+    const char* in_bytes = reinterpret_cast<const char*>(A.in);
+    const uint32_t row_bytes = (uint32_t)A.in_ld * 4u;
+    const uint32_t nbr_addr0 = smem_u32(nbr_mine);
+    auto gather_step = [&]() {
+      const int slot = lk & (kNbrSlots - 1);
+      if (lk != lk_ready) { mbar_wait(bar_n_full0 + 8 * slot, (lk / kNbrSlots) & 1); lk_ready = lk; }
+      const uint32_t nb = nbr_addr0 + (uint32_t)(slot * (kMaxKps * Cfg::ROWS) + lt * kBM) * 4u;
+      const uint32_t dst0 = ring0 + (uint32_t)gstage * Cfg::A_WARP_STAGE + g_off;
+      const uint32_t cbytes = (uint32_t)(lc * kBK + c4 * 4) * 4u;
 #pragma unroll
-      for (int b = 0; b < BATCH; ++b) {
-        const int slot = lk & (kNbrSlots - 1);
-        if ((lc | lt) == 0) mbar_wait(bar_n_full0 + 8 * slot, (lk / kNbrSlots) & 1);
-        const int* nbr = s_nbr + slot * Cfg::ROWS + lt * kBM + rA;
-        const int ja = nbr[0], jb = nbr[8];
-        v[b][0] = v[b][1] = v[b][2] = v[b][3] = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (ja >= 0) {
-          const float4* p = in4 + ((size_t)ja * in_ld4 + lc * (kBK / 4) + j4);
-          v[b][0] = __ldg(p); v[b][1] = __ldg(p + 1);
-        }
-        if (jb >= 0) {
-          const float4* p = in4 + ((size_t)jb * in_ld4 + lc * (kBK / 4) + j4);
-          v[b][2] = __ldg(p); v[b][3] = __ldg(p + 1);
-        }
-        if (++lt == T) {
-          lt = 0;
-          if (++lc == NCHUNK) {
-            lc = 0;
-            __syncwarp();                        // every lane has read this k's indices
-            if (lane == 0) mbar_arrive(bar_n_empty0 + 8 * slot);
-            ++lk;
-          }
+      for (int i = 0; i < 4; ++i) {
+        if (S2D_DBG(A, 1)) break;
+        const int idx = lds32(nb + 16u * i);                                   // row 4i + o of the warp's 16
+        const uint32_t off = (uint32_t)max(idx, 0) * row_bytes + cbytes;
+        const uint32_t dst = (dst0 + (uint32_t)i * 512u) ^ ((uint32_t)(i & 1) << 6);   // chunk ^= 4 on odd i
+        cp_async16_zfill(dst, in_bytes + off, idx >= 0 ? 16u : 0u);
+      }
+      cp_async_commit();
+      if (++gstage == DEPTH) gstage = 0;
+      lt += kGroups;
+      if (lt >= T) {
+        lt -= T;
+        if (++lc == NCHUNK) {
+          lc = 0;
+          __syncwarp();                          // every lane has read this step's indices
+          if (lane == 0) mbar_arrive(bar_n_empty0 + 8 * slot);
+          ++lk;
         }
       }
     };
-    auto store_batch = [&](const float4 (&v)[BATCH][4]) {
-      const int stage0 = sstage;
-#pragma unroll
-      for (int b = 0; b < BATCH; ++b) {
-        mbar_wait(bar_a_empty0 + 8 * sstage, sphase);
-        if (b == BATCH - 1) tc_fence_after();
-        if (++sstage == SA) { sstage = 0; sphase ^= 1; }
+    auto convert_step = [&]() {
+      cp_async_wait<DEPTH - 1>();                // this lane's pieces of the oldest step in flight have landed
+      __syncwarp();                              // ... and so have the other lanes'
+      const uint32_t src = ring0 + (uint32_t)cstage * Cfg::A_WARP_STAGE;
+      if (++cstage == DEPTH) cstage = 0;
+      float4 v[4];
+      if (S2D_DBG(A, 8)) {
+        v[0] = v[1] = v[2] = v[3] = make_float4(1.f, 2.f, 3.f, 4.f);
+      } else {
+        v[0] = lds128(src + f_off0); v[1] = lds128(src + f_off1);
+        v[2] = lds128(src + f_off0 + 1024u); v[3] = lds128(src + f_off1 + 1024u);
       }
-      int st = stage0;
+      // fragment order of tcgen05.st.16x256b.x4: reg 4n+e = row rl, column 8n+2j+e; reg 4n+2+e = row rl+8
+      const float xa[8] = {v[0].x, v[0].y, v[0].z, v[0].w, v[1].x, v[1].y, v[1].z, v[1].w};
+      const float xb[8] = {v[2].x, v[2].y, v[2].z, v[2].w, v[3].x, v[3].y, v[3].z, v[3].w};
+      uint32_t hi[16], lo[16];
+      if constexpr (PASSES == 2) {
+        float la[8], lb[8];
 #pragma unroll
-      for (int b = 0; b < BATCH; ++b) {
-        // fragment order of tcgen05.st.16x256b.x4: reg 4n+e = row rA, column 8n+2j+e; reg 4n+2+e = row rA+8
-        const float xa[8] = {v[b][0].x, v[b][0].y, v[b][0].z, v[b][0].w, v[b][1].x, v[b][1].y, v[b][1].z, v[b][1].w};
-        const float xb[8] = {v[b][2].x, v[b][2].y, v[b][2].z, v[b][2].w, v[b][3].x, v[b][3].y, v[b][3].z, v[b][3].w};
-        uint32_t hi[16], lo[16];
+        for (int i = 0; i < 8; ++i) {
+          const float ah = tf32_round(xa[i]), bh = tf32_round(xb[i]);   // x = hi + lo exactly (integer-pipe rounding)
+          hi[4 * (i >> 1) + (i & 1)] = __float_as_uint(ah);
+          hi[4 * (i >> 1) + 2 + (i & 1)] = __float_as_uint(bh);
+          la[i] = xa[i] - ah;
+          lb[i] = xb[i] - bh;
+        }
+#pragma unroll
+        for (int h = 0; h < 2; ++h)
+#pragma unroll
+          for (int e = 0; e < 2; ++e) {
+            const int i0 = 4 * h + 2 * e;
+            lo[4 * h + e] = pack_bf16x2(la[i0], la[i0 + 1]);             // columns [0,16): A_lo  (x B)
+            lo[4 * h + 2 + e] = pack_bf16x2(lb[i0], lb[i0 + 1]);
+            lo[4 * (h + 2) + e] = pack_bf16x2(xa[i0], xa[i0 + 1]);       // columns [16,32): A    (x B_lo)
+            lo[4 * (h + 2) + 2 + e] = pack_bf16x2(xb[i0], xb[i0 + 1]);
+          }
+      } else {
 #pragma unroll
         for (int n = 0; n < 4; ++n)
 #pragma unroll
           for (int e = 0; e < 2; ++e) {
-            const float a = xa[2 * n + e], c = xb[2 * n + e];
+            const float a = xa[2 * n + e], cc = xb[2 * n + e];
             if constexpr (PASSES == 3) {
-              const float ah = tf32_trunc(a), ch = tf32_trunc(c);   // x = hi + lo exactly
+              const float ah = tf32_trunc(a), ch = tf32_trunc(cc);   // x = hi + lo exactly
               hi[4 * n + e] = __float_as_uint(ah);      lo[4 * n + e] = __float_as_uint(a - ah);
-              hi[4 * n + 2 + e] = __float_as_uint(ch);  lo[4 * n + 2 + e] = __float_as_uint(c - ch);
+              hi[4 * n + 2 + e] = __float_as_uint(ch);  lo[4 * n + 2 + e] = __float_as_uint(cc - ch);
             } else {
               hi[4 * n + e] = __float_as_uint(tf32_round(a));
-              hi[4 * n + 2 + e] = __float_as_uint(tf32_round(c));
+              hi[4 * n + 2 + e] = __float_as_uint(tf32_round(cc));
             }
           }
-        const uint32_t dst = tmem_mine + (uint32_t)(st * A_COLS);
+      }
+      mbar_wait(bar_a_empty0 + 8 * sstage, sphase);
+      tc_fence_after();
+      const uint32_t dst = tmem_mine + (uint32_t)(sstage * A_COLS);
+      if (!S2D_DBG(A, 2)) {
         tmem_st_16x256b_x4(dst, hi);
-        if constexpr (PASSES == 3) tmem_st_16x256b_x4(dst + kBK, lo);
-        if (++st == SA) st = 0;
+        if constexpr (PASSES != 1) tmem_st_16x256b_x4(dst + kBK, lo);
+        tmem_wait_st();
       }
-      tmem_wait_st();
       tc_fence_before();
-      __syncwarp();
-      if (lane == 0) {                           // one arrival per producer warp and stage
-        st = stage0;
-#pragma unroll
-        for (int b = 0; b < BATCH; ++b) {
-          mbar_arrive(bar_a_full0 + 8 * st);
-          if (++st == SA) st = 0;
-        }
-      }
+      __syncwarp();                              // also: every lane is done reading the ring stage
+      if (lane == 0) mbar_arrive(bar_a_full0 + 8 * sstage);      // one arrival per producer warp and stage
+      sstage += kGroups;
+      if (sstage >= SA) { sstage -= SA; sphase ^= 1; }
     };
 
-    const int nbatches = nsteps / BATCH;         // nsteps = K * NCHUNK * T is a multiple of T >= BATCH
-    float4 bufA[BATCH][4], bufB[BATCH][4];
-    if (nbatches > 0) load_batch(bufA);
-    for (int nb = 0; nb < nbatches; nb += 2) {
-      if (nb + 1 < nbatches) load_batch(bufB);
-      store_batch(bufA);
-      if (nb + 2 < nbatches) load_batch(bufA);
-      if (nb + 1 < nbatches) store_batch(bufB);
+    const int my_steps = nsteps / kGroups;       // nsteps = KS * NCHUNK * T is a multiple of kGroups
+#pragma unroll 1
+    for (int i = 0; i < DEPTH; ++i) {
+      if (i < my_steps) gather_step(); else cp_async_commit();
+    }
+#pragma unroll 1
+    for (int s = 0; s < my_steps; ++s) {
+      convert_step();
+      if (s + DEPTH < my_steps) gather_step(); else cp_async_commit();
     }
 
     // ===================== epilogue (same 8 warps) =====================
-    // TMEM lane == row inside a tile; warp w may touch lanes [32*(w%4), +32).  Warps 0-3 take the even tiles,
-    // warps 4-7 the odd ones.
+    // TMEM lane == row inside a tile; warp w may touch lanes [32*(w%4), +32).
     mbar_wait(smem_u32(bar_accum), 0);
     tc_fence_after();
     const int g = warp & 3;
+    // (tile, column block) units: warp>>2 = 0..3 ; T = 4: one tile each; T = 2: tile = unit & 1, column half = unit >> 1
+    const int unit = warp >> 2;
+    const int t_first = unit % T, c_lo = (unit / T) * (COUT / (4 / T)), c_hi = c_lo + COUT / (4 / T);
     const float* __restrict__ scale = A.scale ? A.scale + cblk : nullptr;
     const float* __restrict__ shift = A.shift ? A.shift + cblk : nullptr;
     const int act = A.act, res_after = A.res_after_act;
+    constexpr int EPC = Cfg::EPC;
 #pragma unroll 1
-    for (int t = warp >> 2; t < T; t += 2) {
+    for (int t = t_first; t < T; t += 4) {
       const int row = tile0 + t * kBM + g * 32 + lane;
       const int orow = (row < n_out && A.out_rows) ? __ldg(A.out_rows + row) : row;
 #pragma unroll 1
-      for (int c0 = 0; c0 < COUT; c0 += 32) {
-        uint32_t acc[32];
-        tmem_ld32(tmem_base + ((uint32_t)(g * 32) << 16) + (uint32_t)(t * COUT + c0), acc);
-        if (row < n_out) {
+      for (int c0 = c_lo; c0 < c_hi; c0 += EPC) {
+        uint32_t acc[EPC];
+        tmem_ld<EPC>(tmem_base + ((uint32_t)(g * 32) << 16) + (uint32_t)(t * Cfg::ACC_STRIDE + c0), acc);
+        if (row < n_out && !S2D_DBG(A, 16)) {
           float* dst = A.out + (size_t)orow * A.out_ld + cblk + c0;
           const float* res = A.residual ? A.residual + (size_t)orow * A.res_ld + cblk + c0 : nullptr;
 #pragma unroll
-          for (int q = 0; q < 8; ++q) {
+          for (int q = 0; q < EPC / 4; ++q) {
             float4 y;
             y.x = __uint_as_float(acc[4 * q + 0]); y.y = __uint_as_float(acc[4 * q + 1]);
             y.z = __uint_as_float(acc[4 * q + 2]); y.w = __uint_as_float(acc[4 * q + 3]);
@@ -424,29 +554,40 @@ __global__ void __launch_bounds__(kTcThreads, 1) spconv_tc_kernel(const __grid_c
     }
   } else if (warp == kLoaderWarp) {
     // ===================== loader: neighbour-table slices (all lanes) + weight tiles (lane 0) =====================
-    auto load_nbr = [&](int k) {
-      const int slot = k % kNbrSlots;
-      mbar_wait(smem_u32(bar_n_empty + slot), ((k / kNbrSlots) & 1) ^ 1);
-      int* dst = s_nbr + slot * Cfg::ROWS;
-      const int* src = tbl + (size_t)k * tbl_stride + tile0;
-      int v[Cfg::ROWS / 32];
+    auto load_nbr = [&](int kk) {
+      const int slot = kk % kNbrSlots;
+      mbar_wait(smem_u32(bar_n_empty + slot), ((kk / kNbrSlots) & 1) ^ 1);
+      int v[kMaxKps][Cfg::ROWS / 32];
 #pragma unroll
-      for (int i = 0; i < Cfg::ROWS / 32; ++i)     // all loads in flight before the first store
-        v[i] = (tile0 + lane + 32 * i < n_out) ? __ldg(src + lane + 32 * i) : -1;
+      for (int sb = 0; sb < kMaxKps; ++sb) {
+        const int k = kk * kps + sb;
+        const bool live = sb < kps && k < K && !S2D_DBG(A, 64);   // a padded offset (odd K, kps = 2) gathers nothing
+        const int* src = tbl + (size_t)k * tbl_stride + tile0;
 #pragma unroll
-      for (int i = 0; i < Cfg::ROWS / 32; ++i) dst[lane + 32 * i] = v[i];
+        for (int i = 0; i < Cfg::ROWS / 32; ++i)     // all loads in flight before the first store
+          v[sb][i] = (live && tile0 + lane + 32 * i < n_out) ? __ldg(src + lane + 32 * i) : -1;
+      }
+#pragma unroll
+      for (int sb = 0; sb < kMaxKps; ++sb) {
+        int* dst = s_nbr + (slot * kMaxKps + sb) * Cfg::ROWS;
+        if (sb < kps) {
+#pragma unroll
+          for (int i = 0; i < Cfg::ROWS / 32; ++i) dst[lane + 32 * i] = v[sb][i];
+        }
+      }
       mbar_arrive(smem_u32(bar_n_full + slot));
     };
-    if (0 < K) load_nbr(0);
-    if (1 < K) load_nbr(1);
-    for (int k = 0; k < K; ++k) {
-      if (k + 2 < K) load_nbr(k + 2);
+    if (0 < KS) load_nbr(0);
+    if (1 < KS) load_nbr(1);
+    for (int kk = 0; kk < KS; ++kk) {
+      if (kk + 2 < KS) load_nbr(kk + 2);
       if (lane == 0) {
         for (int c = 0; c < NCHUNK; ++c) {
-          const int bstep = k * NCHUNK + c;
+          const int bstep = kk * NCHUNK + c;
           const int bs = bstep % SB;
           mbar_wait(smem_u32(bar_b_empty + bs), ((bstep / SB) & 1) ^ 1);
           const uint32_t bar = smem_u32(bar_b_full + bs);
+          if (S2D_DBG(A, 32)) { mbar_arrive(bar); continue; }
           mbar_arrive_expect_tx(bar, B_STAGE);
           bulk_copy_g2s(smem_u32(b_ring + (size_t)bs * B_STAGE), packed + (size_t)bstep * 2 * (B_TILE / 4), B_STAGE,
                         bar);
@@ -454,47 +595,63 @@ __global__ void __launch_bounds__(kTcThreads, 1) spconv_tc_kernel(const __grid_c
       }
       __syncwarp();
     }
-  } else {
-    // ===================== MMA issuer =====================
-    // The whole warp runs the (warp-uniform) loop so that descriptors and addresses stay in uniform
-    // registers; one elected lane issues the tcgen05 instructions.  A comes from TMEM (TS mode).
-    constexpr uint32_t idesc = make_idesc_tf32(kBM, COUT);
-    // constant high word of the SW128 K-major descriptor: SBO = 1024 B, version 1, layout SWIZZLE_128B
-    constexpr uint32_t desc_hi = 64u | (1u << 14) | (2u << 29);
-    const uint32_t b_lo0 = ((smem_u32(b_ring) >> 4) & 0x3FFF) | (1u << 16);
-    const uint32_t bar_a_full0 = smem_u32(bar_a_full), bar_a_empty0 = smem_u32(bar_a_empty);
-    const uint32_t bar_b_full0 = smem_u32(bar_b_full), bar_b_empty0 = smem_u32(bar_b_empty);
-    int stage = 0, bs = 0, t = 0;
-    uint32_t a_phase = 0, b_phase = 0, first = 1;
-    for (int s = 0; s < nsteps; ++s) {
-      if (t == 0) mbar_wait(bar_b_full0 + 8 * bs, b_phase);
-      mbar_wait(bar_a_full0 + 8 * stage, a_phase);
-      tc_fence_after();
-      if (elect_one()) {
+  } else if (warp - kMmaWarp0 < T) {
+    // ===================== MMA issuers: warp m owns row tile t = m =====================
+    // One thread per tile issues that tile's MMAs (steps s = bstep * T + t): the issue loop of a single thread
+    // (~100 instructions per step with the barrier handling) was the bottleneck of the whole kernel when one
+    // warp served all T tiles.  A comes from TMEM (TS mode), B from the shared weight ring.
+    if (lane == 0) {
+      const int t = warp - kMmaWarp0;
+      constexpr uint32_t idesc = make_idesc_tf32(kBM, COUT);
+      constexpr uint32_t idesc16 = make_idesc_bf16(kBM, COUT);
+      // constant high word of the SW128 K-major descriptor: SBO = 1024 B, version 1, layout SWIZZLE_128B
+      constexpr uint32_t desc_hi = 64u | (1u << 14) | (2u << 29);
+      const uint32_t b_lo0 = ((smem_u32(b_ring) >> 4) & 0x3FFF) | (1u << 16);
+      const uint32_t bar_a_full0 = smem_u32(bar_a_full), bar_a_empty0 = smem_u32(bar_a_empty);
+      const uint32_t bar_b_full0 = smem_u32(bar_b_full), bar_b_empty0 = smem_u32(bar_b_empty);
+      const uint32_t d = tmem_base + (uint32_t)(t * Cfg::ACC_STRIDE);
+      const int nb = KS * NCHUNK;
+      int stage = t % SA, bs = 0;
+      uint32_t a_phase = (uint32_t)((t / SA) & 1), b_phase = 0;
+      for (int b = 0; b < nb; ++b) {
+        mbar_wait(bar_b_full0 + 8 * bs, b_phase);
+        mbar_wait(bar_a_full0 + 8 * stage, a_phase);
+        tc_fence_after();
         const uint32_t a_hi = tmem_a0 + (uint32_t)(stage * A_COLS);
         const uint32_t b_lo = b_lo0 + (uint32_t)bs * (B_STAGE >> 4);
-        const uint32_t d = tmem_base + (uint32_t)(t * COUT);
+        const uint32_t acc0 = b == 0 ? 0u : 1u;
+        if (S2D_DBG(A, 4)) {
+        } else if constexpr (PASSES == 2) {
+          // corrections first (small terms): 64 BF16 k positions = 32 TMEM columns, 128 B of every B row
 #pragma unroll
-        for (int q = 0; q < kBK / 8; ++q) {   // UMMA K = 8 for TF32: 8 TMEM columns of A, 32 B of every B row
-          const uint64_t db_hi = ((uint64_t)desc_hi << 32) | (b_lo + 2 * q);
-          if constexpr (PASSES == 3) {
-            const uint64_t db_lo = ((uint64_t)desc_hi << 32) | (b_lo + (B_TILE >> 4) + 2 * q);
-            umma_tf32_ts(d, a_hi + kBK + 8 * q, db_hi, idesc, q == 0 ? (first ^ 1u) : 1u);   // small terms first
-            umma_tf32_ts(d, a_hi + 8 * q, db_lo, idesc, 1);
-            umma_tf32_ts(d, a_hi + 8 * q, db_hi, idesc, 1);
-          } else {
-            umma_tf32_ts(d, a_hi + 8 * q, db_hi, idesc, q == 0 ? (first ^ 1u) : 1u);
+          for (int q = 0; q < 4; ++q) {
+            const uint64_t db = ((uint64_t)desc_hi << 32) | (b_lo + (B_TILE >> 4) + 2 * q);
+            umma_bf16_ts(d, a_hi + kBK + 8 * q, db, idesc16, q == 0 ? acc0 : 1u);
+          }
+#pragma unroll
+          for (int q = 0; q < kBK / 8; ++q) {
+            const uint64_t db = ((uint64_t)desc_hi << 32) | (b_lo + 2 * q);
+            umma_tf32_ts(d, a_hi + 8 * q, db, idesc, 1);
+          }
+        } else {
+#pragma unroll
+          for (int q = 0; q < kBK / 8; ++q) {   // UMMA K = 8 for TF32: 8 TMEM columns of A, 32 B of every B row
+            const uint64_t db_hi = ((uint64_t)desc_hi << 32) | (b_lo + 2 * q);
+            if constexpr (PASSES == 3) {
+              const uint64_t db_lo = ((uint64_t)desc_hi << 32) | (b_lo + (B_TILE >> 4) + 2 * q);
+              umma_tf32_ts(d, a_hi + kBK + 8 * q, db_hi, idesc, q == 0 ? acc0 : 1u);   // small terms first
+              umma_tf32_ts(d, a_hi + 8 * q, db_lo, idesc, 1);
+              umma_tf32_ts(d, a_hi + 8 * q, db_hi, idesc, 1);
+            } else {
+              umma_tf32_ts(d, a_hi + 8 * q, db_hi, idesc, q == 0 ? acc0 : 1u);
+            }
           }
         }
         umma_commit(bar_a_empty0 + 8 * stage);                  // gathered tile reusable once read
-        if (t == T - 1) umma_commit(bar_b_empty0 + 8 * bs);     // weight tile reusable
-        if (s == nsteps - 1) umma_commit(smem_u32(bar_accum));  // all accumulators complete
-      }
-      __syncwarp();
-      if (++stage == SA) { stage = 0; a_phase ^= 1; }
-      if (++t == T) {
-        t = 0;
-        first = 0;                                              // every tile has seen its first (k=0,c=0) MMA
+        umma_commit(bar_b_empty0 + 8 * bs);                     // weight tile: one of T arrivals
+        if (b == nb - 1) umma_commit(smem_u32(bar_accum));      // this tile's accumulator complete
+        stage += T;
+        while (stage >= SA) { stage -= SA; a_phase ^= 1; }
         if (++bs == SB) { bs = 0; b_phase ^= 1; }
       }
     }
@@ -506,35 +663,66 @@ __global__ void __launch_bounds__(kTcThreads, 1) spconv_tc_kernel(const __grid_c
 }
 
 // ---------------------------------------------------------------------------------------------
-// weight packing: W [K, Cin, Cout] -> per (cout block, k, chunk): [hi tile | lo tile], each CB rows x 32 fp32 in
-// the exact shared-memory image the kernel's B descriptor expects (K-major, 128B swizzle, K permuted like
-// the TMEM A layout), TF32-rounded.
+// weight packing: W [K, Cin, Cout] -> per (cout block, contraction step): [tile 0 | tile 1], each CB rows x 128 B
+// in the exact shared-memory image the kernel's B descriptor expects (K-major, 128B swizzle, k permuted like
+// the TMEM A layout).  tile 0 = TF32(w).  tile 1 = TF32(w - tile0) for the TF32 / TF32X3 modes, or the BF16
+// pair [bf16(w) | bf16(w - tile0)] (64 k positions) for the BF16-correction mode.
 // ---------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) pack_weights_kernel(const float* __restrict__ W, int K, int Cin, int Cout,
-                                                           int CB, float* __restrict__ packed) {
+                                                           int CB, int kps, int nchunk, int ksteps, int bf16c,
+                                                           float* __restrict__ packed) {
   const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  const long long total = (long long)K * Cin * Cout;
+  const int nstep = ksteps * nchunk;
+  const long long total = (long long)(Cout / CB) * nstep * CB * kBK;
   if (idx >= total) return;
-  const int co = (int)(idx % Cout);
-  const int ci = (int)((idx / Cout) % Cin);
-  const int k = (int)(idx / ((long long)Cout * Cin));
-  const float w = W[idx];
+  const int kk32 = (int)(idx % kBK);
+  const int n = (int)((idx / kBK) % CB);
+  const int step = (int)((idx / ((long long)kBK * CB)) % nstep);
+  const int blk = (int)(idx / ((long long)kBK * CB * nstep));
+  int k, ci;
+  if (kps == 1) {
+    k = step / nchunk;
+    ci = (step % nchunk) * kBK + kk32;
+  } else {
+    const int cs = kBK / kps;                                   // = Cin
+    k = step * kps + kk32 / cs;
+    ci = kk32 % cs;
+  }
+  const int co = blk * CB + n;
+  const float w = k < K ? W[((size_t)k * Cin + ci) * Cout + co] : 0.f;
   const float hi = tf32_rna(w);
-  const float lo = tf32_rna(w - hi);
-  const int c = ci / kBK, kk = ci % kBK;
-  const int nchunk = Cin / kBK;
-  const int blk = co / CB, n = co % CB;
+  const float lo = w - hi;
   const size_t tile = (size_t)CB * kBK;                         // floats per tile
-  const size_t base = ((size_t)(blk * K + k) * nchunk + c) * 2 * tile;
-  const int col = a_col_of_channel(kk);                         // K position the MMA sees (matches the TMEM A layout)
+  const size_t base = ((size_t)blk * nstep + step) * 2 * tile;
+  const int col = a_col_of_channel(kk32);                       // k position the TF32 MMA sees (matches the TMEM A layout)
   const size_t pos = (sw128_chunk_offset(n, col >> 2) >> 2) + (col & 3);
   packed[base + pos] = hi;
-  packed[base + tile + pos] = lo;
+  if (!bf16c) {
+    packed[base + tile + pos] = tf32_rna(lo);
+  } else {
+    __nv_bfloat16* t1 = reinterpret_cast<__nv_bfloat16*>(packed + base + tile);
+    const int kp = bf16_kpos_of_channel(kk32);                  // [0,32): pairs with A_lo; +32: pairs with A
+    t1[(sw128_chunk_offset(n, kp >> 3) >> 1) + (kp & 7)] = __float2bfloat16_rn(w);
+    t1[(sw128_chunk_offset(n, (kp + 32) >> 3) >> 1) + (kp & 7)] = __float2bfloat16_rn(lo);
+  }
 }
 
-static int cout_block(int Cout) { return Cout % 128 == 0 ? 128 : (Cout % 64 == 0 ? 64 : (Cout % 32 == 0 ? 32 : 0)); }
+static int g_tc_debug = 0;
 
-static bool tc_supported(int Cin, int Cout) { return Cin >= kBK && Cin % kBK == 0 && cout_block(Cout) != 0; }
+static int cout_block(int Cout) {
+  return Cout % 128 == 0 ? 128 : (Cout % 64 == 0 ? 64 : (Cout % 32 == 0 ? 32 : (Cout % 16 == 0 ? 16 : 0)));
+}
+static int kps_of(int Cin) { return Cin == 16 ? 2 : 1; }
+// S2D_PRECISION_AUTO: both modes have fp32-level accuracy; the BF16-correction mode needs 2/3 of the tensor time
+// but twice the conversion instructions in the producer warps, so it only wins where the layer is tensor bound.
+static int resolve_precision(int precision, int Cout) {
+  if (precision != S2D_PRECISION_AUTO) return precision;
+  return cout_block(Cout) >= 128 ? S2D_PRECISION_TF32_BF16C : S2D_PRECISION_TF32X3;
+}
+
+static bool tc_supported(int Cin, int Cout) {
+  return (Cin == 16 || (Cin >= kBK && Cin % kBK == 0)) && cout_block(Cout) != 0;
+}
 
 template <int COUT, int PASSES>
 static int launch_tc(const ConvArgs& a, int Cout, cudaStream_t st) {
@@ -552,42 +740,68 @@ static int launch_tc(const ConvArgs& a, int Cout, cudaStream_t st) {
   return S2D_OK;
 }
 
+template <int COUT>
+static int launch_tc_prec(const ConvArgs& a, int Cout, int precision, cudaStream_t st) {
+  if (precision == S2D_PRECISION_TF32X3) return launch_tc<COUT, 3>(a, Cout, st);
+  if (precision == S2D_PRECISION_TF32_BF16C) return launch_tc<COUT, 2>(a, Cout, st);
+  return launch_tc<COUT, 1>(a, Cout, st);
+}
+
 int conv_fwd_tf32(const s2d_conv_params& p, cudaStream_t st) {
   if (!tc_supported(p.Cin, p.Cout)) {
-    set_error("s2d_conv_fwd: no tcgen05 kernel for Cin=%d Cout=%d (need Cin %% 32 == 0 and Cout %% 32 == 0)", p.Cin,
-              p.Cout);
+    set_error("s2d_conv_fwd: no tcgen05 kernel for Cin=%d Cout=%d (need Cin == 16 or Cin %% 32 == 0, Cout %% 16 == 0)",
+              p.Cin, p.Cout);
     return S2D_ERR_UNSUPPORTED;
   }
   S2D_REQUIRE(p.in_ld % 4 == 0 && p.out_ld % 4 == 0 && (!p.residual || p.res_ld % 4 == 0),
               "s2d_conv_fwd: row strides must be multiples of 4 floats");
+  S2D_REQUIRE((unsigned long long)p.n_in * (unsigned long long)p.in_ld * 4ull < (1ull << 32),
+              "s2d_conv_fwd: input tensor larger than 4 GiB (32-bit gather offsets)");
   ConvArgs a;
   a.in = p.in; a.packed = p.weights; a.tbl = p.tbl; a.scale = p.scale; a.shift = p.shift; a.residual = p.residual;
   a.out = p.out; a.out_rows = p.out_rows; a.in_ld = p.in_ld; a.out_ld = p.out_ld; a.res_ld = p.res_ld;
-  a.tbl_stride = p.tbl_stride; a.n_out = p.n_out; a.K = p.K; a.nchunk = p.Cin / kBK; a.act = p.act;
+  a.tbl_stride = p.tbl_stride; a.n_out = p.n_out; a.K = p.K; a.kps = kps_of(p.Cin);
+  a.nchunk = a.kps == 1 ? p.Cin / kBK : 1; a.ksteps = div_up(p.K, a.kps); a.act = p.act;
   a.res_after_act = p.res_after_act;
+  a.dbg = g_tc_debug;
   const int cb = cout_block(p.Cout);
-  const bool x3 = p.precision == S2D_PRECISION_TF32X3;
-  if (cb == 128) return x3 ? launch_tc<128, 3>(a, p.Cout, st) : launch_tc<128, 1>(a, p.Cout, st);
-  if (cb == 64) return x3 ? launch_tc<64, 3>(a, p.Cout, st) : launch_tc<64, 1>(a, p.Cout, st);
-  return x3 ? launch_tc<32, 3>(a, p.Cout, st) : launch_tc<32, 1>(a, p.Cout, st);
+  const int prec = resolve_precision(p.precision, p.Cout);
+  if (cb == 128) return launch_tc_prec<128>(a, p.Cout, prec, st);
+  if (cb == 64) return launch_tc_prec<64>(a, p.Cout, prec, st);
+  if (cb == 32) return launch_tc_prec<32>(a, p.Cout, prec, st);
+  return launch_tc_prec<16>(a, p.Cout, prec, st);
 }
 
 }  // namespace s2d
 
 using namespace s2d;
 
+// ablation switches of the tcgen05 kernel (profiling aid, see ConvArgs::dbg); not part of the public header
+extern "C" void s2d_debug_tc_flags(int flags) { g_tc_debug = flags; }
+
 extern "C" int s2d_spconv_tf32_supported(int Cin, int Cout) { return tc_supported(Cin, Cout) ? 1 : 0; }
 
 extern "C" size_t s2d_spconv_packed_bytes(int K, int Cin, int Cout) {
   if (K < 1 || !tc_supported(Cin, Cout)) return 0;
-  return (size_t)K * Cin * Cout * 2 * sizeof(float);
+  const int kps = kps_of(Cin);
+  const int nchunk = kps == 1 ? Cin / kBK : 1;
+  return (size_t)div_up(K, kps) * nchunk * kBK * Cout * 2 * sizeof(float);
 }
 
-extern "C" int s2d_spconv_pack_weights(const float* W, int K, int Cin, int Cout, float* packed, void* stream) {
+extern "C" int s2d_spconv_pack_weights(const float* W, int K, int Cin, int Cout, int precision, float* packed,
+                                       void* stream) {
   S2D_REQUIRE(W && packed && K >= 1 && K <= kTcMaxK, "s2d_spconv_pack_weights: bad argument");
   S2D_REQUIRE(tc_supported(Cin, Cout), "s2d_spconv_pack_weights: unsupported shape Cin=%d Cout=%d", Cin, Cout);
-  pack_weights_kernel<<<div_up((long long)K * Cin * Cout, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
-      W, K, Cin, Cout, cout_block(Cout), packed);
+  precision = resolve_precision(precision, Cout);
+  S2D_REQUIRE(precision == S2D_PRECISION_TF32 || precision == S2D_PRECISION_TF32X3 ||
+                  precision == S2D_PRECISION_TF32_BF16C,
+              "s2d_spconv_pack_weights: precision %d has no packed image", precision);
+  const int kps = kps_of(Cin);
+  const int nchunk = kps == 1 ? Cin / kBK : 1;
+  const int ksteps = div_up(K, kps);
+  const long long total = (long long)ksteps * nchunk * kBK * Cout;
+  pack_weights_kernel<<<div_up(total, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      W, K, Cin, Cout, cout_block(Cout), kps, nchunk, ksteps, precision == S2D_PRECISION_TF32_BF16C ? 1 : 0, packed);
   S2D_LAUNCH_CHECK();
   count_launches(1);
   return S2D_OK;

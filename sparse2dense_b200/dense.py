@@ -101,7 +101,7 @@ def conv_rows(x, weight_kio, tbl, n_out, scale=None, shift=None, act=ACT_NONE, r
     use_tc = precision != ops.PRECISION_FP32 and ops.tf32_supported(cin, cout)
     w = weight_kio
     if use_tc:
-        w = packed if packed is not None else ops.pack_weights_tf32(weight_kio)
+        w = packed if packed is not None else ops.pack_weights_tf32(weight_kio, precision)
     p = _lib.ConvParams()
     p.in_, p.weights, p.tbl = x.data_ptr(), w.data_ptr(), tbl.data_ptr()
     p.scale = None if scale is None else scale.data_ptr()
@@ -167,7 +167,7 @@ class DenseOps:
                 kio = torch.stack(taps, 0).contiguous()       # [K, Cin, Cout]
             packed = None
             if self.precision != ops.PRECISION_FP32 and ops.tf32_supported(kio.shape[1], kio.shape[2]):
-                packed = ops.pack_weights_tf32(kio)
+                packed = ops.pack_weights_tf32(kio, self.precision)
             return kio, packed
         return self.cache.get(("w", name, transposed_class, self.precision), [conv.weight], build)
 

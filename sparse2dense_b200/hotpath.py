@@ -70,7 +70,7 @@ class FullForwardPath(VoxelBackbonePath):
                     weight=2, code_weights=[1.0] * 8,
                     common_heads={"reg": (2, 2), "height": (1, 2), "dim": (3, 2), "rot": (2, 2)})
 
-    def __init__(self, state=None, neck_state=None, head_state=None, precision=ops.PRECISION_TF32X3, device="cuda"):
+    def __init__(self, state=None, neck_state=None, head_state=None, precision=ops.PRECISION_AUTO, device="cuda"):
         super().__init__(state=state, precision=precision, device=device)
         import logging
         self.neck = registry.build_neck(dict(logger=logging.getLogger("RPN"), **self.NECK_CFG))

@@ -12,6 +12,10 @@ from . import _lib
 PRECISION_FP32 = 0
 PRECISION_TF32 = 1
 PRECISION_TF32X3 = 2
+PRECISION_TF32_BF16C = 3      # TF32 main term + BF16 correction terms: TF32X3 accuracy class at 2/3 of the tensor time
+PRECISION_AUTO = 4            # the library picks TF32_BF16C or TF32X3 per layer shape (both fp32-level accuracy)
+PRECISION_NAMES = {"fp32": PRECISION_FP32, "tf32": PRECISION_TF32, "tf32x3": PRECISION_TF32X3,
+                   "tf32_bf16c": PRECISION_TF32_BF16C, "auto": PRECISION_AUTO}
 
 
 # When set to a list, spconv_fwd appends (key, start_event, end_event) per launch so that bench.py can
@@ -269,7 +273,7 @@ def spconv_fwd(feats, weight, tbl, n_out, scale=None, shift=None, residual=None,
         assert t is None or (t.dtype == torch.float32 and t.is_contiguous())
     w_arg = weight
     if precision != PRECISION_FP32:
-        w_arg = packed if packed is not None else pack_weights_tf32(weight)
+        w_arg = packed if packed is not None else pack_weights_tf32(weight, precision)
     ev = None
     if KERNEL_EVENTS is not None:
         ev = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
@@ -287,9 +291,10 @@ def tf32_supported(cin, cout):
     return bool(_lib.load().s2d_spconv_tf32_supported(int(cin), int(cout)))
 
 
-def pack_weights_tf32(weight):
-    """Weights [kD,kH,kW,Cin,Cout] -> the pre-split (TF32 hi/lo), pre-swizzled shared-memory image the
-    tcgen05 kernel bulk-copies per (offset, 32-channel chunk).  Done once per layer."""
+def pack_weights_tf32(weight, precision=PRECISION_TF32X3):
+    """Weights [kD,kH,kW,Cin,Cout] -> the pre-split, pre-swizzled shared-memory image the tcgen05 kernel
+    bulk-copies per contraction step (TF32 hi | TF32 lo, or TF32 hi | BF16 [w | lo] for PRECISION_TF32_BF16C).
+    Done once per layer and precision."""
     _need_cuda(weight)
     weight = weight.detach().contiguous().float()
     cin, cout = weight.shape[-2], weight.shape[-1]
@@ -298,7 +303,7 @@ def pack_weights_tf32(weight):
     if nbytes == 0:
         raise _lib.S2DError(f"no tcgen05 packing for Cin={cin} Cout={cout}")
     packed = torch.empty((nbytes // 4,), dtype=torch.float32, device=weight.device)
-    _lib.check(_lib.load().s2d_spconv_pack_weights(_ptr(weight), k, cin, cout, _ptr(packed), _stream()),
+    _lib.check(_lib.load().s2d_spconv_pack_weights(_ptr(weight), k, cin, cout, int(precision), _ptr(packed), _stream()),
                "s2d_spconv_pack_weights")
     return packed
 

@@ -178,9 +178,10 @@ class SparseConvolution(SparseModule):
         return cache[1], cache[2]
 
     def _packed_weights(self):
-        key = (self.weight.data_ptr(), self.weight._version, str(self.weight.device))
+        key = (self.weight.data_ptr(), self.weight._version, str(self.weight.device),
+               self.precision)
         if self._packed is None or self._packed[0] != key:
-            self._packed = (key, ops.pack_weights_tf32(self.weight))
+            self._packed = (key, ops.pack_weights_tf32(self.weight, self.precision))
         return self._packed[1]
 
 

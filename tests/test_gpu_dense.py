@@ -38,7 +38,7 @@ def test_conv_table_matches_unfold_geometry(k, s, p):
                 assert t[ky * k + kx, o] == want
 
 
-@pytest.mark.parametrize("precision,tol", [(ops.PRECISION_FP32, 1e-5), (ops.PRECISION_TF32X3, 2e-5),
+@pytest.mark.parametrize("precision,tol", [(ops.PRECISION_FP32, 1e-5), (ops.PRECISION_TF32X3, 2e-5), (ops.PRECISION_AUTO, 2e-5),
                                            (ops.PRECISION_TF32, 3e-3)])
 @pytest.mark.parametrize("kind", ["c3s1", "c3s2", "c2s2", "c1", "t4", "t2"])
 def test_dense_conv_ops_vs_torch(kind, precision, tol):
@@ -104,7 +104,8 @@ def test_dense_bev_nhwc_matches_nchw_form():
     assert torch.equal(dense.to_nchw(rows, B, H, W), nchw)
 
 
-@pytest.mark.parametrize("precision,tol", [(ops.PRECISION_TF32X3, 1e-3), (ops.PRECISION_TF32, 2e-2)])
+@pytest.mark.parametrize("precision,tol", [(ops.PRECISION_TF32X3, 1e-3), (ops.PRECISION_AUTO, 1e-3),
+                                           (ops.PRECISION_TF32, 2e-2)])
 def test_s2d_rpn_and_center_head_full_size_vs_oracle_and_reference_samples(precision, tol):
     g = np.load(os.path.join(GOLDEN, "neck_head_s2d.npz"))
     neck, head = build_modules()

@@ -1,7 +1,8 @@
 """GPU parity of the tcgen05 (TF32) sparse conv kernels through the C ABI vs the fp64-accumulating oracle.
 
 Tolerances (relative to the output scale, north_star bar = 1e-3):
-  TF32X3 (split hi/lo, 3 MMAs): 2e-5  -- this is the mode the backbone uses to meet the bar
+  TF32X3 (split hi/lo, 3 MMAs): 2e-5
+  TF32_BF16C (TF32 hi*hi + BF16 correction terms): 2e-5  -- the mode the backbone ships with
   TF32   (single pass)        : 3e-3 per layer (documented as a fast, reduced-precision mode)
 """
 import numpy as np
@@ -13,7 +14,7 @@ from oracle import ref_ops as R
 from sparse2dense_b200 import ops, registry, synth
 
 pytestmark = pytest.mark.gpu
-SHAPES = [(32, 32), (32, 64), (64, 64), (64, 128), (128, 128)]
+SHAPES = [(16, 16), (16, 32), (32, 32), (32, 64), (64, 64), (64, 128), (128, 128)]
 
 
 def rel_err(a, b):
@@ -31,7 +32,8 @@ def make_case(cin, cout, n, seed, ks=(3, 3, 3)):
 
 
 @pytest.mark.parametrize("cin,cout", SHAPES)
-@pytest.mark.parametrize("precision,tol", [(ops.PRECISION_TF32X3, 2e-5), (ops.PRECISION_TF32, 3e-3)])
+@pytest.mark.parametrize("precision,tol", [(ops.PRECISION_TF32X3, 2e-5), (ops.PRECISION_TF32_BF16C, 2e-5),
+                                           (ops.PRECISION_TF32, 3e-3)])
 @pytest.mark.parametrize("fused", [False, True])
 def test_tc_subm_vs_oracle(cin, cout, precision, tol, fused):
     assert ops.tf32_supported(cin, cout)
@@ -56,7 +58,8 @@ def test_tc_subm_vs_oracle(cin, cout, precision, tol, fused):
 
 
 def test_tc_strided_and_k3_vs_oracle():
-    for (cin, cout, ks, st, pd) in [(32, 64, 3, 2, 1), (64, 128, 3, 2, (0, 1, 1)), (128, 128, (3, 1, 1), (2, 1, 1), 0)]:
+    for (cin, cout, ks, st, pd) in [(16, 32, 3, 2, 1), (32, 64, 3, 2, 1), (64, 128, 3, 2, (0, 1, 1)),
+                                    (128, 128, (3, 1, 1), (2, 1, 1), 0)]:
         kst = (ks,) * 3 if isinstance(ks, int) else ks
         shape, batch, coors, feats, w = make_case(cin, cout, 2500, 5, kst)
         oc, rt, oshape, _ = R.rulebook_sparse(coors, shape, ks, st, pd)
@@ -66,9 +69,10 @@ def test_tc_strided_and_k3_vs_oracle():
         tbl = ops.rulebook_sparse(sc.coors, idx, ks, st, pd)
         np.testing.assert_array_equal(tbl.cpu().numpy(), rt)
         ref = R.spconv_fwd(feats, w, rt, wide=True)
-        out = ops.spconv_fwd(torch.from_numpy(feats).cuda(), torch.from_numpy(w).cuda(), tbl, len(oc),
-                             precision=ops.PRECISION_TF32X3)
-        assert rel_err(out.cpu().numpy(), ref) < 2e-5, (cin, cout)
+        for prec in (ops.PRECISION_TF32X3, ops.PRECISION_TF32_BF16C):
+            out = ops.spconv_fwd(torch.from_numpy(feats).cuda(), torch.from_numpy(w).cuda(), tbl, len(oc),
+                                 precision=prec)
+            assert rel_err(out.cpu().numpy(), ref) < 2e-5, (cin, cout, prec)
 
 
 def test_tc_matches_fp32_kernel_and_is_deterministic():
@@ -90,7 +94,7 @@ def test_backbone_tf32x3_full_size_scene_vs_oracle():
     bb.load_state_dict({k: torch.from_numpy(v) for k, v in state.items()}, strict=False)
     bb = bb.cuda().eval()
     bb.set_precision(ops.PRECISION_TF32X3)
-    assert bb.conv4[3].conv1.precision == ops.PRECISION_TF32X3 and bb.conv1[0].conv1.precision == ops.PRECISION_FP32
+    assert bb.conv4[3].conv1.precision == ops.PRECISION_TF32X3 and bb.conv_input[0].precision == ops.PRECISION_FP32
     cloud = synth.lidar_scene(1000)
     vb = ops.voxelize(torch.from_numpy(cloud).cuda(), [0, len(cloud)], synth.WAYMO_VOXEL, synth.WAYMO_RANGE, 5, 150000,
                       want_voxels=False, mean_channels=5)
@@ -103,6 +107,13 @@ def test_backbone_tf32x3_full_size_scene_vs_oracle():
     err = rel_err(bev.cpu().numpy(), ref_bev)
     print("tf32x3 backbone rel err", err)
     assert err < 1e-3
+    for mode in (ops.PRECISION_TF32_BF16C, ops.PRECISION_AUTO):
+        bb.set_precision(mode)
+        with torch.no_grad():
+            bev2, _ = bb(vb.mean, vb.coors, 1, [1504, 1504, 40])
+        err2 = rel_err(bev2.cpu().numpy(), ref_bev)
+        print("precision mode", mode, "backbone rel err", err2)
+        assert err2 < 1e-3
     bb.set_precision(ops.PRECISION_TF32)
     with torch.no_grad():
         bev1, _ = bb(vb.mean, vb.coors, 1, [1504, 1504, 40])

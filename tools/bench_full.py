@@ -1,6 +1,6 @@
 #!/usr/bin/env python
 """Timing of the full forward built so far (voxelize -> backbone -> S2D_RPN -> CenterHead maps), per stage.
-usage: bench_full.py [--batch 4] [--steps 5] [--precision tf32x3]"""
+usage: bench_full.py [--batch 4] [--steps 5] [--precision auto]"""
 import argparse
 import os
 import sys
@@ -17,9 +17,9 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--batch", type=int, default=4)
     ap.add_argument("--steps", type=int, default=5)
-    ap.add_argument("--precision", default="tf32x3")
+    ap.add_argument("--precision", default="auto")
     a = ap.parse_args()
-    prec = {"fp32": ops.PRECISION_FP32, "tf32": ops.PRECISION_TF32, "tf32x3": ops.PRECISION_TF32X3}[a.precision]
+    prec = ops.PRECISION_NAMES[a.precision]
     path = FullForwardPath(state=synth.backbone_state(0), precision=prec)
     path.neck.load_state_dict({k: torch.as_tensor(v) for k, v in synth.random_module_state(path.neck, 11).items()}, strict=False)
     path.head.load_state_dict({k: torch.as_tensor(v) for k, v in synth.random_module_state(path.head, 12).items()}, strict=False)

@@ -19,9 +19,9 @@ def main():
     ap.add_argument("--batch", type=int, default=4)
     ap.add_argument("--reps", type=int, default=10)
     ap.add_argument("--only", type=int, default=0)
-    ap.add_argument("--precisions", default="fp32,tf32,tf32x3")
+    ap.add_argument("--precisions", default="fp32,tf32,tf32x3,tf32_bf16c")
     args = ap.parse_args()
-    prec = {"fp32": ops.PRECISION_FP32, "tf32": ops.PRECISION_TF32, "tf32x3": ops.PRECISION_TF32X3}
+    prec = ops.PRECISION_NAMES
     clouds = synth.lidar_batch(1, args.batch)
     pts, offs = concat_clouds(clouds)
     vb = ops.voxelize(pts.cuda(), offs, synth.WAYMO_VOXEL, synth.WAYMO_RANGE, 5, 150000, want_voxels=False,
@@ -46,7 +46,7 @@ def main():
             pr = prec[name]
             if pr != ops.PRECISION_FP32 and not ops.tf32_supported(c, c):
                 continue
-            packed = ops.pack_weights_tf32(w) if pr != ops.PRECISION_FP32 else None
+            packed = ops.pack_weights_tf32(w, pr) if pr != ops.PRECISION_FP32 else None
             out = ops.spconv_fwd(feats, w, tbl, n, precision=pr, packed=packed)
             torch.cuda.synchronize()
             ms = []
