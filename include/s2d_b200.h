@@ -228,6 +228,75 @@ int s2d_dense_bev_nhwc(const float* feat, const int* coors, int n_rows, int C, i
 int s2d_dense_bev(const float* feat, const int* coors, int n_rows, int C, int batch, int D, int H, int W,
                   float* bev, void* stream);
 
+/* ---------------------------------------------------------------------------------------
+ * CenterHead.predict on the device (det3d/models/bbox_heads/center_head.py:293-495, one task, no
+ * double flip): decode -> score / range masks -> top nms_pre_max_size by score -> rotated-BEV NMS
+ * -> first nms_post_max_size survivors.  Replaces the eager torch ops of predict/post_processing,
+ * rotate_nms_pcdet (det3d/core/bbox/box_torch_ops.py:449-470) and iou3d_nms_cuda.nms_gpu
+ * (det3d/ops/iou3d_nms/src/iou3d_nms_api.cpp:11-17, iou3d_nms.cpp:90-136, kernel
+ * iou3d_nms_kernel.cu:267-311), which copies the suppression mask to the host and sweeps it on
+ * the CPU; nothing here leaves the device or synchronises.
+ *
+ * s2d_centerhead_decode: head maps as NHWC rows (row = (b*H + y)*W + x, row strides ld_* in floats,
+ *   so the channel slices of one fused head-output buffer can be passed directly):
+ *     score = max_c sigmoid(hm[c]) (first maximum), label = argmax, box = [x, y, height, exp(dim[0..2]),
+ *     atan2(rot[0], rot[1])] with x = (col + reg[0]) * out_size_factor * voxel_x + pc_x (fp32 steps as in
+ *     center_head.py:393-401); key = 0 unless score > score_threshold and the centre lies in `range`
+ *     (post_center_limit_range), else (score bits << 32) | (0xFFFFFFFF - cell): descending key order =
+ *     descending score, ties by ascending cell.
+ *   boxes f32 [B*H*W,7], scores f32 [B*H*W], labels i32 [B*H*W], keys u64 [B*H*W].
+ * s2d_centerhead_select: per sample the first `pre_max` (<= 4096) keys in descending order, NMS at
+ *   iou_threshold, at most post_max survivors gathered to out_* [batch, post_max, ...] (rows past
+ *   n_out[b] are zero / -1); out_cells (nullable) = BEV cell of each detection.
+ * s2d_nms_sorted: drop-in for nms_gpu(boxes sorted by descending score, keep, thresh): keep i32 [n],
+ *   *n_keep on the device; n <= 4096 (rotate_nms_pcdet never passes more than nms_pre_max_size).
+ * s2d_iou_bev: pairwise rotated-BEV IoU [n_a, n_b] (boxes_iou_bev_gpu of the same extension).
+ * ------------------------------------------------------------------------------------- */
+typedef struct s2d_decode_params {
+  const float* reg;
+  const float* height;
+  const float* dim;
+  const float* rot;
+  const float* hm;
+  int ld_reg, ld_height, ld_dim, ld_rot, ld_hm;
+  int B, H, W, num_cls;
+  float out_size_factor, voxel_x, voxel_y, pc_x, pc_y;
+  float score_threshold;
+  float range[6];
+} s2d_decode_params;
+int s2d_centerhead_decode(const s2d_decode_params* params, float* boxes, float* scores, int* labels,
+                          unsigned long long* keys, void* stream);
+size_t s2d_centerhead_select_workspace_bytes(int batch, int pre_max, int post_max);
+int s2d_centerhead_select(const unsigned long long* keys, const float* boxes, const float* scores,
+                          const int* labels, int batch, int cells, int pre_max, float iou_threshold,
+                          int post_max, float* out_boxes, float* out_scores, int* out_labels, int* out_cells,
+                          int* n_out, void* workspace, size_t workspace_bytes, void* stream);
+size_t s2d_nms_workspace_bytes(int n_boxes);
+int s2d_nms_sorted(const float* boxes, int n_boxes, float iou_threshold, int* keep, int* n_keep,
+                   void* workspace, size_t workspace_bytes, void* stream);
+int s2d_iou_bev(const float* boxes_a, int n_a, const float* boxes_b, int n_b, float* ious, void* stream);
+
+/* ---------------------------------------------------------------------------------------
+ * Second stage of the two-stage CenterPoint (det3d/models/detectors/two_stage.py:154-199).
+ *
+ * s2d_bev_box_features: for every first-stage box its centre and (num_point == 5) the four face
+ *   mid-points (two_stage.py:49-76, box_torch_ops.py:386-406) are sampled bilinearly from the BEV map
+ *   (bird_eye_view.py:24-40, center_utils.py:93-122 incl. the clamp-before-weights behaviour) and
+ *   concatenated per box: out f32 [batch*max_boxes, num_point*C] in the order centre, front, back,
+ *   left, right; slots p >= n_boxes[b] are zero (reorder_first_stage_pred_and_feature, :78-119).
+ *   bev: NHWC rows [batch*H*W, bev_ld] (no NCHW->NHWC copy of the map is needed); boxes f32
+ *   [batch, max_boxes, 7]; n_boxes device i32 [batch].
+ * s2d_roi_refine: generate_predicted_boxes (roi_head_template.py:153-183) + post_process
+ *   (two_stage.py:121-151): out_boxes = rotate_z(rcnn_reg + roi(xyz = 0), roi_yaw) + roi_xyz,
+ *   out_scores = sqrt(sigmoid(rcnn_cls) * roi_score); padded slots zero.
+ * ------------------------------------------------------------------------------------- */
+int s2d_bev_box_features(const float* bev, int bev_ld, int batch, int H, int W, int C, const float* boxes,
+                         const int* n_boxes, int max_boxes, int num_point, const float* pc_start_host,
+                         const float* voxel_size_host, float out_stride, float* out, void* stream);
+int s2d_roi_refine(const float* rois, const float* roi_scores, const int* n_boxes, int batch, int max_boxes,
+                   const float* rcnn_cls, int cls_ld, const float* rcnn_reg, int reg_ld, float* out_boxes,
+                   float* out_scores, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -155,3 +155,154 @@ def dense_bev(feats, coors, batch_size, spatial_shape):
     bev = np.zeros((batch_size, c * d, h, w), np.float32)
     lib().orc_dense_bev(_p(feats, _f32p), _p(coors, _i32p), feats.shape[0], c, d, h, w, _p(bev, _f32p))
     return bev
+
+
+# ------------------------------------------------------------------------------------------
+# CenterHead.predict: decode + post_processing + rotated NMS  (center_head.py:293-495,
+# box_torch_ops.py:449-470, iou3d_nms.cpp:90-136)
+# ------------------------------------------------------------------------------------------
+def iou_bev_matrix(a, b):
+    a, b = _f32(a), _f32(b)
+    out = np.empty((a.shape[0], b.shape[0]), np.float32)
+    lib().orc_iou_bev_matrix(_p(a, _f32p), a.shape[0], _p(b, _f32p), b.shape[0], _p(out, _f32p))
+    return out
+
+
+def nms_sorted(boxes, thresh):
+    """iou3d_nms_cuda.nms_gpu on score-sorted boxes [n,7] -> (keep indices int64, min |IoU - thresh| seen)."""
+    boxes = _f32(boxes)
+    n = boxes.shape[0]
+    keep = np.empty((max(n, 1),), np.int64)
+    margin = ctypes.c_float(0)
+    lib().orc_nms_sorted.restype = ctypes.c_int
+    nk = lib().orc_nms_sorted(_p(boxes, _f32p), n, ctypes.c_float(thresh), _p(keep, _i64p), ctypes.byref(margin))
+    return keep[:nk].copy(), float(margin.value)
+
+
+def centerhead_decode(preds, out_size_factor, voxel_size, pc_range):
+    """center_head.py:342-419 for one task, without double flip.  preds: dict of NHWC float32 arrays
+    (reg [B,H,W,2], height [B,H,W,1], dim [B,H,W,3], rot [B,H,W,2], hm [B,H,W,C]) ->
+    (boxes [B,H*W,7], hm sigmoid [B,H*W,C])."""
+    f = np.float32
+    hm = (f(1) / (f(1) + np.exp(-preds["hm"].astype(f)))).astype(f)
+    dim = np.exp(preds["dim"].astype(f)).astype(f)
+    rot = np.arctan2(preds["rot"][..., 0:1].astype(f), preds["rot"][..., 1:2].astype(f)).astype(f)
+    B, H, W, C = hm.shape
+    ys, xs = np.meshgrid(np.arange(H, dtype=f), np.arange(W, dtype=f), indexing="ij")
+    xs = xs.reshape(1, -1, 1) + preds["reg"].reshape(B, H * W, 2)[:, :, 0:1].astype(f)
+    ys = ys.reshape(1, -1, 1) + preds["reg"].reshape(B, H * W, 2)[:, :, 1:2].astype(f)
+    xs = ((xs * f(out_size_factor)).astype(f) * f(voxel_size[0])).astype(f) + f(pc_range[0])
+    ys = ((ys * f(out_size_factor)).astype(f) * f(voxel_size[1])).astype(f) + f(pc_range[1])
+    boxes = np.concatenate([xs.astype(f), ys.astype(f), preds["height"].reshape(B, H * W, 1).astype(f),
+                            dim.reshape(B, H * W, 3), rot.reshape(B, H * W, 1)], axis=2)
+    return boxes.astype(f), hm.reshape(B, H * W, C)
+
+
+def post_processing(boxes, hm, score_threshold, post_center_range, iou_threshold, pre_max, post_max):
+    """center_head.py:450-495 + rotate_nms_pcdet for one sample: boxes [HW,7], hm [HW,C] (after sigmoid).
+    Ties in the score sort are broken by the lower cell index (torch.sort gives no guarantee).
+    -> dict(box3d_lidar, scores, label_preds, cells) + the NMS decision margin."""
+    scores = hm.max(axis=-1)
+    labels = hm.argmax(axis=-1)
+    r = np.asarray(post_center_range, np.float32)
+    mask = (scores > np.float32(score_threshold)) & (boxes[:, :3] >= r[:3]).all(1) & (boxes[:, :3] <= r[3:]).all(1)
+    cells = np.nonzero(mask)[0]
+    b, s, l = boxes[cells], scores[cells], labels[cells]
+    order = np.lexsort((cells, -s.astype(np.float64)))[:pre_max]
+    keep, margin = nms_sorted(b[order], iou_threshold)
+    sel = order[keep][:post_max]
+    return dict(box3d_lidar=b[sel], scores=s[sel], label_preds=l[sel], cells=cells[sel]), margin
+
+
+# ------------------------------------------------------------------------------------------
+# Second stage (two_stage.py:49-199, bird_eye_view.py:24-40, center_utils.py:93-122, roi_head.py:70-106,
+# roi_head_template.py:153-183).  PINNED by tests/golden/two_stage.npz, generated with the reference's own
+# modules imported through the shim (tests/golden/make_golden.py second).
+# ------------------------------------------------------------------------------------------
+def box_sample_points(boxes, num_point=5):
+    """get_box_center: [n,7] -> [num_point, n, 2] BEV points: centre, front, back, left, right."""
+    f = np.float32
+    boxes = boxes.astype(f)
+    c = boxes[:, :2]
+    if num_point == 1:
+        return c[None]
+    norm = np.array([[-0.5, -0.5], [-0.5, 0.5], [0.5, 0.5], [0.5, -0.5]], f)
+    corners = boxes[:, None, 3:5] * norm[None]
+    cs, sn = np.cos(boxes[:, 6]).astype(f), np.sin(boxes[:, 6]).astype(f)
+    x = corners[..., 0] * cs[:, None] + corners[..., 1] * sn[:, None]
+    y = corners[..., 0] * (-sn[:, None]) + corners[..., 1] * cs[:, None]
+    corners = np.stack([x, y], -1).astype(f) + c[:, None]
+    mid = lambda i, j: ((corners[:, i] + corners[:, j]) / f(2)).astype(f)  # noqa: E731
+    return np.stack([c, mid(0, 1), mid(2, 3), mid(0, 3), mid(1, 2)], 0)
+
+
+def bilinear_sample(im, x, y):
+    """bilinear_interpolate_torch: im [H,W,C], x/y [n] in cell units; indices clamped before the weights are formed."""
+    f = np.float32
+    x, y = x.astype(f), y.astype(f)
+    x0 = np.floor(x).astype(np.int64); x1 = x0 + 1
+    y0 = np.floor(y).astype(np.int64); y1 = y0 + 1
+    x0 = np.clip(x0, 0, im.shape[1] - 1); x1 = np.clip(x1, 0, im.shape[1] - 1)
+    y0 = np.clip(y0, 0, im.shape[0] - 1); y1 = np.clip(y1, 0, im.shape[0] - 1)
+    wa = (x1.astype(f) - x) * (y1.astype(f) - y)
+    wb = (x1.astype(f) - x) * (y - y0.astype(f))
+    wc = (x - x0.astype(f)) * (y1.astype(f) - y)
+    wd = (x - x0.astype(f)) * (y - y0.astype(f))
+    return (im[y0, x0] * wa[:, None] + im[y1, x0] * wb[:, None] + im[y0, x1] * wc[:, None] + im[y1, x1] * wd[:, None]).astype(f)
+
+
+def roi_features(bev_nhwc, boxes, pc_start, voxel_size, out_stride, num_point=5):
+    """One sample: bev [H,W,C], boxes [n,7] -> [n, num_point*C]."""
+    f = np.float32
+    pts = box_sample_points(boxes, num_point)
+    feats = []
+    for q in range(pts.shape[0]):
+        xs = ((pts[q][:, 0] - f(pc_start[0])) / f(voxel_size[0]) / f(out_stride)).astype(f)
+        ys = ((pts[q][:, 1] - f(pc_start[1])) / f(voxel_size[1]) / f(out_stride)).astype(f)
+        feats.append(bilinear_sample(bev_nhwc, xs, ys))
+    return np.concatenate(feats, 1)
+
+
+def _fc_chain(state, prefix, x, wide=True):
+    """Conv1d(k=1) [+ BatchNorm1d eval] [+ ReLU] chain of an nn.Sequential stored under ``prefix`` in ``state``."""
+    idx = sorted({int(k[len(prefix) + 1:].split(".")[0]) for k in state if k.startswith(prefix + ".")})
+    acc = np.float64 if wide else np.float32
+    i = 0
+    while i < len(idx):
+        j = idx[i]
+        w = state[f"{prefix}.{j}.weight"]
+        assert w.ndim == 3, "expected a Conv1d weight"
+        y = (x.astype(acc) @ w[:, :, 0].T.astype(acc))
+        if f"{prefix}.{j}.bias" in state:
+            y = y + state[f"{prefix}.{j}.bias"].astype(acc)
+        nxt = idx[i + 1] if i + 1 < len(idx) else None
+        if nxt is not None and f"{prefix}.{nxt}.running_mean" in state:
+            g, b = state[f"{prefix}.{nxt}.weight"], state[f"{prefix}.{nxt}.bias"]
+            m, v = state[f"{prefix}.{nxt}.running_mean"], state[f"{prefix}.{nxt}.running_var"]
+            y = (y - m) / np.sqrt(v.astype(acc) + 1e-5) * g + b
+            y = np.maximum(y, 0)                       # every BN of these heads is followed by ReLU
+            i += 2
+        else:
+            i += 1
+        x = y.astype(np.float32)
+    return x
+
+
+def roi_head_forward(state, feats):
+    """RoIHead.forward (eval): [n, 2560] -> (rcnn_cls [n,1], rcnn_reg [n,7]); ``state`` = RoIHead state dict (numpy)."""
+    shared = _fc_chain(state, "shared_fc_layer", feats)
+    return _fc_chain(state, "cls_layers", shared), _fc_chain(state, "reg_layers", shared)
+
+
+def roi_refine(rois, roi_scores, rcnn_cls, rcnn_reg):
+    """generate_predicted_boxes + post_process: -> (boxes [n,7], scores [n])."""
+    f = np.float32
+    rois, reg = rois.astype(f), rcnn_reg.astype(f)
+    cs, sn = np.cos(rois[:, 6]).astype(f), np.sin(rois[:, 6]).astype(f)
+    out = np.empty_like(rois)
+    out[:, 0] = reg[:, 0] * cs + reg[:, 1] * sn + rois[:, 0]
+    out[:, 1] = reg[:, 0] * (-sn) + reg[:, 1] * cs + rois[:, 1]
+    out[:, 2] = reg[:, 2] + rois[:, 2]
+    out[:, 3:7] = reg[:, 3:7] + rois[:, 3:7]
+    sg = (f(1) / (f(1) + np.exp(-rcnn_cls.reshape(-1).astype(f)))).astype(f)
+    return out, np.sqrt(sg * roi_scores.astype(f)).astype(f)

@@ -367,3 +367,131 @@ void orc_dense_bev(const float* feat, const int* coors, int N, int C, int D, int
       bev[((((size_t)c[0] * C + ch) * D + c[1]) * H + c[2]) * W + c[3]] = feat[(size_t)i * C + ch];
   }
 }
+
+/* ==========================================================================================
+ * Rotated-BEV IoU and greedy NMS  (CenterHead.predict -> rotate_nms_pcdet -> nms_gpu).
+ * Restates det3d/ops/iou3d_nms/src/iou3d_nms_kernel.cu:
+ *   cross / check_rect_cross (:36-50), check_in_box2d (:52-62, MARGIN 1e-2), intersection (:64-93,
+ *   EPS 1e-8), rotate_around_center (:95-99), point_cmp (:101-103), box_overlap (:105-226),
+ *   iou_bev (:228-235), and the host sweep of iou3d_nms.cpp:90-136 (keep box i iff no kept box
+ *   j < i has IoU(j, i) > thresh; boxes arrive sorted by descending score).
+ * PINNED: checked against the reference's own CPU twin (det3d/ops/iou3d_nms/src/iou3d_cpu.cpp,
+ * compiled unmodified into oracle/_ref by oracle/Makefile) and against tests/golden/iou_bev_*.npz
+ * generated from it.  All arithmetic in fp32, no contraction (-ffp-contract=off).
+ * ========================================================================================== */
+typedef struct { float x, y; } orc_pt;
+
+static inline float orc_cross2(orc_pt a, orc_pt b) { return a.x * b.y - a.y * b.x; }
+static inline float orc_cross3(orc_pt p1, orc_pt p2, orc_pt p0) {
+  return (p1.x - p0.x) * (p2.y - p0.y) - (p2.x - p0.x) * (p1.y - p0.y);
+}
+static inline float orc_minf(float a, float b) { return a > b ? b : a; }
+static inline float orc_maxf(float a, float b) { return a > b ? a : b; }
+
+static int orc_rect_cross(orc_pt p1, orc_pt p2, orc_pt q1, orc_pt q2) {
+  return orc_minf(p1.x, p2.x) <= orc_maxf(q1.x, q2.x) && orc_minf(q1.x, q2.x) <= orc_maxf(p1.x, p2.x) &&
+         orc_minf(p1.y, p2.y) <= orc_maxf(q1.y, q2.y) && orc_minf(q1.y, q2.y) <= orc_maxf(p1.y, p2.y);
+}
+
+static int orc_in_box2d(const float* box, orc_pt p) {
+  const float MARGIN = 1e-2f;
+  const float ac = cosf(-box[6]), as = sinf(-box[6]);
+  const float rx = (p.x - box[0]) * ac + (p.y - box[1]) * (-as);
+  const float ry = (p.x - box[0]) * as + (p.y - box[1]) * ac;
+  return fabsf(rx) < box[3] / 2 + MARGIN && fabsf(ry) < box[4] / 2 + MARGIN;
+}
+
+static int orc_intersection(orc_pt p1, orc_pt p0, orc_pt q1, orc_pt q0, orc_pt* ans) {
+  const float EPS = 1e-8f;
+  if (!orc_rect_cross(p0, p1, q0, q1)) return 0;
+  const float s1 = orc_cross3(q0, p1, p0), s2 = orc_cross3(p1, q1, p0);
+  const float s3 = orc_cross3(p0, q1, q0), s4 = orc_cross3(q1, p1, q0);
+  if (!(s1 * s2 > 0 && s3 * s4 > 0)) return 0;
+  const float s5 = orc_cross3(q1, p1, p0);
+  if (fabsf(s5 - s1) > EPS) {
+    ans->x = (s5 * q0.x - s1 * q1.x) / (s5 - s1);
+    ans->y = (s5 * q0.y - s1 * q1.y) / (s5 - s1);
+  } else {
+    const float a0 = p0.y - p1.y, b0 = p1.x - p0.x, c0 = p0.x * p1.y - p1.x * p0.y;
+    const float a1 = q0.y - q1.y, b1 = q1.x - q0.x, c1 = q0.x * q1.y - q1.x * q0.y;
+    const float D = a0 * b1 - a1 * b0;
+    ans->x = (b0 * c1 - b1 * c0) / D;
+    ans->y = (a1 * c0 - a0 * c1) / D;
+  }
+  return 1;
+}
+
+static void orc_corners(const float* box, orc_pt* c) {
+  const float hx = box[3] / 2, hy = box[4] / 2;
+  const float x1 = box[0] - hx, y1 = box[1] - hy, x2 = box[0] + hx, y2 = box[1] + hy;
+  const float ac = cosf(box[6]), as = sinf(box[6]);
+  const float px[4] = {x1, x2, x2, x1}, py[4] = {y1, y1, y2, y2};
+  for (int k = 0; k < 4; ++k) {
+    c[k].x = (px[k] - box[0]) * ac + (py[k] - box[1]) * (-as) + box[0];
+    c[k].y = (px[k] - box[0]) * as + (py[k] - box[1]) * ac + box[1];
+  }
+  c[4] = c[0];
+}
+
+float orc_box_overlap(const float* a, const float* b) {
+  orc_pt ca[5], cb[5], pts[16], ctr = {0.f, 0.f};
+  orc_corners(a, ca);
+  orc_corners(b, cb);
+  int cnt = 0;
+  for (int i = 0; i < 4; ++i)
+    for (int j = 0; j < 4; ++j)
+      if (orc_intersection(ca[i + 1], ca[i], cb[j + 1], cb[j], &pts[cnt])) {
+        ctr.x = ctr.x + pts[cnt].x; ctr.y = ctr.y + pts[cnt].y;
+        ++cnt;
+      }
+  for (int k = 0; k < 4; ++k) {
+    if (orc_in_box2d(a, cb[k])) { ctr.x = ctr.x + cb[k].x; ctr.y = ctr.y + cb[k].y; pts[cnt++] = cb[k]; }
+    if (orc_in_box2d(b, ca[k])) { ctr.x = ctr.x + ca[k].x; ctr.y = ctr.y + ca[k].y; pts[cnt++] = ca[k]; }
+  }
+  ctr.x /= cnt; ctr.y /= cnt;                          /* cnt == 0: NaN centre, empty loops below */
+  for (int j = 0; j < cnt - 1; ++j)                    /* bubble sort by angle about the centroid */
+    for (int i = 0; i < cnt - j - 1; ++i)
+      if (atan2f(pts[i].y - ctr.y, pts[i].x - ctr.x) > atan2f(pts[i + 1].y - ctr.y, pts[i + 1].x - ctr.x)) {
+        orc_pt t = pts[i]; pts[i] = pts[i + 1]; pts[i + 1] = t;
+      }
+  float area = 0.f;
+  for (int k = 0; k < cnt - 1; ++k) {
+    orc_pt u = {pts[k].x - pts[0].x, pts[k].y - pts[0].y}, v = {pts[k + 1].x - pts[0].x, pts[k + 1].y - pts[0].y};
+    area += orc_cross2(u, v);
+  }
+  return (float)(fabs(area) / 2.0);
+}
+
+float orc_iou_bev(const float* a, const float* b) {
+  const float sa = a[3] * a[4], sb = b[3] * b[4];
+  const float ov = orc_box_overlap(a, b);
+  return ov / fmaxf(sa + sb - ov, 1e-8f);
+}
+
+/* ious [na, nb] */
+void orc_iou_bev_matrix(const float* a, int na, const float* b, int nb, float* ious) {
+#pragma omp parallel for schedule(static)
+  for (int i = 0; i < na; ++i)
+    for (int j = 0; j < nb; ++j) ious[(size_t)i * nb + j] = orc_iou_bev(a + 7 * i, b + 7 * j);
+}
+
+/* nms_gpu (iou3d_nms.cpp:90-136): boxes [n,7] sorted by descending score -> keep indices; returns the count.
+ * min_margin (nullable): min |IoU - thresh| over the pairs the sweep evaluated (test diagnostics). */
+int orc_nms_sorted(const float* boxes, int n, float thresh, int64_t* keep, float* min_margin) {
+  unsigned char* removed = (unsigned char*)calloc((size_t)(n > 0 ? n : 1), 1);
+  int nk = 0;
+  float margin = 1e30f;
+  for (int i = 0; i < n; ++i) {
+    if (removed[i]) continue;
+    keep[nk++] = i;
+    for (int j = i + 1; j < n; ++j) {
+      const float iou = orc_iou_bev(boxes + 7 * i, boxes + 7 * j);
+      const float m = fabsf(iou - thresh);
+      if (m < margin) margin = m;
+      if (iou > thresh) removed[j] = 1;
+    }
+  }
+  free(removed);
+  if (min_margin) *min_margin = margin;
+  return nk;
+}

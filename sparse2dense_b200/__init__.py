@@ -4,4 +4,5 @@ operator API.  See DESIGN.md and include/s2d_b200.h."""
 from . import registry  # noqa: F401
 from .registry import (BACKBONES, DETECTORS, HEADS, NECKS, READERS, build_backbone, build_detector,  # noqa: F401
                        build_from_cfg, build_head, build_neck, build_reader)
-from . import readers, backbones, necks, bbox_heads  # noqa: F401,E402  (populate the registries)
+from . import readers, backbones, necks, bbox_heads, detectors, second_stage  # noqa: F401,E402  (populate the registries)
+from .config import Config, ConfigDict, get_downsample_factor  # noqa: F401,E402

@@ -47,6 +47,16 @@ SIGNATURES = {
     "s2d_layernorm_chw": (_i, [_vp, _vp, _vp, _i, _i, _i, ctypes.c_float, _vp, _vp, _sz, _vp]),
     "s2d_dense_bev_nhwc": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _i, _vp, _i, _vp]),
     "s2d_dense_bev": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _i, _vp, _vp]),
+    "s2d_centerhead_decode": (_i, [_vp, _vp, _vp, _vp, _vp, _vp]),
+    "s2d_centerhead_select_workspace_bytes": (_sz, [_i, _i, _i]),
+    "s2d_centerhead_select": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, ctypes.c_float, _i, _vp, _vp, _vp, _vp, _vp, _vp,
+                                   _sz, _vp]),
+    "s2d_nms_workspace_bytes": (_sz, [_i]),
+    "s2d_nms_sorted": (_i, [_vp, _i, ctypes.c_float, _vp, _vp, _vp, _sz, _vp]),
+    "s2d_iou_bev": (_i, [_vp, _i, _vp, _i, _vp, _vp]),
+    "s2d_bev_box_features": (_i, [_vp, _i, _i, _i, _i, _i, _vp, _vp, _i, _i, _c_float_p, _c_float_p, ctypes.c_float,
+                                  _vp, _vp]),
+    "s2d_roi_refine": (_i, [_vp, _vp, _vp, _i, _i, _vp, _i, _vp, _i, _vp, _vp, _vp]),
 }
 
 
@@ -57,6 +67,16 @@ class ConvParams(ctypes.Structure):
                 ("out", _vp), ("out_rows", _vp), ("in_ld", _i), ("out_ld", _i), ("res_ld", _i), ("tbl_stride", _i),
                 ("K", _i), ("n_in", _i), ("n_out", _i), ("Cin", _i), ("Cout", _i), ("act", _i),
                 ("res_after_act", _i), ("precision", _i)]
+
+
+class DecodeParams(ctypes.Structure):
+    """struct s2d_decode_params (include/s2d_b200.h)."""
+    _fields_ = [("reg", _vp), ("height", _vp), ("dim", _vp), ("rot", _vp), ("hm", _vp),
+                ("ld_reg", _i), ("ld_height", _i), ("ld_dim", _i), ("ld_rot", _i), ("ld_hm", _i),
+                ("B", _i), ("H", _i), ("W", _i), ("num_cls", _i),
+                ("out_size_factor", ctypes.c_float), ("voxel_x", ctypes.c_float), ("voxel_y", ctypes.c_float),
+                ("pc_x", ctypes.c_float), ("pc_y", ctypes.c_float), ("score_threshold", ctypes.c_float),
+                ("range", ctypes.c_float * 6)]
 
 
 _lib = None

@@ -119,6 +119,13 @@ class SpMiddleResNetFHD(nn.Module):
                 ok = precision != ops.PRECISION_FP32 and ops.tf32_supported(m.in_channels, m.out_channels)
                 m.precision = precision if ok else ops.PRECISION_FP32
 
+    def bev_hw(self, input_shape):
+        """(H, W) of the BEV map this backbone produces for a voxel grid ``input_shape`` = (x, y, z)."""
+        shape = tuple(int(v) for v in (np.array(input_shape[::-1]) + [1, 0, 0]))
+        for m in (self.conv2[0], self.conv3[0], self.conv4[0], self.extra_conv[0]):
+            shape = ops.conv_out_shape(shape, m.kernel_size, m.stride, m.padding, m.dilation)
+        return int(shape[1]), int(shape[2])
+
     def forward(self, voxel_features, coors, batch_size, input_shape, index=None, as_rows=False):
         """scn.py:156-185.  ``as_rows=True`` returns the BEV map as NHWC rows ``[B*H*W, C*D]`` (what the dense
         stage of this package consumes) instead of the reference's NCHW ``[B, C*D, H, W]``."""

@@ -2,7 +2,8 @@
 ``CenterHead.__init__/forward``).  Same constructor arguments and state-dict keys
 (``shared_conv.0.weight``, ``tasks.0.hm.3.bias`` …).  The shared 3x3 conv and the five 64->64 branch convs
 (fused into one 64->320 launch) run on the tcgen05 gather-GEMM; the tiny output convs (Cout <= 3) on the fp32
-kernel.  ``loss`` / ``predict`` are not built yet."""
+kernel.  ``predict`` (:293-495: decode, masks, top-4096, rotated NMS, top-500) runs as four launches for the whole
+batch on the device (csrc/detect.cu); ``loss`` is not built yet."""
 import copy
 import logging
 
@@ -144,6 +145,59 @@ class CenterHead(nn.Module):
                     out[h] = y
             ret.append(out)
         return ret
+
+    # -- predict (center_head.py:293-495) ---------------------------------------------------------
+    @staticmethod
+    def _cfg(cfg, name, default=None):
+        if isinstance(cfg, dict):
+            return cfg.get(name, default)
+        return getattr(cfg, name, default)
+
+    @torch.no_grad()
+    def predict_rows(self, preds_rows, B, H, W, test_cfg, metadata=None):
+        """preds_rows: list (per task) of dict head -> rows [B*H*W, c] (what ``forward_rows`` returns).
+        Returns the reference's list (per sample) of dict(box3d_lidar, scores, label_preds, metadata)."""
+        g = self._cfg
+        if g(test_cfg, "double_flip", False):
+            raise NotImplementedError("double_flip testing is not used by the Waymo configs and is not built")
+        if g(test_cfg, "circular_nms", False) or g(test_cfg, "per_class_nms", False):
+            raise NotImplementedError("only rotated NMS (nms.use_rotate_nms) is built")
+        per_task = self.select_rows(preds_rows, B, H, W, test_cfg)
+        counts = torch.stack([t[4] for t in per_task]).cpu().tolist()          # the one host sync: [task][sample]
+        meta = metadata if metadata else [None] * B
+        ret = []
+        for i in range(B):
+            bx, sc, lb, flag = [], [], [], 0
+            for ti, (ob, os_, ol, _, _) in enumerate(per_task):
+                n = counts[ti][i]
+                bx.append(ob[i, :n]); sc.append(os_[i, :n]); lb.append(ol[i, :n].long() + flag)
+                flag += self.num_classes[ti]
+            ret.append(dict(box3d_lidar=torch.cat(bx), scores=torch.cat(sc), label_preds=torch.cat(lb), metadata=meta[i]))
+        return ret
+
+    @torch.no_grad()
+    def select_rows(self, preds_rows, B, H, W, test_cfg):
+        """Device part of predict: per task (boxes [B,post_max,7], scores, labels i32, cells i32, counts i32 [B])."""
+        g = self._cfg
+        nms = g(test_cfg, "nms")
+        rng = list(g(test_cfg, "post_center_limit_range"))
+        assert len(rng) == 6, "post_center_limit_range must have 6 entries"
+        per_task = []
+        for preds in preds_rows:
+            boxes, scores, labels, keys = ops.centerhead_decode(
+                preds, B, H, W, g(test_cfg, "out_size_factor"), g(test_cfg, "voxel_size"), g(test_cfg, "pc_range"),
+                g(test_cfg, "score_threshold"), rng)
+            per_task.append(ops.centerhead_select(keys, boxes, scores, labels, B, H * W, int(g(nms, "nms_pre_max_size")),
+                                                  float(g(nms, "nms_iou_threshold")), int(g(nms, "nms_post_max_size"))))
+        return per_task
+
+    @torch.no_grad()
+    def predict(self, example, preds_dicts, test_cfg, **kwargs):
+        """Reference signature: preds_dicts = list of dict head -> NCHW map (``forward`` output)."""
+        B, _, H, W = preds_dicts[0]["hm"].shape
+        rows = [{h: to_rows(v.contiguous()) for h, v in d.items()} for d in preds_dicts]
+        meta = example.get("metadata") if isinstance(example, dict) else None
+        return self.predict_rows(rows, B, H, W, test_cfg, meta if meta else None)
 
     def forward(self, x, *kwargs):
         """x NCHW [B,C,H,W] -> list of dicts of NCHW maps, like center_head.py:236-244."""

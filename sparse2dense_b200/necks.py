@@ -135,6 +135,12 @@ class RPN(nn.Module):
             return x, H, W
         return ups, H0, W0
 
+    def forward_rows(self, x, B, H, W):
+        """RPN.forward on NHWC rows -> (ups rows, (Hu, Wu))."""
+        self._check_eval()
+        ups, Hu, Wu = self._rpn_rows(x, B, H, W, outer_relu=True)
+        return ups, (Hu, Wu)
+
     def forward(self, x):
         """rpn.py:153-162 (note the outer F.relu after every block, which S2D_RPN.forward omits)."""
         self._check_eval()

@@ -329,3 +329,76 @@ def dense_bev_rows(feats, coors, batch, spatial_shape, out=None):
     _lib.check(_lib.load().s2d_dense_bev_nhwc(_ptr(feats.contiguous()), _ptr(coors.contiguous()), n, c, batch, d, h, w,
                                               _ptr(out), out.stride(0), _stream()), "s2d_dense_bev_nhwc")
     return out
+
+
+# ------------------------------------------------------------------------------------------
+# CenterHead.predict: decode + candidate selection + rotated NMS (center_head.py:293-495)
+# ------------------------------------------------------------------------------------------
+def centerhead_decode(heads, B, H, W, out_size_factor, voxel_size, pc_range, score_threshold, post_center_range):
+    """heads: dict name -> 2-D row view [B*H*W, c] (stride(1) == 1) for reg/height/dim/rot/hm.
+    -> boxes [B*H*W,7], scores, labels (i32), keys (u64 as int64)."""
+    for k in ("reg", "height", "dim", "rot", "hm"):
+        t = heads[k]
+        _need_cuda(t)
+        assert t.dtype == torch.float32 and t.dim() == 2 and t.stride(1) == 1 and t.shape[0] == B * H * W, k
+    dev = heads["hm"].device
+    n = B * H * W
+    boxes = torch.empty((n, 7), dtype=torch.float32, device=dev)
+    scores = torch.empty((n,), dtype=torch.float32, device=dev)
+    labels = torch.empty((n,), dtype=torch.int32, device=dev)
+    keys = torch.empty((n,), dtype=torch.int64, device=dev)
+    p = _lib.DecodeParams()
+    p.reg, p.height, p.dim, p.rot, p.hm = (heads[k].data_ptr() for k in ("reg", "height", "dim", "rot", "hm"))
+    p.ld_reg, p.ld_height, p.ld_dim, p.ld_rot, p.ld_hm = (heads[k].stride(0) for k in ("reg", "height", "dim", "rot", "hm"))
+    p.B, p.H, p.W, p.num_cls = B, H, W, heads["hm"].shape[1]
+    p.out_size_factor, p.voxel_x, p.voxel_y = float(out_size_factor), float(voxel_size[0]), float(voxel_size[1])
+    p.pc_x, p.pc_y, p.score_threshold = float(pc_range[0]), float(pc_range[1]), float(score_threshold)
+    for i, v in enumerate(post_center_range):
+        p.range[i] = float(v)
+    _lib.check(_lib.load().s2d_centerhead_decode(_lib.ctypes.byref(p), _ptr(boxes), _ptr(scores), _ptr(labels),
+                                                 _ptr(keys), _stream()), "s2d_centerhead_decode")
+    return boxes, scores, labels, keys
+
+
+def centerhead_select(keys, boxes, scores, labels, B, cells, pre_max, iou_threshold, post_max):
+    """-> out_boxes [B,post_max,7], out_scores [B,post_max], out_labels i32, out_cells i32, n_out i32 [B] (device)."""
+    _need_cuda(keys, boxes, scores, labels)
+    lib = _lib.load()
+    dev = boxes.device
+    ob = torch.empty((B, post_max, 7), dtype=torch.float32, device=dev)
+    os_ = torch.empty((B, post_max), dtype=torch.float32, device=dev)
+    ol = torch.empty((B, post_max), dtype=torch.int32, device=dev)
+    oc = torch.empty((B, post_max), dtype=torch.int32, device=dev)
+    n_out = torch.empty((B,), dtype=torch.int32, device=dev)
+    ws_bytes = lib.s2d_centerhead_select_workspace_bytes(B, pre_max, post_max)
+    ws = torch.empty((ws_bytes,), dtype=torch.uint8, device=dev)
+    _lib.check(lib.s2d_centerhead_select(_ptr(keys), _ptr(boxes), _ptr(scores), _ptr(labels), B, cells, pre_max,
+                                         float(iou_threshold), post_max, _ptr(ob), _ptr(os_), _ptr(ol), _ptr(oc),
+                                         _ptr(n_out), _ptr(ws), ws_bytes, _stream()), "s2d_centerhead_select")
+    return ob, os_, ol, oc, n_out
+
+
+def nms_sorted(boxes, iou_threshold):
+    """Device-side iou3d_nms_cuda.nms_gpu: boxes [n,7] sorted by descending score -> (keep i32 [n], n_keep i32 [1])."""
+    _need_cuda(boxes)
+    boxes = boxes.contiguous().float()
+    n = boxes.shape[0]
+    lib = _lib.load()
+    keep = torch.empty((max(n, 1),), dtype=torch.int32, device=boxes.device)
+    n_keep = torch.zeros((1,), dtype=torch.int32, device=boxes.device)
+    ws_bytes = lib.s2d_nms_workspace_bytes(n)
+    if ws_bytes == 0 and n > 0:
+        raise _lib.S2DError(f"s2d_nms_sorted handles at most 4096 boxes, got {n}")
+    ws = torch.empty((max(ws_bytes, 1),), dtype=torch.uint8, device=boxes.device)
+    _lib.check(lib.s2d_nms_sorted(_ptr(boxes), n, float(iou_threshold), _ptr(keep), _ptr(n_keep), _ptr(ws), ws_bytes,
+                                  _stream()), "s2d_nms_sorted")
+    return keep, n_keep
+
+
+def iou_bev(boxes_a, boxes_b):
+    """Pairwise rotated-BEV IoU [n_a, n_b] (boxes [.,7] = x, y, z, dx, dy, dz, heading)."""
+    _need_cuda(boxes_a, boxes_b)
+    a, b = boxes_a.contiguous().float(), boxes_b.contiguous().float()
+    out = torch.empty((a.shape[0], b.shape[0]), dtype=torch.float32, device=a.device)
+    _lib.check(_lib.load().s2d_iou_bev(_ptr(a), a.shape[0], _ptr(b), b.shape[0], _ptr(out), _stream()), "s2d_iou_bev")
+    return out

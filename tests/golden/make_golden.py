@@ -219,10 +219,231 @@ def make_neck_head_goldens():
     np.savez_compressed(os.path.join(HERE, "neck_head_s2d.npz"), neck_seed=11, head_seed=12, input_seed=21, **out)
 
 
+class Cfg(dict):
+    """Attribute + .get access like the reference's ConfigDict."""
+    __getattr__ = dict.__getitem__
+
+
+TEST_CFG = Cfg(post_center_limit_range=[-80, -80, -10.0, 80, 80, 10.0], max_per_img=4096,
+               nms=Cfg(use_rotate_nms=True, use_multi_class_nms=False, nms_pre_max_size=4096, nms_post_max_size=500,
+                       nms_iou_threshold=0.7),
+               score_threshold=0.1, pc_range=[-75.2, -75.2], out_size_factor=8, voxel_size=[0.1, 0.1])
+
+
+def ref_iou_lib():
+    import ctypes
+    lib = ctypes.CDLL(os.path.join(ROOT, "oracle", "_ref", "libref_iou3d.so"))
+    f32p = ctypes.POINTER(ctypes.c_float)
+
+    def matrix(a, b):
+        a, b = np.ascontiguousarray(a, np.float32), np.ascontiguousarray(b, np.float32)
+        out = np.empty((len(a), len(b)), np.float32)
+        lib.ref_iou_bev_matrix(a.ctypes.data_as(f32p), len(a), b.ctypes.data_as(f32p), len(b), out.ctypes.data_as(f32p))
+        return out
+    return matrix
+
+
+def box_pairs(seed, n=160, m=240):
+    rng = np.random.default_rng(seed)
+    a = np.stack([rng.uniform(-20, 20, n), rng.uniform(-20, 20, n), rng.uniform(-1, 1, n), rng.uniform(0.6, 6, n),
+                  rng.uniform(0.5, 2.5, n), rng.uniform(1, 2, n), rng.uniform(-np.pi, np.pi, n)], 1).astype(np.float32)
+    b = a[rng.integers(0, n, m)].copy()
+    b[:, :2] += rng.normal(0, 0.7, (m, 2)).astype(np.float32)
+    b[:, 3:5] *= rng.uniform(0.8, 1.2, (m, 2)).astype(np.float32)
+    b[:, 6] += rng.normal(0, 0.4, m).astype(np.float32)
+    b[:16] = a[:16]                                    # identical boxes
+    b[16:32, 6] = a[16:32, 6] + np.float32(np.pi / 2)  # right angles about the same centre
+    b[32:40, 6] = 0; b[32:40, :2] = a[32:40, :2]       # axis aligned
+    return a, b.astype(np.float32)
+
+
+def head_maps(seed, B=2, H=48, W=44, n_obj=70):
+    """CenterHead output maps (NCHW) with object-like peaks: 3x3 neighbourhoods of confident, overlapping boxes."""
+    rng = np.random.default_rng(seed)
+    hm = rng.normal(-4.5, 0.6, (B, 3, H, W))
+    reg = rng.uniform(0, 1, (B, 2, H, W))
+    height = rng.normal(0.5, 0.3, (B, 1, H, W))
+    dim = np.log(rng.uniform(0.5, 2.0, (B, 3, H, W)))
+    ang = rng.uniform(-np.pi, np.pi, (B, 1, H, W))
+    for b in range(B):
+        for _ in range(n_obj):
+            cy, cx, cls = rng.integers(1, H - 1), rng.integers(1, W - 1), rng.integers(0, 3)
+            size = np.log([(4.6, 2.0, 1.7), (0.9, 0.8, 1.7), (1.8, 0.8, 1.6)][cls])
+            yaw = rng.uniform(-np.pi, np.pi)
+            for dy in (-1, 0, 1):
+                for dx in (-1, 0, 1):
+                    if rng.uniform() < 0.35:
+                        continue
+                    y, x = cy + dy, cx + dx
+                    hm[b, cls, y, x] = rng.normal(1.0 - 1.2 * (abs(dy) + abs(dx)), 0.5)
+                    reg[b, :, y, x] = np.clip([0.5 - 0.8 * dx + rng.normal(0, 0.1), 0.5 - 0.8 * dy + rng.normal(0, 0.1)], -1, 2)
+                    dim[b, :, y, x] = size + rng.normal(0, 0.05, 3)
+                    ang[b, 0, y, x] = yaw + rng.normal(0, 0.05)
+    rot = np.concatenate([np.sin(ang), np.cos(ang)], 1)
+    f = np.float32
+    return dict(reg=reg.astype(f), height=height.astype(f), dim=dim.astype(f), rot=rot.astype(f), hm=hm.astype(f))
+
+
+def make_predict_goldens():
+    """IoU pairs from the reference's CPU rotated-IoU code (oracle/_ref) and CenterHead.predict outputs from the
+    reference's own predict / post_processing (imported through the shim) with rotate_nms_pcdet's CUDA-only nms_gpu
+    replaced by its protocol (iou3d_nms.cpp:118-131) over the same reference IoU."""
+    import torch
+    from oracle import ref_ops as R
+    iou = ref_iou_lib()
+    a, b = box_pairs(3)
+    r = iou(a, b)
+    o = R.iou_bev_matrix(a, b)
+    print(f"iou pairs: {r.size} pairs, {(r > 0).sum()} overlapping, {(r > 0.7).sum()} above 0.7, "
+          f"oracle == reference bitwise: {bool((r.view(np.uint32) == o.view(np.uint32)).all())}")
+    assert (r.view(np.uint32) == o.view(np.uint32)).all()
+    np.savez_compressed(os.path.join(HERE, "iou_bev_pairs.npz"), boxes_a=a, boxes_b=b, iou=r)
+
+    rpn, ch, logger = reference_dense_modules()
+    margins = []
+
+    def rotate_nms_pcdet(boxes, scores, thresh, pre_maxsize=None, post_max_size=None):    # box_torch_ops.py:449-470
+        order = scores.sort(dim=0, descending=True, stable=True)[1]
+        if pre_maxsize is not None:
+            order = order[:pre_maxsize]
+        bx = boxes[order].contiguous().numpy()
+        n = len(bx)
+        m = iou(bx, bx) if n else np.zeros((0, 0), np.float32)
+        removed, keep = np.zeros(n, bool), []
+        for i in range(n):                                                              # iou3d_nms.cpp:118-131
+            if removed[i]:
+                continue
+            keep.append(i)
+            removed[i + 1:] |= m[i, i + 1:] > thresh
+            if n - i - 1 > 0:
+                margins.append(float(np.abs(m[i, i + 1:] - thresh).min()))
+        sel = order[torch.as_tensor(keep, dtype=torch.long)]
+        return sel[:post_max_size] if post_max_size is not None else sel
+    ch.box_torch_ops.rotate_nms_pcdet = rotate_nms_pcdet
+    head = ch.CenterHead(logger=logger, **HEAD_CFG).eval()
+    maps = head_maps(9)
+    preds = [{k: torch.from_numpy(v.copy()) for k, v in maps.items()}]
+    out = head.predict({"metadata": []}, preds, TEST_CFG)
+    save = {"in_" + k: v for k, v in maps.items()}
+    for i, d in enumerate(out):
+        save[f"boxes_{i}"] = d["box3d_lidar"].numpy()
+        save[f"scores_{i}"] = d["scores"].numpy()
+        save[f"labels_{i}"] = d["label_preds"].numpy()
+        print(f"predict sample {i}: {len(d['scores'])} detections, top score {float(d['scores'].max()):.3f}")
+    save["nms_margin"] = np.float32(min(margins))
+    print(f"predict: min |IoU - thr| over the sweep = {min(margins):.2e}")
+    # our numpy/C restatement must reproduce it
+    nhwc = {k: np.ascontiguousarray(v.transpose(0, 2, 3, 1)) for k, v in maps.items()}
+    boxes, hm = R.centerhead_decode(nhwc, 8, [0.1, 0.1], [-75.2, -75.2])
+    for i in range(len(out)):
+        det, _ = R.post_processing(boxes[i], hm[i], 0.1, TEST_CFG.post_center_limit_range, 0.7, 4096, 500)
+        assert np.array_equal(det["label_preds"], save[f"labels_{i}"]), "labels differ"
+        assert np.allclose(det["box3d_lidar"], save[f"boxes_{i}"], rtol=1e-5, atol=1e-6)
+        assert np.allclose(det["scores"], save[f"scores_{i}"], rtol=1e-6, atol=1e-7)
+    print("predict: oracle restatement reproduces the reference predict() output")
+    np.savez_compressed(os.path.join(HERE, "centerhead_predict.npz"), **save)
+
+
+ROI_CFG = Cfg(CLASS_AGNOSTIC=True, SHARED_FC=[256, 256], CLS_FC=[256, 256], REG_FC=[256, 256], DP_RATIO=0.3,
+              TARGET_CONFIG=Cfg(ROI_PER_IMAGE=128, FG_RATIO=0.5, SAMPLE_ROI_BY_EACH_CLASS=True, CLS_SCORE_TYPE="roi_iou",
+                                CLS_FG_THRESH=0.75, CLS_BG_THRESH=0.25, CLS_BG_THRESH_LO=0.1, HARD_BG_RATIO=0.8,
+                                REG_FG_THRESH=0.55),
+              LOSS_CONFIG=Cfg(CLS_LOSS="BinaryCrossEntropy", REG_LOSS="L1",
+                              LOSS_WEIGHTS={"rcnn_cls_weight": 1.0, "rcnn_reg_weight": 1.0, "code_weights": [1.0] * 7}))
+
+
+def make_second_stage_goldens():
+    """Second stage through the reference's own TwoStageDetector methods / BEVFeatureExtractor / RoIHead on CPU."""
+    import types
+    import torch
+    from oracle import ref_ops as R
+    rpn, ch, logger = reference_dense_modules()
+
+    def stub(name, **kw):
+        m = types.ModuleType(name); m.__dict__.update(kw); sys.modules[name] = m; return m
+    for n, p_ in [("det3d.core", "det3d/core"), ("det3d.core.bbox", "det3d/core/bbox"), ("det3d.core.utils", "det3d/core/utils"),
+                  ("det3d.ops", "det3d/ops"), ("det3d.ops.nms", "det3d/ops/nms"), ("det3d.ops.iou3d_nms", "det3d/ops/iou3d_nms"),
+                  ("det3d.models.detectors", "det3d/models/detectors"), ("det3d.models.second_stage", "det3d/models/second_stage"),
+                  ("det3d.models.roi_heads", "det3d/models/roi_heads"),
+                  ("det3d.models.roi_heads.target_assigner", "det3d/models/roi_heads/target_assigner")]:
+        m = types.ModuleType(n); m.__path__ = [f"{REF}/{p_}"]; sys.modules[n] = m
+    stub("cv2")
+    sys.modules.pop("det3d.core.utils.center_utils", None)          # drop the stub of reference_dense_modules()
+    stub("det3d.core.utils.circle_nms_jit", circle_nms=None)
+    stub("det3d.ops.nms.nms_cpu", rotate_nms_cc=None)
+    stub("det3d.ops.nms.nms_gpu", nms_gpu=None, rotate_iou_gpu=None, rotate_nms_gpu=None)
+    stub("det3d.ops.iou3d_nms.iou3d_nms_utils", boxes_iou3d_gpu=None)
+    stub("det3d.ops.iou3d_nms.iou3d_nms_cuda")
+    import det3d.core.bbox.box_torch_ops as bto
+    sys.modules["det3d.core.bbox"].box_torch_ops = bto
+    sys.modules["det3d.core"].box_torch_ops = bto
+    import det3d.core.utils.center_utils  # noqa: F401
+    stub("det3d.models.detectors.base", BaseDetector=torch.nn.Module)
+    sys.modules["det3d.models"].builder = types.SimpleNamespace()
+    import det3d.models.detectors.two_stage as ts
+    import det3d.models.second_stage.bird_eye_view as bev_mod
+    import det3d.models.roi_heads.roi_head as rh
+
+    rng = np.random.default_rng(17)
+    B, C, H, W, P = 2, 64, 24, 20, 500
+    pc_start, voxel, stride = [-75.2, -75.2], [0.1, 0.1], 8
+    bev = np.abs(rng.normal(0, 1, (B, C, H, W))).astype(np.float32)
+    preds = []
+    for b in range(B):
+        n = [37, 120][b]
+        xy = np.stack([rng.uniform(-76.5, -75.2 + W * 0.8 + 1.0, n), rng.uniform(-76.5, -75.2 + H * 0.8 + 1.0, n)], 1)
+        boxes = np.concatenate([xy, rng.normal(0.5, 0.3, (n, 1)), rng.uniform(0.5, 5, (n, 3)), rng.uniform(-np.pi, np.pi, (n, 1))], 1)
+        preds.append(dict(box3d_lidar=torch.from_numpy(boxes.astype(np.float32)),
+                          scores=torch.from_numpy(rng.uniform(0.1, 1, n).astype(np.float32)),
+                          label_preds=torch.from_numpy(rng.integers(0, 3, n).astype(np.int64))))
+    torch.manual_seed(4)
+    roi = rh.RoIHead(input_channels=C * 5, model_cfg=ROI_CFG, code_size=7).eval()
+    with torch.no_grad():
+        for m in roi.modules():
+            if isinstance(m, torch.nn.BatchNorm1d):
+                m.running_mean.normal_(0, 0.1); m.running_var.uniform_(0.5, 1.5); m.weight.uniform_(0.5, 1.5); m.bias.normal_(0, 0.1)
+        roi.reg_layers[-1].weight.normal_(0, 0.05); roi.reg_layers[-1].bias.normal_(0, 0.1)
+    det = ts.TwoStageDetector.__new__(ts.TwoStageDetector)
+    torch.nn.Module.__init__(det)
+    det.NMS_POST_MAXSIZE, det.num_point, det.roi_head = P, 5, roi
+    det.second_stage = torch.nn.ModuleList([bev_mod.BEVFeatureExtractor(pc_start, voxel, stride)])
+    example = {"bev_feature": torch.from_numpy(bev).permute(0, 2, 3, 1).contiguous(), "metadata": [None] * B}
+    with torch.no_grad():
+        centers = det.get_box_center(preds)
+        feats = [m.forward(example, centers, 5) for m in det.second_stage]
+        example = det.reorder_first_stage_pred_and_feature(first_pred=preds, example=example, features=feats)
+        out = det.post_process(roi(example, training=False))
+    save = dict(bev=bev, roi_features_0=feats[0][0].numpy(), roi_features_1=feats[0][1].numpy())
+    state = {k: v.numpy() for k, v in roi.state_dict().items()}
+    save.update({"roi." + k: v for k, v in state.items()})
+    for b in range(B):
+        save[f"in_boxes_{b}"] = preds[b]["box3d_lidar"].numpy(); save[f"in_scores_{b}"] = preds[b]["scores"].numpy()
+        save[f"in_labels_{b}"] = preds[b]["label_preds"].numpy()
+        save[f"boxes_{b}"] = out[b]["box3d_lidar"].numpy(); save[f"scores_{b}"] = out[b]["scores"].numpy()
+        save[f"labels_{b}"] = out[b]["label_preds"].numpy()
+        # oracle restatement must reproduce the reference modules
+        f = R.roi_features(np.ascontiguousarray(bev[b].transpose(1, 2, 0)), save[f"in_boxes_{b}"], pc_start, voxel, stride)
+        e1 = np.abs(f - save[f"roi_features_{b}"]).max() / np.abs(save[f"roi_features_{b}"]).max()
+        cls, reg = R.roi_head_forward(state, f)
+        ob, os_ = R.roi_refine(save[f"in_boxes_{b}"], save[f"in_scores_{b}"], cls, reg)
+        e2, e3 = np.abs(ob - save[f"boxes_{b}"]).max(), np.abs(os_ - save[f"scores_{b}"]).max()
+        print(f"second stage sample {b}: {len(ob)} rois, oracle-vs-reference: features {e1:.2e}, boxes {e2:.2e}, scores {e3:.2e}")
+        assert e1 < 1e-5 and e2 < 1e-4 and e3 < 1e-5 and np.array_equal(save[f"labels_{b}"], save[f"in_labels_{b}"])
+    np.savez_compressed(os.path.join(HERE, "two_stage.npz"), **save)
+
+
 if __name__ == "__main__":
+    if len(sys.argv) > 1 and sys.argv[1] == "second":
+        make_second_stage_goldens()
+        sys.exit(0)
+    if len(sys.argv) > 1 and sys.argv[1] == "predict":
+        make_predict_goldens()
+        sys.exit(0)
     if len(sys.argv) > 1 and sys.argv[1] == "dense":
         make_neck_head_goldens()
         sys.exit(0)
     make_voxel_goldens()
     make_spconv_goldens()
     make_neck_head_goldens()
+    make_predict_goldens()
+    make_second_stage_goldens()
