@@ -42,6 +42,10 @@ int s2d_version(void);
 const char* s2d_last_error(void);
 /* kernels launched by this library in this process so far (bench.py reports the per-run delta) */
 unsigned long long s2d_kernel_launches(void);
+/* Copies n ints (row counts and similar control values) from device memory into MAPPED pinned host memory with a
+ * kernel store, not a DMA copy, so that the read never queues behind a bulk device->host transfer; the caller
+ * waits for the stream (an event) before reading dst_host_mapped. */
+int s2d_export_i32(const int* src, int n, int* dst_host_mapped, void* stream);
 
 /* ---------------------------------------------------------------------------------------
  * Voxelizer.  Replaces points_to_voxel(points, voxel_size, coors_range, max_points,

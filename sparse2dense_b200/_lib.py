@@ -21,6 +21,7 @@ SIGNATURES = {
     "s2d_version": (_i, []),
     "s2d_last_error": (ctypes.c_char_p, []),
     "s2d_kernel_launches": (ctypes.c_ulonglong, []),
+    "s2d_export_i32": (_i, [_vp, _i, _vp, _vp]),
     "s2d_voxelize_workspace_bytes": (_sz, [_i, _i, _i, _i]),
     "s2d_voxelize": (_i, [_vp, _c_int_p, _i, _i, _i, _c_float_p, _c_float_p, _i, _i, _vp, _vp, _vp, _vp, _i, _vp,
                           _vp, _sz, _vp]),

@@ -163,7 +163,8 @@ class CenterHead(nn.Module):
         if g(test_cfg, "circular_nms", False) or g(test_cfg, "per_class_nms", False):
             raise NotImplementedError("only rotated NMS (nms.use_rotate_nms) is built")
         per_task = self.select_rows(preds_rows, B, H, W, test_cfg)
-        counts = torch.stack([t[4] for t in per_task]).cpu().tolist()          # the one host sync: [task][sample]
+        flat = ops.read_ints(torch.stack([t[4] for t in per_task]).reshape(-1))   # the one host sync
+        counts = [flat[i * B:(i + 1) * B] for i in range(len(per_task))]          # [task][sample]
         meta = metadata if metadata else [None] * B
         ret = []
         for i in range(B):

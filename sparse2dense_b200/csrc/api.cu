@@ -29,6 +29,25 @@ static std::atomic<unsigned long long> g_launches{0};
 void count_launches(int n) { g_launches.fetch_add((unsigned long long)n, std::memory_order_relaxed); }
 }  // namespace s2d
 
+namespace s2d {
+__global__ void export_i32_kernel(const int* __restrict__ src, int n, volatile int* __restrict__ dst) {
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) dst[i] = src[i];
+}
+}  // namespace s2d
+
+// Small control values (row counts) go to the host through MAPPED pinned memory written by a kernel instead of a
+// cudaMemcpy: a DMA copy would queue behind any bulk device->host transfer in flight on the copy engine (the
+// pipelined result read-back) and stall the next step's launch sequence for milliseconds.
+extern "C" int s2d_export_i32(const int* src, int n, int* dst_host_mapped, void* stream) {
+  S2D_REQUIRE(n >= 0 && (n == 0 || (src && dst_host_mapped)), "s2d_export_i32: bad argument");
+  if (n == 0) return S2D_OK;
+  s2d::export_i32_kernel<<<1, n < 256 ? 32 * ((n + 31) / 32) : 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      src, n, dst_host_mapped);
+  S2D_LAUNCH_CHECK();
+  s2d::count_launches(1);
+  return S2D_OK;
+}
+
 extern "C" unsigned long long s2d_kernel_launches(void) { return s2d::g_launches.load(); }
 extern "C" int s2d_version(void) { return 100; }
 extern "C" const char* s2d_last_error(void) { return s2d::g_err; }

@@ -239,8 +239,16 @@ __global__ void __launch_bounds__(kNmsTile) nms_mask_kernel(const float* __restr
 #pragma unroll
     for (int q = 0; q < 7; ++q) cur[q] = src[q];
     unsigned long long bits = 0ull;
-    for (int j = (rb == cbk) ? t + 1 : 0; j < col_size; ++j)
-      if (iou_bev_dev(cur, s_box + j * 7) > thresh) bits |= 1ull << j;
+    // Exact early-out: when the circumscribed circles (plus the 1e-2 corner margin of check_in_box2d) are disjoint,
+    // no edges cross and no corner passes the inside test, so the reference overlap is exactly 0.
+    const float rad = 0.5f * sqrtf(cur[3] * cur[3] + cur[4] * cur[4]) + 0.05f;
+    for (int j = (rb == cbk) ? t + 1 : 0; j < col_size; ++j) {
+      const float* o = s_box + j * 7;
+      const float dx = o[0] - cur[0], dy = o[1] - cur[1];
+      const float reach = rad + 0.5f * sqrtf(o[3] * o[3] + o[4] * o[4]);
+      if (dx * dx + dy * dy > reach * reach) continue;
+      if (iou_bev_dev(cur, o) > thresh) bits |= 1ull << j;
+    }
     mask[((size_t)b * kNmsMaxBoxes + i) * words + cbk] = bits;
   }
 }

@@ -36,6 +36,29 @@ def _ptr(t):
     return None if t is None else t.data_ptr()
 
 
+_EXPORT = {}
+
+
+def read_ints(t):
+    """Device int32 tensor (a few control values: row counts) -> python list, synchronising the current stream.
+    The values travel through mapped pinned host memory written by a kernel (``s2d_export_i32``), not a DMA copy, so
+    the read does not queue behind a bulk device->host transfer running on the copy engine."""
+    _need_cuda(t)
+    t = t.contiguous()
+    assert t.dtype == torch.int32
+    n = t.numel()
+    key = (t.device.index, torch.cuda.current_stream(t.device).cuda_stream)
+    slot = _EXPORT.get(key)
+    if slot is None or slot[0].numel() < n:
+        slot = (torch.empty((max(n, 64),), dtype=torch.int32, pin_memory=True), torch.cuda.Event())
+        _EXPORT[key] = slot
+    buf, ev = slot
+    _lib.check(_lib.load().s2d_export_i32(_ptr(t), n, buf.data_ptr(), _stream()), "s2d_export_i32")
+    ev.record()
+    ev.synchronize()
+    return buf[:n].tolist()
+
+
 def _need_cuda(*tensors):
     for t in tensors:
         if t is not None and not t.is_cuda:
@@ -68,7 +91,7 @@ class VoxelBatch:
 
     def offsets_host(self):
         if self._offsets_host is None:
-            self._offsets_host = self.voxel_offsets.cpu().tolist()   # the one host sync
+            self._offsets_host = read_ints(self.voxel_offsets)       # the one host sync
         return self._offsets_host
 
     @property
@@ -205,7 +228,7 @@ class SparseCoords:
     @property
     def n(self):
         if self._n is None:
-            self._n = int(self.n_dev.item())
+            self._n = int(read_ints(self.n_dev)[0])
             if self._n > self.coors_buffer.shape[0]:
                 raise _lib.S2DError(f"sparse conv produced {self._n} outputs > capacity {self.coors_buffer.shape[0]}")
         return self._n

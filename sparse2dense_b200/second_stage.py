@@ -206,7 +206,7 @@ class TwoStageDetector(BaseDetector):
                                               rcnn_cls.data_ptr(), rcnn_cls.stride(0), rcnn_reg.data_ptr(),
                                               rcnn_reg.stride(0), boxes.data_ptr(), scores.data_ptr(), ops._stream()),
                    "s2d_roi_refine")
-        counts = n_boxes.cpu().tolist()                                     # the one host sync
+        counts = ops.read_ints(n_boxes)                                     # the one host sync
         meta = example.get("metadata") or [None] * B
         ret = [dict(box3d_lidar=boxes[i, :counts[i]], scores=scores[i, :counts[i]],
                     label_preds=roi_labels[i, :counts[i]].long(), metadata=meta[i]) for i in range(B)]

@@ -283,7 +283,7 @@ def plan_coords(x, modules):
         planned.append(sc)
         coors, n, n_dev, shape = sc.coors_buffer, sc.coors_buffer.shape[0], sc.n_dev, sc.shape
     if planned:
-        counts = torch.cat([sc.n_dev for sc in planned]).cpu().tolist()       # the one sync
+        counts = ops.read_ints(torch.cat([sc.n_dev for sc in planned]))       # the one sync
         for m, sc, c in zip(convs, planned, counts):
             sc.set_n(c)
             x._planned[id(m)] = sc
