@@ -82,6 +82,13 @@ def cpu_scene_seconds(cloud, state, repeat=1):
     return best
 
 
+def host_cores():
+    try:
+        return len(os.sched_getaffinity(0))
+    except AttributeError:
+        return os.cpu_count() or 1
+
+
 def run_reference(args):
     """--impl reference: the reference's CPU algorithm (oracle port; spconv itself is not installable,
     see DESIGN.md) on all host cores; each step = one scene of the workload."""
@@ -91,6 +98,7 @@ def run_reference(args):
     from oracle import ref_ops as R
     from sparse2dense_b200 import synth
     R.build()
+    R.set_num_threads(host_cores())        # torchrun exports OMP_NUM_THREADS=1: use every host core explicitly
     cores = R.num_threads()
     state = synth.backbone_state(0)
     clouds = synth.lidar_batch(1, min(args.batch, 2))
@@ -241,6 +249,8 @@ def run_gpu(args):
     e2e_wall = time.perf_counter() - t0
     e2e_ms = e0.elapsed_time(e1) - sum(a.elapsed_time(b) for a, b in flush_ms_evs)
 
+    print(f"[bench rank {rank}] device {dev_ms / args.steps:.3f} ms/step, e2e {e2e_ms / args.steps:.3f} ms/step "
+          f"(wall {1e3 * e2e_wall / args.steps:.3f})", file=sys.stderr, flush=True)
     dev_ms, e2e_ms = sharding.max_over_ranks([dev_ms, e2e_ms], device=dev)     # slowest rank sets the time
     (launches,) = sharding.sum_over_ranks([launches], device=dev)
 
@@ -303,6 +313,7 @@ def run_gpu(args):
         if world == 1 and not args.no_cpu_baseline:
             from oracle import ref_ops as R
             R.build()
+            R.set_num_threads(host_cores())
             sec = cpu_scene_seconds(clouds[0], synth.backbone_state(0))
             cpu = {"value": 1.0 / sec, "unit": UNIT, "cores": R.num_threads(), "kind": "port",
                    "sample": "scene 0 of the batch, once (voxelize + reader + backbone), C/OpenMP oracle port"}
