@@ -174,6 +174,11 @@ __device__ __forceinline__ int lds32(uint32_t addr) {
   asm volatile("ld.shared.b32 %0, [%1];" : "=r"(v) : "r"(addr));
   return v;
 }
+__device__ __forceinline__ int4 lds128i(uint32_t addr) {
+  int4 v;
+  asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr));
+  return v;
+}
 __device__ __forceinline__ float4 lds128(uint32_t addr) {
   float4 v;
   asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
@@ -379,11 +384,12 @@ __global__ void __launch_bounds__(kTcThreads, 1) spconv_tc_kernel(const __grid_c
     const uint32_t bar_a_full0 = smem_u32(bar_a_full), bar_a_empty0 = smem_u32(bar_a_empty);
     const uint32_t bar_n_full0 = smem_u32(bar_n_full), bar_n_empty0 = smem_u32(bar_n_empty);
     const uint32_t tmem_mine = tmem_a0 + ((uint32_t)row16 << 16);
-    const int* nbr_mine = s_nbr + sub * Cfg::ROWS + row16 + o;
+    const int* nbr_mine = s_nbr + sub * Cfg::ROWS + row16 + 4 * o;   // this lane gathers rows 4o .. 4o+3 of the warp's 16
     constexpr int DEPTH = Cfg::DEPTH;
     const uint32_t ring0 = smem_u32(a_ring) + (uint32_t)warp * (DEPTH * Cfg::A_WARP_STAGE);
-    // gather destination of this lane inside a stage (row 4i + o, chunk c, 128B swizzle) and fragment sources
-    const uint32_t g_off = (uint32_t)o * 128u + (uint32_t)((c ^ o) << 4);          // + i*512 ; (4i+o)&7 = o ^ 4*(i&1)
+    // gather destination of this lane inside a stage (row 4o + i, chunk c, 128B swizzle) and fragment sources:
+    // dst_i = (g_off + i*128) ^ (i << 4), because (4o + i) & 7 = 4*(o & 1) + i for i < 4
+    const uint32_t g_off = (uint32_t)o * 512u + (uint32_t)((c ^ (4 * (o & 1))) << 4);
     const uint32_t f_off0 = (uint32_t)rl * 128u + (uint32_t)(((2 * j) ^ rl) << 4);
     const uint32_t f_off1 = (uint32_t)rl * 128u + (uint32_t)(((2 * j + 1) ^ rl) << 4);
 
@@ -401,19 +407,26 @@ __global__ void __launch_bounds__(kTcThreads, 1) spconv_tc_kernel(const __grid_c
     const char* in_bytes = reinterpret_cast<const char*>(A.in);
     const uint32_t row_bytes = (uint32_t)A.in_ld * 4u;
     const uint32_t nbr_addr0 = smem_u32(nbr_mine);
-    auto gather_step = [&]() {
+    // The four neighbour indices of the next gather are fetched with ONE LDS.128 well before they are needed
+    // (gather_prefetch at the top of a conversion step, gather_issue at its end), which takes the index load and
+    // its shared-memory queueing delay off the critical path.
+    int4 pidx = make_int4(-1, -1, -1, -1);
+    auto gather_prefetch = [&]() {
       const int slot = lk & (kNbrSlots - 1);
       if (lk != lk_ready) { mbar_wait(bar_n_full0 + 8 * slot, (lk / kNbrSlots) & 1); lk_ready = lk; }
-      const uint32_t nb = nbr_addr0 + (uint32_t)(slot * (kMaxKps * Cfg::ROWS) + lt * kBM) * 4u;
+      pidx = lds128i(nbr_addr0 + (uint32_t)(slot * (kMaxKps * Cfg::ROWS) + lt * kBM) * 4u);
+    };
+    auto gather_issue = [&]() {
+      const int slot = lk & (kNbrSlots - 1);
       const uint32_t dst0 = ring0 + (uint32_t)gstage * Cfg::A_WARP_STAGE + g_off;
       const uint32_t cbytes = (uint32_t)(lc * kBK + c4 * 4) * 4u;
+      const int idx[4] = {pidx.x, pidx.y, pidx.z, pidx.w};
 #pragma unroll
       for (int i = 0; i < 4; ++i) {
         if (S2D_DBG(A, 1)) break;
-        const int idx = lds32(nb + 16u * i);                                   // row 4i + o of the warp's 16
-        const uint32_t off = (uint32_t)max(idx, 0) * row_bytes + cbytes;
-        const uint32_t dst = (dst0 + (uint32_t)i * 512u) ^ ((uint32_t)(i & 1) << 6);   // chunk ^= 4 on odd i
-        cp_async16_zfill(dst, in_bytes + off, idx >= 0 ? 16u : 0u);
+        const uint32_t off = (uint32_t)max(idx[i], 0) * row_bytes + cbytes;
+        const uint32_t dst = (dst0 + (uint32_t)i * 128u) ^ ((uint32_t)i << 4);
+        cp_async16_zfill(dst, in_bytes + off, idx[i] >= 0 ? 16u : 0u);
       }
       cp_async_commit();
       if (++gstage == DEPTH) gstage = 0;
@@ -428,7 +441,8 @@ __global__ void __launch_bounds__(kTcThreads, 1) spconv_tc_kernel(const __grid_c
         }
       }
     };
-    auto convert_step = [&]() {
+    auto convert_step = [&](bool more) {
+      if (more) gather_prefetch();
       cp_async_wait<DEPTH - 1>();                // this lane's pieces of the oldest step in flight have landed
       __syncwarp();                              // ... and so have the other lanes'
       const uint32_t src = ring0 + (uint32_t)cstage * Cfg::A_WARP_STAGE;
@@ -498,12 +512,13 @@ __global__ void __launch_bounds__(kTcThreads, 1) spconv_tc_kernel(const __grid_c
     const int my_steps = nsteps / kGroups;       // nsteps = KS * NCHUNK * T is a multiple of kGroups
 #pragma unroll 1
     for (int i = 0; i < DEPTH; ++i) {
-      if (i < my_steps) gather_step(); else cp_async_commit();
+      if (i < my_steps) { gather_prefetch(); gather_issue(); } else cp_async_commit();
     }
 #pragma unroll 1
     for (int s = 0; s < my_steps; ++s) {
-      convert_step();
-      if (s + DEPTH < my_steps) gather_step(); else cp_async_commit();
+      const bool more = s + DEPTH < my_steps;
+      convert_step(more);
+      if (more) gather_issue(); else cp_async_commit();
     }
 
     // ===================== epilogue (same 8 warps) =====================
