@@ -22,6 +22,7 @@
 //
 // Precision modes: TF32X3 (error-compensated, ~fp32 accuracy: this is what meets the 1e-3 parity
 // bar through 21 layers) and TF32 (single pass).
+#include <cuda.h>
 #include <cuda_bf16.h>
 
 #include "common.cuh"
@@ -72,6 +73,16 @@ __device__ __forceinline__ void bulk_copy_g2s(uint32_t dst, const void* src, uin
   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
                "l"(src), "r"(bytes), "r"(bar)
                : "memory");
+}
+// TMA gather4: four rows (row coordinates r0..r3, a negative / out-of-range row is zero filled) x one box of columns
+// starting at `col` of a 2-D tensor map -> four consecutive 128 B rows at dst (128B-swizzled), completing on `bar`.
+__device__ __forceinline__ void tma_gather4(uint32_t dst, const CUtensorMap* map, int col, int r0, int r1, int r2, int r3,
+                                            uint32_t bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cta.global.tile::gather4.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4, "
+      "%5, %6}], [%7];" ::"r"(dst),
+      "l"(map), "r"(col), "r"(r0), "r"(r1), "r"(r2), "r"(r3), "r"(bar)
+      : "memory");
 }
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
@@ -302,7 +313,7 @@ struct ConvArgs {
   const float* residual;
   float* out;
   const int* out_rows;
-  int in_ld, out_ld, res_ld, tbl_stride, n_out, K, nchunk, kps, ksteps, act, res_after_act;
+  int in_ld, out_ld, res_ld, tbl_stride, n_out, K, nchunk, kps, ksteps, act, res_after_act, use_tma;
   int dbg;   // ablation switches for tools/ablate_spconv.py (0 in production): 1 no gather, 2 no TMEM store, 4 no MMA
 };
 
@@ -317,7 +328,8 @@ __device__ __forceinline__ float apply_act(float y, int act) {
 // shared memory: the producer warps write it straight into TMEM (tcgen05.st) and the MMAs run in TS mode,
 // so shared-memory bandwidth only carries the small weight slices.
 template <int COUT, int PASSES>
-__global__ void __launch_bounds__(kTcThreads, 1) spconv_tc_kernel(const __grid_constant__ ConvArgs A) {
+__global__ void __launch_bounds__(kTcThreads, 1) spconv_tc_kernel(const __grid_constant__ ConvArgs A,
+                                                                  const __grid_constant__ CUtensorMap in_map) {
   using Cfg = TcCfg<COUT, PASSES>;
   constexpr int SA = Cfg::SA, SB = Cfg::SB, T = Cfg::T;
   constexpr int B_TILE = Cfg::B_TILE, B_STAGE = Cfg::B_STAGE, A_COLS = Cfg::A_COLS;
@@ -341,7 +353,8 @@ __global__ void __launch_bounds__(kTcThreads, 1) spconv_tc_kernel(const __grid_c
   uint64_t* bar_n_full = bar_b_empty + SB;
   uint64_t* bar_n_empty = bar_n_full + kNbrSlots;
   uint64_t* bar_accum = bar_n_empty + kNbrSlots;
-  uint32_t* s_tmem = reinterpret_cast<uint32_t*>(bar_accum + 1);
+  uint64_t* bar_gather = bar_accum + 1;                         // kProducerWarps x DEPTH: one per warp and ring stage
+  uint32_t* s_tmem = reinterpret_cast<uint32_t*>(bar_gather + kProducerWarps * Cfg::DEPTH);
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int tile0 = blockIdx.x * Cfg::ROWS;
@@ -361,6 +374,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) spconv_tc_kernel(const __grid_c
       mbar_init(smem_u32(bar_n_empty + s), kProducerWarps);
     }
     mbar_init(smem_u32(bar_accum), T);
+    for (int s = 0; s < kProducerWarps * Cfg::DEPTH; ++s) mbar_init(smem_u32(bar_gather + s), 1);
     fence_barrier_init();
   }
   if (warp == kLoaderWarp) tmem_alloc(smem_u32(s_tmem), Cfg::TMEM_COLS);
@@ -401,6 +415,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) spconv_tc_kernel(const __grid_c
     int lk = 0, lc = 0, lt = grp;                // gather stream position (offset step, chunk, tile); kGroups <= T
     int lk_ready = -1;                           // last offset step whose neighbour slice this warp has waited for
     int gstage = 0, cstage = 0;                  // ring positions of the gather / convert streams
+    uint32_t cphase = 0;                         // mbarrier phase of the convert stream (TMA gather)
     int sstage = grp;                            // TMEM ring position of step s: s % SA
     uint32_t sphase = 1;                         // first pass over the TMEM ring: slots are free
     // byte offsets are 32 bit (the host checks n_in * in_ld * 4 < 4 GiB); neighbour indices are read with ld.shared
@@ -416,19 +431,32 @@ __global__ void __launch_bounds__(kTcThreads, 1) spconv_tc_kernel(const __grid_c
       if (lk != lk_ready) { mbar_wait(bar_n_full0 + 8 * slot, (lk / kNbrSlots) & 1); lk_ready = lk; }
       pidx = lds128i(nbr_addr0 + (uint32_t)(slot * (kMaxKps * Cfg::ROWS) + lt * kBM) * 4u);
     };
+    const bool use_tma = A.use_tma != 0;         // kps == 1: rows are whole 128 B chunks -> TMA gather4
+    const uint32_t bar_g0 = smem_u32(bar_gather + warp * DEPTH);
     auto gather_issue = [&]() {
       const int slot = lk & (kNbrSlots - 1);
-      const uint32_t dst0 = ring0 + (uint32_t)gstage * Cfg::A_WARP_STAGE + g_off;
-      const uint32_t cbytes = (uint32_t)(lc * kBK + c4 * 4) * 4u;
-      const int idx[4] = {pidx.x, pidx.y, pidx.z, pidx.w};
+      if (use_tma) {
+        // lane 8o issues ONE gather4 for rows 4o..4o+3 (their indices are its pidx): 4 instructions per warp and
+        // step instead of 4 x 32 cp.async lanes, and the copies run on the TMA engine, not through the LSU pipe.
+        const uint32_t bar = bar_g0 + 8u * (uint32_t)gstage;
+        if (lane == 0) mbar_arrive_expect_tx(bar, S2D_DBG(A, 1) ? 0u : (uint32_t)Cfg::A_WARP_STAGE);
+        __syncwarp();
+        if (c == 0 && !S2D_DBG(A, 1))
+          tma_gather4(ring0 + (uint32_t)gstage * Cfg::A_WARP_STAGE + (uint32_t)o * 512u, &in_map, lc * kBK, pidx.x, pidx.y,
+                      pidx.z, pidx.w, bar);
+      } else {
+        const uint32_t dst0 = ring0 + (uint32_t)gstage * Cfg::A_WARP_STAGE + g_off;
+        const uint32_t cbytes = (uint32_t)(lc * kBK + c4 * 4) * 4u;
+        const int idx[4] = {pidx.x, pidx.y, pidx.z, pidx.w};
 #pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        if (S2D_DBG(A, 1)) break;
-        const uint32_t off = (uint32_t)max(idx[i], 0) * row_bytes + cbytes;
-        const uint32_t dst = (dst0 + (uint32_t)i * 128u) ^ ((uint32_t)i << 4);
-        cp_async16_zfill(dst, in_bytes + off, idx[i] >= 0 ? 16u : 0u);
+        for (int i = 0; i < 4; ++i) {
+          if (S2D_DBG(A, 1)) break;
+          const uint32_t off = (uint32_t)max(idx[i], 0) * row_bytes + cbytes;
+          const uint32_t dst = (dst0 + (uint32_t)i * 128u) ^ ((uint32_t)i << 4);
+          cp_async16_zfill(dst, in_bytes + off, idx[i] >= 0 ? 16u : 0u);
+        }
+        cp_async_commit();
       }
-      cp_async_commit();
       if (++gstage == DEPTH) gstage = 0;
       lt += kGroups;
       if (lt >= T) {
@@ -443,10 +471,14 @@ __global__ void __launch_bounds__(kTcThreads, 1) spconv_tc_kernel(const __grid_c
     };
     auto convert_step = [&](bool more) {
       if (more) gather_prefetch();
-      cp_async_wait<DEPTH - 1>();                // this lane's pieces of the oldest step in flight have landed
-      __syncwarp();                              // ... and so have the other lanes'
+      if (use_tma) {
+        mbar_wait(bar_g0 + 8u * (uint32_t)cstage, cphase);   // the four gather4 of the oldest step have landed
+      } else {
+        cp_async_wait<DEPTH - 1>();              // this lane's pieces of the oldest step in flight have landed
+        __syncwarp();                            // ... and so have the other lanes'
+      }
       const uint32_t src = ring0 + (uint32_t)cstage * Cfg::A_WARP_STAGE;
-      if (++cstage == DEPTH) cstage = 0;
+      if (++cstage == DEPTH) { cstage = 0; cphase ^= 1; }
       float4 v[4];
       if (S2D_DBG(A, 8)) {
         v[0] = v[1] = v[2] = v[3] = make_float4(1.f, 2.f, 3.f, 4.f);
@@ -512,13 +544,13 @@ __global__ void __launch_bounds__(kTcThreads, 1) spconv_tc_kernel(const __grid_c
     const int my_steps = nsteps / kGroups;       // nsteps = KS * NCHUNK * T is a multiple of kGroups
 #pragma unroll 1
     for (int i = 0; i < DEPTH; ++i) {
-      if (i < my_steps) { gather_prefetch(); gather_issue(); } else cp_async_commit();
+      if (i < my_steps) { gather_prefetch(); gather_issue(); } else if (!use_tma) cp_async_commit();
     }
 #pragma unroll 1
     for (int s = 0; s < my_steps; ++s) {
       const bool more = s + DEPTH < my_steps;
       convert_step(more);
-      if (more) gather_issue(); else cp_async_commit();
+      if (more) gather_issue(); else if (!use_tma) cp_async_commit();
     }
 
     // ===================== epilogue (same 8 warps) =====================
@@ -723,6 +755,7 @@ __global__ void __launch_bounds__(256) pack_weights_kernel(const float* __restri
 }
 
 static int g_tc_debug = 0;
+static int g_tc_gather = 0;   // 0: cp.async gather ring (default), 2: TMA gather4 where possible
 
 static int cout_block(int Cout) {
   return Cout % 128 == 0 ? 128 : (Cout % 64 == 0 ? 64 : (Cout % 32 == 0 ? 32 : (Cout % 16 == 0 ? 16 : 0)));
@@ -740,7 +773,7 @@ static bool tc_supported(int Cin, int Cout) {
 }
 
 template <int COUT, int PASSES>
-static int launch_tc(const ConvArgs& a, int Cout, cudaStream_t st) {
+static int launch_tc(const ConvArgs& a, const CUtensorMap& in_map, int Cout, cudaStream_t st) {
   using Cfg = TcCfg<COUT, PASSES>;
   static bool configured = false;
   if (!configured) {
@@ -749,17 +782,36 @@ static int launch_tc(const ConvArgs& a, int Cout, cudaStream_t st) {
     configured = true;
   }
   const dim3 grid(div_up(a.n_out, Cfg::ROWS), Cout / COUT);
-  spconv_tc_kernel<COUT, PASSES><<<grid, kTcThreads, Cfg::SMEM_BYTES, st>>>(a);
+  spconv_tc_kernel<COUT, PASSES><<<grid, kTcThreads, Cfg::SMEM_BYTES, st>>>(a, in_map);
   S2D_LAUNCH_CHECK();
   count_launches(1);
   return S2D_OK;
 }
 
 template <int COUT>
-static int launch_tc_prec(const ConvArgs& a, int Cout, int precision, cudaStream_t st) {
-  if (precision == S2D_PRECISION_TF32X3) return launch_tc<COUT, 3>(a, Cout, st);
-  if (precision == S2D_PRECISION_TF32_BF16C) return launch_tc<COUT, 2>(a, Cout, st);
-  return launch_tc<COUT, 1>(a, Cout, st);
+static int launch_tc_prec(const ConvArgs& a, const CUtensorMap& m, int Cout, int precision, cudaStream_t st) {
+  if (precision == S2D_PRECISION_TF32X3) return launch_tc<COUT, 3>(a, m, Cout, st);
+  if (precision == S2D_PRECISION_TF32_BF16C) return launch_tc<COUT, 2>(a, m, Cout, st);
+  return launch_tc<COUT, 1>(a, m, Cout, st);
+}
+
+// 2-D tensor map over the input rows [n_in, Cin] (row stride in_ld floats), box = 32 columns x 1 row, 128B swizzle,
+// zero fill outside: what tile::gather4 needs (four such rows per instruction).
+static int make_input_map(const s2d_conv_params& p, CUtensorMap* map) {
+  const cuuint64_t dims[2] = {(cuuint64_t)p.Cin, (cuuint64_t)(p.n_in > 0 ? p.n_in : 1)};
+  const cuuint64_t strides[1] = {(cuuint64_t)p.in_ld * sizeof(float)};
+  const cuuint32_t box[2] = {(cuuint32_t)kBK, 1u};
+  const cuuint32_t estr[2] = {1u, 1u};
+  const CUresult r = cuTensorMapEncodeTiled(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(p.in), dims,
+                                            strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                                            CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                                            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("s2d_conv_fwd: cuTensorMapEncodeTiled failed (%d) for in=%p n_in=%d Cin=%d in_ld=%d", (int)r, (const void*)p.in,
+              p.n_in, p.Cin, p.in_ld);
+    return S2D_ERR_CUDA;
+  }
+  return S2D_OK;
 }
 
 int conv_fwd_tf32(const s2d_conv_params& p, cudaStream_t st) {
@@ -779,12 +831,22 @@ int conv_fwd_tf32(const s2d_conv_params& p, cudaStream_t st) {
   a.nchunk = a.kps == 1 ? p.Cin / kBK : 1; a.ksteps = div_up(p.K, a.kps); a.act = p.act;
   a.res_after_act = p.res_after_act;
   a.dbg = g_tc_debug;
+  // The TMA gather4 path (whole 128 B row chunks: kps == 1, 16 B aligned base) is functional but measured SLOWER
+  // than the cp.async ring on B200 (one gather4 ~ 38 clk of TMA time: 32->32 0.60 vs 0.38 ms, 64->64 0.68 vs 0.53 ms),
+  // so it is opt-in (s2d_debug_tc_gather(2), tools/microbench_spconv.py --gather 2).
+  a.use_tma = (a.kps == 1 && g_tc_gather == 2 && (reinterpret_cast<uintptr_t>(p.in) & 15) == 0) ? 1 : 0;
+  alignas(64) CUtensorMap in_map;
+  memset(&in_map, 0, sizeof(in_map));
+  if (a.use_tma) {
+    const int rc = make_input_map(p, &in_map);
+    if (rc != S2D_OK) return rc;
+  }
   const int cb = cout_block(p.Cout);
   const int prec = resolve_precision(p.precision, p.Cout);
-  if (cb == 128) return launch_tc_prec<128>(a, p.Cout, prec, st);
-  if (cb == 64) return launch_tc_prec<64>(a, p.Cout, prec, st);
-  if (cb == 32) return launch_tc_prec<32>(a, p.Cout, prec, st);
-  return launch_tc_prec<16>(a, p.Cout, prec, st);
+  if (cb == 128) return launch_tc_prec<128>(a, in_map, p.Cout, prec, st);
+  if (cb == 64) return launch_tc_prec<64>(a, in_map, p.Cout, prec, st);
+  if (cb == 32) return launch_tc_prec<32>(a, in_map, p.Cout, prec, st);
+  return launch_tc_prec<16>(a, in_map, p.Cout, prec, st);
 }
 
 }  // namespace s2d
@@ -793,6 +855,7 @@ using namespace s2d;
 
 // ablation switches of the tcgen05 kernel (profiling aid, see ConvArgs::dbg); not part of the public header
 extern "C" void s2d_debug_tc_flags(int flags) { g_tc_debug = flags; }
+extern "C" void s2d_debug_tc_gather(int mode) { g_tc_gather = mode; }
 
 extern "C" int s2d_spconv_tf32_supported(int Cin, int Cout) { return tc_supported(Cin, Cout) ? 1 : 0; }
 

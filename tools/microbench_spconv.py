@@ -20,8 +20,13 @@ def main():
     ap.add_argument("--reps", type=int, default=10)
     ap.add_argument("--only", type=int, default=0)
     ap.add_argument("--precisions", default="fp32,tf32,tf32x3,tf32_bf16c")
+    ap.add_argument("--gather", type=int, default=0, help="0: cp.async gather ring (default), 2: TMA gather4 where possible")
     args = ap.parse_args()
     prec = ops.PRECISION_NAMES
+    import ctypes
+    from sparse2dense_b200 import _lib
+    _lib.load()
+    ctypes.CDLL(_lib.LIB_PATH).s2d_debug_tc_gather(args.gather)
     clouds = synth.lidar_batch(1, args.batch)
     pts, offs = concat_clouds(clouds)
     vb = ops.voxelize(pts.cuda(), offs, synth.WAYMO_VOXEL, synth.WAYMO_RANGE, 5, 150000, want_voxels=False,
