@@ -301,6 +301,34 @@ int s2d_roi_refine(const float* rois, const float* roi_scores, const int* n_boxe
                    const float* rcnn_cls, int cls_ld, const float* rcnn_reg, int reg_ld, float* out_boxes,
                    float* out_scores, void* stream);
 
+/* ---------------------------------------------------------------------------------------
+ * PointPillars + S2D variant (BASELINE configs[3]).
+ *
+ * s2d_pfn_fwd: PillarFeatureNet.forward with num_filters = [64, 64]
+ *   (det3d/models/readers/pillar_encoder.py:41-56,114-154) as ONE kernel: decorate each point with the offset
+ *   to the pillar's point mean and to the pillar centre (x_offset = vx/2 + pc_range_x), zero the padded
+ *   points, Linear(10->32, no bias) + BN1d (folded scale/shift) + ReLU, max over points, concat [x, max],
+ *   Linear(64->64) + BN1d + ReLU, max -> out f32 [n_pillars, 64].
+ *   voxels f32 [n_pillars, max_points, 5] zero padded, num_points i32, coors i32 [n_pillars,4] (b,z,y,x),
+ *   W0 f32 [32,10], W1 f32 [64,64] (nn.Linear layout [out,in]).
+ * s2d_maxpool2d_rows: nn.MaxPool2d(2,2) on NHWC rows (pillar_encoder.py:236).
+ * s2d_gather_rows: out[o,:] = in[idx[o],:] (zero when idx < 0): nn.Upsample(nearest) with a host-made index map
+ *   (pillar_encoder.py:283,295) and any other row remap.
+ * s2d_grid2d_tconv_table_s: sub-pixel class (py,px) of ConvTranspose2d(k, stride, pad) with k % stride == 0 and
+ *   k - stride == 2*pad (RPN deblocks with stride 2 and 4, det3d/models/necks/rpn.py:82-95); tbl i32
+ *   [(k/stride)^2, B*H*W], out_rows as in s2d_grid2d_tconv_table.
+ * The pillar scatter (PointPillarsScatter*.forward, pillar_encoder.py:337-371) is s2d_dense_bev_nhwc with D = 1.
+ * ------------------------------------------------------------------------------------- */
+int s2d_pfn_fwd(const float* voxels, const int* num_points, const int* coors, int n_pillars, int max_points, int F,
+                float vx, float vy, float x_offset, float y_offset, const float* W0, const float* scale0,
+                const float* shift0, const float* W1, const float* scale1, const float* shift1, float* out,
+                void* stream);
+int s2d_maxpool2d_rows(const float* in, int in_ld, int B, int H, int W, int C, float* out, int out_ld, void* stream);
+int s2d_gather_rows(const float* in, int in_ld, const int* idx, long long n_out, int C, float* out, int out_ld,
+                    void* stream);
+int s2d_grid2d_tconv_table_s(int B, int H, int W, int k, int stride, int pad, int py, int px, int* tbl,
+                             int tbl_stride, int* out_rows, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -58,6 +58,11 @@ SIGNATURES = {
     "s2d_bev_box_features": (_i, [_vp, _i, _i, _i, _i, _i, _vp, _vp, _i, _i, _c_float_p, _c_float_p, ctypes.c_float,
                                   _vp, _vp]),
     "s2d_roi_refine": (_i, [_vp, _vp, _vp, _i, _i, _vp, _i, _vp, _i, _vp, _vp, _vp]),
+    "s2d_pfn_fwd": (_i, [_vp, _vp, _vp, _i, _i, _i, ctypes.c_float, ctypes.c_float, ctypes.c_float, ctypes.c_float,
+                         _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "s2d_maxpool2d_rows": (_i, [_vp, _i, _i, _i, _i, _i, _vp, _i, _vp]),
+    "s2d_gather_rows": (_i, [_vp, _i, _vp, ctypes.c_longlong, _i, _vp, _i, _vp]),
+    "s2d_grid2d_tconv_table_s": (_i, [_i, _i, _i, _i, _i, _i, _i, _i, _vp, _i, _vp, _vp]),
 }
 
 

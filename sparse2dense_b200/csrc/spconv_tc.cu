@@ -802,10 +802,22 @@ static int make_input_map(const s2d_conv_params& p, CUtensorMap* map) {
   const cuuint64_t strides[1] = {(cuuint64_t)p.in_ld * sizeof(float)};
   const cuuint32_t box[2] = {(cuuint32_t)kBK, 1u};
   const cuuint32_t estr[2] = {1u, 1u};
-  const CUresult r = cuTensorMapEncodeTiled(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(p.in), dims,
-                                            strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                                            CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
-                                            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  // The driver entry point is resolved at run time so that the library has no load-time dependency on libcuda.so.1
+  // (it must load on a machine without a driver: build / ABI checks run there).
+  typedef CUresult (*EncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                               const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                               CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+  static EncodeFn encode = nullptr;
+  if (!encode) {
+    void* fn = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    S2D_CUDA(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &q));
+    S2D_REQUIRE(fn && q == cudaDriverEntryPointSuccess, "s2d_conv_fwd: cuTensorMapEncodeTiled not available in this driver");
+    encode = reinterpret_cast<EncodeFn>(fn);
+  }
+  const CUresult r = encode(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(p.in), dims, strides, box, estr,
+                            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
     set_error("s2d_conv_fwd: cuTensorMapEncodeTiled failed (%d) for in=%p n_in=%d Cin=%d in_ld=%d", (int)r, (const void*)p.in,
               p.n_in, p.Cin, p.in_ld);
