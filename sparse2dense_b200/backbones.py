@@ -157,3 +157,87 @@ class SpMiddleResNetFHD(nn.Module):
             "conv4": x_conv4,
         }
         return ret, multi_scale_voxel_features
+
+
+@BACKBONES.register_module
+class PointPillarsScatter_S2D(nn.Module):
+    """Pillar scatter + the S2D module of the pillar student (det3d/models/readers/pillar_encoder.py:219-394, registered
+    under BACKBONES there too).  Same module tree / state-dict keys; eval forward (the PCR generator is train-only).
+    The canvas is built directly as NHWC rows (``s2d_dense_bev_nhwc`` with D = 1) and every layer runs on rows."""
+
+    def __init__(self, num_input_features=64, norm_cfg=None, name="PointPillarsScatter", **kwargs):
+        super().__init__()
+        self.name = "PointPillarsScatter"
+        self.nchannels = num_input_features
+        S = nn.Sequential
+
+        def convnext():
+            return S(nn.Conv2d(256, 256, kernel_size=7, padding=3, groups=256), nn.LayerNorm([256, 59, 59], eps=1e-6),
+                     nn.Conv2d(256, 1024, 1, 1, 0), nn.GELU(), nn.Conv2d(1024, 256, 1, 1, 0))
+        self.encoder_1 = S(nn.MaxPool2d(2, 2), nn.Conv2d(64, 32, 1, 1, 0), nn.BatchNorm2d(32), nn.GELU(),
+                           nn.Conv2d(32, 32, 2, 2), nn.BatchNorm2d(32), nn.GELU(),
+                           nn.Conv2d(32, 128, 1, 1, 0), nn.BatchNorm2d(128), nn.GELU())
+        self.encoder_2 = S(nn.Conv2d(128, 128, 3, 2, 1), nn.BatchNorm2d(128), nn.GELU(),
+                           nn.Conv2d(128, 256, 3, 1, 1), nn.BatchNorm2d(256), nn.GELU())
+        self.convnext_block_1 = convnext()
+        self.convnext_block_2 = convnext()
+        self.convnext_block_3 = convnext()
+        self.decoder_1 = S(nn.Conv2d(256, 128, 3, 1, 1), nn.BatchNorm2d(128), nn.GELU(), nn.Upsample((117, 117)))
+        self.decoder_2 = S(nn.Conv2d(128 + 128, 64, 3, 1, 1), nn.BatchNorm2d(64), nn.GELU(),
+                           nn.ConvTranspose2d(64, 64, 4, 2, 1), nn.BatchNorm2d(64), nn.GELU(),
+                           nn.Conv2d(64, 64, 1, 1, 0), nn.BatchNorm2d(64), nn.GELU(), nn.Upsample(scale_factor=2))
+        self.fusion_sparse = S(nn.Conv2d(64, 64, 1, 1, 0), nn.BatchNorm2d(num_input_features), nn.GELU())
+        self.fusion_dense = S(nn.Conv2d(64, 64, 1, 1, 0), nn.BatchNorm2d(64), nn.GELU())
+        # PCR module (train only; kept for state-dict compatibility)
+        self.generator = S(nn.Conv3d(64, 32, 1, 1, 0), nn.BatchNorm3d(32), nn.GELU(),
+                           nn.Conv3d(32, 16, 1, 1, 0), nn.BatchNorm3d(16), nn.GELU())
+        self.gen_out = S(nn.Conv3d(16, 3, 1, 1, 0))
+        self.gen_mask = S(nn.Conv3d(16, 8, 1, 1, 0), nn.BatchNorm3d(8), nn.GELU(), nn.Conv3d(8, 1, 1, 1, 0))
+        from .dense import DenseOps
+        self._dense = DenseOps()
+
+    def set_precision(self, precision):
+        from .dense import DenseOps
+        self._dense = DenseOps(precision)
+
+    def forward_rows(self, voxel_features, coords, batch_size, input_shape):
+        """-> (F_S_a rows [B*ny*nx, 64], F_S_b rows, (ny, nx))."""
+        from .dense import ACT_GELU, ACT_NONE
+        if self.training:
+            raise NotImplementedError("PointPillarsScatter_S2D is inference only in this build (call .eval())")
+        D = self._dense
+        nx, ny = int(input_shape[0]), int(input_shape[1])
+        B = batch_size
+        assert (ny, nx) == (468, 468), "LayerNorm([256,59,59]) / Upsample((117,117)) fix the canvas to 468 x 468"
+        canvas = ops.dense_bev_rows(voxel_features.contiguous(), coords.int().contiguous(), B, (1, ny, nx))   # scatter
+        e1, e2 = self.encoder_1, self.encoder_2
+        a, H1, W1 = D.maxpool2(canvas, B, ny, nx)                                                   # 234
+        a, _, _ = D.conv("encoder_1.1", a, B, H1, W1, e1[1], e1[2], ACT_GELU)
+        a, H2, W2 = D.conv("encoder_1.4", a, B, H1, W1, e1[4], e1[5], ACT_GELU)                    # 117
+        y_3 = torch.empty((B * H2 * W2, 256), dtype=torch.float32, device=canvas.device)            # cat([decoder_1, y_1])
+        y_1, _, _ = D.conv("encoder_1.7", a, B, H2, W2, e1[7], e1[8], ACT_GELU, out=y_3[:, 128:])
+        a, H3, W3 = D.conv("encoder_2.0", y_1, B, H2, W2, e2[0], e2[1], ACT_GELU)                   # 59
+        att, _, _ = D.conv("encoder_2.3", a, B, H3, W3, e2[3], e2[4], ACT_GELU)
+        for bi, blk in enumerate((self.convnext_block_1, self.convnext_block_2, self.convnext_block_3)):
+            t = D.dwconv(att, B, H3, W3, blk[0])
+            t = D.layernorm(t, B, H3, W3, blk[1])
+            t, _, _ = D.conv(f"convnext_block_{bi + 1}.2", t, B, H3, W3, blk[2], None, ACT_GELU)
+            att, _, _ = D.conv(f"convnext_block_{bi + 1}.4", t, B, H3, W3, blk[4], None, ACT_NONE, residual=att)
+        d1 = self.decoder_1
+        a, _, _ = D.conv("decoder_1.0", att, B, H3, W3, d1[0], d1[1], ACT_GELU)
+        D.upsample_nearest(a, B, H3, W3, H2, W2, out=y_3[:, :128])                                  # Upsample((117,117))
+        d2 = self.decoder_2
+        a, _, _ = D.conv("decoder_2.0", y_3, B, H2, W2, d2[0], d2[1], ACT_GELU)
+        a, H4, W4 = D.tconv("decoder_2.3", a, B, H2, W2, d2[3], d2[4], ACT_GELU)                   # 234
+        a, _, _ = D.conv("decoder_2.6", a, B, H4, W4, d2[6], d2[7], ACT_GELU)
+        F_S_b = D.upsample_nearest(a, B, H4, W4, ny, nx, scale=2)                                   # 468
+        fs, _, _ = D.conv("fusion_sparse.0", canvas, B, ny, nx, self.fusion_sparse[0], self.fusion_sparse[1], ACT_GELU)
+        F_S_a, _, _ = D.conv("fusion_dense.0", F_S_b, B, ny, nx, self.fusion_dense[0], self.fusion_dense[1], ACT_GELU,
+                             residual=fs, res_after_act=True)
+        return F_S_a, F_S_b, (ny, nx)
+
+    def forward(self, voxel_features, coords, batch_size, input_shape):
+        """Reference return value (eval): (F_S_a, F_S_b, None, None) as NCHW maps."""
+        from .dense import to_nchw
+        a, b, (H, W) = self.forward_rows(voxel_features, coords, batch_size, input_shape)
+        return to_nchw(a, batch_size, H, W), to_nchw(b, batch_size, H, W), None, None

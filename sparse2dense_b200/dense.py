@@ -38,21 +38,38 @@ def conv_table(device, B, H, W, k, stride, pad):
     return hit
 
 
-def tconv_tables(device, B, H, W, k, pad):
-    """Four sub-pixel classes of ConvTranspose2d(k, stride 2, pad): list of (py, px, tbl, out_rows) (cached)."""
-    key = (str(device), "tconv", B, H, W, k, pad)
+def tconv_tables(device, B, H, W, k, pad, stride=2):
+    """The stride**2 sub-pixel classes of ConvTranspose2d(k, stride, pad) with k - stride == 2*pad:
+    list of (py, px, tbl, out_rows) (cached)."""
+    key = (str(device), "tconv", B, H, W, k, pad, stride)
     hit = _TABLES.get(key)
     if hit is None:
         n = B * H * W
         hit = []
-        for py in (0, 1):
-            for px in (0, 1):
-                tbl = torch.empty(((k // 2) ** 2, n), dtype=torch.int32, device=device)
+        for py in range(stride):
+            for px in range(stride):
+                tbl = torch.empty(((k // stride) ** 2, n), dtype=torch.int32, device=device)
                 rows = torch.empty((n,), dtype=torch.int32, device=device)
-                _lib.check(_lib.load().s2d_grid2d_tconv_table(B, H, W, k, k, pad, py, px, tbl.data_ptr(), n,
-                                                              rows.data_ptr(), _stream()), "s2d_grid2d_tconv_table")
+                _lib.check(_lib.load().s2d_grid2d_tconv_table_s(B, H, W, k, stride, pad, py, px, tbl.data_ptr(), n,
+                                                                rows.data_ptr(), _stream()), "s2d_grid2d_tconv_table_s")
                 hit.append((py, px, tbl, rows))
         _TABLES[key] = hit
+    return hit
+
+
+def nearest_index(device, B, H, W, Ho, Wo, scale=None):
+    """Row map of nn.Upsample(mode='nearest') from [B,H,W] to [B,Ho,Wo] (cached): src = min(floor(dst * scale), in - 1)
+    with scale = in / out in float32 when a size is given, 1 / scale_factor when a factor is given (torch semantics)."""
+    key = (str(device), "nearest", B, H, W, Ho, Wo, scale)
+    hit = _TABLES.get(key)
+    if hit is None:
+        import numpy as np
+        sy = np.float32(H) / np.float32(Ho) if scale is None else np.float32(1.0 / scale)
+        sx = np.float32(W) / np.float32(Wo) if scale is None else np.float32(1.0 / scale)
+        ys = np.minimum(np.floor(np.arange(Ho, dtype=np.float32) * sy).astype(np.int64), H - 1)
+        xs = np.minimum(np.floor(np.arange(Wo, dtype=np.float32) * sx).astype(np.int64), W - 1)
+        idx = (np.arange(B)[:, None, None] * H + ys[None, :, None]) * W + xs[None, None, :]
+        hit = _TABLES[key] = torch.from_numpy(idx.reshape(-1).astype(np.int32)).to(device)
     return hit
 
 
@@ -160,10 +177,10 @@ class DenseOps:
             if transposed_class is None:                      # Conv2d [Cout,Cin,kh,kw] -> [K,Cin,Cout]
                 kio = w.permute(2, 3, 1, 0).reshape(-1, w.shape[1], w.shape[0]).contiguous()
             else:                                             # ConvTranspose2d [Cin,Cout,kh,kw], taps of one class
-                py, px, pad = transposed_class
+                py, px, pad, st = transposed_class
                 kh, kw = w.shape[2], w.shape[3]
-                ky0, kx0 = (py + pad) & 1, (px + pad) & 1
-                taps = [w[:, :, ky0 + 2 * a, kx0 + 2 * c] for a in range(kh // 2) for c in range(kw // 2)]
+                ky0, kx0 = (py + pad) % st, (px + pad) % st
+                taps = [w[:, :, ky0 + st * a, kx0 + st * c] for a in range(kh // st) for c in range(kw // st)]
                 kio = torch.stack(taps, 0).contiguous()       # [K, Cin, Cout]
             packed = None
             if self.precision != ops.PRECISION_FP32 and ops.tf32_supported(kio.shape[1], kio.shape[2]):
@@ -190,17 +207,36 @@ class DenseOps:
         return y, Ho, Wo
 
     def tconv(self, name, x, B, H, W, conv, bn=None, act=ACT_NONE, out=None):
-        """ConvTranspose2d(stride 2) on rows as four sub-pixel convolutions; returns (out, 2H, 2W)."""
-        k, pad = conv.kernel_size[0], conv.padding[0]
-        assert conv.stride[0] == 2 and (k, pad) in ((4, 1), (2, 0))
+        """ConvTranspose2d(k, stride s, pad) with k - s == 2*pad on rows as s*s sub-pixel convolutions;
+        returns (out, s*H, s*W)."""
+        k, pad, st = conv.kernel_size[0], conv.padding[0], conv.stride[0]
+        assert k % st == 0 and k - st == 2 * pad, "ConvTranspose2d shape outside the sub-pixel scheme"
         cout = conv.weight.shape[1]
         if out is None:
-            out = torch.empty((B * 4 * H * W, cout), dtype=torch.float32, device=x.device)
+            out = torch.empty((B * st * st * H * W, cout), dtype=torch.float32, device=x.device)
         scale, shift = self._affine(name, conv, bn)
-        for py, px, tbl, rows in tconv_tables(x.device, B, H, W, k, pad):
-            kio, packed = self._conv_weights(name, conv, (py, px, pad))
+        for py, px, tbl, rows in tconv_tables(x.device, B, H, W, k, pad, st):
+            kio, packed = self._conv_weights(name, conv, (py, px, pad, st))
             conv_rows(x, kio, tbl, B * H * W, scale, shift, act, None, False, out, rows, self.precision, packed)
-        return out, 2 * H, 2 * W
+        return out, st * H, st * W
+
+    def maxpool2(self, x, B, H, W):
+        """nn.MaxPool2d(2, 2) on rows -> (out, H//2, W//2)."""
+        C = x.shape[1]
+        out = torch.empty((B * (H // 2) * (W // 2), C), dtype=torch.float32, device=x.device)
+        _lib.check(_lib.load().s2d_maxpool2d_rows(x.data_ptr(), x.stride(0), B, H, W, C, out.data_ptr(), out.stride(0),
+                                                  _stream()), "s2d_maxpool2d_rows")
+        return out, H // 2, W // 2
+
+    def upsample_nearest(self, x, B, H, W, Ho, Wo, scale=None, out=None):
+        """nn.Upsample(mode='nearest') on rows (into `out`, a 2-D view with stride(1) == 1, when given)."""
+        C = x.shape[1]
+        idx = nearest_index(x.device, B, H, W, Ho, Wo, scale)
+        if out is None:
+            out = torch.empty((B * Ho * Wo, C), dtype=torch.float32, device=x.device)
+        _lib.check(_lib.load().s2d_gather_rows(x.data_ptr(), x.stride(0), idx.data_ptr(), B * Ho * Wo, C, out.data_ptr(),
+                                               out.stride(0), _stream()), "s2d_gather_rows")
+        return out
 
     def dwconv(self, x, B, H, W, conv):
         C, k = conv.weight.shape[0], conv.kernel_size[0]

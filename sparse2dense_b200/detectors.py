@@ -155,3 +155,57 @@ class KD_VoxelNet(VoxelNet):
         preds = self.bbox_head.forward_rows(ups, B, Hu, Wu)
         raw = self.bbox_head.select_rows(preds, B, Hu, Wu, self.test_cfg)
         return raw, ups, (B, Hu, Wu), voxel_feature, F_S_a, F_S_b, (H, W)
+
+
+@DETECTORS.register_module
+class PointPillars(SingleStageDetector):
+    """Teacher / plain CenterPoint-Pillar (det3d/models/detectors/point_pillars.py:13-124): reader ``PillarFeatureNet``,
+    backbone ``PointPillarsScatter``-style canvas, neck ``RPN``."""
+
+    def extract_feat(self, data):
+        input_features = self.reader(data["features"], data["num_voxels"], data["coors"])
+        x = self.backbone(input_features, data["coors"], data["batch_size"], data["input_shape"])
+        if self.with_neck:
+            x = self.neck(x)
+        return x
+
+
+@DETECTORS.register_module
+class KD_PointPillars(PointPillars):
+    """The pillar student (point_pillars.py:127-251): backbone ``PointPillarsScatter_S2D`` returns (F_S_a, F_S_b, ..),
+    the RPN runs on F_S_a.  Inference path only."""
+
+    def extract_feat(self, data):
+        input_features = self.reader(data["features"], data["num_voxels"], data["coors"])
+        F_S_a, F_S_b, gen_offset, gen_mask = self.backbone(input_features, data["coors"], data["batch_size"],
+                                                           data["input_shape"])
+        x = self.neck(F_S_a) if self.with_neck else F_S_a
+        return x, F_S_a, F_S_b, gen_offset, gen_mask
+
+    def _rows(self, example):
+        data = _example_data(example)
+        B = data["batch_size"]
+        feats = self.reader(data["features"], data["num_voxels"], data["coors"])
+        F_S_a, F_S_b, (H, W) = self.backbone.forward_rows(feats, data["coors"], B, data["input_shape"])
+        ups, (Hu, Wu) = self.neck.forward_rows(F_S_a, B, H, W)
+        preds = self.bbox_head.forward_rows(ups, B, Hu, Wu)
+        return preds, ups, F_S_a, F_S_b, B, H, W, Hu, Wu
+
+    def forward(self, example, return_loss=True, **kwargs):
+        if return_loss or self.training:
+            raise NotImplementedError("the distillation training branch is not built; call .eval() and return_loss=False")
+        preds, _, _, _, B, _, _, Hu, Wu = self._rows(example)
+        return self.bbox_head.predict_rows(preds, B, Hu, Wu, self.test_cfg, example.get("metadata"))
+
+    def forward_two_stage(self, example, return_loss=True, **kwargs):
+        """point_pillars.py:215-251 -> (boxes, bev_feature, None, None, F_S_a, F_S_b)."""
+        if return_loss or self.training:
+            raise NotImplementedError("the training branch is not built")
+        preds, ups, F_S_a, F_S_b, B, H, W, Hu, Wu = self._rows(example)
+        boxes = self.bbox_head.predict_rows(preds, B, Hu, Wu, self.test_cfg, example.get("metadata"))
+        return boxes, to_nchw(ups, B, Hu, Wu), None, None, to_nchw(F_S_a, B, H, W), to_nchw(F_S_b, B, H, W)
+
+    def first_stage_raw(self, example):
+        preds, ups, F_S_a, F_S_b, B, H, W, Hu, Wu = self._rows(example)
+        raw = self.bbox_head.select_rows(preds, B, Hu, Wu, self.test_cfg)
+        return raw, ups, (B, Hu, Wu), None, F_S_a, F_S_b, (H, W)

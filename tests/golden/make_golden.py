@@ -432,7 +432,65 @@ def make_second_stage_goldens():
     np.savez_compressed(os.path.join(HERE, "two_stage.npz"), **save)
 
 
+PP_VOXEL, PP_RANGE = (0.32, 0.32, 6.0), (-74.88, -74.88, -2, 74.88, 74.88, 4.0)
+PP_RPN = dict(layer_nums=[3, 5, 5], ds_layer_strides=[1, 2, 2], ds_num_filters=[64, 128, 256], us_layer_strides=[1, 2, 4],
+              us_num_filters=[128, 128, 128], num_input_features=64)
+
+
+def make_pillar_goldens():
+    """PillarFeatureNet -> PointPillarsScatter_S2D -> RPN([3,5,5]) through the reference's own modules (shim), on the
+    pillars of one synthetic scene voxelized by the reference's numba voxelizer; sampled outputs are committed."""
+    import logging
+    import torch
+    from oracle import pillars as OP
+    from sparse2dense_b200 import registry
+    rpn, ch, logger = reference_dense_modules()
+    import det3d.models.readers.pillar_encoder as pe
+    pco = ref_voxelizer()
+    cloud = synth.lidar_scene(2000)
+    voxels, coors, num = pco(cloud, np.array(PP_VOXEL, np.float32), np.array(PP_RANGE, np.float32), 20, True, 32000)
+    coors4 = np.concatenate([np.zeros((len(coors), 1), np.int32), coors], 1)
+    print(f"pillars: {len(voxels)} of one scene, grid 468 x 468")
+    ours_reader = registry.build_reader(dict(type="PillarFeatureNet", num_filters=[64, 64], num_input_features=5,
+                                             with_distance=False, voxel_size=PP_VOXEL, pc_range=PP_RANGE))
+    ours_bb = registry.build_backbone(dict(type="PointPillarsScatter_S2D", ds_factor=1))
+    ours_neck = registry.build_neck(dict(type="RPN", logger=logging.getLogger("x"), **PP_RPN))
+    rs, bs, ns = (synth.random_module_state(m, sd) for m, sd in ((ours_reader, 31), (ours_bb, 32), (ours_neck, 33)))
+    ref_reader = pe.PillarFeatureNet(num_filters=[64, 64], num_input_features=5, with_distance=False, voxel_size=PP_VOXEL,
+                                     pc_range=PP_RANGE).eval()
+    ref_bb = pe.PointPillarsScatter_S2D(ds_factor=1).eval()
+    ref_neck = rpn.RPN(logger=logger, **PP_RPN).eval()
+    for ref, st in ((ref_reader, rs), (ref_bb, bs), (ref_neck, ns)):
+        res = ref.load_state_dict({k: torch.from_numpy(v) for k, v in st.items()}, strict=False)
+        assert not res.unexpected_keys, res.unexpected_keys
+        assert all(k.endswith("num_batches_tracked") for k in res.missing_keys), res.missing_keys
+    with torch.no_grad():
+        v, c, n = torch.from_numpy(voxels), torch.from_numpy(coors4), torch.from_numpy(num)
+        rf = ref_reader(v, n, c)
+        rfa, rfb, _, _ = ref_bb(rf, c, 1, [468, 468, 1])
+        rx = ref_neck(rfa)
+        of = OP.pfn_forward(rs, voxels, num, coors4, PP_VOXEL, PP_RANGE)
+        ofa, ofb = OP.scatter_s2d_forward(bs, of, coors4, 1, 468, 468)
+        ox = OP.rpn_forward(ns, ofa, PP_RPN["layer_nums"], PP_RPN["ds_layer_strides"], PP_RPN["us_layer_strides"])
+    rng = np.random.default_rng(6)
+    out = {}
+    for name, r, o in [("pfn", rf, of), ("F_S_a", rfa, ofa), ("F_S_b", rfb, ofb), ("x", rx, ox)]:
+        r, o = r.numpy(), o.numpy()
+        err = np.abs(r - o).max() / np.abs(r).max()
+        print(f"pillars {name}: shape {r.shape} max|ref| {np.abs(r).max():.3f} oracle-vs-reference rel err {err:.2e}")
+        assert err < 1e-5, name
+        idx = rng.choice(r.size, size=min(4000, r.size), replace=False)
+        out[name + "_idx"] = idx.astype(np.int64)
+        out[name + "_val"] = r.reshape(-1)[idx]
+        out[name + "_absmax"] = np.float32(np.abs(r).max())
+    np.savez_compressed(os.path.join(HERE, "pillars_s2d.npz"), scene_seed=2000, reader_seed=31, backbone_seed=32,
+                        neck_seed=33, n_pillars=len(voxels), coors_checksum=np.int64(coors4.astype(np.int64).sum()), **out)
+
+
 if __name__ == "__main__":
+    if len(sys.argv) > 1 and sys.argv[1] == "pp":
+        make_pillar_goldens()
+        sys.exit(0)
     if len(sys.argv) > 1 and sys.argv[1] == "second":
         make_second_stage_goldens()
         sys.exit(0)
@@ -447,3 +505,4 @@ if __name__ == "__main__":
     make_neck_head_goldens()
     make_predict_goldens()
     make_second_stage_goldens()
+    make_pillar_goldens()
