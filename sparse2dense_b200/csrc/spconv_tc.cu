@@ -288,7 +288,7 @@ struct TcCfg {
   static_assert(SMEM_BYTES <= 227 * 1024, "shared memory budget");
   static_assert(COUT % 16 == 0 && COUT >= 16 && COUT <= 128, "UMMA N constraint for M=128 / TMEM budget");
   static_assert(SA >= 2 && SA >= kGroups, "gathered-tile ring too small");
-  static_assert(T % kGroups == 0, "every producer group must touch every offset step");
+  static_assert(T >= kGroups, "producer groups split the steps of an offset step");
 };
 
 // Arguments of one launch.  Rows may be strided (in_ld / out_ld / res_ld, in floats) so that layers can read
@@ -314,6 +314,8 @@ struct ConvArgs {
   float* out;
   const int* out_rows;
   int in_ld, out_ld, res_ld, tbl_stride, n_out, K, nchunk, kps, ksteps, act, res_after_act, use_tma;
+  int tile_base, tile_rem;   // CTA b owns tile_base + (b < tile_rem) consecutive 128-row tiles (<= T): see launch_tc
+  int t_min;                 // tiles a CTA executes at least (virtual empty tiles) so that Tr * nchunk >= kGroups
   int dbg;   // ablation switches for tools/ablate_spconv.py (0 in production): 1 no gather, 2 no TMEM store, 4 no MMA
 };
 
@@ -357,8 +359,14 @@ __global__ void __launch_bounds__(kTcThreads, 1) spconv_tc_kernel(const __grid_c
   uint32_t* s_tmem = reinterpret_cast<uint32_t*>(bar_gather + kProducerWarps * Cfg::DEPTH);
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int tile0 = blockIdx.x * Cfg::ROWS;
-  const int nsteps = KS * NCHUNK * T;
+  // Balanced tiling: the 128-row tiles are dealt evenly over a grid that is a multiple of the SM count, so the last
+  // wave is as loaded as the others (a CTA's time is proportional to its tile count Tr <= T).
+  const int t_real = A.tile_base + ((int)blockIdx.x < A.tile_rem ? 1 : 0);
+  if (t_real == 0) return;
+  const int Tr = max(t_real, A.t_min);        // extra tiles are virtual: no rows loaded, none stored
+  const int tile0 = ((int)blockIdx.x * A.tile_base + min((int)blockIdx.x, A.tile_rem)) * kBM;
+  const int row_end = min(n_out, tile0 + t_real * kBM);
+  const int nsteps = KS * NCHUNK * Tr;
 
   if (warp == kMmaWarp0 && lane == 0) {
     for (int s = 0; s < SA; ++s) {
@@ -367,13 +375,13 @@ __global__ void __launch_bounds__(kTcThreads, 1) spconv_tc_kernel(const __grid_c
     }
     for (int s = 0; s < SB; ++s) {
       mbar_init(smem_u32(bar_b_full + s), 1);                     // arrive.expect_tx of the loader
-      mbar_init(smem_u32(bar_b_empty + s), T);                    // one tcgen05.commit per row tile
+      mbar_init(smem_u32(bar_b_empty + s), Tr);                   // one tcgen05.commit per row tile
     }
     for (int s = 0; s < kNbrSlots; ++s) {
       mbar_init(smem_u32(bar_n_full + s), 32);                    // every loader lane arrives
       mbar_init(smem_u32(bar_n_empty + s), kProducerWarps);
     }
-    mbar_init(smem_u32(bar_accum), T);
+    mbar_init(smem_u32(bar_accum), Tr);
     for (int s = 0; s < kProducerWarps * Cfg::DEPTH; ++s) mbar_init(smem_u32(bar_gather + s), 1);
     fence_barrier_init();
   }
@@ -411,8 +419,10 @@ __global__ void __launch_bounds__(kTcThreads, 1) spconv_tc_kernel(const __grid_c
     // straight into the warp's shared-memory ring with cp.async (a missing neighbour is a zero-fill), so the
     // number of rows in flight is bounded by the ring, not by registers or scoreboards.  A warp gathers exactly
     // the 16 rows it later converts, so only warp-level synchronisation is needed.
-    // This warp's steps are s = grp, grp + kGroups, ...; step s = (lk * NCHUNK + lc) * T + lt.
-    int lk = 0, lc = 0, lt = grp;                // gather stream position (offset step, chunk, tile); kGroups <= T
+    // This warp's steps are s = grp, grp + kGroups, ...; step s = (lk * NCHUNK + lc) * Tr + lt.  The host guarantees
+    // Tr * NCHUNK >= kGroups, so every group has a step in every offset step (the slot protocol relies on it).
+    int lk = 0, lc = 0, lt = grp;                // gather stream position (offset step, chunk, tile)
+    while (lt >= Tr) { lt -= Tr; ++lc; }
     int lk_ready = -1;                           // last offset step whose neighbour slice this warp has waited for
     int gstage = 0, cstage = 0;                  // ring positions of the gather / convert streams
     uint32_t cphase = 0;                         // mbarrier phase of the convert stream (TMA gather)
@@ -459,8 +469,8 @@ __global__ void __launch_bounds__(kTcThreads, 1) spconv_tc_kernel(const __grid_c
       }
       if (++gstage == DEPTH) gstage = 0;
       lt += kGroups;
-      if (lt >= T) {
-        lt -= T;
+      while (lt >= Tr) {
+        lt -= Tr;
         if (++lc == NCHUNK) {
           lc = 0;
           __syncwarp();                          // every lane has read this step's indices
@@ -541,7 +551,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) spconv_tc_kernel(const __grid_c
       if (sstage >= SA) { sstage -= SA; sphase ^= 1; }
     };
 
-    const int my_steps = nsteps / kGroups;       // nsteps = KS * NCHUNK * T is a multiple of kGroups
+    const int my_steps = (nsteps - grp + kGroups - 1) / kGroups;
 #pragma unroll 1
     for (int i = 0; i < DEPTH; ++i) {
       if (i < my_steps) { gather_prefetch(); gather_issue(); } else if (!use_tma) cp_async_commit();
@@ -566,14 +576,14 @@ __global__ void __launch_bounds__(kTcThreads, 1) spconv_tc_kernel(const __grid_c
     const int act = A.act, res_after = A.res_after_act;
     constexpr int EPC = Cfg::EPC;
 #pragma unroll 1
-    for (int t = t_first; t < T; t += 4) {
+    for (int t = t_first; t < Tr; t += 4) {
       const int row = tile0 + t * kBM + g * 32 + lane;
-      const int orow = (row < n_out && A.out_rows) ? __ldg(A.out_rows + row) : row;
+      const int orow = (row < row_end && A.out_rows) ? __ldg(A.out_rows + row) : row;
 #pragma unroll 1
       for (int c0 = c_lo; c0 < c_hi; c0 += EPC) {
         uint32_t acc[EPC];
         tmem_ld<EPC>(tmem_base + ((uint32_t)(g * 32) << 16) + (uint32_t)(t * Cfg::ACC_STRIDE + c0), acc);
-        if (row < n_out && !S2D_DBG(A, 16)) {
+        if (row < row_end && !S2D_DBG(A, 16)) {
           float* dst = A.out + (size_t)orow * A.out_ld + cblk + c0;
           const float* res = A.residual ? A.residual + (size_t)orow * A.res_ld + cblk + c0 : nullptr;
 #pragma unroll
@@ -612,7 +622,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) spconv_tc_kernel(const __grid_c
         const int* src = tbl + (size_t)k * tbl_stride + tile0;
 #pragma unroll
         for (int i = 0; i < Cfg::ROWS / 32; ++i)     // all loads in flight before the first store
-          v[sb][i] = (live && tile0 + lane + 32 * i < n_out) ? __ldg(src + lane + 32 * i) : -1;
+          v[sb][i] = (live && tile0 + lane + 32 * i < row_end) ? __ldg(src + lane + 32 * i) : -1;
       }
 #pragma unroll
       for (int sb = 0; sb < kMaxKps; ++sb) {
@@ -642,7 +652,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) spconv_tc_kernel(const __grid_c
       }
       __syncwarp();
     }
-  } else if (warp - kMmaWarp0 < T) {
+  } else if (warp - kMmaWarp0 < Tr) {
     // ===================== MMA issuers: warp m owns row tile t = m =====================
     // One thread per tile issues that tile's MMAs (steps s = bstep * T + t): the issue loop of a single thread
     // (~100 instructions per step with the barrier handling) was the bottleneck of the whole kernel when one
@@ -697,7 +707,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) spconv_tc_kernel(const __grid_c
         umma_commit(bar_a_empty0 + 8 * stage);                  // gathered tile reusable once read
         umma_commit(bar_b_empty0 + 8 * bs);                     // weight tile: one of T arrivals
         if (b == nb - 1) umma_commit(smem_u32(bar_accum));      // this tile's accumulator complete
-        stage += T;
+        stage += Tr;
         while (stage >= SA) { stage -= SA; a_phase ^= 1; }
         if (++bs == SB) { bs = 0; b_phase ^= 1; }
       }
@@ -781,8 +791,18 @@ static int launch_tc(const ConvArgs& a, const CUtensorMap& in_map, int Cout, cud
                                   Cfg::SMEM_BYTES));
     configured = true;
   }
-  const dim3 grid(div_up(a.n_out, Cfg::ROWS), Cout / COUT);
-  spconv_tc_kernel<COUT, PASSES><<<grid, kTcThreads, Cfg::SMEM_BYTES, st>>>(a, in_map);
+  // Deal the 128-row tiles over a grid that is a whole number of waves (one CTA per SM): base..base+1 tiles per CTA,
+  // at most T; small problems get one tile per CTA (more SMs busy).
+  ConvArgs b = a;
+  const int n_tiles = div_up(a.n_out, kBM);
+  const int g_full = div_up(n_tiles, Cfg::T);
+  int gx = div_up(g_full, kNumSMs) * kNumSMs;
+  if (gx > n_tiles) gx = n_tiles;
+  b.tile_base = n_tiles / gx;
+  b.tile_rem = n_tiles % gx;
+  b.t_min = a.nchunk >= kGroups ? 1 : kGroups;                      // Tr * NCHUNK >= kGroups
+  const dim3 grid(gx, Cout / COUT);
+  spconv_tc_kernel<COUT, PASSES><<<grid, kTcThreads, Cfg::SMEM_BYTES, st>>>(b, in_map);
   S2D_LAUNCH_CHECK();
   count_launches(1);
   return S2D_OK;
