@@ -272,12 +272,12 @@ struct TcCfg {
   static constexpr int B_TILE = COUT * kBK * 4;        // 2 / 4 / 8 / 16 KB (COUT rows x 128 B)
   static constexpr int B_STAGE = NPART * B_TILE;
   static constexpr int SB = COUT >= 128 ? 3 : 4;       // weight-tile ring (shared memory)
-  static constexpr int ACC_STRIDE = COUT < 32 ? 32 : COUT;   // accumulators of different tiles (issued by different
-                                                       // threads) never share a 32-column TMEM granule
+  static constexpr int ACC_STRIDE = COUT < 32 ? 32 : COUT;   // TMEM allocation granule
   static constexpr int ACC_COLS = T * ACC_STRIDE;      // TMEM: accumulators ...
   static constexpr int A_COLS = NPART * kBK;           // ... and one gathered A stage: 32 TF32 columns (+ 32 more)
   static constexpr int SA_RAW = (512 - ACC_COLS) / A_COLS;
-  static constexpr int SA = SA_RAW > 8 ? 8 : SA_RAW;   // gathered-tile ring (TMEM)
+  static constexpr int SA_CAP = SA_RAW > 8 ? 8 : SA_RAW;
+  static constexpr int SA = SA_CAP - SA_CAP % kGroups;   // gathered-tile ring (TMEM); see "phase aliasing" below
   static constexpr int TMEM_COLS = 512;
   static constexpr int DEPTH = COUT >= 128 ? 3 : 4;    // gathered steps in flight per producer warp (cp.async ring)
   static constexpr int A_WARP_STAGE = 16 * 128;        // 16 rows x 128 B per producer warp and step
@@ -287,7 +287,14 @@ struct TcCfg {
   static constexpr int SMEM_BYTES = SB * B_STAGE + A_RING_BYTES + NBR_BYTES + 1024 + 1024;
   static_assert(SMEM_BYTES <= 227 * 1024, "shared memory budget");
   static_assert(COUT % 16 == 0 && COUT >= 16 && COUT <= 128, "UMMA N constraint for M=128 / TMEM budget");
-  static_assert(SA >= 2 && SA >= kGroups, "gathered-tile ring too small");
+  // mbarrier waits are parity waits: a waiter must never be more than one phase behind a barrier it waits on.
+  //  * producers: a stage's uses are the steps s = stage (mod SA); with SA a multiple of kGroups they all belong to ONE
+  //    producer group, whose warps therefore see every phase of that stage's barriers (an odd SA broke this);
+  //  * MMA warps: tile t consumes the steps s = t (mod Tr).  It sees every phase of a stage iff Tr divides SA; for
+  //    even Tr the phases it skips were delivered earlier by the same producer group (in order), so they are complete.
+  //    An odd Tr that does not divide SA (3 with SA = 4 or 8) is NOT safe: launch_tc never hands out 3 tiles then.
+  static constexpr bool TR3_OK = SA % 3 == 0;
+  static_assert(SA >= 2 && SA >= kGroups && SA % kGroups == 0, "gathered-tile ring: see phase aliasing");
   static_assert(T >= kGroups, "producer groups split the steps of an offset step");
 };
 
@@ -314,7 +321,7 @@ struct ConvArgs {
   float* out;
   const int* out_rows;
   int in_ld, out_ld, res_ld, tbl_stride, n_out, K, nchunk, kps, ksteps, act, res_after_act, use_tma;
-  int tile_base, tile_rem;   // CTA b owns tile_base + (b < tile_rem) consecutive 128-row tiles (<= T): see launch_tc
+  int tile_unit, unit_base, unit_rem, n_tiles;   // CTA b owns (unit_base + (b < unit_rem)) * tile_unit consecutive tiles
   int t_min;                 // tiles a CTA executes at least (virtual empty tiles) so that Tr * nchunk >= kGroups
   int dbg;   // ablation switches for tools/ablate_spconv.py (0 in production): 1 no gather, 2 no TMEM store, 4 no MMA
 };
@@ -361,11 +368,13 @@ __global__ void __launch_bounds__(kTcThreads, 1) spconv_tc_kernel(const __grid_c
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   // Balanced tiling: the 128-row tiles are dealt evenly over a grid that is a multiple of the SM count, so the last
   // wave is as loaded as the others (a CTA's time is proportional to its tile count Tr <= T).
-  const int t_real = A.tile_base + ((int)blockIdx.x < A.tile_rem ? 1 : 0);
-  if (t_real == 0) return;
-  const int Tr = max(t_real, A.t_min);        // extra tiles are virtual: no rows loaded, none stored
-  const int tile0 = ((int)blockIdx.x * A.tile_base + min((int)blockIdx.x, A.tile_rem)) * kBM;
-  const int row_end = min(n_out, tile0 + t_real * kBM);
+  const int bx = (int)blockIdx.x;
+  const int t_alloc = (A.unit_base + (bx < A.unit_rem ? 1 : 0)) * A.tile_unit;
+  const int tile_first = (bx * A.unit_base + min(bx, A.unit_rem)) * A.tile_unit;
+  if (t_alloc == 0 || tile_first >= A.n_tiles) return;
+  const int Tr = max(t_alloc, A.t_min);       // tiles past the CTA's real ones are virtual: no rows loaded, none stored
+  const int tile0 = tile_first * kBM;
+  const int row_end = min(n_out, tile0 + t_alloc * kBM);
   const int nsteps = KS * NCHUNK * Tr;
 
   if (warp == kMmaWarp0 && lane == 0) {
@@ -791,15 +800,19 @@ static int launch_tc(const ConvArgs& a, const CUtensorMap& in_map, int Cout, cud
                                   Cfg::SMEM_BYTES));
     configured = true;
   }
-  // Deal the 128-row tiles over a grid that is a whole number of waves (one CTA per SM): base..base+1 tiles per CTA,
-  // at most T; small problems get one tile per CTA (more SMs busy).
+  // Deal the 128-row tiles over a grid that is a whole number of waves (one CTA per SM), at most T per CTA; small
+  // problems get one tile per CTA (more SMs busy).  Where 3 tiles per CTA would alias mbarrier phases (TcCfg), tiles
+  // are dealt in pairs (2 or 4 per CTA).
   ConvArgs b = a;
   const int n_tiles = div_up(a.n_out, kBM);
   const int g_full = div_up(n_tiles, Cfg::T);
   int gx = div_up(g_full, kNumSMs) * kNumSMs;
   if (gx > n_tiles) gx = n_tiles;
-  b.tile_base = n_tiles / gx;
-  b.tile_rem = n_tiles % gx;
+  b.tile_unit = (!Cfg::TR3_OK && Cfg::T >= 3 && n_tiles / gx >= 2) ? 2 : 1;
+  const int units = div_up(n_tiles, b.tile_unit);
+  b.unit_base = units / gx;
+  b.unit_rem = units % gx;
+  b.n_tiles = n_tiles;
   b.t_min = a.nchunk >= kGroups ? 1 : kGroups;                      // Tr * NCHUNK >= kGroups
   const dim3 grid(gx, Cout / COUT);
   spconv_tc_kernel<COUT, PASSES><<<grid, kTcThreads, Cfg::SMEM_BYTES, st>>>(b, in_map);
