@@ -329,6 +329,36 @@ int s2d_gather_rows(const float* in, int in_ld, const int* idx, long long n_out,
 int s2d_grid2d_tconv_table_s(int B, int H, int W, int k, int stride, int pad, int py, int px, int* tbl,
                              int tbl_stride, int* out_rows, void* stream);
 
+/* ---------------------------------------------------------------------------------------
+ * Loss values of the distillation training step (forward only).  Every function is a
+ * single pass over its inputs with a deterministic two-level reduction in double; results are device doubles.
+ * A map element (b, c, cell) lives at base + b*sb + c*sc + cell*scell floats (NCHW: sc = H*W, scell = 1; NHWC rows:
+ * sc = 1, scell = row stride), so the head outputs can be read where they are.
+ *
+ * s2d_masked_mse: out4 = { sum_{t>0} (s-t)^2, #{t>0}, sum_{t<=0} (s-t)^2, #{t<=0} } over n elements -- the
+ *   sparse2dense_loss terms F.mse_loss(F_S[F_D>0], F_D[F_D>0]) and F.mse_loss(F_S[~], F_D[~])
+ *   (det3d/torchie/trainer/trainer.py:783-789) are out4[0]/out4[1] and out4[2]/out4[3].
+ * s2d_focal_loss: FastFocalLoss.forward / fastfocalloss (det3d/models/losses/centernet_loss.py:27-54, trainer.py:38-58):
+ *   out3 = { sum log(1-o) o^2 (1-t)^4 over the map, sum log(p)(1-p)^2 mask over the M peaks, sum mask };
+ *   loss = -(out3[0] + out3[1]) / out3[2], or -out3[0] when out3[2] == 0.  out_is_logits applies
+ *   CenterHead._sigmoid (clamped sigmoid, center_head.py:246-248), target_is_logits applies sigmoid (trainer.py:792).
+ *   ind i64 [B,M] (cell), mask u8 [B,M], cat i64 [B,M].
+ * s2d_gather_reg_loss: RegLoss.forward (centernet_loss.py:6-25; squared = 0) and distill_reg_loss (trainer.py:68-76;
+ *   squared = 1, target_map = the teacher's anno_box map): out[d] = sum_{b,m} err(pred*mask, target*mask) for
+ *   d < D <= 16 and out[16] = sum(mask); loss[d] = out[d] / (out[16] + 1e-4).  target_rows f32 [B,M,D] or target_map.
+ * ------------------------------------------------------------------------------------- */
+size_t s2d_loss_workspace_bytes(void);
+int s2d_masked_mse(const float* f_student, const float* f_teacher, long long n, double* out4, void* workspace,
+                   size_t workspace_bytes, void* stream);
+int s2d_focal_loss(const float* out, long long out_sb, long long out_sc, long long out_scell, int out_is_logits,
+                   const float* target, long long tgt_sb, long long tgt_sc, long long tgt_scell, int target_is_logits,
+                   int B, int C, int HW, const long long* ind, const unsigned char* mask, const long long* cat, int M,
+                   double* out3, void* workspace, size_t workspace_bytes, void* stream);
+int s2d_gather_reg_loss(const float* pred, long long pred_sb, long long pred_sc, long long pred_scell,
+                        const float* target_rows, const float* target_map, long long tgt_sb, long long tgt_sc,
+                        long long tgt_scell, int B, int M, int D, int squared, const long long* ind,
+                        const unsigned char* mask, double* out, void* workspace, size_t workspace_bytes, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

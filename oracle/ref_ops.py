@@ -306,3 +306,43 @@ def roi_refine(rois, roi_scores, rcnn_cls, rcnn_reg):
     out[:, 3:7] = reg[:, 3:7] + rois[:, 3:7]
     sg = (f(1) / (f(1) + np.exp(-rcnn_cls.reshape(-1).astype(f)))).astype(f)
     return out, np.sqrt(sg * roi_scores.astype(f)).astype(f)
+
+
+# ------------------------------------------------------------------------------------------
+# Loss values (centernet_loss.py:6-54, trainer.py:38-76,783-789); maps are NCHW numpy arrays.
+# PINNED by tests/golden/losses.npz (the reference's own FastFocalLoss / RegLoss classes through the shim).
+# ------------------------------------------------------------------------------------------
+def _gather_map(m, ind):
+    B, C, H, W = m.shape
+    f = m.transpose(0, 2, 3, 1).reshape(B, H * W, C)
+    return np.take_along_axis(f, ind[:, :, None].astype(np.int64), axis=1)          # [B,M,C]
+
+
+def fast_focal_loss(out, target, ind, mask, cat):
+    out, target = out.astype(np.float32), target.astype(np.float32)
+    m = mask.astype(np.float32)
+    neg = (np.log(1 - out) * out ** 2 * (1 - target) ** 4).astype(np.float64).sum()
+    pp = np.take_along_axis(_gather_map(out, ind), cat[:, :, None].astype(np.int64), axis=2)[:, :, 0]
+    pos = (np.log(pp) * (1 - pp) ** 2 * m).astype(np.float64).sum()
+    n = m.sum()
+    return np.float32(-neg if n == 0 else -(pos + neg) / n)
+
+
+def reg_loss(output, mask, ind, target, squared=False):
+    """RegLoss (L1) / distill_reg_loss (squared, ``target`` an NCHW map)."""
+    pred = _gather_map(output.astype(np.float32), ind)
+    tgt = _gather_map(target.astype(np.float32), ind) if target.ndim == 4 else target.astype(np.float32)
+    m = mask.astype(np.float32)[:, :, None]
+    e = pred * m - tgt * m
+    e = e * e if squared else np.abs(e)
+    return (e.astype(np.float64).sum(axis=(0, 1)) / (m.sum() + 1e-4)).astype(np.float32)
+
+
+def sparse2dense_loss(F_S_a, F_D_a, F_S_b, F_D_b):
+    def terms(s, d):
+        q = (s.astype(np.float32) - d.astype(np.float32)).astype(np.float64) ** 2
+        p = d > 0
+        return q[p].mean(), q[~p].mean()
+    pa, na = terms(F_S_a, F_D_a)
+    pb, nb = terms(F_S_b, F_D_b)
+    return np.float32(10 * pa + 20 * na + 5 * pb + 20 * nb)

@@ -63,6 +63,14 @@ SIGNATURES = {
     "s2d_maxpool2d_rows": (_i, [_vp, _i, _i, _i, _i, _i, _vp, _i, _vp]),
     "s2d_gather_rows": (_i, [_vp, _i, _vp, ctypes.c_longlong, _i, _vp, _i, _vp]),
     "s2d_grid2d_tconv_table_s": (_i, [_i, _i, _i, _i, _i, _i, _i, _i, _vp, _i, _vp, _vp]),
+    "s2d_loss_workspace_bytes": (_sz, []),
+    "s2d_masked_mse": (_i, [_vp, _vp, ctypes.c_longlong, _vp, _vp, _sz, _vp]),
+    "s2d_focal_loss": (_i, [_vp, ctypes.c_longlong, ctypes.c_longlong, ctypes.c_longlong, _i,
+                            _vp, ctypes.c_longlong, ctypes.c_longlong, ctypes.c_longlong, _i,
+                            _i, _i, _i, _vp, _vp, _vp, _i, _vp, _vp, _sz, _vp]),
+    "s2d_gather_reg_loss": (_i, [_vp, ctypes.c_longlong, ctypes.c_longlong, ctypes.c_longlong, _vp, _vp,
+                                 ctypes.c_longlong, ctypes.c_longlong, ctypes.c_longlong, _i, _i, _i, _i, _vp, _vp, _vp,
+                                 _vp, _sz, _vp]),
 }
 
 

@@ -200,6 +200,36 @@ class CenterHead(nn.Module):
         meta = example.get("metadata") if isinstance(example, dict) else None
         return self.predict_rows(rows, B, H, W, test_cfg, meta if meta else None)
 
+    # -- loss values (center_head.py:250-291), forward only -----------------------------------------
+    @torch.no_grad()
+    def loss(self, example, preds_dicts, **kwargs):
+        """Same return structure as the reference (dict of per-task lists).  ``preds_dicts``: list of dict head -> NCHW
+        logits map or ``losses.Rows`` view.  Values only: autograd / backward are not built."""
+        from collections import defaultdict
+        from . import losses as L
+        crit_reg = L.RegLoss()
+        merged = defaultdict(list)
+        for task_id, preds in enumerate(preds_dicts):
+            hm_loss = L.fastfocalloss(preds["hm"], example["hm"][task_id], example["ind"][task_id],
+                                      example["mask"][task_id], example["cat"][task_id], out_is_logits=True)
+            target_box = example["anno_box"][task_id]
+            names = ["reg", "height", "dim"] + (["vel"] if "vel" in preds else []) + ["rot"]
+            if "vel" not in preds:
+                target_box = target_box[..., [0, 1, 2, 3, 4, 5, -2, -1]]                 # remove the velocity target
+            parts, off = [], 0
+            mask, ind = example["mask"][task_id], example["ind"][task_id]
+            for n in names:                                  # anno_box = cat(reg, height, dim, [vel], rot): per-head gathers
+                c = preds[n].rows.shape[1] if isinstance(preds[n], L.Rows) else preds[n].shape[1]
+                parts.append(crit_reg(preds[n], mask, ind, target_box[..., off:off + c].contiguous()))
+                off += c
+            box_loss = torch.cat(parts)
+            loc_loss = (box_loss * box_loss.new_tensor(self.code_weights)).sum()
+            ret = {"loss": hm_loss + self.weight * loc_loss, "hm_loss": hm_loss.detach().cpu(), "loc_loss": loc_loss,
+                   "loc_loss_elem": box_loss.detach().cpu(), "num_positive": mask.float().sum()}
+            for k, v in ret.items():
+                merged[k].append(v)
+        return merged
+
     def forward(self, x, *kwargs):
         """x NCHW [B,C,H,W] -> list of dicts of NCHW maps, like center_head.py:236-244."""
         B, _, H, W = x.shape

@@ -1,0 +1,196 @@
+// losses.cu -- forward values of the distillation / detection losses of the training step,
+// as single-pass, deterministic reductions (per-block partial sums in double, one final block):
+//   * s2d_masked_mse:   sparse2dense_loss terms, det3d/torchie/trainer/trainer.py:783-789
+//                       (F.mse_loss(F_S[F_D > 0], F_D[F_D > 0]) and the complement): the reference materialises four
+//                       boolean-indexed temporaries of up to 36 MB/scene; here one read of each map.
+//   * s2d_focal_loss:   FastFocalLoss.forward (det3d/models/losses/centernet_loss.py:27-54) == fastfocalloss
+//                       (trainer.py:38-58), with CenterHead._sigmoid (center_head.py:246-248) and F.sigmoid of the
+//                       teacher map (trainer.py:792) optionally fused.
+//   * s2d_gather_reg_loss: RegLoss.forward (centernet_loss.py:6-25, L1) and distill_reg_loss (trainer.py:68-76, squared
+//                       error, target gathered from the teacher map) incl. _transpose_and_gather_feat
+//                       (det3d/core/utils/center_utils.py:66-80).
+// Gradients are not built (the backward of the training step is a later round).
+#include "common.cuh"
+
+namespace s2d {
+
+constexpr int kRedThreads = 256;
+constexpr int kRedBlocks = 592;   // 4 per SM
+
+template <int N>
+__device__ __forceinline__ void block_reduce_store(double (&v)[N], double* __restrict__ partial) {
+  __shared__ double sh[N][kRedThreads / 32];
+#pragma unroll
+  for (int i = 0; i < N; ++i) {
+    double x = v[i];
+    for (int d = 16; d > 0; d >>= 1) x += __shfl_xor_sync(0xffffffffu, x, d);
+    if ((threadIdx.x & 31) == 0) sh[i][threadIdx.x >> 5] = x;
+  }
+  __syncthreads();
+  if (threadIdx.x < N) {
+    double s = 0.0;
+    for (int w = 0; w < kRedThreads / 32; ++w) s += sh[threadIdx.x][w];      // fixed order: deterministic
+    partial[(size_t)blockIdx.x * N + threadIdx.x] = s;
+  }
+}
+
+template <int N>
+__global__ void final_reduce_kernel(const double* __restrict__ partial, int nblocks, double* __restrict__ out) {
+  if (threadIdx.x < N) {
+    double s = 0.0;
+    for (int b = 0; b < nblocks; ++b) s += partial[(size_t)b * N + threadIdx.x];
+    out[threadIdx.x] = s;
+  }
+}
+
+// out[0] = sum_{d>0} (s-d)^2, out[1] = #{d>0}, out[2] = sum_{d<=0} (s-d)^2, out[3] = #{d<=0}
+__global__ void __launch_bounds__(kRedThreads) masked_mse_kernel(const float4* __restrict__ fs, const float4* __restrict__ fd,
+                                                                 long long n4, const float* __restrict__ fs_tail,
+                                                                 const float* __restrict__ fd_tail, int tail,
+                                                                 double* __restrict__ partial) {
+  float sp = 0.f, sn = 0.f;
+  unsigned cp = 0, cn = 0;
+  double acc[4] = {0.0, 0.0, 0.0, 0.0};
+  int since = 0;
+  auto one = [&](float s, float d) {
+    const float e = s - d, q = e * e;
+    if (d > 0.f) { sp += q; ++cp; } else { sn += q; ++cn; }
+  };
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
+    const float4 a = __ldg(fs + i), b = __ldg(fd + i);
+    one(a.x, b.x); one(a.y, b.y); one(a.z, b.z); one(a.w, b.w);
+    if (++since == 64) {                         // flush the fp32 running sums into double every 256 elements
+      acc[0] += sp; acc[2] += sn; sp = sn = 0.f; since = 0;
+    }
+  }
+  if (blockIdx.x == 0 && threadIdx.x < tail) one(fs_tail[threadIdx.x], fd_tail[threadIdx.x]);
+  acc[0] += sp; acc[2] += sn; acc[1] = (double)cp; acc[3] = (double)cn;
+  block_reduce_store<4>(acc, partial);
+}
+
+// element (b, c, cell) of a map lives at base + b*sb + c*sc + cell*scell (NCHW: sc = HW, scell = 1; NHWC rows: sc = 1, scell = ld)
+struct MapView { const float* p; long long sb, sc, scell; };
+__device__ __forceinline__ float map_at(const MapView& m, int b, int c, int cell) {
+  return __ldg(m.p + (long long)b * m.sb + (long long)c * m.sc + (long long)cell * m.scell);
+}
+__device__ __forceinline__ float sigmoidf_rn(float x) { return __fdiv_rn(1.f, __fadd_rn(1.f, expf(-x))); }
+
+// out[0] = neg_loss sum, out[1] = pos_loss sum, out[2] = num_pos
+__global__ void __launch_bounds__(kRedThreads) focal_loss_kernel(MapView out, MapView tgt, int B, int C, int HW,
+                                                                 int out_logits, int tgt_logits,
+                                                                 const long long* __restrict__ ind,
+                                                                 const unsigned char* __restrict__ mask,
+                                                                 const long long* __restrict__ cat, int M,
+                                                                 double* __restrict__ partial) {
+  double acc[3] = {0.0, 0.0, 0.0};
+  const long long total = (long long)B * C * HW;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int cell = (int)(i % HW), c = (int)((i / HW) % C), b = (int)(i / ((long long)HW * C));
+    float o = map_at(out, b, c, cell), t = map_at(tgt, b, c, cell);
+    if (out_logits) o = fminf(fmaxf(sigmoidf_rn(o), 1e-4f), 1.f - 1e-4f);        // CenterHead._sigmoid
+    if (tgt_logits) t = sigmoidf_rn(t);
+    const float g1 = 1.f - t, g2 = g1 * g1;
+    acc[0] += (double)(logf(1.f - o) * (o * o) * (g2 * g2));                       // log(1-out) * out^2 * (1-target)^4
+  }
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < (long long)B * M; i += (long long)gridDim.x * blockDim.x) {
+    const int b = (int)(i / M);
+    const float m = mask[i] ? 1.f : 0.f;
+    float p = map_at(out, b, (int)cat[i], (int)ind[i]);
+    if (out_logits) p = fminf(fmaxf(sigmoidf_rn(p), 1e-4f), 1.f - 1e-4f);
+    const float q = 1.f - p;
+    acc[1] += (double)(logf(p) * (q * q) * m);
+    acc[2] += (double)m;
+  }
+  block_reduce_store<3>(acc, partial);
+}
+
+// out[d] = sum_{b,m} err(pred*mask, target*mask), d < D; out[D] = sum(mask).  squared: 0 = L1 (RegLoss), 1 = squared error.
+// target: either tgt_rows f32 [B, M, D] or a map (tgt_map.p != null) gathered at the same indices.
+constexpr int kRegMaxD = 16;
+__global__ void __launch_bounds__(kRedThreads) gather_reg_loss_kernel(MapView pred, const float* __restrict__ tgt_rows,
+                                                                      MapView tgt_map, int B, int M, int D, int squared,
+                                                                      const long long* __restrict__ ind,
+                                                                      const unsigned char* __restrict__ mask,
+                                                                      double* __restrict__ partial) {
+  double acc[kRegMaxD + 1];
+#pragma unroll
+  for (int d = 0; d <= kRegMaxD; ++d) acc[d] = 0.0;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < (long long)B * M; i += (long long)gridDim.x * blockDim.x) {
+    const int b = (int)(i / M);
+    const float m = mask[i] ? 1.f : 0.f;
+    const int cell = (int)ind[i];
+#pragma unroll
+    for (int d = 0; d < kRegMaxD; ++d) {
+      if (d < D) {
+        const float p = map_at(pred, b, d, cell) * m;
+        const float t = (tgt_map.p ? map_at(tgt_map, b, d, cell) : tgt_rows[i * D + d]) * m;
+        const float e = p - t;
+        acc[d] += (double)(squared ? e * e : fabsf(e));
+      }
+    }
+    acc[kRegMaxD] += (double)m;
+  }
+  block_reduce_store<kRegMaxD + 1>(acc, partial);
+}
+
+}  // namespace s2d
+
+using namespace s2d;
+
+extern "C" size_t s2d_loss_workspace_bytes(void) { return (size_t)kRedBlocks * (kRegMaxD + 1) * sizeof(double); }
+
+extern "C" int s2d_masked_mse(const float* f_student, const float* f_teacher, long long n, double* out4, void* workspace,
+                              size_t workspace_bytes, void* stream) {
+  S2D_REQUIRE(f_student && f_teacher && out4 && workspace && n >= 0, "s2d_masked_mse: bad argument");
+  S2D_REQUIRE(workspace_bytes >= s2d_loss_workspace_bytes(), "s2d_masked_mse: workspace too small");
+  S2D_REQUIRE(((reinterpret_cast<uintptr_t>(f_student) | reinterpret_cast<uintptr_t>(f_teacher)) & 15) == 0,
+              "s2d_masked_mse: maps must be 16-byte aligned");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  double* partial = static_cast<double*>(workspace);
+  const long long n4 = n / 4;
+  masked_mse_kernel<<<kRedBlocks, kRedThreads, 0, st>>>(reinterpret_cast<const float4*>(f_student),
+                                                       reinterpret_cast<const float4*>(f_teacher), n4, f_student + 4 * n4,
+                                                       f_teacher + 4 * n4, (int)(n - 4 * n4), partial);
+  final_reduce_kernel<4><<<1, 32, 0, st>>>(partial, kRedBlocks, out4);
+  S2D_LAUNCH_CHECK();
+  count_launches(2);
+  return S2D_OK;
+}
+
+extern "C" int s2d_focal_loss(const float* out, long long out_sb, long long out_sc, long long out_scell, int out_is_logits,
+                              const float* target, long long tgt_sb, long long tgt_sc, long long tgt_scell,
+                              int target_is_logits, int B, int C, int HW, const long long* ind, const unsigned char* mask,
+                              const long long* cat, int M, double* out3, void* workspace, size_t workspace_bytes,
+                              void* stream) {
+  S2D_REQUIRE(out && target && ind && mask && cat && out3 && workspace, "s2d_focal_loss: null argument");
+  S2D_REQUIRE(B >= 1 && C >= 1 && HW >= 1 && M >= 0, "s2d_focal_loss: bad sizes");
+  S2D_REQUIRE(workspace_bytes >= s2d_loss_workspace_bytes(), "s2d_focal_loss: workspace too small");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  double* partial = static_cast<double*>(workspace);
+  focal_loss_kernel<<<kRedBlocks, kRedThreads, 0, st>>>(MapView{out, out_sb, out_sc, out_scell},
+                                                       MapView{target, tgt_sb, tgt_sc, tgt_scell}, B, C, HW, out_is_logits,
+                                                       target_is_logits, ind, mask, cat, M, partial);
+  final_reduce_kernel<3><<<1, 32, 0, st>>>(partial, kRedBlocks, out3);
+  S2D_LAUNCH_CHECK();
+  count_launches(2);
+  return S2D_OK;
+}
+
+extern "C" int s2d_gather_reg_loss(const float* pred, long long pred_sb, long long pred_sc, long long pred_scell,
+                                   const float* target_rows, const float* target_map, long long tgt_sb, long long tgt_sc,
+                                   long long tgt_scell, int B, int M, int D, int squared, const long long* ind,
+                                   const unsigned char* mask, double* out, void* workspace, size_t workspace_bytes,
+                                   void* stream) {
+  S2D_REQUIRE(pred && (target_rows || target_map) && ind && mask && out && workspace, "s2d_gather_reg_loss: null argument");
+  S2D_REQUIRE(B >= 1 && M >= 0 && D >= 1 && D <= kRegMaxD, "s2d_gather_reg_loss: D outside [1,%d]", kRegMaxD);
+  S2D_REQUIRE(workspace_bytes >= s2d_loss_workspace_bytes(), "s2d_gather_reg_loss: workspace too small");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  double* partial = static_cast<double*>(workspace);
+  gather_reg_loss_kernel<<<kRedBlocks, kRedThreads, 0, st>>>(MapView{pred, pred_sb, pred_sc, pred_scell}, target_rows,
+                                                            MapView{target_map, tgt_sb, tgt_sc, tgt_scell}, B, M, D,
+                                                            squared, ind, mask, partial);
+  final_reduce_kernel<kRegMaxD + 1><<<1, 32, 0, st>>>(partial, kRedBlocks, out);
+  S2D_LAUNCH_CHECK();
+  count_launches(2);
+  return S2D_OK;
+}

@@ -1,0 +1,104 @@
+"""Loss values of the detection / distillation training step, forward only:
+``FastFocalLoss`` / ``RegLoss`` (det3d/models/losses/centernet_loss.py:6-54), ``fastfocalloss`` / ``distill_reg_loss`` and the
+``sparse2dense_loss`` expression of ``TS_Trainer.batch_processor_inline`` (det3d/torchie/trainer/trainer.py:38-76,783-799),
+each as ONE deterministic reduction launch (csrc/losses.cu).  No autograd: the backward pass is not built yet.
+
+A *map* argument is either a torch NCHW tensor ``[B,C,H,W]`` or a ``Rows`` view (NHWC rows ``[B*H*W, c]`` that may be a
+column slice of a wider buffer, as the heads of this package produce them)."""
+from collections import namedtuple
+
+import torch
+from torch import nn
+
+from . import _lib, ops
+
+Rows = namedtuple("Rows", "rows B HW")     # rows: 2-D tensor with stride(1) == 1
+
+
+def _view(m):
+    """-> (tensor keeping the storage alive, ptr, sb, sc, scell, B, C, HW)."""
+    if isinstance(m, Rows):
+        r = m.rows
+        assert r.dim() == 2 and r.stride(1) == 1 and r.shape[0] == m.B * m.HW and r.dtype == torch.float32
+        return r, r.data_ptr(), m.HW * r.stride(0), 1, r.stride(0), m.B, r.shape[1], m.HW
+    t = m.contiguous().float()
+    B, C, H, W = t.shape
+    return t, t.data_ptr(), C * H * W, H * W, 1, B, C, H * W
+
+
+def _ws(dev):
+    n = _lib.load().s2d_loss_workspace_bytes()
+    return torch.empty((n,), dtype=torch.uint8, device=dev), n
+
+
+def masked_mse_terms(f_student, f_teacher):
+    """-> float64 [4]: sum / count over teacher > 0, sum / count over teacher <= 0 of (student - teacher)^2."""
+    ops._need_cuda(f_student, f_teacher)
+    fs, fd = f_student.contiguous().float(), f_teacher.contiguous().float()
+    assert fs.numel() == fd.numel()
+    out = torch.empty((4,), dtype=torch.float64, device=fs.device)
+    ws, n = _ws(fs.device)
+    _lib.check(_lib.load().s2d_masked_mse(fs.data_ptr(), fd.data_ptr(), fs.numel(), out.data_ptr(), ws.data_ptr(), n,
+                                          ops._stream()), "s2d_masked_mse")
+    return out
+
+
+def sparse2dense_loss(F_S_a, F_D_a, F_S_b, F_D_b, w=(10.0, 20.0, 5.0, 20.0)):
+    """trainer.py:783-789: 10*MSE(a | F_D_a>0) + 20*MSE(a | <=0) + 5*MSE(b | F_D_b>0) + 20*MSE(b | <=0) (fp32 scalar)."""
+    a, b = masked_mse_terms(F_S_a, F_D_a), masked_mse_terms(F_S_b, F_D_b)
+    return (w[0] * a[0] / a[1] + w[1] * a[2] / a[3] + w[2] * b[0] / b[1] + w[3] * b[2] / b[3]).float()
+
+
+def _peaks(ind, mask, cat=None):
+    ind = ind.contiguous().long()
+    mask8 = mask.contiguous().to(torch.uint8)
+    return ind, mask8, (None if cat is None else cat.contiguous().long())
+
+
+def fastfocalloss(out, target, ind, mask, cat, out_is_logits=False, target_is_logits=False):
+    """FastFocalLoss.forward.  ``out_is_logits`` fuses CenterHead._sigmoid, ``target_is_logits`` fuses F.sigmoid."""
+    ko, po, osb, osc, oscell, B, C, HW = _view(out)
+    kt, pt, tsb, tsc, tscell, Bt, Ct, HWt = _view(target)
+    assert (B, C, HW) == (Bt, Ct, HWt)
+    ind, mask8, cat = _peaks(ind, mask, cat)
+    res = torch.empty((3,), dtype=torch.float64, device=ko.device)
+    ws, n = _ws(ko.device)
+    _lib.check(_lib.load().s2d_focal_loss(po, osb, osc, oscell, int(out_is_logits), pt, tsb, tsc, tscell,
+                                          int(target_is_logits), B, C, HW, ind.data_ptr(), mask8.data_ptr(), cat.data_ptr(),
+                                          ind.shape[1], res.data_ptr(), ws.data_ptr(), n, ops._stream()), "s2d_focal_loss")
+    neg, pos, num = res[0], res[1], res[2]
+    return torch.where(num == 0, -neg, -(pos + neg) / torch.clamp(num, min=1.0)).float()
+
+
+def _reg(output, mask, ind, target_rows, target_map, squared):
+    ko, po, osb, osc, oscell, B, D, HW = _view(output)
+    ind, mask8, _ = _peaks(ind, mask)
+    res = torch.empty((17,), dtype=torch.float64, device=ko.device)
+    ws, n = _ws(ko.device)
+    if target_map is not None:
+        kt, pt, tsb, tsc, tscell, _, Dt, _ = _view(target_map)
+        assert Dt == D
+        tr = None
+    else:
+        kt, pt, tsb, tsc, tscell = None, None, 0, 0, 0
+        tr = target_rows.contiguous().float()
+        assert tuple(tr.shape) == (B, ind.shape[1], D)
+    _lib.check(_lib.load().s2d_gather_reg_loss(po, osb, osc, oscell, None if tr is None else tr.data_ptr(), pt, tsb, tsc,
+                                               tscell, B, ind.shape[1], D, int(squared), ind.data_ptr(), mask8.data_ptr(),
+                                               res.data_ptr(), ws.data_ptr(), n, ops._stream()), "s2d_gather_reg_loss")
+    return (res[:D] / (res[16] + 1e-4)).float()
+
+
+def distill_reg_loss(output, target, mask, ind):
+    """trainer.py:68-76: squared error between the student's and the teacher's anno_box maps gathered at ``ind``."""
+    return _reg(output, mask, ind, None, target, True)
+
+
+class RegLoss(nn.Module):
+    def forward(self, output, mask, ind, target):
+        return _reg(output, mask, ind, target, None, False)
+
+
+class FastFocalLoss(nn.Module):
+    def forward(self, out, target, ind, mask, cat):
+        return fastfocalloss(out, target, ind, mask, cat)

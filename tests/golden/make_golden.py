@@ -487,7 +487,64 @@ def make_pillar_goldens():
                         neck_seed=33, n_pillars=len(voxels), coors_checksum=np.int64(coors4.astype(np.int64).sum()), **out)
 
 
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+from loss_common import loss_inputs  # noqa: E402
+
+
+def make_loss_goldens():
+    """FastFocalLoss / RegLoss of the reference (shim) + the trainer's distill expressions restated on torch CPU."""
+    import torch
+    import torch.nn.functional as F
+    from oracle import ref_ops as R
+    rpn, ch, logger = reference_dense_modules()
+    sys.modules.pop("det3d.core.utils.center_utils", None)
+    import types
+    cu = types.ModuleType("det3d.core.utils.center_utils")
+
+    def _tg(feat, ind):                      # center_utils.py:66-80 (the real file needs cv2 + numba)
+        feat = feat.permute(0, 2, 3, 1).contiguous()
+        feat = feat.view(feat.size(0), -1, feat.size(3))
+        return feat.gather(1, ind.unsqueeze(2).expand(ind.size(0), ind.size(1), feat.size(2)))
+    cu._transpose_and_gather_feat = _tg
+    sys.modules["det3d.core.utils.center_utils"] = cu
+    import det3d.models.losses.centernet_loss as cl
+    cl._transpose_and_gather_feat = _tg          # the module may have been imported earlier with the stub
+    save = {}
+    for seed in (40, 41):
+        d = loss_inputs(seed)
+        t = {k: torch.from_numpy(v) for k, v in d.items()}
+        out = torch.clamp(torch.sigmoid(t["hm_logits"]), min=1e-4, max=1 - 1e-4)
+        hm = cl.FastFocalLoss()(out, t["gt_hm"], t["ind"], t["mask"], t["cat"])
+        kd = cl.FastFocalLoss()(out, torch.sigmoid(t["t_logits"]), t["ind"], t["mask"], t["cat"])
+        reg = cl.RegLoss()(t["box"], t["mask"], t["ind"], t["anno"])
+        pred, gt = _tg(t["box"], t["ind"]), _tg(t["t_box"], t["ind"])                        # trainer.py:68-76
+        m = t["mask"].float().unsqueeze(2)
+        dl = (F.mse_loss(pred * m, gt * m, reduction="none") / (m.sum() + 1e-4)).transpose(2, 0).sum(dim=2).sum(dim=1)
+        fs, fd = t["box"], t["t_box"]                                                        # trainer.py:783-789 on small maps
+        inds = fd > 0
+        s2d = F.mse_loss(fs[inds], fd[inds]) * 10 + F.mse_loss(fs[~inds], fd[~inds]) * 20
+        inds = t["t_logits"] > 0
+        s2d = s2d + F.mse_loss(t["hm_logits"][inds], t["t_logits"][inds]) * 5 + F.mse_loss(t["hm_logits"][~inds], t["t_logits"][~inds]) * 20
+        ref = dict(hm=hm.numpy(), kd=kd.numpy(), reg=reg.numpy(), dl=dl.numpy(), s2d=s2d.numpy())
+        o_out = np.clip(1 / (1 + np.exp(-d["hm_logits"])), 1e-4, 1 - 1e-4).astype(np.float32)
+        o_t = (1 / (1 + np.exp(-d["t_logits"]))).astype(np.float32)
+        got = dict(hm=R.fast_focal_loss(o_out, d["gt_hm"], d["ind"], d["mask"], d["cat"]),
+                   kd=R.fast_focal_loss(o_out, o_t, d["ind"], d["mask"], d["cat"]),
+                   reg=R.reg_loss(d["box"], d["mask"], d["ind"], d["anno"]),
+                   dl=R.reg_loss(d["box"], d["mask"], d["ind"], d["t_box"], squared=True),
+                   s2d=R.sparse2dense_loss(d["box"], d["t_box"], d["hm_logits"], d["t_logits"]))
+        for k in ref:
+            err = np.abs(np.asarray(got[k]) - ref[k]).max() / max(np.abs(ref[k]).max(), 1e-12)
+            print(f"loss seed {seed} {k}: reference {np.asarray(ref[k]).reshape(-1)[:3]} oracle rel err {err:.1e}")
+            assert err < 2e-5, k
+            save[f"{seed}_{k}"] = np.asarray(ref[k], np.float32)
+    np.savez_compressed(os.path.join(HERE, "losses.npz"), **save)
+
+
 if __name__ == "__main__":
+    if len(sys.argv) > 1 and sys.argv[1] == "loss":
+        make_loss_goldens()
+        sys.exit(0)
     if len(sys.argv) > 1 and sys.argv[1] == "pp":
         make_pillar_goldens()
         sys.exit(0)
@@ -506,3 +563,4 @@ if __name__ == "__main__":
     make_predict_goldens()
     make_second_stage_goldens()
     make_pillar_goldens()
+    make_loss_goldens()
