@@ -288,7 +288,9 @@ def run_gpu(args):
                     "fp32_simt": {"achieved_tflops": tfl, "nominal_peak_tflops": FP32_SIMT_PEAK_TFLOPS,
                                   "frac": tfl / FP32_SIMT_PEAK_TFLOPS}}
         else:
-            tf32_peak = pk_peaks["bf16"] / 2.0
+            # the kernel is timed inside the step (events around every launch of a ~10 ms step), so the sustained
+            # cuBLAS figure is the denominator (B200_PROFILING.md); TF32 runs at half the bf16 rate
+            tf32_peak = pk_peaks["bf16_sustained"] / 2.0
             if prec == ops.PRECISION_AUTO:                     # what the library resolves AUTO to for this shape
                 prec = ops.PRECISION_TF32_BF16C if cout % 128 == 0 else ops.PRECISION_TF32X3
             passes = {ops.PRECISION_TF32: 1, ops.PRECISION_TF32_BF16C: 2, ops.PRECISION_TF32X3: 3}[prec]
@@ -300,7 +302,7 @@ def run_gpu(args):
                     "algorithmic_bytes": bytes_launch, "kernel": f"spconv_tc_kernel<{cin},{cout}> (K={K})",
                     "launches_per_step": dom_n / args.steps, "avg_launch_ms": avg_ms,
                     "share_of_step": dom_ms / dev_ms if world == 1 else None,
-                    "peak_source": pk_peaks["source"] + " bf16 burst / 2 (TF32 runs at half the bf16 rate)",
+                    "peak_source": pk_peaks["source"] + " bf16 sustained / 2 (TF32 runs at half the bf16 rate; burst / 2 = %.1f)" % (pk_peaks["bf16"] / 2.0),
                     "note": "achieved = algorithmic flops 2*P*Cin*Cout (real neighbour pairs only); the kernel "
                             "executes dense 128-row tiles (zero rows for missing neighbours)"
                             + mode_note,

@@ -513,7 +513,8 @@ __global__ void __launch_bounds__(kTcThreads, 1) spconv_tc_kernel(const __grid_c
         float la[8], lb[8];
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
-          const float ah = tf32_round(xa[i]), bh = tf32_round(xb[i]);   // x = hi + lo exactly (integer-pipe rounding)
+          const float ah = tf32_trunc(xa[i]), bh = tf32_trunc(xb[i]);   // x = hi + lo exactly; one LOP each (lo < 2^-10 |x|,
+                                                                          // its BF16 truncation then costs ~2^-18 |x|)
           hi[4 * (i >> 1) + (i & 1)] = __float_as_uint(ah);
           hi[4 * (i >> 1) + 2 + (i & 1)] = __float_as_uint(bh);
           la[i] = xa[i] - ah;
