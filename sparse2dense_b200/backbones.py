@@ -241,3 +241,24 @@ class PointPillarsScatter_S2D(nn.Module):
         from .dense import to_nchw
         a, b, (H, W) = self.forward_rows(voxel_features, coords, batch_size, input_shape)
         return to_nchw(a, batch_size, H, W), to_nchw(b, batch_size, H, W), None, None
+
+
+@BACKBONES.register_module
+class PointPillarsScatter(nn.Module):
+    """Plain pillar scatter of the teacher / baseline pillar models (pillar_encoder.py:157-217): the canvas
+    ``[B, 64, ny, nx]`` with each pillar's feature at ``(y, x)``; one launch (``s2d_dense_bev_nhwc`` with D = 1)."""
+
+    def __init__(self, num_input_features=64, norm_cfg=None, name="PointPillarsScatter", **kwargs):
+        super().__init__()
+        self.name = "PointPillarsScatter"
+        self.nchannels = num_input_features
+
+    def forward_rows(self, voxel_features, coords, batch_size, input_shape):
+        nx, ny = int(input_shape[0]), int(input_shape[1])
+        rows = ops.dense_bev_rows(voxel_features.contiguous(), coords.int().contiguous(), batch_size, (1, ny, nx))
+        return rows, (ny, nx)
+
+    def forward(self, voxel_features, coords, batch_size, input_shape):
+        from .dense import to_nchw
+        rows, (ny, nx) = self.forward_rows(voxel_features, coords, batch_size, input_shape)
+        return to_nchw(rows, batch_size, ny, nx)

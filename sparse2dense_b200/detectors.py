@@ -164,10 +164,30 @@ class PointPillars(SingleStageDetector):
 
     def extract_feat(self, data):
         input_features = self.reader(data["features"], data["num_voxels"], data["coors"])
-        x = self.backbone(input_features, data["coors"], data["batch_size"], data["input_shape"])
-        if self.with_neck:
-            x = self.neck(x)
-        return x
+        x_fea = self.backbone(input_features, data["coors"], data["batch_size"], data["input_shape"])
+        x = self.neck(x_fea) if self.with_neck else x_fea
+        return x, x_fea
+
+    def forward(self, example, return_loss=True, **kwargs):
+        """point_pillars.py:37-89, ``return_loss=False``: the teacher's role in distillation ->
+        (preds, F_D_a, F_D_b): head maps on the dense pillars, the dense canvas and the reconstruction canvas."""
+        if return_loss or self.training:
+            raise NotImplementedError("the training branch (losses) is not built; call .eval() and return_loss=False")
+        pre = "dense_" if "dense_voxels" in example else ""
+        B = len(example[pre + "num_voxels"])
+        shape = example["shape"][0]
+        feats = self.reader(example[pre + "voxels"], example[pre + "num_points"], example[pre + "coordinates"])
+        rows, (H, W) = self.backbone.forward_rows(feats, example[pre + "coordinates"], B, shape)
+        ups, (Hu, Wu) = self.neck.forward_rows(rows, B, H, W)
+        preds = self.bbox_head.forward_rows(ups, B, Hu, Wu)
+        preds = [{h: to_nchw(v, B, Hu, Wu) for h, v in d.items()} for d in preds]
+        F_D_a = to_nchw(rows, B, H, W)
+        F_D_b = None
+        if "reconstruction_voxels" in example:
+            f2 = self.reader(example["reconstruction_voxels"], example["reconstruction_num_points"],
+                             example["reconstruction_coordinates"])
+            F_D_b = self.backbone(f2, example["reconstruction_coordinates"], B, shape)
+        return preds, F_D_a, F_D_b
 
 
 @DETECTORS.register_module

@@ -110,3 +110,33 @@ def test_pp_two_stage_detector_runs_from_reference_style_config():
         k = len(d["scores"])
         assert d["box3d_lidar"].shape == (k, 7) and d["label_preds"].shape == (k,) and k <= 500
         assert torch.isfinite(d["scores"]).all()
+
+
+def test_pillar_teacher_forward_shapes_and_exact_scatter():
+    import logging
+    from sparse2dense_b200 import registry, synth
+    tasks = [dict(num_class=3, class_names=["VEHICLE", "PEDESTRIAN", "CYCLIST"])]
+    cfg = dict(type="PointPillars", pretrained=None,
+               reader=dict(type="PillarFeatureNet", num_filters=[64, 64], num_input_features=5, with_distance=False,
+                           voxel_size=PP_VOXEL, pc_range=PP_RANGE),
+               backbone=dict(type="PointPillarsScatter", ds_factor=1),
+               neck=dict(type="RPN", logger=logging.getLogger("RPN"), **PP_RPN),
+               bbox_head=dict(type="CenterHead", in_channels=128 * 3, tasks=tasks, dataset="waymo", weight=2, code_weights=[1.0] * 8,
+                              common_heads={"reg": (2, 2), "height": (1, 2), "dim": (3, 2), "rot": (2, 2)}))
+    torch.manual_seed(0)
+    model = registry.build_detector(cfg, train_cfg=None, test_cfg=None)
+    for m, seed in ((model.reader, 31), (model.neck, 33), (model.bbox_head, 34)):
+        m.load_state_dict({k: torch.as_tensor(v) for k, v in synth.random_module_state(m, seed).items()}, strict=False)
+    model = model.cuda().eval()
+    v, c, n = pillar_inputs(2000)
+    vc, cc, nc = torch.from_numpy(v).cuda(), torch.from_numpy(c).cuda(), torch.from_numpy(n).cuda()
+    example = dict(voxels=vc, coordinates=cc, num_points=nc, num_voxels=torch.tensor([len(v)]), shape=[np.array([468, 468, 1])],
+                   reconstruction_voxels=vc, reconstruction_coordinates=cc, reconstruction_num_points=nc,
+                   reconstruction_num_voxels=torch.tensor([len(v)]))
+    preds, F_D_a, F_D_b = model(example, return_loss=False)
+    assert preds[0]["hm"].shape == (1, 3, 468, 468) and preds[0]["dim"].shape == (1, 3, 468, 468)
+    assert F_D_a.shape == (1, 64, 468, 468) and torch.equal(F_D_a, F_D_b)
+    f = model.reader(vc, nc, cc).cpu().numpy()
+    canvas = np.zeros((64, 468 * 468), np.float32)
+    canvas[:, c[:, 2] * 468 + c[:, 3]] = f.T                                  # pillar_encoder.py:357-363
+    assert np.array_equal(F_D_a.cpu().numpy().reshape(64, -1), canvas)

@@ -73,3 +73,52 @@ def test_out_capacity_bound_is_an_upper_bound():
     for ks, st, pd in ((3, 2, 1), (3, 2, (0, 1, 1)), ((3, 1, 1), (2, 1, 1), 0)):
         oc, _, oshape, _ = R.rulebook_sparse(coors, (9, 20, 20), ks, st, pd)
         assert len(oc) <= ops.out_capacity_bound(len(coors), 2, tuple(oshape), ks, st)
+
+
+def test_every_loadable_waymo_style_config_builds_its_detectors(tmp_path):
+    """Reference-style configs (the Waymo VoxelNet / pillar, one- and two-stage, teacher and student dicts) build through
+    the det3d-compatible entry points on the CPU; module trees carry the reference's state-dict key names."""
+    import logging
+    from det3d.models import build_detector
+    from det3d.torchie import Config
+    src = '''
+import itertools, logging
+from det3d.utils.config_tool import get_downsample_factor
+tasks = [dict(num_class=3, class_names=['VEHICLE', 'PEDESTRIAN', 'CYCLIST'])]
+class_names = list(itertools.chain(*[t["class_names"] for t in tasks]))
+head = dict(type="CenterHead", in_channels=sum([256, 256]), tasks=tasks, dataset='waymo', weight=2, code_weights=[1.0] * 8,
+            common_heads={'reg': (2, 2), 'height': (1, 2), 'dim': (3, 2), 'rot': (2, 2)})
+model = dict(type="VoxelNet", pretrained=None, reader=dict(type="VoxelFeatureExtractorV3", num_input_features=5),
+             backbone=dict(type="SpMiddleResNetFHD", num_input_features=5, ds_factor=8),
+             neck=dict(type="RPN", layer_nums=[5, 5], ds_layer_strides=[1, 2], ds_num_filters=[128, 256], us_layer_strides=[1, 2],
+                       us_num_filters=[256, 256], num_input_features=256, logger=logging.getLogger("RPN")), bbox_head=head)
+S_model = dict(type="KD_VoxelNet", pretrained=None, reader=dict(type="VoxelFeatureExtractorV3", num_input_features=5),
+               backbone=dict(type="SpMiddleResNetFHD", num_input_features=5, ds_factor=8),
+               neck=dict(type="S2D_RPN", layer_nums=[5, 5], ds_layer_strides=[1, 2], ds_num_filters=[128, 256],
+                         us_layer_strides=[1, 2], us_num_filters=[256, 256], num_input_features=256, logger=logging.getLogger("RPN")),
+               bbox_head=head)
+pp_reader = dict(type="PillarFeatureNet", num_filters=[64, 64], num_input_features=5, with_distance=False,
+                 voxel_size=(0.32, 0.32, 6.0), pc_range=(-74.88, -74.88, -2, 74.88, 74.88, 4.0))
+pp_neck = dict(type="RPN", layer_nums=[3, 5, 5], ds_layer_strides=[1, 2, 2], ds_num_filters=[64, 128, 256], us_layer_strides=[1, 2, 4],
+               us_num_filters=[128, 128, 128], num_input_features=64, logger=logging.getLogger("RPN"))
+pp_head = dict(head, in_channels=128 * 3)
+pp_teacher = dict(type="PointPillars", pretrained=None, reader=pp_reader, backbone=dict(type="PointPillarsScatter", ds_factor=1),
+                  neck=pp_neck, bbox_head=pp_head)
+pp_student = dict(type="KD_PointPillars", pretrained=None, reader=pp_reader, backbone=dict(type="PointPillarsScatter_S2D", ds_factor=1),
+                  neck=pp_neck, bbox_head=pp_head)
+test_cfg = dict(out_size_factor=get_downsample_factor(S_model), pp_factor=get_downsample_factor(pp_student))
+'''
+    p = tmp_path / "cfg_all.py"
+    p.write_text(src)
+    cfg = Config.fromfile(str(p))
+    assert cfg.test_cfg.out_size_factor == 8 and cfg.test_cfg.pp_factor == 1 and cfg.class_names[1] == "PEDESTRIAN"
+    names = {}
+    for key in ("model", "S_model", "pp_teacher", "pp_student"):
+        m = build_detector(cfg[key], train_cfg=None, test_cfg=cfg.test_cfg)
+        names[key] = set(m.state_dict().keys())
+    assert "backbone.conv_input.0.weight" in names["S_model"] and "neck.encoder_1.0.weight" in names["S_model"]
+    assert "bbox_head.tasks.0.hm.3.bias" in names["model"] and "neck.blocks.0.1.weight" in names["model"]
+    assert "reader.pfn_layers.1.linear.weight" in names["pp_student"] and "backbone.decoder_2.3.weight" in names["pp_student"]
+    assert not any(k.startswith("backbone.") for k in names["pp_teacher"])          # the plain scatter has no parameters
+    with __import__("pytest").raises(KeyError):
+        build_detector(dict(type="NoSuchDetector"), train_cfg=None, test_cfg=None)
