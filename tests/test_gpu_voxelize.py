@@ -87,3 +87,33 @@ def test_voxelize_rejects_bad_arguments():
     pts = torch.zeros((10, 5), device="cuda")
     with pytest.raises(RuntimeError):
         ops.voxelize(pts, [0, 5], synth.WAYMO_VOXEL, synth.WAYMO_RANGE, 5, 100)      # offsets do not end at N
+
+
+def test_device_side_voxelization_step_all_five_variants_bit_exact():
+    """pipeline.Voxelization (the distillation pipeline's five voxelizations, batched on the device) vs the oracle."""
+    from sparse2dense_b200.pipeline import Voxelization
+    cfg = dict(range=list(synth.WAYMO_RANGE), voxel_size=list(synth.WAYMO_VOXEL), max_points_in_voxel=5,
+               max_voxel_num=150000, distillation=True)
+    step = Voxelization(cfg=cfg)
+    rng = np.random.default_rng(0)
+    pts = [synth.small_scene(11), synth.small_scene(12)]
+    dense = [np.concatenate([p, p[rng.integers(0, len(p), 3000)] + rng.normal(0, 0.05, (3000, 5)).astype(np.float32)]) for p in pts]
+    recon = [d[rng.permutation(len(d))[: len(d) // 2]] for d in dense]
+    ex = step(pts, dense_points=dense, reconstruction_points=recon)
+    vs = np.asarray(synth.WAYMO_VOXEL, np.float32)
+    for prefix, suffix, clouds, scale in [("", "", pts, 1), ("dense_", "", dense, 1), ("reconstruction_", "", recon, 1),
+                                          ("reconstruction_", "_2", recon, 2), ("reconstruction_", "_4", recon, 4)]:
+        v = ex[f"{prefix}voxels{suffix}"].cpu().numpy()
+        c = ex[f"{prefix}coordinates{suffix}"].cpu().numpy()
+        n = ex[f"{prefix}num_points{suffix}"].cpu().numpy()
+        counts = ex[f"{prefix}num_voxels{suffix}"].numpy()
+        off = 0
+        for b, cloud in enumerate(clouds):
+            rv, rc, rn = R.points_to_voxel(cloud, [x * scale for x in vs], synth.WAYMO_RANGE, 5, True, 150000)
+            k = len(rv)
+            assert counts[b] == k
+            assert np.array_equal(v[off:off + k], rv) and np.array_equal(n[off:off + k], rn)
+            assert np.array_equal(c[off:off + k, 1:], rc) and (c[off:off + k, 0] == b).all()
+            off += k
+        assert off == len(v)
+    assert tuple(ex["shape"][0]) == (1504, 1504, 40)
