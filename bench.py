@@ -132,7 +132,12 @@ class ClockSampler:
          "clocks_event_reasons.sw_power_cap")
 
     def __init__(self, gpu_index):
-        self.rows, self.proc, self.gpu = [], None, gpu_index
+        self.rows, self.proc, self.gpu, self.mark_at = [], None, gpu_index, 0
+
+    def mark(self):
+        """Samples from here on belong to the timed regions (nvidia-smi needs a few hundred ms to start on an 8-GPU box,
+        so it is launched before the warm-up)."""
+        self.mark_at = len(self.rows)
 
     def start(self):
         try:
@@ -156,7 +161,8 @@ class ClockSampler:
                 self.proc.kill()
         sm, mx, reasons = [], [], set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for r in self.rows:
+        rows = self.rows[self.mark_at:] or self.rows          # fall back to the warm-up samples (same workload)
+        for r in rows:
             try:
                 sm.append(float(r[1])); mx.append(float(r[2]))
             except (ValueError, IndexError):
@@ -200,13 +206,14 @@ def run_gpu(args):
             dist.barrier()
         torch.cuda.synchronize()
 
+    sampler = ClockSampler(local)
+    sampler.start()
     for _ in range(max(args.warmup, 3)):
         path.forward_points(pts_dev, offs)
     barrier()
 
     # ---- device-resident timing: K steps, L2 flushed before each, CUDA events per step -------
-    sampler = ClockSampler(local)
-    sampler.start()
+    sampler.mark()
     ops.KERNEL_EVENTS = []
     launches0 = ops.kernel_launches()
     evs = []
@@ -223,7 +230,6 @@ def run_gpu(args):
     wall = time.perf_counter() - t_wall0
     launches = ops.kernel_launches() - launches0
     kernel_events, ops.KERNEL_EVENTS = ops.KERNEL_EVENTS, None
-    clocks = sampler.stop()
     dev_ms = sum(a.elapsed_time(b) for a, b in evs)
 
     # ---- end to end: pinned host points in, pinned host BEV out, every copy inside the timed region.  The public
@@ -248,6 +254,7 @@ def run_gpu(args):
     barrier()
     e2e_wall = time.perf_counter() - t0
     e2e_ms = e0.elapsed_time(e1) - sum(a.elapsed_time(b) for a, b in flush_ms_evs)
+    clocks = sampler.stop()                                   # samples cover the device-resident AND the end-to-end region
 
     print(f"[bench rank {rank}] device {dev_ms / args.steps:.3f} ms/step, e2e {e2e_ms / args.steps:.3f} ms/step "
           f"(wall {1e3 * e2e_wall / args.steps:.3f})", file=sys.stderr, flush=True)
