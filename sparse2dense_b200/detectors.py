@@ -62,10 +62,9 @@ class SingleStageDetector(BaseDetector):
         """single_stage.py:33-40: a missing checkpoint file is reported, not fatal."""
         if pretrained is None:
             return
+        from .checkpoint import load_checkpoint
         try:
-            state = torch.load(pretrained, map_location="cpu")
-            state = state.get("state_dict", state)
-            self.load_state_dict({k[7:] if k.startswith("module.") else k: v for k, v in state.items()}, strict=False)
+            load_checkpoint(self, pretrained, map_location="cpu", strict=False)
             print("init weight from {}".format(pretrained))
         except Exception:
             print("no pretrained model at {}".format(pretrained))

@@ -122,3 +122,37 @@ test_cfg = dict(out_size_factor=get_downsample_factor(S_model), pp_factor=get_do
     assert not any(k.startswith("backbone.") for k in names["pp_teacher"])          # the plain scatter has no parameters
     with __import__("pytest").raises(KeyError):
         build_detector(dict(type="NoSuchDetector"), train_cfg=None, test_cfg=None)
+
+
+def test_checkpoint_round_trip_reference_format(tmp_path):
+    """save_checkpoint / load_checkpoint keep the reference's file format and prefix handling (checkpoint.py:146-240)."""
+    import torch
+    from det3d.torchie.trainer import load_checkpoint, save_checkpoint
+    from sparse2dense_b200 import registry
+    cfg = dict(type="SpMiddleResNetFHD", num_input_features=5, ds_factor=8)
+    a, b = registry.build_backbone(cfg), registry.build_backbone(cfg)
+    path = str(tmp_path / "work" / "epoch_1.pth")
+    save_checkpoint(a, path, meta=dict(epoch=1, iter=10))
+    ck = torch.load(path)
+    assert set(ck) == {"meta", "state_dict"} and ck["meta"]["epoch"] == 1
+    assert tuple(ck["state_dict"]["conv_input.0.weight"].shape) == (3, 3, 3, 5, 16)       # spconv layout [kD,kH,kW,Cin,Cout]
+    load_checkpoint(b, path, map_location="cpu", strict=True)
+    assert all(torch.equal(v, b.state_dict()[k]) for k, v in a.state_dict().items())
+    # DistributedDataParallel prefix + a wrapper with .module + a foreign / missing key, non-strict
+    sd = {"module." + k: v for k, v in a.state_dict().items()}
+    sd["module.not_there"] = torch.zeros(1)
+    sd.pop("module.conv1.0.conv1.weight")
+    torch.save({"state_dict": sd, "meta": {}}, str(tmp_path / "ddp.pth"))
+
+    class Wrap(torch.nn.Module):
+        def __init__(self, m):
+            super().__init__()
+            self.module = m
+    c = registry.build_backbone(cfg)
+    load_checkpoint(Wrap(c), str(tmp_path / "ddp.pth"), map_location="cpu")
+    assert torch.equal(c.state_dict()["conv4.3.conv2.weight"], a.state_dict()["conv4.3.conv2.weight"])
+    import pytest
+    with pytest.raises(RuntimeError):
+        load_checkpoint(c, str(tmp_path / "ddp.pth"), map_location="cpu", strict=True)
+    with pytest.raises(IOError):
+        load_checkpoint(c, str(tmp_path / "nope.pth"))
