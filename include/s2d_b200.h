@@ -231,6 +231,11 @@ int s2d_dense_bev_nhwc(const float* feat, const int* coors, int n_rows, int C, i
  * bev[b, c*D + z, y, x] = feat[row, c].  The kernel zero-fills bev itself. */
 int s2d_dense_bev(const float* feat, const int* coors, int n_rows, int C, int batch, int D, int H, int W,
                   float* bev, void* stream);
+/* Same result, output-stationary: a cell -> row map in `workspace` (s2d_dense_bev_workspace_bytes), then every global
+ * access is a full 128 B line and empty cells are zero-filled in the same pass (no memset of the whole map). */
+size_t s2d_dense_bev_workspace_bytes(int batch, int D, int H, int W);
+int s2d_dense_bev_tiled(const float* feat, const int* coors, int n_rows, int C, int batch, int D, int H, int W,
+                        float* bev, void* workspace, size_t workspace_bytes, void* stream);
 
 /* ---------------------------------------------------------------------------------------
  * CenterHead.predict on the device (det3d/models/bbox_heads/center_head.py:293-495, one task, no

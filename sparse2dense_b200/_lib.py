@@ -48,6 +48,8 @@ SIGNATURES = {
     "s2d_layernorm_chw": (_i, [_vp, _vp, _vp, _i, _i, _i, ctypes.c_float, _vp, _vp, _sz, _vp]),
     "s2d_dense_bev_nhwc": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _i, _vp, _i, _vp]),
     "s2d_dense_bev": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _i, _vp, _vp]),
+    "s2d_dense_bev_workspace_bytes": (_sz, [_i, _i, _i, _i]),
+    "s2d_dense_bev_tiled": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _i, _vp, _vp, _sz, _vp]),
     "s2d_centerhead_decode": (_i, [_vp, _vp, _vp, _vp, _vp, _vp]),
     "s2d_centerhead_select_workspace_bytes": (_sz, [_i, _i, _i]),
     "s2d_centerhead_select": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, ctypes.c_float, _i, _vp, _vp, _vp, _vp, _vp, _vp,

@@ -239,6 +239,48 @@ __global__ void __launch_bounds__(256) dense_bev_kernel(const float* __restrict_
   for (int ch = lane; ch < C; ch += 32) dst[(size_t)ch * D * plane] = __ldg(feat + (size_t)row * C + ch);
 }
 
+// Output-stationary form of dense() + view: cell map (row index or -1 per (b,z,y,x)), then one warp per 32 consecutive
+// x cells moves 32-channel chunks through a padded shared-memory tile, so every global access is a full 128 B line
+// (the row-stationary kernel above writes 4-byte pieces into C*D different planes) and empty cells are written as
+// zeros in the same pass (no separate memset of the 36 MB / scene map).
+__global__ void __launch_bounds__(256) bev_cell_map_kernel(const int4* __restrict__ coors, int n, int D, int H, int W,
+                                                           int* __restrict__ cell_row) {
+  const int row = blockIdx.x * blockDim.x + threadIdx.x;
+  if (row >= n) return;
+  const int4 c = coors[row];
+  cell_row[(((size_t)c.x * D + c.y) * H + c.z) * W + c.w] = row;
+}
+
+__global__ void __launch_bounds__(256) dense_bev_tiled_kernel(const float* __restrict__ feat,
+                                                              const int* __restrict__ cell_row, int C, int batch, int D,
+                                                              int H, int W, float* __restrict__ bev) {
+  __shared__ float tile[8][32][33];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int xt = (W + 31) / 32;
+  const long long task = (long long)blockIdx.x * 8 + warp;              // (b, z, y, x tile)
+  if (task >= (long long)batch * D * H * xt) return;
+  const int x0 = (int)(task % xt) * 32;
+  const int y = (int)((task / xt) % H), z = (int)((task / ((long long)xt * H)) % D), b = (int)(task / ((long long)xt * H * D));
+  const int x = x0 + lane;
+  const int my_row = x < W ? __ldg(cell_row + (((size_t)b * D + z) * H + y) * W + x) : -1;
+  const size_t plane = (size_t)H * W;
+  float (*t)[33] = tile[warp];
+  for (int c0 = 0; c0 < C; c0 += 32) {
+#pragma unroll 4
+    for (int i = 0; i < 32; ++i) {                                       // cell i of the tile: 32 consecutive channels
+      const int r = __shfl_sync(0xffffffffu, my_row, i);
+      t[i][lane] = (r >= 0 && c0 + lane < C) ? __ldg(feat + (size_t)r * C + c0 + lane) : 0.f;
+    }
+    __syncwarp();
+    if (x < W) {
+#pragma unroll 4
+      for (int ch = 0; ch < 32; ++ch)
+        if (c0 + ch < C) bev[((size_t)b * C * D + (size_t)(c0 + ch) * D + z) * plane + (size_t)y * W + x] = t[lane][ch];
+    }
+    __syncwarp();
+  }
+}
+
 static int check_shape(int batch, const int* shape, const char* who) {
   S2D_REQUIRE(shape && batch >= 1 && shape[0] > 0 && shape[1] > 0 && shape[2] > 0, "%s: bad batch/shape", who);
   S2D_REQUIRE((long long)batch * shape[0] * shape[1] * shape[2] < (1ll << 36), "%s: grid too large", who);
@@ -382,6 +424,29 @@ extern "C" int s2d_rulebook_sparse(const int* out_coors, int n_out, int batch, c
       reinterpret_cast<const int4*>(out_coors), n_out, Si, C, I.view(), tbl, tbl_stride, n_pairs);
   S2D_LAUNCH_CHECK();
   count_launches(1);
+  return S2D_OK;
+}
+
+extern "C" size_t s2d_dense_bev_workspace_bytes(int batch, int D, int H, int W) {
+  if (batch < 1 || D < 1 || H < 1 || W < 1) return 0;
+  return (size_t)batch * D * H * W * sizeof(int);
+}
+
+extern "C" int s2d_dense_bev_tiled(const float* feat, const int* coors, int n_rows, int C, int batch, int D, int H, int W,
+                                   float* bev, void* workspace, size_t workspace_bytes, void* stream) {
+  S2D_REQUIRE(n_rows >= 0 && C >= 1 && batch >= 1 && D >= 1 && H >= 1 && W >= 1 && bev && workspace,
+              "s2d_dense_bev_tiled: bad argument");
+  S2D_REQUIRE(workspace_bytes >= s2d_dense_bev_workspace_bytes(batch, D, H, W), "s2d_dense_bev_tiled: workspace too small");
+  S2D_REQUIRE(n_rows == 0 || (feat && coors), "s2d_dense_bev_tiled: null argument");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  int* cell_row = static_cast<int*>(workspace);
+  S2D_CUDA(cudaMemsetAsync(cell_row, 0xff, s2d_dense_bev_workspace_bytes(batch, D, H, W), st));
+  if (n_rows > 0)
+    bev_cell_map_kernel<<<div_up(n_rows, 256), 256, 0, st>>>(reinterpret_cast<const int4*>(coors), n_rows, D, H, W, cell_row);
+  const long long tasks = (long long)batch * D * H * ((W + 31) / 32);
+  dense_bev_tiled_kernel<<<div_up(tasks, 8), 256, 0, st>>>(feat, cell_row, C, batch, D, H, W, bev);
+  S2D_LAUNCH_CHECK();
+  count_launches(n_rows > 0 ? 2 : 1);
   return S2D_OK;
 }
 

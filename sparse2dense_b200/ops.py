@@ -337,6 +337,20 @@ def dense_bev(feats, coors, batch, spatial_shape):
     d, h, w = _triple(spatial_shape)
     n, c = feats.shape
     bev = torch.empty((batch, c * d, h, w), dtype=torch.float32, device=feats.device)
+    lib = _lib.load()
+    nbytes = lib.s2d_dense_bev_workspace_bytes(batch, d, h, w)
+    ws = torch.empty((nbytes,), dtype=torch.uint8, device=feats.device)
+    _lib.check(lib.s2d_dense_bev_tiled(_ptr(feats.contiguous()), _ptr(coors.contiguous()), n, c, batch, d, h, w,
+                                       _ptr(bev), _ptr(ws), nbytes, _stream()), "s2d_dense_bev_tiled")
+    return bev
+
+
+def dense_bev_rowwise(feats, coors, batch, spatial_shape):
+    """The row-stationary kernel (memset + scatter); kept for comparison / as the simple reference implementation."""
+    _need_cuda(feats, coors)
+    d, h, w = _triple(spatial_shape)
+    n, c = feats.shape
+    bev = torch.empty((batch, c * d, h, w), dtype=torch.float32, device=feats.device)
     _lib.check(_lib.load().s2d_dense_bev(_ptr(feats.contiguous()), _ptr(coors.contiguous()), n, c, batch, d, h, w,
                                          _ptr(bev), _stream()), "s2d_dense_bev")
     return bev

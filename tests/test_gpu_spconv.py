@@ -128,3 +128,5 @@ def test_dense_bev_matches_oracle():
     feats = rng.normal(size=(n, C)).astype(np.float32)
     bev = ops.dense_bev(torch.from_numpy(feats).cuda(), torch.from_numpy(coors).cuda(), B, (D, H, W))
     np.testing.assert_array_equal(bev.cpu().numpy(), R.dense_bev(feats, coors, B, (D, H, W)))
+    bev2 = ops.dense_bev_rowwise(torch.from_numpy(feats).cuda(), torch.from_numpy(coors).cuda(), B, (D, H, W))
+    assert torch.equal(bev, bev2)                                # tiled (output-stationary) == row-stationary kernel
