@@ -364,6 +364,61 @@ int s2d_gather_reg_loss(const float* pred, long long pred_sb, long long pred_sc,
                         long long tgt_scell, int B, int M, int D, int squared, const long long* ind,
                         const unsigned char* mask, double* out, void* workspace, size_t workspace_bytes, void* stream);
 
+/* ---------------------------------------------------------------------------------------
+ * Training step (SURVEY.md section 8 rows a7 train-mode, a16 backward, a17): csrc/train.cu.
+ *
+ * Every convolution of this library is out[i] = sum_k in[tbl[k][i]] . W[k]; its backward is
+ *   dIn  = s2d_conv_fwd over the TRANSPOSED table (s2d_table_transpose) with W[k]^T            (data gradient)
+ *   dW[k][a][b] = sum_i G[tbl[k][i]][a] * D[d_rows ? d_rows[i] : i][b]    (s2d_conv_wgrad; G = layer input, D = dOut)
+ * which replaces spconv's indice_conv_backward (per-offset gather -> mm -> scatter) and cuDNN's dgrad / wgrad.
+ * s2d_table_transpose: inv[k][j] = (out_rows ? out_rows[i] : i) for every tbl[k][i] = j >= 0, -1 elsewhere.
+ * s2d_conv_wgrad: deterministic (per-chunk partial sums, fixed-order reduction); accumulate != 0 adds to out.
+ *
+ * Rows normalisation [n, C] (BatchNorm1d over active voxels scn.py:100-107, BatchNorm2d over BEV pixels rpn.py:126-145,
+ * det3d/models/utils/norm.py:59-108), training mode:
+ *   s2d_bn_train_stats  -> mean, invstd (biased variance), folded scale = gamma*invstd, shift = beta - mean*scale, and the
+ *                          running statistics update (momentum, unbiased variance) in place;
+ *   s2d_rows_affine_act -> out = act(x*scale + shift (+ residual))  or  act(x*scale + shift) + residual;
+ *   s2d_rows_affine_act_bwd -> dz = dy * act'(.) (also the residual gradient when the residual is added before the
+ *                          activation), column sums {sum dz, sum dz*x} into the workspace, optional dshift = sum dz;
+ *   s2d_bn_train_bwd    -> dx, dgamma, dbeta from the workspace the previous call filled.
+ * s2d_layernorm_chw_bwd / s2d_dwconv2d_wgrad: backward of the ConvNeXt pieces (rpn.py:204-222); the depthwise data
+ *   gradient is s2d_dwconv2d with the flipped kernel.  dweight of the depthwise conv is [C][k*k].
+ * s2d_grad_norm_clip: out2 = { ||g||_2, min(1, max_norm / (norm + 1e-6)) } (clip_grad_norm_, hooks/optimizer.py:15-21).
+ * s2d_adam_step: p *= 1 - weight_decay*lr, then Adam with bias correction (det3d/solver/fastai_optim.py:158-174 with
+ *   true_wd, torch.optim.Adam arithmetic); grad_scale: optional device float multiplied into g (the clip coefficient).
+ * ------------------------------------------------------------------------------------- */
+int s2d_table_transpose(const int* tbl, int tbl_stride, int K, int n_out, const int* out_rows, int* inv, int inv_stride,
+                        int n_in, void* stream);
+size_t s2d_conv_wgrad_workspace_bytes(int n_rows, int K, int Cg, int Cd);
+int s2d_conv_wgrad(const float* g, int g_ld, int n_g, int Cg, const float* d, int d_ld, const int* d_rows, int Cd,
+                   const int* tbl, int tbl_stride, int n_rows, int K, float* out, int accumulate, void* workspace,
+                   size_t workspace_bytes, void* stream);
+size_t s2d_rows_workspace_bytes(int C);
+int s2d_bn_train_stats(const float* x, int ld, int n, int C, float eps, float momentum, const float* gamma,
+                       const float* beta, float* running_mean, float* running_var, float* mean, float* invstd,
+                       float* scale, float* shift, void* workspace, size_t workspace_bytes, void* stream);
+int s2d_rows_affine_act(const float* x, int ld, int n, int C, const float* scale, const float* shift,
+                        const float* residual, int res_ld, int act, int res_after_act, float* out, int out_ld,
+                        void* stream);
+int s2d_rows_affine_act_bwd(const float* x, int ld, int n, int C, const float* scale, const float* shift,
+                            const float* residual, int res_ld, int act, int res_after_act, const float* dy, int dy_ld,
+                            float* dz, int dz_ld, float* dshift, void* workspace, size_t workspace_bytes, void* stream);
+int s2d_bn_train_bwd(const float* x, int ld, int n, int C, const float* dz, int dz_ld, const float* mean,
+                     const float* invstd, const float* gamma, float* dx, int dx_ld, float* dgamma, float* dbeta,
+                     void* workspace, size_t workspace_bytes, void* stream);
+size_t s2d_layernorm_bwd_workspace_bytes(int B);
+int s2d_layernorm_chw_bwd(const float* x, const float* weight, int B, int C, int HW, float eps, const float* dy, float* dx,
+                          float* dweight, float* dbias, void* workspace, size_t workspace_bytes, void* stream);
+size_t s2d_dwconv2d_wgrad_workspace_bytes(int B, int H, int W, int C, int k);
+int s2d_dwconv2d_wgrad(const float* x, const float* dy, int B, int H, int W, int C, int k, int pad, float* dweight,
+                       void* workspace, size_t workspace_bytes, void* stream);
+size_t s2d_grad_norm_workspace_bytes(void);
+int s2d_grad_norm_clip(const float* g, long long n, float max_norm, float* out2, void* workspace, size_t workspace_bytes,
+                       void* stream);
+int s2d_adam_step(float* p, const float* g, float* exp_avg, float* exp_avg_sq, long long n, float lr, float beta1,
+                  float beta2, float eps, float weight_decay, int step, const float* grad_scale, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -73,6 +73,23 @@ SIGNATURES = {
     "s2d_gather_reg_loss": (_i, [_vp, ctypes.c_longlong, ctypes.c_longlong, ctypes.c_longlong, _vp, _vp,
                                  ctypes.c_longlong, ctypes.c_longlong, ctypes.c_longlong, _i, _i, _i, _i, _vp, _vp, _vp,
                                  _vp, _sz, _vp]),
+    "s2d_table_transpose": (_i, [_vp, _i, _i, _i, _vp, _vp, _i, _i, _vp]),
+    "s2d_conv_wgrad_workspace_bytes": (_sz, [_i, _i, _i, _i]),
+    "s2d_conv_wgrad": (_i, [_vp, _i, _i, _i, _vp, _i, _vp, _i, _vp, _i, _i, _i, _vp, _i, _vp, _sz, _vp]),
+    "s2d_rows_workspace_bytes": (_sz, [_i]),
+    "s2d_bn_train_stats": (_i, [_vp, _i, _i, _i, ctypes.c_float, ctypes.c_float, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp,
+                                _vp, _sz, _vp]),
+    "s2d_rows_affine_act": (_i, [_vp, _i, _i, _i, _vp, _vp, _vp, _i, _i, _i, _vp, _i, _vp]),
+    "s2d_rows_affine_act_bwd": (_i, [_vp, _i, _i, _i, _vp, _vp, _vp, _i, _i, _i, _vp, _i, _vp, _i, _vp, _vp, _sz, _vp]),
+    "s2d_bn_train_bwd": (_i, [_vp, _i, _i, _i, _vp, _i, _vp, _vp, _vp, _vp, _i, _vp, _vp, _vp, _sz, _vp]),
+    "s2d_layernorm_bwd_workspace_bytes": (_sz, [_i]),
+    "s2d_layernorm_chw_bwd": (_i, [_vp, _vp, _i, _i, _i, ctypes.c_float, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
+    "s2d_dwconv2d_wgrad_workspace_bytes": (_sz, [_i, _i, _i, _i, _i]),
+    "s2d_dwconv2d_wgrad": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _i, _vp, _vp, _sz, _vp]),
+    "s2d_grad_norm_workspace_bytes": (_sz, []),
+    "s2d_grad_norm_clip": (_i, [_vp, ctypes.c_longlong, ctypes.c_float, _vp, _vp, _sz, _vp]),
+    "s2d_adam_step": (_i, [_vp, _vp, _vp, _vp, ctypes.c_longlong, ctypes.c_float, ctypes.c_float, ctypes.c_float,
+                           ctypes.c_float, ctypes.c_float, _i, _vp, _vp]),
 }
 
 

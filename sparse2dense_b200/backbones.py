@@ -46,7 +46,7 @@ class SparseBasicBlock(spconv.SparseModule):
 
     def forward(self, x):
         identity = x
-        if spconv._is_eval_bn(self.bn1) and spconv._is_eval_bn(self.bn2):
+        if spconv._is_fusable_bn(self.bn1) and spconv._is_fusable_bn(self.bn2):
             out = self.conv1.fused_forward(x, bn=self.bn1, relu=True)
             if self.downsample is not None:
                 identity = self.downsample(x)
@@ -143,7 +143,10 @@ class SpMiddleResNetFHD(nn.Module):
         x_conv4 = self.conv4(x_conv3)
         ret = self.extra_conv(x_conv4)
 
-        if as_rows:
+        if torch.is_grad_enabled() and ret.features.requires_grad:
+            from .autograd import DenseBEV
+            ret = DenseBEV.apply(ret.features, ret.indices, batch_size, ret.spatial_shape, bool(as_rows))
+        elif as_rows:
             ret = ops.dense_bev_rows(ret.features, ret.indices, batch_size, ret.spatial_shape)
         else:
             ret = ret.dense()

@@ -169,6 +169,54 @@ class DenseOps:
     def __init__(self, precision=ops.PRECISION_TF32X3):
         self.precision = precision
         self.cache = ParamCache()
+        self.training = False         # set by the owning module: batch-statistics BN + autograd (autograd.py)
+
+    # -- training mode ---------------------------------------------------------------------
+    @staticmethod
+    def _train_table(key, tbl, n_in, n_out):
+        from . import autograd as AG
+        hit = _TABLES.get(("train",) + key)
+        if hit is None:
+            hit = _TABLES[("train",) + key] = AG.Table(tbl, n_in, n_out)
+        return hit
+
+    @staticmethod
+    def _train_norm(y, bias, bn, act, residual, res_after_act):
+        from . import autograd as AG
+        if bn is None:
+            return AG.norm_act(y, None, bias, act, residual, res_after_act)
+        return AG.norm_act(y, bn, None, act, residual, res_after_act, pre_bias=bias)
+
+    def _conv_train(self, x, B, H, W, conv, bn, act, residual, res_after_act, out, pad):
+        from . import autograd as AG
+        k, s = conv.kernel_size[0], conv.stride[0]
+        tbl, Ho, Wo = conv_table(x.device, B, H, W, k, s, pad)
+        table = self._train_table((str(x.device), "conv", B, H, W, k, s, pad), tbl, B * H * W, B * Ho * Wo)
+        w = conv.weight
+        kio = w.permute(2, 3, 1, 0).reshape(k * k, w.shape[1], w.shape[0])
+        y = AG.GatherConv.apply(x, kio, table, self.precision)
+        y = self._train_norm(y, conv.bias, bn, act, residual, res_after_act)
+        if out is not None:
+            out.copy_(y)
+        return y, Ho, Wo
+
+    def _tconv_train(self, x, B, H, W, conv, bn, act, out):
+        from . import autograd as AG
+        k, pad, st = conv.kernel_size[0], conv.padding[0], conv.stride[0]
+        classes = []
+        for py, px, tbl, rows in tconv_tables(x.device, B, H, W, k, pad, st):
+            ky0, kx0 = (py + pad) % st, (px + pad) % st
+            taps = [(ky0 + st * a, kx0 + st * c) for a in range(k // st) for c in range(k // st)]
+            classes.append((taps, tbl, rows))
+        adj_tbl, Hc, Wc = conv_table(x.device, B, st * H, st * W, k, st, pad)
+        assert (Hc, Wc) == (H, W)
+        adj = self._train_table((str(x.device), "conv", B, st * H, st * W, k, st, pad), adj_tbl, B * st * H * st * W,
+                                B * H * W)
+        y = AG.TransposedConv.apply(x, conv.weight, classes, adj, self.precision)
+        y = self._train_norm(y, conv.bias, bn, act, None, False)
+        if out is not None:
+            out.copy_(y)
+        return y, st * H, st * W
 
     # -- parameter preparation -------------------------------------------------------------
     def _conv_weights(self, name, conv, transposed_class=None):
@@ -199,6 +247,8 @@ class DenseOps:
         """Conv2d on rows; returns (out_rows_tensor, Ho, Wo)."""
         k, s = conv.kernel_size[0], conv.stride[0]
         pad = conv.padding[0] if pad is None else pad
+        if self.training:
+            return self._conv_train(x, B, H, W, conv, bn, act, residual, res_after_act, out, pad)
         tbl, Ho, Wo = conv_table(x.device, B, H, W, k, s, pad)
         kio, packed = self._conv_weights(name, conv)
         scale, shift = self._affine(name, conv, bn)
@@ -211,6 +261,8 @@ class DenseOps:
         returns (out, s*H, s*W)."""
         k, pad, st = conv.kernel_size[0], conv.padding[0], conv.stride[0]
         assert k % st == 0 and k - st == 2 * pad, "ConvTranspose2d shape outside the sub-pixel scheme"
+        if self.training:
+            return self._tconv_train(x, B, H, W, conv, bn, act, out)
         cout = conv.weight.shape[1]
         if out is None:
             out = torch.empty((B * st * st * H * W, cout), dtype=torch.float32, device=x.device)
@@ -240,6 +292,10 @@ class DenseOps:
 
     def dwconv(self, x, B, H, W, conv):
         C, k = conv.weight.shape[0], conv.kernel_size[0]
+        if self.training:
+            from . import autograd as AG
+            assert conv.groups == C
+            return AG.DepthwiseConv.apply(x, conv.weight, conv.bias, B, H, W, conv.padding[0])
         assert conv.groups == C and x.is_contiguous()
         out = torch.empty_like(x)
         w = conv.weight.detach().float().contiguous()
@@ -250,6 +306,10 @@ class DenseOps:
 
     def layernorm(self, x, B, H, W, ln):
         C = x.shape[1]
+        if self.training:
+            from . import autograd as AG
+            assert tuple(ln.normalized_shape) == (C, H, W)
+            return AG.LayerNormCHW.apply(x, ln.weight, ln.bias, B, ln.eps)
         assert tuple(ln.normalized_shape) == (C, H, W) and x.is_contiguous()
         out = torch.empty_like(x)
         lib = _lib.load()

@@ -154,6 +154,8 @@ class SparseConvolution(SparseModule):
         """conv (+ eval BatchNorm1d) (+ residual) (+ ReLU) in one kernel launch."""
         assert isinstance(x, SparseConvTensor)
         ind = self._indice(x)
+        if (bn is not None and bn.training) or (bn is None and self.training and torch.is_grad_enabled()):
+            return self._train_forward(x, ind, bn, relu, residual)
         scale, shift = self._folded(bn, x.features.device)
         n_out = ind.out_indices.shape[0]
         packed = self._packed_weights() if self.precision != ops.PRECISION_FP32 else None
@@ -163,6 +165,26 @@ class SparseConvolution(SparseModule):
         if self.subm:
             return x._like(feats)
         return x._like(feats, ind.out_indices, ind.out_shape, ind.out_index)
+
+    def _train_forward(self, x, ind, bn, relu, residual):
+        """Training mode: conv -> BatchNorm1d with batch statistics over the active rows (scn.py:100-107) -> (+ residual)
+        -> ReLU, each with its backward in libs2d_b200.so (autograd.py)."""
+        from . import autograd as AG
+        table = ind.__dict__.get("table")
+        if table is None:
+            table = ind.table = AG.Table(ind.tbl, x.features.shape[0], ind.out_indices.shape[0], symmetric=self.subm)
+        K = self.kernel_size[0] * self.kernel_size[1] * self.kernel_size[2]
+        w = self.weight.view(K, self.in_channels, self.out_channels)
+        y = AG.GatherConv.apply(x.features, w, table, self.precision)
+        act = 1 if relu else 0
+        if bn is None:
+            if self.bias is not None or relu or residual is not None:
+                y = AG.norm_act(y, None, self.bias, act, residual)
+        else:
+            y = AG.norm_act(y, bn, None, act, residual, pre_bias=self.bias)
+        if self.subm:
+            return x._like(y)
+        return x._like(y, ind.out_indices, ind.out_shape, ind.out_index)
 
     def forward(self, x):
         return self.fused_forward(x)
@@ -204,6 +226,11 @@ class SparseConv3d(SparseConvolution):
 
 def _is_eval_bn(m):
     return isinstance(m, nn.BatchNorm1d) and not m.training and m.track_running_stats
+
+
+def _is_fusable_bn(m):
+    """eval-mode BN folds into the conv epilogue; training-mode BN runs the batch-statistics kernels of train.cu."""
+    return isinstance(m, nn.BatchNorm1d) and m.track_running_stats
 
 
 class SparseSequential(SparseModule):
@@ -249,7 +276,7 @@ class SparseSequential(SparseModule):
         while i < len(mods):
             m = mods[i]
             if isinstance(m, SparseConvolution) and isinstance(input, SparseConvTensor):
-                bn = mods[i + 1] if i + 1 < len(mods) and _is_eval_bn(mods[i + 1]) else None
+                bn = mods[i + 1] if i + 1 < len(mods) and _is_fusable_bn(mods[i + 1]) else None
                 relu = bn is not None and i + 2 < len(mods) and isinstance(mods[i + 2], nn.ReLU)
                 input = m.fused_forward(input, bn=bn, relu=relu)
                 i += 1 + (bn is not None) + int(relu)
