@@ -364,6 +364,23 @@ int s2d_gather_reg_loss(const float* pred, long long pred_sb, long long pred_sc,
                         long long tgt_scell, int B, int M, int D, int squared, const long long* ind,
                         const unsigned char* mask, double* out, void* workspace, size_t workspace_bytes, void* stream);
 
+/* Gradients of the three losses w.r.t. the student's map.  out4 / out3 / sums: the device result of the forward call;
+ * upstream: optional device float (per regression dimension: float[D]) multiplied in; d_*: gradient buffer addressed with
+ * its own (sb, sc, scell) strides.  s2d_gather_reg_loss_bwd zero-fills d_pred[0 .. d_numel) first and then adds the <= B*M
+ * peak contributions; s2d_focal_loss_bwd writes every element.  With squared = 0 the derivative of |e| at 0 is 0. */
+int s2d_masked_mse_bwd(const float* f_student, const float* f_teacher, long long n, const double* out4, float w_pos,
+                       float w_neg, const float* upstream, float* d_student, void* stream);
+int s2d_focal_loss_bwd(const float* out, long long out_sb, long long out_sc, long long out_scell, int out_is_logits,
+                       const float* target, long long tgt_sb, long long tgt_sc, long long tgt_scell, int target_is_logits,
+                       int B, int C, int HW, const long long* ind, const unsigned char* mask, const long long* cat, int M,
+                       const double* out3, const float* upstream, float* d_out, long long d_sb, long long d_sc,
+                       long long d_scell, void* stream);
+int s2d_gather_reg_loss_bwd(const float* pred, long long pred_sb, long long pred_sc, long long pred_scell,
+                            const float* target_rows, const float* target_map, long long tgt_sb, long long tgt_sc,
+                            long long tgt_scell, int B, int M, int D, int squared, const long long* ind,
+                            const unsigned char* mask, const double* sums, const float* upstream, float* d_pred,
+                            long long d_numel, long long d_sb, long long d_sc, long long d_scell, void* stream);
+
 /* ---------------------------------------------------------------------------------------
  * Training step (SURVEY.md section 8 rows a7 train-mode, a16 backward, a17): csrc/train.cu.
  *

@@ -75,16 +75,15 @@ class CenterHead(nn.Module):
 
     def forward_rows(self, x, B, H, W):
         """x rows [B*H*W, C] -> list (per task) of dict head -> rows [B*H*W, classes]."""
-        if self.training:
-            raise NotImplementedError("CenterHead is forward/eval only in this version (call .eval())")
         D = self._dense
+        D.training = self.training      # training: batch-statistics BN + autograd, one launch per conv (autograd.py)
         s, _, _ = D.conv("shared_conv.0", x, B, H, W, self.shared_conv[0], self.shared_conv[1], ACT_RELU)
         tbl, _, _ = conv_table(x.device, B, H, W, 3, 1, 1)
         n = B * H * W
         ret = []
         for ti, task in enumerate(self.tasks):
             names = list(task.heads)
-            two_conv = all(task.heads[h][1] == 2 for h in names)
+            two_conv = (not self.training) and all(task.heads[h][1] == 2 for h in names)
             out = {}
             if two_conv:
                 # the first conv of every branch reads the same 64-channel map: one 64 -> 64*len(heads) launch
@@ -200,11 +199,10 @@ class CenterHead(nn.Module):
         meta = example.get("metadata") if isinstance(example, dict) else None
         return self.predict_rows(rows, B, H, W, test_cfg, meta if meta else None)
 
-    # -- loss values (center_head.py:250-291), forward only -----------------------------------------
-    @torch.no_grad()
+    # -- losses (center_head.py:250-291) --------------------------------------------------------------
     def loss(self, example, preds_dicts, **kwargs):
         """Same return structure as the reference (dict of per-task lists).  ``preds_dicts``: list of dict head -> NCHW
-        logits map or ``losses.Rows`` view.  Values only: autograd / backward are not built."""
+        logits map or ``losses.Rows`` view.  Differentiable w.r.t. the prediction maps (losses.py)."""
         from collections import defaultdict
         from . import losses as L
         crit_reg = L.RegLoss()
@@ -224,8 +222,8 @@ class CenterHead(nn.Module):
                 off += c
             box_loss = torch.cat(parts)
             loc_loss = (box_loss * box_loss.new_tensor(self.code_weights)).sum()
-            ret = {"loss": hm_loss + self.weight * loc_loss, "hm_loss": hm_loss.detach().cpu(), "loc_loss": loc_loss,
-                   "loc_loss_elem": box_loss.detach().cpu(), "num_positive": mask.float().sum()}
+            ret = {"loss": hm_loss + self.weight * loc_loss, "hm_loss": hm_loss.detach(), "loc_loss": loc_loss,
+                   "loc_loss_elem": box_loss.detach(), "num_positive": mask.float().sum()}
             for k, v in ret.items():
                 merged[k].append(v)
         return merged

@@ -9,7 +9,7 @@
 //   * s2d_gather_reg_loss: RegLoss.forward (centernet_loss.py:6-25, L1) and distill_reg_loss (trainer.py:68-76, squared
 //                       error, target gathered from the teacher map) incl. _transpose_and_gather_feat
 //                       (det3d/core/utils/center_utils.py:66-80).
-// Gradients are not built (the backward of the training step is a later round).
+// The *_bwd entry points give the gradient w.r.t. the student's map (the teacher / targets are constants).
 #include "common.cuh"
 
 namespace s2d {
@@ -133,6 +133,86 @@ __global__ void __launch_bounds__(kRedThreads) gather_reg_loss_kernel(MapView pr
   block_reduce_store<kRegMaxD + 1>(acc, partial);
 }
 
+// ---- backward ------------------------------------------------------------------------------------------------------
+struct GradView { float* p; long long sb, sc, scell; };
+__device__ __forceinline__ float* grad_at(const GradView& m, int b, int c, int cell) {
+  return m.p + (long long)b * m.sb + (long long)c * m.sc + (long long)cell * m.scell;
+}
+
+// d/ds [ w_pos * sum_{t>0}(s-t)^2 / n_pos + w_neg * sum_{t<=0}(s-t)^2 / n_neg ] * upstream
+__global__ void masked_mse_bwd_kernel(const float* __restrict__ fs, const float* __restrict__ ft, long long n,
+                                      const double* __restrict__ out4, float w_pos, float w_neg,
+                                      const float* __restrict__ upstream, float* __restrict__ dfs) {
+  const float up = upstream ? *upstream : 1.f;
+  const float cp = out4[1] > 0.0 ? (float)(2.0 * w_pos / out4[1]) * up : 0.f;
+  const float cn = out4[3] > 0.0 ? (float)(2.0 * w_neg / out4[3]) * up : 0.f;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const float s = fs[i], t = __ldg(ft + i);
+    dfs[i] = (s - t) * (t > 0.f ? cp : cn);
+  }
+}
+
+// loss = -(pos + neg) / num (num > 0)  or  -neg;  gradient w.r.t. the student map (probabilities, or logits when fused)
+__global__ void focal_loss_bwd_map_kernel(MapView out, MapView tgt, int B, int C, int HW, int out_logits, int tgt_logits,
+                                          const double* __restrict__ out3, const float* __restrict__ upstream, GradView g) {
+  const float up = upstream ? *upstream : 1.f;
+  const float coef = -up / (out3[2] > 0.0 ? (float)out3[2] : 1.f);
+  const long long total = (long long)B * C * HW;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int cell = (int)(i % HW), c = (int)((i / HW) % C), b = (int)(i / ((long long)HW * C));
+    float o = map_at(out, b, c, cell), t = map_at(tgt, b, c, cell);
+    float chain = 1.f;
+    if (out_logits) {
+      const float sg = sigmoidf_rn(o);
+      o = fminf(fmaxf(sg, 1e-4f), 1.f - 1e-4f);
+      chain = (sg >= 1e-4f && sg <= 1.f - 1e-4f) ? sg * (1.f - sg) : 0.f;       // clamp passes the gradient inside only
+    }
+    if (tgt_logits) t = sigmoidf_rn(t);
+    const float g1 = 1.f - t, g4 = (g1 * g1) * (g1 * g1);
+    const float d = g4 * (2.f * o * logf(1.f - o) - o * o / (1.f - o));
+    *grad_at(g, b, c, cell) = coef * d * chain;
+  }
+}
+
+__global__ void focal_loss_bwd_peaks_kernel(MapView out, int B, int out_logits, const long long* __restrict__ ind,
+                                            const unsigned char* __restrict__ mask, const long long* __restrict__ cat, int M,
+                                            const double* __restrict__ out3, const float* __restrict__ upstream, GradView g) {
+  if (!(out3[2] > 0.0)) return;                       // num_pos == 0: the loss is -neg only
+  const float up = upstream ? *upstream : 1.f;
+  const float coef = -up / (float)out3[2];
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < (long long)B * M; i += (long long)gridDim.x * blockDim.x) {
+    if (!mask[i]) continue;
+    const int b = (int)(i / M), c = (int)cat[i], cell = (int)ind[i];
+    float p = map_at(out, b, c, cell), chain = 1.f;
+    if (out_logits) {
+      const float sg = sigmoidf_rn(p);
+      p = fminf(fmaxf(sg, 1e-4f), 1.f - 1e-4f);
+      chain = (sg >= 1e-4f && sg <= 1.f - 1e-4f) ? sg * (1.f - sg) : 0.f;
+    }
+    const float q = 1.f - p;
+    const float d = q * q / p - 2.f * q * logf(p);
+    atomicAdd(grad_at(g, b, c, cell), coef * d * chain);
+  }
+}
+
+__global__ void gather_reg_loss_bwd_kernel(MapView pred, const float* __restrict__ tgt_rows, MapView tgt_map, int B, int M,
+                                           int D, int squared, const long long* __restrict__ ind,
+                                           const unsigned char* __restrict__ mask, const double* __restrict__ sums,
+                                           const float* __restrict__ upstream, GradView g) {
+  const float inv = 1.f / ((float)sums[kRegMaxD] + 1e-4f);
+  for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < (long long)B * M * D; e += (long long)gridDim.x * blockDim.x) {
+    const long long i = e / D;
+    const int d = (int)(e - i * D);
+    if (!mask[i]) continue;
+    const int b = (int)(i / M), cell = (int)ind[i];
+    const float p = map_at(pred, b, d, cell);
+    const float t = tgt_map.p ? map_at(tgt_map, b, d, cell) : tgt_rows[i * D + d];
+    const float err = p - t;
+    const float dd = squared ? 2.f * err : (err > 0.f ? 1.f : (err < 0.f ? -1.f : 0.f));
+    atomicAdd(grad_at(g, b, d, cell), dd * inv * (upstream ? upstream[d] : 1.f));
+  }
+}
+
 }  // namespace s2d
 
 using namespace s2d;
@@ -192,5 +272,61 @@ extern "C" int s2d_gather_reg_loss(const float* pred, long long pred_sb, long lo
   final_reduce_kernel<kRegMaxD + 1><<<1, 32, 0, st>>>(partial, kRedBlocks, out);
   S2D_LAUNCH_CHECK();
   count_launches(2);
+  return S2D_OK;
+}
+
+extern "C" int s2d_masked_mse_bwd(const float* f_student, const float* f_teacher, long long n, const double* out4, float w_pos,
+                                  float w_neg, const float* upstream, float* d_student, void* stream) {
+  S2D_REQUIRE(f_student && f_teacher && out4 && d_student && n >= 0, "s2d_masked_mse_bwd: bad argument");
+  if (n == 0) return S2D_OK;
+  long long blocks = (n + 255) / 256;
+  if (blocks > 148 * 16) blocks = 148 * 16;
+  masked_mse_bwd_kernel<<<(int)blocks, 256, 0, static_cast<cudaStream_t>(stream)>>>(f_student, f_teacher, n, out4, w_pos, w_neg,
+                                                                                  upstream, d_student);
+  S2D_LAUNCH_CHECK();
+  count_launches(1);
+  return S2D_OK;
+}
+
+extern "C" int s2d_focal_loss_bwd(const float* out, long long out_sb, long long out_sc, long long out_scell, int out_is_logits,
+                                  const float* target, long long tgt_sb, long long tgt_sc, long long tgt_scell,
+                                  int target_is_logits, int B, int C, int HW, const long long* ind, const unsigned char* mask,
+                                  const long long* cat, int M, const double* out3, const float* upstream, float* d_out,
+                                  long long d_sb, long long d_sc, long long d_scell, void* stream) {
+  S2D_REQUIRE(out && target && ind && mask && cat && out3 && d_out, "s2d_focal_loss_bwd: null argument");
+  S2D_REQUIRE(B >= 1 && C >= 1 && HW >= 1 && M >= 0, "s2d_focal_loss_bwd: bad sizes");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const GradView g{d_out, d_sb, d_sc, d_scell};
+  focal_loss_bwd_map_kernel<<<kRedBlocks, kRedThreads, 0, st>>>(MapView{out, out_sb, out_sc, out_scell},
+                                                               MapView{target, tgt_sb, tgt_sc, tgt_scell}, B, C, HW,
+                                                               out_is_logits, target_is_logits, out3, upstream, g);
+  S2D_LAUNCH_CHECK();
+  count_launches(1);
+  if (M > 0) {
+    focal_loss_bwd_peaks_kernel<<<((long long)B * M + 255) / 256, 256, 0, st>>>(MapView{out, out_sb, out_sc, out_scell}, B,
+                                                                               out_is_logits, ind, mask, cat, M, out3,
+                                                                               upstream, g);
+    S2D_LAUNCH_CHECK();
+    count_launches(1);
+  }
+  return S2D_OK;
+}
+
+extern "C" int s2d_gather_reg_loss_bwd(const float* pred, long long pred_sb, long long pred_sc, long long pred_scell,
+                                       const float* target_rows, const float* target_map, long long tgt_sb, long long tgt_sc,
+                                       long long tgt_scell, int B, int M, int D, int squared, const long long* ind,
+                                       const unsigned char* mask, const double* sums, const float* upstream, float* d_pred,
+                                       long long d_numel, long long d_sb, long long d_sc, long long d_scell, void* stream) {
+  S2D_REQUIRE(pred && (target_rows || target_map) && ind && mask && sums && d_pred, "s2d_gather_reg_loss_bwd: null argument");
+  S2D_REQUIRE(B >= 1 && M >= 0 && D >= 1 && D <= kRegMaxD && d_numel >= 0, "s2d_gather_reg_loss_bwd: bad sizes");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  S2D_CUDA(cudaMemsetAsync(d_pred, 0, (size_t)d_numel * sizeof(float), st));
+  if (M > 0) {
+    gather_reg_loss_bwd_kernel<<<((long long)B * M * D + 255) / 256, 256, 0, st>>>(
+        MapView{pred, pred_sb, pred_sc, pred_scell}, target_rows, MapView{target_map, tgt_sb, tgt_sc, tgt_scell}, B, M, D, squared,
+        ind, mask, sums, upstream, GradView{d_pred, d_sb, d_sc, d_scell});
+    S2D_LAUNCH_CHECK();
+    count_launches(1);
+  }
   return S2D_OK;
 }

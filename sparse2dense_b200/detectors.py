@@ -1,7 +1,8 @@
 """Detectors (det3d/models/detectors/{base,single_stage,voxelnet}.py): the glue that picks the example-dict keys and
 calls reader -> backbone -> neck -> head -> predict.  Same registry names, constructor arguments, ``forward`` flags and
-return shapes as the reference for the inference path (``return_loss=False``); the training branches (losses, PCR
-targets) are not built and raise.
+return shapes as the reference.  ``VoxelNet`` / ``KD_VoxelNet`` also carry the training branches (``return_loss=True``:
+CenterHead losses, the student's feature maps and PCR losses) on the autograd operators of
+``autograd.py``; the pillar detectors are inference only.
 
 Inside, the dense stage runs on NHWC rows end to end (backbone densifies straight into rows, the head output buffer
 feeds the decode kernel), so no NCHW<->NHWC copy of a 512-channel map is made unless a caller asks for the feature maps.
@@ -76,9 +77,23 @@ class SingleStageDetector(BaseDetector):
         return self.eval()
 
 
-def _example_data(example):
-    return dict(features=example["voxels"], num_voxels=example["num_points"], coors=example["coordinates"],
-                batch_size=len(example["num_voxels"]), input_shape=example["shape"][0])
+def _example_data(example, prefix=""):
+    return dict(features=example[prefix + "voxels"], num_voxels=example[prefix + "num_points"],
+                coors=example[prefix + "coordinates"], batch_size=len(example[prefix + "num_voxels"]),
+                input_shape=example["shape"][0])
+
+
+def _as_loss_maps(preds_rows, B, H, W):
+    from .losses import Rows
+    return [{h: Rows(v, B, H * W) for h, v in d.items()} for d in preds_rows]
+
+
+def _nchw(rows, B, H, W, differentiable):
+    if rows is None:
+        return None
+    if differentiable:
+        return rows.reshape(B, H, W, rows.shape[1]).permute(0, 3, 1, 2)
+    return to_nchw(rows, B, H, W)
 
 
 @DETECTORS.register_module
@@ -92,24 +107,43 @@ class VoxelNet(SingleStageDetector):
             x = self.neck(x)
         return x, voxel_feature
 
-    def _rows_forward(self, example):
-        data = _example_data(example)
+    def _rows_forward(self, example, prefix=""):
+        data = _example_data(example, prefix)
         B = data["batch_size"]
         feats = self.reader(data["features"], data["num_voxels"])
         rows, voxel_feature = self.backbone(feats, data["coors"], B, data["input_shape"], as_rows=True)
         H, W = self.backbone.bev_hw(data["input_shape"])
         return rows, voxel_feature, B, H, W
 
-    def forward(self, example, return_loss=True, return_feature=False, **kwargs):
-        if return_loss or self.training:
-            raise NotImplementedError("the training branch (losses) is not built; call .eval() and return_loss=False")
-        rows, _, B, H, W = self._rows_forward(example)
-        backbone_rows = rows
+    def teacher_rows(self, example, recon=True):
+        """The teacher's part of a distillation step (voxelnet.py:47-92 with return_feature / return_recon_feature), all on
+        NHWC rows: head logits on the DENSE (multi-sweep) voxels, F_D_a = backbone BEV map of the dense voxels,
+        F_D_b = backbone BEV map of the reconstruction voxels."""
+        prefix = "dense_" if "dense_voxels" in example else ""
+        rows, _, B, H, W = self._rows_forward(example, prefix)
+        F_D_b = None
+        if recon and "reconstruction_voxels" in example:
+            F_D_b = self._rows_forward(example, "reconstruction_")[0]
         ups, (Hu, Wu) = self.neck.forward_rows(rows, B, H, W)
         preds = self.bbox_head.forward_rows(ups, B, Hu, Wu)
+        return preds, rows, F_D_b, (B, H, W, Hu, Wu)
+
+    def forward(self, example, return_loss=True, return_feature=False, return_recon_feature=False, **kwargs):
+        """voxelnet.py:47-104."""
+        grad = torch.is_grad_enabled() and self.training
+        preds, F_D_a, F_D_b, (B, H, W, Hu, Wu) = self.teacher_rows(example, recon=return_recon_feature)
+        if return_loss:
+            loss = self.bbox_head.loss(example, _as_loss_maps(preds, B, Hu, Wu))
+            if not return_feature:
+                return loss
+            return loss, _nchw(F_D_a, B, H, W, grad), _nchw(F_D_b, B, H, W, grad)
+        if return_feature and return_recon_feature:
+            preds_nchw = [{h: _nchw(v, B, Hu, Wu, grad) for h, v in d.items()} for d in preds]
+            return preds_nchw, _nchw(F_D_a, B, H, W, grad), _nchw(F_D_b, B, H, W, grad)
         dets = self.bbox_head.predict_rows(preds, B, Hu, Wu, self.test_cfg, example.get("metadata"))
         if return_feature:
-            return dets, to_nchw(backbone_rows, B, H, W)          # F_D_a: the backbone's dense BEV map (voxelnet.py:66-72)
+            # F_D_a: the backbone's dense BEV map (voxelnet.py:66-72); F_D_b only exists with return_recon_feature
+            return dets, _nchw(F_D_a, B, H, W, grad)
         return dets
 
 
@@ -131,9 +165,32 @@ class KD_VoxelNet(VoxelNet):
         dets = self.bbox_head.predict_rows(preds, B, Hu, Wu, self.test_cfg, example.get("metadata"))
         return dets, ups, voxel_feature, F_S_a, F_S_b, B, H, W, Hu, Wu
 
+    def student_rows(self, example, with_loss=True):
+        """The student's part of a distillation step (voxelnet.py:188-260) on NHWC rows ->
+        dict(loss, preds, F_S_a, F_S_b, mask_loss, comp_loss, dims).  The PCR losses (mask_offset_loss, :171-185) come from
+        ``pcr.pcr_losses`` over the neck's generator outputs when the neck ran its PCR branch."""
+        rows, voxel_feature, B, H, W = self._rows_forward(example)
+        ups, (Hu, Wu), F_S_a, F_S_b = self.neck.forward_rows(rows, B, H, W)
+        mask_loss = comp_loss = 0
+        if self.training and with_loss and getattr(self.neck, "pcr_rows", None) is not None:
+            from . import pcr
+            mask_loss, comp_loss = pcr.pcr_losses(self, example, self.neck.pcr_rows, B, H, W)
+        preds = self.bbox_head.forward_rows(ups, B, Hu, Wu)
+        loss = self.bbox_head.loss(example, _as_loss_maps(preds, B, Hu, Wu)) if with_loss else None
+        return dict(loss=loss, preds=preds, F_S_a=F_S_a, F_S_b=F_S_b, mask_loss=mask_loss, comp_loss=comp_loss,
+                    dims=(B, H, W, Hu, Wu), ups=ups, voxel_feature=voxel_feature)
+
     def forward(self, example, return_loss=True, return_feature=False, **kwargs):
-        if return_loss or self.training:
-            raise NotImplementedError("the distillation training branch is not built; call .eval() and return_loss=False")
+        """voxelnet.py:188-265."""
+        if return_loss:
+            r = self.student_rows(example)
+            B, H, W, Hu, Wu = r["dims"]
+            grad = torch.is_grad_enabled()
+            preds = [{h: _nchw(v, B, Hu, Wu, grad) for h, v in d.items()} for d in r["preds"]]
+            if not return_feature:
+                return r["loss"], preds
+            return (r["loss"], _nchw(r["F_S_a"], B, H, W, grad), _nchw(r["F_S_b"], B, H, W, grad), preds, r["mask_loss"],
+                    r["comp_loss"])
         dets, _, _, F_S_a, F_S_b, B, H, W, _, _ = self._first_stage_rows(example)
         if return_feature:
             return dets, to_nchw(F_S_a, B, H, W), to_nchw(F_S_b, B, H, W)

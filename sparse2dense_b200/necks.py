@@ -3,8 +3,9 @@
 ``RPN`` (:24-162) and ``S2D_RPN`` (:164-337) keep the reference's constructor arguments, module tree and
 state-dict keys (``encoder_1.0.weight``, ``blocks.0.1.weight``, ``deblocks.1.0.weight`` …) so that reference
 checkpoints load; the eval-mode forward runs on NHWC rows through the tcgen05 gather-GEMM kernel with
-BatchNorm / bias / GELU / ReLU / residual / concat fused (``sparse2dense_b200/dense.py``).  Forward only:
-training mode (batch-statistics BN, the PCR branch rpn.py:314-323) raises.
+BatchNorm / bias / GELU / ReLU / residual / concat fused (``sparse2dense_b200/dense.py``).  In training mode the same
+layer sequence runs through the autograd operators of ``autograd.py`` (batch-statistics BatchNorm, backward kernels of
+csrc/train.cu) and ``S2D_RPN`` adds the PCR branch (rpn.py:314-323).
 """
 import logging
 
@@ -87,9 +88,23 @@ class RPN(nn.Module):
 
     # ---------------------------------------------------------------------------------------
     def _check_eval(self):
-        if self.training:
-            raise NotImplementedError("sparse2dense_b200 necks are forward/eval only in this version "
-                                      "(call .eval(); training-mode BatchNorm and the PCR branch are not built)")
+        """Select the execution mode of the dense operators: eval = fused inference kernels, train = autograd.py."""
+        self._dense.training = self.training
+
+    @staticmethod
+    def _rows_in(x, training):
+        B, C, H, W = x.shape
+        if training:                              # differentiable layout change (torch permute: plumbing)
+            return x.permute(0, 2, 3, 1).reshape(B * H * W, C)
+        return to_rows(x)
+
+    @staticmethod
+    def _nchw_out(rows, B, H, W, training):
+        if rows is None:
+            return None
+        if training:
+            return rows.reshape(B, H, W, rows.shape[1]).permute(0, 3, 1, 2)
+        return to_nchw(rows, B, H, W)
 
     def _run_block(self, i, x, B, H, W, outer_relu):
         """blocks[i] on rows: ZeroPad2d(1)+Conv3x3(stride) + BN + ReLU, then conv3x3 + BN (+ReLU) ... (rpn.py:126-145)."""
@@ -145,8 +160,8 @@ class RPN(nn.Module):
         """rpn.py:153-162 (note the outer F.relu after every block, which S2D_RPN.forward omits)."""
         self._check_eval()
         B, _, H, W = x.shape
-        rows, H, W = self._rpn_rows(to_rows(x), B, H, W, outer_relu=True)
-        return to_nchw(rows, B, H, W)
+        rows, H, W = self._rpn_rows(self._rows_in(x, self.training), B, H, W, outer_relu=True)
+        return self._nchw_out(rows, B, H, W, self.training)
 
 
 @NECKS.register_module
@@ -184,6 +199,8 @@ class S2D_RPN(RPN):
                                          nn.ConvTranspose3d(16, 3, 4, 2, 1), nn.BatchNorm3d(3), nn.ReLU())
         self.gen_out_2 = nn.Sequential(nn.Conv3d(3, 3, 1, 1, 0))
         self.gen_mask_2 = nn.Sequential(nn.Conv3d(3, 1, 1, 1, 0))
+        self.train_pcr = True         # training mode runs the PCR branch (rpn.py:314-323)
+        self.pcr_rows = None          # outputs of the last training forward's PCR branch (pcr.pcr_branch)
 
     def forward_rows(self, x, B, H, W):
         """S2D_RPN.forward (rpn.py:300-337) on NHWC rows ``x [B*H*W, C]`` -> (ups rows, F_S_a rows, F_S_b rows)."""
@@ -205,6 +222,10 @@ class S2D_RPN(RPN):
         d2 = self.decoder_2
         a, _, _ = D.conv("decoder_2.0", y_3, B, H1, W1, d2[0], d2[1], ACT_GELU)
         F_S_b, _, _ = D.tconv("decoder_2.3", a, B, H1, W1, d2[3], d2[4], ACT_GELU)                 # 188
+        self.pcr_rows = None
+        if self.training and self.train_pcr:
+            from . import pcr
+            self.pcr_rows = pcr.pcr_branch(self, F_S_b, B, H, W)
         fs, _, _ = D.conv("fusion_sparse.0", x, B, H, W, self.fusion_sparse[0], self.fusion_sparse[1], ACT_GELU)
         F_S_a, _, _ = D.conv("fusion_dense.0", F_S_b, B, H, W, self.fusion_dense[0], self.fusion_dense[1], ACT_GELU,
                              residual=fs, res_after_act=True)                                      # gelu(.) + gelu(.)
@@ -214,5 +235,11 @@ class S2D_RPN(RPN):
     def forward(self, x):
         """x: NCHW [B,C,188,188] -> (x [B,512,188,188], None, None, None, None, F_S_a, F_S_b) like the reference."""
         B, _, H, W = x.shape
-        ups, (Hu, Wu), F_S_a, F_S_b = self.forward_rows(to_rows(x), B, H, W)
-        return to_nchw(ups, B, Hu, Wu), None, None, None, None, to_nchw(F_S_a, B, H, W), to_nchw(F_S_b, B, H, W)
+        t = self.training
+        ups, (Hu, Wu), F_S_a, F_S_b = self.forward_rows(self._rows_in(x, t), B, H, W)
+        gen = (None, None, None, None)
+        if t and self.pcr_rows is not None:                           # NCDHW maps of the PCR branch (train only)
+            from . import pcr
+            gen = pcr.as_ncdhw(self.pcr_rows, B, H, W)
+        return (self._nchw_out(ups, B, Hu, Wu, t),) + tuple(gen) + (self._nchw_out(F_S_a, B, H, W, t),
+                                                                  self._nchw_out(F_S_b, B, H, W, t))

@@ -146,3 +146,96 @@ def random_module_state(module, seed):
             v = rng.normal(0, 0.05, shape)                  # biases
         out[key] = v.astype(np.float32)
     return out
+
+
+# ------------------------------------------------------------------------------------------
+# distillation training step (BASELINE configs[4]; configs/waymo/voxelnet/waymo_centerpoint_voxelnet_1x_distill.py)
+# ------------------------------------------------------------------------------------------
+WAYMO_TASKS = [dict(num_class=3, class_names=["VEHICLE", "PEDESTRIAN", "CYCLIST"])]
+WAYMO_VOXEL_CFG = dict(range=list(WAYMO_RANGE), voxel_size=[0.1, 0.1, 0.15], max_points_in_voxel=5,
+                       max_voxel_num=[150000, 200000], distillation=True)
+WAYMO_TEST_CFG = dict(post_center_limit_range=[-80, -80, -10.0, 80, 80, 10.0],
+                      nms=dict(use_rotate_nms=True, use_multi_class_nms=False, nms_pre_max_size=4096,
+                               nms_post_max_size=500, nms_iou_threshold=0.7),
+                      score_threshold=0.1, pc_range=[-75.2, -75.2], out_size_factor=8, voxel_size=[0.1, 0.1])
+
+
+def distill_model_cfgs():
+    """(teacher VoxelNet, student KD_VoxelNet) config dicts of the reference's Waymo distillation config (lines 17-75)."""
+    import logging
+
+    def det(kind, neck):
+        return dict(type=kind, pretrained=None, reader=dict(type="VoxelFeatureExtractorV3", num_input_features=5),
+                    backbone=dict(type="SpMiddleResNetFHD", num_input_features=5, ds_factor=8),
+                    neck=dict(type=neck, layer_nums=[5, 5], ds_layer_strides=[1, 2], ds_num_filters=[128, 256],
+                              us_layer_strides=[1, 2], us_num_filters=[256, 256], num_input_features=256,
+                              logger=logging.getLogger(neck)),
+                    bbox_head=dict(type="CenterHead", in_channels=512, tasks=WAYMO_TASKS, dataset="waymo", weight=2,
+                                   code_weights=[1.0] * 8,
+                                   common_heads={"reg": (2, 2), "height": (1, 2), "dim": (3, 2), "rot": (2, 2)}))
+    return det("VoxelNet", "RPN"), det("KD_VoxelNet", "S2D_RPN")
+
+
+def build_distill_models(device="cuda", precision=None, seed=0):
+    """Teacher + student with seeded random weights (no checkpoints exist on the build / GPU boxes)."""
+    import torch
+    from . import registry
+    t_cfg, s_cfg = distill_model_cfgs()
+    models = []
+    for i, cfg in enumerate((t_cfg, s_cfg)):
+        m = registry.build_detector(cfg, train_cfg=None, test_cfg=WAYMO_TEST_CFG)
+        m.backbone.load_state_dict({k: torch.as_tensor(v) for k, v in backbone_state(seed + i).items()})
+        for j, sub in enumerate((m.neck, m.bbox_head)):
+            sub.load_state_dict({k: torch.as_tensor(v) for k, v in random_module_state(sub, 100 * (seed + i) + 11 + j).items()},
+                                strict=False)
+        with torch.no_grad():
+            m.bbox_head.tasks[0].hm[-1].bias.fill_(-2.19)
+        m.to(device)
+        if precision is not None:
+            m.set_precision(precision)
+        models.append(m)
+    return models[0], models[1]
+
+
+def random_targets(batch, H=188, W=188, max_objs=500, n_obj=60, num_cls=3, seed=0):
+    """Synthetic CenterPoint targets in the layout ``AssignLabel`` produces (preprocess.py:489-653; lists with one entry per
+    task): hm [B,C,H,W] with gaussian peaks, anno_box [B,max_objs,10], ind / cat i64 [B,max_objs], mask u8."""
+    import torch
+    rng = np.random.default_rng(seed)
+    hm = np.zeros((batch, num_cls, H, W), np.float32)
+    anno = np.zeros((batch, max_objs, 10), np.float32)
+    ind = np.zeros((batch, max_objs), np.int64)
+    mask = np.zeros((batch, max_objs), np.uint8)
+    cat = np.zeros((batch, max_objs), np.int64)
+    ys, xs = np.mgrid[0:H, 0:W]
+    for b in range(batch):
+        n = int(rng.integers(n_obj // 2, n_obj + 1))
+        cells = rng.choice(H * W, n, replace=False)
+        for k, cell in enumerate(cells):
+            cy, cx, c = cell // W, cell % W, int(rng.integers(0, num_cls))
+            r = float(rng.uniform(1.0, 3.0))
+            g = np.exp(-((xs - cx) ** 2 + (ys - cy) ** 2) / (2 * r * r)).astype(np.float32)
+            g[g < 1e-3] = 0
+            hm[b, c] = np.maximum(hm[b, c], g)
+            ind[b, k], mask[b, k], cat[b, k] = cell, 1, c
+            rot = rng.uniform(-np.pi, np.pi)
+            anno[b, k] = np.concatenate([rng.uniform(0, 1, 2), rng.uniform(-1, 2, 1), np.log(rng.uniform(0.5, 6, 3)),
+                                         rng.normal(0, 1, 2), [np.sin(rot), np.cos(rot)]])
+    t = torch.as_tensor
+    return dict(hm=[t(hm)], anno_box=[t(anno)], ind=[t(ind)], mask=[t(mask)], cat=[t(cat)])
+
+
+def distill_example(batch, cfg=1, device="cuda", small=False):
+    """One synthetic distillation batch: the student's input is a thinned sweep of each scene, the teacher's dense /
+    reconstruction input the full cloud (the reference's multi-sweep object-completed clouds are dataset products)."""
+    import torch
+    from .pipeline import Voxelization
+    scenes = [small_scene(1000 * cfg + i) for i in range(batch)] if small else lidar_batch(cfg, batch)
+    scenes = [s[in_range_mask(s)] for s in scenes]
+    sparse = [s[::2] for s in scenes]
+    vox = Voxelization(cfg=WAYMO_VOXEL_CFG)
+    ex = vox(sparse, dense_points=scenes, reconstruction_points=scenes, mode="train", device=device)
+    tg = random_targets(batch, seed=cfg)
+    ex.update({k: [v[0].to(device)] for k, v in tg.items()})
+    ex["metadata"] = [dict(token=f"synthetic_{cfg}_{i}") for i in range(batch)]
+    return ex

@@ -1,0 +1,51 @@
+#!/usr/bin/env python
+"""Timing of one distillation training step (teacher forward, student forward + backward, gradient clip, Adam) on
+synthetic Waymo-shaped batches (BASELINE configs[4]).  usage: bench_train.py [--batch 2] [--steps 5] [--no-pcr] [--small]"""
+import argparse
+import os
+import sys
+import time
+
+import numpy as np
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from sparse2dense_b200 import ops, synth  # noqa: E402
+from sparse2dense_b200.trainer import DistillTrainer  # noqa: E402
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--batch", type=int, default=2)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=2)
+    ap.add_argument("--precision", default="auto")
+    ap.add_argument("--no-pcr", action="store_true")
+    ap.add_argument("--small", action="store_true")
+    a = ap.parse_args()
+    teacher, student = synth.build_distill_models("cuda", ops.PRECISION_NAMES[a.precision])
+    student.neck.train_pcr = not a.no_pcr
+    tr = DistillTrainer(teacher, student, total_steps=1000)
+    ex = synth.distill_example(a.batch, small=a.small)
+    print("voxels student/dense/recon:", ex["voxels"].shape[0], ex["dense_voxels"].shape[0], ex["reconstruction_voxels"].shape[0])
+    for i in range(a.warmup):
+        log = tr.step(ex)
+        print("warmup", i, {k: (round(float(v), 5)) for k, v in log.items()})
+    torch.cuda.synchronize()
+    ms = []
+    for i in range(a.steps):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        t0 = time.perf_counter()
+        e0.record()
+        log = tr.step(ex)
+        e1.record()
+        torch.cuda.synchronize()
+        ms.append(e0.elapsed_time(e1))
+        print("step", i, f"{ms[-1]:.1f} ms (wall {1e3 * (time.perf_counter() - t0):.1f})", {k: round(float(v), 5) for k, v in log.items()})
+    t = float(np.median(ms))
+    print(f"distillation step batch {a.batch} {a.precision} pcr={not a.no_pcr}: {t:.1f} ms/step -> {a.batch / t * 1e3:.2f} scenes/s; "
+          f"peak memory {torch.cuda.max_memory_allocated() / 2**30:.1f} GiB")
+
+
+if __name__ == "__main__":
+    main()
