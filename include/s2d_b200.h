@@ -381,6 +381,21 @@ int s2d_gather_reg_loss_bwd(const float* pred, long long pred_sb, long long pred
                             const unsigned char* mask, const double* sums, const float* upstream, float* d_pred,
                             long long d_numel, long long d_sb, long long d_sc, long long d_scell, void* stream);
 
+/* PCR losses, KD_VoxelNet.mask_offset_loss (det3d/models/detectors/voxelnet.py:171-185,229-249) without the dense gt / grid
+ * tensors: predictions are rows in (b, y, x, z) order (row = ((b*H + y)*W + x)*D + z; mask_logits [n], offset [n,3]); the
+ * reconstruction voxels are coors i32 [M,4] (b,z,y,x) + gt_feats f32 [M,5] (voxel means).  centre9 = {scale, minus, half} per
+ * axis x, y, z: voxel centre = idx*scale - minus + half evaluated in fp32 in that order (the reference's grid expression).
+ * sums6 = { sum softplus(x) over all cells, sum softplus(-x) over occupied, sum softplus(x) over occupied, #occupied,
+ *           sum |offset - (gt_xyz - centre)| over the non-zero targets, their count };
+ *   mask loss = (sums[0] - sums[2] + beta*sums[1]) / n with beta = (n - #occ) / #occ;  offset loss = sums[4] / sums[5].
+ * s2d_pcr_loss_bwd: upstream2 = device {d mask loss, d offset loss}; writes d_mask_logits [n] and d_offset [n,3] (zero-filled). */
+int s2d_pcr_loss(const float* mask_logits, const float* offset, int B, int D, int H, int W, const int* coors,
+                 const float* gt_feats, long long M, const float* centre9, double* sums6, void* workspace,
+                 size_t workspace_bytes, void* stream);
+int s2d_pcr_loss_bwd(const float* mask_logits, const float* offset, int B, int D, int H, int W, const int* coors,
+                     const float* gt_feats, long long M, const float* centre9, const double* sums6, const float* upstream2,
+                     float* d_mask_logits, float* d_offset, void* stream);
+
 /* ---------------------------------------------------------------------------------------
  * Training step (SURVEY.md section 8 rows a7 train-mode, a16 backward, a17): csrc/train.cu.
  *

@@ -78,6 +78,8 @@ SIGNATURES = {
                                 _vp, ctypes.c_longlong, ctypes.c_longlong, ctypes.c_longlong, _vp]),
     "s2d_gather_reg_loss_bwd": (_i, [_vp, ctypes.c_longlong, ctypes.c_longlong, ctypes.c_longlong, _vp, _vp, ctypes.c_longlong, ctypes.c_longlong, ctypes.c_longlong, _i, _i, _i, _i, _vp, _vp, _vp, _vp,
                                      _vp, ctypes.c_longlong, ctypes.c_longlong, ctypes.c_longlong, ctypes.c_longlong, _vp]),
+    "s2d_pcr_loss": (_i, [_vp, _vp, _i, _i, _i, _i, _vp, _vp, ctypes.c_longlong, _c_float_p, _vp, _vp, _sz, _vp]),
+    "s2d_pcr_loss_bwd": (_i, [_vp, _vp, _i, _i, _i, _i, _vp, _vp, ctypes.c_longlong, _c_float_p, _vp, _vp, _vp, _vp, _vp]),
     "s2d_table_transpose": (_i, [_vp, _i, _i, _i, _vp, _vp, _i, _i, _vp]),
     "s2d_conv_wgrad_workspace_bytes": (_sz, [_i, _i, _i, _i]),
     "s2d_conv_wgrad": (_i, [_vp, _i, _i, _i, _vp, _i, _vp, _i, _vp, _i, _i, _i, _vp, _i, _vp, _sz, _vp]),

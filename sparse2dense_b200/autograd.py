@@ -56,6 +56,22 @@ def conv_wgrad(g, d, tbl, n_rows, d_rows=None):
     return out
 
 
+_MAX_K = 27          # taps per s2d_conv_fwd launch (kMaxK of the library)
+
+
+def conv_rows_any_k(x, w, tbl, n_out, precision):
+    """conv_rows for any number of taps: more than 27 (the 4x4x4 adjoint of ConvTranspose3d) run as successive launches
+    that accumulate through the residual input."""
+    K = tbl.shape[0]
+    if K <= _MAX_K:
+        return conv_rows(x, w, tbl, n_out, precision=precision)
+    out = None
+    for k0 in range(0, K, _MAX_K):
+        k1 = min(K, k0 + _MAX_K)
+        out = conv_rows(x, w[k0:k1].contiguous(), tbl[k0:k1], n_out, residual=out, precision=precision)
+    return out
+
+
 class GatherConv(torch.autograd.Function):
     """out[i] = sum_k x[tbl[k][i]] . w[k]   (x [n_in, Cin], w [K, Cin, Cout])."""
 
@@ -92,13 +108,14 @@ class TransposedConv(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, x, w_t, classes, adj_table, precision):
-        # x [B*H*W, Cin]; w_t torch layout [Cin, Cout, k, k]; classes: [(kio_builder args, tbl, rows)]
+        # x [n_coarse, Cin]; w_t torch layout [Cin, Cout, *kernel] (2-D or 3-D); classes: [(taps, tbl, out_rows)] with
+        # taps = kernel index tuples in the order of the class table's rows
         x = x if x.stride(1) == 1 else x.contiguous()
-        cin, cout, kh, kw = w_t.shape
+        cin, cout = w_t.shape[:2]
         n_fine = adj_table.n_in
         out = torch.empty((n_fine, cout), dtype=torch.float32, device=x.device)
         for taps, tbl, rows in classes:
-            kio = torch.stack([w_t[:, :, ky, kx] for ky, kx in taps], 0).contiguous()
+            kio = torch.stack([w_t[(slice(None), slice(None)) + tuple(t)] for t in taps], 0).contiguous()
             conv_rows(x, kio, tbl, x.shape[0], out=out, out_rows=rows, precision=precision)
         ctx.save_for_backward(x, w_t)
         ctx.adj, ctx.precision = adj_table, precision
@@ -108,15 +125,15 @@ class TransposedConv(torch.autograd.Function):
     def backward(ctx, dy):
         x, w_t = ctx.saved_tensors
         adj = ctx.adj                                                  # fine grid (n_in) -> coarse grid (n_out)
-        cin, cout, kh, kw = w_t.shape
+        cin, cout = w_t.shape[:2]
         dy = dy.contiguous()
         dx = dw = None
         if ctx.needs_input_grad[0]:
-            kio = w_t.permute(2, 3, 1, 0).reshape(kh * kw, cout, cin).contiguous()
-            dx = conv_rows(dy, kio, adj.tbl, adj.n_out, precision=ctx.precision)
+            kio = w_t.flatten(2).permute(2, 1, 0).contiguous()         # [K, Cout, Cin], K row-major over the kernel dims
+            dx = conv_rows_any_k(dy, kio, adj.tbl, adj.n_out, ctx.precision)
         if ctx.needs_input_grad[1]:
             g = conv_wgrad(dy, x, adj.tbl, adj.n_out)                  # [K, Cout, Cin]
-            dw = g.permute(2, 1, 0).reshape(cin, cout, kh, kw).contiguous()
+            dw = g.permute(2, 1, 0).reshape(w_t.shape).contiguous()
         return dx, dw, None, None, None
 
 

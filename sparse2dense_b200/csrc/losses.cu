@@ -213,6 +213,96 @@ __global__ void gather_reg_loss_bwd_kernel(MapView pred, const float* __restrict
   }
 }
 
+// ---- PCR losses: KD_VoxelNet.mask_offset_loss (det3d/models/detectors/voxelnet.py:171-185) -------------------------------
+// The reference densifies the reconstruction voxels into gt [N,5,D,H,W] (136-543 MB at B = 4), builds a same-sized grid of
+// voxel centres and evaluates  BCEWithLogits(gen_mask, gt.sum(1) != 0, pos_weight = #neg / #pos)  and
+// L1(gen_offset[sel], (gt[:, :3] - grid * mask)[sel]),  sel = that difference != 0.  Only occupied voxels have a non-zero
+// gt, so here: one dense pass over the mask logits (softplus sum) plus one pass over the M occupied voxels.
+// Predictions are rows in (b, y, x, z) order (z fastest): row = ((b*H + y)*W + x)*D + z.
+__device__ __forceinline__ float softplusf(float x) { return fmaxf(x, 0.f) + log1pf(expf(-fabsf(x))); }
+
+struct PcrGrid { int D, H, W; float sx, mx, hx, sy, my, hy, sz, mz, hz; };   // centre = idx*s - m + h, in that order (fp32)
+
+__global__ void __launch_bounds__(kRedThreads) pcr_softplus_sum_kernel(const float* __restrict__ logits, long long n,
+                                                                       double* __restrict__ partial) {
+  double acc[1] = {0.0};
+  float f = 0.f;
+  int since = 0;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    f += softplusf(__ldg(logits + i));
+    if (++since == 64) { acc[0] += (double)f; f = 0.f; since = 0; }
+  }
+  acc[0] += (double)f;
+  block_reduce_store<1>(acc, partial);
+}
+
+__device__ __forceinline__ bool pcr_voxel(const PcrGrid& g, const int* __restrict__ coors, const float* __restrict__ gt,
+                                          long long v, long long& row, float (&t3)[3]) {
+  const int b = coors[v * 4], z = coors[v * 4 + 1], y = coors[v * 4 + 2], x = coors[v * 4 + 3];
+  const float* f = gt + v * 5;
+  const float sum = (((f[0] + f[1]) + f[2]) + f[3]) + f[4];
+  row = (((long long)b * g.H + y) * g.W + x) * g.D + z;
+  if (sum == 0.f) return false;
+  t3[0] = __fsub_rn(f[0], __fadd_rn(__fsub_rn(__fmul_rn((float)x, g.sx), g.mx), g.hx));
+  t3[1] = __fsub_rn(f[1], __fadd_rn(__fsub_rn(__fmul_rn((float)y, g.sy), g.my), g.hy));
+  t3[2] = __fsub_rn(f[2], __fadd_rn(__fsub_rn(__fmul_rn((float)z, g.sz), g.mz), g.hz));
+  return true;
+}
+
+// partial sums: {softplus(-x) over pos, softplus(x) over pos, #pos, sum |offset - t3| over sel, #sel}
+__global__ void __launch_bounds__(kRedThreads) pcr_voxel_loss_kernel(PcrGrid g, const float* __restrict__ logits,
+                                                                     const float* __restrict__ offset,
+                                                                     const int* __restrict__ coors, const float* __restrict__ gt,
+                                                                     long long M, double* __restrict__ partial) {
+  double acc[5] = {0.0, 0.0, 0.0, 0.0, 0.0};
+  for (long long v = (long long)blockIdx.x * blockDim.x + threadIdx.x; v < M; v += (long long)gridDim.x * blockDim.x) {
+    long long row;
+    float t3[3];
+    if (!pcr_voxel(g, coors, gt, v, row, t3)) continue;
+    const float x = __ldg(logits + row);
+    acc[0] += (double)softplusf(-x);
+    acc[1] += (double)softplusf(x);
+    acc[2] += 1.0;
+#pragma unroll
+    for (int c = 0; c < 3; ++c)
+      if (t3[c] != 0.f) { acc[3] += (double)fabsf(__ldg(offset + row * 3 + c) - t3[c]); acc[4] += 1.0; }
+  }
+  block_reduce_store<5>(acc, partial);
+}
+
+// sums6 = {softplus over all, softplus(-x) pos, softplus(x) pos, #pos, l1 sum, #sel}
+__global__ void pcr_mask_bwd_dense_kernel(const float* __restrict__ logits, long long n, const float* __restrict__ up,
+                                          float* __restrict__ d_logits) {
+  const float c = (up ? up[0] : 1.f) / (float)n;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const float x = __ldg(logits + i);
+    d_logits[i] = c * __fdiv_rn(1.f, 1.f + expf(-x));
+  }
+}
+
+__global__ void pcr_voxel_bwd_kernel(PcrGrid g, const float* __restrict__ logits, const float* __restrict__ offset,
+                                     const int* __restrict__ coors, const float* __restrict__ gt, long long M, long long n,
+                                     const double* __restrict__ sums6, const float* __restrict__ up,
+                                     float* __restrict__ d_logits, float* __restrict__ d_offset) {
+  const float npos = (float)sums6[3];
+  const float beta = ((float)n - npos) / npos;
+  const float cm = (up ? up[0] : 1.f) / (float)n;
+  const float co = sums6[5] > 0.0 ? (up ? up[1] : 1.f) / (float)sums6[5] : 0.f;
+  for (long long v = (long long)blockIdx.x * blockDim.x + threadIdx.x; v < M; v += (long long)gridDim.x * blockDim.x) {
+    long long row;
+    float t3[3];
+    if (!pcr_voxel(g, coors, gt, v, row, t3)) continue;
+    const float x = __ldg(logits + row);
+    d_logits[row] = -cm * beta * __fdiv_rn(1.f, 1.f + expf(x));                 // replaces the negative-cell gradient
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      if (t3[c] == 0.f) continue;
+      const float e = __ldg(offset + row * 3 + c) - t3[c];
+      d_offset[row * 3 + c] = co * (e > 0.f ? 1.f : (e < 0.f ? -1.f : 0.f));
+    }
+  }
+}
+
 }  // namespace s2d
 
 using namespace s2d;
@@ -325,6 +415,52 @@ extern "C" int s2d_gather_reg_loss_bwd(const float* pred, long long pred_sb, lon
     gather_reg_loss_bwd_kernel<<<((long long)B * M * D + 255) / 256, 256, 0, st>>>(
         MapView{pred, pred_sb, pred_sc, pred_scell}, target_rows, MapView{target_map, tgt_sb, tgt_sc, tgt_scell}, B, M, D, squared,
         ind, mask, sums, upstream, GradView{d_pred, d_sb, d_sc, d_scell});
+    S2D_LAUNCH_CHECK();
+    count_launches(1);
+  }
+  return S2D_OK;
+}
+
+static PcrGrid pcr_grid(int D, int H, int W, const float* c9) {
+  return PcrGrid{D, H, W, c9[0], c9[1], c9[2], c9[3], c9[4], c9[5], c9[6], c9[7], c9[8]};
+}
+
+extern "C" int s2d_pcr_loss(const float* mask_logits, const float* offset, int B, int D, int H, int W, const int* coors,
+                            const float* gt_feats, long long M, const float* centre9, double* sums6, void* workspace,
+                            size_t workspace_bytes, void* stream) {
+  S2D_REQUIRE(mask_logits && offset && centre9 && sums6 && workspace && (M == 0 || (coors && gt_feats)),
+              "s2d_pcr_loss: null argument");
+  S2D_REQUIRE(B >= 1 && D >= 1 && H >= 1 && W >= 1 && M >= 0, "s2d_pcr_loss: bad sizes");
+  S2D_REQUIRE(workspace_bytes >= s2d_loss_workspace_bytes(), "s2d_pcr_loss: workspace too small");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  double* partial = static_cast<double*>(workspace);
+  const long long n = (long long)B * D * H * W;
+  pcr_softplus_sum_kernel<<<kRedBlocks, kRedThreads, 0, st>>>(mask_logits, n, partial);
+  final_reduce_kernel<1><<<1, 32, 0, st>>>(partial, kRedBlocks, sums6);
+  pcr_voxel_loss_kernel<<<kRedBlocks, kRedThreads, 0, st>>>(pcr_grid(D, H, W, centre9), mask_logits, offset, coors, gt_feats, M,
+                                                           partial);
+  final_reduce_kernel<5><<<1, 32, 0, st>>>(partial, kRedBlocks, sums6 + 1);
+  S2D_LAUNCH_CHECK();
+  count_launches(4);
+  return S2D_OK;
+}
+
+extern "C" int s2d_pcr_loss_bwd(const float* mask_logits, const float* offset, int B, int D, int H, int W, const int* coors,
+                                const float* gt_feats, long long M, const float* centre9, const double* sums6,
+                                const float* upstream2, float* d_mask_logits, float* d_offset, void* stream) {
+  S2D_REQUIRE(mask_logits && offset && centre9 && sums6 && d_mask_logits && d_offset && (M == 0 || (coors && gt_feats)),
+              "s2d_pcr_loss_bwd: null argument");
+  S2D_REQUIRE(B >= 1 && D >= 1 && H >= 1 && W >= 1 && M >= 0, "s2d_pcr_loss_bwd: bad sizes");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const long long n = (long long)B * D * H * W;
+  S2D_CUDA(cudaMemsetAsync(d_offset, 0, (size_t)n * 3 * sizeof(float), st));
+  pcr_mask_bwd_dense_kernel<<<148 * 16, 256, 0, st>>>(mask_logits, n, upstream2, d_mask_logits);
+  S2D_LAUNCH_CHECK();
+  count_launches(1);
+  if (M > 0) {
+    long long blocks = (M + 255) / 256;
+    pcr_voxel_bwd_kernel<<<(int)blocks, 256, 0, st>>>(pcr_grid(D, H, W, centre9), mask_logits, offset, coors, gt_feats, M, n,
+                                                     sums6, upstream2, d_mask_logits, d_offset);
     S2D_LAUNCH_CHECK();
     count_launches(1);
   }

@@ -101,6 +101,9 @@ class FlatAdam:
                                      self.exp_avg_sq.data_ptr(), n, float(lr), float(mom), float(self.beta2),
                                      float(self.eps), float(self.wd), self.steps, self._norm[1:].data_ptr(), st),
                    "s2d_adam_step")
+        # the kernel wrote the parameters behind autograd's back: bump their version counters so that derived-weight
+        # caches (packed tensor-core images, folded BN) keyed on tensor versions are rebuilt by the next eval forward
+        torch.autograd.graph.increment_version(self.params)
         return self._norm                                        # device [2]: gradient norm before clipping, coefficient
 
 

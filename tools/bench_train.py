@@ -23,10 +23,15 @@ def main():
     ap.add_argument("--no-pcr", action="store_true")
     ap.add_argument("--small", action="store_true")
     a = ap.parse_args()
+    world, rank = int(os.environ.get("WORLD_SIZE", "1")), int(os.environ.get("RANK", "0"))
+    if world > 1:                                              # DDP: one process per GPU, scenes sharded over ranks
+        import torch.distributed as dist
+        torch.cuda.set_device(int(os.environ.get("LOCAL_RANK", "0")))
+        dist.init_process_group("nccl")
     teacher, student = synth.build_distill_models("cuda", ops.PRECISION_NAMES[a.precision])
     student.neck.train_pcr = not a.no_pcr
     tr = DistillTrainer(teacher, student, total_steps=1000)
-    ex = synth.distill_example(a.batch, small=a.small)
+    ex = synth.distill_example(a.batch, cfg=1 + rank, small=a.small)
     print("voxels student/dense/recon:", ex["voxels"].shape[0], ex["dense_voxels"].shape[0], ex["reconstruction_voxels"].shape[0])
     for i in range(a.warmup):
         log = tr.step(ex)
@@ -43,6 +48,17 @@ def main():
         ms.append(e0.elapsed_time(e1))
         print("step", i, f"{ms[-1]:.1f} ms (wall {1e3 * (time.perf_counter() - t0):.1f})", {k: round(float(v), 5) for k, v in log.items()})
     t = float(np.median(ms))
+    if world > 1:
+        tt = torch.tensor([t], device="cuda")
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        t = float(tt)
+        w0 = next(student.parameters()).detach().flatten()[:1000].clone()
+        w1 = w0.clone()
+        dist.broadcast(w1, src=0)
+        print(f"rank {rank}: weights identical to rank 0 after {a.warmup + a.steps} steps: {bool(torch.equal(w0, w1))}")
+        if rank != 0:
+            return
+        a.batch *= world
     print(f"distillation step batch {a.batch} {a.precision} pcr={not a.no_pcr}: {t:.1f} ms/step -> {a.batch / t * 1e3:.2f} scenes/s; "
           f"peak memory {torch.cuda.max_memory_allocated() / 2**30:.1f} GiB")
 
