@@ -22,6 +22,7 @@ def main():
     ap.add_argument("--precision", default="auto")
     ap.add_argument("--no-pcr", action="store_true")
     ap.add_argument("--small", action="store_true")
+    ap.add_argument("--profile", action="store_true", help="print the per-kernel device time of one step (torch.profiler)")
     a = ap.parse_args()
     world, rank = int(os.environ.get("WORLD_SIZE", "1")), int(os.environ.get("RANK", "0"))
     if world > 1:                                              # DDP: one process per GPU, scenes sharded over ranks
@@ -47,6 +48,21 @@ def main():
         torch.cuda.synchronize()
         ms.append(e0.elapsed_time(e1))
         print("step", i, f"{ms[-1]:.1f} ms (wall {1e3 * (time.perf_counter() - t0):.1f})", {k: round(float(v), 5) for k, v in log.items()})
+    if a.profile:
+        from torch.profiler import ProfilerActivity, profile
+        with profile(activities=[ProfilerActivity.CUDA]) as prof:
+            tr.step(ex)
+            torch.cuda.synchronize()
+        agg = {}
+        for e in prof.events():
+            if e.device_type == torch.autograd.DeviceType.CUDA:
+                v = agg.setdefault(e.name.split("(")[0][:100], [0.0, 0])
+                v[0] += e.device_time / 1e3
+                v[1] += 1
+        tot = sum(v[0] for v in agg.values())
+        print(f"kernel time of one step: {tot:.1f} ms over {sum(v[1] for v in agg.values())} launches")
+        for k, (m, n) in sorted(agg.items(), key=lambda kv: -kv[1][0])[:32]:
+            print(f"  {m:8.2f} ms {n:5d}  {k}")
     t = float(np.median(ms))
     if world > 1:
         tt = torch.tensor([t], device="cuda")
