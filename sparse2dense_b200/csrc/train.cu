@@ -40,8 +40,12 @@ template <int TA, int TB>
 __global__ void __launch_bounds__(256) conv_wgrad_kernel(const float* __restrict__ G, int g_ld, int n_g, int Cg,
                                                          const float* __restrict__ D, int d_ld, const int* __restrict__ d_rows,
                                                          int Cd, const int* __restrict__ tbl, int tbl_stride, int n_rows,
-                                                         int rows_per_chunk, int na_tiles, float* __restrict__ partial) {
+                                                         int rows_per_chunk, int na_tiles, int vec4,
+                                                         float* __restrict__ partial) {
   constexpr int CA = 16 * TA, CB = 16 * TB;
+  // column of register v of thread tb: 8-wide tiles are split in two float4 halves 64 columns apart so that the 16 lanes of
+  // a row read consecutive 16-byte words (no shared-memory bank conflicts)
+  auto bcol = [](int tb, int v) { return TB == 8 ? (v < 4 ? tb * 4 + v : 64 + tb * 4 + (v - 4)) : tb * TB + v; };
   __shared__ __align__(16) float Gs[kWgSlab][CA];
   __shared__ __align__(16) float Ds[kWgSlab][CB];
   __shared__ int js[kWgSlab], is[kWgSlab];
@@ -70,15 +74,32 @@ __global__ void __launch_bounds__(256) conv_wgrad_kernel(const float* __restrict
       is[threadIdx.x] = j >= 0 ? di : -1;
     }
     __syncthreads();
-    for (int e = threadIdx.x; e < kWgSlab * CA; e += 256) {
-      const int r = e / CA, c = e - r * CA;
-      const int j = js[r];
-      Gs[r][c] = (j >= 0 && a0 + c < Cg) ? __ldg(G + (size_t)j * g_ld + a0 + c) : 0.f;
-    }
-    for (int e = threadIdx.x; e < kWgSlab * CB; e += 256) {
-      const int r = e / CB, c = e - r * CB;
-      const int i = is[r];
-      Ds[r][c] = (i >= 0 && b0 + c < Cd) ? __ldg(D + (size_t)i * d_ld + b0 + c) : 0.f;
+    if (vec4) {                                   // rows are 16-byte aligned and the channel counts multiples of 4
+      for (int e = threadIdx.x; e < kWgSlab * (CA / 4); e += 256) {
+        const int r = e / (CA / 4), c = (e - r * (CA / 4)) * 4;
+        const int j = js[r];
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (j >= 0 && a0 + c < Cg) v = __ldg(reinterpret_cast<const float4*>(G + (size_t)j * g_ld + a0 + c));
+        *reinterpret_cast<float4*>(&Gs[r][c]) = v;
+      }
+      for (int e = threadIdx.x; e < kWgSlab * (CB / 4); e += 256) {
+        const int r = e / (CB / 4), c = (e - r * (CB / 4)) * 4;
+        const int i = is[r];
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (i >= 0 && b0 + c < Cd) v = __ldg(reinterpret_cast<const float4*>(D + (size_t)i * d_ld + b0 + c));
+        *reinterpret_cast<float4*>(&Ds[r][c]) = v;
+      }
+    } else {
+      for (int e = threadIdx.x; e < kWgSlab * CA; e += 256) {
+        const int r = e / CA, c = e - r * CA;
+        const int j = js[r];
+        Gs[r][c] = (j >= 0 && a0 + c < Cg) ? __ldg(G + (size_t)j * g_ld + a0 + c) : 0.f;
+      }
+      for (int e = threadIdx.x; e < kWgSlab * CB; e += 256) {
+        const int r = e / CB, c = e - r * CB;
+        const int i = is[r];
+        Ds[r][c] = (i >= 0 && b0 + c < Cd) ? __ldg(D + (size_t)i * d_ld + b0 + c) : 0.f;
+      }
     }
     __syncthreads();
 #pragma unroll 4
@@ -87,7 +108,7 @@ __global__ void __launch_bounds__(256) conv_wgrad_kernel(const float* __restrict
 #pragma unroll
       for (int u = 0; u < TA; ++u) ga[u] = Gs[r][ta * TA + u];
 #pragma unroll
-      for (int v = 0; v < TB; ++v) db[v] = Ds[r][tb * TB + v];
+      for (int v = 0; v < TB; ++v) db[v] = Ds[r][bcol(tb, v)];
 #pragma unroll
       for (int u = 0; u < TA; ++u)
 #pragma unroll
@@ -103,7 +124,7 @@ __global__ void __launch_bounds__(256) conv_wgrad_kernel(const float* __restrict
     if (a >= Cg) continue;
 #pragma unroll
     for (int v = 0; v < TB; ++v) {
-      const int b = b0 + tb * TB + v;
+      const int b = b0 + bcol(tb, v);
       if (b < Cd) dst[(size_t)a * Cd + b] = acc[u][v];
     }
   }
@@ -118,9 +139,76 @@ __global__ void wgrad_reduce_kernel(const float* __restrict__ partial, int n_chu
   }
 }
 
+// Small channel counts (the 5-channel input layer, the 1/3-channel heads and generators of the PCR branch): a 16x16-thread
+// channel tile would idle most lanes, so here a THREAD owns rows and keeps the whole Cg x Cd block in registers; rows of
+// consecutive threads are consecutive in memory (coalesced), the block is reduced once per CTA with shuffles.
+template <int CG, int CD>
+__global__ void __launch_bounds__(256) conv_wgrad_small_kernel(const float* __restrict__ G, int g_ld, int n_g, int Cg,
+                                                               const float* __restrict__ D, int d_ld,
+                                                               const int* __restrict__ d_rows, int Cd,
+                                                               const int* __restrict__ tbl, int tbl_stride, int n_rows,
+                                                               int rows_per_chunk, float* __restrict__ partial) {
+  const int k = blockIdx.y;
+  float acc[CG][CD];
+#pragma unroll
+  for (int a = 0; a < CG; ++a)
+#pragma unroll
+    for (int b = 0; b < CD; ++b) acc[a][b] = 0.f;
+  const int r_begin = blockIdx.x * rows_per_chunk;
+  const int r_end = min(n_rows, r_begin + rows_per_chunk);
+  for (int i = r_begin + threadIdx.x; i < r_end; i += 256) {
+    const int j = __ldg(tbl + (size_t)k * tbl_stride + i);
+    if (j < 0 || j >= n_g) continue;
+    const int di = d_rows ? __ldg(d_rows + i) : i;
+    float g[CG], d[CD];
+#pragma unroll
+    for (int a = 0; a < CG; ++a) g[a] = a < Cg ? __ldg(G + (size_t)j * g_ld + a) : 0.f;
+#pragma unroll
+    for (int b = 0; b < CD; ++b) d[b] = b < Cd ? __ldg(D + (size_t)di * d_ld + b) : 0.f;
+#pragma unroll
+    for (int a = 0; a < CG; ++a)
+#pragma unroll
+      for (int b = 0; b < CD; ++b) acc[a][b] = fmaf(g[a], d[b], acc[a][b]);
+  }
+  __shared__ float sh[8][CG * CD];
+#pragma unroll
+  for (int a = 0; a < CG; ++a)
+#pragma unroll
+    for (int b = 0; b < CD; ++b) {
+      float v = acc[a][b];
+      for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+      if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5][a * CD + b] = v;
+    }
+  __syncthreads();
+  float* dst = partial + ((size_t)blockIdx.x * gridDim.y + k) * (size_t)Cg * Cd;
+  for (int e = threadIdx.x; e < CG * CD; e += 256) {
+    const int a = e / CD, b = e - a * CD;
+    if (a < Cg && b < Cd) {
+      float v = 0.f;
+      for (int w = 0; w < 8; ++w) v += sh[w][e];            // fixed order
+      dst[(size_t)a * Cd + b] = v;
+    }
+  }
+}
+
+// 0: tiled kernel; otherwise the (CG, CD) bucket of the small kernel encoded as CG * 100 + CD
+static int wgrad_small_bucket(int Cg, int Cd) {
+  if (Cg <= 4 && Cd <= 4) return 404;
+  if (Cg <= 4 && Cd <= 16) return 416;
+  if (Cg <= 8 && Cd <= 16) return 816;
+  if (Cg <= 32 && Cd <= 4) return 3204;
+  return 0;
+}
+
 static int wgrad_tile(int c) { return c <= 16 ? 1 : c <= 32 ? 2 : c <= 64 ? 4 : 8; }
 
 static int wgrad_chunks(int n_rows, int K, int Cg, int Cd) {
+  if (wgrad_small_bucket(Cg, Cd)) {
+    long long want = (148LL * 4 + K - 1) / K;
+    const long long max_chunks = (n_rows + 2047) / 2048;                         // at least 8 rows per thread
+    if (want > max_chunks) want = max_chunks;
+    return (int)(want < 1 ? 1 : want);
+  }
   const int ta = wgrad_tile(Cg), tb = wgrad_tile(Cd);
   const long long tiles = (long long)K * ((Cg + 16 * ta - 1) / (16 * ta)) * ((Cd + 16 * tb - 1) / (16 * tb));
   long long want = (148LL * 4 + tiles - 1) / tiles;                              // ~4 CTAs per SM in total
@@ -531,7 +619,10 @@ extern "C" size_t s2d_conv_wgrad_workspace_bytes(int n_rows, int K, int Cg, int 
 template <int TA, int TB>
 static void launch_wgrad(dim3 grid, cudaStream_t st, const float* g, int g_ld, int n_g, int Cg, const float* d, int d_ld,
                          const int* d_rows, int Cd, const int* tbl, int tbl_stride, int n_rows, int rpc, int na, float* partial) {
-  conv_wgrad_kernel<TA, TB><<<grid, 256, 0, st>>>(g, g_ld, n_g, Cg, d, d_ld, d_rows, Cd, tbl, tbl_stride, n_rows, rpc, na, partial);
+  const int vec4 = (g_ld % 4 == 0) && (d_ld % 4 == 0) && (Cg % 4 == 0) && (Cd % 4 == 0) &&
+                   ((reinterpret_cast<uintptr_t>(g) | reinterpret_cast<uintptr_t>(d)) & 15) == 0;
+  conv_wgrad_kernel<TA, TB><<<grid, 256, 0, st>>>(g, g_ld, n_g, Cg, d, d_ld, d_rows, Cd, tbl, tbl_stride, n_rows, rpc, na, vec4,
+                                                  partial);
 }
 
 extern "C" int s2d_conv_wgrad(const float* g, int g_ld, int n_g, int Cg, const float* d, int d_ld, const int* d_rows, int Cd,
@@ -550,6 +641,22 @@ extern "C" int s2d_conv_wgrad(const float* g, int g_ld, int n_g, int Cg, const f
   if (rpc < kWgSlab) rpc = kWgSlab;
   dim3 grid(chunks, K, na * nb);
   float* partial = static_cast<float*>(ws);
+  const int bucket = wgrad_small_bucket(Cg, Cd);
+  if (bucket) {
+    dim3 gs(chunks, K);
+#define S2D_WGS(CG_, CD_)                                                                                              \
+  if (bucket == CG_ * 100 + CD_)                                                                                        \
+    conv_wgrad_small_kernel<CG_, CD_><<<gs, 256, 0, st>>>(g, g_ld, n_g, Cg, d, d_ld, d_rows, Cd, tbl, tbl_stride, n_rows, \
+                                                          rpc, partial);
+    S2D_WGS(4, 4) S2D_WGS(4, 16) S2D_WGS(8, 16) S2D_WGS(32, 4)
+#undef S2D_WGS
+    S2D_LAUNCH_CHECK();
+    const long long n_elem_s = (long long)K * Cg * Cd;
+    wgrad_reduce_kernel<<<grid_for(n_elem_s, 256, 148 * 8), 256, 0, st>>>(partial, chunks, n_elem_s, accumulate, out);
+    S2D_LAUNCH_CHECK();
+    count_launches(2);
+    return S2D_OK;
+  }
 #define S2D_WG(TA_, TB_) \
   if (ta == TA_ && tb == TB_) launch_wgrad<TA_, TB_>(grid, st, g, g_ld, n_g, Cg, d, d_ld, d_rows, Cd, tbl, tbl_stride, n_rows, rpc, na, partial);
   S2D_WG(1, 1) S2D_WG(1, 2) S2D_WG(1, 4) S2D_WG(1, 8)

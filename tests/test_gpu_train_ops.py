@@ -81,6 +81,26 @@ def test_gather_conv_forward_backward(cin, cout, K, precision):
     assert rel(wc.grad, w.grad) < 1e-4
 
 
+@pytest.mark.parametrize("cg,cd,K", [(3, 16, 8), (5, 16, 27), (32, 3, 1), (32, 1, 1), (3, 1, 1), (3, 3, 1), (16, 3, 8),
+                                     (64, 64, 9), (128, 256, 3), (20, 36, 4)])
+def test_conv_wgrad_shapes(cg, cd, K):
+    """Row-parallel small-channel kernel, vectorised and scalar tile loaders, with and without a row indirection on D."""
+    n_g, n_rows = 5000, 4321
+    tbl = random_table(K, n_g, n_rows, 0.5, cg * 31 + cd)
+    rng = np.random.default_rng(cg + cd)
+    G, Dm = rng.normal(size=(n_g, cg)), rng.normal(size=(2 * n_rows, cd))
+    d_rows = rng.permutation(2 * n_rows)[:n_rows].astype(np.int32)
+    for use_rows in (False, True):
+        di = d_rows if use_rows else np.arange(n_rows)
+        want = np.zeros((K, cg, cd))
+        for k in range(K):
+            i = np.nonzero(tbl[k] >= 0)[0]
+            want[k] = G[tbl[k, i]].T @ Dm[di[i]]
+        got = AG.conv_wgrad(torch.from_numpy(G).float().to(DEV), torch.from_numpy(Dm).float().to(DEV),
+                            torch.from_numpy(tbl).to(DEV), n_rows, torch.from_numpy(d_rows).to(DEV) if use_rows else None)
+        assert float(np.abs(got.double().cpu().numpy() - want).max() / np.abs(want).max()) < 2e-5
+
+
 def test_subm_table_is_its_own_transpose():
     """The SubM rulebook satisfies tbl[k][i] = j <=> tbl[K-1-k][j] = i, which GatherConv uses for the data gradient."""
     rng = np.random.default_rng(4)
