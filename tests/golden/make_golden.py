@@ -541,7 +541,57 @@ def make_loss_goldens():
     np.savez_compressed(os.path.join(HERE, "losses.npz"), **save)
 
 
+def make_optim_goldens():
+    """The reference's own OptimWrapper (det3d/solver/fastai_optim.py:118-174, true_wd / bn_wd as build_one_cycle_optimizer
+    sets them, apis/train.py:168-186) over torch Adam, driven by the reference's OneCycle
+    (det3d/solver/learning_schedules_fastai.py:7-95) with the Waymo config's hyper-parameters, plus clip_grad_norm_(35)
+    (hooks/optimizer.py:15-21): parameter values after every step for fixed gradients."""
+    import collections
+    import collections.abc
+    from functools import partial
+    import torch
+    from torch import nn
+    collections.Iterable = collections.abc.Iterable            # the reference predates python 3.10
+    def load(name, path):
+        spec = importlib.util.spec_from_file_location(name, REF + path)
+        m = importlib.util.module_from_spec(spec)
+        spec.loader.exec_module(m)
+        return m
+    fo = load("fastai_optim", "/det3d/solver/fastai_optim.py")
+    ls = load("learning_schedules_fastai", "/det3d/solver/learning_schedules_fastai.py")
+    torch.manual_seed(3)
+    model = nn.Sequential(nn.Linear(7, 16), nn.BatchNorm1d(16), nn.ReLU(), nn.Linear(16, 5))
+    opt = fo.OptimWrapper.create(partial(torch.optim.Adam, betas=(0.9, 0.99), amsgrad=0.0), 3e-3, [model], wd=0.01,
+                                 true_wd=True, bn_wd=True)
+    total = 20
+    sched = ls.OneCycle(opt, total, 0.003, [0.95, 0.85], 10.0, 0.3)
+    names = [k for k, _ in model.named_parameters()]
+    save = {"names": np.array(names), "total_step": np.array(total)}
+    for k, p in model.named_parameters():
+        save["init_" + k] = p.detach().numpy().copy()
+    rng = np.random.default_rng(5)
+    lrs, moms, norms = [], [], []
+    for step in range(12):
+        sched.step(step)
+        lrs.append(opt.lr); moms.append(opt.mom)
+        scale = 40.0 if step % 3 == 0 else 0.5                  # every third step is clipped
+        for k, p in model.named_parameters():
+            g = (rng.normal(size=tuple(p.shape)) * scale).astype(np.float32)
+            save[f"grad{step}_{k}"] = g
+            p.grad = torch.from_numpy(g.copy())
+        norms.append(float(torch.nn.utils.clip_grad_norm_(model.parameters(), 35.0)))
+        opt.step()
+        for k, p in model.named_parameters():
+            save[f"param{step}_{k}"] = p.detach().numpy().copy()
+    save["lr"], save["mom"], save["norm"] = np.array(lrs), np.array(moms), np.array(norms)
+    np.savez_compressed(os.path.join(HERE, "optim.npz"), **save)
+    print("optim golden: lr", lrs[:4], "mom", moms[:4], "norms", norms[:4])
+
+
 if __name__ == "__main__":
+    if len(sys.argv) > 1 and sys.argv[1] == "optim":
+        make_optim_goldens()
+        sys.exit(0)
     if len(sys.argv) > 1 and sys.argv[1] == "loss":
         make_loss_goldens()
         sys.exit(0)
@@ -564,3 +614,4 @@ if __name__ == "__main__":
     make_second_stage_goldens()
     make_pillar_goldens()
     make_loss_goldens()
+    make_optim_goldens()

@@ -146,6 +146,34 @@ def test_one_cycle_matches_reference_formula():
     assert lr < 1e-6 and abs(m - 0.95) < 1e-4
 
 
+def test_flat_adam_follows_the_reference_optimizer_trajectory():
+    """FlatAdam (one grad-norm + one fused Adam launch on flat buffers) against the parameter values the reference's
+    OptimWrapper(true_wd) + torch Adam + OneCycle + clip_grad_norm_(35) produced for the same gradients (optim.npz)."""
+    import os
+    from torch import nn
+    from conftest import GOLDEN
+    from sparse2dense_b200.trainer import FlatAdam
+    g = np.load(os.path.join(GOLDEN, "optim.npz"))
+    model = nn.Sequential(nn.Linear(7, 16), nn.BatchNorm1d(16), nn.ReLU(), nn.Linear(16, 5)).cuda()
+    names = [str(k) for k in g["names"]]
+    assert names == [k for k, _ in model.named_parameters()]
+    with torch.no_grad():
+        for k, p in model.named_parameters():
+            p.copy_(torch.from_numpy(g["init_" + k]))
+    opt = FlatAdam(model.parameters(), wd=0.01)
+    sched = OneCycle(int(g["total_step"]), 0.003, (0.95, 0.85), 10.0, 0.3)
+    for step in range(len(g["lr"])):
+        lr, mom = sched.step(step)
+        opt.zero_grad()
+        for k, p in model.named_parameters():
+            p.grad.copy_(torch.from_numpy(g[f"grad{step}_{k}"]))
+        norm = opt.step(lr, mom, 35.0)
+        assert abs(float(norm[0]) - float(g["norm"][step])) < 1e-4 * float(g["norm"][step])
+        for k, p in model.named_parameters():
+            want = g[f"param{step}_{k}"]
+            assert np.abs(p.detach().cpu().numpy() - want).max() <= 2e-6 * max(1.0, np.abs(want).max()), (step, k)
+
+
 def test_trainer_steps_reduce_the_loss_and_update_every_parameter():
     teacher, student = synth.build_distill_models("cuda", ops.PRECISION_AUTO)
     student.neck.train_pcr = False
