@@ -397,6 +397,20 @@ int s2d_pcr_loss_bwd(const float* mask_logits, const float* offset, int B, int D
                      float* d_mask_logits, float* d_offset, void* stream);
 
 /* ---------------------------------------------------------------------------------------
+ * CenterPoint training targets for a batch: AssignLabel.__call__
+ * (det3d/datasets/pipelines/preprocess.py:489-653; gaussian_radius / draw_umich_gaussian, det3d/core/utils/center_utils.py:18-64;
+ * limit_period, det3d/core/bbox/box_np_ops.py:360-361) for ONE task.  gt_boxes f32 [B, max_objs, 9] (x y z w l h vx vy rot) in
+ * the task's class-major object order, gt_classes i32 [B, max_objs] 1-based inside the task, num_objs i32 [B].
+ * Outputs (zero-filled here): hm f32 [B, num_cls, H, W], anno_box f32 [B, max_objs, 10] (reg2, z, log wlh, vx, vy, sin, cos),
+ * ind / cat i64 [B, max_objs], mask u8 [B, max_objs], optional gt_boxes_and_cls f32 [B, max_objs, 10] (x y z w l h rot vx vy,
+ * class + cls_offset).  Objects with a non-positive size or a centre outside the map are skipped exactly as the reference does.
+ * ------------------------------------------------------------------------------------- */
+int s2d_assign_label(const float* gt_boxes, const int* gt_classes, const int* num_objs, int B, int max_objs, int num_cls,
+                     int H, int W, float pc_x, float pc_y, float voxel_x, float voxel_y, int out_size_factor,
+                     double gaussian_overlap, int min_radius, int cls_offset, float* hm, float* anno_box, long long* ind,
+                     unsigned char* mask, long long* cat, float* gt_boxes_and_cls, void* stream);
+
+/* ---------------------------------------------------------------------------------------
  * Training step (SURVEY.md section 8 rows a7 train-mode, a16 backward, a17): csrc/train.cu.
  *
  * Every convolution of this library is out[i] = sum_k in[tbl[k][i]] . W[k]; its backward is
@@ -439,6 +453,23 @@ int s2d_rows_affine_act_bwd(const float* x, int ld, int n, int C, const float* s
 int s2d_bn_train_bwd(const float* x, int ld, int n, int C, const float* dz, int dz_ld, const float* mean,
                      const float* invstd, const float* gamma, float* dx, int dx_ld, float* dgamma, float* dbeta,
                      void* workspace, size_t workspace_bytes, void* stream);
+/* SyncBatchNorm (tools/train.py:92-96 --sync_bn, apis/train.py:281-303): the same statistics / backward in two halves.
+ * The local column sums (2*C doubles) sit at byte offset s2d_rows_workspace_sums_offset(C) of the workspace after
+ * s2d_bn_train_sums / s2d_rows_affine_act_bwd; the caller all-reduces (sum) them together with its row count over the ranks
+ * (one NCCL all-reduce of 2*C + 1 doubles) and hands the result back as device pointers, so no host synchronisation:
+ * forward  s2d_bn_train_sums -> all-reduce -> s2d_bn_train_finalize(global sums, global rows);
+ * backward s2d_rows_affine_act_bwd -> s2d_bn_train_bwd_params (dgamma / dbeta from the LOCAL sums) -> all-reduce ->
+ *          s2d_bn_train_bwd_dx (global sums and rows).  n = 0 rows on a rank is allowed in the sums / dx calls. */
+size_t s2d_rows_workspace_sums_offset(int C);
+int s2d_bn_train_sums(const float* x, int ld, int n, int C, void* workspace, size_t workspace_bytes, void* stream);
+int s2d_bn_train_finalize(const double* sums2c, const double* n_total_dev, int C, float eps, float momentum,
+                          const float* gamma, const float* beta, float* running_mean, float* running_var, float* mean,
+                          float* invstd, float* scale, float* shift, void* stream);
+int s2d_bn_train_bwd_params(const double* sums2c_local, int C, const float* mean, const float* invstd, float* dgamma,
+                            float* dbeta, void* stream);
+int s2d_bn_train_bwd_dx(const float* x, int ld, int n, int C, const float* dz, int dz_ld, const float* mean,
+                        const float* invstd, const float* gamma, const double* sums2c_global, const double* n_total_dev,
+                        float* dx, int dx_ld, void* workspace, size_t workspace_bytes, void* stream);
 size_t s2d_layernorm_bwd_workspace_bytes(int B);
 int s2d_layernorm_chw_bwd(const float* x, const float* weight, int B, int C, int HW, float eps, const float* dy, float* dx,
                           float* dweight, float* dbias, void* workspace, size_t workspace_bytes, void* stream);

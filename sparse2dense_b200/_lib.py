@@ -80,6 +80,8 @@ SIGNATURES = {
                                      _vp, ctypes.c_longlong, ctypes.c_longlong, ctypes.c_longlong, ctypes.c_longlong, _vp]),
     "s2d_pcr_loss": (_i, [_vp, _vp, _i, _i, _i, _i, _vp, _vp, ctypes.c_longlong, _c_float_p, _vp, _vp, _sz, _vp]),
     "s2d_pcr_loss_bwd": (_i, [_vp, _vp, _i, _i, _i, _i, _vp, _vp, ctypes.c_longlong, _c_float_p, _vp, _vp, _vp, _vp, _vp]),
+    "s2d_assign_label": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _i, ctypes.c_float, ctypes.c_float, ctypes.c_float, ctypes.c_float, _i, ctypes.c_double, _i, _i, _vp, _vp, _vp, _vp,
+                              _vp, _vp, _vp]),
     "s2d_table_transpose": (_i, [_vp, _i, _i, _i, _vp, _vp, _i, _i, _vp]),
     "s2d_conv_wgrad_workspace_bytes": (_sz, [_i, _i, _i, _i]),
     "s2d_conv_wgrad": (_i, [_vp, _i, _i, _i, _vp, _i, _vp, _i, _vp, _i, _i, _i, _vp, _i, _vp, _sz, _vp]),
@@ -89,6 +91,11 @@ SIGNATURES = {
     "s2d_rows_affine_act": (_i, [_vp, _i, _i, _i, _vp, _vp, _vp, _i, _i, _i, _vp, _i, _vp]),
     "s2d_rows_affine_act_bwd": (_i, [_vp, _i, _i, _i, _vp, _vp, _vp, _i, _i, _i, _vp, _i, _vp, _i, _vp, _vp, _sz, _vp]),
     "s2d_bn_train_bwd": (_i, [_vp, _i, _i, _i, _vp, _i, _vp, _vp, _vp, _vp, _i, _vp, _vp, _vp, _sz, _vp]),
+    "s2d_rows_workspace_sums_offset": (_sz, [_i]),
+    "s2d_bn_train_sums": (_i, [_vp, _i, _i, _i, _vp, _sz, _vp]),
+    "s2d_bn_train_finalize": (_i, [_vp, _vp, _i, ctypes.c_float, ctypes.c_float, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "s2d_bn_train_bwd_params": (_i, [_vp, _i, _vp, _vp, _vp, _vp, _vp]),
+    "s2d_bn_train_bwd_dx": (_i, [_vp, _i, _i, _i, _vp, _i, _vp, _vp, _vp, _vp, _vp, _vp, _i, _vp, _sz, _vp]),
     "s2d_layernorm_bwd_workspace_bytes": (_sz, [_i]),
     "s2d_layernorm_chw_bwd": (_i, [_vp, _vp, _i, _i, _i, ctypes.c_float, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
     "s2d_dwconv2d_wgrad_workspace_bytes": (_sz, [_i, _i, _i, _i, _i]),

@@ -142,9 +142,21 @@ def _rows_ws(C, device):
     return torch.empty((nbytes,), dtype=torch.uint8, device=device), nbytes
 
 
+def _all_reduce_sums(ws, C, n, group):
+    """[2*C column sums, row count] of this rank (float64) summed over the ranks: ONE small all-reduce, no host sync."""
+    import torch.distributed as dist
+    off = _lib.load().s2d_rows_workspace_sums_offset(C)
+    buf = torch.empty((2 * C + 1,), dtype=torch.float64, device=ws.device)
+    buf[:2 * C].copy_(ws[off:off + 16 * C].view(torch.float64))
+    buf[2 * C:].fill_(float(n))
+    dist.all_reduce(buf, op=dist.ReduceOp.SUM, group=None if group is True else group)
+    return buf
+
+
 class RowsNormAct(torch.autograd.Function):
     """y = act(norm(x) (+ res))  or  act(norm(x)) + res  on rows [n, C].
-    ``bn`` = (running_mean, running_var, momentum, eps): training-mode BatchNorm with affine (gamma, beta);
+    ``bn`` = (running_mean, running_var, momentum, eps, group): training-mode BatchNorm with affine (gamma, beta);
+    ``group`` None = statistics of this rank, True / a process group = SyncBatchNorm over that group;
     ``bn`` = None: plain bias (gamma ignored, beta = bias or None)."""
 
     @staticmethod
@@ -154,14 +166,25 @@ class RowsNormAct(torch.autograd.Function):
         lib = _lib.load()
         residual = None if residual is None else (residual if residual.stride(1) == 1 else residual.contiguous())
         out = torch.empty_like(x)
+        group = None
         if bn is not None:
-            running_mean, running_var, momentum, eps = bn
+            running_mean, running_var, momentum, eps, group = bn
             stats = torch.empty((4, C), dtype=torch.float32, device=x.device)      # mean, invstd, scale, shift
             ws, nbytes = _rows_ws(C, x.device)
-            _lib.check(lib.s2d_bn_train_stats(x.data_ptr(), x.stride(0), n, C, float(eps), float(momentum), _ptr(gamma),
-                                              _ptr(beta), _ptr(running_mean), _ptr(running_var), stats[0].data_ptr(),
-                                              stats[1].data_ptr(), stats[2].data_ptr(), stats[3].data_ptr(),
-                                              ws.data_ptr(), nbytes, _stream()), "s2d_bn_train_stats")
+            if group is None:
+                _lib.check(lib.s2d_bn_train_stats(x.data_ptr(), x.stride(0), n, C, float(eps), float(momentum), _ptr(gamma),
+                                                  _ptr(beta), _ptr(running_mean), _ptr(running_var), stats[0].data_ptr(),
+                                                  stats[1].data_ptr(), stats[2].data_ptr(), stats[3].data_ptr(),
+                                                  ws.data_ptr(), nbytes, _stream()), "s2d_bn_train_stats")
+            else:                                     # SyncBatchNorm: statistics over the rows of every rank
+                _lib.check(lib.s2d_bn_train_sums(x.data_ptr(), x.stride(0), n, C, ws.data_ptr(), nbytes, _stream()),
+                           "s2d_bn_train_sums")
+                glob = _all_reduce_sums(ws, C, n, group)
+                _lib.check(lib.s2d_bn_train_finalize(glob.data_ptr(), glob[2 * C:].data_ptr(), C, float(eps),
+                                                     float(momentum), _ptr(gamma), _ptr(beta), _ptr(running_mean),
+                                                     _ptr(running_var), stats[0].data_ptr(), stats[1].data_ptr(),
+                                                     stats[2].data_ptr(), stats[3].data_ptr(), _stream()),
+                           "s2d_bn_train_finalize")
             scale, shift = stats[2], stats[3]
         else:
             stats, scale = None, None
@@ -170,7 +193,7 @@ class RowsNormAct(torch.autograd.Function):
                                            0 if residual is None else residual.stride(0), act, int(res_after_act),
                                            out.data_ptr(), out.stride(0), _stream()), "s2d_rows_affine_act")
         ctx.save_for_backward(x, gamma, beta, residual, stats)
-        ctx.is_bn, ctx.act, ctx.res_after_act = bn is not None, act, bool(res_after_act)
+        ctx.is_bn, ctx.act, ctx.res_after_act, ctx.group = bn is not None, act, bool(res_after_act), group
         return out
 
     @staticmethod
@@ -201,9 +224,21 @@ class RowsNormAct(torch.autograd.Function):
         dx = torch.empty_like(x)
         dgamma = torch.empty((C,), dtype=torch.float32, device=x.device)
         dbeta = torch.empty((C,), dtype=torch.float32, device=x.device)
-        _lib.check(lib.s2d_bn_train_bwd(x.data_ptr(), x.stride(0), n, C, dz.data_ptr(), dz.stride(0), stats[0].data_ptr(),
-                                        stats[1].data_ptr(), _ptr(gamma), dx.data_ptr(), dx.stride(0), dgamma.data_ptr(),
-                                        dbeta.data_ptr(), ws.data_ptr(), nbytes, _stream()), "s2d_bn_train_bwd")
+        if ctx.group is None:
+            _lib.check(lib.s2d_bn_train_bwd(x.data_ptr(), x.stride(0), n, C, dz.data_ptr(), dz.stride(0),
+                                            stats[0].data_ptr(), stats[1].data_ptr(), _ptr(gamma), dx.data_ptr(),
+                                            dx.stride(0), dgamma.data_ptr(), dbeta.data_ptr(), ws.data_ptr(), nbytes,
+                                            _stream()), "s2d_bn_train_bwd")
+        else:
+            off = lib.s2d_rows_workspace_sums_offset(C)
+            local = ws[off:off + 16 * C].view(torch.float64)
+            _lib.check(lib.s2d_bn_train_bwd_params(local.data_ptr(), C, stats[0].data_ptr(), stats[1].data_ptr(),
+                                                   dgamma.data_ptr(), dbeta.data_ptr(), _stream()), "s2d_bn_train_bwd_params")
+            glob = _all_reduce_sums(ws, C, n, ctx.group)
+            _lib.check(lib.s2d_bn_train_bwd_dx(x.data_ptr(), x.stride(0), n, C, dz.data_ptr(), dz.stride(0),
+                                               stats[0].data_ptr(), stats[1].data_ptr(), _ptr(gamma), glob.data_ptr(),
+                                               glob[2 * C:].data_ptr(), dx.data_ptr(), dx.stride(0), ws.data_ptr(), nbytes,
+                                               _stream()), "s2d_bn_train_bwd_dx")
         return dx, (dgamma if gamma is not None else None), (dbeta if beta is not None else None), dres, None, None, None
 
 
@@ -234,8 +269,13 @@ def norm_act(x, norm, bias=None, act=ACT_NONE, residual=None, res_after_act=Fals
         norm.num_batches_tracked += 1
     if pre_bias is not None and pre_bias.requires_grad:
         x = _ZeroGradBias.apply(x, pre_bias)
+    group = None
+    if isinstance(norm, torch.nn.SyncBatchNorm):                  # nn.SyncBatchNorm.convert_sync_batchnorm(model)
+        import torch.distributed as dist
+        if dist.is_available() and dist.is_initialized() and dist.get_world_size(norm.process_group) > 1:
+            group = True if norm.process_group is None else norm.process_group
     y = RowsNormAct.apply(x, norm.weight, norm.bias, residual,
-                          (norm.running_mean, norm.running_var, momentum, norm.eps), act, res_after_act)
+                          (norm.running_mean, norm.running_var, momentum, norm.eps, group), act, res_after_act)
     if pre_bias is not None:
         with torch.no_grad():
             norm.running_mean.add_(pre_bias.detach(), alpha=momentum)

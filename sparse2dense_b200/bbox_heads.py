@@ -134,7 +134,7 @@ class CenterHead(nn.Module):
                     while j < len(mods):
                         m = mods[j]
                         if isinstance(m, nn.Conv2d):
-                            bn = mods[j + 1] if j + 1 < len(mods) and isinstance(mods[j + 1], nn.BatchNorm2d) else None
+                            bn = mods[j + 1] if j + 1 < len(mods) and isinstance(mods[j + 1], nn.modules.batchnorm._BatchNorm) else None
                             k = j + 1 + int(bn is not None)
                             relu = k < len(mods) and isinstance(mods[k], nn.ReLU)
                             y, _, _ = D.conv(f"tasks.{ti}.{h}.{j}", y, B, H, W, m, bn, ACT_RELU if relu else ACT_NONE)

@@ -306,13 +306,14 @@ __global__ void __launch_bounds__(kColThreads) bn_stats_partial_kernel(const flo
   });
 }
 
-__global__ void bn_finalize_kernel(const double* __restrict__ sums, int n, int C, float eps, float momentum,
+__global__ void bn_finalize_kernel(const double* __restrict__ sums, double n, const double* __restrict__ n_dev, int C, float eps, float momentum,
                                    const float* __restrict__ gamma, const float* __restrict__ beta,
                                    float* __restrict__ running_mean, float* __restrict__ running_var,
                                    float* __restrict__ mean, float* __restrict__ invstd, float* __restrict__ scale,
                                    float* __restrict__ shift) {
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
   if (c >= C) return;
+  if (n_dev) n = *n_dev;
   const double m = sums[c] / n;
   double var = sums[C + c] / n - m * m;
   if (var < 0.0) var = 0.0;
@@ -324,7 +325,7 @@ __global__ void bn_finalize_kernel(const double* __restrict__ sums, int n, int C
   shift[c] = b - (float)m * g * is;
   if (running_mean) running_mean[c] = (1.f - momentum) * running_mean[c] + momentum * (float)m;
   if (running_var) {
-    const double unbiased = n > 1 ? var * ((double)n / (double)(n - 1)) : var;
+    const double unbiased = n > 1.0 ? var * (n / (n - 1.0)) : var;
     running_var[c] = (1.f - momentum) * running_var[c] + momentum * (float)unbiased;
   }
 }
@@ -367,16 +368,18 @@ __global__ void __launch_bounds__(kColThreads) rows_affine_act_bwd_kernel(
 }
 
 // dx = gamma*invstd * (dz - mean(dz) - xhat * mean(dz*xhat)); also dgamma / dbeta
-__global__ void bn_bwd_coeff_kernel(const double* __restrict__ sums, int n, int C, const float* __restrict__ mean,
+__global__ void bn_bwd_coeff_kernel(const double* __restrict__ sums, double n, const double* __restrict__ n_dev, int C, const float* __restrict__ mean,
                                     const float* __restrict__ invstd, const float* __restrict__ gamma,
                                     float* __restrict__ dgamma, float* __restrict__ dbeta, float* __restrict__ coef) {
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
   if (c >= C) return;
+  if (n_dev) n = *n_dev;
   const double sdz = sums[c], sdzx = sums[C + c];
   const double m = mean[c], is = invstd[c];
   const double dg = is * (sdzx - m * sdz);               // sum dz * xhat
   if (dgamma) dgamma[c] = (float)dg;
   if (dbeta) dbeta[c] = (float)sdz;
+  if (!coef) return;
   const double g = gamma ? (double)gamma[c] : 1.0;
   // dx = a*dz + b*x + d  with  a = g*is,  b = -g*is*is*dg/n,  d = -g*is*(sdz/n) + g*is*is*m*dg/n
   coef[c] = (float)(g * is);
@@ -691,10 +694,40 @@ extern "C" int s2d_bn_train_stats(const float* x, int ld, int n, int C, float ep
   S2D_LAUNCH_CHECK();
   column_final_kernel<<<(2 * C + 255) / 256, 256, 0, st>>>(partial, kColBlocks, 2 * C, sums);
   S2D_LAUNCH_CHECK();
-  bn_finalize_kernel<<<(C + 255) / 256, 256, 0, st>>>(sums, n, C, eps, momentum, gamma, beta, running_mean, running_var, mean,
-                                                      invstd, scale, shift);
+  bn_finalize_kernel<<<(C + 255) / 256, 256, 0, st>>>(sums, (double)n, nullptr, C, eps, momentum, gamma, beta, running_mean,
+                                                      running_var, mean, invstd, scale, shift);
   S2D_LAUNCH_CHECK();
   count_launches(3);
+  return S2D_OK;
+}
+
+// ---- the same in two halves, for SyncBatchNorm: the caller all-reduces the column sums (2*C doubles at
+// s2d_rows_workspace_sums_offset(C) inside the workspace) and the row counts between the two calls ----------------------
+extern "C" size_t s2d_rows_workspace_sums_offset(int C) { return C < 1 ? 0 : (size_t)kColBlocks * 2 * C * sizeof(double); }
+
+extern "C" int s2d_bn_train_sums(const float* x, int ld, int n, int C, void* ws, size_t ws_bytes, void* stream) {
+  S2D_REQUIRE(ws && (n == 0 || x), "s2d_bn_train_sums: null pointer");
+  S2D_REQUIRE(n >= 0 && C >= 1 && ld >= C, "s2d_bn_train_sums: bad sizes (n %d, C %d, ld %d)", n, C, ld);
+  S2D_REQUIRE(ws_bytes >= s2d_rows_workspace_bytes(C), "s2d_bn_train_sums: workspace too small");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  double* partial = static_cast<double*>(ws);
+  double* sums = partial + (size_t)kColBlocks * 2 * C;
+  bn_stats_partial_kernel<<<kColBlocks, kColThreads, 0, st>>>(x, ld, n, C, partial);
+  S2D_LAUNCH_CHECK();
+  column_final_kernel<<<(2 * C + 255) / 256, 256, 0, st>>>(partial, kColBlocks, 2 * C, sums);
+  S2D_LAUNCH_CHECK();
+  count_launches(2);
+  return S2D_OK;
+}
+
+extern "C" int s2d_bn_train_finalize(const double* sums2c, const double* n_total_dev, int C, float eps, float momentum,
+                                     const float* gamma, const float* beta, float* running_mean, float* running_var,
+                                     float* mean, float* invstd, float* scale, float* shift, void* stream) {
+  S2D_REQUIRE(sums2c && n_total_dev && mean && invstd && scale && shift && C >= 1, "s2d_bn_train_finalize: bad argument");
+  bn_finalize_kernel<<<(C + 255) / 256, 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      sums2c, 1.0, n_total_dev, C, eps, momentum, gamma, beta, running_mean, running_var, mean, invstd, scale, shift);
+  S2D_LAUNCH_CHECK();
+  count_launches(1);
   return S2D_OK;
 }
 
@@ -746,11 +779,45 @@ extern "C" int s2d_bn_train_bwd(const float* x, int ld, int n, int C, const floa
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   double* sums = static_cast<double*>(ws) + (size_t)kColBlocks * 2 * C;
   float* coef = reinterpret_cast<float*>(sums + 2 * (size_t)C);
-  bn_bwd_coeff_kernel<<<(C + 255) / 256, 256, 0, st>>>(sums, n, C, mean, invstd, gamma, dgamma, dbeta, coef);
+  bn_bwd_coeff_kernel<<<(C + 255) / 256, 256, 0, st>>>(sums, (double)n, nullptr, C, mean, invstd, gamma, dgamma, dbeta, coef);
   S2D_LAUNCH_CHECK();
   bn_bwd_apply_kernel<<<grid_for((long long)n * C, 256, 148 * 16), 256, 0, st>>>(x, ld, n, C, dz, dz_ld, coef, dx, dx_ld);
   S2D_LAUNCH_CHECK();
   count_launches(2);
+  return S2D_OK;
+}
+
+// SyncBatchNorm backward in two halves around the all-reduce of the column sums in the workspace: the affine gradients
+// come from the LOCAL sums (data-parallel gradient averaging treats them like any other parameter gradient), dx from the
+// GLOBAL sums and row count.
+extern "C" int s2d_bn_train_bwd_params(const double* sums2c_local, int C, const float* mean, const float* invstd,
+                                       float* dgamma, float* dbeta, void* stream) {
+  S2D_REQUIRE(sums2c_local && mean && invstd && C >= 1, "s2d_bn_train_bwd_params: bad argument");
+  bn_bwd_coeff_kernel<<<(C + 255) / 256, 256, 0, static_cast<cudaStream_t>(stream)>>>(sums2c_local, 1.0, nullptr, C, mean,
+                                                                                     invstd, nullptr, dgamma, dbeta, nullptr);
+  S2D_LAUNCH_CHECK();
+  count_launches(1);
+  return S2D_OK;
+}
+
+extern "C" int s2d_bn_train_bwd_dx(const float* x, int ld, int n, int C, const float* dz, int dz_ld, const float* mean,
+                                   const float* invstd, const float* gamma, const double* sums2c_global,
+                                   const double* n_total_dev, float* dx, int dx_ld, void* ws, size_t ws_bytes, void* stream) {
+  S2D_REQUIRE(ws && mean && invstd && sums2c_global && n_total_dev && (n == 0 || (x && dz && dx)),
+              "s2d_bn_train_bwd_dx: null pointer");
+  S2D_REQUIRE(n >= 0 && C >= 1 && ld >= C && dz_ld >= C && dx_ld >= C, "s2d_bn_train_bwd_dx: bad sizes");
+  S2D_REQUIRE(ws_bytes >= s2d_rows_workspace_bytes(C), "s2d_bn_train_bwd_dx: workspace too small");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  float* coef = reinterpret_cast<float*>(static_cast<double*>(ws) + (size_t)kColBlocks * 2 * C + 2 * (size_t)C);
+  bn_bwd_coeff_kernel<<<(C + 255) / 256, 256, 0, st>>>(sums2c_global, 1.0, n_total_dev, C, mean, invstd, gamma, nullptr, nullptr,
+                                                      coef);
+  S2D_LAUNCH_CHECK();
+  count_launches(1);
+  if (n > 0) {
+    bn_bwd_apply_kernel<<<grid_for((long long)n * C, 256, 148 * 16), 256, 0, st>>>(x, ld, n, C, dz, dz_ld, coef, dx, dx_ld);
+    S2D_LAUNCH_CHECK();
+    count_launches(1);
+  }
   return S2D_OK;
 }
 

@@ -75,3 +75,73 @@ class Voxelization(object):
             self._voxels(self.voxel_generator_2, reconstruction_points, device, "reconstruction_", "_2", ex, max_voxels)
             self._voxels(self.voxel_generator_4, reconstruction_points, device, "reconstruction_", "_4", ex, max_voxels)
         return ex
+
+
+class AssignLabel(object):
+    """``AssignLabel`` pipeline step (det3d/datasets/pipelines/preprocess.py:479-653) for a whole batch on the device:
+    same constructor contract (``cfg`` with out_size_factor / target_assigner.tasks / gaussian_overlap / max_objs /
+    min_radius); ``__call__`` takes the per-scene annotations and returns the training keys of the example dict
+    (``hm``, ``anno_box``, ``ind``, ``mask``, ``cat``: lists with one ``[B, ...]`` device tensor per task, and
+    ``gt_boxes_and_cls``).  The host only regroups the (<= 500) objects of a scene class-major per task as the reference
+    does (:505-537) and uploads 18 KB per scene; heat maps, indices and regression targets are one kernel launch per task
+    (``s2d_assign_label``)."""
+
+    def __init__(self, **kwargs):
+        cfg = kwargs["cfg"]
+        self.out_size_factor = _cfg(cfg, "out_size_factor")
+        tasks = _cfg(_cfg(cfg, "target_assigner"), "tasks")
+        self.num_classes = [int(_cfg(t, "num_class")) for t in tasks]
+        self.gaussian_overlap = _cfg(cfg, "gaussian_overlap")
+        self._max_objs = int(_cfg(cfg, "max_objs"))
+        self._min_radius = int(_cfg(cfg, "min_radius"))
+
+    def __call__(self, gt_boxes, gt_classes, grid_size, pc_range, voxel_size, device="cuda"):
+        """gt_boxes: list (per scene) of ``[n,9]`` float32 (x,y,z,w,l,h,vx,vy,rot); gt_classes: list of ``[n]`` ints,
+        1-based over all tasks; grid_size (x, y[, z]), pc_range, voxel_size as ``res["lidar"]["voxels"]`` holds them."""
+        import ctypes
+        from . import _lib
+        B, M = len(gt_boxes), self._max_objs
+        W, H = int(grid_size[0]) // self.out_size_factor, int(grid_size[1]) // self.out_size_factor
+        lib = _lib.load()
+        out = dict(hm=[], anno_box=[], ind=[], mask=[], cat=[])
+        flag, per_task_bc = 0, []
+        for ncls in self.num_classes:
+            boxes = np.zeros((B, M, 9), np.float32)
+            classes = np.zeros((B, M), np.int32)
+            counts = np.zeros((B,), np.int32)
+            for b in range(B):
+                gb, gc = np.asarray(gt_boxes[b], np.float32).reshape(-1, 9), np.asarray(gt_classes[b]).reshape(-1)
+                order = np.concatenate([np.where(gc == c + 1 + flag)[0] for c in range(ncls)]) if gc.size else np.zeros(0, int)
+                n = min(order.size, M)
+                assert order.size <= M, "more objects than max_objs"
+                boxes[b, :n], classes[b, :n], counts[b] = gb[order[:n]], gc[order[:n]] - flag, n
+            t = lambda a: torch.from_numpy(a).to(device)
+            d_boxes, d_cls, d_cnt = t(boxes), t(classes), t(counts)
+            hm = torch.empty((B, ncls, H, W), dtype=torch.float32, device=device)
+            anno = torch.empty((B, M, 10), dtype=torch.float32, device=device)
+            ind = torch.empty((B, M), dtype=torch.int64, device=device)
+            mask = torch.empty((B, M), dtype=torch.uint8, device=device)
+            cat = torch.empty((B, M), dtype=torch.int64, device=device)
+            bc = torch.empty((B, M, 10), dtype=torch.float32, device=device)
+            _lib.check(lib.s2d_assign_label(d_boxes.data_ptr(), d_cls.data_ptr(), d_cnt.data_ptr(), B, M, ncls, H, W,
+                                            float(pc_range[0]), float(pc_range[1]), float(voxel_size[0]), float(voxel_size[1]),
+                                            int(self.out_size_factor), float(self.gaussian_overlap), self._min_radius, flag,
+                                            hm.data_ptr(), anno.data_ptr(), ind.data_ptr(), mask.data_ptr(), cat.data_ptr(),
+                                            bc.data_ptr(), torch.cuda.current_stream().cuda_stream), "s2d_assign_label")
+            for key, v in zip(("hm", "anno_box", "ind", "mask", "cat"), (hm, anno, ind, mask, cat)):
+                out[key].append(v)
+            per_task_bc.append((bc, counts))
+            flag += ncls
+        if len(per_task_bc) == 1:
+            out["gt_boxes_and_cls"] = per_task_bc[0][0]
+        else:                                   # flatten(gt_boxes) over tasks (preprocess.py:625-640): task-major rows
+            bc = torch.zeros((B, M, 10), dtype=torch.float32, device=device)
+            for b in range(B):
+                off = 0
+                for t_bc, counts in per_task_bc:
+                    n = int(counts[b])
+                    assert off + n <= M
+                    bc[b, off:off + n] = t_bc[b, :n]
+                    off += n
+            out["gt_boxes_and_cls"] = bc
+        return out

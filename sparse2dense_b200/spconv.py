@@ -225,12 +225,12 @@ class SparseConv3d(SparseConvolution):
 
 
 def _is_eval_bn(m):
-    return isinstance(m, nn.BatchNorm1d) and not m.training and m.track_running_stats
+    return isinstance(m, (nn.BatchNorm1d, nn.SyncBatchNorm)) and not m.training and m.track_running_stats
 
 
 def _is_fusable_bn(m):
     """eval-mode BN folds into the conv epilogue; training-mode BN runs the batch-statistics kernels of train.cu."""
-    return isinstance(m, nn.BatchNorm1d) and m.track_running_stats
+    return isinstance(m, (nn.BatchNorm1d, nn.SyncBatchNorm)) and m.track_running_stats
 
 
 class SparseSequential(SparseModule):

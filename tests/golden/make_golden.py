@@ -541,6 +541,74 @@ def make_loss_goldens():
     np.savez_compressed(os.path.join(HERE, "losses.npz"), **save)
 
 
+def random_gt(seed, n=80, num_cls=3):
+    """Synthetic Waymo-like annotations: boxes f32 [n,9] (x,y,z,w,l,h,vx,vy,rot) incl. out-of-range centres, degenerate
+    sizes and angles far outside [-pi, pi]; classes 1..num_cls in random order."""
+    rng = np.random.default_rng(seed)
+    xy = rng.uniform(-80, 80, (n, 2))
+    z = rng.uniform(-1, 3, (n, 1))
+    cls = rng.integers(1, num_cls + 1, n)
+    base = np.array([[2.0, 4.6, 1.7], [0.8, 0.9, 1.7], [0.8, 1.8, 1.6]])[cls - 1]
+    wlh = base * rng.uniform(0.6, 1.8, (n, 3))
+    wlh[rng.integers(0, n, 2), 0] = 0.0                       # degenerate boxes are skipped (preprocess.py:585)
+    vel = rng.normal(0, 3, (n, 2))
+    rot = rng.uniform(-7, 7, (n, 1))
+    return np.concatenate([xy, z, wlh, vel, rot], 1).astype(np.float32), cls.astype(np.int64)
+
+
+def make_assign_goldens():
+    """The reference's own AssignLabel.__call__ (det3d/datasets/pipelines/preprocess.py:479-653) executed from its source
+    text with the real center_utils / limit_period, on synthetic annotations; also checks oracle/assign_label.py."""
+    import ast
+    import types
+    from oracle import assign_label as OA
+
+    def pkg(name, path):
+        m = types.ModuleType(name); m.__path__ = [path]; sys.modules[name] = m; return m
+    for n in [k for k in sys.modules if k == "det3d" or k.startswith("det3d.")]:
+        sys.modules.pop(n)
+    pkg("det3d", REF + "/det3d"); pkg("det3d.core", REF + "/det3d/core"); pkg("det3d.core.utils", REF + "/det3d/core/utils")
+    import det3d.core.utils.center_utils as cu                  # real file: numba circle_nms + cv2 are importable here
+    src = open(REF + "/det3d/datasets/pipelines/preprocess.py").read()
+    tree = ast.parse(src)
+    want = {"flatten", "merge_multi_group_label", "AssignLabel"}
+    code = "\n\n".join(ast.get_source_segment(src, n) for n in tree.body
+                       if isinstance(n, (ast.FunctionDef, ast.ClassDef)) and n.name in want)
+    ns = dict(np=np, draw_umich_gaussian=cu.draw_umich_gaussian, gaussian_radius=cu.gaussian_radius,
+              box_np_ops=types.SimpleNamespace(limit_period=lambda val, offset=0.5, period=np.pi:
+                                               val - np.floor(val / period + offset) * period),      # box_np_ops.py:360-361
+              PIPELINES=types.SimpleNamespace(register_module=lambda c: c))
+    exec(compile(code, "preprocess.py[AssignLabel]", "exec"), ns)
+    tasks = [types.SimpleNamespace(num_class=3, class_names=["VEHICLE", "PEDESTRIAN", "CYCLIST"])]
+    cfg = types.SimpleNamespace(out_size_factor=8, target_assigner=types.SimpleNamespace(tasks=tasks), gaussian_overlap=0.1,
+                                max_objs=500, min_radius=2)
+    assigner = ns["AssignLabel"](cfg=cfg)
+    names = np.array(["VEHICLE", "PEDESTRIAN", "CYCLIST"])
+    save = {}
+    for seed, n in ((50, 80), (51, 200), (52, 0), (53, 499)):
+        boxes, cls = random_gt(seed, n) if n else (np.zeros((0, 9), np.float32), np.zeros((0,), np.int64))
+        res = dict(mode="train", type="WaymoDataset",
+                   lidar=dict(voxels=dict(shape=np.array([1504, 1504, 40]), range=np.array(synth.WAYMO_RANGE, np.float32),
+                                          size=np.array(synth.WAYMO_VOXEL, np.float32)),
+                              annotations=dict(gt_boxes=boxes.copy(), gt_classes=cls.copy(), gt_names=names[cls - 1])))
+        out, _ = assigner(res, {})
+        t = out["lidar"]["targets"]
+        mine = OA.assign_label(boxes, cls, [3], (1504, 1504), synth.WAYMO_RANGE, synth.WAYMO_VOXEL, 8, 0.1, 500, 2)
+        for k in ("hm", "anno_box", "ind", "mask", "cat"):
+            ref = np.asarray(t[k][0])
+            got = mine[k][0]
+            if k == "anno_box":
+                assert np.allclose(got, ref, rtol=0, atol=2e-7 * max(1.0, np.abs(ref).max())), (seed, k)
+            else:
+                assert np.array_equal(got, ref), (seed, k, np.abs(got.astype(np.float64) - ref).max())
+            save[f"{seed}_{k}"] = ref
+        assert np.array_equal(mine["gt_boxes_and_cls"], t["gt_boxes_and_cls"])
+        save[f"{seed}_gt_boxes_and_cls"] = t["gt_boxes_and_cls"]
+        save[f"{seed}_boxes"], save[f"{seed}_classes"] = boxes, cls
+        print(f"assign seed {seed}: {int(t['mask'][0].sum())} objects drawn, hm max {t['hm'][0].max():.3f}, oracle identical")
+    np.savez_compressed(os.path.join(HERE, "assign_label.npz"), **save)
+
+
 def make_optim_goldens():
     """The reference's own OptimWrapper (det3d/solver/fastai_optim.py:118-174, true_wd / bn_wd as build_one_cycle_optimizer
     sets them, apis/train.py:168-186) over torch Adam, driven by the reference's OneCycle
@@ -589,6 +657,9 @@ def make_optim_goldens():
 
 
 if __name__ == "__main__":
+    if len(sys.argv) > 1 and sys.argv[1] == "assign":
+        make_assign_goldens()
+        sys.exit(0)
     if len(sys.argv) > 1 and sys.argv[1] == "optim":
         make_optim_goldens()
         sys.exit(0)
@@ -615,3 +686,4 @@ if __name__ == "__main__":
     make_pillar_goldens()
     make_loss_goldens()
     make_optim_goldens()
+    make_assign_goldens()

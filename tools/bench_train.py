@@ -22,6 +22,7 @@ def main():
     ap.add_argument("--precision", default="auto")
     ap.add_argument("--no-pcr", action="store_true")
     ap.add_argument("--small", action="store_true")
+    ap.add_argument("--sync-bn", action="store_true", help="nn.SyncBatchNorm.convert_sync_batchnorm (tools/train.py:92-96)")
     ap.add_argument("--profile", action="store_true", help="print the per-kernel device time of one step (torch.profiler)")
     a = ap.parse_args()
     world, rank = int(os.environ.get("WORLD_SIZE", "1")), int(os.environ.get("RANK", "0"))
@@ -31,6 +32,8 @@ def main():
         dist.init_process_group("nccl")
     teacher, student = synth.build_distill_models("cuda", ops.PRECISION_NAMES[a.precision])
     student.neck.train_pcr = not a.no_pcr
+    if a.sync_bn:
+        student = torch.nn.SyncBatchNorm.convert_sync_batchnorm(student)
     tr = DistillTrainer(teacher, student, total_steps=1000)
     ex = synth.distill_example(a.batch, cfg=1 + rank, small=a.small)
     print("voxels student/dense/recon:", ex["voxels"].shape[0], ex["dense_voxels"].shape[0], ex["reconstruction_voxels"].shape[0])
