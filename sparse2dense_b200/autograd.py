@@ -59,17 +59,59 @@ def conv_wgrad(g, d, tbl, n_rows, d_rows=None):
 _MAX_K = 27          # taps per s2d_conv_fwd launch (kMaxK of the library)
 
 
+def _pad_channels(c, is_input):
+    """Smallest channel count >= c the tcgen05 kernel takes (Cin: 16 or a multiple of 32; Cout: a multiple of 16)."""
+    if is_input:
+        return 16 if c <= 16 else -(-c // 32) * 32
+    return -(-c // 16) * 16
+
+
+def conv_rows_tc(x, w, tbl, n_out, precision, out_rows=None, n_total=None):
+    """conv_rows that keeps small-channel layers (the 3-channel generators of the PCR branch, the 1..3-channel head
+    convolutions and their data gradients) on the tensor-core kernel by zero-padding the channel counts, when there is
+    enough work per row to pay for the padded traffic; otherwise the exact-shape kernel.  With ``out_rows`` the result
+    is scattered into a fresh ``[n_total, Cout(_padded)]`` buffer.  Returns a 2-D tensor whose first Cout columns hold
+    the result (possibly a strided view of the padded buffer)."""
+    K, cin, cout = w.shape
+    tc = precision != ops.PRECISION_FP32
+    if tc and not ops.tf32_supported(cin, cout) and K * cin >= 64:
+        cin_p, cout_p = _pad_channels(cin, True), _pad_channels(cout, False)
+        if ops.tf32_supported(cin_p, cout_p) and cin_p <= 8 * cin and cout_p <= 16 * cout:
+            if cin_p != cin:
+                xp = torch.zeros((x.shape[0], cin_p), dtype=torch.float32, device=x.device)
+                xp[:, :cin] = x
+                x = xp
+            wp = torch.zeros((K, cin_p, cout_p), dtype=torch.float32, device=w.device)
+            wp[:, :cin, :cout] = w
+            w = wp
+    cout_eff = w.shape[2]
+    out = None
+    if out_rows is not None:
+        out = torch.empty((n_total, cout_eff), dtype=torch.float32, device=x.device)
+    y = conv_rows(x, w.contiguous(), tbl, n_out, out=out, out_rows=out_rows, precision=precision)
+    return y if cout_eff == cout else y[:, :cout]
+
+
 def conv_rows_any_k(x, w, tbl, n_out, precision):
     """conv_rows for any number of taps: more than 27 (the 4x4x4 adjoint of ConvTranspose3d) run as successive launches
     that accumulate through the residual input."""
     K = tbl.shape[0]
     if K <= _MAX_K:
-        return conv_rows(x, w, tbl, n_out, precision=precision)
+        return conv_rows_tc(x, w, tbl, n_out, precision)
+    cin, cout = w.shape[1], w.shape[2]
+    if precision != ops.PRECISION_FP32 and not ops.tf32_supported(cin, cout):
+        cin_p, cout_p = _pad_channels(cin, True), _pad_channels(cout, False)
+        if ops.tf32_supported(cin_p, cout_p) and cin_p <= 8 * cin and cout_p <= 16 * cout:     # pad once for all chunks
+            xp = torch.zeros((x.shape[0], cin_p), dtype=torch.float32, device=x.device)
+            xp[:, :cin] = x
+            wp = torch.zeros((K, cin_p, cout_p), dtype=torch.float32, device=w.device)
+            wp[:, :cin, :cout] = w
+            x, w = xp, wp
     out = None
     for k0 in range(0, K, _MAX_K):
         k1 = min(K, k0 + _MAX_K)
         out = conv_rows(x, w[k0:k1].contiguous(), tbl[k0:k1], n_out, residual=out, precision=precision)
-    return out
+    return out if out.shape[1] == cout else out[:, :cout]
 
 
 class GatherConv(torch.autograd.Function):
@@ -81,7 +123,7 @@ class GatherConv(torch.autograd.Function):
         w = w.contiguous()
         ctx.save_for_backward(x, w)
         ctx.table, ctx.precision = table, precision
-        return conv_rows(x, w, table.tbl, table.n_out, precision=precision)
+        return conv_rows_tc(x, w, table.tbl, table.n_out, precision)
 
     @staticmethod
     def backward(ctx, dy):
@@ -93,9 +135,9 @@ class GatherConv(torch.autograd.Function):
             wt = w.transpose(1, 2).contiguous()                       # [K, Cout, Cin]
             if t.symmetric:
                 wt = torch.flip(wt, dims=[0])
-                dx = conv_rows(dy, wt, t.tbl, t.n_in, precision=ctx.precision)
+                dx = conv_rows_tc(dy, wt, t.tbl, t.n_in, ctx.precision)
             else:
-                dx = conv_rows(dy, wt, t.transposed(), t.n_in, precision=ctx.precision)
+                dx = conv_rows_tc(dy, wt, t.transposed(), t.n_in, ctx.precision)
         if ctx.needs_input_grad[1]:
             dw = conv_wgrad(x, dy, t.tbl, t.n_out)
         return dx, dw, None, None
@@ -113,13 +155,21 @@ class TransposedConv(torch.autograd.Function):
         x = x if x.stride(1) == 1 else x.contiguous()
         cin, cout = w_t.shape[:2]
         n_fine = adj_table.n_in
-        out = torch.empty((n_fine, cout), dtype=torch.float32, device=x.device)
+        K0 = len(classes[0][0])
+        pad = (precision != ops.PRECISION_FP32 and not ops.tf32_supported(cin, cout) and K0 * cin >= 64 and
+               ops.tf32_supported(cin, _pad_channels(cout, False)))
+        cout_p = _pad_channels(cout, False) if pad else cout       # small Cout (generator_2: 16 -> 3): padded, tensor cores
+        out = torch.empty((n_fine, cout_p), dtype=torch.float32, device=x.device)
         for taps, tbl, rows in classes:
-            kio = torch.stack([w_t[(slice(None), slice(None)) + tuple(t)] for t in taps], 0).contiguous()
-            conv_rows(x, kio, tbl, x.shape[0], out=out, out_rows=rows, precision=precision)
+            kio = torch.stack([w_t[(slice(None), slice(None)) + tuple(t)] for t in taps], 0)
+            if cout_p != cout:
+                kp = torch.zeros((kio.shape[0], cin, cout_p), dtype=torch.float32, device=x.device)
+                kp[:, :, :cout] = kio
+                kio = kp
+            conv_rows(x, kio.contiguous(), tbl, x.shape[0], out=out, out_rows=rows, precision=precision)
         ctx.save_for_backward(x, w_t)
         ctx.adj, ctx.precision = adj_table, precision
-        return out
+        return out if cout_p == cout else out[:, :cout]
 
     @staticmethod
     def backward(ctx, dy):
