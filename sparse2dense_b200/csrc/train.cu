@@ -13,6 +13,8 @@
 // and the depthwise 7x7 convolution of the ConvNeXt blocks (rpn.py:204-222) get their backward here too, and the
 // optimizer is one fused launch over a flat parameter buffer (fastai-style true weight decay + Adam,
 // det3d/solver/fastai_optim.py:158-174).
+#include <initializer_list>
+
 #include "common.cuh"
 
 namespace s2d {
@@ -147,7 +149,7 @@ __global__ void __launch_bounds__(256) conv_wgrad_small_kernel(const float* __re
                                                                const float* __restrict__ D, int d_ld,
                                                                const int* __restrict__ d_rows, int Cd,
                                                                const int* __restrict__ tbl, int tbl_stride, int n_rows,
-                                                               int rows_per_chunk, float* __restrict__ partial) {
+                                                               int rows_per_chunk, int d_vec4, float* __restrict__ partial) {
   const int k = blockIdx.y;
   float acc[CG][CD];
 #pragma unroll
@@ -163,8 +165,16 @@ __global__ void __launch_bounds__(256) conv_wgrad_small_kernel(const float* __re
     float g[CG], d[CD];
 #pragma unroll
     for (int a = 0; a < CG; ++a) g[a] = a < Cg ? __ldg(G + (size_t)j * g_ld + a) : 0.f;
+    if (CD % 4 == 0 && d_vec4) {                      // Cd % 4 == 0, 16-byte aligned rows
 #pragma unroll
-    for (int b = 0; b < CD; ++b) d[b] = b < Cd ? __ldg(D + (size_t)di * d_ld + b) : 0.f;
+      for (int b = 0; b < CD; b += 4) {
+        const float4 v = b < Cd ? __ldg(reinterpret_cast<const float4*>(D + (size_t)di * d_ld + b)) : make_float4(0.f, 0.f, 0.f, 0.f);
+        d[b] = v.x; d[b + 1] = v.y; d[b + 2] = v.z; d[b + 3] = v.w;
+      }
+    } else {
+#pragma unroll
+      for (int b = 0; b < CD; ++b) d[b] = b < Cd ? __ldg(D + (size_t)di * d_ld + b) : 0.f;
+    }
 #pragma unroll
     for (int a = 0; a < CG; ++a)
 #pragma unroll
@@ -222,7 +232,7 @@ static int wgrad_chunks(int n_rows, int K, int Cg, int Cd) {
 // --------------------------------------------------------------------------------------------------------------------
 // column reductions over rows: per-block partial sums in double, fixed-order final pass
 // --------------------------------------------------------------------------------------------------------------------
-constexpr int kColBlocks = 296;   // 2 per SM
+constexpr int kColBlocks = 1184;  // 8 per SM: enough loads in flight to approach the HBM rate on the 0.5 GB PCR tensors
 constexpr int kColThreads = 256;
 
 __device__ __forceinline__ float act_fwd(float z, int act) {
@@ -288,13 +298,15 @@ __device__ __forceinline__ void column_partial(int n, int C, double* __restrict_
   }
 }
 
-// sums[v][c] = sum over blocks
+// sums[v][c] = sum over blocks: one warp per output, lane l adds blocks l, l+32, ... in order, then a fixed shuffle tree
+// (deterministic for a given block count)
 __global__ void column_final_kernel(const double* __restrict__ partial, int nblocks, int nv_c, double* __restrict__ sums) {
-  const int e = blockIdx.x * blockDim.x + threadIdx.x;
+  const int e = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
   if (e >= nv_c) return;
   double s = 0.0;
-  for (int b = 0; b < nblocks; ++b) s += partial[(size_t)b * nv_c + e];
-  sums[e] = s;
+  for (int b = lane; b < nblocks; b += 32) s += partial[(size_t)b * nv_c + e];
+  for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  if (lane == 0) sums[e] = s;
 }
 
 __global__ void __launch_bounds__(kColThreads) bn_stats_partial_kernel(const float* __restrict__ x, int ld, int n, int C,
@@ -349,6 +361,35 @@ __global__ void rows_affine_act_kernel(const float* __restrict__ x, int ld, long
   }
 }
 
+// the same, four channels per thread (C, the row strides and the base addresses multiples of 4 floats)
+__global__ void rows_affine_act_vec4_kernel(const float* __restrict__ x, int ld, long long n, int C,
+                                            const float* __restrict__ scale, const float* __restrict__ shift,
+                                            const float* __restrict__ residual, int res_ld, int act, int res_after_act,
+                                            float* __restrict__ out, int out_ld) {
+  const int c4n = C >> 2;
+  const long long total = n * c4n;
+  for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
+    const long long r = e / c4n;
+    const int c = (int)(e - r * c4n) << 2;
+    const float4 xv = *reinterpret_cast<const float4*>(x + (size_t)r * ld + c);
+    const float4 sc = scale ? __ldg(reinterpret_cast<const float4*>(scale + c)) : make_float4(1.f, 1.f, 1.f, 1.f);
+    const float4 sh = shift ? __ldg(reinterpret_cast<const float4*>(shift + c)) : make_float4(0.f, 0.f, 0.f, 0.f);
+    const float4 rv = residual ? *reinterpret_cast<const float4*>(residual + (size_t)r * res_ld + c)
+                               : make_float4(0.f, 0.f, 0.f, 0.f);
+    const float zx[4] = {xv.x, xv.y, xv.z, xv.w}, s4[4] = {sc.x, sc.y, sc.z, sc.w}, h4[4] = {sh.x, sh.y, sh.z, sh.w},
+                r4[4] = {rv.x, rv.y, rv.z, rv.w};
+    float y[4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      float z = zx[q];
+      if (scale) z *= s4[q];
+      if (shift) z += h4[q];
+      y[q] = res_after_act ? act_fwd(z, act) + r4[q] : act_fwd(z + r4[q], act);
+    }
+    *reinterpret_cast<float4*>(out + (size_t)r * out_ld + c) = make_float4(y[0], y[1], y[2], y[3]);
+  }
+}
+
 // dz = dy * act'(pre-activation); partial sums of dz and dz * x per column
 __global__ void __launch_bounds__(kColThreads) rows_affine_act_bwd_kernel(
     const float* __restrict__ x, int ld, int n, int C, const float* __restrict__ scale, const float* __restrict__ shift,
@@ -396,6 +437,30 @@ __global__ void bn_bwd_apply_kernel(const float* __restrict__ x, int ld, long lo
     dx[(size_t)r * dx_ld + c] = fmaf(__ldg(coef + c), dz[(size_t)r * dz_ld + c],
                                      fmaf(__ldg(coef + C + c), x[(size_t)r * ld + c], __ldg(coef + 2 * C + c)));
   }
+}
+
+__global__ void bn_bwd_apply_vec4_kernel(const float* __restrict__ x, int ld, long long n, int C, const float* __restrict__ dz,
+                                         int dz_ld, const float* __restrict__ coef, float* __restrict__ dx, int dx_ld) {
+  const int c4n = C >> 2;
+  const long long total = n * c4n;
+  for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
+    const long long r = e / c4n;
+    const int c = (int)(e - r * c4n) << 2;
+    const float4 a = __ldg(reinterpret_cast<const float4*>(coef + c)), b = __ldg(reinterpret_cast<const float4*>(coef + C + c)),
+                 d = __ldg(reinterpret_cast<const float4*>(coef + 2 * C + c));
+    const float4 g = *reinterpret_cast<const float4*>(dz + (size_t)r * dz_ld + c);
+    const float4 xv = *reinterpret_cast<const float4*>(x + (size_t)r * ld + c);
+    *reinterpret_cast<float4*>(dx + (size_t)r * dx_ld + c) =
+        make_float4(fmaf(a.x, g.x, fmaf(b.x, xv.x, d.x)), fmaf(a.y, g.y, fmaf(b.y, xv.y, d.y)),
+                    fmaf(a.z, g.z, fmaf(b.z, xv.z, d.z)), fmaf(a.w, g.w, fmaf(b.w, xv.w, d.w)));
+  }
+}
+
+static bool vec4_ok(int C, std::initializer_list<int> lds, std::initializer_list<const void*> ptrs) {
+  if (C % 4) return false;
+  for (int l : lds) if (l % 4) return false;
+  for (const void* p : ptrs) if (p && (reinterpret_cast<uintptr_t>(p) & 15)) return false;
+  return true;
 }
 
 __global__ void sums_to_float_kernel(const double* __restrict__ sums, int C, float* __restrict__ out) {
@@ -647,10 +712,11 @@ extern "C" int s2d_conv_wgrad(const float* g, int g_ld, int n_g, int Cg, const f
   const int bucket = wgrad_small_bucket(Cg, Cd);
   if (bucket) {
     dim3 gs(chunks, K);
+    const int d_vec4 = (d_ld % 4 == 0) && (Cd % 4 == 0) && (reinterpret_cast<uintptr_t>(d) & 15) == 0;
 #define S2D_WGS(CG_, CD_)                                                                                              \
   if (bucket == CG_ * 100 + CD_)                                                                                        \
     conv_wgrad_small_kernel<CG_, CD_><<<gs, 256, 0, st>>>(g, g_ld, n_g, Cg, d, d_ld, d_rows, Cd, tbl, tbl_stride, n_rows, \
-                                                          rpc, partial);
+                                                          rpc, d_vec4, partial);
     S2D_WGS(4, 4) S2D_WGS(4, 16) S2D_WGS(8, 16) S2D_WGS(32, 4)
 #undef S2D_WGS
     S2D_LAUNCH_CHECK();
@@ -692,7 +758,7 @@ extern "C" int s2d_bn_train_stats(const float* x, int ld, int n, int C, float ep
   double* sums = partial + (size_t)kColBlocks * 2 * C;
   bn_stats_partial_kernel<<<kColBlocks, kColThreads, 0, st>>>(x, ld, n, C, partial);
   S2D_LAUNCH_CHECK();
-  column_final_kernel<<<(2 * C + 255) / 256, 256, 0, st>>>(partial, kColBlocks, 2 * C, sums);
+  column_final_kernel<<<(2 * C * 32 + 255) / 256, 256, 0, st>>>(partial, kColBlocks, 2 * C, sums);
   S2D_LAUNCH_CHECK();
   bn_finalize_kernel<<<(C + 255) / 256, 256, 0, st>>>(sums, (double)n, nullptr, C, eps, momentum, gamma, beta, running_mean,
                                                       running_var, mean, invstd, scale, shift);
@@ -714,7 +780,7 @@ extern "C" int s2d_bn_train_sums(const float* x, int ld, int n, int C, void* ws,
   double* sums = partial + (size_t)kColBlocks * 2 * C;
   bn_stats_partial_kernel<<<kColBlocks, kColThreads, 0, st>>>(x, ld, n, C, partial);
   S2D_LAUNCH_CHECK();
-  column_final_kernel<<<(2 * C + 255) / 256, 256, 0, st>>>(partial, kColBlocks, 2 * C, sums);
+  column_final_kernel<<<(2 * C * 32 + 255) / 256, 256, 0, st>>>(partial, kColBlocks, 2 * C, sums);
   S2D_LAUNCH_CHECK();
   count_launches(2);
   return S2D_OK;
@@ -738,8 +804,12 @@ extern "C" int s2d_rows_affine_act(const float* x, int ld, int n, int C, const f
   S2D_REQUIRE(act >= S2D_ACT_NONE && act <= S2D_ACT_GELU, "s2d_rows_affine_act: unknown activation %d", act);
   if (n == 0) return S2D_OK;
   S2D_REQUIRE(x && out, "s2d_rows_affine_act: null pointer");
-  rows_affine_act_kernel<<<grid_for((long long)n * C, 256, 148 * 16), 256, 0, static_cast<cudaStream_t>(stream)>>>(
-      x, ld, n, C, scale, shift, residual, res_ld, act, res_after_act, out, out_ld);
+  if (vec4_ok(C, {ld, out_ld, residual ? res_ld : 0}, {x, out, residual, scale, shift}))
+    rows_affine_act_vec4_kernel<<<grid_for((long long)n * (C / 4), 256, 148 * 16), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+        x, ld, n, C, scale, shift, residual, res_ld, act, res_after_act, out, out_ld);
+  else
+    rows_affine_act_kernel<<<grid_for((long long)n * C, 256, 148 * 16), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+        x, ld, n, C, scale, shift, residual, res_ld, act, res_after_act, out, out_ld);
   S2D_LAUNCH_CHECK();
   count_launches(1);
   return S2D_OK;
@@ -758,7 +828,7 @@ extern "C" int s2d_rows_affine_act_bwd(const float* x, int ld, int n, int C, con
   rows_affine_act_bwd_kernel<<<kColBlocks, kColThreads, 0, st>>>(x, ld, n, C, scale, shift, residual, res_ld, act,
                                                                 res_after_act, dy, dy_ld, dz, dz_ld, partial);
   S2D_LAUNCH_CHECK();
-  column_final_kernel<<<(2 * C + 255) / 256, 256, 0, st>>>(partial, kColBlocks, 2 * C, sums);
+  column_final_kernel<<<(2 * C * 32 + 255) / 256, 256, 0, st>>>(partial, kColBlocks, 2 * C, sums);
   S2D_LAUNCH_CHECK();
   count_launches(2);
   if (dshift) {                       // plain bias: d(bias) = column sums of dz
@@ -781,7 +851,11 @@ extern "C" int s2d_bn_train_bwd(const float* x, int ld, int n, int C, const floa
   float* coef = reinterpret_cast<float*>(sums + 2 * (size_t)C);
   bn_bwd_coeff_kernel<<<(C + 255) / 256, 256, 0, st>>>(sums, (double)n, nullptr, C, mean, invstd, gamma, dgamma, dbeta, coef);
   S2D_LAUNCH_CHECK();
-  bn_bwd_apply_kernel<<<grid_for((long long)n * C, 256, 148 * 16), 256, 0, st>>>(x, ld, n, C, dz, dz_ld, coef, dx, dx_ld);
+  if (vec4_ok(C, {ld, dz_ld, dx_ld}, {x, dz, dx, coef}))
+    bn_bwd_apply_vec4_kernel<<<grid_for((long long)n * (C / 4), 256, 148 * 16), 256, 0, st>>>(x, ld, n, C, dz, dz_ld, coef, dx,
+                                                                                           dx_ld);
+  else
+    bn_bwd_apply_kernel<<<grid_for((long long)n * C, 256, 148 * 16), 256, 0, st>>>(x, ld, n, C, dz, dz_ld, coef, dx, dx_ld);
   S2D_LAUNCH_CHECK();
   count_launches(2);
   return S2D_OK;
@@ -814,7 +888,11 @@ extern "C" int s2d_bn_train_bwd_dx(const float* x, int ld, int n, int C, const f
   S2D_LAUNCH_CHECK();
   count_launches(1);
   if (n > 0) {
-    bn_bwd_apply_kernel<<<grid_for((long long)n * C, 256, 148 * 16), 256, 0, st>>>(x, ld, n, C, dz, dz_ld, coef, dx, dx_ld);
+    if (vec4_ok(C, {ld, dz_ld, dx_ld}, {x, dz, dx, coef}))
+      bn_bwd_apply_vec4_kernel<<<grid_for((long long)n * (C / 4), 256, 148 * 16), 256, 0, st>>>(x, ld, n, C, dz, dz_ld, coef,
+                                                                                             dx, dx_ld);
+    else
+      bn_bwd_apply_kernel<<<grid_for((long long)n * C, 256, 148 * 16), 256, 0, st>>>(x, ld, n, C, dz, dz_ld, coef, dx, dx_ld);
     S2D_LAUNCH_CHECK();
     count_launches(1);
   }
