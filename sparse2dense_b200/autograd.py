@@ -314,7 +314,9 @@ def norm_act(x, norm, bias=None, act=ACT_NONE, residual=None, res_after_act=Fals
     assert isinstance(norm, torch.nn.modules.batchnorm._BatchNorm)
     if not norm.training:
         raise NotImplementedError("frozen (eval-mode) BatchNorm inside a training graph is not built")
-    momentum = 0.1 if norm.momentum is None else norm.momentum
+    if norm.momentum is None:
+        raise NotImplementedError("BatchNorm(momentum=None) (cumulative average) is not used by the reference configs")
+    momentum = norm.momentum
     if norm.num_batches_tracked is not None:
         norm.num_batches_tracked += 1
     if pre_bias is not None and pre_bias.requires_grad:

@@ -107,6 +107,22 @@ class FlatAdam:
         return self._norm                                        # device [2]: gradient norm before clipping, coefficient
 
 
+    # -- checkpoint / resume (the role of optimizer.state_dict() in det3d/torchie/trainer/checkpoint.py:199-240) -----------
+    def state_dict(self):
+        """Moments in the flat layout plus the per-parameter shapes they were taken with (so that a load into a model with a
+        different parameter order fails loudly)."""
+        return dict(exp_avg=self.exp_avg.detach().cpu(), exp_avg_sq=self.exp_avg_sq.detach().cpu(), steps=self.steps,
+                    shapes=[tuple(p.shape) for p in self.params], wd=self.wd, beta2=self.beta2, eps=self.eps)
+
+    def load_state_dict(self, state):
+        if [tuple(x) for x in state["shapes"]] != [tuple(p.shape) for p in self.params]:
+            raise ValueError("optimizer state was saved for a different parameter list")
+        self.exp_avg.copy_(state["exp_avg"])
+        self.exp_avg_sq.copy_(state["exp_avg_sq"])
+        self.steps = int(state["steps"])
+        self.wd, self.beta2, self.eps = state["wd"], state["beta2"], state["eps"]
+
+
 def distill_losses(student, r, T_preds, F_D_a, F_D_b, example, s2d_weights=(10.0, 20.0, 5.0, 20.0)):
     """The CenterPoint branch of batch_processor_inline (trainer.py:775-811) on rows.  ``r`` = KD_VoxelNet.student_rows()."""
     B, H, W, Hu, Wu = r["dims"]
@@ -172,3 +188,19 @@ class DistillTrainer:
         log["grad_norm"] = norm[0]
         log["lr"], log["mom"] = lr, mom
         return log
+
+    def state_dict(self):
+        """What the reference's ``save_checkpoint`` stores (model ``state_dict``, ``optimizer``, ``meta`` with the
+        iteration; trainer/checkpoint.py:199-240), for the student."""
+        return dict(state_dict=self.student.state_dict(), optimizer=self.opt.state_dict(),
+                    meta=dict(iter=self.global_step))
+
+    def load_state_dict(self, ckpt):
+        with torch.no_grad():                                # parameters stay views of the flat buffer: copy in place
+            own = self.student.state_dict()
+            for k, v in ckpt["state_dict"].items():
+                own[k].copy_(v)
+        torch.autograd.graph.increment_version(self.opt.params)
+        self.opt.load_state_dict(ckpt["optimizer"])
+        self.global_step = int(ckpt["meta"]["iter"])
+

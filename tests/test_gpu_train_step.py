@@ -193,3 +193,31 @@ def test_trainer_steps_reduce_the_loss_and_update_every_parameter():
     with torch.no_grad():
         dets = student(ex, return_loss=False)
     assert len(dets) == 1 and dets[0]["box3d_lidar"].shape[1] == 7
+
+
+def test_trainer_checkpoint_resume_reproduces_the_run():
+    """2 steps + save + load into a fresh trainer + 2 steps == 4 uninterrupted steps (kernels are deterministic)."""
+    ex = synth.distill_example(1, small=True)
+
+    def fresh():
+        teacher, student = synth.build_distill_models("cuda", ops.PRECISION_AUTO)
+        student.neck.train_pcr = False
+        return DistillTrainer(teacher, student, total_steps=50)
+    a = fresh()
+    for _ in range(4):
+        log_a = a.step(ex)
+    b = fresh()
+    for _ in range(2):
+        b.step(ex)
+    ckpt = b.state_dict()
+    ckpt = {k: (v if k != "state_dict" else {n: t.detach().clone() for n, t in v.items()}) for k, v in ckpt.items()}
+    c = fresh()
+    c.load_state_dict(ckpt)
+    assert c.global_step == 2 and c.opt.steps == 2
+    for _ in range(2):
+        log_c = c.step(ex)
+    assert abs(float(log_a["loss"]) - float(log_c["loss"])) <= 1e-4 * abs(float(log_a["loss"]))
+    pa = torch.cat([p.detach().flatten() for p in a.student.parameters()])
+    pc = torch.cat([p.detach().flatten() for p in c.student.parameters()])
+    assert float((pa - pc).abs().max()) <= 1e-5 * float(pa.abs().max())
+
