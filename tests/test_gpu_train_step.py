@@ -221,3 +221,30 @@ def test_trainer_checkpoint_resume_reproduces_the_run():
     pc = torch.cat([p.detach().flatten() for p in c.student.parameters()])
     assert float((pa - pc).abs().max()) <= 1e-5 * float(pa.abs().max())
 
+
+
+def test_detector_forward_api_in_training_mode():
+    """The reference-facing signatures: KD_VoxelNet.forward(return_loss=True, return_feature=True) returns
+    (loss dict, F_S_a, F_S_b, preds, mask_loss, comp_loss) with NCHW maps (voxelnet.py:251-258) and VoxelNet.forward
+    (return_loss=True) the CenterHead loss dict (:93-97); both are differentiable down to the first sparse layer."""
+    teacher, student = synth.build_distill_models("cuda", ops.PRECISION_AUTO)
+    ex = synth.distill_example(1, small=True)
+    student.train()
+    losses, F_S_a, F_S_b, preds, mask_loss, comp_loss = student(ex, return_loss=True, return_feature=True)
+    assert tuple(F_S_a.shape) == (1, 256, 188, 188) and tuple(F_S_b.shape) == (1, 256, 188, 188)
+    assert tuple(preds[0]["hm"].shape) == (1, 3, 188, 188) and tuple(preds[0]["dim"].shape) == (1, 3, 188, 188)
+    assert set(losses) >= {"loss", "hm_loss", "loc_loss", "loc_loss_elem", "num_positive"}
+    (losses["loss"][0] + mask_loss + comp_loss + F_S_a.mean()).backward()
+    for name in ("backbone.conv_input.0.weight", "neck.encoder_1.0.weight", "neck.generator_2.3.weight",
+                 "bbox_head.tasks.0.hm.3.bias"):
+        g = dict(student.named_parameters())[name].grad
+        assert g is not None and bool(torch.isfinite(g).all()) and float(g.abs().max()) > 0, name
+    # the neck's own NCHW API in training mode returns the PCR maps in the reference's [N,C,D,H,W] layout
+    x = torch.randn(1, 256, 188, 188, device="cuda")
+    ups, off2, mask2, off4, mask4, a, b = student.neck(x)
+    assert tuple(ups.shape) == (1, 512, 188, 188) and tuple(off2.shape) == (1, 3, 20, 752, 752)
+    assert tuple(mask2.shape) == (1, 1, 20, 752, 752) and tuple(off4.shape) == (1, 3, 10, 376, 376) and tuple(mask4.shape) == (1, 1, 10, 376, 376)
+    teacher.train()
+    out = teacher(ex, return_loss=True)
+    out["loss"][0].backward()
+    assert dict(teacher.named_parameters())["backbone.conv_input.0.weight"].grad is not None
