@@ -83,3 +83,24 @@ def test_sync_batchnorm_two_ranks_match_full_batch():
     assert rel(res[0][5] + res[1][5], beta.grad) < 1e-4
     for k in (0, 1):
         assert rel(res[k][6], rm) < 1e-5 and rel(res[k][7], rv) < 1e-5      # both ranks hold the global running statistics
+
+
+def test_converted_model_runs_like_the_original_in_one_process():
+    """nn.SyncBatchNorm.convert_sync_batchnorm(student) (tools/train.py:92-96): with no process group the converted modules
+    behave as plain BatchNorm -- eval detections unchanged (folded into the conv epilogues), training step finite."""
+    from sparse2dense_b200 import ops, synth
+    from sparse2dense_b200.trainer import DistillTrainer
+    teacher, student = synth.build_distill_models("cuda", ops.PRECISION_AUTO)
+    ex = synth.distill_example(1, small=True)
+    student.eval()
+    with torch.no_grad():
+        d0 = student(ex, return_loss=False)
+    conv = torch.nn.SyncBatchNorm.convert_sync_batchnorm(student)
+    assert any(isinstance(m, torch.nn.SyncBatchNorm) for m in conv.modules())
+    conv.eval()
+    with torch.no_grad():
+        d1 = conv(ex, return_loss=False)
+    assert torch.equal(d0[0]["box3d_lidar"], d1[0]["box3d_lidar"]) and torch.equal(d0[0]["scores"], d1[0]["scores"])
+    conv.neck.train_pcr = False
+    log = DistillTrainer(teacher, conv, total_steps=10).step(ex)
+    assert all(np.isfinite(float(v)) for v in log.values())
