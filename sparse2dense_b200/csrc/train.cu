@@ -132,6 +132,110 @@ __global__ void __launch_bounds__(256) conv_wgrad_kernel(const float* __restrict
   }
 }
 
+// Square channel tiles up to 64 x 64 (the 16 / 32 / 64-channel sparse stages, the 64-channel head branches): one CTA takes
+// FOUR taps at once, 64 threads per tap, so that the rows of D (dOut, independent of the tap) are staged once for four
+// taps and every thread still owns a T x T register tile (T = 2, 4, 8 for 16, 32, 64 channels).
+constexpr int kWgTaps = 4;
+
+template <int T>
+__global__ void __launch_bounds__(256) conv_wgrad_mt_kernel(const float* __restrict__ G, int g_ld, int n_g, int Cg,
+                                                            const float* __restrict__ D, int d_ld, const int* __restrict__ d_rows,
+                                                            int Cd, const int* __restrict__ tbl, int tbl_stride, int n_rows, int K,
+                                                            int rows_per_chunk, int vec4, float* __restrict__ partial) {
+  constexpr int C = 8 * T;
+  __shared__ __align__(16) float Gs[kWgTaps][kWgSlab][C];
+  __shared__ __align__(16) float Ds[kWgSlab][C];
+  __shared__ int js[kWgTaps][kWgSlab], is[kWgSlab];
+  auto col = [](int t, int v) { return T == 8 ? (v < 4 ? t * 4 + v : 32 + t * 4 + (v - 4)) : t * T + v; };
+  const int k0 = blockIdx.y * kWgTaps;
+  const int kt = threadIdx.x >> 6, t = threadIdx.x & 63, ta = t >> 3, tb = t & 7;
+  float acc[T][T];
+#pragma unroll
+  for (int u = 0; u < T; ++u)
+#pragma unroll
+    for (int v = 0; v < T; ++v) acc[u][v] = 0.f;
+  const int r_begin = blockIdx.x * rows_per_chunk;
+  const int r_end = min(n_rows, r_begin + rows_per_chunk);
+  for (int r0 = r_begin; r0 < r_end; r0 += kWgSlab) {
+    if (threadIdx.x < kWgSlab) {
+      const int i = r0 + threadIdx.x;
+      is[threadIdx.x] = i < r_end ? (d_rows ? __ldg(d_rows + i) : i) : -1;
+    }
+    if (threadIdx.x < kWgTaps * kWgSlab) {
+      const int kk = threadIdx.x / kWgSlab, r = threadIdx.x - kk * kWgSlab, i = r0 + r;
+      int j = -1;
+      if (k0 + kk < K && i < r_end) {
+        j = __ldg(tbl + (size_t)(k0 + kk) * tbl_stride + i);
+        if (j >= n_g) j = -1;
+      }
+      js[kk][r] = j;
+    }
+    __syncthreads();
+    if (vec4) {
+      for (int e = threadIdx.x; e < kWgSlab * (C / 4); e += 256) {
+        const int r = e / (C / 4), c = (e - r * (C / 4)) * 4;
+        const int i = is[r];
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (i >= 0 && c < Cd) v = __ldg(reinterpret_cast<const float4*>(D + (size_t)i * d_ld + c));
+        *reinterpret_cast<float4*>(&Ds[r][c]) = v;
+      }
+      for (int e = threadIdx.x; e < kWgTaps * kWgSlab * (C / 4); e += 256) {
+        const int kk = e / (kWgSlab * (C / 4)), rem = e - kk * (kWgSlab * (C / 4));
+        const int r = rem / (C / 4), c = (rem - r * (C / 4)) * 4;
+        const int j = js[kk][r];
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (j >= 0 && c < Cg) v = __ldg(reinterpret_cast<const float4*>(G + (size_t)j * g_ld + c));
+        *reinterpret_cast<float4*>(&Gs[kk][r][c]) = v;
+      }
+    } else {
+      for (int e = threadIdx.x; e < kWgSlab * C; e += 256) {
+        const int r = e / C, c = e - r * C;
+        const int i = is[r];
+        Ds[r][c] = (i >= 0 && c < Cd) ? __ldg(D + (size_t)i * d_ld + c) : 0.f;
+      }
+      for (int e = threadIdx.x; e < kWgTaps * kWgSlab * C; e += 256) {
+        const int kk = e / (kWgSlab * C), rem = e - kk * (kWgSlab * C);
+        const int r = rem / C, c = rem - r * C;
+        const int j = js[kk][r];
+        Gs[kk][r][c] = (j >= 0 && c < Cg) ? __ldg(G + (size_t)j * g_ld + c) : 0.f;
+      }
+    }
+    __syncthreads();
+#pragma unroll 4
+    for (int r = 0; r < kWgSlab; ++r) {
+      float ga[T], db[T];
+#pragma unroll
+      for (int u = 0; u < T; ++u) ga[u] = Gs[kt][r][col(ta, u)];
+#pragma unroll
+      for (int v = 0; v < T; ++v) db[v] = Ds[r][col(tb, v)];
+#pragma unroll
+      for (int u = 0; u < T; ++u)
+#pragma unroll
+        for (int v = 0; v < T; ++v) acc[u][v] = fmaf(ga[u], db[v], acc[u][v]);
+    }
+    __syncthreads();
+  }
+  const int k = k0 + kt;
+  if (k >= K) return;
+  float* dst = partial + ((size_t)blockIdx.x * K + k) * (size_t)Cg * Cd;
+#pragma unroll
+  for (int u = 0; u < T; ++u) {
+    const int a = col(ta, u);
+    if (a >= Cg) continue;
+#pragma unroll
+    for (int v = 0; v < T; ++v) {
+      const int b = col(tb, v);
+      if (b < Cd) dst[(size_t)a * Cd + b] = acc[u][v];
+    }
+  }
+}
+
+// T of the multi-tap kernel, or 0: both channel counts in the same bucket 9..16 / 17..32 / 33..64
+static int wgrad_mt_tile(int Cg, int Cd) {
+  auto bucket = [](int c) { return c <= 8 ? 0 : c <= 16 ? 2 : c <= 32 ? 4 : c <= 64 ? 8 : 0; };
+  return bucket(Cg) == bucket(Cd) ? bucket(Cg) : 0;
+}
+
 __global__ void wgrad_reduce_kernel(const float* __restrict__ partial, int n_chunks, long long n_elem, int accumulate,
                                     float* __restrict__ out) {
   for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < n_elem; e += (long long)gridDim.x * blockDim.x) {
@@ -217,6 +321,14 @@ static int wgrad_chunks(int n_rows, int K, int Cg, int Cd) {
     long long want = (148LL * 4 + K - 1) / K;
     const long long max_chunks = (n_rows + 2047) / 2048;                         // at least 8 rows per thread
     if (want > max_chunks) want = max_chunks;
+    return (int)(want < 1 ? 1 : want);
+  }
+  if (wgrad_mt_tile(Cg, Cd)) {
+    const long long tiles = (K + kWgTaps - 1) / kWgTaps;
+    long long want = (148LL * 4 + tiles - 1) / tiles;
+    const long long max_chunks = (n_rows + 4 * kWgSlab - 1) / (4 * kWgSlab);
+    if (want > max_chunks) want = max_chunks;
+    if (want > 65535) want = 65535;
     return (int)(want < 1 ? 1 : want);
   }
   const int ta = wgrad_tile(Cg), tb = wgrad_tile(Cd);
@@ -710,6 +822,21 @@ extern "C" int s2d_conv_wgrad(const float* g, int g_ld, int n_g, int Cg, const f
   dim3 grid(chunks, K, na * nb);
   float* partial = static_cast<float*>(ws);
   const int bucket = wgrad_small_bucket(Cg, Cd);
+  const int mt = bucket ? 0 : wgrad_mt_tile(Cg, Cd);
+  if (mt) {
+    const int vec4 = (g_ld % 4 == 0) && (d_ld % 4 == 0) && (Cg % 4 == 0) && (Cd % 4 == 0) &&
+                     ((reinterpret_cast<uintptr_t>(g) | reinterpret_cast<uintptr_t>(d)) & 15) == 0;
+    dim3 gm(chunks, (K + kWgTaps - 1) / kWgTaps);
+    if (mt == 2) conv_wgrad_mt_kernel<2><<<gm, 256, 0, st>>>(g, g_ld, n_g, Cg, d, d_ld, d_rows, Cd, tbl, tbl_stride, n_rows, K, rpc, vec4, partial);
+    if (mt == 4) conv_wgrad_mt_kernel<4><<<gm, 256, 0, st>>>(g, g_ld, n_g, Cg, d, d_ld, d_rows, Cd, tbl, tbl_stride, n_rows, K, rpc, vec4, partial);
+    if (mt == 8) conv_wgrad_mt_kernel<8><<<gm, 256, 0, st>>>(g, g_ld, n_g, Cg, d, d_ld, d_rows, Cd, tbl, tbl_stride, n_rows, K, rpc, vec4, partial);
+    S2D_LAUNCH_CHECK();
+    const long long n_elem_m = (long long)K * Cg * Cd;
+    wgrad_reduce_kernel<<<grid_for(n_elem_m, 256, 148 * 8), 256, 0, st>>>(partial, chunks, n_elem_m, accumulate, out);
+    S2D_LAUNCH_CHECK();
+    count_launches(2);
+    return S2D_OK;
+  }
   if (bucket) {
     dim3 gs(chunks, K);
     const int d_vec4 = (d_ld % 4 == 0) && (Cd % 4 == 0) && (reinterpret_cast<uintptr_t>(d) & 15) == 0;
