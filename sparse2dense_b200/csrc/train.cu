@@ -132,6 +132,94 @@ __global__ void __launch_bounds__(256) conv_wgrad_kernel(const float* __restrict
   }
 }
 
+// The 128 x 128 tile with the next slab in flight: rows go global -> shared with cp.async (16 B, zero-fill for missing
+// neighbours) into the other half of a double buffer while the FFMA loop runs on the current one.  Needs 16-byte aligned
+// rows and channel counts that are multiples of 4 (every 128 / 256 / 512-channel layer of the path).
+__device__ __forceinline__ void wg_cp16(uint32_t dst, const void* src, uint32_t bytes) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(bytes) : "memory");
+}
+
+__global__ void __launch_bounds__(256) conv_wgrad_pipe_kernel(const float* __restrict__ G, int g_ld, int n_g, int Cg,
+                                                              const float* __restrict__ D, int d_ld,
+                                                              const int* __restrict__ d_rows, int Cd,
+                                                              const int* __restrict__ tbl, int tbl_stride, int n_rows,
+                                                              int rows_per_chunk, int na_tiles, float* __restrict__ partial) {
+  constexpr int TA = 8, TB = 8, CA = 128, CB = 128;
+  extern __shared__ __align__(16) float wg_smem[];              // [2][32][128] G, then [2][32][128] D
+  float(*Gs)[kWgSlab][CA] = reinterpret_cast<float(*)[kWgSlab][CA]>(wg_smem);
+  float(*Ds)[kWgSlab][CB] = reinterpret_cast<float(*)[kWgSlab][CB]>(wg_smem + 2 * kWgSlab * CA);
+  auto bcol = [](int t, int v) { return v < 4 ? t * 4 + v : 64 + t * 4 + (v - 4); };
+  const int k = blockIdx.y;
+  const int a_tile = blockIdx.z % na_tiles, b_tile = blockIdx.z / na_tiles;
+  const int a0 = a_tile * CA, b0 = b_tile * CB;
+  const int ta = threadIdx.x >> 4, tb = threadIdx.x & 15;
+  float acc[TA][TB];
+#pragma unroll
+  for (int u = 0; u < TA; ++u)
+#pragma unroll
+    for (int v = 0; v < TB; ++v) acc[u][v] = 0.f;
+  const int r_begin = blockIdx.x * rows_per_chunk;
+  const int r_end = min(n_rows, r_begin + rows_per_chunk);
+  const int c4 = (threadIdx.x & 31) * 4, rr = threadIdx.x >> 5;   // this thread copies column chunk c4 of rows rr, rr+8, ...
+  const uint32_t gs_base = (uint32_t)__cvta_generic_to_shared(&Gs[0][0][0]);
+  const uint32_t ds_base = (uint32_t)__cvta_generic_to_shared(&Ds[0][0][0]);
+
+  auto issue = [&](int r0, int buf) {
+#pragma unroll
+    for (int q = 0; q < kWgSlab / 8; ++q) {
+      const int r = rr + 8 * q, i = r0 + r;
+      int j = -1, di = 0;
+      if (i < r_end) {
+        j = __ldg(tbl + (size_t)k * tbl_stride + i);
+        if (j >= n_g) j = -1;
+        di = d_rows ? __ldg(d_rows + i) : i;
+      }
+      const bool ga = j >= 0 && a0 + c4 < Cg, da = j >= 0 && b0 + c4 < Cd;
+      const uint32_t off = (uint32_t)((buf * kWgSlab + r) * CA + c4) * 4u;
+      wg_cp16(gs_base + off, ga ? (const void*)(G + (size_t)j * g_ld + a0 + c4) : (const void*)G, ga ? 16u : 0u);
+      wg_cp16(ds_base + off, da ? (const void*)(D + (size_t)di * d_ld + b0 + c4) : (const void*)D, da ? 16u : 0u);
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+  };
+
+  if (r_begin < r_end) issue(r_begin, 0);
+  int buf = 0;
+  for (int r0 = r_begin; r0 < r_end; r0 += kWgSlab, buf ^= 1) {
+    const bool more = r0 + kWgSlab < r_end;
+    if (more) {
+      issue(r0 + kWgSlab, buf ^ 1);
+      asm volatile("cp.async.wait_group 1;" ::: "memory");
+    } else {
+      asm volatile("cp.async.wait_group 0;" ::: "memory");
+    }
+    __syncthreads();
+#pragma unroll 4
+    for (int r = 0; r < kWgSlab; ++r) {
+      float ga[TA], db[TB];
+#pragma unroll
+      for (int u = 0; u < TA; ++u) ga[u] = Gs[buf][r][ta * TA + u];
+#pragma unroll
+      for (int v = 0; v < TB; ++v) db[v] = Ds[buf][r][bcol(tb, v)];
+#pragma unroll
+      for (int u = 0; u < TA; ++u)
+#pragma unroll
+        for (int v = 0; v < TB; ++v) acc[u][v] = fmaf(ga[u], db[v], acc[u][v]);
+    }
+    __syncthreads();                                              // everyone is done with `buf` before it is refilled
+  }
+  float* dst = partial + ((size_t)blockIdx.x * gridDim.y + k) * (size_t)Cg * Cd;
+#pragma unroll
+  for (int u = 0; u < TA; ++u) {
+    const int a = a0 + ta * TA + u;
+    if (a >= Cg) continue;
+#pragma unroll
+    for (int v = 0; v < TB; ++v) {
+      const int b = b0 + bcol(tb, v);
+      if (b < Cd) dst[(size_t)a * Cd + b] = acc[u][v];
+    }
+  }
+}
+
 // Square channel tiles up to 64 x 64 (the 16 / 32 / 64-channel sparse stages, the 64-channel head branches): one CTA takes
 // FOUR taps at once, 64 threads per tap, so that the rows of D (dOut, independent of the tap) are staged once for four
 // taps and every thread still owns a T x T register tile (T = 2, 4, 8 for 16, 32, 64 channels).
@@ -849,6 +937,23 @@ extern "C" int s2d_conv_wgrad(const float* g, int g_ld, int n_g, int Cg, const f
     S2D_LAUNCH_CHECK();
     const long long n_elem_s = (long long)K * Cg * Cd;
     wgrad_reduce_kernel<<<grid_for(n_elem_s, 256, 148 * 8), 256, 0, st>>>(partial, chunks, n_elem_s, accumulate, out);
+    S2D_LAUNCH_CHECK();
+    count_launches(2);
+    return S2D_OK;
+  }
+  if (ta == 8 && tb == 8 && (g_ld % 4 == 0) && (d_ld % 4 == 0) && (Cg % 4 == 0) && (Cd % 4 == 0) &&
+      ((reinterpret_cast<uintptr_t>(g) | reinterpret_cast<uintptr_t>(d)) & 15) == 0) {
+    constexpr int smem = 4 * kWgSlab * 128 * (int)sizeof(float);                // 64 KB: two slabs of G and of D
+    static bool configured = false;
+    if (!configured) {
+      S2D_CUDA(cudaFuncSetAttribute(conv_wgrad_pipe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+      configured = true;
+    }
+    conv_wgrad_pipe_kernel<<<grid, 256, smem, st>>>(g, g_ld, n_g, Cg, d, d_ld, d_rows, Cd, tbl, tbl_stride, n_rows, rpc, na,
+                                                    partial);
+    S2D_LAUNCH_CHECK();
+    const long long n_elem_p = (long long)K * Cg * Cd;
+    wgrad_reduce_kernel<<<grid_for(n_elem_p, 256, 148 * 8), 256, 0, st>>>(partial, chunks, n_elem_p, accumulate, out);
     S2D_LAUNCH_CHECK();
     count_launches(2);
     return S2D_OK;
