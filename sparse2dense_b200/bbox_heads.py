@@ -1,9 +1,10 @@
-"""CenterPoint head, forward part (det3d/models/bbox_heads/center_head.py:65-110 ``SepHead``, :167-244
-``CenterHead.__init__/forward``).  Same constructor arguments and state-dict keys
+"""CenterPoint head (det3d/models/bbox_heads/center_head.py:65-110 ``SepHead``, :167-244
+``CenterHead.__init__/forward``, :250-291 ``loss``).  Same constructor arguments and state-dict keys
 (``shared_conv.0.weight``, ``tasks.0.hm.3.bias`` …).  The shared 3x3 conv and the five 64->64 branch convs
 (fused into one 64->320 launch) run on the tcgen05 gather-GEMM; the tiny output convs (Cout <= 3) on the fp32
 kernel.  ``predict`` (:293-495: decode, masks, top-4096, rotated NMS, top-500) runs as four launches for the whole
-batch on the device (csrc/detect.cu); ``loss`` is not built yet."""
+batch on the device (csrc/detect.cu); ``loss`` runs the reduction kernels of csrc/losses.cu and is differentiable; in
+training mode every conv is its own launch on the autograd operators of ``autograd.py`` (batch-statistics BatchNorm)."""
 import copy
 import logging
 

@@ -11,8 +11,9 @@ det3d/models/detectors/voxelnet.py:203-215), so reference-style model code keeps
     SparseSequential(*modules), SparseModule
 
 Underneath, every step is one call into libs2d_b200.so (output-stationary gather-GEMM with a
-fused BatchNorm/ReLU/residual epilogue) -- see include/s2d_b200.h.  Forward only in this
-version; there is no CPU implementation.
+fused BatchNorm/ReLU/residual epilogue) -- see include/s2d_b200.h.  In training mode (batch-statistics
+BatchNorm) the layers run on the autograd operators of ``autograd.py``, whose backward is the same
+gather-GEMM over the transposed rulebook plus ``s2d_conv_wgrad``.  There is no CPU implementation.
 """
 import math
 from collections import OrderedDict
