@@ -609,6 +609,48 @@ def make_assign_goldens():
     np.savez_compressed(os.path.join(HERE, "assign_label.npz"), **save)
 
 
+def make_pcr_loss_goldens():
+    """KD_VoxelNet.mask_offset_loss (det3d/models/detectors/voxelnet.py:171-185) executed from the reference source on a small
+    synthetic reconstruction target; inputs and outputs are stored (the GPU kernel works from the sparse voxel list)."""
+    import ast
+    import torch
+    import torch.nn.functional as F
+    src = open(REF + "/det3d/models/detectors/voxelnet.py").read()
+    tree = ast.parse(src)
+    fn = None
+    for node in ast.walk(tree):
+        if isinstance(node, ast.FunctionDef) and node.name == "mask_offset_loss":
+            fn = ast.get_source_segment(src, node)
+    import textwrap
+    ns = dict(F=F, torch=torch)
+    exec(compile(textwrap.dedent(fn), "voxelnet.py[mask_offset_loss]", "exec"), ns)
+    ref_fn = ns["mask_offset_loss"]
+    from oracle import train_ref as TR
+    save = {}
+    for seed, (B, D, H, W, M) in ((60, (2, 4, 12, 10, 150)), (61, (1, 6, 9, 16, 300))):
+        rng = np.random.default_rng(seed)
+        cells = rng.choice(B * D * H * W, M, replace=False)
+        b, r = np.divmod(cells, D * H * W)
+        z, r = np.divmod(r, H * W)
+        y, x = np.divmod(r, W)
+        coors = np.stack([b, z, y, x], 1).astype(np.int32)
+        grid = TR.voxel_grid(B, D, H, W, torch.zeros(1))
+        centre = grid[torch.from_numpy(b).long(), :, torch.from_numpy(z).long(), torch.from_numpy(y).long(), torch.from_numpy(x).long()].numpy()
+        feats = np.concatenate([centre + rng.uniform(-0.3, 0.3, (M, 3)), rng.uniform(0, 1, (M, 2))], 1).astype(np.float32)
+        feats[:5, 0] = centre[:5, 0]                       # some exact-zero offset components (dropped by `gt != 0`)
+        gt = TR.dense_from_voxels(torch.from_numpy(feats), torch.from_numpy(coors), B, (D, H, W))
+        gen_offset = torch.from_numpy(rng.normal(0, 0.5, (B, 3, D, H, W)).astype(np.float32))
+        gen_mask = torch.from_numpy(rng.normal(0, 2.0, (B, 1, D, H, W)).astype(np.float32))
+        loss, com = ref_fn(None, gen_offset, gen_mask, gt, grid)
+        mine = TR.mask_offset_loss(gen_offset, gen_mask, gt, grid)
+        assert abs(float(mine[0]) - float(loss)) < 1e-6 and abs(float(mine[1]) - float(com)) < 1e-6
+        save.update({f"{seed}_dims": np.array([B, D, H, W]), f"{seed}_coors": coors, f"{seed}_feats": feats,
+                     f"{seed}_gen_offset": gen_offset.numpy(), f"{seed}_gen_mask": gen_mask.numpy(),
+                     f"{seed}_mask_loss": np.float32(loss), f"{seed}_offset_loss": np.float32(com)})
+        print(f"pcr loss seed {seed}: mask {float(loss):.6f} offset {float(com):.6f}")
+    np.savez_compressed(os.path.join(HERE, "pcr_loss.npz"), **save)
+
+
 def make_optim_goldens():
     """The reference's own OptimWrapper (det3d/solver/fastai_optim.py:118-174, true_wd / bn_wd as build_one_cycle_optimizer
     sets them, apis/train.py:168-186) over torch Adam, driven by the reference's OneCycle
@@ -660,6 +702,9 @@ if __name__ == "__main__":
     if len(sys.argv) > 1 and sys.argv[1] == "assign":
         make_assign_goldens()
         sys.exit(0)
+    if len(sys.argv) > 1 and sys.argv[1] == "pcr":
+        make_pcr_loss_goldens()
+        sys.exit(0)
     if len(sys.argv) > 1 and sys.argv[1] == "optim":
         make_optim_goldens()
         sys.exit(0)
@@ -687,3 +732,4 @@ if __name__ == "__main__":
     make_loss_goldens()
     make_optim_goldens()
     make_assign_goldens()
+    make_pcr_loss_goldens()

@@ -83,3 +83,30 @@ def test_center_head_loss_matches_oracle():
     assert abs(float(ret["loc_loss"][0]) - loc) < 1e-4 * abs(loc)
     assert abs(float(ret["loss"][0]) - (float(w["hm"]) + 2 * loc)) < 1e-4 * abs(float(w["hm"]) + 2 * loc)
     assert float(ret["num_positive"][0]) == d["mask"].sum()
+
+
+@pytest.mark.parametrize("seed", [60, 61])
+def test_pcr_loss_kernel_matches_reference_golden_and_autograd(seed):
+    """s2d_pcr_loss / s2d_pcr_loss_bwd (sparse voxel list, rows in (b,y,x,z) order) against the values of the reference's own
+    KD_VoxelNet.mask_offset_loss on dense tensors (tests/golden/pcr_loss.npz) and its torch-autograd gradients."""
+    import os
+    from conftest import GOLDEN
+    from oracle import train_ref as TR
+    from sparse2dense_b200 import pcr
+    g = np.load(os.path.join(GOLDEN, "pcr_loss.npz"))
+    B, D, H, W = (int(v) for v in g[f"{seed}_dims"])
+    off = torch.from_numpy(g[f"{seed}_gen_offset"]).requires_grad_(True)
+    msk = torch.from_numpy(g[f"{seed}_gen_mask"]).requires_grad_(True)
+    gt = TR.dense_from_voxels(torch.from_numpy(g[f"{seed}_feats"]), torch.from_numpy(g[f"{seed}_coors"]), B, (D, H, W))
+    m_ref, o_ref = TR.mask_offset_loss(off, msk, gt, TR.voxel_grid(B, D, H, W, gt))
+    (0.7 * m_ref + 1.3 * o_ref).backward()
+
+    to_rows = lambda t: t.detach().permute(0, 3, 4, 2, 1).reshape(-1, t.shape[1]).contiguous().cuda()   # [B,C,D,H,W] -> (b,y,x,z) rows
+    off_r, msk_r = to_rows(off).requires_grad_(True), to_rows(msk).requires_grad_(True)
+    out = pcr._PcrLoss.apply(msk_r, off_r, torch.from_numpy(g[f"{seed}_coors"]).cuda(), torch.from_numpy(g[f"{seed}_feats"]).cuda(),
+                             (B, D, H, W), pcr._centre9(D, H, W))
+    assert abs(float(out[0]) - float(g[f"{seed}_mask_loss"])) < 2e-6 * max(1.0, float(g[f"{seed}_mask_loss"]))
+    assert abs(float(out[1]) - float(g[f"{seed}_offset_loss"])) < 2e-6
+    (0.7 * out[0] + 1.3 * out[1]).backward()
+    assert torch.allclose(off_r.grad.cpu(), to_rows(off.grad).cpu(), rtol=1e-5, atol=1e-9)
+    assert torch.allclose(msk_r.grad.cpu(), to_rows(msk.grad).cpu(), rtol=1e-4, atol=1e-9)
