@@ -156,3 +156,19 @@ def test_checkpoint_round_trip_reference_format(tmp_path):
         load_checkpoint(c, str(tmp_path / "ddp.pth"), map_location="cpu", strict=True)
     with pytest.raises(IOError):
         load_checkpoint(c, str(tmp_path / "nope.pth"))
+
+
+def test_det3d_alias_package_exposes_training_and_pipeline_names():
+    """Pure import aliases (no arithmetic) under the reference's module paths."""
+    from det3d.datasets.pipelines import AssignLabel, Voxelization
+    from det3d.solver import FlatAdam, OneCycle
+    from det3d.torchie.trainer import DistillTrainer, load_checkpoint
+    from sparse2dense_b200 import pipeline, trainer
+    assert AssignLabel is pipeline.AssignLabel and Voxelization is pipeline.Voxelization
+    assert OneCycle is trainer.OneCycle and FlatAdam is trainer.FlatAdam and DistillTrainer is trainer.DistillTrainer
+    assert callable(load_checkpoint)
+    cfg = dict(out_size_factor=8, target_assigner=dict(tasks=[dict(num_class=3, class_names=["A", "B", "C"])]),
+               gaussian_overlap=0.1, max_objs=500, min_radius=2)
+    a = AssignLabel(cfg=cfg)
+    assert a.num_classes == [3] and a._max_objs == 500 and a._min_radius == 2
+
