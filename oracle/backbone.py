@@ -71,6 +71,36 @@ def backbone_forward(state, voxel_features, coors, batch_size, input_shape, wide
     return (bev, multi, stats) if return_stats else (bev, multi)
 
 
+FHD_LAYERS = [("s", 0), ("s", 0), ("d", (3, 2, 1)), ("s", 1), ("s", 1), ("d", (3, 2, 1)), ("s", 2), ("s", 2), ("s", 2),
+              ("d", (3, 2, (0, 1, 1))), ("s", 3), ("s", 3), ("s", 3)]
+
+
+def fhd_forward(state, voxel_features, coors, batch_size, input_shape, wide=False):
+    """SpMiddleFHD.forward (det3d/models/backbones/scn.py:187-289): conv / BN(eval) / ReLU groups ``middle_conv.{3i}``,
+    ``middle_conv.{3i+1}`` and ``extra_conv.{0,1}`` -> (bev [B,128,H,W], (conv_4 features, indices, spatial_shape))."""
+    shape = tuple((np.array(input_shape[::-1]) + [1, 0, 0]).tolist())
+    coors = np.ascontiguousarray(coors, np.int32)
+    x, tables = voxel_features, {}
+    for i, (kind, arg) in enumerate(FHD_LAYERS):
+        w = state[f"middle_conv.{3 * i}.weight"]
+        s, h = _bn(state, f"middle_conv.{3 * i + 1}")
+        if kind == "s":
+            key = (arg, len(coors))
+            if key not in tables:
+                tables[key] = R.rulebook_subm(coors, shape, 3)[0]
+            tbl = tables[key]
+        else:
+            ks, st, pd = arg
+            coors, tbl, shape_o, _ = R.rulebook_sparse(coors, shape, ks, st, pd)
+            shape = tuple(shape_o.tolist())
+        x = R.bn_act(R.spconv_fwd(x, w, tbl, wide), s, h, None, True)
+    conv_4 = (x, coors, shape)
+    oc, tbl_e, shape_e, _ = R.rulebook_sparse(coors, shape, (3, 1, 1), (2, 1, 1), 0)
+    s, h = _bn(state, "extra_conv.1")
+    x = R.bn_act(R.spconv_fwd(x, state["extra_conv.0.weight"], tbl_e, wide), s, h, None, True)
+    return R.dense_bev(x, oc, batch_size, shape_e), conv_4
+
+
 def random_state(seed=0, num_input_features=5):
     """Seeded random reference-format weights (shared with bench.py so both arms use the same numbers)."""
     from sparse2dense_b200.synth import backbone_state

@@ -163,6 +163,68 @@ class SpMiddleResNetFHD(nn.Module):
 
 
 @BACKBONES.register_module
+class SpMiddleFHD(nn.Module):
+    """The SECOND backbone (det3d/models/backbones/scn.py:187-289): the plain (non-residual) sparse stack
+    16-16 | 32-32-32 | 64-64-64-64 | 64-64-64-64 + the (3,1,1) ``extra_conv``; same constructor arguments, module tree and
+    state-dict keys (``middle_conv.0.weight`` ...), returns ``(dense [B, 128, H, W], conv_4 SparseConvTensor)``.
+    Every conv -> BatchNorm1d -> ReLU group is one fused launch in eval mode and runs the training operators in train mode
+    (``spconv.SparseSequential``)."""
+
+    def __init__(self, num_input_features=128, norm_cfg=None, name="SpMiddleFHD", **kwargs):
+        super(SpMiddleFHD, self).__init__()
+        self.name = name
+        self.dcn = None
+        self.zero_init_residual = False
+        if norm_cfg is None:
+            norm_cfg = dict(type="BN1d", eps=1e-3, momentum=0.01)
+
+        def group(conv):
+            return [conv, build_norm_layer(norm_cfg, conv.out_channels)[1], nn.ReLU()]
+        layers = []
+        layers += group(SubMConv3d(num_input_features, 16, 3, bias=False, indice_key="subm0"))
+        layers += group(SubMConv3d(16, 16, 3, bias=False, indice_key="subm0"))
+        layers += group(SparseConv3d(16, 32, 3, 2, padding=1, bias=False))
+        layers += group(SubMConv3d(32, 32, 3, indice_key="subm1", bias=False))
+        layers += group(SubMConv3d(32, 32, 3, indice_key="subm1", bias=False))
+        layers += group(SparseConv3d(32, 64, 3, 2, padding=1, bias=False))
+        for _ in range(3):
+            layers += group(SubMConv3d(64, 64, 3, indice_key="subm2", bias=False))
+        layers += group(SparseConv3d(64, 64, 3, 2, padding=[0, 1, 1], bias=False))
+        for _ in range(3):
+            layers += group(SubMConv3d(64, 64, 3, indice_key="subm3", bias=False))
+        self.middle_conv = spconv.SparseSequential(*layers)
+        self.extra_conv = spconv.SparseSequential(*group(SparseConv3d(64, 64, (3, 1, 1), (2, 1, 1), bias=False)))
+
+    set_precision = SpMiddleResNetFHD.set_precision
+
+    def _strided(self):
+        return [m for m in list(self.middle_conv) + list(self.extra_conv)
+                if isinstance(m, spconv.SparseConvolution) and not m.subm]
+
+    def bev_hw(self, input_shape):
+        shape = tuple(int(v) for v in (np.array(input_shape[::-1]) + [1, 0, 0]))
+        for m in self._strided():
+            shape = ops.conv_out_shape(shape, m.kernel_size, m.stride, m.padding, m.dilation)
+        return int(shape[1]), int(shape[2])
+
+    def forward(self, voxel_features, coors, batch_size, input_shape):
+        sparse_shape = np.array(input_shape[::-1]) + [1, 0, 0]          # scn.py:274
+        coors = coors.int().contiguous()
+        ret = spconv.SparseConvTensor(voxel_features, coors, sparse_shape, batch_size)
+        spconv.plan_coords(ret, self._strided())                        # all output coordinate sets, one host sync
+        conv_4 = self.middle_conv(ret)
+        ret = self.extra_conv(conv_4)
+        if torch.is_grad_enabled() and ret.features.requires_grad:
+            from .autograd import DenseBEV
+            ret = DenseBEV.apply(ret.features, ret.indices, batch_size, ret.spatial_shape, False)
+        else:
+            ret = ret.dense()
+            N, C, D, H, W = ret.shape
+            ret = ret.view(N, C * D, H, W)
+        return ret, conv_4
+
+
+@BACKBONES.register_module
 class PointPillarsScatter_S2D(nn.Module):
     """Pillar scatter + the S2D module of the pillar student (det3d/models/readers/pillar_encoder.py:219-394, registered
     under BACKBONES there too).  Same module tree / state-dict keys; eval forward (the PCR generator is train-only).

@@ -172,3 +172,14 @@ def test_det3d_alias_package_exposes_training_and_pipeline_names():
     a = AssignLabel(cfg=cfg)
     assert a.num_classes == [3] and a._max_objs == 500 and a._min_radius == 2
 
+
+def test_spmiddlefhd_module_tree_matches_reference_keys():
+    """SECOND backbone (scn.py:187-289): 13 conv/BN/ReLU groups in ``middle_conv`` + ``extra_conv``, spconv weight layout."""
+    from sparse2dense_b200 import registry
+    bb = registry.build_backbone(dict(type="SpMiddleFHD", num_input_features=5, ds_factor=8))
+    sd = bb.state_dict()
+    assert tuple(sd["middle_conv.0.weight"].shape) == (3, 3, 3, 5, 16)
+    assert tuple(sd["middle_conv.27.weight"].shape) == (3, 3, 3, 64, 64) and "middle_conv.37.running_var" in sd
+    assert tuple(sd["extra_conv.0.weight"].shape) == (3, 1, 1, 64, 64)
+    assert len(bb.middle_conv) == 39 and not any(k.endswith(".bias") and ".0." in k for k in sd if k.startswith("extra"))
+
