@@ -153,6 +153,8 @@ int s2d_rulebook_sparse(const int* out_coors, int n_out, int batch, const int* s
 #define S2D_PRECISION_TF32X3 2
 #define S2D_PRECISION_TF32_BF16C 3
 #define S2D_PRECISION_AUTO 4 /* TF32_BF16C where the layer is tensor bound (Cout % 128 == 0), TF32X3 elsewhere */
+#define S2D_PRECISION_BF16X2 5 /* operands pre-split into BF16 pairs (x = hi + lo, 16 mantissa bits): hi*w1 + hi*w2 + lo*w1,
+                                  three BF16 MMAs with fp32 accumulation, ~4e-6 relative per layer.  Needs in_split. */
 int s2d_spconv_tf32_supported(int Cin, int Cout);
 size_t s2d_spconv_packed_bytes(int K, int Cin, int Cout);
 int s2d_spconv_pack_weights(const float* W, int K, int Cin, int Cout, int precision, float* packed, void* stream);
@@ -194,8 +196,22 @@ typedef struct s2d_conv_params {
   int tbl_stride, K;
   int n_in, n_out, Cin, Cout;
   int act, res_after_act, precision;
+  /* S2D_PRECISION_BF16X2 only (zero / null otherwise).  A "split row" stores, per 32-channel chunk (or per 16-channel
+   * row), [hi words | lo words], two BF16 per 32-bit word, at word offset = channel offset: the same geometry and byte
+   * size as the fp32 row.  in_split: the input rows in that form (s2d_rows_split, or the out_split of the producing
+   * layer; `in` may then be null).  out_split: optional second output for the next layer (`out` may be null).
+   * tile_masks: optional i32 [ceil(n_out / 128)], bit k set iff some row of the 128-row tile has tbl[k][row] >= 0
+   * (s2d_table_tile_masks); offsets whose bit is clear are skipped for the whole tile. */
+  const void* in_split;
+  void* out_split;
+  const int* tile_masks;
+  int in_split_ld, out_split_ld;
 } s2d_conv_params;
 int s2d_conv_fwd(const s2d_conv_params* params, void* stream);
+/* fp32 rows [n_rows, C] (row stride in_ld floats) -> split rows (row stride out_ld words); C == 16 or C % 32 == 0. */
+int s2d_rows_split(const float* in, long long n_rows, int C, int in_ld, void* out, int out_ld, void* stream);
+/* tile_masks[t] = OR over the rows r of tile t (128 rows) and the offsets k < K (<= 31) of (tbl[k][r] >= 0) << k. */
+int s2d_table_tile_masks(const int* tbl, int tbl_stride, int K, int n_rows, int* tile_masks, void* stream);
 
 /* Regular-grid neighbour tables for dense 2-D convolutions over NHWC rows (row = (b*H + y)*W + x).
  *   s2d_grid2d_table       : Conv2d(kh x kw, stride, pad): tbl i32 [kh*kw, B*Ho*Wo], -1 outside the map

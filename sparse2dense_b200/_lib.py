@@ -39,6 +39,8 @@ SIGNATURES = {
     "s2d_spconv_packed_bytes": (_sz, [_i, _i, _i]),
     "s2d_spconv_pack_weights": (_i, [_vp, _i, _i, _i, _i, _vp, _vp]),
     "s2d_conv_fwd": (_i, [_vp, _vp]),
+    "s2d_rows_split": (_i, [_vp, ctypes.c_longlong, _i, _i, _vp, _i, _vp]),
+    "s2d_table_tile_masks": (_i, [_vp, _i, _i, _i, _vp, _vp]),
     "s2d_grid2d_table": (_i, [_i, _i, _i, _i, _i, _i, _i, _vp, _i, _vp]),
     "s2d_grid2d_tconv_table": (_i, [_i, _i, _i, _i, _i, _i, _i, _i, _vp, _i, _vp, _vp]),
     "s2d_nchw_to_nhwc": (_i, [_vp, _i, _i, _i, _vp, _i, _vp]),
@@ -113,7 +115,8 @@ class ConvParams(ctypes.Structure):
     _fields_ = [("in_", _vp), ("weights", _vp), ("tbl", _vp), ("scale", _vp), ("shift", _vp), ("residual", _vp),
                 ("out", _vp), ("out_rows", _vp), ("in_ld", _i), ("out_ld", _i), ("res_ld", _i), ("tbl_stride", _i),
                 ("K", _i), ("n_in", _i), ("n_out", _i), ("Cin", _i), ("Cout", _i), ("act", _i),
-                ("res_after_act", _i), ("precision", _i)]
+                ("res_after_act", _i), ("precision", _i), ("in_split", _vp), ("out_split", _vp), ("tile_masks", _vp),
+                ("in_split_ld", _i), ("out_split_ld", _i)]
 
 
 class DecodeParams(ctypes.Structure):

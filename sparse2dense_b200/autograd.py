@@ -331,6 +331,9 @@ def norm_act(x, norm, bias=None, act=ACT_NONE, residual=None, res_after_act=Fals
     if pre_bias is not None:
         with torch.no_grad():
             norm.running_mean.add_(pre_bias.detach(), alpha=momentum)
+    # the statistics kernels updated the running buffers through raw pointers: bump their version counters so that the
+    # folded-BN caches keyed on (data_ptr, _version) are rebuilt by the next eval-mode forward
+    torch.autograd.graph.increment_version([norm.running_mean, norm.running_var])
     return y
 
 

@@ -199,6 +199,7 @@ static int conv_fwd_fp32(const s2d_conv_params& p, cudaStream_t st) {
 }
 
 int conv_fwd_tf32(const s2d_conv_params& p, cudaStream_t st);  // spconv_tc.cu
+int conv_fwd_bf2(const s2d_conv_params& p, cudaStream_t st);   // conv_bf2.cu
 
 }  // namespace s2d
 
@@ -210,11 +211,14 @@ extern "C" int s2d_conv_fwd(const s2d_conv_params* params, void* stream) {
   S2D_REQUIRE(p.n_in >= 0 && p.n_out >= 0 && p.Cin >= 1 && p.Cout >= 1, "s2d_conv_fwd: bad sizes");
   S2D_REQUIRE(p.K >= 1 && p.K <= kMaxK, "s2d_conv_fwd: K=%d outside [1,%d]", p.K, kMaxK);
   S2D_REQUIRE(p.tbl_stride >= p.n_out, "s2d_conv_fwd: tbl_stride %d < n_out %d", p.tbl_stride, p.n_out);
-  S2D_REQUIRE(p.in_ld >= p.Cin && p.out_ld >= p.Cout && (!p.residual || p.res_ld >= p.Cout),
+  const bool b2 = p.precision == S2D_PRECISION_BF16X2;   // reads in_split, may write out_split only
+  S2D_REQUIRE(((b2 && !p.in) || p.in_ld >= p.Cin) && ((b2 && !p.out) || p.out_ld >= p.Cout) &&
+                  (!p.residual || p.res_ld >= p.Cout),
               "s2d_conv_fwd: row stride smaller than the channel count");
   S2D_REQUIRE(p.act >= S2D_ACT_NONE && p.act <= S2D_ACT_GELU, "s2d_conv_fwd: unknown activation %d", p.act);
   if (p.n_out == 0) return S2D_OK;
-  S2D_REQUIRE(p.in && p.weights && p.tbl && p.out, "s2d_conv_fwd: null argument");
+  S2D_REQUIRE((p.in || (b2 && p.in_split)) && p.weights && p.tbl && (p.out || (b2 && p.out_split)),
+              "s2d_conv_fwd: null argument");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   switch (p.precision) {
     case S2D_PRECISION_FP32:
@@ -224,6 +228,8 @@ extern "C" int s2d_conv_fwd(const s2d_conv_params* params, void* stream) {
     case S2D_PRECISION_TF32_BF16C:
     case S2D_PRECISION_AUTO:
       return conv_fwd_tf32(p, st);
+    case S2D_PRECISION_BF16X2:
+      return conv_fwd_bf2(p, st);
     default:
       set_error("s2d_conv_fwd: unknown precision %d", p.precision);
       return S2D_ERR_INVALID;
@@ -238,5 +244,6 @@ extern "C" int s2d_spconv_fwd(const float* in, int n_in, const float* W, const i
   p.out_rows = nullptr; p.in_ld = Cin; p.out_ld = Cout; p.res_ld = Cout; p.tbl_stride = tbl_stride; p.K = K;
   p.n_in = n_in; p.n_out = n_out; p.Cin = Cin; p.Cout = Cout; p.act = relu ? S2D_ACT_RELU : S2D_ACT_NONE;
   p.res_after_act = 0; p.precision = precision;
+  p.in_split = nullptr; p.out_split = nullptr; p.tile_masks = nullptr; p.in_split_ld = 0; p.out_split_ld = 0;
   return s2d_conv_fwd(&p, stream);
 }

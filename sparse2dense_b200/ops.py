@@ -14,8 +14,9 @@ PRECISION_TF32 = 1
 PRECISION_TF32X3 = 2
 PRECISION_TF32_BF16C = 3      # TF32 main term + BF16 correction terms: TF32X3 accuracy class at 2/3 of the tensor time
 PRECISION_AUTO = 4            # the library picks TF32_BF16C or TF32X3 per layer shape (both fp32-level accuracy)
+PRECISION_BF16X2 = 5          # activations and weights pre-split into BF16 pairs, three BF16 MMAs (conv_bf2.cu): ~4e-6 per layer
 PRECISION_NAMES = {"fp32": PRECISION_FP32, "tf32": PRECISION_TF32, "tf32x3": PRECISION_TF32X3,
-                   "tf32_bf16c": PRECISION_TF32_BF16C, "auto": PRECISION_AUTO}
+                   "tf32_bf16c": PRECISION_TF32_BF16C, "auto": PRECISION_AUTO, "bf16x2": PRECISION_BF16X2}
 
 
 # When set to a list, spconv_fwd appends (key, start_event, end_event) per launch so that bench.py can
@@ -194,10 +195,10 @@ def rulebook_subm(coors, index, ksize=3, dilation=1, count_pairs=False):
     n = coors.shape[0]
     ks, dl = _triple(ksize), _triple(dilation)
     k = ks[0] * ks[1] * ks[2]
-    tbl = torch.empty((k, max(n, 1)), dtype=torch.int32, device=coors.device)
+    tbl = alloc_table(k, n, coors.device)
     pairs = torch.zeros((1,), dtype=torch.int64, device=coors.device) if count_pairs else None
     _lib.check(_lib.load().s2d_rulebook_subm(_ptr(coors), n, index.batch, _lib.ints(index.shape), _lib.ints(ks),
-                                             _lib.ints(dl), _ptr(index.buf), _ptr(tbl), tbl.shape[1], _ptr(pairs),
+                                             _lib.ints(dl), _ptr(index.buf), _ptr(tbl), tbl.stride(0), _ptr(pairs),
                                              _stream()), "s2d_rulebook_subm")
     return (tbl, pairs) if count_pairs else tbl
 
@@ -267,11 +268,11 @@ def rulebook_sparse(out_coors, index_in, ksize, stride, pad, dilation=1, count_p
     n_out = out_coors.shape[0]
     ks, st, pd, dl = _triple(ksize), _triple(stride), _triple(pad), _triple(dilation)
     k = ks[0] * ks[1] * ks[2]
-    tbl = torch.empty((k, max(n_out, 1)), dtype=torch.int32, device=out_coors.device)
+    tbl = alloc_table(k, n_out, out_coors.device)
     pairs = torch.zeros((1,), dtype=torch.int64, device=out_coors.device) if count_pairs else None
     _lib.check(_lib.load().s2d_rulebook_sparse(_ptr(out_coors), n_out, index_in.batch, _lib.ints(index_in.shape),
                                                _lib.ints(ks), _lib.ints(st), _lib.ints(pd), _lib.ints(dl),
-                                               _ptr(index_in.buf), _ptr(tbl), tbl.shape[1], _ptr(pairs), _stream()),
+                                               _ptr(index_in.buf), _ptr(tbl), tbl.stride(0), _ptr(pairs), _stream()),
                "s2d_rulebook_sparse")
     return (tbl, pairs) if count_pairs else tbl
 
@@ -279,12 +280,110 @@ def rulebook_sparse(out_coors, index_in, ksize, stride, pad, dilation=1, count_p
 # ------------------------------------------------------------------------------------------
 # convolution + densify
 # ------------------------------------------------------------------------------------------
+def round_up(n, m):
+    return (int(n) + m - 1) // m * m
+
+
+def alloc_table(k, n, device):
+    """Neighbour table i32 [k, n] whose row stride is a multiple of 128 entries (16 B aligned int4 index loads)."""
+    return torch.empty((k, round_up(max(n, 1), 128)), dtype=torch.int32, device=device)[:, :max(n, 1)]
+
+
+def get_split(t):
+    """The split-row twin of an fp32 row tensor (written by the bf16x2 conv epilogue or rows_split), if still valid."""
+    hit = getattr(t, "_s2d_split", None)
+    if hit is None or hit[1] != t._version or hit[0].shape != t.shape:
+        return None
+    return hit[0]
+
+
+def set_split(t, split):
+    t._s2d_split = (split, t._version)
+
+
+def rows_split(x, cache=True):
+    """fp32 rows [n, C] (stride(1) == 1) -> split rows int32 [n, C]: per 32-channel chunk (or 16-channel row)
+    [hi words | lo words], two BF16 per word (x = hi + lo to 16 mantissa bits) -- the operand format of PRECISION_BF16X2."""
+    _need_cuda(x)
+    hit = get_split(x) if cache else None
+    if hit is not None:
+        return hit
+    assert x.dtype == torch.float32 and x.dim() == 2 and x.stride(1) == 1
+    n, c = x.shape
+    out = torch.empty((n, c), dtype=torch.int32, device=x.device)
+    _lib.check(_lib.load().s2d_rows_split(_ptr(x), n, c, x.stride(0), _ptr(out), out.stride(0), _stream()), "s2d_rows_split")
+    if cache:
+        set_split(x, out)
+    return out
+
+
+def table_tile_masks(tbl, n_rows):
+    """i32 [ceil(n_rows/128)]: bit k set iff some row of the 128-row tile has a neighbour at kernel offset k."""
+    _need_cuda(tbl)
+    masks = torch.empty((max((n_rows + 127) // 128, 1),), dtype=torch.int32, device=tbl.device)
+    _lib.check(_lib.load().s2d_table_tile_masks(_ptr(tbl), tbl.stride(0), tbl.shape[0], n_rows, _ptr(masks), _stream()),
+               "s2d_table_tile_masks")
+    return masks
+
+
+def bf2_ok(cin, cout, tbl):
+    return (cin == 16 or (cin >= 32 and cin % 32 == 0)) and cout % 16 == 0 and tbl.stride(0) % 4 == 0 and \
+        tbl.data_ptr() % 16 == 0 and tbl.shape[0] <= 27
+
+
+def conv_launch(x, w_arg, tbl, n_out, cin, cout, k, scale=None, shift=None, act=0, residual=None, res_after_act=False,
+                out=None, out_rows=None, precision=PRECISION_FP32, x_split=None, out_split=None, tile_masks=None):
+    """One ``s2d_conv_fwd`` call.  x / out / residual / x_split / out_split: 2-D row views with stride(1) == 1 (or None)."""
+    p = _lib.ConvParams()
+    p.in_, p.weights, p.tbl = _ptr(x), _ptr(w_arg), _ptr(tbl)
+    p.scale, p.shift, p.residual = _ptr(scale), _ptr(shift), _ptr(residual)
+    p.out, p.out_rows = _ptr(out), _ptr(out_rows)
+    p.in_ld = 0 if x is None else x.stride(0)
+    p.out_ld = 0 if out is None else out.stride(0)
+    p.res_ld = 0 if residual is None else residual.stride(0)
+    p.tbl_stride, p.K = tbl.stride(0), k
+    p.n_in = (x if x is not None else x_split).shape[0]
+    p.n_out, p.Cin, p.Cout = n_out, cin, cout
+    p.act, p.res_after_act, p.precision = int(act), int(bool(res_after_act)), int(precision)
+    p.in_split, p.out_split, p.tile_masks = _ptr(x_split), _ptr(out_split), _ptr(tile_masks)
+    p.in_split_ld = 0 if x_split is None else x_split.stride(0)
+    p.out_split_ld = 0 if out_split is None else out_split.stride(0)
+    ev = None
+    if KERNEL_EVENTS is not None:
+        ev = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
+        ev[0].record()
+    _lib.check(_lib.load().s2d_conv_fwd(_lib.ctypes.byref(p), _stream()), "s2d_conv_fwd")
+    if ev is not None:
+        ev[1].record()
+        KERNEL_EVENTS.append(((cin, cout, k, residual is not None, p.n_in, n_out, int(precision)), ev[0], ev[1]))
+
+
 def spconv_fwd(feats, weight, tbl, n_out, scale=None, shift=None, residual=None, relu=False,
-               precision=PRECISION_FP32, out=None, packed=None):
+               precision=PRECISION_FP32, out=None, packed=None, tile_masks=None, want_split=True):
     """out[o] = act((sum_k feats[tbl[k][o]] @ W[k]) * scale + shift (+ residual[o])).
 
     weight: [kD,kH,kW,Cin,Cout] (spconv layout) or [K,Cin,Cout], fp32 contiguous.
+    With PRECISION_BF16X2 the input is read in split-row form (the producer's ``out_split`` when ``feats`` carries one,
+    else converted here) and, if ``want_split``, the result carries its own split twin for the next layer.
     """
+    _need_cuda(feats, weight, tbl)
+    if precision == PRECISION_BF16X2:
+        cin, cout = weight.shape[-2], weight.shape[-1]
+        k = weight.numel() // (cin * cout)
+        assert feats.shape[1] == cin and tbl.shape[0] == k and tbl.dtype == torch.int32
+        if not bf2_ok(cin, cout, tbl):
+            raise _lib.S2DError(f"no bf16x2 kernel for Cin={cin} Cout={cout} K={k} tbl stride {tbl.stride(0)}")
+        xs = rows_split(feats)
+        if out is None:
+            out = torch.empty((n_out, cout), dtype=torch.float32, device=feats.device)
+        split_ok = want_split and (cout % 32 == 0 or cout == 16) and out.is_contiguous()
+        out_split = torch.empty((n_out, cout), dtype=torch.int32, device=feats.device) if split_ok else None
+        w_arg = packed if packed is not None else pack_weights_tf32(weight, precision)
+        conv_launch(None, w_arg, tbl, n_out, cin, cout, k, scale, shift, 1 if relu else 0, residual, False, out, None,
+                    precision, xs, out_split, tile_masks)
+        if out_split is not None:
+            set_split(out, out_split)
+        return out
     _need_cuda(feats, weight, tbl)
     assert feats.dtype == torch.float32 and feats.is_contiguous() and weight.is_contiguous()
     cin, cout = weight.shape[-2], weight.shape[-1]

@@ -157,6 +157,10 @@ class SparseConvolution(SparseModule):
         ind = self._indice(x)
         if (bn is not None and bn.training) or (bn is None and self.training and torch.is_grad_enabled()):
             return self._train_forward(x, ind, bn, relu, residual)
+        if torch.is_grad_enabled() and (self.weight.requires_grad and self.training or x.features.requires_grad):
+            # an eval-mode (frozen) BatchNorm inside a training graph would silently cut the gradient here
+            raise NotImplementedError("frozen (eval-mode) BatchNorm inside a training graph is not built "
+                                      "(use torch.no_grad() for inference or bn.train() for training)")
         scale, shift = self._folded(bn, x.features.device)
         n_out = ind.out_indices.shape[0]
         packed = self._packed_weights() if self.precision != ops.PRECISION_FP32 else None

@@ -139,7 +139,9 @@ def distill_losses(student, r, T_preds, F_D_a, F_D_b, example, s2d_weights=(10.0
     kd_reg = (kd_reg * kd_reg.new_tensor(head.code_weights)).sum() * head.weight
     distill = kd_hm + kd_reg + s2d
     pcr = r["mask_loss"] + r["comp_loss"]
-    total = losses["loss"][0] + distill + pcr
+    # trainer.py:799-803 adds the distillation terms to losses['loss'][0]; parse_second_losses then SUMS losses['loss'] over
+    # all tasks, so every task's detection loss reaches backward (single-task Waymo: one entry)
+    total = sum(losses["loss"][1:], losses["loss"][0]) + distill + pcr
     with torch.no_grad():
         t_hm = L.fastfocalloss(rows(T["hm"]), example["hm"][0], ind, mask, cat, out_is_logits=True)
     log = dict(loss=total.detach(), hm_loss=losses["hm_loss"][0], loc_loss=losses["loc_loss"][0].detach(),
@@ -168,6 +170,8 @@ class DistillTrainer:
         self.global_step = 0
         if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
             dist.broadcast(self.opt.flat_p, src=0)               # DDP: every rank starts from rank 0's weights
+            for b in self.student.buffers():                     # ... and buffers (DDP broadcast_buffers: BN running stats)
+                dist.broadcast(b, src=0)
 
     def forward_backward(self, example):
         with torch.no_grad():

@@ -1,0 +1,122 @@
+#!/usr/bin/env python
+"""Per-layer timing of the BF16-pair conv kernel (conv_bf2.cu) vs the TF32 kernel on the real rulebooks of a batch of
+synthetic scenes.  usage: microbench_bf2.py [--batch 4] [--reps 10] [--variants 0,1,2]"""
+import argparse
+import ctypes
+import os
+import sys
+
+import numpy as np
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from sparse2dense_b200 import _lib, ops, spconv, synth  # noqa: E402
+from sparse2dense_b200.backbones import SpMiddleResNetFHD  # noqa: E402
+from sparse2dense_b200.hotpath import concat_clouds  # noqa: E402
+
+
+def timeit(fn, flush, reps):
+    fn()
+    torch.cuda.synchronize()
+    ms = []
+    for _ in range(reps):
+        flush.fill_(0)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(); fn(); e1.record()
+        torch.cuda.synchronize()
+        ms.append(e0.elapsed_time(e1))
+    return float(np.median(ms))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--batch", type=int, default=4)
+    ap.add_argument("--reps", type=int, default=7)
+    ap.add_argument("--variants", default="0,1,2")
+    ap.add_argument("--dense", action="store_true", help="also time dense 3x3 / 1x1 convs of the neck shapes")
+    ap.add_argument("--ablate", default="", help="comma list of ablation flag sets (see conv_bf2.cu B2Args::dbg), timed with variant 0")
+    ap.add_argument("--only", type=int, default=0)
+    args = ap.parse_args()
+    _lib.load()
+    setv = ctypes.CDLL(_lib.LIB_PATH).s2d_debug_bf2_variant
+    clouds = synth.lidar_batch(1, args.batch)
+    pts, offs = concat_clouds(clouds)
+    vb = ops.voxelize(pts.cuda(), offs, synth.WAYMO_VOXEL, synth.WAYMO_RANGE, 5, 150000, want_voxels=False, mean_channels=5)
+    n0 = vb.n
+    bb = SpMiddleResNetFHD(num_input_features=5).cuda().eval()
+    x = spconv.SparseConvTensor(vb.mean_buffer[:n0], vb.coors_buffer[:n0], (41, 1504, 1504), args.batch)
+    plan = spconv.plan_coords(x, [bb.conv2[0], bb.conv3[0], bb.conv4[0], bb.extra_conv[0]])
+    stages = [(x.indices, x.index())] + [(sc.coors, sc.index) for sc in plan]
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
+    print(f"rows per stage: {[int(s[0].shape[0]) for s in stages]}", flush=True)
+    setf = ctypes.CDLL(_lib.LIB_PATH).s2d_debug_bf2_flags
+    for si, c in enumerate([16, 32, 64, 128]):
+        if args.only and c != args.only:
+            continue
+        coors, index = stages[si]
+        n = coors.shape[0]
+        tbl, pairs = ops.rulebook_subm(coors, index, 3, count_pairs=True)
+        p = int(pairs.item())
+        masks = ops.table_tile_masks(tbl, n)
+        live = float(sum(bin(int(m) & 0x7ffffff).count("1") for m in masks.cpu().tolist())) / (27 * masks.numel())
+        feats = torch.relu(torch.randn(n, c, device="cuda"))
+        w = torch.randn(3, 3, 3, c, c, device="cuda") / (27 * c) ** 0.5
+        ref = ops.spconv_fwd(feats, w, tbl, n, precision=ops.PRECISION_TF32X3)
+        old = ops.PRECISION_TF32_BF16C if c == 128 else ops.PRECISION_TF32X3
+        pk_old = ops.pack_weights_tf32(w, old)
+        out = torch.empty(n, c, device="cuda")
+        t_old = timeit(lambda: ops.spconv_fwd(feats, w, tbl, n, precision=old, packed=pk_old, out=out), flush, args.reps)
+        pk = ops.pack_weights_tf32(w, ops.PRECISION_BF16X2)
+        xs = ops.rows_split(feats)
+        t_split = timeit(lambda: ops.rows_split(feats, cache=False), flush, args.reps)
+        line = f"subm {c:3d} N={n:7d} P={p:8d} pairs/27N={p / (27.0 * n):.3f} tile-tap live={live:.3f} | v5 {t_old:.3f} ms | split {t_split:.3f} ms"
+        for v in [int(s) for s in args.variants.split(",")]:
+            setv(v)
+            for use_masks in (False, True):
+                o2 = ops.spconv_fwd(feats, w, tbl, n, precision=ops.PRECISION_BF16X2, packed=pk,
+                                    tile_masks=masks if use_masks else None)
+                err = float((o2 - ref).abs().max() / ref.abs().max())
+                t = timeit(lambda: ops.spconv_fwd(feats, w, tbl, n, precision=ops.PRECISION_BF16X2, packed=pk, out=out,
+                                                  tile_masks=masks if use_masks else None), flush, args.reps)
+                line += f" | v{v}{'m' if use_masks else ' '} {t:.3f} ms (err {err:.1e})"
+        setv(0)
+        print(line, flush=True)
+        if args.ablate:
+            line = f"   ablate {c:3d}:"
+            for fl in [int(v) for v in args.ablate.split(",")]:
+                setf(fl)
+                t = timeit(lambda: ops.spconv_fwd(feats, w, tbl, n, precision=ops.PRECISION_BF16X2, packed=pk, out=out), flush, args.reps)
+                line += f" f{fl}={t:.3f}"
+            setf(0)
+            print(line, flush=True)
+    if args.dense:
+        from sparse2dense_b200 import dense
+        B = args.batch
+        for (H, cin, cout, k) in [(188, 256, 128, 3), (188, 128, 128, 3), (94, 256, 256, 3), (47, 256, 1024, 1), (47, 1024, 256, 1),
+                                  (188, 512, 64, 3), (188, 64, 320, 3)]:
+            tbl, Ho, Wo = dense.conv_table(torch.device("cuda"), B, H, H, k, 1, k // 2)
+            n = B * H * H
+            x = torch.relu(torch.randn(n, cin, device="cuda"))
+            w = torch.randn(k * k, cin, cout, device="cuda") / (k * k * cin) ** 0.5
+            out = torch.empty(n, cout, device="cuda")
+            old = ops.PRECISION_TF32_BF16C if cout % 128 == 0 else ops.PRECISION_TF32X3
+            pk_old = ops.pack_weights_tf32(w, old)
+            ref = dense.conv_rows(x, w, tbl, n, precision=ops.PRECISION_TF32X3)
+            t_old = timeit(lambda: dense.conv_rows(x, w, tbl, n, out=out, precision=old, packed=pk_old), flush, args.reps)
+            pk = ops.pack_weights_tf32(w, ops.PRECISION_BF16X2)
+            xs = ops.rows_split(x)
+            line = f"dense {H}x{H} {cin}->{cout} k{k} | v5 {t_old:.3f} ms"
+            for v in [int(s) for s in args.variants.split(",")]:
+                setv(v)
+                ops.conv_launch(None, pk, tbl, n, cin, cout, k * k, out=out, precision=ops.PRECISION_BF16X2, x_split=xs)
+                err = float((out - ref).abs().max() / ref.abs().max())
+                t = timeit(lambda: ops.conv_launch(None, pk, tbl, n, cin, cout, k * k, out=out, precision=ops.PRECISION_BF16X2,
+                                                   x_split=xs), flush, args.reps)
+                fl = 2.0 * n * k * k * cin * cout / (t * 1e-3) / 1e12
+                line += f" | v{v} {t:.3f} ms {fl:.0f} TF/s (err {err:.1e})"
+            setv(0)
+            print(line, flush=True)
+
+
+if __name__ == "__main__":
+    main()
