@@ -35,11 +35,13 @@
 namespace s2d {
 
 constexpr int kB2ProducerWarps = 8;
-constexpr int kB2LoaderWarp = 8;
+constexpr int kB2UtilWarp = 8;
 constexpr int kB2MmaWarp = 9;
-constexpr int kB2Threads = 32 * 10;
-constexpr int kB2MaxSteps = 2048;          // (offset steps) x (chunks) x (tiles) of one CTA; host-checked
+constexpr int kB2EpiWarp0 = 10;            // four epilogue warps; warp w reads TMEM lanes [32 (w % 4), +32)
+constexpr int kB2Threads = 32 * 14;
+constexpr int kB2ListCap = 1024;           // (offset steps) x (chunks) x (tiles) of one tile group; host-checked
 constexpr int kB2AStage = kBM * 128;       // 128 rows x 128 B
+constexpr int kB2EpiRow = 144;             // staged accumulator row: 128 B + 16 B pad (conflict-free 16 B accesses)
 
 // D[tmem] (+)= A[smem] * B[smem], BF16 inputs, fp32 accumulate
 __device__ __forceinline__ void umma_bf16_ss(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc,
@@ -51,23 +53,28 @@ __device__ __forceinline__ void umma_bf16_ss(uint32_t tmem_d, uint64_t desc_a, u
       "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
       : "memory");
 }
+__device__ __forceinline__ void sts128(uint32_t addr, float a, float b, float c, float d) {
+  asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+}
 
 template <int COUT, int T_, int SA_, int SB_>
 struct B2Cfg {
   static constexpr int T = T_, SA = SA_, SB = SB_;
   static constexpr int B_STAGE = COUT * 128;                   // COUT rows x [w1 (64 B) | w2 (64 B)]
   static constexpr int ACC_STRIDE = COUT < 32 ? 32 : COUT;
-  static constexpr int ACC_COLS = T * ACC_STRIDE;
+  static constexpr int ACC_BUF = T * ACC_STRIDE;               // one accumulator set (T tiles)
+  static constexpr int ACC_COLS = 2 * ACC_BUF;                 // double buffered: the epilogue of a group runs under the next
   static constexpr int TMEM_COLS = ACC_COLS <= 32 ? 32 : ACC_COLS <= 64 ? 64 : ACC_COLS <= 128 ? 128 : ACC_COLS <= 256 ? 256 : 512;
   static constexpr int EPC = COUT < 32 ? COUT : 32;
-  static constexpr int STEP_BYTES = kB2MaxSteps * 2;
-  static constexpr int BAR_BYTES = 256;
-  static constexpr int SMEM_BYTES = SA * kB2AStage + SB * B_STAGE + STEP_BYTES + BAR_BYTES + 1024;
-  static constexpr int OCC = (2 * (SMEM_BYTES + 1024) <= 227 * 1024 + 1024 && 2 * TMEM_COLS <= 512) ? 2 : 1;
+  static constexpr int LIST_BYTES = 2 * kB2ListCap * 2;
+  static constexpr int EPI_BYTES = 4 * 32 * kB2EpiRow;
+  static constexpr int BAR_BYTES = 512;
+  static constexpr int SMEM_BYTES = SA * kB2AStage + SB * B_STAGE + LIST_BYTES + EPI_BYTES + kB2ProducerWarps * 1024 + BAR_BYTES + 1024;
+  static_assert(SA == kB2ProducerWarps, "producer warp w owns stage w");
   static_assert(ACC_COLS <= 512, "TMEM budget");
   static_assert(SMEM_BYTES <= 227 * 1024, "shared memory budget");
   static_assert(COUT % 16 == 0 && COUT >= 16 && COUT <= 128, "UMMA N constraint for M = 128");
-  static_assert(2 * SA + 2 * SB + 1 <= BAR_BYTES / 8 - 2, "barrier block");
+  static_assert(2 * SA + 2 * SB + 8 <= BAR_BYTES / 8 - 2, "barrier block");
 };
 
 struct B2Args {
@@ -82,7 +89,8 @@ struct B2Args {
   uint32_t* out_split;       // split rows or null
   const int* out_rows;
   int in_ld, out_ld, res_ld, split_ld, tbl_stride, n_out, K, nchunk, kps, ksteps, act, res_after_act;
-  int tile_unit, unit_base, unit_rem, n_tiles;
+  int n_tiles, n_groups;     // 128-row tiles; groups of T consecutive tiles (the unit a CTA works on)
+  long long* prof;   // optional [gridDim.x][16] cycle counters (tools/microbench_bf2.py --prof), null in production
   int dbg;   // ablation switches (tools/microbench_bf2.py): 1 no gather, 2 no MMA, 4 no weight copies, 8 no stores, 16 all rows missing
 };
 
@@ -102,251 +110,272 @@ __device__ __forceinline__ void split_pair(float a, float b, uint32_t& hi, uint3
   lo = *reinterpret_cast<const uint32_t*>(&l);
 }
 
+// Persistent CTA (one per SM): group j of this CTA is tile group blockIdx.x + j * gridDim.x.  Per group the utility warp
+// writes a step list (double buffered), the producers / MMA issuer walk it, and the four epilogue warps drain the
+// group's accumulators from the other TMEM buffer while the next group is already being gathered and multiplied.
 template <int COUT, int T, int SA, int SB>
-__global__ void __launch_bounds__(kB2Threads, B2Cfg<COUT, T, SA, SB>::OCC)
-conv_bf2_kernel(const __grid_constant__ B2Args A) {
+__global__ void __launch_bounds__(kB2Threads, 1) conv_bf2_kernel(const __grid_constant__ B2Args A) {
   using Cfg = B2Cfg<COUT, T, SA, SB>;
   constexpr int B_STAGE = Cfg::B_STAGE;
   const int NCHUNK = A.nchunk, K = A.K, KS = A.ksteps, kps = A.kps, n_out = A.n_out;
   const int cblk = blockIdx.y * COUT;
+  const int n_groups = A.n_groups, gstep = (int)gridDim.x;
 
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* a_ring = smem;                                        // SA x [128 rows x 128 B], 128B-swizzled
   uint8_t* b_ring = a_ring + SA * kB2AStage;                     // SB x [COUT rows x 128 B], 128B-swizzled
-  uint16_t* steps = reinterpret_cast<uint16_t*>(b_ring + SB * B_STAGE);
-  uint64_t* bars = reinterpret_cast<uint64_t*>(reinterpret_cast<uint8_t*>(steps) + Cfg::STEP_BYTES);
+  uint8_t* lists = b_ring + SB * B_STAGE;                        // 2 x kB2ListCap u16 step entries
+  uint8_t* epi = lists + Cfg::LIST_BYTES;                        // 4 warps x [32 rows x 144 B]
+  uint8_t* idx_scratch = epi + Cfg::EPI_BYTES;                   // 8 producer warps x 1 KB
+  uint64_t* bars = reinterpret_cast<uint64_t*>(idx_scratch + kB2ProducerWarps * 1024);
   uint64_t* bar_a_full = bars;
   uint64_t* bar_a_empty = bar_a_full + SA;
   uint64_t* bar_b_full = bar_a_empty + SA;
   uint64_t* bar_b_empty = bar_b_full + SB;
-  uint64_t* bar_accum = bar_b_empty + SB;
-  uint32_t* s_tmem = reinterpret_cast<uint32_t*>(bar_accum + 1);
-  uint32_t* s_nsteps = s_tmem + 1;
+  uint64_t* bar_list_full = bar_b_empty + SB;                    // [2]
+  uint64_t* bar_list_empty = bar_list_full + 2;                  // [2]
+  uint64_t* bar_acc_full = bar_list_empty + 2;                   // [2]
+  uint64_t* bar_acc_empty = bar_acc_full + 2;                    // [2]
+  uint32_t* s_tmem = reinterpret_cast<uint32_t*>(bar_acc_empty + 2);
+  uint32_t* s_nsteps = s_tmem + 1;                               // [2]
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int bx = (int)blockIdx.x;
-  const int t_alloc = (A.unit_base + (bx < A.unit_rem ? 1 : 0)) * A.tile_unit;
-  const int tile_first = (bx * A.unit_base + min(bx, A.unit_rem)) * A.tile_unit;
-  if (t_alloc == 0 || tile_first >= A.n_tiles) return;
-  const int Tr = min(t_alloc, A.n_tiles - tile_first);
-  const int tile0 = tile_first * kBM;
-  const int row_end = min(n_out, tile0 + Tr * kBM);
+  if ((int)blockIdx.x >= n_groups) return;
 
   if (warp == kB2MmaWarp && lane == 0) {
     for (int s = 0; s < SA; ++s) {
-      mbar_init(smem_u32(bar_a_full + s), kB2ProducerWarps * 32);   // every producer lane: cp.async.mbarrier.arrive.noinc
+      mbar_init(smem_u32(bar_a_full + s), 1);                     // the producer warp that owns the stage
       mbar_init(smem_u32(bar_a_empty + s), 1);                    // one tcgen05.commit
     }
     for (int s = 0; s < SB; ++s) {
       mbar_init(smem_u32(bar_b_full + s), 1);                     // arrive.expect_tx of the loader
       mbar_init(smem_u32(bar_b_empty + s), 1);                    // one tcgen05.commit after the last tile of the stage
     }
-    mbar_init(smem_u32(bar_accum), 1);
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(smem_u32(bar_list_full + s), 1);                  // utility warp, after writing the list
+      mbar_init(smem_u32(bar_list_empty + s), kB2ProducerWarps + 1);   // producer warps + MMA issuer done reading it
+      mbar_init(smem_u32(bar_acc_full + s), 1);                   // tcgen05.commit after the group's last MMA
+      mbar_init(smem_u32(bar_acc_empty + s), 4);                  // the four epilogue warps
+    }
     fence_barrier_init();
   }
-  if (warp == kB2LoaderWarp) {
-    tmem_alloc(smem_u32(s_tmem), Cfg::TMEM_COLS);
-    // ---- step list: lane = offset step kk; entries ordered (kk, chunk, tile), tiles without a neighbour at kk skipped ----
-    // entry = kk | chunk << 5 | tile << 10 | first-of-(kk,chunk) << 12 | last-of-(kk,chunk) << 13
-    uint32_t nib = 0;
-    uint32_t tmask[T];
-#pragma unroll
-    for (int t = 0; t < T; ++t)                                   // all loads in flight together
-      tmask[t] = (A.tile_masks && t < Tr) ? (uint32_t)__ldg(A.tile_masks + tile_first + t) : 0xffffffffu;
-    if (lane < KS) {
-#pragma unroll
-      for (int t = 0; t < T; ++t) {
-        if (t >= Tr) break;
-        uint32_t m = tmask[t];
-        m &= K >= 32 ? 0xffffffffu : ((1u << K) - 1u);
-        if (m == 0) m = 1;                                        // a tile always runs at least one step (zero rows)
-        const uint32_t live = kps == 1 ? (m >> lane) & 1u : ((m >> (2 * lane)) & 3u) != 0;
-        nib |= live << t;
-      }
-    }
-    const int cnt = NCHUNK * __popc(nib);
-    const int off = warp_inclusive_scan(cnt) - cnt;
-    int w = off;
-    if (nib) {
-      const int t_first = __ffs(nib) - 1, t_last = 31 - __clz(nib);
-      for (int c = 0; c < NCHUNK; ++c)
-        for (int t = t_first; t <= t_last; ++t)
-          if ((nib >> t) & 1u) {
-            if (w < kB2MaxSteps)
-              steps[w] = (uint16_t)(lane | (c << 5) | (t << 10) | ((t == t_first) << 12) | ((t == t_last) << 13));
-            ++w;
-          }
-    }
-    const int total = __shfl_sync(0xffffffffu, off + cnt, 31);
-    if (lane == 0) *s_nsteps = (uint32_t)min(total, kB2MaxSteps);
-  }
+  if (warp == kB2UtilWarp) tmem_alloc(smem_u32(s_tmem), Cfg::TMEM_COLS);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *s_tmem;
-  const int nsteps = (int)*s_nsteps;
+  const uint32_t lists0 = smem_u32(lists);
 
   if (warp < kB2ProducerWarps) {
-    // ===================== producers: warp w gathers rows [16w, 16w + 16) of every step =====================
-    const int o = lane >> 3, c8 = lane & 7;                  // lane = (row quad, 16 B piece of the 128 B operand row)
-    const int rbase = 16 * warp + 4 * o;                     // this lane's rows inside a tile: rbase .. rbase + 3
+    // ===================== producers: warp w gathers every 8th step (all 128 rows) into stage w =====================
+    // A warp's iteration is a serial chain of ~100 dependent instructions plus the latency of its own copies, so the
+    // steps are dealt over the warps instead of splitting every step over all of them: eight steps are in flight, one
+    // mbarrier arrival publishes a stage, and the per-step rate is set by the LSU, not by one warp's instruction latency.
+    //   lane = (o = lane >> 3, c8 = lane & 7): copy r (0..31) moves piece c8 of row 4r + o.
+    const int o = lane >> 3, c8 = lane & 7;
     const int sub = kps == 2 ? (c8 >> 2) : 0;                // Cin = 16: pieces 0-3 come from offset 2kk, 4-7 from 2kk + 1
     const uint32_t piece = (uint32_t)(kps == 2 ? (c8 & 3) : c8) * 16u;
-    const uint32_t dst_lane = (uint32_t)rbase * 128u + (uint32_t)((c8 ^ (4 * (o & 1))) << 4);   // (rbase + i) & 7 = 4(o&1) + i
     const char* in_bytes = reinterpret_cast<const char*>(A.in);
     const uint32_t row_bytes = (uint32_t)A.in_ld * 4u;
     const int* tbl = A.tbl;
     const int tbl_stride = A.tbl_stride;
-    const uint32_t a_ring0 = smem_u32(a_ring);
-    const uint32_t bar_full0 = smem_u32(bar_a_full), bar_empty0 = smem_u32(bar_a_empty);
-
-    // Step entries and neighbour indices run three steps ahead of the copies in registers.  The entries are read with
-    // ld.shared (a generic load of the list would queue behind the global traffic), the indices raw: rows past the end
-    // of the tensor are masked at use, so nothing depends on the index load until the step is issued.
-    const uint32_t steps0 = smem_u32(steps);
-    auto load_entry = [&](int i) -> uint32_t { return i < nsteps ? lds_u16(steps0 + 2u * (uint32_t)i) : 0xffffffffu; };
-    auto load_idx = [&](uint32_t e) -> int4 {
-      int4 v = make_int4(-1, -1, -1, -1);
-      if (e != 0xffffffffu && !(A.dbg & 64)) {
-        const int k = (int)(e & 31u) * kps + sub;
-        const int row0 = tile0 + (int)((e >> 10) & 3u) * kBM + rbase;
-        if (k < K && row0 < row_end) v = __ldg(reinterpret_cast<const int4*>(tbl + (size_t)k * tbl_stride + row0));
+    const uint32_t a_stage = smem_u32(a_ring) + (uint32_t)warp * kB2AStage;
+    const uint32_t bar_full = smem_u32(bar_a_full + warp), bar_empty = smem_u32(bar_a_empty + warp);
+    // index scratch of this warp: [2 offsets][4 row residues o][32 copies r] -> idx of row 4r + o, read back as int4 over r
+    const uint32_t scr = smem_u32(idx_scratch) + (uint32_t)warp * 1024u;
+    const uint32_t scr_rd = scr + (uint32_t)sub * 512u + (uint32_t)o * 128u;
+    const uint32_t dst_lane = (uint32_t)o * 128u;            // row 4r + o: byte (4r + o) * 128, swizzle ((4r + o) & 7) ^ c8
+    uint32_t phase = 1;                                      // first use of the stage: free
+    int gbase = 0;                                           // steps of this CTA before the current group
+    long long pw_empty = 0, pw_data = 0, pw_list = 0, p_steps = 0;
+    const bool prof = A.prof != nullptr;
+    const long long p_t0 = prof ? clock64() : 0;
+    int j = 0;
+#pragma unroll 1
+    for (int g = (int)blockIdx.x; g < n_groups; g += gstep, ++j) {
+      const int buf = j & 1;
+      long long c0 = prof ? clock64() : 0;
+      mbar_wait(smem_u32(bar_list_full + buf), (uint32_t)(j >> 1) & 1u);
+      if (prof) pw_list += clock64() - c0;
+      const int nsteps = (int)s_nsteps[buf];
+      const uint32_t steps0 = lists0 + (uint32_t)buf * (kB2ListCap * 2);
+      const int tile0 = g * T * kBM;
+      const int row_end = min(n_out, tile0 + T * kBM);
+      // this lane's four consecutive rows 4 lane .. 4 lane + 3 of the step's tile, one int4 per offset of the step
+      auto load_idx = [&](uint32_t e, int s2) -> int4 {
+        int4 v = make_int4(-1, -1, -1, -1);
+        const int k = (int)(e & 31u) * kps + s2;
+        const int row0 = tile0 + (int)((e >> 10) & 3u) * kBM + 4 * lane;
+        if (k < K && row0 < row_end && !(A.dbg & 64)) {
+          v = __ldg(reinterpret_cast<const int4*>(tbl + (size_t)k * tbl_stride + row0));
+          const int lim = row_end - row0;
+          if (lim < 4) { if (lim < 2) v.y = -1; if (lim < 3) v.z = -1; v.w = -1; }
+        }
+        return v;
+      };
+      int i = (warp - gbase) & 7;                            // first step of this group with (gbase + i) % 8 == warp
+      uint32_t e = 0;
+      int4 qa = make_int4(-1, -1, -1, -1), qb = qa;
+      if (i < nsteps) {
+        e = lds_u16(steps0 + 2u * (uint32_t)i);
+        qa = load_idx(e, 0);
+        if (kps == 2) qb = load_idx(e, 1);
       }
-      return v;
-    };
-
-    uint32_t e0 = load_entry(0), e1 = load_entry(1), e2 = load_entry(2);
-    int4 q0 = load_idx(e0), q1 = load_idx(e1), q2 = load_idx(e2);
-    int stage = 0;
-    uint32_t phase = 1;                                      // first pass over the ring: stages are free
 #pragma unroll 1
-    for (int i = 0; i < nsteps; ++i) {
-      int4 cur = q0;
-      const uint32_t e = e0;
-      e0 = e1; e1 = e2; e2 = load_entry(i + 3);
-      q0 = q1; q1 = q2; q2 = load_idx(e2);
-      const uint32_t cbytes = (kps == 2 ? 0u : ((e >> 5) & 31u) * 128u) + piece;
-      const int lim = row_end - (tile0 + (int)((e >> 10) & 3u) * kBM + rbase);   // rows of this quad inside the tensor
-      if (lim < 4) { if (lim < 2) cur.y = -1; if (lim < 3) cur.z = -1; cur.w = -1; }
-      mbar_wait(bar_empty0 + 8 * stage, phase);
-      const uint32_t dst0 = a_ring0 + (uint32_t)stage * kB2AStage + dst_lane;
-      const int idx[4] = {cur.x, cur.y, cur.z, cur.w};
+      for (; i < nsteps; i += 8) {
+        // indices -> scratch, transposed so that the copies of row residue o read four consecutive r with one LDS.128
+        asm volatile("st.shared.b32 [%0], %1;" ::"r"(scr + 4u * lane), "r"(qa.x) : "memory");
+        asm volatile("st.shared.b32 [%0], %1;" ::"r"(scr + 128u + 4u * lane), "r"(qa.y) : "memory");
+        asm volatile("st.shared.b32 [%0], %1;" ::"r"(scr + 256u + 4u * lane), "r"(qa.z) : "memory");
+        asm volatile("st.shared.b32 [%0], %1;" ::"r"(scr + 384u + 4u * lane), "r"(qa.w) : "memory");
+        if (kps == 2) {
+          asm volatile("st.shared.b32 [%0], %1;" ::"r"(scr + 512u + 4u * lane), "r"(qb.x) : "memory");
+          asm volatile("st.shared.b32 [%0], %1;" ::"r"(scr + 640u + 4u * lane), "r"(qb.y) : "memory");
+          asm volatile("st.shared.b32 [%0], %1;" ::"r"(scr + 768u + 4u * lane), "r"(qb.z) : "memory");
+          asm volatile("st.shared.b32 [%0], %1;" ::"r"(scr + 896u + 4u * lane), "r"(qb.w) : "memory");
+        }
+        const uint32_t cbytes = (kps == 2 ? 0u : ((e >> 5) & 31u) * 128u) + piece;
+        // prefetch the entry and the indices of this warp's next step (eight steps ahead)
+        uint32_t e_n = 0;
+        int4 qa_n = make_int4(-1, -1, -1, -1), qb_n = qa_n;
+        if (i + 8 < nsteps) {
+          e_n = lds_u16(steps0 + 2u * (uint32_t)(i + 8));
+          qa_n = load_idx(e_n, 0);
+          if (kps == 2) qb_n = load_idx(e_n, 1);
+        }
+        __syncwarp();
+        c0 = prof ? clock64() : 0;
+        mbar_wait(bar_empty, phase);
+        if (prof) { pw_empty += clock64() - c0; ++p_steps; }
+        phase ^= 1;
 #pragma unroll
-      for (int r = 0; r < 4; ++r) {
-        if (A.dbg & 1) break;
-        const uint32_t off = (uint32_t)max(idx[r], 0) * row_bytes + cbytes;
-        cp_async16_zfill((dst0 + (uint32_t)r * 128u) ^ ((uint32_t)r << 4), in_bytes + off,
-                         (idx[r] >= 0 && !(A.dbg & 16)) ? 16u : 0u);
-      }
-      // the stage's full barrier gets this thread's arrival when its copies have landed (no wait in the producer)
-      cp_async_mbar_arrive_noinc(bar_full0 + 8 * stage);
-      if (++stage == SA) { stage = 0; phase ^= 1; }
-    }
-
-    // ===================== epilogue (same 8 warps) =====================
-    // TMEM lane == row inside a tile; warp w may touch lanes [32*(w%4), +32); warps 0-3 take even tiles, 4-7 odd ones
-    mbar_wait(smem_u32(bar_accum), 0);
-    tc_fence_after();
-    const int g = warp & 3;
-    const float* __restrict__ scale = A.scale ? A.scale + cblk : nullptr;
-    const float* __restrict__ shift = A.shift ? A.shift + cblk : nullptr;
-    const int act = A.act, res_after = A.res_after_act;
-    constexpr int EPC = Cfg::EPC;
-#pragma unroll 1
-    for (int t = warp >> 2; t < Tr; t += 2) {
-      if (A.dbg & 128) break;
-      const int row = tile0 + t * kBM + g * 32 + lane;
-      const int orow = (row < row_end && A.out_rows) ? __ldg(A.out_rows + row) : row;
-#pragma unroll 1
-      for (int c0 = 0; c0 < COUT; c0 += EPC) {
-        uint32_t acc[EPC];
-        tmem_ld<EPC>(tmem_base + ((uint32_t)(g * 32) << 16) + (uint32_t)(t * Cfg::ACC_STRIDE + c0), acc);
-        if (row < row_end && !(A.dbg & 8)) {
-          const float* res = A.residual ? A.residual + (size_t)orow * A.res_ld + cblk + c0 : nullptr;
-          float y[EPC];
+        for (int q = 0; q < 8; ++q) {
+          if (A.dbg & 1) break;
+          const int4 ii = lds128i(scr_rd + 16u * q);
+          const int idx[4] = {ii.x, ii.y, ii.z, ii.w};
 #pragma unroll
-          for (int q = 0; q < EPC / 4; ++q) {
-            float4 v;
-            v.x = __uint_as_float(acc[4 * q + 0]); v.y = __uint_as_float(acc[4 * q + 1]);
-            v.z = __uint_as_float(acc[4 * q + 2]); v.w = __uint_as_float(acc[4 * q + 3]);
-            if (scale) {
-              const float4 sc = __ldg(reinterpret_cast<const float4*>(scale + c0) + q);
-              v.x *= sc.x; v.y *= sc.y; v.z *= sc.z; v.w *= sc.w;
-            }
-            if (shift) {
-              const float4 sh = __ldg(reinterpret_cast<const float4*>(shift + c0) + q);
-              v.x += sh.x; v.y += sh.y; v.z += sh.z; v.w += sh.w;
-            }
-            float4 rr = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (res) rr = __ldg(reinterpret_cast<const float4*>(res) + q);
-            if (!res_after) { v.x += rr.x; v.y += rr.y; v.z += rr.z; v.w += rr.w; }
-            v.x = b2_act(v.x, act); v.y = b2_act(v.y, act); v.z = b2_act(v.z, act); v.w = b2_act(v.w, act);
-            if (res_after) { v.x += rr.x; v.y += rr.y; v.z += rr.z; v.w += rr.w; }
-            y[4 * q + 0] = v.x; y[4 * q + 1] = v.y; y[4 * q + 2] = v.z; y[4 * q + 3] = v.w;
-          }
-          if (A.out) {
-            float4* dst = reinterpret_cast<float4*>(A.out + (size_t)orow * A.out_ld + cblk + c0);
-#pragma unroll
-            for (int q = 0; q < EPC / 4; ++q) dst[q] = make_float4(y[4 * q], y[4 * q + 1], y[4 * q + 2], y[4 * q + 3]);
-          }
-          if (A.out_split) {
-            // split row: per chunk of EPC channels [EPC/2 words hi | EPC/2 words lo]
-            uint32_t hi[EPC / 2], lo[EPC / 2];
-#pragma unroll
-            for (int q = 0; q < EPC / 2; ++q) split_pair(y[2 * q], y[2 * q + 1], hi[q], lo[q]);
-            uint4* dst = reinterpret_cast<uint4*>(A.out_split + (size_t)orow * A.split_ld + cblk + c0);
-#pragma unroll
-            for (int q = 0; q < EPC / 8; ++q) {
-              dst[q] = make_uint4(hi[4 * q], hi[4 * q + 1], hi[4 * q + 2], hi[4 * q + 3]);
-              dst[EPC / 8 + q] = make_uint4(lo[4 * q], lo[4 * q + 1], lo[4 * q + 2], lo[4 * q + 3]);
-            }
+          for (int rr = 0; rr < 4; ++rr) {
+            const int r = 4 * q + rr;                        // row 4r + o; (4r + o) & 7 = 4 (r & 1) + o
+            const uint32_t dst = a_stage + (uint32_t)r * 512u + dst_lane + (uint32_t)((c8 ^ (4 * (r & 1) + o)) << 4);
+            const uint32_t off = (uint32_t)max(idx[rr], 0) * row_bytes + cbytes;
+            cp_async16_zfill(dst, in_bytes + off, (idx[rr] >= 0 && !(A.dbg & 16)) ? 16u : 0u);
           }
         }
+        cp_async_commit();
+        c0 = prof ? clock64() : 0;
+        cp_async_wait<0>();                                  // this lane's pieces have landed ...
+        if (prof) pw_data += clock64() - c0;
+        fence_proxy_async();                                 // ... and are visible to the tensor core (async proxy)
+        __syncwarp();
+        if (lane == 0) mbar_arrive(bar_full);
+        e = e_n; qa = qa_n; qb = qb_n;
       }
+      gbase += nsteps;
+      __syncwarp();                                          // every lane has read its last list entry
+      if (lane == 0) mbar_arrive(smem_u32(bar_list_empty + buf));
     }
-  } else if (warp == kB2LoaderWarp) {
-    // ===================== weight tiles: one bulk copy per live (offset step, chunk) =====================
-    // All lanes: pull the neighbour-table lines of the steps kIdxAhead ahead into L2 (the table is 27 x 4 B per row,
+    if (prof && warp == 0 && lane == 0) {
+      long long* o = A.prof + (size_t)blockIdx.x * 16;
+      o[0] = clock64() - p_t0; o[1] = pw_empty; o[2] = pw_data; o[3] = pw_list; o[4] = p_steps;
+    }
+  } else if (warp == kB2UtilWarp) {
+    // ===================== utility warp: step lists, weight tiles, index prefetch =====================
+    // Step list of a group: lane = offset step kk; entries ordered (kk, chunk, tile), tiles without a neighbour at kk
+    // skipped.  entry = kk | chunk << 5 | tile << 10 | first-of-(kk,chunk) << 12 | last-of-(kk,chunk) << 13
+    auto build_list = [&](int g, int jj) {
+      const int buf = jj & 1;
+      mbar_wait(smem_u32(bar_list_empty + buf), ((uint32_t)(jj >> 1) & 1u) ^ 1u);
+      const int tile_first = g * T;
+      const int Tr = min(T, A.n_tiles - tile_first);
+      uint16_t* steps = reinterpret_cast<uint16_t*>(lists) + buf * kB2ListCap;
+      uint32_t tmask[T];
+#pragma unroll
+      for (int t = 0; t < T; ++t)                                   // all loads in flight together
+        tmask[t] = (A.tile_masks && t < Tr) ? (uint32_t)__ldg(A.tile_masks + tile_first + t) : 0xffffffffu;
+      uint32_t nib = 0;
+      if (lane < KS) {
+#pragma unroll
+        for (int t = 0; t < T; ++t) {
+          if (t >= Tr) break;
+          uint32_t m = tmask[t];
+          m &= K >= 32 ? 0xffffffffu : ((1u << K) - 1u);
+          if (m == 0) m = 1;                                        // a tile always runs at least one step (zero rows)
+          const uint32_t live = kps == 1 ? (m >> lane) & 1u : ((m >> (2 * lane)) & 3u) != 0;
+          nib |= live << t;
+        }
+      }
+      const int cnt = NCHUNK * __popc(nib);
+      const int off = warp_inclusive_scan(cnt) - cnt;
+      int w = off;
+      if (nib) {
+        const int t_first = __ffs(nib) - 1, t_last = 31 - __clz(nib);
+        for (int c = 0; c < NCHUNK; ++c)
+          for (int t = t_first; t <= t_last; ++t)
+            if ((nib >> t) & 1u) {
+              if (w < kB2ListCap)
+                steps[w] = (uint16_t)(lane | (c << 5) | (t << 10) | ((t == t_first) << 12) | ((t == t_last) << 13));
+              ++w;
+            }
+      }
+      const int total = __shfl_sync(0xffffffffu, off + cnt, 31);
+      if (lane == 0) s_nsteps[buf] = (uint32_t)min(total, kB2ListCap);
+      __syncwarp();
+      if (lane == 0) mbar_arrive(smem_u32(bar_list_full + buf));
+    };
+    // All lanes pull the neighbour-table lines of the steps kIdxAhead ahead into L2 (the table is 27 x 4 B per row,
     // larger than the feature maps, and streams from DRAM; the producers' index loads then hit L2 and their
     // three-step register prefetch covers the latency).  Lane 0 also feeds the weight ring.
     constexpr int kIdxAhead = 24;
     const uint8_t* packed = reinterpret_cast<const uint8_t*>(A.packed) + (size_t)blockIdx.y * KS * NCHUNK * B_STAGE;
-    const uint32_t steps0 = smem_u32(steps);
     const int* tbl = A.tbl;
     const int tbl_stride = A.tbl_stride;
-    auto prefetch_idx = [&](int i) {
-      if (i >= nsteps || lane >= 4 * kps || (A.dbg & 64)) return;
-      const uint32_t e = lds_u16(steps0 + 2u * (uint32_t)i);
-      if (((e >> 5) & 31u) != 0u) return;                      // all chunks of an (offset, tile) use the same indices
-      const int k = (int)(e & 31u) * kps + (lane >> 2);
-      const int row = tile0 + (int)((e >> 10) & 3u) * kBM + 32 * (lane & 3);     // 128 rows x 4 B = four 128 B lines
-      if (k < K && row < row_end) asm volatile("prefetch.global.L2 [%0];" ::"l"(tbl + (size_t)k * tbl_stride + row));
-    };
-    for (int i = 0; i < kIdxAhead; ++i) prefetch_idx(i);
     int bs = 0;
-    uint32_t phase = 1;
-    for (int i = 0; i < nsteps; ++i) {
-      prefetch_idx(i + kIdxAhead);
-      const uint32_t e = lds_u16(steps0 + 2u * (uint32_t)i);
-      if (!((e >> 12) & 1u)) continue;
-      if (lane == 0) {
-        const int bstep = (int)(e & 31u) * NCHUNK + (int)((e >> 5) & 31u);
-        mbar_wait(smem_u32(bar_b_empty + bs), phase);
-        const uint32_t bar = smem_u32(bar_b_full + bs);
-        if (A.dbg & 4) {
-          mbar_arrive(bar);
-        } else {
-          mbar_arrive_expect_tx(bar, B_STAGE);
-          bulk_copy_g2s(smem_u32(b_ring + (size_t)bs * B_STAGE), packed + (size_t)bstep * B_STAGE, B_STAGE, bar);
+    uint32_t bphase = 1;
+    int j = 0;
+    build_list((int)blockIdx.x, 0);
+#pragma unroll 1
+    for (int g = (int)blockIdx.x; g < n_groups; g += gstep, ++j) {
+      if (g + gstep < n_groups) build_list(g + gstep, j + 1);
+      const int buf = j & 1;
+      const int nsteps = (int)s_nsteps[buf];
+      const uint32_t steps0 = lists0 + (uint32_t)buf * (kB2ListCap * 2);
+      const int tile0 = g * T * kBM;
+      const int row_end = min(n_out, tile0 + T * kBM);
+      auto prefetch_idx = [&](int i) {
+        if (i >= nsteps || lane >= 4 * kps || (A.dbg & 64)) return;
+        const uint32_t e = lds_u16(steps0 + 2u * (uint32_t)i);
+        if (((e >> 5) & 31u) != 0u) return;                      // all chunks of an (offset, tile) use the same indices
+        const int k = (int)(e & 31u) * kps + (lane >> 2);
+        const int row = tile0 + (int)((e >> 10) & 3u) * kBM + 32 * (lane & 3);     // 128 rows x 4 B = four 128 B lines
+        if (k < K && row < row_end) asm volatile("prefetch.global.L2 [%0];" ::"l"(tbl + (size_t)k * tbl_stride + row));
+      };
+      for (int i = 0; i < kIdxAhead; ++i) prefetch_idx(i);
+#pragma unroll 1
+      for (int i = 0; i < nsteps; ++i) {
+        prefetch_idx(i + kIdxAhead);
+        const uint32_t e = lds_u16(steps0 + 2u * (uint32_t)i);
+        if (!((e >> 12) & 1u)) continue;
+        if (lane == 0) {
+          const int bstep = (int)(e & 31u) * NCHUNK + (int)((e >> 5) & 31u);
+          mbar_wait(smem_u32(bar_b_empty + bs), bphase);
+          const uint32_t bar = smem_u32(bar_b_full + bs);
+          if (A.dbg & 4) {
+            mbar_arrive(bar);
+          } else {
+            mbar_arrive_expect_tx(bar, B_STAGE);
+            bulk_copy_g2s(smem_u32(b_ring + (size_t)bs * B_STAGE), packed + (size_t)bstep * B_STAGE, B_STAGE, bar);
+          }
         }
+        if (++bs == SB) { bs = 0; bphase ^= 1; }
+        __syncwarp();
       }
-      if (++bs == SB) { bs = 0; phase ^= 1; }
-      __syncwarp();
     }
   } else if (warp == kB2MmaWarp) {
     // ===================== MMA issuer =====================
-    if (lane == 0) {
+    // The whole warp walks the list with warp-uniform control flow and values (the entry is broadcast with a shuffle so
+    // that the compiler keeps descriptors and barrier addresses in uniform registers); one elected lane issues.
+    {
       constexpr uint32_t idesc = make_idesc_bf16(kBM, COUT);
       constexpr uint32_t desc_hi = 64u | (1u << 14) | (2u << 29);   // SBO = 1024 B, version 1, SWIZZLE_128B
       const uint32_t a_lo0 = ((smem_u32(a_ring) >> 4) & 0x3FFF) | (1u << 16);
@@ -355,56 +384,163 @@ conv_bf2_kernel(const __grid_constant__ B2Args A) {
       const uint32_t bar_b_full0 = smem_u32(bar_b_full), bar_b_empty0 = smem_u32(bar_b_empty);
       // (A slice, B slice) of the six MMAs of a step, small terms first; a slice = 32 B = 16 BF16 k positions.
       //   Cin >= 32: A = [hi 0-15 | hi 16-31 | lo 0-15 | lo 16-31], B = [w1 0-15 | w1 16-31 | w2 0-15 | w2 16-31]
+      //              pairs (2,0) (3,1) (0,2) (1,3) (0,0) (1,1)
       //   Cin == 16: A = [hi k0 | lo k0 | hi k1 | lo k1],            B = [w1 k0 | w2 k0 | w1 k1 | w2 k1]
-      const uint32_t pa = kps == 1 ? ((2u) | (3u << 2) | (0u << 4) | (1u << 6) | (0u << 8) | (1u << 10))
-                                   : ((1u) | (0u << 2) | (3u << 4) | (2u << 6) | (0u << 8) | (2u << 10));
-      const uint32_t pb = kps == 1 ? ((0u) | (1u << 2) | (2u << 4) | (3u << 6) | (0u << 8) | (1u << 10))
-                                   : ((0u) | (1u << 2) | (2u << 4) | (3u << 6) | (0u << 8) | (2u << 10));
+      //              pairs (1,0) (0,1) (3,2) (2,3) (0,0) (2,2)
+      const bool leader = elect_one();
       int as = 0, bs = -1;
       uint32_t a_phase = 0, b_phase = 1;
-      uint32_t started = 0;
-      const uint32_t steps0 = smem_u32(steps);
-      uint32_t e_next = lds_u16(steps0);
-      for (int i = 0; i < nsteps; ++i) {
-        const uint32_t e = e_next;
-        e_next = lds_u16(steps0 + 2u * (uint32_t)min(i + 1, nsteps - 1));
-        const int t = (int)((e >> 10) & 3u);
-        if ((e >> 12) & 1u) {                                     // first tile of a new weight stage
-          if (++bs == SB) bs = 0;
-          if (bs == 0) b_phase ^= 1;
-          mbar_wait(bar_b_full0 + 8 * bs, b_phase);
-        }
-        mbar_wait(bar_a_full0 + 8 * as, a_phase);
+      int j = 0;
+      long long mw_a = 0, mw_b = 0, mw_acc = 0, mw_list = 0, m_steps = 0;
+      const bool prof = A.prof != nullptr;
+      const long long m_t0 = prof ? clock64() : 0;
+      for (int g = (int)blockIdx.x; g < n_groups; g += gstep, ++j) {
+        const int buf = j & 1;
+        long long c0 = prof ? clock64() : 0;
+        mbar_wait(smem_u32(bar_list_full + buf), (uint32_t)(j >> 1) & 1u);
+        if (prof) { const long long c1 = clock64(); mw_list += c1 - c0; c0 = c1; }
+        mbar_wait(smem_u32(bar_acc_empty + buf), ((uint32_t)(j >> 1) & 1u) ^ 1u);   // the epilogue has drained this accumulator set
+        if (prof) mw_acc += clock64() - c0;
         tc_fence_after();
-        const uint32_t d = tmem_base + (uint32_t)(t * Cfg::ACC_STRIDE);
-        const uint32_t a_lo = a_lo0 + (uint32_t)as * (kB2AStage >> 4);
-        const uint32_t b_lo = b_lo0 + (uint32_t)bs * (B_STAGE >> 4);
-        uint32_t acc = (started >> t) & 1u;
-        started |= 1u << t;
-#pragma unroll
-        for (int q = 0; q < 6; ++q) {
-          if (A.dbg & 2) break;
-          const uint64_t da = ((uint64_t)desc_hi << 32) | (a_lo + 2u * ((pa >> (2 * q)) & 3u));
-          const uint64_t db = ((uint64_t)desc_hi << 32) | (b_lo + 2u * ((pb >> (2 * q)) & 3u));
-          umma_bf16_ss(d, da, db, idesc, acc);
-          acc = 1u;
+        const int nsteps = __shfl_sync(0xffffffffu, (int)s_nsteps[buf], 0);
+        const uint32_t steps0 = lists0 + (uint32_t)buf * (kB2ListCap * 2);
+        const uint32_t d0 = tmem_base + (uint32_t)(buf * Cfg::ACC_BUF);
+        uint32_t started = 0;
+        uint32_t e_next = lds_u16(steps0);
+#pragma unroll 1
+        for (int i = 0; i < nsteps; ++i) {
+          const uint32_t e = __shfl_sync(0xffffffffu, e_next, 0);
+          e_next = lds_u16(steps0 + 2u * (uint32_t)min(i + 1, nsteps - 1));
+          const int t = (int)((e >> 10) & 3u);
+          if ((e >> 12) & 1u) {                                     // first tile of a new weight stage
+            if (++bs == SB) bs = 0;
+            if (bs == 0) b_phase ^= 1;
+            c0 = prof ? clock64() : 0;
+            mbar_wait(bar_b_full0 + 8 * bs, b_phase);
+            if (prof) mw_b += clock64() - c0;
+          }
+          c0 = prof ? clock64() : 0;
+          mbar_wait(bar_a_full0 + 8 * as, a_phase);
+          if (prof) { mw_a += clock64() - c0; ++m_steps; }
+          tc_fence_after();
+          const uint32_t d = d0 + (uint32_t)(t * Cfg::ACC_STRIDE);
+          const uint32_t a_lo = a_lo0 + (uint32_t)as * (kB2AStage >> 4);
+          const uint32_t b_lo = b_lo0 + (uint32_t)bs * (B_STAGE >> 4);
+          const uint32_t acc = (started >> t) & 1u;
+          started |= 1u << t;
+          if (leader && !(A.dbg & 2)) {
+            const uint64_t hi64 = (uint64_t)desc_hi << 32;
+            if (kps == 1) {
+              umma_bf16_ss(d, hi64 | (a_lo + 4u), hi64 | (b_lo + 0u), idesc, acc);
+              umma_bf16_ss(d, hi64 | (a_lo + 6u), hi64 | (b_lo + 2u), idesc, 1u);
+              umma_bf16_ss(d, hi64 | (a_lo + 0u), hi64 | (b_lo + 4u), idesc, 1u);
+              umma_bf16_ss(d, hi64 | (a_lo + 2u), hi64 | (b_lo + 6u), idesc, 1u);
+              umma_bf16_ss(d, hi64 | (a_lo + 0u), hi64 | (b_lo + 0u), idesc, 1u);
+              umma_bf16_ss(d, hi64 | (a_lo + 2u), hi64 | (b_lo + 2u), idesc, 1u);
+            } else {
+              umma_bf16_ss(d, hi64 | (a_lo + 2u), hi64 | (b_lo + 0u), idesc, acc);
+              umma_bf16_ss(d, hi64 | (a_lo + 0u), hi64 | (b_lo + 2u), idesc, 1u);
+              umma_bf16_ss(d, hi64 | (a_lo + 6u), hi64 | (b_lo + 4u), idesc, 1u);
+              umma_bf16_ss(d, hi64 | (a_lo + 4u), hi64 | (b_lo + 6u), idesc, 1u);
+              umma_bf16_ss(d, hi64 | (a_lo + 0u), hi64 | (b_lo + 0u), idesc, 1u);
+              umma_bf16_ss(d, hi64 | (a_lo + 4u), hi64 | (b_lo + 4u), idesc, 1u);
+            }
+          }
+          if (leader) {
+            umma_commit(bar_a_empty0 + 8 * as);                       // gathered tile reusable once read
+            if ((e >> 13) & 1u) umma_commit(bar_b_empty0 + 8 * bs);   // weight tile: last tile of the stage
+          }
+          __syncwarp();
+          if (++as == SA) { as = 0; a_phase ^= 1; }
         }
-        if (A.dbg & 32) {                                         // ablation (with 2): plain arrivals instead of commits
-          mbar_arrive(bar_a_empty0 + 8 * as);
-          if ((e >> 13) & 1u) mbar_arrive(bar_b_empty0 + 8 * bs);
-        } else {
-          umma_commit(bar_a_empty0 + 8 * as);                       // gathered tile reusable once read
-          if ((e >> 13) & 1u) umma_commit(bar_b_empty0 + 8 * bs);   // weight tile: last tile of the stage
+        if (leader) {
+          umma_commit(smem_u32(bar_acc_full + buf));                  // the group's accumulators are complete
+          mbar_arrive(smem_u32(bar_list_empty + buf));
         }
-        if (++as == SA) { as = 0; a_phase ^= 1; }
+        __syncwarp();
       }
-      umma_commit(smem_u32(bar_accum));
+      if (prof && lane == 0) {
+        long long* o = A.prof + (size_t)blockIdx.x * 16;
+        o[5] = clock64() - m_t0; o[6] = mw_a; o[7] = mw_b; o[8] = mw_acc; o[9] = mw_list; o[10] = m_steps;
+      }
+    }
+  } else {
+    // ===================== epilogue warps: TMEM -> staged rows -> coalesced BN / residual / activation / stores ==========
+    // A warp reads the accumulator rows of its TMEM lane quarter (lane = row), stages 32 (16) channels per row in shared
+    // memory and re-reads them with 8 (4) lanes per row, so that every global access is a whole 128 B (64 B) row piece.
+    const int g4 = warp & 3;
+    const uint32_t stg = smem_u32(epi) + (uint32_t)(warp - kB2EpiWarp0) * (32 * kB2EpiRow);
+    const float* __restrict__ scale = A.scale ? A.scale + cblk : nullptr;
+    const float* __restrict__ shift = A.shift ? A.shift + cblk : nullptr;
+    const int act = A.act, res_after = A.res_after_act;
+    constexpr int EPC = Cfg::EPC;
+    constexpr int PPR = EPC / 4;                                    // 16 B pieces per staged row
+    constexpr int RPI = 32 / PPR;                                   // rows covered by one warp-wide access
+    const int pr = lane / PPR, pp = lane % PPR;
+    int j = 0;
+#pragma unroll 1
+    for (int g = (int)blockIdx.x; g < n_groups; g += gstep, ++j) {
+      const int buf = j & 1;
+      const int tile_first = g * T;
+      const int Tr = min(T, A.n_tiles - tile_first);
+      const int tile0 = tile_first * kBM;
+      const int row_end = min(n_out, tile0 + T * kBM);
+      mbar_wait(smem_u32(bar_acc_full + buf), (uint32_t)(j >> 1) & 1u);
+      tc_fence_after();
+#pragma unroll 1
+      for (int t = 0; t < Tr; ++t) {
+        if (A.dbg & 128) break;
+        const int row_l = tile0 + t * kBM + g4 * 32 + lane;
+        const int orow_l = (row_l < row_end && A.out_rows) ? __ldg(A.out_rows + row_l) : row_l;
+#pragma unroll 1
+        for (int c0 = 0; c0 < COUT; c0 += EPC) {
+          uint32_t acc[EPC];
+          tmem_ld<EPC>(tmem_base + ((uint32_t)(g4 * 32) << 16) + (uint32_t)(buf * Cfg::ACC_BUF + t * Cfg::ACC_STRIDE + c0), acc);
+#pragma unroll
+          for (int q = 0; q < PPR; ++q)
+            sts128(stg + (uint32_t)lane * kB2EpiRow + 16u * q, __uint_as_float(acc[4 * q]), __uint_as_float(acc[4 * q + 1]),
+                   __uint_as_float(acc[4 * q + 2]), __uint_as_float(acc[4 * q + 3]));
+          __syncwarp();
+          float4 sc = make_float4(1.f, 1.f, 1.f, 1.f), sh = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (scale) sc = __ldg(reinterpret_cast<const float4*>(scale + c0) + pp);
+          if (shift) sh = __ldg(reinterpret_cast<const float4*>(shift + c0) + pp);
+#pragma unroll
+          for (int jj = 0; jj < PPR; ++jj) {
+            const int r = pr + RPI * jj;
+            const int orow = __shfl_sync(0xffffffffu, orow_l, r);
+            const int row = tile0 + t * kBM + g4 * 32 + r;
+            float4 v = lds128(stg + (uint32_t)r * kB2EpiRow + 16u * pp);
+            if (row < row_end && !(A.dbg & 8)) {
+              v.x = v.x * sc.x + sh.x; v.y = v.y * sc.y + sh.y; v.z = v.z * sc.z + sh.z; v.w = v.w * sc.w + sh.w;
+              float4 rr = make_float4(0.f, 0.f, 0.f, 0.f);
+              if (A.residual) rr = __ldg(reinterpret_cast<const float4*>(A.residual + (size_t)orow * A.res_ld + cblk + c0) + pp);
+              if (!res_after) { v.x += rr.x; v.y += rr.y; v.z += rr.z; v.w += rr.w; }
+              v.x = b2_act(v.x, act); v.y = b2_act(v.y, act); v.z = b2_act(v.z, act); v.w = b2_act(v.w, act);
+              if (res_after) { v.x += rr.x; v.y += rr.y; v.z += rr.z; v.w += rr.w; }
+              if (A.out) reinterpret_cast<float4*>(A.out + (size_t)orow * A.out_ld + cblk + c0)[pp] = v;
+              if (A.out_split) {
+                // split row: per chunk of EPC channels [EPC/2 words hi | EPC/2 words lo]; this lane owns channels 4pp..4pp+3
+                uint32_t h0, l0, h1, l1;
+                split_pair(v.x, v.y, h0, l0);
+                split_pair(v.z, v.w, h1, l1);
+                uint32_t* dst = A.out_split + (size_t)orow * A.split_ld + cblk + c0;
+                *reinterpret_cast<uint2*>(dst + 2 * pp) = make_uint2(h0, h1);
+                *reinterpret_cast<uint2*>(dst + EPC / 2 + 2 * pp) = make_uint2(l0, l1);
+              }
+            }
+          }
+          __syncwarp();                                             // staged rows are consumed before the next chunk lands
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(smem_u32(bar_acc_empty + buf));
     }
   }
 
   tc_fence_before();
   __syncthreads();
-  if (warp == kB2LoaderWarp) tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
+  if (warp == kB2UtilWarp) tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -484,6 +620,7 @@ __global__ void __launch_bounds__(128) tile_masks_kernel(const int* __restrict__
 
 static int g_b2_variant = 0;
 static int g_b2_dbg = 0;
+static long long* g_b2_prof = nullptr;
 
 static int b2_cout_block(int Cout) {
   return Cout % 128 == 0 ? 128 : (Cout % 64 == 0 ? 64 : (Cout % 32 == 0 ? 32 : (Cout % 16 == 0 ? 16 : 0)));
@@ -500,19 +637,16 @@ static int launch_b2(const B2Args& a, int Cout, cudaStream_t st) {
     configured = true;
   }
   B2Args b = a;
-  const int n_tiles = div_up(a.n_out, kBM);
-  S2D_REQUIRE(a.ksteps * a.nchunk * T <= kB2MaxSteps, "s2d_conv_fwd(bf16x2): %d x %d x %d contraction steps per CTA exceed %d",
-              a.ksteps, a.nchunk, T, kB2MaxSteps);
-  // Deal the 128-row tiles over a grid that is a whole number of waves (OCC CTAs per SM), at most T per CTA
-  const int wave = kNumSMs * Cfg::OCC;
-  const int g_full = div_up(n_tiles, T);
-  int gx = div_up(g_full, wave) * wave;
-  if (gx > n_tiles) gx = n_tiles;
-  b.tile_unit = 1;
-  b.unit_base = n_tiles / gx;
-  b.unit_rem = n_tiles % gx;
-  b.n_tiles = n_tiles;
-  const dim3 grid(gx, Cout / COUT);
+  S2D_REQUIRE(a.ksteps * a.nchunk * T <= kB2ListCap, "s2d_conv_fwd(bf16x2): %d x %d x %d contraction steps per tile group exceed %d",
+              a.ksteps, a.nchunk, T, kB2ListCap);
+  // persistent CTAs, one per SM: CTA b works on the tile groups b, b + grid, b + 2 grid, ...
+  b.n_tiles = div_up(a.n_out, kBM);
+  b.n_groups = div_up(b.n_tiles, T);
+  const int gy = Cout / COUT;
+  int gx = kNumSMs / gy;
+  if (gx < 1) gx = 1;
+  if (gx > b.n_groups) gx = b.n_groups;
+  const dim3 grid(gx, gy);
   conv_bf2_kernel<COUT, T, SA, SB><<<grid, kB2Threads, Cfg::SMEM_BYTES, st>>>(b);
   S2D_LAUNCH_CHECK();
   count_launches(1);
@@ -549,25 +683,22 @@ int conv_fwd_bf2(const s2d_conv_params& p, cudaStream_t st) {
   a.kps = p.Cin == 16 ? 2 : 1; a.nchunk = a.kps == 1 ? p.Cin / 32 : 1; a.ksteps = div_up(p.K, a.kps); a.act = p.act;
   a.res_after_act = p.res_after_act;
   a.dbg = g_b2_dbg;
+  a.prof = g_b2_prof;
   const int v = g_b2_variant;
   if (cb == 128) {
-    if (v == 1) return launch_b2<128, 2, 3, 3>(a, p.Cout, st);
-    if (v == 2) return launch_b2<128, 4, 6, 4>(a, p.Cout, st);
-    return launch_b2<128, 2, 4, 2>(a, p.Cout, st);
+    if (v == 1) return launch_b2<128, 2, 8, 2>(a, p.Cout, st);
+    return launch_b2<128, 2, 8, 3>(a, p.Cout, st);
   }
   if (cb == 64) {
-    if (v == 1) return launch_b2<64, 4, 5, 3>(a, p.Cout, st);
-    if (v == 2) return launch_b2<64, 4, 8, 4>(a, p.Cout, st);
-    return launch_b2<64, 4, 4, 4>(a, p.Cout, st);
+    if (v == 1) return launch_b2<64, 2, 8, 4>(a, p.Cout, st);
+    return launch_b2<64, 4, 8, 4>(a, p.Cout, st);
   }
   if (cb == 32) {
-    if (v == 1) return launch_b2<32, 4, 4, 4>(a, p.Cout, st);
-    if (v == 2) return launch_b2<32, 4, 8, 4>(a, p.Cout, st);
-    return launch_b2<32, 4, 5, 4>(a, p.Cout, st);
+    if (v == 1) return launch_b2<32, 2, 8, 4>(a, p.Cout, st);
+    return launch_b2<32, 4, 8, 4>(a, p.Cout, st);
   }
-  if (v == 1) return launch_b2<16, 4, 4, 4>(a, p.Cout, st);
-  if (v == 2) return launch_b2<16, 4, 8, 4>(a, p.Cout, st);
-  return launch_b2<16, 4, 6, 4>(a, p.Cout, st);
+  if (v == 1) return launch_b2<16, 2, 8, 4>(a, p.Cout, st);
+  return launch_b2<16, 4, 8, 4>(a, p.Cout, st);
 }
 
 int pack_weights_bf2(const float* W, int K, int Cin, int Cout, void* packed, cudaStream_t st) {
@@ -589,6 +720,7 @@ using namespace s2d;
 // which (tiles per CTA, A stages, B stages) instantiation conv_fwd_bf2 launches (tuning aid; not part of the public header)
 extern "C" void s2d_debug_bf2_variant(int v) { g_b2_variant = v; }
 extern "C" void s2d_debug_bf2_flags(int f) { g_b2_dbg = f; }
+extern "C" void s2d_debug_bf2_prof(long long* p) { g_b2_prof = p; }
 
 extern "C" int s2d_table_tile_masks(const int* tbl, int tbl_stride, int K, int n_rows, int* tile_masks, void* stream) {
   S2D_REQUIRE(K >= 1 && K <= 31 && n_rows >= 0 && tbl_stride >= n_rows, "s2d_table_tile_masks: bad argument");

@@ -36,6 +36,7 @@ def main():
     ap.add_argument("--dense", action="store_true", help="also time dense 3x3 / 1x1 convs of the neck shapes")
     ap.add_argument("--ablate", default="", help="comma list of ablation flag sets (see conv_bf2.cu B2Args::dbg), timed with variant 0")
     ap.add_argument("--only", type=int, default=0)
+    ap.add_argument("--prof", action="store_true", help="print the in-kernel cycle counters (producer / MMA waits)")
     args = ap.parse_args()
     _lib.load()
     setv = ctypes.CDLL(_lib.LIB_PATH).s2d_debug_bf2_variant
@@ -81,6 +82,20 @@ def main():
                 line += f" | v{v}{'m' if use_masks else ' '} {t:.3f} ms (err {err:.1e})"
         setv(0)
         print(line, flush=True)
+        if args.prof:
+            lib = ctypes.CDLL(_lib.LIB_PATH)
+            lib.s2d_debug_bf2_prof.argtypes = [ctypes.c_void_p]
+            for fl in (0, 227):
+                buf = torch.zeros(148 * 16, dtype=torch.int64, device="cuda")
+                setf(fl)
+                lib.s2d_debug_bf2_prof(buf.data_ptr())
+                ops.spconv_fwd(feats, w, tbl, n, precision=ops.PRECISION_BF16X2, packed=pk, out=out)
+                torch.cuda.synchronize()
+                lib.s2d_debug_bf2_prof(None)
+                setf(0)
+                m = buf.view(148, 16).double().mean(0).tolist()
+                print(f"   prof {c:3d} flags {fl}: producer0 total {m[0]:.0f} clk: wait_empty {m[1]:.0f} wait_data {m[2]:.0f} wait_list {m[3]:.0f} over {m[4]:.0f} steps "
+                      f"| mma total {m[5]:.0f}: wait_a {m[6]:.0f} wait_b {m[7]:.0f} wait_acc {m[8]:.0f} wait_list {m[9]:.0f} over {m[10]:.0f} steps", flush=True)
         if args.ablate:
             line = f"   ablate {c:3d}:"
             for fl in [int(v) for v in args.ablate.split(",")]:
