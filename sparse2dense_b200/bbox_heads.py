@@ -94,8 +94,7 @@ class CenterHead(nn.Module):
                 def build():
                     w = torch.cat([c.weight.detach().float() for c in firsts], 0)               # [320,64,3,3]
                     kio = w.permute(2, 3, 1, 0).reshape(9, w.shape[1], w.shape[0]).contiguous()
-                    packed = ops.pack_weights_tf32(kio, D.precision) if (D.precision != ops.PRECISION_FP32 and
-                                                            ops.tf32_supported(kio.shape[1], kio.shape[2])) else None
+                    packed = {}                                   # effective precision -> image (filled by conv_rows)
                     sc, sh = zip(*[fold_bn(b, c.bias, c.weight.shape[0], c.weight.device) for c, b in zip(firsts, bns)])
                     return kio, packed, torch.cat(sc).contiguous(), torch.cat(sh).contiguous()
                 src = [c.weight for c in firsts] + [c.bias for c in firsts] + \
@@ -117,9 +116,7 @@ class CenterHead(nn.Module):
                         kio[:, hi * hc:(hi + 1) * hc, off:off + c.weight.shape[0]] = w
                         bias[off:off + c.weight.shape[0]] = c.bias.detach().float()
                         off += c.weight.shape[0]
-                    packed = ops.pack_weights_tf32(kio, D.precision) if (D.precision != ops.PRECISION_FP32 and
-                                                            ops.tf32_supported(kio.shape[1], kio.shape[2])) else None
-                    return kio, packed, bias
+                    return kio, {}, bias
                 kio_l, packed_l, bias_l = D.cache.get(("lasts", ti, D.precision),
                                                       [c.weight for c in lasts] + [c.bias for c in lasts], build_last)
                 y = conv_rows(mid, kio_l, tbl, n, None, bias_l, ACT_NONE, precision=D.precision, packed=packed_l)

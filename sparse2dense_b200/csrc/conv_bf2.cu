@@ -35,11 +35,10 @@
 namespace s2d {
 
 constexpr int kB2ProducerWarps = 8;
+constexpr int kB2Stages = 8;               // gathered-tile stages (one per producer warp)
 constexpr int kB2UtilWarp = 8;
-constexpr int kB2MmaWarp = 9;
-constexpr int kB2EpiWarp0 = 10;            // four epilogue warps; warp w reads TMEM lanes [32 (w % 4), +32)
-constexpr int kB2Threads = 32 * 14;
-constexpr int kB2ListCap = 1024;           // (offset steps) x (chunks) x (tiles) of one tile group; host-checked
+constexpr int kB2MmaWarp0 = 9;             // T MMA warps (one per tile of the group), then four epilogue warps
+constexpr int kB2ListCap = 1024;           // (offset steps) x (chunks) of one tile group; host-checked
 constexpr int kB2AStage = kBM * 128;       // 128 rows x 128 B
 constexpr int kB2EpiRow = 144;             // staged accumulator row: 128 B + 16 B pad (conflict-free 16 B accesses)
 
@@ -56,10 +55,22 @@ __device__ __forceinline__ void umma_bf16_ss(uint32_t tmem_d, uint64_t desc_a, u
 __device__ __forceinline__ void sts128(uint32_t addr, float a, float b, float c, float d) {
   asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
 }
+__device__ __forceinline__ void sts32(uint32_t addr, int v) {
+  asm volatile("st.shared.b32 [%0], %1;" ::"r"(addr), "r"(v) : "memory");
+}
 
-template <int COUT, int T_, int SA_, int SB_>
+// A tile GROUP = T consecutive 128-row tiles (the unit a CTA works on); a BLOCK = one (offset step, channel chunk) of a
+// group: one weight tile and up to T gathered tiles (one per tile of the group that has a neighbour at that offset).
+// The eight gathered-tile stages form NB = 8 / T block slots; stage (slot, t) = slot * T + t always belongs to tile t, so
+// producer warp w = stage w and MMA warp t = tile t see every phase of "their" barriers whatever the masks skip.
+template <int COUT, int T_>
 struct B2Cfg {
-  static constexpr int T = T_, SA = SA_, SB = SB_;
+  static constexpr int T = T_;
+  static constexpr int NB = kB2Stages / T;                     // gathered-tile slots per tile (stage = slot * T + t)
+  static constexpr int SB = COUT >= 128 ? 3 : 4;               // weight-tile ring
+  static constexpr int WARPS = kB2MmaWarp0 + T + 4;
+  static constexpr int THREADS = 32 * WARPS;
+  static constexpr int EPI_WARP0 = kB2MmaWarp0 + T;
   static constexpr int B_STAGE = COUT * 128;                   // COUT rows x [w1 (64 B) | w2 (64 B)]
   static constexpr int ACC_STRIDE = COUT < 32 ? 32 : COUT;
   static constexpr int ACC_BUF = T * ACC_STRIDE;               // one accumulator set (T tiles)
@@ -69,12 +80,12 @@ struct B2Cfg {
   static constexpr int LIST_BYTES = 2 * kB2ListCap * 2;
   static constexpr int EPI_BYTES = 4 * 32 * kB2EpiRow;
   static constexpr int BAR_BYTES = 512;
-  static constexpr int SMEM_BYTES = SA * kB2AStage + SB * B_STAGE + LIST_BYTES + EPI_BYTES + kB2ProducerWarps * 1024 + BAR_BYTES + 1024;
-  static_assert(SA == kB2ProducerWarps, "producer warp w owns stage w");
+  static constexpr int SMEM_BYTES = kB2Stages * kB2AStage + SB * B_STAGE + LIST_BYTES + EPI_BYTES + kB2ProducerWarps * 1024 + BAR_BYTES + 1024;
+  static_assert(T == 2 || T == 4, "tiles per group");
   static_assert(ACC_COLS <= 512, "TMEM budget");
   static_assert(SMEM_BYTES <= 227 * 1024, "shared memory budget");
   static_assert(COUT % 16 == 0 && COUT >= 16 && COUT <= 128, "UMMA N constraint for M = 128");
-  static_assert(2 * SA + 2 * SB + 8 <= BAR_BYTES / 8 - 2, "barrier block");
+  static_assert(2 * kB2Stages + 2 * SB + 8 <= BAR_BYTES / 8 - 2, "barrier block");
 };
 
 struct B2Args {
@@ -89,9 +100,10 @@ struct B2Args {
   uint32_t* out_split;       // split rows or null
   const int* out_rows;
   int in_ld, out_ld, res_ld, split_ld, tbl_stride, n_out, K, nchunk, kps, ksteps, act, res_after_act;
-  int n_tiles, n_groups;     // 128-row tiles; groups of T consecutive tiles (the unit a CTA works on)
+  int n_tiles, n_groups;     // 128-row tiles; groups of T consecutive tiles
   long long* prof;   // optional [gridDim.x][16] cycle counters (tools/microbench_bf2.py --prof), null in production
-  int dbg;   // ablation switches (tools/microbench_bf2.py): 1 no gather, 2 no MMA, 4 no weight copies, 8 no stores, 16 all rows missing
+  int dbg;   // ablation switches (tools/microbench_bf2.py): 1 no gather, 2 no MMA, 4 no weight copies, 8 no stores, 16 all rows
+             // missing, 64 no index loads, 128 no epilogue
 };
 
 __device__ __forceinline__ float b2_act(float y, int act) {
@@ -111,51 +123,53 @@ __device__ __forceinline__ void split_pair(float a, float b, uint32_t& hi, uint3
 }
 
 // Persistent CTA (one per SM): group j of this CTA is tile group blockIdx.x + j * gridDim.x.  Per group the utility warp
-// writes a step list (double buffered), the producers / MMA issuer walk it, and the four epilogue warps drain the
-// group's accumulators from the other TMEM buffer while the next group is already being gathered and multiplied.
-template <int COUT, int T, int SA, int SB>
-__global__ void __launch_bounds__(kB2Threads, 1) conv_bf2_kernel(const __grid_constant__ B2Args A) {
-  using Cfg = B2Cfg<COUT, T, SA, SB>;
-  constexpr int B_STAGE = Cfg::B_STAGE;
+// writes the block list (double buffered); every role walks ALL blocks of the list (so every waiter sees every phase of
+// the per-slot barriers); the four epilogue warps drain a group's accumulators from one TMEM buffer while the next group
+// is gathered and multiplied into the other.
+//   block entry = kk | live-tile nibble << 5 | chunk << 9
+template <int COUT, int T>
+__global__ void __launch_bounds__(B2Cfg<COUT, T>::THREADS, 1) conv_bf2_kernel(const __grid_constant__ B2Args A) {
+  using Cfg = B2Cfg<COUT, T>;
+  constexpr int B_STAGE = Cfg::B_STAGE, NB = Cfg::NB, SB = Cfg::SB;
   const int NCHUNK = A.nchunk, K = A.K, KS = A.ksteps, kps = A.kps, n_out = A.n_out;
   const int cblk = blockIdx.y * COUT;
   const int n_groups = A.n_groups, gstep = (int)gridDim.x;
 
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint8_t* a_ring = smem;                                        // SA x [128 rows x 128 B], 128B-swizzled
-  uint8_t* b_ring = a_ring + SA * kB2AStage;                     // SB x [COUT rows x 128 B], 128B-swizzled
-  uint8_t* lists = b_ring + SB * B_STAGE;                        // 2 x kB2ListCap u16 step entries
+  uint8_t* a_ring = smem;                                        // 8 x [128 rows x 128 B], 128B-swizzled
+  uint8_t* b_ring = a_ring + kB2Stages * kB2AStage;              // NB x [COUT rows x 128 B], 128B-swizzled
+  uint8_t* lists = b_ring + SB * B_STAGE;                        // 2 x kB2ListCap u16 block entries
   uint8_t* epi = lists + Cfg::LIST_BYTES;                        // 4 warps x [32 rows x 144 B]
   uint8_t* idx_scratch = epi + Cfg::EPI_BYTES;                   // 8 producer warps x 1 KB
   uint64_t* bars = reinterpret_cast<uint64_t*>(idx_scratch + kB2ProducerWarps * 1024);
-  uint64_t* bar_a_full = bars;
-  uint64_t* bar_a_empty = bar_a_full + SA;
-  uint64_t* bar_b_full = bar_a_empty + SA;
-  uint64_t* bar_b_empty = bar_b_full + SB;
+  uint64_t* bar_a_full = bars;                                   // [8]  producer warp -> MMA warp of the stage's tile
+  uint64_t* bar_a_empty = bar_a_full + kB2Stages;                // [8]  MMA warp of the tile -> producer warp of the stage
+  uint64_t* bar_b_full = bar_a_empty + kB2Stages;                // [SB] weight tile landed
+  uint64_t* bar_b_empty = bar_b_full + SB;                       // [SB] T MMA warps -> weight loader
   uint64_t* bar_list_full = bar_b_empty + SB;                    // [2]
   uint64_t* bar_list_empty = bar_list_full + 2;                  // [2]
   uint64_t* bar_acc_full = bar_list_empty + 2;                   // [2]
   uint64_t* bar_acc_empty = bar_acc_full + 2;                    // [2]
   uint32_t* s_tmem = reinterpret_cast<uint32_t*>(bar_acc_empty + 2);
-  uint32_t* s_nsteps = s_tmem + 1;                               // [2]
+  uint32_t* s_nblocks = s_tmem + 1;                              // [2]
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   if ((int)blockIdx.x >= n_groups) return;
 
-  if (warp == kB2MmaWarp && lane == 0) {
-    for (int s = 0; s < SA; ++s) {
+  if (warp == kB2MmaWarp0 && lane == 0) {
+    for (int s = 0; s < kB2Stages; ++s) {
       mbar_init(smem_u32(bar_a_full + s), 1);                     // the producer warp that owns the stage
-      mbar_init(smem_u32(bar_a_empty + s), 1);                    // one tcgen05.commit
+      mbar_init(smem_u32(bar_a_empty + s), 1);                    // tcgen05.commit of the MMA warp that owns the tile
     }
     for (int s = 0; s < SB; ++s) {
       mbar_init(smem_u32(bar_b_full + s), 1);                     // arrive.expect_tx of the loader
-      mbar_init(smem_u32(bar_b_empty + s), 1);                    // one tcgen05.commit after the last tile of the stage
+      mbar_init(smem_u32(bar_b_empty + s), T);                    // every MMA warp: commit (or plain arrival if its tile is dead)
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(smem_u32(bar_list_full + s), 1);                  // utility warp, after writing the list
-      mbar_init(smem_u32(bar_list_empty + s), kB2ProducerWarps + 1);   // producer warps + MMA issuer done reading it
-      mbar_init(smem_u32(bar_acc_full + s), 1);                   // tcgen05.commit after the group's last MMA
+      mbar_init(smem_u32(bar_list_empty + s), kB2ProducerWarps + T);   // producer + MMA warps done reading it
+      mbar_init(smem_u32(bar_acc_full + s), T);                   // every MMA warp after its last MMA of the group
       mbar_init(smem_u32(bar_acc_empty + s), 4);                  // the four epilogue warps
     }
     fence_barrier_init();
@@ -166,13 +180,14 @@ __global__ void __launch_bounds__(kB2Threads, 1) conv_bf2_kernel(const __grid_co
   tc_fence_after();
   const uint32_t tmem_base = *s_tmem;
   const uint32_t lists0 = smem_u32(lists);
+  const bool prof = A.prof != nullptr;
 
   if (warp < kB2ProducerWarps) {
-    // ===================== producers: warp w gathers every 8th step (all 128 rows) into stage w =====================
-    // A warp's iteration is a serial chain of ~100 dependent instructions plus the latency of its own copies, so the
-    // steps are dealt over the warps instead of splitting every step over all of them: eight steps are in flight, one
-    // mbarrier arrival publishes a stage, and the per-step rate is set by the LSU, not by one warp's instruction latency.
+    // ===================== producers: warp w owns stage w = (slot w / T, tile w % T) =====================
+    // A warp's iteration is a serial chain of ~100 dependent instructions plus the latency of its own copies, so whole
+    // 128-row tiles are dealt over the warps: eight gathers are in flight and one mbarrier arrival publishes a stage.
     //   lane = (o = lane >> 3, c8 = lane & 7): copy r (0..31) moves piece c8 of row 4r + o.
+    const int my_slot = warp / T, my_t = warp % T;
     const int o = lane >> 3, c8 = lane & 7;
     const int sub = kps == 2 ? (c8 >> 2) : 0;                // Cin = 16: pieces 0-3 come from offset 2kk, 4-7 from 2kk + 1
     const uint32_t piece = (uint32_t)(kps == 2 ? (c8 & 3) : c8) * 16u;
@@ -182,113 +197,113 @@ __global__ void __launch_bounds__(kB2Threads, 1) conv_bf2_kernel(const __grid_co
     const int tbl_stride = A.tbl_stride;
     const uint32_t a_stage = smem_u32(a_ring) + (uint32_t)warp * kB2AStage;
     const uint32_t bar_full = smem_u32(bar_a_full + warp), bar_empty = smem_u32(bar_a_empty + warp);
+    uint32_t phase = 1;                                      // first use of the stage: free
     // index scratch of this warp: [2 offsets][4 row residues o][32 copies r] -> idx of row 4r + o, read back as int4 over r
     const uint32_t scr = smem_u32(idx_scratch) + (uint32_t)warp * 1024u;
     const uint32_t scr_rd = scr + (uint32_t)sub * 512u + (uint32_t)o * 128u;
     const uint32_t dst_lane = (uint32_t)o * 128u;            // row 4r + o: byte (4r + o) * 128, swizzle ((4r + o) & 7) ^ c8
-    uint32_t phase = 1;                                      // first use of the stage: free
-    int gbase = 0;                                           // steps of this CTA before the current group
-    long long pw_empty = 0, pw_data = 0, pw_list = 0, p_steps = 0;
-    const bool prof = A.prof != nullptr;
-    const long long p_t0 = prof ? clock64() : 0;
+    int gblk = 0;                                            // blocks of this CTA before the current group
     int j = 0;
+    long long pw_empty = 0, pw_data = 0, pw_list = 0, p_steps = 0;
+    const long long p_t0 = prof ? clock64() : 0;
 #pragma unroll 1
     for (int g = (int)blockIdx.x; g < n_groups; g += gstep, ++j) {
       const int buf = j & 1;
       long long c0 = prof ? clock64() : 0;
       mbar_wait(smem_u32(bar_list_full + buf), (uint32_t)(j >> 1) & 1u);
       if (prof) pw_list += clock64() - c0;
-      const int nsteps = (int)s_nsteps[buf];
-      const uint32_t steps0 = lists0 + (uint32_t)buf * (kB2ListCap * 2);
-      const int tile0 = g * T * kBM;
-      const int row_end = min(n_out, tile0 + T * kBM);
-      // this lane's four consecutive rows 4 lane .. 4 lane + 3 of the step's tile, one int4 per offset of the step
+      const int nblocks = (int)s_nblocks[buf];
+      const uint32_t list0 = lists0 + (uint32_t)buf * (kB2ListCap * 2);
+      const int tile0 = (g * T + my_t) * kBM;                // first row of this warp's tile
+      const int row_end = min(n_out, tile0 + kBM);
+      // this lane's four consecutive rows 4 lane .. 4 lane + 3 of the tile, one int4 per offset of the block
       auto load_idx = [&](uint32_t e, int s2) -> int4 {
         int4 v = make_int4(-1, -1, -1, -1);
         const int k = (int)(e & 31u) * kps + s2;
-        const int row0 = tile0 + (int)((e >> 10) & 3u) * kBM + 4 * lane;
-        if (k < K && row0 < row_end && !(A.dbg & 64)) {
+        const int row0 = tile0 + 4 * lane;
+        if (((e >> (5 + my_t)) & 1u) && k < K && row0 < row_end && !(A.dbg & 64)) {
           v = __ldg(reinterpret_cast<const int4*>(tbl + (size_t)k * tbl_stride + row0));
           const int lim = row_end - row0;
           if (lim < 4) { if (lim < 2) v.y = -1; if (lim < 3) v.z = -1; v.w = -1; }
         }
         return v;
       };
-      int i = (warp - gbase) & 7;                            // first step of this group with (gbase + i) % 8 == warp
+      int ib = (my_slot - gblk) & (NB - 1);                  // first block of this group in this warp's slot
       uint32_t e = 0;
       int4 qa = make_int4(-1, -1, -1, -1), qb = qa;
-      if (i < nsteps) {
-        e = lds_u16(steps0 + 2u * (uint32_t)i);
+      if (ib < nblocks) {
+        e = lds_u16(list0 + 2u * (uint32_t)ib);
         qa = load_idx(e, 0);
         if (kps == 2) qb = load_idx(e, 1);
       }
 #pragma unroll 1
-      for (; i < nsteps; i += 8) {
-        // indices -> scratch, transposed so that the copies of row residue o read four consecutive r with one LDS.128
-        asm volatile("st.shared.b32 [%0], %1;" ::"r"(scr + 4u * lane), "r"(qa.x) : "memory");
-        asm volatile("st.shared.b32 [%0], %1;" ::"r"(scr + 128u + 4u * lane), "r"(qa.y) : "memory");
-        asm volatile("st.shared.b32 [%0], %1;" ::"r"(scr + 256u + 4u * lane), "r"(qa.z) : "memory");
-        asm volatile("st.shared.b32 [%0], %1;" ::"r"(scr + 384u + 4u * lane), "r"(qa.w) : "memory");
-        if (kps == 2) {
-          asm volatile("st.shared.b32 [%0], %1;" ::"r"(scr + 512u + 4u * lane), "r"(qb.x) : "memory");
-          asm volatile("st.shared.b32 [%0], %1;" ::"r"(scr + 640u + 4u * lane), "r"(qb.y) : "memory");
-          asm volatile("st.shared.b32 [%0], %1;" ::"r"(scr + 768u + 4u * lane), "r"(qb.z) : "memory");
-          asm volatile("st.shared.b32 [%0], %1;" ::"r"(scr + 896u + 4u * lane), "r"(qb.w) : "memory");
+      for (; ib < nblocks; ib += NB) {
+        const bool live = (e >> (5 + my_t)) & 1u;
+        if (live) {
+          // indices -> scratch, transposed so that the copies of row residue o read four consecutive r with one LDS.128
+          sts32(scr + 4u * lane, qa.x); sts32(scr + 128u + 4u * lane, qa.y);
+          sts32(scr + 256u + 4u * lane, qa.z); sts32(scr + 384u + 4u * lane, qa.w);
+          if (kps == 2) {
+            sts32(scr + 512u + 4u * lane, qb.x); sts32(scr + 640u + 4u * lane, qb.y);
+            sts32(scr + 768u + 4u * lane, qb.z); sts32(scr + 896u + 4u * lane, qb.w);
+          }
         }
-        const uint32_t cbytes = (kps == 2 ? 0u : ((e >> 5) & 31u) * 128u) + piece;
-        // prefetch the entry and the indices of this warp's next step (eight steps ahead)
+        const uint32_t cbytes = (kps == 2 ? 0u : (e >> 9) * 128u) + piece;
+        // prefetch the entry and the indices of this warp's next block (NB blocks ahead)
         uint32_t e_n = 0;
         int4 qa_n = make_int4(-1, -1, -1, -1), qb_n = qa_n;
-        if (i + 8 < nsteps) {
-          e_n = lds_u16(steps0 + 2u * (uint32_t)(i + 8));
+        if (ib + NB < nblocks) {
+          e_n = lds_u16(list0 + 2u * (uint32_t)(ib + NB));
           qa_n = load_idx(e_n, 0);
           if (kps == 2) qb_n = load_idx(e_n, 1);
         }
         __syncwarp();
-        c0 = prof ? clock64() : 0;
-        mbar_wait(bar_empty, phase);
-        if (prof) { pw_empty += clock64() - c0; ++p_steps; }
-        phase ^= 1;
+        if (live) {
+          c0 = prof ? clock64() : 0;
+          mbar_wait(bar_empty, phase);                         // the MMAs that read the stage's previous tile are done
+          if (prof) { pw_empty += clock64() - c0; ++p_steps; }
+          phase ^= 1;
 #pragma unroll
-        for (int q = 0; q < 8; ++q) {
-          if (A.dbg & 1) break;
-          const int4 ii = lds128i(scr_rd + 16u * q);
-          const int idx[4] = {ii.x, ii.y, ii.z, ii.w};
+          for (int q = 0; q < 8; ++q) {
+            if (A.dbg & 1) break;
+            const int4 ii = lds128i(scr_rd + 16u * q);
+            const int idx[4] = {ii.x, ii.y, ii.z, ii.w};
 #pragma unroll
-          for (int rr = 0; rr < 4; ++rr) {
-            const int r = 4 * q + rr;                        // row 4r + o; (4r + o) & 7 = 4 (r & 1) + o
-            const uint32_t dst = a_stage + (uint32_t)r * 512u + dst_lane + (uint32_t)((c8 ^ (4 * (r & 1) + o)) << 4);
-            const uint32_t off = (uint32_t)max(idx[rr], 0) * row_bytes + cbytes;
-            cp_async16_zfill(dst, in_bytes + off, (idx[rr] >= 0 && !(A.dbg & 16)) ? 16u : 0u);
+            for (int rr = 0; rr < 4; ++rr) {
+              const int r = 4 * q + rr;                        // row 4r + o; (4r + o) & 7 = 4 (r & 1) + o
+              const uint32_t dst = a_stage + (uint32_t)r * 512u + dst_lane + (uint32_t)((c8 ^ (4 * (r & 1) + o)) << 4);
+              const uint32_t off = (uint32_t)max(idx[rr], 0) * row_bytes + cbytes;
+              cp_async16_zfill(dst, in_bytes + off, (idx[rr] >= 0 && !(A.dbg & 16)) ? 16u : 0u);
+            }
           }
+          cp_async_commit();
+          c0 = prof ? clock64() : 0;
+          cp_async_wait<0>();                                  // this lane's pieces have landed ...
+          if (prof) pw_data += clock64() - c0;
+          fence_proxy_async();                                 // ... and are visible to the tensor core (async proxy)
+          __syncwarp();
+          if (lane == 0) mbar_arrive(bar_full);
         }
-        cp_async_commit();
-        c0 = prof ? clock64() : 0;
-        cp_async_wait<0>();                                  // this lane's pieces have landed ...
-        if (prof) pw_data += clock64() - c0;
-        fence_proxy_async();                                 // ... and are visible to the tensor core (async proxy)
-        __syncwarp();
-        if (lane == 0) mbar_arrive(bar_full);
         e = e_n; qa = qa_n; qb = qb_n;
       }
-      gbase += nsteps;
+      gblk += nblocks;
       __syncwarp();                                          // every lane has read its last list entry
       if (lane == 0) mbar_arrive(smem_u32(bar_list_empty + buf));
     }
     if (prof && warp == 0 && lane == 0) {
-      long long* o = A.prof + (size_t)blockIdx.x * 16;
-      o[0] = clock64() - p_t0; o[1] = pw_empty; o[2] = pw_data; o[3] = pw_list; o[4] = p_steps;
+      long long* po = A.prof + (size_t)blockIdx.x * 16;
+      po[0] = clock64() - p_t0; po[1] = pw_empty; po[2] = pw_data; po[3] = pw_list; po[4] = p_steps;
     }
   } else if (warp == kB2UtilWarp) {
-    // ===================== utility warp: step lists, weight tiles, index prefetch =====================
-    // Step list of a group: lane = offset step kk; entries ordered (kk, chunk, tile), tiles without a neighbour at kk
-    // skipped.  entry = kk | chunk << 5 | tile << 10 | first-of-(kk,chunk) << 12 | last-of-(kk,chunk) << 13
+    // ===================== utility warp: block lists, weight tiles, index prefetch =====================
+    // Block list of a group: lane = offset step kk; entries ordered (kk, chunk); offsets at which no tile of the group has
+    // a neighbour are skipped.  entry = kk | live-tile nibble << 5 | chunk << 9
     auto build_list = [&](int g, int jj) {
       const int buf = jj & 1;
       mbar_wait(smem_u32(bar_list_empty + buf), ((uint32_t)(jj >> 1) & 1u) ^ 1u);
       const int tile_first = g * T;
       const int Tr = min(T, A.n_tiles - tile_first);
-      uint16_t* steps = reinterpret_cast<uint16_t*>(lists) + buf * kB2ListCap;
+      uint16_t* blocks = reinterpret_cast<uint16_t*>(lists) + buf * kB2ListCap;
       uint32_t tmask[T];
 #pragma unroll
       for (int t = 0; t < T; ++t)                                   // all loads in flight together
@@ -300,134 +315,122 @@ __global__ void __launch_bounds__(kB2Threads, 1) conv_bf2_kernel(const __grid_co
           if (t >= Tr) break;
           uint32_t m = tmask[t];
           m &= K >= 32 ? 0xffffffffu : ((1u << K) - 1u);
-          if (m == 0) m = 1;                                        // a tile always runs at least one step (zero rows)
+          if (m == 0) m = 1;                                        // a tile always runs at least one block (zero rows)
           const uint32_t live = kps == 1 ? (m >> lane) & 1u : ((m >> (2 * lane)) & 3u) != 0;
           nib |= live << t;
         }
       }
-      const int cnt = NCHUNK * __popc(nib);
+      const int cnt = nib ? NCHUNK : 0;
       const int off = warp_inclusive_scan(cnt) - cnt;
-      int w = off;
-      if (nib) {
-        const int t_first = __ffs(nib) - 1, t_last = 31 - __clz(nib);
+      if (nib)
         for (int c = 0; c < NCHUNK; ++c)
-          for (int t = t_first; t <= t_last; ++t)
-            if ((nib >> t) & 1u) {
-              if (w < kB2ListCap)
-                steps[w] = (uint16_t)(lane | (c << 5) | (t << 10) | ((t == t_first) << 12) | ((t == t_last) << 13));
-              ++w;
-            }
-      }
+          if (off + c < kB2ListCap) blocks[off + c] = (uint16_t)(lane | (nib << 5) | (c << 9));
       const int total = __shfl_sync(0xffffffffu, off + cnt, 31);
-      if (lane == 0) s_nsteps[buf] = (uint32_t)min(total, kB2ListCap);
+      if (lane == 0) s_nblocks[buf] = (uint32_t)min(total, kB2ListCap);
       __syncwarp();
       if (lane == 0) mbar_arrive(smem_u32(bar_list_full + buf));
     };
-    // All lanes pull the neighbour-table lines of the steps kIdxAhead ahead into L2 (the table is 27 x 4 B per row,
-    // larger than the feature maps, and streams from DRAM; the producers' index loads then hit L2 and their
-    // three-step register prefetch covers the latency).  Lane 0 also feeds the weight ring.
-    constexpr int kIdxAhead = 24;
+    // All lanes pull the neighbour-table lines of the blocks kIdxAhead ahead into L2 (the table is 27 x 4 B per row, larger
+    // than the feature maps, and streams from DRAM; the producers' index loads then hit L2).  lane = (tile, offset of the
+    // block, 128 B line of the tile's 512 B index slice).  Lane 0 also feeds the weight ring.
+    constexpr int kIdxAhead = 8;
     const uint8_t* packed = reinterpret_cast<const uint8_t*>(A.packed) + (size_t)blockIdx.y * KS * NCHUNK * B_STAGE;
     const int* tbl = A.tbl;
     const int tbl_stride = A.tbl_stride;
-    int bs = 0;
-    uint32_t bphase = 1;
+    int gblk = 0;
     int j = 0;
     build_list((int)blockIdx.x, 0);
 #pragma unroll 1
     for (int g = (int)blockIdx.x; g < n_groups; g += gstep, ++j) {
       if (g + gstep < n_groups) build_list(g + gstep, j + 1);
       const int buf = j & 1;
-      const int nsteps = (int)s_nsteps[buf];
-      const uint32_t steps0 = lists0 + (uint32_t)buf * (kB2ListCap * 2);
-      const int tile0 = g * T * kBM;
-      const int row_end = min(n_out, tile0 + T * kBM);
-      auto prefetch_idx = [&](int i) {
-        if (i >= nsteps || lane >= 4 * kps || (A.dbg & 64)) return;
-        const uint32_t e = lds_u16(steps0 + 2u * (uint32_t)i);
-        if (((e >> 5) & 31u) != 0u) return;                      // all chunks of an (offset, tile) use the same indices
-        const int k = (int)(e & 31u) * kps + (lane >> 2);
-        const int row = tile0 + (int)((e >> 10) & 3u) * kBM + 32 * (lane & 3);     // 128 rows x 4 B = four 128 B lines
+      const int nblocks = (int)s_nblocks[buf];
+      const uint32_t list0 = lists0 + (uint32_t)buf * (kB2ListCap * 2);
+      const int row_end = min(n_out, (g + 1) * T * kBM);
+      auto prefetch_idx = [&](int ib) {
+        const int pt = lane >> 3, ps = (lane >> 2) & 1, pl = lane & 3;
+        if (ib >= nblocks || pt >= T || ps >= kps || (A.dbg & 64)) return;
+        const uint32_t e = lds_u16(list0 + 2u * (uint32_t)ib);
+        if ((e >> 9) != 0u || !((e >> (5 + pt)) & 1u)) return;      // all chunks of an offset use the same indices
+        const int k = (int)(e & 31u) * kps + ps;
+        const int row = (g * T + pt) * kBM + 32 * pl;                        // 128 rows x 4 B = four 128 B lines
         if (k < K && row < row_end) asm volatile("prefetch.global.L2 [%0];" ::"l"(tbl + (size_t)k * tbl_stride + row));
       };
-      for (int i = 0; i < kIdxAhead; ++i) prefetch_idx(i);
+      for (int ib = 0; ib < kIdxAhead; ++ib) prefetch_idx(ib);
 #pragma unroll 1
-      for (int i = 0; i < nsteps; ++i) {
-        prefetch_idx(i + kIdxAhead);
-        const uint32_t e = lds_u16(steps0 + 2u * (uint32_t)i);
-        if (!((e >> 12) & 1u)) continue;
+      for (int ib = 0; ib < nblocks; ++ib) {
+        prefetch_idx(ib + kIdxAhead);
         if (lane == 0) {
-          const int bstep = (int)(e & 31u) * NCHUNK + (int)((e >> 5) & 31u);
-          mbar_wait(smem_u32(bar_b_empty + bs), bphase);
-          const uint32_t bar = smem_u32(bar_b_full + bs);
+          const uint32_t e = lds_u16(list0 + 2u * (uint32_t)ib);
+          const int gb = gblk + ib, slot = gb % SB;
+          const int bstep = (int)(e & 31u) * NCHUNK + (int)(e >> 9);
+          mbar_wait(smem_u32(bar_b_empty + slot), ((uint32_t)(gb / SB) & 1u) ^ 1u);
+          const uint32_t bar = smem_u32(bar_b_full + slot);
           if (A.dbg & 4) {
             mbar_arrive(bar);
           } else {
             mbar_arrive_expect_tx(bar, B_STAGE);
-            bulk_copy_g2s(smem_u32(b_ring + (size_t)bs * B_STAGE), packed + (size_t)bstep * B_STAGE, B_STAGE, bar);
+            bulk_copy_g2s(smem_u32(b_ring + (size_t)slot * B_STAGE), packed + (size_t)bstep * B_STAGE, B_STAGE, bar);
           }
         }
-        if (++bs == SB) { bs = 0; bphase ^= 1; }
         __syncwarp();
       }
+      gblk += nblocks;
     }
-  } else if (warp == kB2MmaWarp) {
-    // ===================== MMA issuer =====================
-    // The whole warp walks the list with warp-uniform control flow and values (the entry is broadcast with a shuffle so
-    // that the compiler keeps descriptors and barrier addresses in uniform registers); one elected lane issues.
-    {
-      constexpr uint32_t idesc = make_idesc_bf16(kBM, COUT);
-      constexpr uint32_t desc_hi = 64u | (1u << 14) | (2u << 29);   // SBO = 1024 B, version 1, SWIZZLE_128B
-      const uint32_t a_lo0 = ((smem_u32(a_ring) >> 4) & 0x3FFF) | (1u << 16);
-      const uint32_t b_lo0 = ((smem_u32(b_ring) >> 4) & 0x3FFF) | (1u << 16);
-      const uint32_t bar_a_full0 = smem_u32(bar_a_full), bar_a_empty0 = smem_u32(bar_a_empty);
-      const uint32_t bar_b_full0 = smem_u32(bar_b_full), bar_b_empty0 = smem_u32(bar_b_empty);
-      // (A slice, B slice) of the six MMAs of a step, small terms first; a slice = 32 B = 16 BF16 k positions.
-      //   Cin >= 32: A = [hi 0-15 | hi 16-31 | lo 0-15 | lo 16-31], B = [w1 0-15 | w1 16-31 | w2 0-15 | w2 16-31]
-      //              pairs (2,0) (3,1) (0,2) (1,3) (0,0) (1,1)
-      //   Cin == 16: A = [hi k0 | lo k0 | hi k1 | lo k1],            B = [w1 k0 | w2 k0 | w1 k1 | w2 k1]
-      //              pairs (1,0) (0,1) (3,2) (2,3) (0,0) (2,2)
-      const bool leader = elect_one();
-      int as = 0, bs = -1;
-      uint32_t a_phase = 0, b_phase = 1;
-      int j = 0;
-      long long mw_a = 0, mw_b = 0, mw_acc = 0, mw_list = 0, m_steps = 0;
-      const bool prof = A.prof != nullptr;
-      const long long m_t0 = prof ? clock64() : 0;
-      for (int g = (int)blockIdx.x; g < n_groups; g += gstep, ++j) {
-        const int buf = j & 1;
-        long long c0 = prof ? clock64() : 0;
-        mbar_wait(smem_u32(bar_list_full + buf), (uint32_t)(j >> 1) & 1u);
-        if (prof) { const long long c1 = clock64(); mw_list += c1 - c0; c0 = c1; }
-        mbar_wait(smem_u32(bar_acc_empty + buf), ((uint32_t)(j >> 1) & 1u) ^ 1u);   // the epilogue has drained this accumulator set
-        if (prof) mw_acc += clock64() - c0;
-        tc_fence_after();
-        const int nsteps = __shfl_sync(0xffffffffu, (int)s_nsteps[buf], 0);
-        const uint32_t steps0 = lists0 + (uint32_t)buf * (kB2ListCap * 2);
-        const uint32_t d0 = tmem_base + (uint32_t)(buf * Cfg::ACC_BUF);
-        uint32_t started = 0;
-        uint32_t e_next = lds_u16(steps0);
+  } else if (warp < Cfg::EPI_WARP0) {
+    // ===================== MMA warps: warp t issues the MMAs of tile t =====================
+    // One issuing thread needs ~500-700 clk per step for six tcgen05.mma and a commit (measured), more than the gather;
+    // with a warp per tile the T accumulators advance in parallel.  Warp-uniform control flow and values (the entry is
+    // broadcast with a shuffle) keep descriptors and barrier addresses in uniform registers; one elected lane issues.
+    const int t = warp - kB2MmaWarp0;
+    constexpr uint32_t idesc = make_idesc_bf16(kBM, COUT);
+    constexpr uint32_t desc_hi = 64u | (1u << 14) | (2u << 29);   // SBO = 1024 B, version 1, SWIZZLE_128B
+    const uint32_t a_lo0 = ((smem_u32(a_ring) >> 4) & 0x3FFF) | (1u << 16);
+    const uint32_t b_lo0 = ((smem_u32(b_ring) >> 4) & 0x3FFF) | (1u << 16);
+    const uint32_t bar_a_full0 = smem_u32(bar_a_full), bar_a_empty0 = smem_u32(bar_a_empty);
+    const uint32_t bar_b_full0 = smem_u32(bar_b_full), bar_b_empty0 = smem_u32(bar_b_empty);
+    // (A slice, B slice) of the six MMAs of a tile and block, small terms first; a slice = 32 B = 16 BF16 k positions.
+    //   Cin >= 32: A = [hi 0-15 | hi 16-31 | lo 0-15 | lo 16-31], B = [w1 0-15 | w1 16-31 | w2 0-15 | w2 16-31]
+    //              pairs (2,0) (3,1) (0,2) (1,3) (0,0) (1,1)
+    //   Cin == 16: A = [hi k0 | lo k0 | hi k1 | lo k1],            B = [w1 k0 | w2 k0 | w1 k1 | w2 k1]
+    //              pairs (1,0) (0,1) (3,2) (2,3) (0,0) (2,2)
+    const bool leader = elect_one();
+    uint32_t a_ph = 0;                                            // phase bit per slot of this tile's a_full barriers
+    int gblk = 0;
+    int j = 0;
+    long long mw_a = 0, mw_b = 0, mw_acc = 0, mw_list = 0, m_steps = 0;
+    const long long m_t0 = prof ? clock64() : 0;
+    for (int g = (int)blockIdx.x; g < n_groups; g += gstep, ++j) {
+      const int buf = j & 1;
+      long long c0 = prof ? clock64() : 0;
+      mbar_wait(smem_u32(bar_list_full + buf), (uint32_t)(j >> 1) & 1u);
+      if (prof) { const long long c1 = clock64(); mw_list += c1 - c0; c0 = c1; }
+      mbar_wait(smem_u32(bar_acc_empty + buf), ((uint32_t)(j >> 1) & 1u) ^ 1u);   // the epilogue has drained this accumulator set
+      if (prof) mw_acc += clock64() - c0;
+      tc_fence_after();
+      const int nblocks = __shfl_sync(0xffffffffu, (int)s_nblocks[buf], 0);
+      const uint32_t list0 = lists0 + (uint32_t)buf * (kB2ListCap * 2);
+      const uint32_t d = tmem_base + (uint32_t)(buf * Cfg::ACC_BUF + t * Cfg::ACC_STRIDE);
+      uint32_t acc = 0;
+      uint32_t e_next = lds_u16(list0);
 #pragma unroll 1
-        for (int i = 0; i < nsteps; ++i) {
-          const uint32_t e = __shfl_sync(0xffffffffu, e_next, 0);
-          e_next = lds_u16(steps0 + 2u * (uint32_t)min(i + 1, nsteps - 1));
-          const int t = (int)((e >> 10) & 3u);
-          if ((e >> 12) & 1u) {                                     // first tile of a new weight stage
-            if (++bs == SB) bs = 0;
-            if (bs == 0) b_phase ^= 1;
-            c0 = prof ? clock64() : 0;
-            mbar_wait(bar_b_full0 + 8 * bs, b_phase);
-            if (prof) mw_b += clock64() - c0;
-          }
+      for (int ib = 0; ib < nblocks; ++ib) {
+        const uint32_t e = __shfl_sync(0xffffffffu, e_next, 0);
+        e_next = lds_u16(list0 + 2u * (uint32_t)min(ib + 1, nblocks - 1));
+        const int gb = gblk + ib, slot = gb & (NB - 1), bslot = gb % SB;
+        const bool live = (e >> (5 + t)) & 1u;
+        c0 = prof ? clock64() : 0;
+        mbar_wait(bar_b_full0 + 8 * bslot, (uint32_t)(gb / SB) & 1u);     // every block: this warp sees every phase
+        if (prof) mw_b += clock64() - c0;
+        if (live) {
+          const int stage = slot * T + t;
           c0 = prof ? clock64() : 0;
-          mbar_wait(bar_a_full0 + 8 * as, a_phase);
+          mbar_wait(bar_a_full0 + 8 * stage, (a_ph >> slot) & 1u);
           if (prof) { mw_a += clock64() - c0; ++m_steps; }
+          a_ph ^= 1u << slot;
           tc_fence_after();
-          const uint32_t d = d0 + (uint32_t)(t * Cfg::ACC_STRIDE);
-          const uint32_t a_lo = a_lo0 + (uint32_t)as * (kB2AStage >> 4);
-          const uint32_t b_lo = b_lo0 + (uint32_t)bs * (B_STAGE >> 4);
-          const uint32_t acc = (started >> t) & 1u;
-          started |= 1u << t;
+          const uint32_t a_lo = a_lo0 + (uint32_t)stage * (kB2AStage >> 4);
+          const uint32_t b_lo = b_lo0 + (uint32_t)bslot * (B_STAGE >> 4);
           if (leader && !(A.dbg & 2)) {
             const uint64_t hi64 = (uint64_t)desc_hi << 32;
             if (kps == 1) {
@@ -446,30 +449,34 @@ __global__ void __launch_bounds__(kB2Threads, 1) conv_bf2_kernel(const __grid_co
               umma_bf16_ss(d, hi64 | (a_lo + 4u), hi64 | (b_lo + 4u), idesc, 1u);
             }
           }
+          acc = 1u;
           if (leader) {
-            umma_commit(bar_a_empty0 + 8 * as);                       // gathered tile reusable once read
-            if ((e >> 13) & 1u) umma_commit(bar_b_empty0 + 8 * bs);   // weight tile: last tile of the stage
+            umma_commit(bar_a_empty0 + 8 * stage);                  // the gathered tile is reusable once read ...
+            umma_commit(bar_b_empty0 + 8 * bslot);                  // ... and so is this warp's share of the weight tile
           }
-          __syncwarp();
-          if (++as == SA) { as = 0; a_phase ^= 1; }
-        }
-        if (leader) {
-          umma_commit(smem_u32(bar_acc_full + buf));                  // the group's accumulators are complete
-          mbar_arrive(smem_u32(bar_list_empty + buf));
+        } else {
+          if (leader) mbar_arrive(bar_b_empty0 + 8 * bslot);        // dead tile: nothing to read
         }
         __syncwarp();
       }
-      if (prof && lane == 0) {
-        long long* o = A.prof + (size_t)blockIdx.x * 16;
-        o[5] = clock64() - m_t0; o[6] = mw_a; o[7] = mw_b; o[8] = mw_acc; o[9] = mw_list; o[10] = m_steps;
+      gblk += nblocks;
+      if (leader) {
+        if (acc) umma_commit(smem_u32(bar_acc_full + buf));         // this tile's accumulator is complete
+        else mbar_arrive(smem_u32(bar_acc_full + buf));             // tile past the end of the tensor: nothing issued
+        mbar_arrive(smem_u32(bar_list_empty + buf));
       }
+      __syncwarp();
+    }
+    if (prof && t == 0 && lane == 0) {
+      long long* po = A.prof + (size_t)blockIdx.x * 16;
+      po[5] = clock64() - m_t0; po[6] = mw_a; po[7] = mw_b; po[8] = mw_acc; po[9] = mw_list; po[10] = m_steps;
     }
   } else {
     // ===================== epilogue warps: TMEM -> staged rows -> coalesced BN / residual / activation / stores ==========
     // A warp reads the accumulator rows of its TMEM lane quarter (lane = row), stages 32 (16) channels per row in shared
     // memory and re-reads them with 8 (4) lanes per row, so that every global access is a whole 128 B (64 B) row piece.
     const int g4 = warp & 3;
-    const uint32_t stg = smem_u32(epi) + (uint32_t)(warp - kB2EpiWarp0) * (32 * kB2EpiRow);
+    const uint32_t stg = smem_u32(epi) + (uint32_t)(warp - Cfg::EPI_WARP0) * (32 * kB2EpiRow);
     const float* __restrict__ scale = A.scale ? A.scale + cblk : nullptr;
     const float* __restrict__ shift = A.shift ? A.shift + cblk : nullptr;
     const int act = A.act, res_after = A.res_after_act;
@@ -627,18 +634,18 @@ static int b2_cout_block(int Cout) {
 }
 bool bf2_supported(int Cin, int Cout) { return (Cin == 16 || (Cin >= 32 && Cin % 32 == 0)) && b2_cout_block(Cout) != 0; }
 
-template <int COUT, int T, int SA, int SB>
+template <int COUT, int T>
 static int launch_b2(const B2Args& a, int Cout, cudaStream_t st) {
-  using Cfg = B2Cfg<COUT, T, SA, SB>;
+  using Cfg = B2Cfg<COUT, T>;
   static bool configured = false;
   if (!configured) {
-    S2D_CUDA(cudaFuncSetAttribute(conv_bf2_kernel<COUT, T, SA, SB>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                  Cfg::SMEM_BYTES));
+    S2D_CUDA(cudaFuncSetAttribute(conv_bf2_kernel<COUT, T>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
     configured = true;
   }
   B2Args b = a;
-  S2D_REQUIRE(a.ksteps * a.nchunk * T <= kB2ListCap, "s2d_conv_fwd(bf16x2): %d x %d x %d contraction steps per tile group exceed %d",
-              a.ksteps, a.nchunk, T, kB2ListCap);
+  S2D_REQUIRE(a.ksteps * a.nchunk <= kB2ListCap && a.nchunk <= 128,
+              "s2d_conv_fwd(bf16x2): %d x %d contraction blocks per tile group exceed %d (or more than 128 chunks)", a.ksteps,
+              a.nchunk, kB2ListCap);
   // persistent CTAs, one per SM: CTA b works on the tile groups b, b + grid, b + 2 grid, ...
   b.n_tiles = div_up(a.n_out, kBM);
   b.n_groups = div_up(b.n_tiles, T);
@@ -647,7 +654,7 @@ static int launch_b2(const B2Args& a, int Cout, cudaStream_t st) {
   if (gx < 1) gx = 1;
   if (gx > b.n_groups) gx = b.n_groups;
   const dim3 grid(gx, gy);
-  conv_bf2_kernel<COUT, T, SA, SB><<<grid, kB2Threads, Cfg::SMEM_BYTES, st>>>(b);
+  conv_bf2_kernel<COUT, T><<<grid, Cfg::THREADS, Cfg::SMEM_BYTES, st>>>(b);
   S2D_LAUNCH_CHECK();
   count_launches(1);
   return S2D_OK;
@@ -685,20 +692,10 @@ int conv_fwd_bf2(const s2d_conv_params& p, cudaStream_t st) {
   a.dbg = g_b2_dbg;
   a.prof = g_b2_prof;
   const int v = g_b2_variant;
-  if (cb == 128) {
-    if (v == 1) return launch_b2<128, 2, 8, 2>(a, p.Cout, st);
-    return launch_b2<128, 2, 8, 3>(a, p.Cout, st);
-  }
-  if (cb == 64) {
-    if (v == 1) return launch_b2<64, 2, 8, 4>(a, p.Cout, st);
-    return launch_b2<64, 4, 8, 4>(a, p.Cout, st);
-  }
-  if (cb == 32) {
-    if (v == 1) return launch_b2<32, 2, 8, 4>(a, p.Cout, st);
-    return launch_b2<32, 4, 8, 4>(a, p.Cout, st);
-  }
-  if (v == 1) return launch_b2<16, 2, 8, 4>(a, p.Cout, st);
-  return launch_b2<16, 4, 8, 4>(a, p.Cout, st);
+  if (cb == 128) return launch_b2<128, 2>(a, p.Cout, st);
+  if (cb == 64) return v == 1 ? launch_b2<64, 2>(a, p.Cout, st) : launch_b2<64, 4>(a, p.Cout, st);
+  if (cb == 32) return v == 1 ? launch_b2<32, 2>(a, p.Cout, st) : launch_b2<32, 4>(a, p.Cout, st);
+  return v == 1 ? launch_b2<16, 2>(a, p.Cout, st) : launch_b2<16, 4>(a, p.Cout, st);
 }
 
 int pack_weights_bf2(const float* W, int K, int Cin, int Cout, void* packed, cudaStream_t st) {

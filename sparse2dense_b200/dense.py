@@ -31,8 +31,8 @@ def conv_table(device, B, H, W, k, stride, pad):
     if hit is None:
         Ho, Wo = (H + 2 * pad - k) // stride + 1, (W + 2 * pad - k) // stride + 1
         n = B * Ho * Wo
-        tbl = torch.empty((k * k, n), dtype=torch.int32, device=device)
-        _lib.check(_lib.load().s2d_grid2d_table(B, H, W, k, k, stride, pad, tbl.data_ptr(), n, _stream()),
+        tbl = ops.alloc_table(k * k, n, device)
+        _lib.check(_lib.load().s2d_grid2d_table(B, H, W, k, k, stride, pad, tbl.data_ptr(), tbl.stride(0), _stream()),
                    "s2d_grid2d_table")
         hit = _TABLES[key] = (tbl, Ho, Wo)
     return hit
@@ -48,10 +48,11 @@ def tconv_tables(device, B, H, W, k, pad, stride=2):
         hit = []
         for py in range(stride):
             for px in range(stride):
-                tbl = torch.empty(((k // stride) ** 2, n), dtype=torch.int32, device=device)
+                tbl = ops.alloc_table((k // stride) ** 2, n, device)
                 rows = torch.empty((n,), dtype=torch.int32, device=device)
-                _lib.check(_lib.load().s2d_grid2d_tconv_table_s(B, H, W, k, stride, pad, py, px, tbl.data_ptr(), n,
-                                                                rows.data_ptr(), _stream()), "s2d_grid2d_tconv_table_s")
+                _lib.check(_lib.load().s2d_grid2d_tconv_table_s(B, H, W, k, stride, pad, py, px, tbl.data_ptr(),
+                                                                tbl.stride(0), rows.data_ptr(), _stream()),
+                           "s2d_grid2d_tconv_table_s")
                 hit.append((py, px, tbl, rows))
         _TABLES[key] = hit
     return hit
@@ -107,39 +108,38 @@ def fold_bn(bn, bias, cout, device):
 
 
 def conv_rows(x, weight_kio, tbl, n_out, scale=None, shift=None, act=ACT_NONE, residual=None, res_after_act=False,
-              out=None, out_rows=None, precision=ops.PRECISION_TF32X3, packed=None):
-    """One gather-GEMM launch.  x / out / residual: 2-D views with stride(1) == 1; weight_kio: [K,Cin,Cout]."""
+              out=None, out_rows=None, precision=ops.PRECISION_TF32X3, packed=None, out_split=None, want_split=True):
+    """One gather-GEMM launch.  x / out / residual: 2-D views with stride(1) == 1; weight_kio: [K,Cin,Cout].
+    ``packed``: a weight image for ``ops.effective_precision(precision, ...)`` or a dict precision -> image.
+    With the BF16-pair kernel the input is read in split-row form (the producer's twin when ``x`` carries one, else
+    converted here) and a freshly allocated result gets its own twin (``want_split``) for the next layer."""
     K, cin, cout = weight_kio.shape
     assert x.stride(1) == 1 and x.shape[1] == cin and tbl.shape[0] == K
+    fresh = out is None
     if out is None:
         out = torch.empty((n_out if out_rows is None else int(out_rows.numel()), cout), dtype=torch.float32,
                           device=x.device)
     assert out.stride(1) == 1 and out.shape[1] == cout
-    use_tc = precision != ops.PRECISION_FP32 and ops.tf32_supported(cin, cout)
+    prec = ops.effective_precision(precision, cin, cout, tbl)
     w = weight_kio
-    if use_tc:
-        w = packed if packed is not None else ops.pack_weights_tf32(weight_kio, precision)
-    p = _lib.ConvParams()
-    p.in_, p.weights, p.tbl = x.data_ptr(), w.data_ptr(), tbl.data_ptr()
-    p.scale = None if scale is None else scale.data_ptr()
-    p.shift = None if shift is None else shift.data_ptr()
-    p.residual = None if residual is None else residual.data_ptr()
-    p.out = out.data_ptr()
-    p.out_rows = None if out_rows is None else out_rows.data_ptr()
-    p.in_ld, p.out_ld = x.stride(0), out.stride(0)
-    p.res_ld = 0 if residual is None else residual.stride(0)
-    p.tbl_stride, p.K = tbl.stride(0), K
-    p.n_in, p.n_out, p.Cin, p.Cout = x.shape[0], n_out, cin, cout
-    p.act, p.res_after_act = act, int(bool(res_after_act))
-    p.precision = precision if use_tc else ops.PRECISION_FP32
-    ev = None
-    if ops.KERNEL_EVENTS is not None:
-        ev = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
-        ev[0].record()
-    _lib.check(_lib.load().s2d_conv_fwd(ctypes.byref(p), _stream()), "s2d_conv_fwd")
-    if ev is not None:
-        ev[1].record()
-        ops.KERNEL_EVENTS.append(((cin, cout, K, residual is not None, x.shape[0], n_out, int(p.precision)), ev[0], ev[1]))
+    if prec != ops.PRECISION_FP32:
+        if isinstance(packed, dict):
+            w = packed.get(prec)
+            if w is None:
+                w = packed[prec] = ops.pack_weights_tf32(weight_kio, prec)
+        else:
+            w = packed if packed is not None else ops.pack_weights_tf32(weight_kio, prec)
+    xs = None
+    if prec == ops.PRECISION_BF16X2:
+        xs = ops.rows_split(x)
+        if out_split is None and fresh and want_split and (cout % 32 == 0 or cout == 16):
+            out_split = torch.empty((out.shape[0], cout), dtype=torch.int32, device=x.device)
+    else:
+        out_split = None
+    ops.conv_launch(x, w, tbl, n_out, cin, cout, K, scale, shift, act, residual, res_after_act, out, out_rows, prec, xs,
+                    out_split)
+    if out_split is not None and fresh:
+        ops.set_split(out, out_split)
     return out
 
 
@@ -230,10 +230,7 @@ class DenseOps:
                 ky0, kx0 = (py + pad) % st, (px + pad) % st
                 taps = [w[:, :, ky0 + st * a, kx0 + st * c] for a in range(kh // st) for c in range(kw // st)]
                 kio = torch.stack(taps, 0).contiguous()       # [K, Cin, Cout]
-            packed = None
-            if self.precision != ops.PRECISION_FP32 and ops.tf32_supported(kio.shape[1], kio.shape[2]):
-                packed = ops.pack_weights_tf32(kio, self.precision)
-            return kio, packed
+            return kio, {}                                    # effective precision -> packed image (filled by conv_rows)
         return self.cache.get(("w", name, transposed_class, self.precision), [conv.weight], build)
 
     def _affine(self, name, conv, bn):
@@ -267,9 +264,17 @@ class DenseOps:
         if out is None:
             out = torch.empty((B * st * st * H * W, cout), dtype=torch.float32, device=x.device)
         scale, shift = self._affine(name, conv, bn)
+        cin = conv.weight.shape[0]
+        split = None
         for py, px, tbl, rows in tconv_tables(x.device, B, H, W, k, pad, st):
             kio, packed = self._conv_weights(name, conv, (py, px, pad, st))
-            conv_rows(x, kio, tbl, B * H * W, scale, shift, act, None, False, out, rows, self.precision, packed)
+            if split is None and out.is_contiguous() and cout % 32 == 0 and \
+                    ops.effective_precision(self.precision, cin, cout, tbl) == ops.PRECISION_BF16X2:
+                split = torch.empty(out.shape, dtype=torch.int32, device=x.device)   # one twin for the s*s classes
+            conv_rows(x, kio, tbl, B * H * W, scale, shift, act, None, False, out, rows, self.precision, packed,
+                      out_split=split)
+        if split is not None:
+            ops.set_split(out, split)
         return out, st * H, st * W
 
     def maxpool2(self, x, B, H, W):

@@ -301,11 +301,11 @@ def set_split(t, split):
     t._s2d_split = (split, t._version)
 
 
-def rows_split(x, cache=True):
+def rows_split(x, cache=False):
     """fp32 rows [n, C] (stride(1) == 1) -> split rows int32 [n, C]: per 32-channel chunk (or 16-channel row)
     [hi words | lo words], two BF16 per word (x = hi + lo to 16 mantissa bits) -- the operand format of PRECISION_BF16X2."""
     _need_cuda(x)
-    hit = get_split(x) if cache else None
+    hit = get_split(x)               # written by the epilogue of the layer that produced x
     if hit is not None:
         return hit
     assert x.dtype == torch.float32 and x.dim() == 2 and x.stride(1) == 1
@@ -327,8 +327,22 @@ def table_tile_masks(tbl, n_rows):
 
 
 def bf2_ok(cin, cout, tbl):
+    k = tbl.shape[0]
+    nchunk = 1 if cin == 16 else cin // 32
     return (cin == 16 or (cin >= 32 and cin % 32 == 0)) and cout % 16 == 0 and tbl.stride(0) % 4 == 0 and \
-        tbl.data_ptr() % 16 == 0 and tbl.shape[0] <= 27
+        tbl.data_ptr() % 16 == 0 and k <= 27 and nchunk <= 128 and -(-k // (2 if cin == 16 else 1)) * nchunk <= 1024
+
+
+def effective_precision(precision, cin, cout, tbl):
+    """What a conv launch actually runs: AUTO -> BF16X2 (conv_bf2.cu) where that kernel exists for the shape and table
+    layout, else the TF32-based AUTO of spconv_tc.cu; shapes without any tensor-core kernel -> FP32 (CUDA cores)."""
+    if precision in (PRECISION_AUTO, PRECISION_BF16X2):
+        if bf2_ok(cin, cout, tbl):
+            return PRECISION_BF16X2
+        precision = PRECISION_AUTO
+    if precision != PRECISION_FP32 and not tf32_supported(cin, cout):
+        return PRECISION_FP32
+    return precision
 
 
 def conv_launch(x, w_arg, tbl, n_out, cin, cout, k, scale=None, shift=None, act=0, residual=None, res_after_act=False,

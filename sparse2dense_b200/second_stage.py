@@ -115,7 +115,8 @@ class RoIHead(nn.Module):
         n = x.shape[0]
         key = (n, str(x.device))
         if key not in self._ident:
-            self._ident[key] = torch.arange(n, dtype=torch.int32, device=x.device).view(1, n)
+            self._ident[key] = ops.alloc_table(1, n, x.device)
+            self._ident[key][0].copy_(torch.arange(n, dtype=torch.int32, device=x.device))
         tbl = self._ident[key]
         mods = list(seq)
         j = 0
@@ -128,9 +129,7 @@ class RoIHead(nn.Module):
 
                 def build(m=m, bn=bn):
                     kio = m.weight.detach().float()[:, :, 0].t().contiguous().unsqueeze(0)       # [1, Cin, Cout]
-                    packed = None
-                    if D.precision != ops.PRECISION_FP32 and ops.tf32_supported(kio.shape[1], kio.shape[2]):
-                        packed = ops.pack_weights_tf32(kio, D.precision)
+                    packed = {}                                   # effective precision -> image (filled by conv_rows)
                     sc, sh = fold_bn(bn, m.bias, m.weight.shape[0], m.weight.device)
                     return kio, packed, sc, sh
                 src = [m.weight, m.bias] + ([bn.weight, bn.bias, bn.running_mean, bn.running_var] if bn is not None else [])

@@ -163,10 +163,16 @@ class SparseConvolution(SparseModule):
                                       "(use torch.no_grad() for inference or bn.train() for training)")
         scale, shift = self._folded(bn, x.features.device)
         n_out = ind.out_indices.shape[0]
-        packed = self._packed_weights() if self.precision != ops.PRECISION_FP32 else None
+        prec = ops.effective_precision(self.precision, self.in_channels, self.out_channels, ind.tbl)
+        packed = self._packed_weights(prec) if prec != ops.PRECISION_FP32 else None
+        masks = None
+        if prec == ops.PRECISION_BF16X2:                     # per-tile live-offset masks, once per rulebook
+            masks = ind.__dict__.get("tile_masks")
+            if masks is None:
+                masks = ind.tile_masks = ops.table_tile_masks(ind.tbl, n_out)
         feats = ops.spconv_fwd(x.features.contiguous(), self.weight.detach(), ind.tbl, n_out, scale, shift,
-                               None if residual is None else residual.contiguous(), relu, self.precision,
-                               packed=packed)
+                               None if residual is None else residual.contiguous(), relu, prec,
+                               packed=packed, tile_masks=masks)
         if self.subm:
             return x._like(feats)
         return x._like(feats, ind.out_indices, ind.out_shape, ind.out_index)
@@ -204,11 +210,11 @@ class SparseConvolution(SparseModule):
             self.__dict__["_fold_cache"] = cache
         return cache[1], cache[2]
 
-    def _packed_weights(self):
-        key = (self.weight.data_ptr(), self.weight._version, str(self.weight.device),
-               self.precision)
+    def _packed_weights(self, precision=None):
+        precision = self.precision if precision is None else precision
+        key = (self.weight.data_ptr(), self.weight._version, str(self.weight.device), precision)
         if self._packed is None or self._packed[0] != key:
-            self._packed = (key, ops.pack_weights_tf32(self.weight, self.precision))
+            self._packed = (key, ops.pack_weights_tf32(self.weight, precision))
         return self._packed[1]
 
 

@@ -32,7 +32,7 @@ def test_rows_split_bit_exact(c):
     rng = np.random.default_rng(c)
     x = (rng.normal(size=(1037, c)) * np.exp(rng.normal(size=(1037, c)) * 4)).astype(np.float32)
     x[3, 1] = 0.0
-    got = ops.rows_split(torch.from_numpy(x).cuda(), cache=False).cpu().numpy()
+    got = ops.rows_split(torch.from_numpy(x).cuda()).cpu().numpy()
     np.testing.assert_array_equal(got, split_ref(x))
 
 

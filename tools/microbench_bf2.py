@@ -69,7 +69,7 @@ def main():
         t_old = timeit(lambda: ops.spconv_fwd(feats, w, tbl, n, precision=old, packed=pk_old, out=out), flush, args.reps)
         pk = ops.pack_weights_tf32(w, ops.PRECISION_BF16X2)
         xs = ops.rows_split(feats)
-        t_split = timeit(lambda: ops.rows_split(feats, cache=False), flush, args.reps)
+        t_split = timeit(lambda: ops.rows_split(feats), flush, args.reps)
         line = f"subm {c:3d} N={n:7d} P={p:8d} pairs/27N={p / (27.0 * n):.3f} tile-tap live={live:.3f} | v5 {t_old:.3f} ms | split {t_split:.3f} ms"
         for v in [int(s) for s in args.variants.split(",")]:
             setv(v)
