@@ -216,10 +216,12 @@ __global__ void __launch_bounds__(kNmsTile) nms_mask_kernel(const float* __restr
                                                             const int* __restrict__ order, int order_stride,
                                                             const int* __restrict__ counts, int n_fixed,
                                                             float thresh, int words,
-                                                            unsigned long long* __restrict__ mask) {
+                                                            unsigned long long* __restrict__ mask, int blk_lo,
+                                                            const int* __restrict__ done) {
   const int b = blockIdx.z, rb = blockIdx.y, cbk = blockIdx.x;
   const int n = counts ? counts[b] : n_fixed;
   if (cbk < rb || rb * kNmsTile >= n || cbk * kNmsTile >= n) return;      // the sweep reads only words >= the row block
+  if (cbk < blk_lo || (done && done[b])) return;                          // an earlier stage computed it / the sweep has finished
   const float* bx = boxes + (size_t)b * sample_stride * 7;
   const int* ord = order ? order + (size_t)b * order_stride : nullptr;
   __shared__ float s_box[kNmsTile * 7];
@@ -256,11 +258,22 @@ __global__ void __launch_bounds__(kNmsTile) nms_mask_kernel(const float* __restr
 // Greedy sweep of iou3d_nms.cpp:118-131 by one warp per sample (the running `remv` mask lives in two registers per
 // lane), stopped after post_max kept boxes (rotate_nms_pcdet slices [:post_max_size]); then the kept detections
 // are gathered.  keep[b][k] = position in the sorted order.
+//
+// Staged form (s2d_centerhead_select): the reference sweep stops at the post_max-th kept box, so only the pairs (i, j) with
+// i < j <= i_stop are ever consulted -- with 4096 candidates and 500 kept that is a few percent of the IoU triangle.  Stage s
+// computes the mask blocks below `limit_s` candidates that earlier stages have not, then sweeps the first limit_s candidates
+// from scratch; when the sweep ends inside the stage (post_max kept, or all n candidates seen) it raises done[b] and the
+// later stages' blocks exit at once.  The last stage has limit = pre_max, i.e. it is the unstaged algorithm: keep sets are
+// identical by construction.
 __global__ void __launch_bounds__(32) nms_sweep_kernel(const unsigned long long* __restrict__ mask, int words,
                                                        const int* __restrict__ counts, int n_fixed, int post_max,
-                                                       int* __restrict__ keep, int* __restrict__ n_keep) {
+                                                       int* __restrict__ keep, int* __restrict__ n_keep, int limit,
+                                                       int* __restrict__ done) {
   const int b = blockIdx.x, lane = threadIdx.x;
-  const int n = counts ? counts[b] : n_fixed;
+  const int n_all = counts ? counts[b] : n_fixed;
+  if (done && done[b]) return;
+  const int n = min(n_all, limit);
+  const int live_words = min(words, (n + kNmsTile - 1) / kNmsTile);   // words the stages so far have computed
   const unsigned long long* m = mask + (size_t)b * kNmsMaxBoxes * words;
   int* kp = keep + (size_t)b * post_max;
   unsigned long long r0 = 0ull, r1 = 0ull;      // remv words lane and lane + 32
@@ -272,10 +285,13 @@ __global__ void __launch_bounds__(32) nms_sweep_kernel(const unsigned long long*
     if (lane == 0) kp[nk] = i;
     ++nk;
     const unsigned long long* row = m + (size_t)i * words;
-    if (lane >= nb && lane < words) r0 |= row[lane];
-    if (lane + 32 >= nb && lane + 32 < words) r1 |= row[lane + 32];
+    if (lane >= nb && lane < live_words) r0 |= row[lane];
+    if (lane + 32 >= nb && lane + 32 < live_words) r1 |= row[lane + 32];
   }
-  if (lane == 0) n_keep[b] = nk;
+  if (lane == 0) {
+    n_keep[b] = nk;
+    if (done) done[b] = (nk >= post_max || n >= n_all) ? 1 : 0;
+  }
 }
 
 __global__ void __launch_bounds__(128) gather_detections_kernel(const float* __restrict__ boxes,
@@ -310,7 +326,7 @@ __global__ void __launch_bounds__(128) gather_detections_kernel(const float* __r
 }
 
 struct SelectWs {
-  int* order; int* counts; int* keep; unsigned long long* mask; size_t total;
+  int* order; int* counts; int* keep; int* done; unsigned long long* mask; size_t total;
 };
 static SelectWs carve_select(void* ws, int batch, int pre_max, int post_max) {
   Carver c(ws);
@@ -318,6 +334,7 @@ static SelectWs carve_select(void* ws, int batch, int pre_max, int post_max) {
   w.order = c.take<int>((size_t)batch * pre_max);
   w.counts = c.take<int>(batch);
   w.keep = c.take<int>((size_t)batch * post_max);
+  w.done = c.take<int>(batch);
   w.mask = c.take<unsigned long long>((size_t)batch * kNmsMaxBoxes * (kNmsMaxBoxes / kNmsTile));
   w.total = c.off;
   return w;
@@ -363,15 +380,24 @@ extern "C" int s2d_centerhead_select(const unsigned long long* keys, const float
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const int words = kNmsMaxBoxes / kNmsTile;
   topk_sort_kernel<<<batch, 1024, 0, st>>>(keys, cells, pre_max, w.order, w.counts);
-  const int blocks = div_up(pre_max, kNmsTile);
-  nms_mask_kernel<<<dim3(blocks, blocks, batch), kNmsTile, 0, st>>>(boxes, cells, w.order, pre_max, w.counts, 0,
-                                                                    iou_threshold, words, w.mask);
-  nms_sweep_kernel<<<batch, 32, 0, st>>>(w.mask, words, w.counts, 0, post_max, w.keep, n_out);
+  S2D_CUDA(cudaMemsetAsync(w.done, 0, sizeof(int) * batch, st));
+  int launches = 2;
+  int lo = 0;
+  for (int limit : {post_max + post_max / 4 + kNmsTile, 3 * post_max + kNmsTile, pre_max}) {
+    limit = min(limit, pre_max);
+    const int blocks = div_up(limit, kNmsTile);
+    if (blocks <= lo) continue;
+    nms_mask_kernel<<<dim3(blocks, blocks, batch), kNmsTile, 0, st>>>(boxes, cells, w.order, pre_max, w.counts, 0,
+                                                                      iou_threshold, words, w.mask, lo, w.done);
+    nms_sweep_kernel<<<batch, 32, 0, st>>>(w.mask, words, w.counts, 0, post_max, w.keep, n_out, blocks * kNmsTile, w.done);
+    lo = blocks;
+    launches += 2;
+  }
   gather_detections_kernel<<<dim3(div_up(post_max, 128), batch), 128, 0, st>>>(
       boxes, scores, labels, cells, w.order, pre_max, w.keep, n_out, post_max, out_boxes, out_scores, out_labels,
       out_cells);
   S2D_LAUNCH_CHECK();
-  count_launches(4);
+  count_launches(launches);
   return S2D_OK;
 }
 
@@ -398,8 +424,8 @@ extern "C" int s2d_nms_sorted(const float* boxes, int n_boxes, float iou_thresho
   unsigned long long* mask = static_cast<unsigned long long*>(workspace);
   const int blocks = div_up(n_boxes, kNmsTile);
   nms_mask_kernel<<<dim3(blocks, blocks, 1), kNmsTile, 0, st>>>(boxes, 0, nullptr, 0, nullptr, n_boxes, iou_threshold,
-                                                                words, mask);
-  nms_sweep_kernel<<<1, 32, 0, st>>>(mask, words, nullptr, n_boxes, n_boxes, keep, n_keep);
+                                                                words, mask, 0, nullptr);
+  nms_sweep_kernel<<<1, 32, 0, st>>>(mask, words, nullptr, n_boxes, n_boxes, keep, n_keep, n_boxes, nullptr);
   S2D_LAUNCH_CHECK();
   count_launches(2);
   return S2D_OK;

@@ -17,6 +17,7 @@ PRECISION_AUTO = 4            # the library picks TF32_BF16C or TF32X3 per layer
 PRECISION_BF16X2 = 5          # activations and weights pre-split into BF16 pairs, three BF16 MMAs (conv_bf2.cu): ~4e-6 per layer
 PRECISION_NAMES = {"fp32": PRECISION_FP32, "tf32": PRECISION_TF32, "tf32x3": PRECISION_TF32X3,
                    "tf32_bf16c": PRECISION_TF32_BF16C, "auto": PRECISION_AUTO, "bf16x2": PRECISION_BF16X2}
+PRECISION_NAMES_INV = {v: k for k, v in PRECISION_NAMES.items()}
 
 
 # When set to a list, spconv_fwd appends (key, start_event, end_event) per launch so that bench.py can
@@ -346,7 +347,8 @@ def effective_precision(precision, cin, cout, tbl):
 
 
 def conv_launch(x, w_arg, tbl, n_out, cin, cout, k, scale=None, shift=None, act=0, residual=None, res_after_act=False,
-                out=None, out_rows=None, precision=PRECISION_FP32, x_split=None, out_split=None, tile_masks=None):
+                out=None, out_rows=None, precision=PRECISION_FP32, x_split=None, out_split=None, tile_masks=None,
+                kind="dense"):
     """One ``s2d_conv_fwd`` call.  x / out / residual / x_split / out_split: 2-D row views with stride(1) == 1 (or None)."""
     p = _lib.ConvParams()
     p.in_, p.weights, p.tbl = _ptr(x), _ptr(w_arg), _ptr(tbl)
@@ -369,7 +371,7 @@ def conv_launch(x, w_arg, tbl, n_out, cin, cout, k, scale=None, shift=None, act=
     _lib.check(_lib.load().s2d_conv_fwd(_lib.ctypes.byref(p), _stream()), "s2d_conv_fwd")
     if ev is not None:
         ev[1].record()
-        KERNEL_EVENTS.append(((cin, cout, k, residual is not None, p.n_in, n_out, int(precision)), ev[0], ev[1]))
+        KERNEL_EVENTS.append(((cin, cout, k, residual is not None, p.n_in, n_out, int(precision), kind), ev[0], ev[1]))
 
 
 def spconv_fwd(feats, weight, tbl, n_out, scale=None, shift=None, residual=None, relu=False,
@@ -394,7 +396,7 @@ def spconv_fwd(feats, weight, tbl, n_out, scale=None, shift=None, residual=None,
         out_split = torch.empty((n_out, cout), dtype=torch.int32, device=feats.device) if split_ok else None
         w_arg = packed if packed is not None else pack_weights_tf32(weight, precision)
         conv_launch(None, w_arg, tbl, n_out, cin, cout, k, scale, shift, 1 if relu else 0, residual, False, out, None,
-                    precision, xs, out_split, tile_masks)
+                    precision, xs, out_split, tile_masks, kind="sparse")
         if out_split is not None:
             set_split(out, out_split)
         return out
@@ -419,7 +421,7 @@ def spconv_fwd(feats, weight, tbl, n_out, scale=None, shift=None, residual=None,
                                           _ptr(out), int(precision), _stream()), "s2d_spconv_fwd")
     if ev is not None:
         ev[1].record()
-        KERNEL_EVENTS.append(((cin, cout, k, residual is not None, feats.shape[0], n_out, int(precision)), ev[0], ev[1]))
+        KERNEL_EVENTS.append(((cin, cout, k, residual is not None, feats.shape[0], n_out, int(precision), "sparse"), ev[0], ev[1]))
     return out
 
 

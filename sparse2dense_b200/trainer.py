@@ -168,6 +168,7 @@ class DistillTrainer:
         self.sched = OneCycle(total_steps, lr_max, moms, div_factor, pct_start)
         self.max_norm = max_norm
         self.global_step = 0
+        self.events = None
         if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
             dist.broadcast(self.opt.flat_p, src=0)               # DDP: every rank starts from rank 0's weights
             for b in self.student.buffers():                     # ... and buffers (DDP broadcast_buffers: BN running stats)
@@ -183,11 +184,22 @@ class DistillTrainer:
         total.backward()
         return log
 
+    def _timed(self, name, fn):
+        """Run ``fn`` between two CUDA events when ``self.events`` is a list (bench.py's per-phase breakdown)."""
+        if self.events is None:
+            return fn()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        out = fn()
+        e1.record()
+        self.events.append((name, e0, e1))
+        return out
+
     def step(self, example):
         lr, mom = self.sched.step(self.global_step)
-        log = self.forward_backward(example)
-        self.opt.all_reduce()
-        norm = self.opt.step(lr, mom, self.max_norm)
+        log = self._timed("forward_backward", lambda: self.forward_backward(example))
+        self._timed("all_reduce", self.opt.all_reduce)
+        norm = self._timed("optimizer", lambda: self.opt.step(lr, mom, self.max_norm))
         self.global_step += 1
         log["grad_norm"] = norm[0]
         log["lr"], log["mom"] = lr, mom
