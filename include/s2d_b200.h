@@ -212,6 +212,14 @@ int s2d_conv_fwd(const s2d_conv_params* params, void* stream);
 int s2d_rows_split(const float* in, long long n_rows, int C, int in_ld, void* out, int out_ld, void* stream);
 /* tile_masks[t] = OR over the rows r of tile t (128 rows) and the offsets k < K (<= 31) of (tbl[k][r] >= 0) << k. */
 int s2d_table_tile_masks(const int* tbl, int tbl_stride, int K, int n_rows, int* tile_masks, void* stream);
+/* Row grouping for the tile kernel (conv_bf2.cu): a stable counting sort of the table's rows by the 9-bit key "which
+ * (dz, dy) offset triples k/3 have a neighbour" -> perm[p] = original row of position p, tbl_out[k][p] = tbl[k][perm[p]] and
+ * the tile masks of tbl_out.  A conv launched with tbl_out, out_rows = perm and these masks writes bit-identical results
+ * (each output row still sums its offsets in the same order) while skipping the (tile, offset) pairs grouping has emptied.
+ * Replaces nothing in the reference (spconv executes per-offset pair lists, spconv/ops.py indice_conv); K <= 27. */
+size_t s2d_table_group_rows_workspace_bytes(int n_rows);
+int s2d_table_group_rows(const int* tbl, int tbl_stride, int K, int n_rows, int* perm, int* tbl_out, int out_stride,
+                         int* tile_masks, void* workspace, size_t workspace_bytes, void* stream);
 
 /* Regular-grid neighbour tables for dense 2-D convolutions over NHWC rows (row = (b*H + y)*W + x).
  *   s2d_grid2d_table       : Conv2d(kh x kw, stride, pad): tbl i32 [kh*kw, B*Ho*Wo], -1 outside the map

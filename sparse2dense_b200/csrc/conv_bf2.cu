@@ -34,10 +34,9 @@
 
 namespace s2d {
 
-constexpr int kB2ProducerWarps = 8;
-constexpr int kB2Stages = 8;               // gathered-tile stages (one per producer warp)
-constexpr int kB2UtilWarp = 8;
-constexpr int kB2MmaWarp0 = 9;             // T MMA warps (one per tile of the group), then four epilogue warps
+// S gathered-tile stages, one producer warp each (warps 0..S-1); warp S = utility; warps S+1..S+T = MMA (one per tile of the
+// group); then four epilogue warps.  S = 8: one CTA per SM; S = 4: two CTAs per SM (half the ring each), whose independent
+// pipelines hide each other's barrier round trips.
 constexpr int kB2ListCap = 1024;           // (offset steps) x (chunks) of one tile group; host-checked
 constexpr int kB2AStage = kBM * 128;       // 128 rows x 128 B
 constexpr int kB2EpiRow = 144;             // staged accumulator row: 128 B + 16 B pad (conflict-free 16 B accesses)
@@ -63,14 +62,18 @@ __device__ __forceinline__ void sts32(uint32_t addr, int v) {
 // group: one weight tile and up to T gathered tiles (one per tile of the group that has a neighbour at that offset).
 // The eight gathered-tile stages form NB = 8 / T block slots; stage (slot, t) = slot * T + t always belongs to tile t, so
 // producer warp w = stage w and MMA warp t = tile t see every phase of "their" barriers whatever the masks skip.
-template <int COUT, int T_>
+template <int COUT, int T_, int S_>
 struct B2Cfg {
   static constexpr int T = T_;
-  static constexpr int NB = kB2Stages / T;                     // gathered-tile slots per tile (stage = slot * T + t)
-  static constexpr int SB = COUT >= 128 ? 3 : 4;               // weight-tile ring
-  static constexpr int WARPS = kB2MmaWarp0 + T + 4;
+  static constexpr int S = S_;
+  static constexpr int CTAS_PER_SM = S == 4 ? 2 : 1;
+  static constexpr int NB = S / T;                             // gathered-tile slots per tile (stage = slot * T + t)
+  static constexpr int SB = S == 4 ? (COUT >= 64 ? 2 : 4) : (COUT >= 128 ? 3 : 4);   // weight-tile ring
+  static constexpr int UTIL_WARP = S;
+  static constexpr int MMA_WARP0 = S + 1;
+  static constexpr int WARPS = MMA_WARP0 + T + 4;
   static constexpr int THREADS = 32 * WARPS;
-  static constexpr int EPI_WARP0 = kB2MmaWarp0 + T;
+  static constexpr int EPI_WARP0 = MMA_WARP0 + T;
   static constexpr int B_STAGE = COUT * 128;                   // COUT rows x [w1 (64 B) | w2 (64 B)]
   static constexpr int ACC_STRIDE = COUT < 32 ? 32 : COUT;
   static constexpr int ACC_BUF = T * ACC_STRIDE;               // one accumulator set (T tiles)
@@ -80,12 +83,14 @@ struct B2Cfg {
   static constexpr int LIST_BYTES = 2 * kB2ListCap * 2;
   static constexpr int EPI_BYTES = 4 * 32 * kB2EpiRow;
   static constexpr int BAR_BYTES = 512;
-  static constexpr int SMEM_BYTES = kB2Stages * kB2AStage + SB * B_STAGE + LIST_BYTES + EPI_BYTES + kB2ProducerWarps * 1024 + BAR_BYTES + 1024;
+  static constexpr int SMEM_BYTES = S * kB2AStage + SB * B_STAGE + LIST_BYTES + EPI_BYTES + S * 1024 + BAR_BYTES + 1024;
   static_assert(T == 2 || T == 4, "tiles per group");
-  static_assert(ACC_COLS <= 512, "TMEM budget");
-  static_assert(SMEM_BYTES <= 227 * 1024, "shared memory budget");
+  static_assert((S == 4 || S == 8) && NB >= 1 && (NB & (NB - 1)) == 0, "stage ring");
+  static_assert(ACC_COLS * CTAS_PER_SM <= 512, "TMEM budget");
+  static_assert(TMEM_COLS * CTAS_PER_SM <= 512, "TMEM budget");
+  static_assert((SMEM_BYTES + 1024) * CTAS_PER_SM <= 227 * 1024, "shared memory budget");
   static_assert(COUT % 16 == 0 && COUT >= 16 && COUT <= 128, "UMMA N constraint for M = 128");
-  static_assert(2 * kB2Stages + 2 * SB + 8 <= BAR_BYTES / 8 - 2, "barrier block");
+  static_assert(2 * S + 2 * SB + 8 <= BAR_BYTES / 8 - 2, "barrier block");
 };
 
 struct B2Args {
@@ -127,9 +132,11 @@ __device__ __forceinline__ void split_pair(float a, float b, uint32_t& hi, uint3
 // the per-slot barriers); the four epilogue warps drain a group's accumulators from one TMEM buffer while the next group
 // is gathered and multiplied into the other.
 //   block entry = kk | live-tile nibble << 5 | chunk << 9
-template <int COUT, int T>
-__global__ void __launch_bounds__(B2Cfg<COUT, T>::THREADS, 1) conv_bf2_kernel(const __grid_constant__ B2Args A) {
-  using Cfg = B2Cfg<COUT, T>;
+template <int COUT, int T, int S>
+__global__ void __launch_bounds__(B2Cfg<COUT, T, S>::THREADS, B2Cfg<COUT, T, S>::CTAS_PER_SM)
+conv_bf2_kernel(const __grid_constant__ B2Args A) {
+  using Cfg = B2Cfg<COUT, T, S>;
+  constexpr int kB2Stages = S, kB2ProducerWarps = S, kB2UtilWarp = Cfg::UTIL_WARP, kB2MmaWarp0 = Cfg::MMA_WARP0;
   constexpr int B_STAGE = Cfg::B_STAGE, NB = Cfg::NB, SB = Cfg::SB;
   const int NCHUNK = A.nchunk, K = A.K, KS = A.ksteps, kps = A.kps, n_out = A.n_out;
   const int cblk = blockIdx.y * COUT;
@@ -625,6 +632,141 @@ __global__ void __launch_bounds__(128) tile_masks_kernel(const int* __restrict__
   if (threadIdx.x == 0) masks[blockIdx.x] = (int)s_mask;
 }
 
+// ---------------------------------------------------------------------------------------------
+// Row grouping (s2d_table_group_rows): cut the EXECUTED work of the tile kernel.
+//
+// The kernel multiplies whole 128-row tiles per kernel offset, although only 17 % (stage 0) .. 64 % (stage 3) of the
+// (row, offset) pairs of a LiDAR scene exist: a voxel on a flat surface has no neighbour above or below, one on a thin
+// vertical structure none to the sides.  In scan order a tile mixes all kinds of rows, so nearly every offset is live for
+// some row of every tile (79-96 %).  Output rows may be processed in ANY order, though: the kernel scatters row p of the
+// permuted table to out_rows[p], so the results are bit-identical.  Rows are therefore grouped by WHICH of the nine
+// (dz, dy) offset triples have a neighbour (9-bit key, stable counting sort, so spatial locality survives inside a group);
+// tiles become homogeneous and whole triples of offsets are skipped through the tile masks: live (tile, offset) pairs drop
+// to 35 % / 62 % / 68 % / 76 % on the four SubM stages and to 23-49 % on the strided layers.
+// ---------------------------------------------------------------------------------------------
+constexpr int kGrpRows = 1024;     // rows per block of the counting sort (one per thread)
+constexpr int kGrpBuckets = 512;
+
+// per-warp bucket counts of a block's 1024 rows: s_cnt[w][key] = rows of warp w with that key (match.any: no atomics, so
+// the order inside a bucket is the row order = a STABLE sort).  Returns this thread's rank among its warp's equal keys.
+__device__ __forceinline__ int group_block_counts(unsigned key, bool valid, unsigned short (*s_cnt)[kGrpBuckets]) {
+  uint4* z = reinterpret_cast<uint4*>(&s_cnt[0][0]);
+  for (int i = threadIdx.x; i < 32 * kGrpBuckets * 2 / 16; i += kGrpRows) z[i] = make_uint4(0, 0, 0, 0);
+  __syncthreads();
+  const unsigned m = __match_any_sync(0xffffffffu, valid ? key : 0xffffu);
+  const int lane = threadIdx.x & 31;
+  if (valid && lane == __ffs(m) - 1) s_cnt[threadIdx.x >> 5][key] = (unsigned short)__popc(m);
+  __syncthreads();
+  return __popc(m & ((1u << lane) - 1u));
+}
+
+__global__ void __launch_bounds__(kGrpRows) group_keys_hist_kernel(const int* __restrict__ tbl, int stride, int K, int n,
+                                                                   unsigned short* __restrict__ keys, int* __restrict__ counts) {
+  __shared__ __align__(16) unsigned short s_cnt[32][kGrpBuckets];
+  const int row = blockIdx.x * kGrpRows + threadIdx.x;
+  unsigned key = 0;
+  if (row < n) {
+    for (int k = 0; k < K; ++k)
+      if (__ldg(tbl + (size_t)k * stride + row) >= 0) key |= 1u << (k / 3);
+    keys[row] = (unsigned short)key;
+  }
+  group_block_counts(key, row < n, s_cnt);
+  if (threadIdx.x < kGrpBuckets) {
+    int total = 0;
+#pragma unroll
+    for (int w = 0; w < 32; ++w) total += s_cnt[w][threadIdx.x];
+    counts[(size_t)blockIdx.x * kGrpBuckets + threadIdx.x] = total;
+  }
+}
+
+// counts[blk][b] -> exclusive prefix over the blocks of each half of the block range; tails[0..511] = start of bucket b in
+// the sorted order, tails[512..1023] = rows of bucket b in the first half (added by the scatter to second-half blocks)
+__global__ void __launch_bounds__(1024) group_scan_kernel(int* __restrict__ counts, int nblk, int* __restrict__ tails) {
+  __shared__ int s_tot[2][kGrpBuckets];
+  __shared__ int s_scan[kGrpBuckets];
+  const int b = threadIdx.x & (kGrpBuckets - 1), half = threadIdx.x >> 9;
+  const int mid = nblk / 2;
+  const int lo = half ? mid : 0, hi = half ? nblk : mid;
+  int run = 0;
+  int blk = lo;
+  for (; blk + 8 <= hi; blk += 8) {
+    int c[8];
+#pragma unroll
+    for (int u = 0; u < 8; ++u) c[u] = counts[(size_t)(blk + u) * kGrpBuckets + b];
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+      counts[(size_t)(blk + u) * kGrpBuckets + b] = run;
+      run += c[u];
+    }
+  }
+  for (; blk < hi; ++blk) {
+    const int c = counts[(size_t)blk * kGrpBuckets + b];
+    counts[(size_t)blk * kGrpBuckets + b] = run;
+    run += c;
+  }
+  s_tot[half][b] = run;
+  __syncthreads();
+  if (half == 0) s_scan[b] = s_tot[0][b] + s_tot[1][b];
+  __syncthreads();
+  for (int off = 1; off < kGrpBuckets; off <<= 1) {
+    int add = 0;
+    if (half == 0 && b >= off) add = s_scan[b - off];
+    __syncthreads();
+    if (half == 0) s_scan[b] += add;
+    __syncthreads();
+  }
+  if (half == 0) {
+    tails[b] = s_scan[b] - (s_tot[0][b] + s_tot[1][b]);
+    tails[kGrpBuckets + b] = s_tot[0][b];
+  }
+}
+
+__global__ void __launch_bounds__(kGrpRows) group_scatter_kernel(const unsigned short* __restrict__ keys, int n, int nblk,
+                                                                 const int* __restrict__ counts, const int* __restrict__ tails,
+                                                                 int* __restrict__ perm) {
+  __shared__ __align__(16) unsigned short s_cnt[32][kGrpBuckets];
+  const int row = blockIdx.x * kGrpRows + threadIdx.x;
+  const bool valid = row < n;
+  const unsigned key = valid ? keys[row] : 0u;
+  const int rank = group_block_counts(key, valid, s_cnt);
+  if (threadIdx.x < kGrpBuckets) {                       // exclusive prefix over the block's warps, per bucket
+    int run = 0;
+#pragma unroll
+    for (int w = 0; w < 32; ++w) {
+      const int c = s_cnt[w][threadIdx.x];
+      s_cnt[w][threadIdx.x] = (unsigned short)run;
+      run += c;
+    }
+  }
+  __syncthreads();
+  if (valid) {
+    const int pos = counts[(size_t)blockIdx.x * kGrpBuckets + key] + tails[key] +
+                    ((int)blockIdx.x >= nblk / 2 ? tails[kGrpBuckets + key] : 0) + s_cnt[threadIdx.x >> 5][key] + rank;
+    perm[pos] = row;
+  }
+}
+
+// tbl_out[k][p] = tbl[k][perm[p]] and the live-offset mask of every 128-row tile of tbl_out, one block per tile
+__global__ void __launch_bounds__(128) group_permute_table_kernel(const int* __restrict__ tbl, int stride, int K, int n,
+                                                                  const int* __restrict__ perm, int* __restrict__ out,
+                                                                  int out_stride, int* __restrict__ masks) {
+  __shared__ unsigned s_mask;
+  if (threadIdx.x == 0) s_mask = 0u;
+  __syncthreads();
+  const int p = blockIdx.x * 128 + threadIdx.x;
+  const int src = p < n ? __ldg(perm + p) : -1;
+  unsigned m = 0;
+#pragma unroll 9
+  for (int k = 0; k < K; ++k) {
+    const int v = src >= 0 ? __ldg(tbl + (size_t)k * stride + src) : -1;
+    if (p < n) out[(size_t)k * out_stride + p] = v;
+    if (__ballot_sync(0xffffffffu, v >= 0)) m |= 1u << k;
+  }
+  if ((threadIdx.x & 31) == 0 && m) atomicOr(&s_mask, m);
+  __syncthreads();
+  if (threadIdx.x == 0) masks[blockIdx.x] = (int)s_mask;
+}
+
 static int g_b2_variant = 0;
 static int g_b2_dbg = 0;
 static long long* g_b2_prof = nullptr;
@@ -634,12 +776,12 @@ static int b2_cout_block(int Cout) {
 }
 bool bf2_supported(int Cin, int Cout) { return (Cin == 16 || (Cin >= 32 && Cin % 32 == 0)) && b2_cout_block(Cout) != 0; }
 
-template <int COUT, int T>
+template <int COUT, int T, int S>
 static int launch_b2(const B2Args& a, int Cout, cudaStream_t st) {
-  using Cfg = B2Cfg<COUT, T>;
+  using Cfg = B2Cfg<COUT, T, S>;
   static bool configured = false;
   if (!configured) {
-    S2D_CUDA(cudaFuncSetAttribute(conv_bf2_kernel<COUT, T>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
+    S2D_CUDA(cudaFuncSetAttribute(conv_bf2_kernel<COUT, T, S>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
     configured = true;
   }
   B2Args b = a;
@@ -650,11 +792,11 @@ static int launch_b2(const B2Args& a, int Cout, cudaStream_t st) {
   b.n_tiles = div_up(a.n_out, kBM);
   b.n_groups = div_up(b.n_tiles, T);
   const int gy = Cout / COUT;
-  int gx = kNumSMs / gy;
+  int gx = kNumSMs * Cfg::CTAS_PER_SM / gy;
   if (gx < 1) gx = 1;
   if (gx > b.n_groups) gx = b.n_groups;
   const dim3 grid(gx, gy);
-  conv_bf2_kernel<COUT, T><<<grid, Cfg::THREADS, Cfg::SMEM_BYTES, st>>>(b);
+  conv_bf2_kernel<COUT, T, S><<<grid, Cfg::THREADS, Cfg::SMEM_BYTES, st>>>(b);
   S2D_LAUNCH_CHECK();
   count_launches(1);
   return S2D_OK;
@@ -692,10 +834,11 @@ int conv_fwd_bf2(const s2d_conv_params& p, cudaStream_t st) {
   a.dbg = g_b2_dbg;
   a.prof = g_b2_prof;
   const int v = g_b2_variant;
-  if (cb == 128) return launch_b2<128, 2>(a, p.Cout, st);
-  if (cb == 64) return v == 1 ? launch_b2<64, 2>(a, p.Cout, st) : launch_b2<64, 4>(a, p.Cout, st);
-  if (cb == 32) return v == 1 ? launch_b2<32, 2>(a, p.Cout, st) : launch_b2<32, 4>(a, p.Cout, st);
-  return v == 1 ? launch_b2<16, 2>(a, p.Cout, st) : launch_b2<16, 4>(a, p.Cout, st);
+  // variant 0: production choice; 1: T = 2, one CTA per SM; 2: two CTAs per SM (S = 4, T = 2)
+  if (cb == 128) return launch_b2<128, 2, 8>(a, p.Cout, st);
+  if (cb == 64) return v == 1 ? launch_b2<64, 2, 8>(a, p.Cout, st) : v == 2 ? launch_b2<64, 2, 4>(a, p.Cout, st) : launch_b2<64, 4, 8>(a, p.Cout, st);
+  if (cb == 32) return v == 1 ? launch_b2<32, 2, 8>(a, p.Cout, st) : v == 2 ? launch_b2<32, 2, 4>(a, p.Cout, st) : launch_b2<32, 4, 8>(a, p.Cout, st);
+  return v == 1 ? launch_b2<16, 2, 8>(a, p.Cout, st) : v == 2 ? launch_b2<16, 2, 4>(a, p.Cout, st) : launch_b2<16, 4, 8>(a, p.Cout, st);
 }
 
 int pack_weights_bf2(const float* W, int K, int Cin, int Cout, void* packed, cudaStream_t st) {
@@ -726,6 +869,34 @@ extern "C" int s2d_table_tile_masks(const int* tbl, int tbl_stride, int K, int n
   tile_masks_kernel<<<div_up(n_rows, 128), 128, 0, static_cast<cudaStream_t>(stream)>>>(tbl, tbl_stride, K, n_rows, tile_masks);
   S2D_LAUNCH_CHECK();
   count_launches(1);
+  return S2D_OK;
+}
+
+extern "C" size_t s2d_table_group_rows_workspace_bytes(int n_rows) {
+  if (n_rows < 0) return 0;
+  const size_t nblk = (size_t)div_up(n_rows > 0 ? n_rows : 1, kGrpRows);
+  return (nblk + 2) * kGrpBuckets * sizeof(int) + (((size_t)n_rows * sizeof(unsigned short) + 15) & ~size_t(15)) + 16;
+}
+
+extern "C" int s2d_table_group_rows(const int* tbl, int tbl_stride, int K, int n_rows, int* perm, int* tbl_out,
+                                    int out_stride, int* tile_masks, void* workspace, size_t workspace_bytes, void* stream) {
+  S2D_REQUIRE(K >= 1 && K <= 27 && n_rows >= 0 && tbl_stride >= n_rows && out_stride >= n_rows,
+              "s2d_table_group_rows: bad argument (K = %d must be <= 27)", K);
+  if (n_rows == 0) return S2D_OK;
+  S2D_REQUIRE(tbl && perm && tbl_out && tile_masks && workspace, "s2d_table_group_rows: null argument");
+  S2D_REQUIRE(workspace_bytes >= s2d_table_group_rows_workspace_bytes(n_rows), "s2d_table_group_rows: workspace too small");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const int nblk = div_up(n_rows, kGrpRows);
+  int* counts = static_cast<int*>(workspace);
+  int* tails = counts + (size_t)nblk * kGrpBuckets;
+  unsigned short* keys = reinterpret_cast<unsigned short*>(tails + 2 * kGrpBuckets);
+  group_keys_hist_kernel<<<nblk, kGrpRows, 0, st>>>(tbl, tbl_stride, K, n_rows, keys, counts);
+  group_scan_kernel<<<1, 1024, 0, st>>>(counts, nblk, tails);
+  group_scatter_kernel<<<nblk, kGrpRows, 0, st>>>(keys, n_rows, nblk, counts, tails, perm);
+  group_permute_table_kernel<<<div_up(n_rows, 128), 128, 0, st>>>(tbl, tbl_stride, K, n_rows, perm, tbl_out, out_stride,
+                                                                   tile_masks);
+  S2D_LAUNCH_CHECK();
+  count_launches(4);
   return S2D_OK;
 }
 

@@ -327,6 +327,22 @@ def table_tile_masks(tbl, n_rows):
     return masks
 
 
+def table_group_rows(tbl, n_rows):
+    """Group the rows of a neighbour table by their live (dz, dy) offset triples (``s2d_table_group_rows``) ->
+    (tbl_out i32 [K, n_rows], perm i32 [n_rows], tile_masks): launch the conv with tbl_out, out_rows=perm, tile_masks."""
+    _need_cuda(tbl)
+    k = tbl.shape[0]
+    lib = _lib.load()
+    out = alloc_table(k, n_rows, tbl.device)
+    perm = torch.empty((max(n_rows, 1),), dtype=torch.int32, device=tbl.device)
+    masks = torch.empty((max((n_rows + 127) // 128, 1),), dtype=torch.int32, device=tbl.device)
+    nbytes = lib.s2d_table_group_rows_workspace_bytes(n_rows)
+    ws = torch.empty((max(nbytes, 16),), dtype=torch.uint8, device=tbl.device)
+    _lib.check(lib.s2d_table_group_rows(_ptr(tbl), tbl.stride(0), k, n_rows, _ptr(perm), _ptr(out), out.stride(0), _ptr(masks),
+                                        _ptr(ws), nbytes, _stream()), "s2d_table_group_rows")
+    return out, perm, masks
+
+
 def bf2_ok(cin, cout, tbl):
     k = tbl.shape[0]
     nchunk = 1 if cin == 16 else cin // 32
@@ -375,7 +391,7 @@ def conv_launch(x, w_arg, tbl, n_out, cin, cout, k, scale=None, shift=None, act=
 
 
 def spconv_fwd(feats, weight, tbl, n_out, scale=None, shift=None, residual=None, relu=False,
-               precision=PRECISION_FP32, out=None, packed=None, tile_masks=None, want_split=True):
+               precision=PRECISION_FP32, out=None, packed=None, tile_masks=None, want_split=True, out_rows=None):
     """out[o] = act((sum_k feats[tbl[k][o]] @ W[k]) * scale + shift (+ residual[o])).
 
     weight: [kD,kH,kW,Cin,Cout] (spconv layout) or [K,Cin,Cout], fp32 contiguous.
@@ -395,12 +411,13 @@ def spconv_fwd(feats, weight, tbl, n_out, scale=None, shift=None, residual=None,
         split_ok = want_split and (cout % 32 == 0 or cout == 16) and out.is_contiguous()
         out_split = torch.empty((n_out, cout), dtype=torch.int32, device=feats.device) if split_ok else None
         w_arg = packed if packed is not None else pack_weights_tf32(weight, precision)
-        conv_launch(None, w_arg, tbl, n_out, cin, cout, k, scale, shift, 1 if relu else 0, residual, False, out, None,
+        conv_launch(None, w_arg, tbl, n_out, cin, cout, k, scale, shift, 1 if relu else 0, residual, False, out, out_rows,
                     precision, xs, out_split, tile_masks, kind="sparse")
         if out_split is not None:
             set_split(out, out_split)
         return out
     _need_cuda(feats, weight, tbl)
+    assert out_rows is None, "out_rows needs the bf16x2 kernel"
     assert feats.dtype == torch.float32 and feats.is_contiguous() and weight.is_contiguous()
     cin, cout = weight.shape[-2], weight.shape[-1]
     k = weight.numel() // (cin * cout)

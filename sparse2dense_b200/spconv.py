@@ -94,6 +94,11 @@ def _fold_bn(bn, bias, cout, device):
     return scale.detach().contiguous(), shift.detach().contiguous()
 
 
+# group the rows of 27-offset rulebooks by neighbour pattern before the tile kernel (ops.table_group_rows):
+# 0 never, 1 submanifold rulebooks only (shared by the four convolutions of a stage), 2 strided rulebooks too
+GROUP_ROWS = int(__import__("os").environ.get("S2D_GROUP_ROWS", "2"))
+
+
 class SparseConvolution(SparseModule):
     def __init__(self, ndim, in_channels, out_channels, kernel_size=3, stride=1, padding=0, dilation=1, groups=1,
                  bias=True, subm=False, indice_key=None):
@@ -165,14 +170,21 @@ class SparseConvolution(SparseModule):
         n_out = ind.out_indices.shape[0]
         prec = ops.effective_precision(self.precision, self.in_channels, self.out_channels, ind.tbl)
         packed = self._packed_weights(prec) if prec != ops.PRECISION_FP32 else None
-        masks = None
-        if prec == ops.PRECISION_BF16X2:                     # per-tile live-offset masks, once per rulebook
-            masks = ind.__dict__.get("tile_masks")
-            if masks is None:
-                masks = ind.tile_masks = ops.table_tile_masks(ind.tbl, n_out)
-        feats = ops.spconv_fwd(x.features.contiguous(), self.weight.detach(), ind.tbl, n_out, scale, shift,
+        masks, tbl, out_rows = None, ind.tbl, None
+        if prec == ops.PRECISION_BF16X2:
+            # once per rulebook: rows grouped by their live offset triples (bit-identical results, far fewer live
+            # (tile, offset) pairs -- ops.table_group_rows) and the per-tile live-offset masks of the grouped table
+            grouped = ind.__dict__.get("grouped")
+            if grouped is None:
+                if ind.tbl.shape[0] == 27 and GROUP_ROWS >= (1 if self.subm else 2):
+                    grouped = ops.table_group_rows(ind.tbl, n_out)
+                else:
+                    grouped = (ind.tbl, None, ops.table_tile_masks(ind.tbl, n_out))
+                ind.grouped = grouped
+            tbl, out_rows, masks = grouped
+        feats = ops.spconv_fwd(x.features.contiguous(), self.weight.detach(), tbl, n_out, scale, shift,
                                None if residual is None else residual.contiguous(), relu, prec,
-                               packed=packed, tile_masks=masks)
+                               packed=packed, tile_masks=masks, out_rows=out_rows)
         if self.subm:
             return x._like(feats)
         return x._like(feats, ind.out_indices, ind.out_shape, ind.out_index)

@@ -125,3 +125,33 @@ def test_bf2_chain_uses_producer_split_and_is_deterministic():
     assert rel_err(b2.cpu().numpy(), s.cpu().numpy()) < TOL
     a.add_(1.0)                                                                      # stale twin must not be used
     assert ops.get_split(a) is None
+
+
+def test_grouped_rows_are_a_permutation_and_give_bit_identical_results():
+    """s2d_table_group_rows: perm is a permutation, tbl_out[k][p] == tbl[k][perm[p]], the grouped launch (out_rows = perm)
+    writes exactly the bits of the plain launch -- with and without residual -- and the grouped tile masks skip more."""
+    from sparse2dense_b200 import synth
+    from sparse2dense_b200.hotpath import concat_clouds
+    pts, offs = concat_clouds([synth.lidar_scene(21), synth.small_scene(22)])
+    vb = ops.voxelize(pts.cuda(), offs, synth.WAYMO_VOXEL, synth.WAYMO_RANGE, 5, 150000, want_voxels=False, mean_channels=5)
+    n = vb.n
+    coors = vb.coors_buffer[:n]
+    index = ops.build_grid_index(coors, 2, (41, 1504, 1504))
+    tbl = ops.rulebook_subm(coors, index, 3)
+    gt, perm, gmasks = ops.table_group_rows(tbl, n)
+    assert torch.equal(torch.sort(perm.long())[0], torch.arange(n, device="cuda"))
+    assert torch.equal(gt[:, :n], tbl[:, :n][:, perm.long()])
+    masks = ops.table_tile_masks(tbl, n)
+    live = lambda m: sum(bin(int(v) & 0x7ffffff).count("1") for v in m.cpu().tolist())
+    assert live(gmasks) < 0.6 * live(masks), (live(gmasks), live(masks))
+    torch.manual_seed(3)
+    for c in (16, 32, 64):
+        x = torch.relu(torch.randn(n, c, device="cuda"))
+        w = torch.randn(27, c, c, device="cuda") / (27 * c) ** 0.5
+        res = torch.randn(n, c, device="cuda")
+        sc, sh = torch.rand(c, device="cuda") + 0.5, torch.randn(c, device="cuda")
+        for r in (None, res):
+            a = ops.spconv_fwd(x, w, tbl, n, sc, sh, r, True, ops.PRECISION_BF16X2, tile_masks=masks)
+            b = ops.spconv_fwd(x, w, gt, n, sc, sh, r, True, ops.PRECISION_BF16X2, tile_masks=gmasks, out_rows=perm)
+            assert torch.equal(a, b), c
+            assert torch.equal(ops.get_split(a), ops.get_split(b)), c

@@ -81,6 +81,14 @@ def main():
                                                   tile_masks=masks if use_masks else None), flush, args.reps)
                 line += f" | v{v}{'m' if use_masks else ' '} {t:.3f} ms (err {err:.1e})"
         setv(0)
+        gt, gperm, gmasks = ops.table_group_rows(tbl, n)
+        t_grp = timeit(lambda: ops.table_group_rows(tbl, n), flush, args.reps)
+        glive = float(sum(bin(int(m) & 0x7ffffff).count("1") for m in gmasks.cpu().tolist())) / (27 * gmasks.numel())
+        o3 = ops.spconv_fwd(feats, w, gt, n, precision=ops.PRECISION_BF16X2, packed=pk, tile_masks=gmasks, out_rows=gperm)
+        o2 = ops.spconv_fwd(feats, w, tbl, n, precision=ops.PRECISION_BF16X2, packed=pk, tile_masks=masks)
+        t = timeit(lambda: ops.spconv_fwd(feats, w, gt, n, precision=ops.PRECISION_BF16X2, packed=pk, out=out, tile_masks=gmasks,
+                                          out_rows=gperm), flush, args.reps)
+        line += f" | grouped live={glive:.3f} {t:.3f} ms (bit-equal {bool(torch.equal(o2, o3))}; grouping itself {t_grp:.3f} ms)"
         print(line, flush=True)
         if args.prof:
             lib = ctypes.CDLL(_lib.LIB_PATH)
