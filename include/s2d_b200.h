@@ -464,6 +464,15 @@ size_t s2d_conv_wgrad_workspace_bytes(int n_rows, int K, int Cg, int Cd);
 int s2d_conv_wgrad(const float* g, int g_ld, int n_g, int Cg, const float* d, int d_ld, const int* d_rows, int Cd,
                    const int* tbl, int tbl_stride, int n_rows, int K, float* out, int accumulate, void* workspace,
                    size_t workspace_bytes, void* stream);
+/* The same weight gradient on the tensor cores (csrc/wgrad_tc.cu) for Cg, Cd multiples of 32: both operands are given as SPLIT
+ * rows (s2d_rows_split: per 32-channel chunk [32 BF16 hi | 32 BF16 lo]), gathered straight into MN-major operand tiles; one
+ * tcgen05.mma yields the hi/lo cross products as accumulator quadrants, summed by the epilogue (fp32-level result: both
+ * operands carry 16 mantissa bits).  Deterministic (row chunks, fixed-order reduction). */
+int s2d_conv_wgrad_bf2_supported(int Cg, int Cd);
+size_t s2d_conv_wgrad_bf2_workspace_bytes(int n_rows, int K, int Cg, int Cd);
+int s2d_conv_wgrad_bf2(const void* g_split, int g_ld, int n_g, int Cg, const void* d_split, int d_ld, const int* d_rows, int Cd,
+                       const int* tbl, int tbl_stride, int n_rows, int K, float* out, int accumulate, void* workspace,
+                       size_t workspace_bytes, void* stream);
 size_t s2d_rows_workspace_bytes(int C);
 int s2d_bn_train_stats(const float* x, int ld, int n, int C, float eps, float momentum, const float* gamma,
                        const float* beta, float* running_mean, float* running_var, float* mean, float* invstd,

@@ -89,6 +89,9 @@ SIGNATURES = {
     "s2d_table_transpose": (_i, [_vp, _i, _i, _i, _vp, _vp, _i, _i, _vp]),
     "s2d_conv_wgrad_workspace_bytes": (_sz, [_i, _i, _i, _i]),
     "s2d_conv_wgrad": (_i, [_vp, _i, _i, _i, _vp, _i, _vp, _i, _vp, _i, _i, _i, _vp, _i, _vp, _sz, _vp]),
+    "s2d_conv_wgrad_bf2_supported": (_i, [_i, _i]),
+    "s2d_conv_wgrad_bf2_workspace_bytes": (_sz, [_i, _i, _i, _i]),
+    "s2d_conv_wgrad_bf2": (_i, [_vp, _i, _i, _i, _vp, _i, _vp, _i, _vp, _i, _i, _i, _vp, _i, _vp, _sz, _vp]),
     "s2d_rows_workspace_bytes": (_sz, [_i]),
     "s2d_bn_train_stats": (_i, [_vp, _i, _i, _i, ctypes.c_float, ctypes.c_float, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp,
                                 _vp, _sz, _vp]),

@@ -42,12 +42,24 @@ class Table:
         return self._inv
 
 
-def conv_wgrad(g, d, tbl, n_rows, d_rows=None):
-    """out[k][a][b] = sum_i g[tbl[k][i]][a] * d[d_rows[i] or i][b]  ->  f32 [K, Cg, Cd]."""
+WGRAD_TC = int(__import__("os").environ.get("S2D_WGRAD_TC", "1"))     # 0: CUDA-core weight gradient everywhere (debug / A-B)
+
+
+def conv_wgrad(g, d, tbl, n_rows, d_rows=None, precision=ops.PRECISION_AUTO):
+    """out[k][a][b] = sum_i g[tbl[k][i]][a] * d[d_rows[i] or i][b]  ->  f32 [K, Cg, Cd].  Channel counts that are multiples of 32
+    run on the tensor cores (wgrad_tc.cu) from the split-row twins of both operands unless ``precision`` is FP32."""
     assert g.stride(1) == 1 and d.stride(1) == 1
     K, cg, cd = tbl.shape[0], g.shape[1], d.shape[1]
     lib = _lib.load()
     out = torch.empty((K, cg, cd), dtype=torch.float32, device=g.device)
+    if WGRAD_TC and precision != ops.PRECISION_FP32 and n_rows >= 256 and lib.s2d_conv_wgrad_bf2_supported(cg, cd):
+        gs, ds = ops.rows_split(g, cache=True), ops.rows_split(d, cache=True)
+        nbytes = lib.s2d_conv_wgrad_bf2_workspace_bytes(n_rows, K, cg, cd)
+        ws = torch.empty((max(nbytes, 16),), dtype=torch.uint8, device=g.device)
+        _lib.check(lib.s2d_conv_wgrad_bf2(gs.data_ptr(), gs.stride(0), gs.shape[0], cg, ds.data_ptr(), ds.stride(0), _ptr(d_rows),
+                                          cd, tbl.data_ptr(), tbl.stride(0), n_rows, K, out.data_ptr(), 0, ws.data_ptr(), nbytes,
+                                          _stream()), "s2d_conv_wgrad_bf2")
+        return out
     nbytes = lib.s2d_conv_wgrad_workspace_bytes(n_rows, K, cg, cd)
     ws = torch.empty((max(nbytes, 16),), dtype=torch.uint8, device=g.device)
     _lib.check(lib.s2d_conv_wgrad(g.data_ptr(), g.stride(0), g.shape[0], cg, d.data_ptr(), d.stride(0), _ptr(d_rows), cd,
@@ -139,7 +151,7 @@ class GatherConv(torch.autograd.Function):
             else:
                 dx = conv_rows_tc(dy, wt, t.transposed(), t.n_in, ctx.precision)
         if ctx.needs_input_grad[1]:
-            dw = conv_wgrad(x, dy, t.tbl, t.n_out)
+            dw = conv_wgrad(x, dy, t.tbl, t.n_out, precision=ctx.precision)
         return dx, dw, None, None
 
 
@@ -182,7 +194,7 @@ class TransposedConv(torch.autograd.Function):
             kio = w_t.flatten(2).permute(2, 1, 0).contiguous()         # [K, Cout, Cin], K row-major over the kernel dims
             dx = conv_rows_any_k(dy, kio, adj.tbl, adj.n_out, ctx.precision)
         if ctx.needs_input_grad[1]:
-            g = conv_wgrad(dy, x, adj.tbl, adj.n_out)                  # [K, Cout, Cin]
+            g = conv_wgrad(dy, x, adj.tbl, adj.n_out, precision=ctx.precision)                  # [K, Cout, Cin]
             dw = g.permute(2, 1, 0).reshape(w_t.shape).contiguous()
         return dx, dw, None, None, None
 

@@ -83,7 +83,9 @@ def test_gather_conv_forward_backward(cin, cout, K, precision):
 
 @pytest.mark.parametrize("cg,cd,K", [(3, 16, 8), (5, 16, 27), (32, 3, 1), (32, 1, 1), (3, 1, 1), (3, 3, 1), (16, 3, 8),
                                      (64, 64, 9), (128, 256, 3), (20, 36, 4), (16, 16, 27), (32, 32, 27), (48, 40, 5),
-                                     (24, 30, 3), (10, 13, 2)])
+                                     (24, 30, 3), (10, 13, 2),
+                                     # tensor-core kernel (wgrad_tc.cu): lone / odd chunk counts, partial channel blocks, many blocks
+                                     (32, 64, 2), (96, 160, 4), (256, 512, 1), (320, 32, 9), (512, 64, 2), (128, 128, 27)])
 def test_conv_wgrad_shapes(cg, cd, K):
     """Row-parallel small-channel kernel, vectorised and scalar tile loaders, with and without a row indirection on D."""
     n_g, n_rows = 5000, 4321
