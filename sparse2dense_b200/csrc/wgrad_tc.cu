@@ -40,6 +40,7 @@ struct WtArgs {
   const int* tbl;
   float* partial;                          // [chunks][K][Cg][Cd]
   int g_ld, d_ld, tbl_stride, n_rows, K, Cg, Cd, ca, cb, rows_per_chunk, n_ablk;
+  int tpc;                                 // kernel offsets per CTA: 4 / ca when Cg <= 64 (their G-chunks share one D tile), else 1
 };
 
 template <int NA, int NB>
@@ -82,10 +83,13 @@ __global__ void __launch_bounds__(kWtThreads, 1) wgrad_tc_kernel(const __grid_co
   uint32_t* s_tmem = reinterpret_cast<uint32_t*>(bar_acc + 1);
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int chunk = blockIdx.x, k = blockIdx.y;
+  const int chunk = blockIdx.x, k0 = blockIdx.y * A.tpc;
   const int ablk = blockIdx.z % A.n_ablk, bblk = blockIdx.z / A.n_ablk;
   const int a0 = ablk * NA, b0 = bblk * NB;
-  const int na = min(NA, A.ca - a0), nb = min(NB, A.cb - b0);
+  // A-chunk c of the CTA = G-chunk a0 + c % cpt of kernel offset k0 + c / cpt (cpt = G-chunks per offset in this CTA)
+  const int cpt = A.tpc > 1 ? A.ca : min(NA, A.ca - a0);
+  const int ntaps = min(A.tpc, A.K - k0);
+  const int na = cpt * ntaps, nb = min(NB, A.cb - b0);
   const int row0 = chunk * A.rows_per_chunk;
   const int row_end = min(A.n_rows, row0 + A.rows_per_chunk);
   const int n_slabs = row_end > row0 ? (row_end - row0 + kWtRows - 1) / kWtRows : 0;
@@ -116,34 +120,39 @@ __global__ void __launch_bounds__(kWtThreads, 1) wgrad_tc_kernel(const __grid_co
     const char* gb = reinterpret_cast<const char*>(A.g);
     const char* db = reinterpret_cast<const char*>(A.d);
     const size_t g_row = (size_t)A.g_ld * 4, d_row = (size_t)A.d_ld * 4;
-    const int* tk = A.tbl + (size_t)k * A.tbl_stride;
-    auto indices = [&](int slab, int& ia, int& id) {
+    const int* tk = A.tbl + (size_t)k0 * A.tbl_stride;
+    auto indices = [&](int slab, int (&ia)[4], int& id) {
       const int i = row0 + slab * kWtRows + r;
-      ia = id = -1;
+      ia[0] = ia[1] = ia[2] = ia[3] = id = -1;
       if (i < row_end) {
-        ia = __ldg(tk + i);
+#pragma unroll
+        for (int t = 0; t < 4; ++t)
+          if (t < ntaps) ia[t] = __ldg(tk + (size_t)t * A.tbl_stride + i);
         id = A.d_rows ? __ldg(A.d_rows + i) : i;
       }
     };
-    int ia, id;
+    int ia[4], id;
     indices(0, ia, id);
 #pragma unroll 1
     for (int j = 0; j < n_slabs; ++j) {
       const int s = j % S;
       if (j >= S) mbar_wait(smem_u32(bar_empty + s), (uint32_t)((j / S) - 1) & 1u);
-      int ia_n = -1, id_n = -1;
+      int ia_n[4] = {-1, -1, -1, -1}, id_n = -1;
       if (j + 1 < n_slabs) indices(j + 1, ia_n, id_n);
       const uint32_t base = smem0 + (uint32_t)s * Cfg::STAGE + row_off;
-      const char* gs = gb + (size_t)max(ia, 0) * g_row + (size_t)a0 * 128;
       const char* ds = db + (size_t)max(id, 0) * d_row + (size_t)b0 * 128;
-      const uint32_t ga = ia >= 0 ? 16u : 0u, da = id >= 0 ? 16u : 0u;
+      const uint32_t da = id >= 0 ? 16u : 0u;
 #pragma unroll
       for (int c = 0; c < NA; ++c) {
         if (c < na) {
+          const int t = A.tpc > 1 ? c / cpt : 0, cc = A.tpc > 1 ? c % cpt : c;
+          const int it = ia[t];
+          const char* gs = gb + (size_t)max(it, 0) * g_row + (size_t)(a0 + cc) * 128;
+          const uint32_t ga = it >= 0 ? 16u : 0u;
 #pragma unroll
           for (int p = 0; p < 4; ++p) {
             const uint32_t piece = (uint32_t)(4 * h + p);
-            cp_async16_zfill(base + (uint32_t)c * kWtChunk + ((piece ^ sw) << 4), gs + c * 128 + piece * 16, ga);
+            cp_async16_zfill(base + (uint32_t)c * kWtChunk + ((piece ^ sw) << 4), gs + piece * 16, ga);
           }
         }
       }
@@ -163,7 +172,9 @@ __global__ void __launch_bounds__(kWtThreads, 1) wgrad_tc_kernel(const __grid_co
         fence_proxy_async();                                 // ... and are visible to the tensor core (async proxy)
         mbar_arrive(smem_u32(bar_full + (j - kWtLag) % S));
       }
-      ia = ia_n; id = id_n;
+#pragma unroll
+      for (int t = 0; t < 4; ++t) ia[t] = ia_n[t];
+      id = id_n;
     }
     if (n_slabs >= 2) {
       cp_async_wait<1>();
@@ -183,7 +194,7 @@ __global__ void __launch_bounds__(kWtThreads, 1) wgrad_tc_kernel(const __grid_co
     }
     float* stg = reinterpret_cast<float*>(smem);             // [2 G-chunks of the block][32 lanes][33]: lo-lane sums
     const int cpair = warp >> 1, is_lo = warp & 1;
-    float* out_k = A.partial + ((size_t)chunk * A.K + k) * (size_t)A.Cg * A.Cd;
+    float* out_c = A.partial + (size_t)chunk * A.K * (size_t)A.Cg * A.Cd;
 #pragma unroll 1
     for (int mb = 0; mb < Cfg::MB; ++mb) {
       const int achunk = 2 * mb + cpair;
@@ -208,7 +219,8 @@ __global__ void __launch_bounds__(kWtThreads, 1) wgrad_tc_kernel(const __grid_co
         }
         wt_bar_sync();
         if (!is_lo && active) {
-          float* dst = out_k + (size_t)((a0 + achunk) * 32 + lane) * A.Cd + (size_t)(b0 + cbk) * 32;
+          const int t = A.tpc > 1 ? achunk / cpt : 0, cc = A.tpc > 1 ? achunk % cpt : achunk;
+          float* dst = out_c + ((size_t)(k0 + t) * A.Cg + (size_t)((a0 + cc) * 32 + lane)) * A.Cd + (size_t)(b0 + cbk) * 32;
 #pragma unroll
           for (int q = 0; q < 8; ++q) {
             float4 v;
@@ -264,16 +276,18 @@ __global__ void wt_reduce_kernel(const float* __restrict__ partial, int n_chunks
 }
 
 struct WtPlan {
-  int NA, NB, n_ablk, n_bblk, chunks, rpc;
+  int NA, NB, n_ablk, n_bblk, chunks, rpc, tpc, ktiles;
 };
 static WtPlan wt_plan(int n_rows, int K, int Cg, int Cd) {
   WtPlan p;
   const int ca = Cg / 32, cb = Cd / 32;
-  p.NA = ca >= 3 ? 4 : ca;
+  p.tpc = (ca <= 2 && K > 1) ? 4 / ca : 1;          // narrow G: several kernel offsets share the CTA's D tile
+  p.NA = (ca >= 3 || p.tpc > 1) ? 4 : ca;
   p.NB = cb >= 3 ? 4 : cb;
-  p.n_ablk = div_up(ca, p.NA);
+  p.n_ablk = p.tpc > 1 ? 1 : div_up(ca, p.NA);
   p.n_bblk = div_up(cb, p.NB);
-  const long long tiles = (long long)K * p.n_ablk * p.n_bblk;
+  p.ktiles = div_up(K, p.tpc);
+  const long long tiles = (long long)p.ktiles * p.n_ablk * p.n_bblk;
   long long want = (2LL * kNumSMs + tiles - 1) / tiles;               // ~two CTAs per SM in total
   const long long max_chunks = (n_rows + 511) / 512;                   // at least 512 rows per chunk
   if (want > max_chunks) want = max_chunks;
@@ -294,7 +308,7 @@ static int wt_launch(const WtArgs& a, const WtPlan& p, cudaStream_t st) {
     S2D_CUDA(cudaFuncSetAttribute(wgrad_tc_kernel<NA, NB>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM));
     configured = true;
   }
-  const dim3 grid(p.chunks, a.K, p.n_ablk * p.n_bblk);
+  const dim3 grid(p.chunks, p.ktiles, p.n_ablk * p.n_bblk);
   wgrad_tc_kernel<NA, NB><<<grid, kWtThreads, Cfg::SMEM, st>>>(a);
   S2D_LAUNCH_CHECK();
   return S2D_OK;
@@ -327,7 +341,7 @@ extern "C" int s2d_conv_wgrad_bf2(const void* g_split, int g_ld, int n_g, int Cg
   WtArgs a;
   a.g = static_cast<const uint32_t*>(g_split); a.d = static_cast<const uint32_t*>(d_split); a.d_rows = d_rows; a.tbl = tbl;
   a.partial = static_cast<float*>(workspace); a.g_ld = g_ld; a.d_ld = d_ld; a.tbl_stride = tbl_stride; a.n_rows = n_rows;
-  a.K = K; a.Cg = Cg; a.Cd = Cd; a.ca = Cg / 32; a.cb = Cd / 32; a.rows_per_chunk = p.rpc; a.n_ablk = p.n_ablk;
+  a.K = K; a.Cg = Cg; a.Cd = Cd; a.ca = Cg / 32; a.cb = Cd / 32; a.rows_per_chunk = p.rpc; a.n_ablk = p.n_ablk; a.tpc = p.tpc;
   int rc = S2D_OK;
 #define S2D_WT(NA_, NB_) \
   if (p.NA == NA_ && p.NB == NB_) rc = wt_launch<NA_, NB_>(a, p, st);

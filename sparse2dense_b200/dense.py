@@ -131,7 +131,7 @@ def conv_rows(x, weight_kio, tbl, n_out, scale=None, shift=None, act=ACT_NONE, r
             w = packed if packed is not None else ops.pack_weights_tf32(weight_kio, prec)
     xs = None
     if prec == ops.PRECISION_BF16X2:
-        xs = ops.rows_split(x)
+        xs = ops.rows_split(x, cache=True)       # the twin is reused by the weight gradient / the next consumer of x
         if out_split is None and fresh and want_split and (cout % 32 == 0 or cout == 16):
             out_split = torch.empty((out.shape[0], cout), dtype=torch.int32, device=x.device)
     else:

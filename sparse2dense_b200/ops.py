@@ -405,7 +405,7 @@ def spconv_fwd(feats, weight, tbl, n_out, scale=None, shift=None, residual=None,
         assert feats.shape[1] == cin and tbl.shape[0] == k and tbl.dtype == torch.int32
         if not bf2_ok(cin, cout, tbl):
             raise _lib.S2DError(f"no bf16x2 kernel for Cin={cin} Cout={cout} K={k} tbl stride {tbl.stride(0)}")
-        xs = rows_split(feats)
+        xs = rows_split(feats, cache=True)
         if out is None:
             out = torch.empty((n_out, cout), dtype=torch.float32, device=feats.device)
         split_ok = want_split and (cout % 32 == 0 or cout == 16) and out.is_contiguous()
