@@ -35,7 +35,7 @@
 namespace s2d {
 
 // S gathered-tile stages, one producer warp each (warps 0..S-1); warp S = utility; warps S+1..S+T = MMA (one per tile of the
-// group); then four epilogue warps.  S = 8: one CTA per SM; S = 4: two CTAs per SM (half the ring each), whose independent
+// group); then eight epilogue warps.  S = 8: one CTA per SM; S = 4: two CTAs per SM (half the ring each), whose independent
 // pipelines hide each other's barrier round trips.
 constexpr int kB2ListCap = 1024;           // (offset steps) x (chunks) of one tile group; host-checked
 constexpr int kB2AStage = kBM * 128;       // 128 rows x 128 B
@@ -71,7 +71,8 @@ struct B2Cfg {
   static constexpr int SB = S == 4 ? (COUT >= 64 ? 2 : 4) : (COUT >= 128 ? 3 : 4);   // weight-tile ring
   static constexpr int UTIL_WARP = S;
   static constexpr int MMA_WARP0 = S + 1;
-  static constexpr int WARPS = MMA_WARP0 + T + 4;
+  static constexpr int EPI_WARPS = 8;                          // two per TMEM lane quarter: they split the (tile, column chunk) items
+  static constexpr int WARPS = MMA_WARP0 + T + EPI_WARPS;
   static constexpr int THREADS = 32 * WARPS;
   static constexpr int EPI_WARP0 = MMA_WARP0 + T;
   static constexpr int B_STAGE = COUT * 128;                   // COUT rows x [w1 (64 B) | w2 (64 B)]
@@ -81,7 +82,7 @@ struct B2Cfg {
   static constexpr int TMEM_COLS = ACC_COLS <= 32 ? 32 : ACC_COLS <= 64 ? 64 : ACC_COLS <= 128 ? 128 : ACC_COLS <= 256 ? 256 : 512;
   static constexpr int EPC = COUT < 32 ? COUT : 32;
   static constexpr int LIST_BYTES = 2 * kB2ListCap * 2;
-  static constexpr int EPI_BYTES = 4 * 32 * kB2EpiRow;
+  static constexpr int EPI_BYTES = EPI_WARPS * 32 * kB2EpiRow;
   static constexpr int BAR_BYTES = 512;
   static constexpr int SMEM_BYTES = S * kB2AStage + SB * B_STAGE + LIST_BYTES + EPI_BYTES + S * 1024 + BAR_BYTES + 1024;
   static_assert(T == 2 || T == 4, "tiles per group");
@@ -129,7 +130,7 @@ __device__ __forceinline__ void split_pair(float a, float b, uint32_t& hi, uint3
 
 // Persistent CTA (one per SM): group j of this CTA is tile group blockIdx.x + j * gridDim.x.  Per group the utility warp
 // writes the block list (double buffered); every role walks ALL blocks of the list (so every waiter sees every phase of
-// the per-slot barriers); the four epilogue warps drain a group's accumulators from one TMEM buffer while the next group
+// the per-slot barriers); the epilogue warps drain a group's accumulators from one TMEM buffer while the next group
 // is gathered and multiplied into the other.
 //   block entry = kk | live-tile nibble << 5 | chunk << 9
 template <int COUT, int T, int S>
@@ -147,7 +148,7 @@ conv_bf2_kernel(const __grid_constant__ B2Args A) {
   uint8_t* a_ring = smem;                                        // 8 x [128 rows x 128 B], 128B-swizzled
   uint8_t* b_ring = a_ring + kB2Stages * kB2AStage;              // NB x [COUT rows x 128 B], 128B-swizzled
   uint8_t* lists = b_ring + SB * B_STAGE;                        // 2 x kB2ListCap u16 block entries
-  uint8_t* epi = lists + Cfg::LIST_BYTES;                        // 4 warps x [32 rows x 144 B]
+  uint8_t* epi = lists + Cfg::LIST_BYTES;                        // 8 warps x [32 rows x 144 B]
   uint8_t* idx_scratch = epi + Cfg::EPI_BYTES;                   // 8 producer warps x 1 KB
   uint64_t* bars = reinterpret_cast<uint64_t*>(idx_scratch + kB2ProducerWarps * 1024);
   uint64_t* bar_a_full = bars;                                   // [8]  producer warp -> MMA warp of the stage's tile
@@ -177,7 +178,7 @@ conv_bf2_kernel(const __grid_constant__ B2Args A) {
       mbar_init(smem_u32(bar_list_full + s), 1);                  // utility warp, after writing the list
       mbar_init(smem_u32(bar_list_empty + s), kB2ProducerWarps + T);   // producer + MMA warps done reading it
       mbar_init(smem_u32(bar_acc_full + s), T);                   // every MMA warp after its last MMA of the group
-      mbar_init(smem_u32(bar_acc_empty + s), 4);                  // the four epilogue warps
+      mbar_init(smem_u32(bar_acc_empty + s), Cfg::EPI_WARPS);     // the epilogue warps
     }
     fence_barrier_init();
   }
@@ -327,12 +328,15 @@ conv_bf2_kernel(const __grid_constant__ B2Args A) {
           nib |= live << t;
         }
       }
-      const int cnt = nib ? NCHUNK : 0;
-      const int off = warp_inclusive_scan(cnt) - cnt;
+      // chunk-major order: the live offsets of one 32-channel chunk run back to back, so the 128 B pieces a tile gathers
+      // for neighbouring offsets (the same rows, shifted) are re-read while still in L2 -- with offset-major order a
+      // 188 x 188 x 512-channel map (290 MB) streamed from DRAM once per offset (ncu: 2.5 GB read, 8 % L2 hits)
+      const unsigned live_mask = __ballot_sync(0xffffffffu, nib != 0);
+      const int n_live = __popc(live_mask), rank = __popc(live_mask & ((1u << lane) - 1u));
       if (nib)
         for (int c = 0; c < NCHUNK; ++c)
-          if (off + c < kB2ListCap) blocks[off + c] = (uint16_t)(lane | (nib << 5) | (c << 9));
-      const int total = __shfl_sync(0xffffffffu, off + cnt, 31);
+          if (c * n_live + rank < kB2ListCap) blocks[c * n_live + rank] = (uint16_t)(lane | (nib << 5) | (c << 9));
+      const int total = n_live * NCHUNK;
       if (lane == 0) s_nblocks[buf] = (uint32_t)min(total, kB2ListCap);
       __syncwarp();
       if (lane == 0) mbar_arrive(smem_u32(bar_list_full + buf));
@@ -482,7 +486,10 @@ conv_bf2_kernel(const __grid_constant__ B2Args A) {
     // ===================== epilogue warps: TMEM -> staged rows -> coalesced BN / residual / activation / stores ==========
     // A warp reads the accumulator rows of its TMEM lane quarter (lane = row), stages 32 (16) channels per row in shared
     // memory and re-reads them with 8 (4) lanes per row, so that every global access is a whole 128 B (64 B) row piece.
+    // The BN affine + activation (GELU: erff) + split of a 128 x 128 tile is ~150 k warp instructions; with four warps the
+    // 1x1 layers of the neck were epilogue-bound (256->256 at 188 x 188: 585 us against 180 us for the same shape with ReLU).
     const int g4 = warp & 3;
+    const int half = (warp - Cfg::EPI_WARP0) >> 2;                  // which of the quarter's two warps
     const uint32_t stg = smem_u32(epi) + (uint32_t)(warp - Cfg::EPI_WARP0) * (32 * kB2EpiRow);
     const float* __restrict__ scale = A.scale ? A.scale + cblk : nullptr;
     const float* __restrict__ shift = A.shift ? A.shift + cblk : nullptr;
@@ -501,6 +508,7 @@ conv_bf2_kernel(const __grid_constant__ B2Args A) {
       const int row_end = min(n_out, tile0 + T * kBM);
       mbar_wait(smem_u32(bar_acc_full + buf), (uint32_t)(j >> 1) & 1u);
       tc_fence_after();
+      int item = 0;
 #pragma unroll 1
       for (int t = 0; t < Tr; ++t) {
         if (A.dbg & 128) break;
@@ -508,6 +516,7 @@ conv_bf2_kernel(const __grid_constant__ B2Args A) {
         const int orow_l = (row_l < row_end && A.out_rows) ? __ldg(A.out_rows + row_l) : row_l;
 #pragma unroll 1
         for (int c0 = 0; c0 < COUT; c0 += EPC) {
+          if ((item++ & 1) != half) continue;
           uint32_t acc[EPC];
           tmem_ld<EPC>(tmem_base + ((uint32_t)(g4 * 32) << 16) + (uint32_t)(buf * Cfg::ACC_BUF + t * Cfg::ACC_STRIDE + c0), acc);
 #pragma unroll
@@ -834,11 +843,12 @@ int conv_fwd_bf2(const s2d_conv_params& p, cudaStream_t st) {
   a.dbg = g_b2_dbg;
   a.prof = g_b2_prof;
   const int v = g_b2_variant;
-  // variant 0: production choice; 1: T = 2, one CTA per SM; 2: two CTAs per SM (S = 4, T = 2)
+  // variant 0: production choice; 1: T = 2.  (Two CTAs per SM with half the stage ring each, S = 4, measured no faster: the
+  // kernel is bound by shared-memory bandwidth and the tensor pipe, which both CTAs share, not by barrier latency.)
   if (cb == 128) return launch_b2<128, 2, 8>(a, p.Cout, st);
-  if (cb == 64) return v == 1 ? launch_b2<64, 2, 8>(a, p.Cout, st) : v == 2 ? launch_b2<64, 2, 4>(a, p.Cout, st) : launch_b2<64, 4, 8>(a, p.Cout, st);
-  if (cb == 32) return v == 1 ? launch_b2<32, 2, 8>(a, p.Cout, st) : v == 2 ? launch_b2<32, 2, 4>(a, p.Cout, st) : launch_b2<32, 4, 8>(a, p.Cout, st);
-  return v == 1 ? launch_b2<16, 2, 8>(a, p.Cout, st) : v == 2 ? launch_b2<16, 2, 4>(a, p.Cout, st) : launch_b2<16, 4, 8>(a, p.Cout, st);
+  if (cb == 64) return v == 1 ? launch_b2<64, 2, 8>(a, p.Cout, st) : launch_b2<64, 4, 8>(a, p.Cout, st);
+  if (cb == 32) return v == 1 ? launch_b2<32, 2, 8>(a, p.Cout, st) : launch_b2<32, 4, 8>(a, p.Cout, st);
+  return v == 1 ? launch_b2<16, 2, 8>(a, p.Cout, st) : launch_b2<16, 4, 8>(a, p.Cout, st);
 }
 
 int pack_weights_bf2(const float* W, int K, int Cin, int Cout, void* packed, cudaStream_t st) {
