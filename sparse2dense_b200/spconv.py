@@ -96,7 +96,7 @@ def _fold_bn(bn, bias, cout, device):
 
 # group the rows of 27-offset rulebooks by neighbour pattern before the tile kernel (ops.table_group_rows):
 # 0 never, 1 submanifold rulebooks only (shared by the four convolutions of a stage), 2 strided rulebooks too
-GROUP_ROWS = int(__import__("os").environ.get("S2D_GROUP_ROWS", "2"))
+GROUP_ROWS = int(__import__("os").environ.get("S2D_GROUP_ROWS", "1"))
 
 
 class SparseConvolution(SparseModule):

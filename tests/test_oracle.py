@@ -145,3 +145,18 @@ def test_synth_is_deterministic_and_waymo_sized():
     assert np.array_equal(a, b) and a.dtype == np.float32 and a.shape[1] == 5
     n_in = int(synth.in_range_mask(a).sum())
     assert 0.95 * 180000 <= n_in <= 1.05 * 180000
+
+
+def test_bench_cpu_arm_states_match_the_oracle_full_forward_keys():
+    """bench.py --impl reference builds the same seeded weights as the GPU arm WITHOUT a CUDA device; one small scene goes
+    through the CPU restatement of the whole two-stage forward (configs[2]) and of the pillar student (configs[3])."""
+    import bench
+    from oracle import full_forward as FF
+    from sparse2dense_b200 import synth
+    cloud = synth.small_scene(5)
+    for name, fn in (("full", FF.scene_forward), ("pillar", FF.pillar_scene_forward)):
+        states = bench.cpu_states(name)
+        t = {}
+        out = fn(states, cloud, timings=t)
+        assert out["boxes"].shape[1] == 7 and len(out["scores"]) == len(out["labels"]) == len(out["boxes"]) <= 500
+        assert set(t) >= {"neck_head", "decode_nms", "second_stage"}

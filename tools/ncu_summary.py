@@ -1,32 +1,31 @@
 #!/usr/bin/env python
-"""Compact summary of an `ncu --set full` report: ncu_summary.py REPORT.ncu-rep  (runs `ncu -i ... --page raw --csv`)."""
+"""Summarise an `ncu --set full` report of tools/ncu_targets.py into a text table (the metrics B200_PROFILING.md names).
+usage: ncu_summary.py report.ncu-rep [label ...] > profiles/xxx.txt"""
 import csv
-import io
 import subprocess
 import sys
 
-WANT = ["gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum",
-        "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed", "lts__throughput.avg.pct_of_peak_sustained_elapsed",
-        "lts__t_sector_hit_rate.pct", "l1tex__throughput.avg.pct_of_peak_sustained_elapsed",
-        "sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_elapsed",
-        "sm__throughput.avg.pct_of_peak_sustained_elapsed", "sm__warps_active.avg.pct_of_peak_sustained_active",
-        "sm__pipe_fma_cycles_active.avg.pct_of_peak_sustained_active", "sm__inst_executed_pipe_fma.sum",
-        "sm__pipe_fmaheavy_cycles_active.avg.pct_of_peak_sustained_active",
-        "smsp__issue_active.avg.pct_of_peak_sustained_active", "l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum",
-        "launch__registers_per_thread", "launch__grid_size", "launch__block_size",
-        "launch__shared_mem_per_block_dynamic", "smsp__inst_executed.sum", "sm__cycles_elapsed.max"]
+WANT = ["gpu__time_duration.sum", "sm__throughput.avg.pct_of_peak_sustained_elapsed",
+        "sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active", "smsp__issue_active.avg.pct_of_peak_sustained_active",
+        "l1tex__throughput.avg.pct_of_peak_sustained_elapsed", "l1tex__data_pipe_lsu_wavefronts_mem_shared.sum",
+        "lts__throughput.avg.pct_of_peak_sustained_elapsed", "lts__t_sector_hit_rate.pct",
+        "dram__throughput.avg.pct_of_peak_sustained_elapsed", "dram__bytes_read.sum", "dram__bytes_write.sum",
+        "l1tex__m_xbar2l1tex_read_bytes.sum", "smsp__inst_executed.sum", "sm__warps_active.avg.pct_of_peak_sustained_active",
+        "launch__registers_per_thread", "launch__grid_size", "launch__block_size", "sm__cycles_elapsed.max"]
 
 
 def main():
-    raw = subprocess.run(["ncu", "-i", sys.argv[1], "--page", "raw", "--csv"], capture_output=True, text=True).stdout
-    rows = list(csv.reader(io.StringIO(raw)))
-    hdr, units = rows[0], rows[1]
-    col = {h: i for i, h in enumerate(hdr)}
-    for r in rows[2:]:
-        print(r[col["Kernel Name"]][:80], "grid", r[col.get("launch__grid_size", 0)])
+    rep, labels = sys.argv[1], sys.argv[2:]
+    raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True, check=True).stdout
+    rows = list(csv.reader(raw.splitlines()))
+    h, units = rows[0], rows[1]
+    kn = h.index("Kernel Name")
+    print(f"# {rep}: ncu --set full --clock-control none, one launch per kernel (warm L2: the same launch ran once before)")
+    for i, r in enumerate(rows[2:]):
+        print(f"\n== launch {i}: {labels[i] if i < len(labels) else ''} :: {r[kn][:70]}")
         for w in WANT:
-            if w in col:
-                print(f"    {w:70s} {r[col[w]]:>16s} {units[col[w]]}")
+            if w in h:
+                print(f"   {w:72s} {r[h.index(w)]:>18s} {units[h.index(w)]}")
 
 
 if __name__ == "__main__":
