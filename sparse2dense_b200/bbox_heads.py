@@ -6,6 +6,7 @@ kernel.  ``predict`` (:293-495: decode, masks, top-4096, rotated NMS, top-500) r
 batch on the device (csrc/detect.cu); ``loss`` runs the reduction kernels of csrc/losses.cu and is differentiable; in
 training mode every conv is its own launch on the autograd operators of ``autograd.py`` (batch-statistics BatchNorm)."""
 import copy
+import math
 import logging
 
 import torch
@@ -231,3 +232,170 @@ class CenterHead(nn.Module):
         B, _, H, W = x.shape
         rows = self.forward_rows(to_rows(x), B, H, W)
         return [{h: to_nchw(v, B, H, W) for h, v in d.items()} for d in rows]
+
+
+class Head(nn.Module):
+    """mg_head.py:199-231: the 1x1 box / class / direction convolutions of one task."""
+
+    def __init__(self, num_input, num_pred, num_cls, use_dir=False, num_dir=0, header=True, name="", focal_loss_init=False,
+                 **kwargs):
+        super(Head, self).__init__(**kwargs)
+        self.use_dir = use_dir
+        self.conv_box = nn.Conv2d(num_input, num_pred, 1)
+        self.conv_cls = nn.Conv2d(num_input, num_cls, 1)
+        if self.use_dir:
+            self.conv_dir = nn.Conv2d(num_input, num_dir, 1)
+
+
+@HEADS.register_module
+class MultiGroupHead(nn.Module):
+    """Anchor-based SECOND head (det3d/models/bbox_heads/mg_head.py:386-533 ``__init__/forward``, :697-1086 ``predict``):
+    same constructor arguments and state-dict keys (``tasks.0.conv_box.weight`` ...).  Inference only.
+
+    forward: the three 1x1 convolutions of a task are ONE gather-GEMM launch (weights concatenated on Cout, padded to a
+    multiple of 16); predict: box decoding against the anchors (``box_coder.decode_torch``), sigmoid scores, per-anchor
+    best class, score threshold, top ``nms_pre_max_size``, rotated NMS, direction flip and the centre-range mask.
+    The rotated NMS is the library's exact polygon-clipping IoU (csrc/detect.cu, pinned to the reference's iou3d_cpu.cpp); the
+    reference routes this head through ``box_torch_ops.rotate_nms`` -> ``rotate_nms_cc`` (boost::geometry, not buildable
+    here): that one stage is therefore PARITY-UNPINNED.  ``use_multi_class_nms`` and the non-rotated
+    NMS are not built (the Waymo SECOND configs use neither)."""
+
+    def __init__(self, mode="3d", in_channels=[128, ], norm_cfg=None, tasks=[], weights=[], num_classes=[1, ], box_coder=None,
+                 with_cls=True, with_reg=True, reg_class_agnostic=False, encode_background_as_zeros=True,
+                 loss_norm=None, loss_cls=None, use_sigmoid_score=True, loss_bbox=None, encode_rad_error_by_sin=True,
+                 loss_aux=None, direction_offset=0.0, name="rpn", logger=None):
+        super(MultiGroupHead, self).__init__()
+        assert with_cls or with_reg
+        assert box_coder is not None, "MultiGroupHead needs a box_coder (det3d.builder.build_box_coder)"
+        num_classes = [len(t["class_names"]) for t in tasks]
+        self.class_names = [t["class_names"] for t in tasks]
+        self.num_anchor_per_locs = [2 * n for n in num_classes]
+        self.box_coder = box_coder
+        self.in_channels, self.num_classes = in_channels, num_classes
+        self.encode_background_as_zeros, self.use_sigmoid_score = encode_background_as_zeros, use_sigmoid_score
+        self.box_n_dim, self.anchor_dim = box_coder.code_size, box_coder.n_dim
+        self.use_direction_classifier = loss_aux is not None
+        self.direction_offset = direction_offset
+        self.bev_only = mode == "bev"
+        self.loss_cfg = dict(loss_norm=loss_norm, loss_cls=loss_cls, loss_bbox=loss_bbox, loss_aux=loss_aux, weights=weights,
+                             encode_rad_error_by_sin=encode_rad_error_by_sin)
+        self.logger = logger or logging.getLogger("MultiGroupHead")
+        self.tasks = nn.ModuleList()
+        for num_c, num_a in zip(num_classes, self.num_anchor_per_locs):
+            num_cls = num_a * num_c if encode_background_as_zeros else num_a * (num_c + 1)
+            num_pred = num_a * (self.box_n_dim - 2) if self.bev_only else num_a * self.box_n_dim
+            self.tasks.append(Head(in_channels, num_pred, num_cls, use_dir=self.use_direction_classifier,
+                                   num_dir=num_a * 2 if self.use_direction_classifier else None, header=False))
+        self._dense = DenseOps()
+
+    def set_precision(self, precision):
+        self._dense = DenseOps(precision)
+
+    def init_weights(self, pretrained=None):
+        for m in self.modules():
+            if isinstance(m, nn.Conv2d):
+                nn.init.kaiming_normal_(m.weight, mode="fan_out", nonlinearity="relu")
+                if m.bias is not None:
+                    nn.init.constant_(m.bias, 0)
+
+    def forward_rows(self, x, B, H, W):
+        """x rows [B*H*W, C] -> list (per task) of dict(box_preds, cls_preds[, dir_cls_preds]) as rows [B*H*W, c]
+        (= the reference's NHWC ``permute(0, 2, 3, 1)`` tensors flattened over B, H, W)."""
+        if self.training:
+            raise NotImplementedError("MultiGroupHead: the training branch (anchor losses) is not built")
+        D = self._dense
+        tbl, _, _ = conv_table(x.device, B, H, W, 1, 1, 0)
+        n = B * H * W
+        ret = []
+        for ti, task in enumerate(self.tasks):
+            convs = [("box_preds", task.conv_box), ("cls_preds", task.conv_cls)]
+            if task.use_dir:
+                convs.append(("dir_cls_preds", task.conv_dir))
+            couts = [c.weight.shape[0] for _, c in convs]
+            cpad = -(-sum(couts) // 16) * 16
+
+            def build():
+                cin = convs[0][1].weight.shape[1]
+                kio = torch.zeros((1, cin, cpad), dtype=torch.float32, device=x.device)
+                bias = torch.zeros((cpad,), dtype=torch.float32, device=x.device)
+                off = 0
+                for (_, c), co in zip(convs, couts):
+                    kio[0, :, off:off + co] = c.weight.detach().float().reshape(co, cin).t()
+                    bias[off:off + co] = c.bias.detach().float()
+                    off += co
+                return kio, {}, bias
+            kio, packed, bias = D.cache.get(("mg", ti, D.precision), [c.weight for _, c in convs] + [c.bias for _, c in convs],
+                                            build)
+            y = conv_rows(x, kio, tbl, n, None, bias, ACT_NONE, precision=D.precision, packed=packed)
+            out, off = {}, 0
+            for (name, _), co in zip(convs, couts):
+                out[name] = y[:, off:off + co]
+                off += co
+            ret.append(out)
+        return ret
+
+    def forward(self, x):
+        """mg_head.py:528-533: NCHW feature map -> list of dicts of NHWC tensors [B, H, W, c]."""
+        B, _, H, W = x.shape
+        rows = self.forward_rows(to_rows(x.contiguous()), B, H, W)
+        return [{k: v.reshape(B, H, W, -1) for k, v in d.items()} for d in rows]
+
+    @torch.no_grad()
+    def predict(self, example, preds_dicts, test_cfg, **kwargs):
+        """mg_head.py:697-1086 -> list (per sample) of dict(box3d_lidar, scores, label_preds, metadata)."""
+        g = CenterHead._cfg
+        nms = g(test_cfg, "nms")
+        if g(nms, "use_multi_class_nms", False) or not g(nms, "use_rotate_nms", True):
+            raise NotImplementedError("MultiGroupHead.predict: only class-agnostic rotated NMS is built")
+        assert self.encode_background_as_zeros and self.use_sigmoid_score, "only sigmoid scores without a background column"
+        rng = g(test_cfg, "post_center_limit_range")
+        thr = float(g(test_cfg, "score_threshold"))
+        pre, post, iou = int(g(nms, "nms_pre_max_size")), int(g(nms, "nms_post_max_size")), float(g(nms, "nms_iou_threshold"))
+        batch_anchors = example["anchors"]
+        B = batch_anchors[0].shape[0]
+        meta = example.get("metadata") or [None] * B
+        rets = []
+        for ti, preds in enumerate(preds_dicts):
+            anchors = batch_anchors[ti].view(B, -1, self.anchor_dim)
+            box = preds["box_preds"].reshape(B, -1, self.box_n_dim)
+            cls = preds["cls_preds"].reshape(B, -1, self.num_classes[ti]).float()
+            reg = self.box_coder.decode_torch(box[:, :, :self.box_coder.code_size], anchors).float()
+            dirs = preds["dir_cls_preds"].reshape(B, -1, 2) if self.use_direction_classifier else None
+            task_out = []
+            for b in range(B):
+                scores = torch.sigmoid(cls[b])
+                top_scores, top_labels = (scores.squeeze(-1), torch.zeros_like(scores[:, 0], dtype=torch.long)) \
+                    if scores.shape[1] == 1 else torch.max(scores, dim=-1)
+                keep = top_scores >= thr if thr > 0.0 else torch.ones_like(top_scores, dtype=torch.bool)
+                bx, sc, lb = reg[b][keep], top_scores[keep], top_labels[keep]
+                dl = torch.max(dirs[b], dim=-1)[1][keep] if dirs is not None else None
+                if sc.shape[0]:
+                    k = min(pre, sc.shape[0])
+                    sc_k, idx = torch.topk(sc, k=k)                       # box_torch_ops.rotate_nms :522-526
+                    kept, n_kept = ops.nms_sorted(bx[idx][:, [0, 1, 2, 3, 4, 5, -1]].contiguous(), iou)
+                    sel = idx[kept[:int(n_kept.item())].long()][:post]
+                    bx, sc, lb = bx[sel], sc[sel], lb[sel]
+                    if dl is not None:
+                        dl = dl[sel]
+                        opp = ((bx[..., -1] - self.direction_offset) > 0) ^ dl.bool()
+                        bx = bx.clone()
+                        bx[..., -1] += torch.where(opp, torch.tensor(math.pi).type_as(bx), torch.tensor(0.0).type_as(bx))
+                    if rng is not None and len(rng) > 0:
+                        r = torch.tensor(rng, dtype=bx.dtype, device=bx.device)
+                        m = (bx[:, :3] >= r[:3]).all(1) & (bx[:, :3] <= r[3:]).all(1)
+                        bx, sc, lb = bx[m], sc[m], lb[m]
+                task_out.append(dict(box3d_lidar=bx, scores=sc, label_preds=lb, metadata=meta[b]))
+            rets.append(task_out)
+        out = []
+        for b in range(B):
+            flag, labels = 0, []
+            for ti, nc in enumerate(self.num_classes):
+                labels.append(rets[ti][b]["label_preds"] + flag)
+                flag += nc
+            out.append(dict(box3d_lidar=torch.cat([r[b]["box3d_lidar"] for r in rets]),
+                            scores=torch.cat([r[b]["scores"] for r in rets]), label_preds=torch.cat(labels),
+                            metadata=rets[0][b]["metadata"]))
+        return out
+
+    def loss(self, example, preds_dicts, **kwargs):
+        raise NotImplementedError("MultiGroupHead.loss (anchor target losses, mg_head.py:580-695) is not built")

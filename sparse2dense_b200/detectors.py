@@ -46,6 +46,14 @@ class BaseDetector(nn.Module):
         return self
 
 
+def _predict(head, preds, B, Hu, Wu, test_cfg, example):
+    """Head-specific decoding of row-form predictions: CenterHead decodes on the device from the rows; the anchor head
+    (MultiGroupHead) needs ``example["anchors"]`` and takes its reference-style dicts (rows are already NHWC-flattened)."""
+    if hasattr(head, "box_coder"):
+        return head.predict(example, preds, test_cfg)
+    return head.predict_rows(preds, B, Hu, Wu, test_cfg, example.get("metadata"))
+
+
 @DETECTORS.register_module
 class SingleStageDetector(BaseDetector):
     def __init__(self, reader, backbone, neck=None, bbox_head=None, train_cfg=None, test_cfg=None, pretrained=None):
@@ -140,7 +148,7 @@ class VoxelNet(SingleStageDetector):
         if return_feature and return_recon_feature:
             preds_nchw = [{h: _nchw(v, B, Hu, Wu, grad) for h, v in d.items()} for d in preds]
             return preds_nchw, _nchw(F_D_a, B, H, W, grad), _nchw(F_D_b, B, H, W, grad)
-        dets = self.bbox_head.predict_rows(preds, B, Hu, Wu, self.test_cfg, example.get("metadata"))
+        dets = _predict(self.bbox_head, preds, B, Hu, Wu, self.test_cfg, example)
         if return_feature:
             # F_D_a: the backbone's dense BEV map (voxelnet.py:66-72); F_D_b only exists with return_recon_feature
             return dets, _nchw(F_D_a, B, H, W, grad)
@@ -162,7 +170,7 @@ class KD_VoxelNet(VoxelNet):
         rows, voxel_feature, B, H, W = self._rows_forward(example)
         ups, (Hu, Wu), F_S_a, F_S_b = self.neck.forward_rows(rows, B, H, W)
         preds = self.bbox_head.forward_rows(ups, B, Hu, Wu)
-        dets = self.bbox_head.predict_rows(preds, B, Hu, Wu, self.test_cfg, example.get("metadata"))
+        dets = _predict(self.bbox_head, preds, B, Hu, Wu, self.test_cfg, example)
         return dets, ups, voxel_feature, F_S_a, F_S_b, B, H, W, Hu, Wu
 
     def student_rows(self, example, with_loss=True):
@@ -271,14 +279,14 @@ class KD_PointPillars(PointPillars):
         if return_loss or self.training:
             raise NotImplementedError("the distillation training branch is not built; call .eval() and return_loss=False")
         preds, _, _, _, B, _, _, Hu, Wu = self._rows(example)
-        return self.bbox_head.predict_rows(preds, B, Hu, Wu, self.test_cfg, example.get("metadata"))
+        return _predict(self.bbox_head, preds, B, Hu, Wu, self.test_cfg, example)
 
     def forward_two_stage(self, example, return_loss=True, **kwargs):
         """point_pillars.py:215-251 -> (boxes, bev_feature, None, None, F_S_a, F_S_b)."""
         if return_loss or self.training:
             raise NotImplementedError("the training branch is not built")
         preds, ups, F_S_a, F_S_b, B, H, W, Hu, Wu = self._rows(example)
-        boxes = self.bbox_head.predict_rows(preds, B, Hu, Wu, self.test_cfg, example.get("metadata"))
+        boxes = _predict(self.bbox_head, preds, B, Hu, Wu, self.test_cfg, example)
         return boxes, to_nchw(ups, B, Hu, Wu), None, None, to_nchw(F_S_a, B, H, W), to_nchw(F_S_b, B, H, W)
 
     def first_stage_raw(self, example):

@@ -491,6 +491,114 @@ sys.path.insert(0, os.path.join(ROOT, "tests"))
 from loss_common import loss_inputs  # noqa: E402
 
 
+MG_TASKS = [dict(num_class=3, class_names=["VEHICLE", "PEDESTRIAN", "CYCLIST"])]
+MG_ASSIGNER = dict(tasks=MG_TASKS, anchor_generators=[
+    dict(type="anchor_generator_range", sizes=[2.08, 4.73, 1.77], anchor_ranges=[-74.88, -74.88, 0, 74.88, 74.88, 0],
+         rotations=[0, 1.57], matched_threshold=0.55, unmatched_threshold=0.4, class_name="VEHICLE"),
+    dict(type="anchor_generator_range", sizes=[0.84, 0.91, 1.74], anchor_ranges=[-74.88, -74.88, 0, 74.88, 74.88, 0],
+         rotations=[0, 1.57], matched_threshold=0.5, unmatched_threshold=0.35, class_name="PEDESTRIAN"),
+    dict(type="anchor_generator_range", sizes=[0.84, 1.81, 1.77], anchor_ranges=[-74.88, -74.88, 0, 74.88, 74.88, 0],
+         rotations=[0, 1.57], matched_threshold=0.5, unmatched_threshold=0.3, class_name="CYCLIST")])
+
+
+def reference_mg_modules():
+    """The reference's own anchor generator (box_np_ops), box coder (box_torch_ops) and MultiGroupHead through the shim; the
+    compiled NMS extensions they import at module level (det3d.ops.nms.*) are stubbed -- they are not called here."""
+    import types
+    reference_dense_modules()
+
+    def stub(name, **kw):
+        m = types.ModuleType(name); m.__dict__.update(kw); sys.modules[name] = m; return m
+
+    def pkg(name, path):
+        m = types.ModuleType(name); m.__path__ = [path]; sys.modules[name] = m; return m
+    core = pkg("det3d.core", REF + "/det3d/core")
+    pkg("det3d.core.bbox", REF + "/det3d/core/bbox")
+    pkg("det3d.ops", REF + "/det3d/ops")
+    pkg("det3d.ops.nms", REF + "/det3d/ops/nms")
+    stub("det3d.ops.nms.nms_cpu", rotate_nms_cc=None)
+    stub("det3d.ops.nms.nms_gpu", nms_gpu=None, rotate_iou_gpu=None, rotate_nms_gpu=None)
+    import det3d.core.bbox.box_np_ops as bnp
+    import det3d.core.bbox.box_torch_ops as bto
+    core.box_torch_ops = bto
+    import det3d.core.bbox.box_coders as bc
+    import det3d.models.bbox_heads.mg_head as mg
+    from det3d.models.registry import LOSSES            # the losses are constructed by __init__ but not used by forward
+    for name in ("SigmoidFocalLoss", "WeightedSmoothL1Loss", "WeightedSoftmaxClassificationLoss"):
+        if name not in LOSSES.module_dict:
+            LOSSES.register_module(type(name, (object,), {"__init__": lambda self, **kw: None}))
+    return bnp, bc, mg
+
+
+def mg_input(seed, H, W):
+    rng = np.random.default_rng(seed)
+    return (rng.normal(size=(2, 128, H, W)) * (rng.random((2, 1, H, W)) < 0.4)).astype(np.float32)
+
+
+def make_mg_head_goldens():
+    """Anchors, Head.forward maps, decoded boxes and the pre-NMS selection of the reference's anchor head on a random
+    128-channel BEV map (SECOND configs: RPN[5] 128 -> MultiGroupHead, 2 anchors x 3 classes per cell)."""
+    import torch
+    from oracle import mg_head as OM
+    from sparse2dense_b200 import anchors as A
+    from sparse2dense_b200 import registry
+    bnp, bc, mg = reference_mg_modules()
+    H, W = 40, 36
+    # numpy >= 2 returns a tuple from meshgrid and the reference assigns into it (box_np_ops.py:915): hand it a list
+    meshgrid = np.meshgrid
+    bnp.np.meshgrid = lambda *a, **k: list(meshgrid(*a, **k))
+    ref_parts = []
+    for g in MG_ASSIGNER["anchor_generators"]:
+        a = bnp.create_anchors_3d_range([1, H, W], g["anchor_ranges"], g["sizes"], g["rotations"], None, np.float32)
+        ref_parts.append(a.reshape([*a.shape[:3], -1, a.shape[-1]]))
+    ref_anchors = np.concatenate(ref_parts, axis=-2).reshape(-1, 7)
+    bnp.np.meshgrid = meshgrid
+    ours = A.task_anchors(MG_ASSIGNER, [1, H, W])[0]
+    assert ours.shape == ref_anchors.shape and (ours.view(np.uint32) == ref_anchors.view(np.uint32)).all()
+    coder = bc.GroundBox3dCoderTorch(False, False, n_dim=7)
+    ref_head = mg.MultiGroupHead(mode="3d", in_channels=128, tasks=MG_TASKS, weights=[1], box_coder=coder,
+                                 encode_background_as_zeros=True, loss_norm=dict(type="NormByNumPositives", pos_cls_weight=1.0,
+                                                                                 neg_cls_weight=2.0),
+                                 loss_cls=dict(type="SigmoidFocalLoss", alpha=0.25, gamma=2.0, loss_weight=1.0),
+                                 use_sigmoid_score=True,
+                                 loss_bbox=dict(type="WeightedSmoothL1Loss", sigma=3.0, code_weights=[1.0] * 7, codewise=True,
+                                                loss_weight=2.0),
+                                 encode_rad_error_by_sin=True,
+                                 loss_aux=dict(type="WeightedSoftmaxClassificationLoss", name="direction_classifier",
+                                               loss_weight=0.2), direction_offset=0.0).eval()
+    mine = registry.build_head(dict(type="MultiGroupHead", mode="3d", in_channels=128, tasks=MG_TASKS, weights=[1],
+                                    box_coder=A.build_box_coder(dict(type="ground_box3d_coder", n_dim=7, linear_dim=False,
+                                                                     encode_angle_vector=False)),
+                                    loss_aux=dict(type="x"), direction_offset=0.0))
+    st = synth.random_module_state(mine, 41)
+    res = ref_head.load_state_dict({k: torch.from_numpy(v) for k, v in st.items()}, strict=False)
+    assert not res.unexpected_keys and not res.missing_keys, res
+    x = torch.from_numpy(mg_input(8, H, W))
+    with torch.no_grad():
+        rp = ref_head(x)[0]
+        op = OM.head_forward(st, x)
+        dec = coder.decode_torch(rp["box_preds"].view(2, -1, 7), torch.from_numpy(ref_anchors)[None].repeat(2, 1, 1)).numpy()
+    out = dict(head_seed=41, input_seed=8, H=H, W=W)
+    srng = np.random.default_rng(9)
+
+    def sample(name, arr):
+        idx = srng.choice(arr.size, size=min(4000, arr.size), replace=False)
+        out[name + "_idx"], out[name + "_val"] = idx.astype(np.int64), arr.reshape(-1)[idx]
+        out[name + "_absmax"] = np.float32(np.abs(arr).max())
+    sample("anchors", ref_anchors)
+    sample("decoded", dec)
+    for k in rp:
+        e = float((rp[k] - op[k]).abs().max() / rp[k].abs().max())
+        print(f"mg_head {k}: shape {tuple(rp[k].shape)} oracle-vs-reference rel err {e:.2e}")
+        assert e < 1e-5
+        sample(k, rp[k].numpy())
+    od = OM.decode(rp["box_preds"].reshape(2, -1, 7).numpy(), ref_anchors[None])
+    e = float(np.abs(od - dec).max() / np.abs(dec).max())
+    print(f"mg_head decode: oracle-vs-reference rel err {e:.2e}")
+    assert e < 1e-6
+    np.savez_compressed(os.path.join(HERE, "mg_head.npz"), **out)
+
+
 def make_loss_goldens():
     """FastFocalLoss / RegLoss of the reference (shim) + the trainer's distill expressions restated on torch CPU."""
     import torch
@@ -705,6 +813,9 @@ if __name__ == "__main__":
     if len(sys.argv) > 1 and sys.argv[1] == "pcr":
         make_pcr_loss_goldens()
         sys.exit(0)
+    if len(sys.argv) > 1 and sys.argv[1] == "mg":
+        make_mg_head_goldens()
+        sys.exit(0)
     if len(sys.argv) > 1 and sys.argv[1] == "optim":
         make_optim_goldens()
         sys.exit(0)
@@ -733,3 +844,4 @@ if __name__ == "__main__":
     make_optim_goldens()
     make_assign_goldens()
     make_pcr_loss_goldens()
+    make_mg_head_goldens()
