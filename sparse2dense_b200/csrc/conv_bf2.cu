@@ -200,7 +200,7 @@ conv_bf2_kernel(const __grid_constant__ B2Args A) {
     const int sub = kps == 2 ? (c8 >> 2) : 0;                // Cin = 16: pieces 0-3 come from offset 2kk, 4-7 from 2kk + 1
     const uint32_t piece = (uint32_t)(kps == 2 ? (c8 & 3) : c8) * 16u;
     const char* in_bytes = reinterpret_cast<const char*>(A.in);
-    const uint32_t row_bytes = (uint32_t)A.in_ld * 4u;
+    const uint32_t row_units = (uint32_t)A.in_ld >> 2;       // row stride in 16 B units (32-bit offsets reach 64 GiB)
     const int* tbl = A.tbl;
     const int tbl_stride = A.tbl_stride;
     const uint32_t a_stage = smem_u32(a_ring) + (uint32_t)warp * kB2AStage;
@@ -256,7 +256,7 @@ conv_bf2_kernel(const __grid_constant__ B2Args A) {
             sts32(scr + 768u + 4u * lane, qb.z); sts32(scr + 896u + 4u * lane, qb.w);
           }
         }
-        const uint32_t cbytes = (kps == 2 ? 0u : (e >> 9) * 128u) + piece;
+        const uint32_t cunits = (kps == 2 ? 0u : (e >> 9) * 8u) + (piece >> 4);
         // prefetch the entry and the indices of this warp's next block (NB blocks ahead)
         uint32_t e_n = 0;
         int4 qa_n = make_int4(-1, -1, -1, -1), qb_n = qa_n;
@@ -280,8 +280,8 @@ conv_bf2_kernel(const __grid_constant__ B2Args A) {
             for (int rr = 0; rr < 4; ++rr) {
               const int r = 4 * q + rr;                        // row 4r + o; (4r + o) & 7 = 4 (r & 1) + o
               const uint32_t dst = a_stage + (uint32_t)r * 512u + dst_lane + (uint32_t)((c8 ^ (4 * (r & 1) + o)) << 4);
-              const uint32_t off = (uint32_t)max(idx[rr], 0) * row_bytes + cbytes;
-              cp_async16_zfill(dst, in_bytes + off, (idx[rr] >= 0 && !(A.dbg & 16)) ? 16u : 0u);
+              const uint32_t off = (uint32_t)max(idx[rr], 0) * row_units + cunits;
+              cp_async16_zfill(dst, in_bytes + ((size_t)off << 4), (idx[rr] >= 0 && !(A.dbg & 16)) ? 16u : 0u);
             }
           }
           cp_async_commit();
@@ -825,8 +825,8 @@ int conv_fwd_bf2(const s2d_conv_params& p, cudaStream_t st) {
   S2D_REQUIRE(!p.residual || p.res_ld % 4 == 0, "s2d_conv_fwd: row strides must be multiples of 4 floats");
   S2D_REQUIRE(p.tbl_stride % 4 == 0 && (reinterpret_cast<uintptr_t>(p.tbl) & 15) == 0,
               "s2d_conv_fwd(bf16x2): the neighbour table must be 16 B aligned with tbl_stride %% 4 == 0 (got %d)", p.tbl_stride);
-  S2D_REQUIRE((unsigned long long)p.n_in * (unsigned long long)p.in_split_ld * 4ull < (1ull << 32),
-              "s2d_conv_fwd: input tensor larger than 4 GiB (32-bit gather offsets)");
+  S2D_REQUIRE((unsigned long long)p.n_in * (unsigned long long)p.in_split_ld * 4ull < (1ull << 36),
+              "s2d_conv_fwd: input tensor larger than 64 GiB (32-bit gather offsets in 16 B units)");
   const int cb = b2_cout_block(p.Cout);
   if (p.out_split) {
     S2D_REQUIRE(p.out_split_ld % 4 == 0 && (reinterpret_cast<uintptr_t>(p.out_split) & 15) == 0 &&

@@ -107,6 +107,38 @@ def fold_bn(bn, bias, cout, device):
     return scale.detach().contiguous(), shift.detach().contiguous()
 
 
+def rows_with_twin(n, c, device):
+    """A row buffer that several launches fill by column slices (``torch.cat`` by offset) together with its split-row twin:
+    every BF16-pair launch that writes a slice of the buffer also writes the same slice of the twin (``conv_rows`` finds it
+    through the view's base), and ``commit_twin`` publishes the twin once all slices are in, so the consumer's
+    ``ops.rows_split`` is a cache hit instead of a pass over the whole concatenation (1.2 GB of traffic for the 512-channel
+    188 x 188 maps of a batch of 8)."""
+    buf = torch.empty((n, c), dtype=torch.float32, device=device)
+    buf._s2d_twin = torch.empty((n, c), dtype=torch.int32, device=device)
+    buf._s2d_twin_state = [0, True]                      # [channels x launches written with a twin, no launch without one]
+    return buf
+
+
+def commit_twin(buf, expected):
+    """Publish the twin of ``rows_with_twin`` when ``expected`` twin-writing launches happened and none wrote fp32 only."""
+    st = getattr(buf, "_s2d_twin_state", None)
+    if st is not None and st[1] and st[0] == expected:
+        ops.set_split(buf, buf._s2d_twin)
+
+
+def _twin_slice(out, cout):
+    """The slice of the base buffer's twin that corresponds to the row view ``out`` (or None)."""
+    base = out._base if out._base is not None else out
+    twin = getattr(base, "_s2d_twin", None)
+    if twin is None or base.dim() != 2:
+        return None, None
+    off = (out.data_ptr() - base.data_ptr()) // 4
+    r0, c0 = divmod(off, base.stride(0))
+    if c0 % 32 or cout % 32 or out.stride(0) != base.stride(0):
+        return None, base
+    return twin[r0:r0 + out.shape[0], c0:c0 + cout], base
+
+
 def conv_rows(x, weight_kio, tbl, n_out, scale=None, shift=None, act=ACT_NONE, residual=None, res_after_act=False,
               out=None, out_rows=None, precision=ops.PRECISION_TF32X3, packed=None, out_split=None, want_split=True):
     """One gather-GEMM launch.  x / out / residual: 2-D views with stride(1) == 1; weight_kio: [K,Cin,Cout].
@@ -130,6 +162,14 @@ def conv_rows(x, weight_kio, tbl, n_out, scale=None, shift=None, act=ACT_NONE, r
         else:
             w = packed if packed is not None else ops.pack_weights_tf32(weight_kio, prec)
     xs = None
+    twin_base = None
+    if not fresh and out_split is None:
+        tw, twin_base = _twin_slice(out, cout)
+        if prec == ops.PRECISION_BF16X2 and tw is not None:
+            out_split = tw
+            twin_base._s2d_twin_state[0] += 1
+        elif twin_base is not None:
+            twin_base._s2d_twin_state[1] = False           # an fp32-only write: the twin must not be published
     if prec == ops.PRECISION_BF16X2:
         xs = ops.rows_split(x, cache=True)       # the twin is reused by the weight gradient / the next consumer of x
         if out_split is None and fresh and want_split and (cout % 32 == 0 or cout == 16):

@@ -15,7 +15,7 @@ from torch import nn
 from torch.nn import Conv2d
 
 from . import ops
-from .dense import ACT_GELU, ACT_NONE, ACT_RELU, DenseOps, to_nchw, to_rows
+from .dense import ACT_GELU, ACT_NONE, ACT_RELU, DenseOps, commit_twin, rows_with_twin, to_nchw, to_rows
 from .registry import NECKS, build_norm_layer
 
 
@@ -142,12 +142,16 @@ class RPN(nn.Module):
                 if ups is None:
                     s = self._upsample_strides[d]
                     H0, W0 = (int(H * s), int(W * s)) if s >= 1 else (int(H / round(1 / s)), int(W / round(1 / s)))
-                    ups = torch.empty((B * H0 * W0, sum(self._num_upsample_filters)), dtype=torch.float32,
-                                      device=x.device)
+                    ups = rows_with_twin(B * H0 * W0, sum(self._num_upsample_filters), x.device)
+                    launches = 0
+                m = self.deblocks[d][0]
+                launches += m.stride[0] * m.stride[1] if isinstance(m, nn.ConvTranspose2d) else 1   # sub-pixel classes
                 self._run_deblock(d, x, B, H, W, ups[:, off:off + cout])
                 off += cout
         if n_up == 0:
             return x, H, W
+        if not self._dense.training:
+            commit_twin(ups, launches)
         return ups, H0, W0
 
     def forward_rows(self, x, B, H, W):
@@ -208,7 +212,7 @@ class S2D_RPN(RPN):
         D = self._dense
         e1, e2 = self.encoder_1, self.encoder_2
         a, H1, W1 = D.conv("encoder_1.0", x, B, H, W, e1[0], e1[1], ACT_GELU)                      # 94
-        y_3 = torch.empty((B * H1 * W1, 512), dtype=torch.float32, device=x.device)              # cat([decoder_1, y_1])
+        y_3 = rows_with_twin(B * H1 * W1, 512, x.device)                                         # cat([decoder_1, y_1])
         y_1, _, _ = D.conv("encoder_1.3", a, B, H1, W1, e1[3], e1[4], ACT_GELU, out=y_3[:, 256:])
         a, H2, W2 = D.conv("encoder_2.0", y_1, B, H1, W1, e2[0], e2[1], ACT_GELU)                  # 47
         att, _, _ = D.conv("encoder_2.3", a, B, H2, W2, e2[3], e2[4], ACT_GELU)
@@ -219,6 +223,7 @@ class S2D_RPN(RPN):
             att, _, _ = D.conv(f"convnext_block_{bi + 1}.4", t, B, H2, W2, blk[4], None,
                                ACT_GELU if bi == 2 else ACT_NONE, residual=att)                    # (+ att), F.gelu on the last
         D.tconv("decoder_1.0", att, B, H2, W2, self.decoder_1[0], self.decoder_1[1], ACT_GELU, out=y_3[:, :256])
+        commit_twin(y_3, 1 + self.decoder_1[0].stride[0] ** 2)                                     # one conv + the sub-pixel classes
         d2 = self.decoder_2
         a, _, _ = D.conv("decoder_2.0", y_3, B, H1, W1, d2[0], d2[1], ACT_GELU)
         F_S_b, _, _ = D.tconv("decoder_2.3", a, B, H1, W1, d2[3], d2[4], ACT_GELU)                 # 188
