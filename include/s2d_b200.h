@@ -217,6 +217,13 @@ int s2d_table_tile_masks(const int* tbl, int tbl_stride, int K, int n_rows, int*
  * the tile masks of tbl_out.  A conv launched with tbl_out, out_rows = perm and these masks writes bit-identical results
  * (each output row still sums its offsets in the same order) while skipping the (tile, offset) pairs grouping has emptied.
  * Replaces nothing in the reference (spconv executes per-offset pair lists, spconv/ops.py indice_conv); K <= 27. */
+size_t s2d_rulebook_subm_grouped_workspace_bytes(int n_rows);
+/* s2d_rulebook_subm (3 x 3 x 3) built directly in grouped row order: perm, tbl[k][p] = neighbour k of row perm[p], tile masks;
+ * the key comes from the occupancy bitmap, so the scan-order table is never written (same result as s2d_rulebook_subm +
+ * s2d_table_group_rows). */
+int s2d_rulebook_subm_grouped(const int* coors, int n_rows, int batch, const int* shape_host, const int* dilation_host,
+                              const void* index, int* perm, int* tbl, int tbl_stride, int* tile_masks, void* workspace,
+                              size_t workspace_bytes, void* stream);
 size_t s2d_table_group_rows_workspace_bytes(int n_rows);
 int s2d_table_group_rows(const int* tbl, int tbl_stride, int K, int n_rows, int* perm, int* tbl_out, int out_stride,
                          int* tile_masks, void* workspace, size_t workspace_bytes, void* stream);

@@ -84,6 +84,8 @@ SIGNATURES = {
     "s2d_pcr_loss_bwd": (_i, [_vp, _vp, _i, _i, _i, _i, _vp, _vp, ctypes.c_longlong, _c_float_p, _vp, _vp, _vp, _vp, _vp]),
     "s2d_assign_label": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _i, ctypes.c_float, ctypes.c_float, ctypes.c_float, ctypes.c_float, _i, ctypes.c_double, _i, _i, _vp, _vp, _vp, _vp,
                               _vp, _vp, _vp]),
+    "s2d_rulebook_subm_grouped_workspace_bytes": (_sz, [_i]),
+    "s2d_rulebook_subm_grouped": (_i, [_vp, _i, _i, _vp, _vp, _vp, _vp, _vp, _i, _vp, _vp, _sz, _vp]),
     "s2d_table_group_rows_workspace_bytes": (_sz, [_i]),
     "s2d_table_group_rows": (_i, [_vp, _i, _i, _i, _vp, _vp, _i, _vp, _vp, _sz, _vp]),
     "s2d_table_transpose": (_i, [_vp, _i, _i, _i, _vp, _vp, _i, _i, _vp]),

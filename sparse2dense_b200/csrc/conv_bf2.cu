@@ -30,6 +30,7 @@
 //   warp 9      MMA issuer: one thread, six tcgen05.mma.kind::f16 per step (M = 128, N = COUT, K = 16), tcgen05.commit
 //               releases the rings / publishes the accumulators.  A single in-order issuer sees every mbarrier phase,
 //               so the dynamic step list needs no phase-aliasing rules.
+#include "grouping.cuh"
 #include "tc_ptx.cuh"
 
 namespace s2d {
@@ -653,22 +654,6 @@ __global__ void __launch_bounds__(128) tile_masks_kernel(const int* __restrict__
 // tiles become homogeneous and whole triples of offsets are skipped through the tile masks: live (tile, offset) pairs drop
 // to 35 % / 62 % / 68 % / 76 % on the four SubM stages and to 23-49 % on the strided layers.
 // ---------------------------------------------------------------------------------------------
-constexpr int kGrpRows = 1024;     // rows per block of the counting sort (one per thread)
-constexpr int kGrpBuckets = 512;
-
-// per-warp bucket counts of a block's 1024 rows: s_cnt[w][key] = rows of warp w with that key (match.any: no atomics, so
-// the order inside a bucket is the row order = a STABLE sort).  Returns this thread's rank among its warp's equal keys.
-__device__ __forceinline__ int group_block_counts(unsigned key, bool valid, unsigned short (*s_cnt)[kGrpBuckets]) {
-  uint4* z = reinterpret_cast<uint4*>(&s_cnt[0][0]);
-  for (int i = threadIdx.x; i < 32 * kGrpBuckets * 2 / 16; i += kGrpRows) z[i] = make_uint4(0, 0, 0, 0);
-  __syncthreads();
-  const unsigned m = __match_any_sync(0xffffffffu, valid ? key : 0xffffu);
-  const int lane = threadIdx.x & 31;
-  if (valid && lane == __ffs(m) - 1) s_cnt[threadIdx.x >> 5][key] = (unsigned short)__popc(m);
-  __syncthreads();
-  return __popc(m & ((1u << lane) - 1u));
-}
-
 __global__ void __launch_bounds__(kGrpRows) group_keys_hist_kernel(const int* __restrict__ tbl, int stride, int K, int n,
                                                                    unsigned short* __restrict__ keys, int* __restrict__ counts) {
   __shared__ __align__(16) unsigned short s_cnt[32][kGrpBuckets];
@@ -685,73 +670,6 @@ __global__ void __launch_bounds__(kGrpRows) group_keys_hist_kernel(const int* __
 #pragma unroll
     for (int w = 0; w < 32; ++w) total += s_cnt[w][threadIdx.x];
     counts[(size_t)blockIdx.x * kGrpBuckets + threadIdx.x] = total;
-  }
-}
-
-// counts[blk][b] -> exclusive prefix over the blocks of each half of the block range; tails[0..511] = start of bucket b in
-// the sorted order, tails[512..1023] = rows of bucket b in the first half (added by the scatter to second-half blocks)
-__global__ void __launch_bounds__(1024) group_scan_kernel(int* __restrict__ counts, int nblk, int* __restrict__ tails) {
-  __shared__ int s_tot[2][kGrpBuckets];
-  __shared__ int s_scan[kGrpBuckets];
-  const int b = threadIdx.x & (kGrpBuckets - 1), half = threadIdx.x >> 9;
-  const int mid = nblk / 2;
-  const int lo = half ? mid : 0, hi = half ? nblk : mid;
-  int run = 0;
-  int blk = lo;
-  for (; blk + 8 <= hi; blk += 8) {
-    int c[8];
-#pragma unroll
-    for (int u = 0; u < 8; ++u) c[u] = counts[(size_t)(blk + u) * kGrpBuckets + b];
-#pragma unroll
-    for (int u = 0; u < 8; ++u) {
-      counts[(size_t)(blk + u) * kGrpBuckets + b] = run;
-      run += c[u];
-    }
-  }
-  for (; blk < hi; ++blk) {
-    const int c = counts[(size_t)blk * kGrpBuckets + b];
-    counts[(size_t)blk * kGrpBuckets + b] = run;
-    run += c;
-  }
-  s_tot[half][b] = run;
-  __syncthreads();
-  if (half == 0) s_scan[b] = s_tot[0][b] + s_tot[1][b];
-  __syncthreads();
-  for (int off = 1; off < kGrpBuckets; off <<= 1) {
-    int add = 0;
-    if (half == 0 && b >= off) add = s_scan[b - off];
-    __syncthreads();
-    if (half == 0) s_scan[b] += add;
-    __syncthreads();
-  }
-  if (half == 0) {
-    tails[b] = s_scan[b] - (s_tot[0][b] + s_tot[1][b]);
-    tails[kGrpBuckets + b] = s_tot[0][b];
-  }
-}
-
-__global__ void __launch_bounds__(kGrpRows) group_scatter_kernel(const unsigned short* __restrict__ keys, int n, int nblk,
-                                                                 const int* __restrict__ counts, const int* __restrict__ tails,
-                                                                 int* __restrict__ perm) {
-  __shared__ __align__(16) unsigned short s_cnt[32][kGrpBuckets];
-  const int row = blockIdx.x * kGrpRows + threadIdx.x;
-  const bool valid = row < n;
-  const unsigned key = valid ? keys[row] : 0u;
-  const int rank = group_block_counts(key, valid, s_cnt);
-  if (threadIdx.x < kGrpBuckets) {                       // exclusive prefix over the block's warps, per bucket
-    int run = 0;
-#pragma unroll
-    for (int w = 0; w < 32; ++w) {
-      const int c = s_cnt[w][threadIdx.x];
-      s_cnt[w][threadIdx.x] = (unsigned short)run;
-      run += c;
-    }
-  }
-  __syncthreads();
-  if (valid) {
-    const int pos = counts[(size_t)blockIdx.x * kGrpBuckets + key] + tails[key] +
-                    ((int)blockIdx.x >= nblk / 2 ? tails[kGrpBuckets + key] : 0) + s_cnt[threadIdx.x >> 5][key] + rank;
-    perm[pos] = row;
   }
 }
 
@@ -884,8 +802,7 @@ extern "C" int s2d_table_tile_masks(const int* tbl, int tbl_stride, int K, int n
 
 extern "C" size_t s2d_table_group_rows_workspace_bytes(int n_rows) {
   if (n_rows < 0) return 0;
-  const size_t nblk = (size_t)div_up(n_rows > 0 ? n_rows : 1, kGrpRows);
-  return (nblk + 2) * kGrpBuckets * sizeof(int) + (((size_t)n_rows * sizeof(unsigned short) + 15) & ~size_t(15)) + 16;
+  return group_workspace_bytes(n_rows);
 }
 
 extern "C" int s2d_table_group_rows(const int* tbl, int tbl_stride, int K, int n_rows, int* perm, int* tbl_out,

@@ -14,6 +14,7 @@
 //
 // All kernels are integer, HBM/L2-latency bound, one thread per row (or per bitmap word).
 #include "common.cuh"
+#include "grouping.cuh"
 
 namespace s2d {
 
@@ -198,6 +199,73 @@ __global__ void __launch_bounds__(256) subm_table_kernel(const int4* __restrict_
   add_pairs(n_pairs, local);
 }
 
+// ---- submanifold rulebook built directly in GROUPED row order (conv_bf2.cu "Row grouping") -----------------------------
+// Pass 1: the 9-bit key of a row needs only the occupancy bits of its 27 neighbours (no rank, no permutation lookup);
+// pass 2 (after the counting sort of grouping.cuh): thread p builds the table column of row perm[p] and the block's
+// ballots give the live-offset mask of the 128-row tile.  The scan-order table is never written.
+__global__ void __launch_bounds__(kGrpRows) subm_keys_hist_kernel(const int4* __restrict__ coors, int n, ShapeP S, ConvP C,
+                                                                  GridIndexView idx, unsigned short* __restrict__ keys,
+                                                                  int* __restrict__ counts) {
+  __shared__ __align__(16) unsigned short s_cnt[32][kGrpBuckets];
+  const int row = blockIdx.x * kGrpRows + threadIdx.x;
+  unsigned key = 0;
+  if (row < n) {
+    const int4 c = coors[row];
+    int k = 0;
+    for (int kz = 0; kz < 3; ++kz) {
+      const int z = c.y + (kz - 1) * C.d[0];
+      for (int ky = 0; ky < 3; ++ky) {
+        const int y = c.z + (ky - 1) * C.d[1];
+        for (int kx = 0; kx < 3; ++kx, ++k) {
+          const int x = c.w + (kx - 1) * C.d[2];
+          if ((unsigned)z < (unsigned)S.D && (unsigned)y < (unsigned)S.H && (unsigned)x < (unsigned)S.W) {
+            const long long lin = S.lin(c.x, z, y, x);
+            if ((__ldg(idx.words + (lin >> 5)) >> (lin & 31)) & 1u) key |= 1u << (k / 3);
+          }
+        }
+      }
+    }
+    keys[row] = (unsigned short)key;
+  }
+  group_block_counts(key, row < n, s_cnt);
+  if (threadIdx.x < kGrpBuckets) {
+    int total = 0;
+#pragma unroll
+    for (int w = 0; w < 32; ++w) total += s_cnt[w][threadIdx.x];
+    counts[(size_t)blockIdx.x * kGrpBuckets + threadIdx.x] = total;
+  }
+}
+
+__global__ void __launch_bounds__(128) subm_table_grouped_kernel(const int4* __restrict__ coors, int n, ShapeP S, ConvP C,
+                                                                 GridIndexView idx, const int* __restrict__ perm,
+                                                                 int* __restrict__ tbl, int stride, int* __restrict__ masks) {
+  __shared__ unsigned s_mask;
+  if (threadIdx.x == 0) s_mask = 0u;
+  __syncthreads();
+  const int p = blockIdx.x * 128 + threadIdx.x;
+  int4 c = make_int4(0, 0, 0, 0);
+  if (p < n) c = coors[__ldg(perm + p)];
+  unsigned m = 0;
+  int k = 0;
+  for (int kz = 0; kz < 3; ++kz) {
+    const int z = c.y + (kz - 1) * C.d[0];
+    for (int ky = 0; ky < 3; ++ky) {
+      const int y = c.z + (ky - 1) * C.d[1];
+      for (int kx = 0; kx < 3; ++kx, ++k) {
+        const int x = c.w + (kx - 1) * C.d[2];
+        int j = -1;
+        if (p < n && (unsigned)z < (unsigned)S.D && (unsigned)y < (unsigned)S.H && (unsigned)x < (unsigned)S.W)
+          j = idx.lookup(S.lin(c.x, z, y, x));
+        if (p < n) tbl[(size_t)k * stride + p] = j;
+        if (__ballot_sync(0xffffffffu, j >= 0)) m |= 1u << k;
+      }
+    }
+  }
+  if ((threadIdx.x & 31) == 0 && m) atomicOr(&s_mask, m);
+  __syncthreads();
+  if (threadIdx.x == 0) masks[blockIdx.x] = (int)s_mask;
+}
+
 // Strided table: tbl[k][o] = row of the active input at o*s - p + k*d, or -1.
 __global__ void __launch_bounds__(256) sparse_table_kernel(const int4* __restrict__ out_coors, int n_out,
                                                            ShapeP Si, ConvP C, GridIndexView idx_in,
@@ -354,6 +422,39 @@ extern "C" int s2d_rulebook_subm(const int* coors, int n_rows, int batch, const 
       reinterpret_cast<const int4*>(coors), n_rows, S, C, I.view(), tbl, tbl_stride, n_pairs);
   S2D_LAUNCH_CHECK();
   count_launches(1);
+  return S2D_OK;
+}
+
+extern "C" size_t s2d_rulebook_subm_grouped_workspace_bytes(int n_rows) { return n_rows < 0 ? 0 : group_workspace_bytes(n_rows); }
+
+extern "C" int s2d_rulebook_subm_grouped(const int* coors, int n_rows, int batch, const int* shape_host,
+                                         const int* dilation_host, const void* index, int* perm, int* tbl, int tbl_stride,
+                                         int* tile_masks, void* workspace, size_t workspace_bytes, void* stream) {
+  int rc = check_shape(batch, shape_host, "s2d_rulebook_subm_grouped");
+  if (rc) return rc;
+  const int k3[3] = {3, 3, 3};
+  ConvP C;
+  rc = load_conv(C, k3, nullptr, nullptr, dilation_host, "s2d_rulebook_subm_grouped");
+  if (rc) return rc;
+  S2D_REQUIRE(n_rows >= 0 && tbl_stride >= n_rows, "s2d_rulebook_subm_grouped: tbl_stride %d < n_rows %d", tbl_stride, n_rows);
+  if (n_rows == 0) return S2D_OK;
+  S2D_REQUIRE(coors && index && perm && tbl && tile_masks && workspace, "s2d_rulebook_subm_grouped: null argument");
+  S2D_REQUIRE(workspace_bytes >= group_workspace_bytes(n_rows), "s2d_rulebook_subm_grouped: workspace too small");
+  const GridIndexLayout L = grid_index_layout(batch, shape_host, 0);
+  const GridIndexPtrs I = grid_index_ptrs(index, L);
+  const ShapeP S{batch, shape_host[0], shape_host[1], shape_host[2]};
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const int nblk = div_up(n_rows, kGrpRows);
+  int* counts = static_cast<int*>(workspace);
+  int* tails = counts + (size_t)nblk * kGrpBuckets;
+  unsigned short* keys = reinterpret_cast<unsigned short*>(tails + 2 * kGrpBuckets);
+  const int4* c4 = reinterpret_cast<const int4*>(coors);
+  subm_keys_hist_kernel<<<nblk, kGrpRows, 0, st>>>(c4, n_rows, S, C, I.view(), keys, counts);
+  group_scan_kernel<<<1, 1024, 0, st>>>(counts, nblk, tails);
+  group_scatter_kernel<<<nblk, kGrpRows, 0, st>>>(keys, n_rows, nblk, counts, tails, perm);
+  subm_table_grouped_kernel<<<div_up(n_rows, 128), 128, 0, st>>>(c4, n_rows, S, C, I.view(), perm, tbl, tbl_stride, tile_masks);
+  S2D_LAUNCH_CHECK();
+  count_launches(4);
   return S2D_OK;
 }
 

@@ -204,6 +204,23 @@ def rulebook_subm(coors, index, ksize=3, dilation=1, count_pairs=False):
     return (tbl, pairs) if count_pairs else tbl
 
 
+def rulebook_subm_grouped(coors, index, dilation=1):
+    """The 3x3x3 submanifold rulebook built directly in grouped row order (``s2d_rulebook_subm_grouped``) ->
+    (tbl i32 [27, n], perm i32 [n], tile_masks): identical to ``table_group_rows(rulebook_subm(...))``."""
+    _need_cuda(coors)
+    n = coors.shape[0]
+    lib = _lib.load()
+    tbl = alloc_table(27, n, coors.device)
+    perm = torch.empty((max(n, 1),), dtype=torch.int32, device=coors.device)
+    masks = torch.empty((max((n + 127) // 128, 1),), dtype=torch.int32, device=coors.device)
+    nbytes = lib.s2d_rulebook_subm_grouped_workspace_bytes(n)
+    ws = torch.empty((max(nbytes, 16),), dtype=torch.uint8, device=coors.device)
+    _lib.check(lib.s2d_rulebook_subm_grouped(_ptr(coors), n, index.batch, _lib.ints(index.shape), _lib.ints(_triple(dilation)),
+                                             _ptr(index.buf), _ptr(perm), _ptr(tbl), tbl.stride(0), _ptr(masks), _ptr(ws),
+                                             nbytes, _stream()), "s2d_rulebook_subm_grouped")
+    return tbl, perm, masks
+
+
 def conv_out_shape(shape, ksize, stride, pad, dilation=1):
     out = (_lib.ctypes.c_int * 3)()
     _lib.check(_lib.load().s2d_conv_out_shape(_lib.ints(_triple(shape)), _lib.ints(_triple(ksize)),
@@ -343,11 +360,15 @@ def table_group_rows(tbl, n_rows):
     return out, perm, masks
 
 
-def bf2_ok(cin, cout, tbl):
-    k = tbl.shape[0]
+def bf2_shape_ok(cin, cout, k):
+    """Shape part of ``bf2_ok`` (every table from ``alloc_table`` satisfies the layout part)."""
     nchunk = 1 if cin == 16 else cin // 32
-    return (cin == 16 or (cin >= 32 and cin % 32 == 0)) and cout % 16 == 0 and tbl.stride(0) % 4 == 0 and \
-        tbl.data_ptr() % 16 == 0 and k <= 27 and nchunk <= 128 and -(-k // (2 if cin == 16 else 1)) * nchunk <= 1024
+    return (cin == 16 or (cin >= 32 and cin % 32 == 0)) and cout % 16 == 0 and k <= 27 and nchunk <= 128 and \
+        -(-k // (2 if cin == 16 else 1)) * nchunk <= 1024
+
+
+def bf2_ok(cin, cout, tbl):
+    return bf2_shape_ok(cin, cout, tbl.shape[0]) and tbl.stride(0) % 4 == 0 and tbl.data_ptr() % 16 == 0
 
 
 def effective_precision(precision, cin, cout, tbl):

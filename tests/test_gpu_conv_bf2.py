@@ -155,3 +155,18 @@ def test_grouped_rows_are_a_permutation_and_give_bit_identical_results():
             b = ops.spconv_fwd(x, w, gt, n, sc, sh, r, True, ops.PRECISION_BF16X2, tile_masks=gmasks, out_rows=perm)
             assert torch.equal(a, b), c
             assert torch.equal(ops.get_split(a), ops.get_split(b)), c
+
+
+def test_grouped_submanifold_builder_equals_group_rows_of_the_scan_order_table():
+    """s2d_rulebook_subm_grouped (key from the occupancy bitmap, table written in grouped order) == s2d_rulebook_subm followed
+    by s2d_table_group_rows, bit for bit: permutation, table and tile masks."""
+    from sparse2dense_b200 import synth
+    from sparse2dense_b200.hotpath import concat_clouds
+    pts, offs = concat_clouds([synth.lidar_scene(31), synth.small_scene(32), synth.small_scene(33)])
+    vb = ops.voxelize(pts.cuda(), offs, synth.WAYMO_VOXEL, synth.WAYMO_RANGE, 5, 150000, want_voxels=False, mean_channels=5)
+    n = vb.n
+    coors = vb.coors_buffer[:n]
+    index = ops.build_grid_index(coors, 3, (41, 1504, 1504))
+    a_tbl, a_perm, a_masks = ops.table_group_rows(ops.rulebook_subm(coors, index, 3), n)
+    b_tbl, b_perm, b_masks = ops.rulebook_subm_grouped(coors, index)
+    assert torch.equal(a_perm[:n], b_perm[:n]) and torch.equal(a_tbl[:, :n], b_tbl[:, :n]) and torch.equal(a_masks, b_masks)
