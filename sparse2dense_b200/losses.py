@@ -45,7 +45,13 @@ def masked_mse_terms(f_student, f_teacher):
 
 
 class _MaskedMSE(torch.autograd.Function):
-    """w_pos * MSE(s | t > 0) + w_neg * MSE(s | t <= 0)."""
+    """w_pos * MSE(s | t > 0) + w_neg * MSE(s | t <= 0).
+
+    Empty partition (a map that is all-positive or all-non-positive): the VALUE is NaN (0 / 0), exactly what the reference's
+    ``F.mse_loss`` returns for an empty boolean selection (trainer.py:783-789), and the GRADIENT of that partition is zero --
+    also what the reference produces: autograd routes the NaN term's gradient through ``index`` of an empty selection, i.e. to
+    no element, so the student's gradient stays finite while the logged loss is NaN.  Value and gradient are therefore
+    consistent with the reference, not with each other."""
 
     @staticmethod
     def forward(ctx, fs, ft, w_pos, w_neg):
