@@ -117,10 +117,11 @@ class SpMiddleResNetFHD(nn.Module):
         for m in self.modules():
             if isinstance(m, spconv.SparseConvolution):
                 ok = precision != ops.PRECISION_FP32 and ops.tf32_supported(m.in_channels, m.out_channels)
-                # AUTO / BF16X2: narrow inputs (the 5-channel first layer) are zero-padded onto the tensor-core kernel
-                ok = ok or (precision in (ops.PRECISION_AUTO, ops.PRECISION_BF16X2) and m.in_channels < 16 and
-                            m.out_channels % 16 == 0)
                 m.precision = precision if ok else ops.PRECISION_FP32
+                # AUTO / BF16X2, inference only: a narrow input (the 5-channel first layer) is zero-padded onto the
+                # tensor-core kernel; its training path stays on the fp32 kernel (m.precision)
+                m.pad_narrow_input = (precision in (ops.PRECISION_AUTO, ops.PRECISION_BF16X2) and m.in_channels < 16 and
+                                      m.out_channels % 16 == 0)
 
     def bev_hw(self, input_shape):
         """(H, W) of the BEV map this backbone produces for a voxel grid ``input_shape`` = (x, y, z)."""

@@ -113,58 +113,55 @@ __global__ void __launch_bounds__(kWtThreads, 1) wgrad_tc_kernel(const __grid_co
   const uint32_t tmem_base = *s_tmem;
 
   if (warp < 4) {
-    // ===================== gather: thread = (row r of the stage, half h of its 128 B chunk rows) =====================
-    const int r = tid >> 1, h = tid & 1;
-    const uint32_t row_off = (uint32_t)r * 128u;
-    const uint32_t sw = (uint32_t)(r & 7);
-    const char* gb = reinterpret_cast<const char*>(A.g);
-    const char* db = reinterpret_cast<const char*>(A.d);
+    // ===================== gather: thread = (16 B piece of a 128 B chunk row, row group); four rows per thread ==========
+    // Eight lanes copy one whole 128 B row of a chunk, so a warp instruction moves four full rows (the first version gave
+    // a thread half a row: 32 half-used sectors per instruction, and the kernel ran at 10 B/clk/SM).
+    const int piece = tid & 7, rg = tid >> 3;                // rows rg, rg + 16, rg + 32, rg + 48 of the stage
+    const char* gb = reinterpret_cast<const char*>(A.g) + (size_t)a0 * 128 + piece * 16;
+    const char* db = reinterpret_cast<const char*>(A.d) + (size_t)b0 * 128 + piece * 16;
     const size_t g_row = (size_t)A.g_ld * 4, d_row = (size_t)A.d_ld * 4;
     const int* tk = A.tbl + (size_t)k0 * A.tbl_stride;
-    auto indices = [&](int slab, int (&ia)[4], int& id) {
-      const int i = row0 + slab * kWtRows + r;
-      ia[0] = ia[1] = ia[2] = ia[3] = id = -1;
-      if (i < row_end) {
+    auto indices = [&](int slab, int (&ia)[4][4], int (&id)[4]) {
 #pragma unroll
-        for (int t = 0; t < 4; ++t)
-          if (t < ntaps) ia[t] = __ldg(tk + (size_t)t * A.tbl_stride + i);
-        id = A.d_rows ? __ldg(A.d_rows + i) : i;
+      for (int q = 0; q < 4; ++q) {
+        const int i = row0 + slab * kWtRows + q * 16 + rg;
+        ia[q][0] = ia[q][1] = ia[q][2] = ia[q][3] = id[q] = -1;
+        if (i < row_end) {
+#pragma unroll
+          for (int t = 0; t < 4; ++t)
+            if (t < ntaps) ia[q][t] = __ldg(tk + (size_t)t * A.tbl_stride + i);
+          id[q] = A.d_rows ? __ldg(A.d_rows + i) : i;
+        }
       }
     };
-    int ia[4], id;
+    int ia[4][4], id[4];
     indices(0, ia, id);
+    const bool multi = A.tpc > 1;                            // several kernel offsets per CTA: chunk c -> offset c / cpt
 #pragma unroll 1
     for (int j = 0; j < n_slabs; ++j) {
       const int s = j % S;
       if (j >= S) mbar_wait(smem_u32(bar_empty + s), (uint32_t)((j / S) - 1) & 1u);
-      int ia_n[4] = {-1, -1, -1, -1}, id_n = -1;
-      if (j + 1 < n_slabs) indices(j + 1, ia_n, id_n);
-      const uint32_t base = smem0 + (uint32_t)s * Cfg::STAGE + row_off;
-      const char* ds = db + (size_t)max(id, 0) * d_row + (size_t)b0 * 128;
-      const uint32_t da = id >= 0 ? 16u : 0u;
+      int ia_n[4][4], id_n[4];
+      if (j + 1 < n_slabs) indices(j + 1, ia_n, id_n);       // next stage's index loads fly under this stage's copies
+      const uint32_t stage = smem0 + (uint32_t)s * Cfg::STAGE;
 #pragma unroll
-      for (int c = 0; c < NA; ++c) {
-        if (c < na) {
-          const int t = A.tpc > 1 ? c / cpt : 0, cc = A.tpc > 1 ? c % cpt : c;
-          const int it = ia[t];
-          const char* gs = gb + (size_t)max(it, 0) * g_row + (size_t)(a0 + cc) * 128;
-          const uint32_t ga = it >= 0 ? 16u : 0u;
+      for (int q = 0; q < 4; ++q) {
+        const int r = q * 16 + rg;
+        const uint32_t dst = stage + (uint32_t)r * 128u + (uint32_t)((piece ^ (r & 7)) << 4);
 #pragma unroll
-          for (int p = 0; p < 4; ++p) {
-            const uint32_t piece = (uint32_t)(4 * h + p);
-            cp_async16_zfill(base + (uint32_t)c * kWtChunk + ((piece ^ sw) << 4), gs + piece * 16, ga);
+        for (int c = 0; c < NA; ++c) {
+          if (c < na) {
+            // static register indices only (a runtime index would put ia[][] in local memory): cpt is 1 or 2 when multi
+            const int it = !multi ? ia[q][0] : (cpt == 1 ? ia[q][c & 3] : ia[q][(c >> 1) & 3]);
+            const int cc = !multi ? c : (cpt == 1 ? 0 : (c & 1));
+            cp_async16_zfill(dst + (uint32_t)c * kWtChunk, gb + (size_t)max(it, 0) * g_row + cc * 128, it >= 0 ? 16u : 0u);
           }
         }
-      }
+        const char* ds = db + (size_t)max(id[q], 0) * d_row;
+        const uint32_t da = id[q] >= 0 ? 16u : 0u;
 #pragma unroll
-      for (int c = 0; c < NB; ++c) {
-        if (c < nb) {
-#pragma unroll
-          for (int p = 0; p < 4; ++p) {
-            const uint32_t piece = (uint32_t)(4 * h + p);
-            cp_async16_zfill(base + (uint32_t)(NA + c) * kWtChunk + ((piece ^ sw) << 4), ds + c * 128 + piece * 16, da);
-          }
-        }
+        for (int c = 0; c < NB; ++c)
+          if (c < nb) cp_async16_zfill(dst + (uint32_t)(NA + c) * kWtChunk, ds + c * 128, da);
       }
       cp_async_commit();
       if (j >= kWtLag) {
@@ -172,9 +169,14 @@ __global__ void __launch_bounds__(kWtThreads, 1) wgrad_tc_kernel(const __grid_co
         fence_proxy_async();                                 // ... and are visible to the tensor core (async proxy)
         mbar_arrive(smem_u32(bar_full + (j - kWtLag) % S));
       }
+      if (j + 1 < n_slabs) {
 #pragma unroll
-      for (int t = 0; t < 4; ++t) ia[t] = ia_n[t];
-      id = id_n;
+        for (int q = 0; q < 4; ++q) {
+#pragma unroll
+          for (int t = 0; t < 4; ++t) ia[q][t] = ia_n[q][t];
+          id[q] = id_n[q];
+        }
+      }
     }
     if (n_slabs >= 2) {
       cp_async_wait<1>();

@@ -179,7 +179,7 @@ class SparseConvolution(SparseModule):
         K = self.kernel_size[0] * self.kernel_size[1] * self.kernel_size[2]
         feats_in, weight = x.features.contiguous(), self.weight.detach()
         cin = self.in_channels
-        auto = self.precision in (ops.PRECISION_AUTO, ops.PRECISION_BF16X2)
+        auto = self.precision in (ops.PRECISION_AUTO, ops.PRECISION_BF16X2) or self.__dict__.get("pad_narrow_input", False)
         if auto and cin < 16 and ops.bf2_shape_ok(16, self.out_channels, K):
             # the 5-channel input layer: zero-pad to 16 channels so that it runs on the tensor-core kernel over the stage's
             # grouped rulebook like every other layer (0.33 -> 0.12 ms at batch 8; the CUDA-core kernel needs the scan-order table)
