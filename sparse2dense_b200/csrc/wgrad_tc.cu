@@ -28,9 +28,13 @@
 
 namespace s2d {
 
-constexpr int kWtRows = 64;                // gathered rows per stage = 4 MMA k-steps of 16 rows
-constexpr int kWtChunk = kWtRows * 128;    // bytes of one 32-channel chunk of a stage (64 swizzled 128 B rows)
-constexpr int kWtLag = 2;                  // stages a gather thread keeps in flight behind the one it is issuing
+constexpr int kWtRows = 32;                // gathered rows per stage = 2 MMA k-steps of 16 rows
+constexpr int kWtChunk = kWtRows * 128;    // bytes of one 32-channel chunk of a stage (32 swizzled 128 B rows)
+// Stages a gather thread keeps in flight behind the one it is issuing.  A stage is published when the thread issues the
+// stage kWtLag later, and a stage can only be issued once the MMAs of the stage S earlier are done: the gather runs
+// S - kWtLag stages ahead of the tensor core.  (First version: 64-row stages, S = 3, lag 2 -> one stage of slack, i.e. MMA,
+// issue and barrier round trip fully serialised: 4.1 k clk per 64 rows against 1 k clk of MMA time.)
+constexpr int kWtLag = 3;
 constexpr int kWtThreads = 160;
 
 struct WtArgs {
@@ -52,7 +56,7 @@ struct WtCfg {
   static constexpr int COLS = MB * 64 * NB;
   static constexpr int TMEM_COLS = COLS <= 32 ? 32 : COLS <= 64 ? 64 : COLS <= 128 ? 128 : COLS <= 256 ? 256 : 512;
   static constexpr int SMEM = S * STAGE + 1024 + 256;
-  static_assert(S >= kWtLag + 1 && COLS <= 512, "stage ring / TMEM budget");
+  static_assert(S >= kWtLag + 2 && COLS <= 512, "stage ring / TMEM budget");
 };
 
 // MN-major, 128B-swizzled shared-memory matrix descriptor: start | LBO (between 64-element groups of M / N) | SBO (between
@@ -116,14 +120,15 @@ __global__ void __launch_bounds__(kWtThreads, 1) wgrad_tc_kernel(const __grid_co
     // ===================== gather: thread = (16 B piece of a 128 B chunk row, row group); four rows per thread ==========
     // Eight lanes copy one whole 128 B row of a chunk, so a warp instruction moves four full rows (the first version gave
     // a thread half a row: 32 half-used sectors per instruction, and the kernel ran at 10 B/clk/SM).
-    const int piece = tid & 7, rg = tid >> 3;                // rows rg, rg + 16, rg + 32, rg + 48 of the stage
+    constexpr int RQ = kWtRows / 16;                         // rows per thread and stage
+    const int piece = tid & 7, rg = tid >> 3;                // rows rg, rg + 16 of the stage
     const char* gb = reinterpret_cast<const char*>(A.g) + (size_t)a0 * 128 + piece * 16;
     const char* db = reinterpret_cast<const char*>(A.d) + (size_t)b0 * 128 + piece * 16;
     const size_t g_row = (size_t)A.g_ld * 4, d_row = (size_t)A.d_ld * 4;
     const int* tk = A.tbl + (size_t)k0 * A.tbl_stride;
-    auto indices = [&](int slab, int (&ia)[4][4], int (&id)[4]) {
+    auto indices = [&](int slab, int (&ia)[RQ][4], int (&id)[RQ]) {
 #pragma unroll
-      for (int q = 0; q < 4; ++q) {
+      for (int q = 0; q < RQ; ++q) {
         const int i = row0 + slab * kWtRows + q * 16 + rg;
         ia[q][0] = ia[q][1] = ia[q][2] = ia[q][3] = id[q] = -1;
         if (i < row_end) {
@@ -134,18 +139,18 @@ __global__ void __launch_bounds__(kWtThreads, 1) wgrad_tc_kernel(const __grid_co
         }
       }
     };
-    int ia[4][4], id[4];
+    int ia[RQ][4], id[RQ];
     indices(0, ia, id);
     const bool multi = A.tpc > 1;                            // several kernel offsets per CTA: chunk c -> offset c / cpt
 #pragma unroll 1
     for (int j = 0; j < n_slabs; ++j) {
       const int s = j % S;
       if (j >= S) mbar_wait(smem_u32(bar_empty + s), (uint32_t)((j / S) - 1) & 1u);
-      int ia_n[4][4], id_n[4];
+      int ia_n[RQ][4], id_n[RQ];
       if (j + 1 < n_slabs) indices(j + 1, ia_n, id_n);       // next stage's index loads fly under this stage's copies
       const uint32_t stage = smem0 + (uint32_t)s * Cfg::STAGE;
 #pragma unroll
-      for (int q = 0; q < 4; ++q) {
+      for (int q = 0; q < RQ; ++q) {
         const int r = q * 16 + rg;
         const uint32_t dst = stage + (uint32_t)r * 128u + (uint32_t)((piece ^ (r & 7)) << 4);
 #pragma unroll
@@ -171,12 +176,18 @@ __global__ void __launch_bounds__(kWtThreads, 1) wgrad_tc_kernel(const __grid_co
       }
       if (j + 1 < n_slabs) {
 #pragma unroll
-        for (int q = 0; q < 4; ++q) {
+        for (int q = 0; q < RQ; ++q) {
 #pragma unroll
           for (int t = 0; t < 4; ++t) ia[q][t] = ia_n[q][t];
           id[q] = id_n[q];
         }
       }
+    }
+    // drain: publish the last (up to kWtLag) stages in order
+    if (n_slabs >= 3) {
+      cp_async_wait<2>();
+      fence_proxy_async();
+      mbar_arrive(smem_u32(bar_full + (n_slabs - 3) % S));
     }
     if (n_slabs >= 2) {
       cp_async_wait<1>();
@@ -290,7 +301,7 @@ static WtPlan wt_plan(int n_rows, int K, int Cg, int Cd) {
   p.n_bblk = div_up(cb, p.NB);
   p.ktiles = div_up(K, p.tpc);
   const long long tiles = (long long)p.ktiles * p.n_ablk * p.n_bblk;
-  long long want = (2LL * kNumSMs + tiles - 1) / tiles;               // ~two CTAs per SM in total
+  long long want = (2LL * kNumSMs) / tiles;                            // at most two full waves of CTAs (one CTA per SM)
   const long long max_chunks = (n_rows + 511) / 512;                   // at least 512 rows per chunk
   if (want > max_chunks) want = max_chunks;
   if (want < 1) want = 1;
