@@ -224,6 +224,10 @@ size_t s2d_rulebook_subm_grouped_workspace_bytes(int n_rows);
 int s2d_rulebook_subm_grouped(const int* coors, int n_rows, int batch, const int* shape_host, const int* dilation_host,
                               const void* index, int* perm, int* tbl, int tbl_stride, int* tile_masks, void* workspace,
                               size_t workspace_bytes, void* stream);
+/* The strided 3 x 3 x 3 rulebook (s2d_rulebook_sparse) built directly in grouped row order; workspace as above. */
+int s2d_rulebook_sparse_grouped(const int* out_coors, int n_out, int batch, const int* shape_in_host, const int* stride_host,
+                                const int* pad_host, const int* dilation_host, const void* index_in, int* perm, int* tbl,
+                                int tbl_stride, int* tile_masks, void* workspace, size_t workspace_bytes, void* stream);
 size_t s2d_table_group_rows_workspace_bytes(int n_rows);
 int s2d_table_group_rows(const int* tbl, int tbl_stride, int K, int n_rows, int* perm, int* tbl_out, int out_stride,
                          int* tile_masks, void* workspace, size_t workspace_bytes, void* stream);

@@ -86,6 +86,7 @@ SIGNATURES = {
                               _vp, _vp, _vp]),
     "s2d_rulebook_subm_grouped_workspace_bytes": (_sz, [_i]),
     "s2d_rulebook_subm_grouped": (_i, [_vp, _i, _i, _vp, _vp, _vp, _vp, _vp, _i, _vp, _vp, _sz, _vp]),
+    "s2d_rulebook_sparse_grouped": (_i, [_vp, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _vp, _vp, _sz, _vp]),
     "s2d_table_group_rows_workspace_bytes": (_sz, [_i]),
     "s2d_table_group_rows": (_i, [_vp, _i, _i, _i, _vp, _vp, _i, _vp, _vp, _sz, _vp]),
     "s2d_table_transpose": (_i, [_vp, _i, _i, _i, _vp, _vp, _i, _i, _vp]),

@@ -199,7 +199,8 @@ __global__ void __launch_bounds__(256) subm_table_kernel(const int4* __restrict_
   add_pairs(n_pairs, local);
 }
 
-// ---- submanifold rulebook built directly in GROUPED row order (conv_bf2.cu "Row grouping") -----------------------------
+// ---- 3 x 3 x 3 rulebooks built directly in GROUPED row order (conv_bf2.cu "Row grouping") ----------------------------------
+// Input position of offset k for output voxel c: c * s - p + k * d (a submanifold layer is s = 1, p = d).
 // Pass 1: the 9-bit key of a row needs only the occupancy bits of its 27 neighbours (no rank, no permutation lookup);
 // pass 2 (after the counting sort of grouping.cuh): thread p builds the table column of row perm[p] and the block's
 // ballots give the live-offset mask of the 128-row tile.  The scan-order table is never written.
@@ -213,11 +214,11 @@ __global__ void __launch_bounds__(kGrpRows) subm_keys_hist_kernel(const int4* __
     const int4 c = coors[row];
     int k = 0;
     for (int kz = 0; kz < 3; ++kz) {
-      const int z = c.y + (kz - 1) * C.d[0];
+      const int z = c.y * C.s[0] - C.p[0] + kz * C.d[0];
       for (int ky = 0; ky < 3; ++ky) {
-        const int y = c.z + (ky - 1) * C.d[1];
+        const int y = c.z * C.s[1] - C.p[1] + ky * C.d[1];
         for (int kx = 0; kx < 3; ++kx, ++k) {
-          const int x = c.w + (kx - 1) * C.d[2];
+          const int x = c.w * C.s[2] - C.p[2] + kx * C.d[2];
           if ((unsigned)z < (unsigned)S.D && (unsigned)y < (unsigned)S.H && (unsigned)x < (unsigned)S.W) {
             const long long lin = S.lin(c.x, z, y, x);
             if ((__ldg(idx.words + (lin >> 5)) >> (lin & 31)) & 1u) key |= 1u << (k / 3);
@@ -248,11 +249,11 @@ __global__ void __launch_bounds__(128) subm_table_grouped_kernel(const int4* __r
   unsigned m = 0;
   int k = 0;
   for (int kz = 0; kz < 3; ++kz) {
-    const int z = c.y + (kz - 1) * C.d[0];
+    const int z = c.y * C.s[0] - C.p[0] + kz * C.d[0];
     for (int ky = 0; ky < 3; ++ky) {
-      const int y = c.z + (ky - 1) * C.d[1];
+      const int y = c.z * C.s[1] - C.p[1] + ky * C.d[1];
       for (int kx = 0; kx < 3; ++kx, ++k) {
-        const int x = c.w + (kx - 1) * C.d[2];
+        const int x = c.w * C.s[2] - C.p[2] + kx * C.d[2];
         int j = -1;
         if (p < n && (unsigned)z < (unsigned)S.D && (unsigned)y < (unsigned)S.H && (unsigned)x < (unsigned)S.W)
           j = idx.lookup(S.lin(c.x, z, y, x));
@@ -427,23 +428,13 @@ extern "C" int s2d_rulebook_subm(const int* coors, int n_rows, int batch, const 
 
 extern "C" size_t s2d_rulebook_subm_grouped_workspace_bytes(int n_rows) { return n_rows < 0 ? 0 : group_workspace_bytes(n_rows); }
 
-extern "C" int s2d_rulebook_subm_grouped(const int* coors, int n_rows, int batch, const int* shape_host,
-                                         const int* dilation_host, const void* index, int* perm, int* tbl, int tbl_stride,
-                                         int* tile_masks, void* workspace, size_t workspace_bytes, void* stream) {
-  int rc = check_shape(batch, shape_host, "s2d_rulebook_subm_grouped");
-  if (rc) return rc;
-  const int k3[3] = {3, 3, 3};
-  ConvP C;
-  rc = load_conv(C, k3, nullptr, nullptr, dilation_host, "s2d_rulebook_subm_grouped");
-  if (rc) return rc;
-  S2D_REQUIRE(n_rows >= 0 && tbl_stride >= n_rows, "s2d_rulebook_subm_grouped: tbl_stride %d < n_rows %d", tbl_stride, n_rows);
-  if (n_rows == 0) return S2D_OK;
-  S2D_REQUIRE(coors && index && perm && tbl && tile_masks && workspace, "s2d_rulebook_subm_grouped: null argument");
-  S2D_REQUIRE(workspace_bytes >= group_workspace_bytes(n_rows), "s2d_rulebook_subm_grouped: workspace too small");
-  const GridIndexLayout L = grid_index_layout(batch, shape_host, 0);
+namespace s2d {
+// shared by the two grouped builders: coors = OUTPUT coordinates, index / shape = INPUT tensor
+static int build_grouped(const int* coors, int n_rows, int batch, const int* shape_in_host, const ConvP& C, const void* index,
+                         int* perm, int* tbl, int tbl_stride, int* tile_masks, void* workspace, cudaStream_t st) {
+  const GridIndexLayout L = grid_index_layout(batch, shape_in_host, 0);
   const GridIndexPtrs I = grid_index_ptrs(index, L);
-  const ShapeP S{batch, shape_host[0], shape_host[1], shape_host[2]};
-  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const ShapeP S{batch, shape_in_host[0], shape_in_host[1], shape_in_host[2]};
   const int nblk = div_up(n_rows, kGrpRows);
   int* counts = static_cast<int*>(workspace);
   int* tails = counts + (size_t)nblk * kGrpBuckets;
@@ -456,6 +447,43 @@ extern "C" int s2d_rulebook_subm_grouped(const int* coors, int n_rows, int batch
   S2D_LAUNCH_CHECK();
   count_launches(4);
   return S2D_OK;
+}
+}  // namespace s2d
+
+extern "C" int s2d_rulebook_subm_grouped(const int* coors, int n_rows, int batch, const int* shape_host,
+                                         const int* dilation_host, const void* index, int* perm, int* tbl, int tbl_stride,
+                                         int* tile_masks, void* workspace, size_t workspace_bytes, void* stream) {
+  int rc = check_shape(batch, shape_host, "s2d_rulebook_subm_grouped");
+  if (rc) return rc;
+  const int k3[3] = {3, 3, 3};
+  ConvP C;
+  rc = load_conv(C, k3, nullptr, nullptr, dilation_host, "s2d_rulebook_subm_grouped");
+  if (rc) return rc;
+  for (int a = 0; a < 3; ++a) { C.s[a] = 1; C.p[a] = C.d[a]; }          // centred kernel: c - d + k * d
+  S2D_REQUIRE(n_rows >= 0 && tbl_stride >= n_rows, "s2d_rulebook_subm_grouped: tbl_stride %d < n_rows %d", tbl_stride, n_rows);
+  if (n_rows == 0) return S2D_OK;
+  S2D_REQUIRE(coors && index && perm && tbl && tile_masks && workspace, "s2d_rulebook_subm_grouped: null argument");
+  S2D_REQUIRE(workspace_bytes >= group_workspace_bytes(n_rows), "s2d_rulebook_subm_grouped: workspace too small");
+  return build_grouped(coors, n_rows, batch, shape_host, C, index, perm, tbl, tbl_stride, tile_masks, workspace,
+                       static_cast<cudaStream_t>(stream));
+}
+
+extern "C" int s2d_rulebook_sparse_grouped(const int* out_coors, int n_out, int batch, const int* shape_in_host,
+                                           const int* stride_host, const int* pad_host, const int* dilation_host,
+                                           const void* index_in, int* perm, int* tbl, int tbl_stride, int* tile_masks,
+                                           void* workspace, size_t workspace_bytes, void* stream) {
+  int rc = check_shape(batch, shape_in_host, "s2d_rulebook_sparse_grouped");
+  if (rc) return rc;
+  const int k3[3] = {3, 3, 3};
+  ConvP C;
+  rc = load_conv(C, k3, stride_host, pad_host, dilation_host, "s2d_rulebook_sparse_grouped");
+  if (rc) return rc;
+  S2D_REQUIRE(n_out >= 0 && tbl_stride >= n_out, "s2d_rulebook_sparse_grouped: tbl_stride %d < n_out %d", tbl_stride, n_out);
+  if (n_out == 0) return S2D_OK;
+  S2D_REQUIRE(out_coors && index_in && perm && tbl && tile_masks && workspace, "s2d_rulebook_sparse_grouped: null argument");
+  S2D_REQUIRE(workspace_bytes >= group_workspace_bytes(n_out), "s2d_rulebook_sparse_grouped: workspace too small");
+  return build_grouped(out_coors, n_out, batch, shape_in_host, C, index_in, perm, tbl, tbl_stride, tile_masks, workspace,
+                       static_cast<cudaStream_t>(stream));
 }
 
 extern "C" int s2d_conv_out_shape(const int* shape_in_host, const int* ksize_host, const int* stride_host,

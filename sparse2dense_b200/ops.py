@@ -221,6 +221,23 @@ def rulebook_subm_grouped(coors, index, dilation=1):
     return tbl, perm, masks
 
 
+def rulebook_sparse_grouped(out_coors, index_in, stride, pad, dilation=1):
+    """The strided 3x3x3 rulebook built directly in grouped row order -> (tbl i32 [27, n_out], perm, tile_masks)."""
+    _need_cuda(out_coors)
+    n = out_coors.shape[0]
+    lib = _lib.load()
+    tbl = alloc_table(27, n, out_coors.device)
+    perm = torch.empty((max(n, 1),), dtype=torch.int32, device=out_coors.device)
+    masks = torch.empty((max((n + 127) // 128, 1),), dtype=torch.int32, device=out_coors.device)
+    nbytes = lib.s2d_rulebook_subm_grouped_workspace_bytes(n)
+    ws = torch.empty((max(nbytes, 16),), dtype=torch.uint8, device=out_coors.device)
+    _lib.check(lib.s2d_rulebook_sparse_grouped(_ptr(out_coors), n, index_in.batch, _lib.ints(index_in.shape),
+                                               _lib.ints(_triple(stride)), _lib.ints(_triple(pad)), _lib.ints(_triple(dilation)),
+                                               _ptr(index_in.buf), _ptr(perm), _ptr(tbl), tbl.stride(0), _ptr(masks), _ptr(ws),
+                                               nbytes, _stream()), "s2d_rulebook_sparse_grouped")
+    return tbl, perm, masks
+
+
 def conv_out_shape(shape, ksize, stride, pad, dilation=1):
     out = (_lib.ctypes.c_int * 3)()
     _lib.check(_lib.load().s2d_conv_out_shape(_lib.ints(_triple(shape)), _lib.ints(_triple(ksize)),

@@ -103,8 +103,9 @@ def _fold_bn(bn, bias, cout, device):
 
 
 # group the rows of 27-offset rulebooks by neighbour pattern before the tile kernel (ops.table_group_rows):
-# 0 never, 1 submanifold rulebooks only (shared by the four convolutions of a stage), 2 strided rulebooks too
-GROUP_ROWS = int(__import__("os").environ.get("S2D_GROUP_ROWS", "1"))
+# 0 never, 1 submanifold rulebooks only (shared by the four convolutions of a stage), 2 strided rulebooks too (default:
+# both kinds are built directly in grouped order, which costs about as much as the scan-order table)
+GROUP_ROWS = int(__import__("os").environ.get("S2D_GROUP_ROWS", "2"))
 
 
 class SparseConvolution(SparseModule):
@@ -156,9 +157,10 @@ class SparseConvolution(SparseModule):
                 coords = ops.sparse_out_coords(x.indices, x.indices.shape[0], x.batch_size, x.spatial_shape,
                                                self.kernel_size, self.stride, self.padding, self.dilation)
             out_indices = coords.coors          # host count read here unless plan_coords() already did
-            tbl = ops.rulebook_sparse(out_indices, x.index(), self.kernel_size, self.stride, self.padding,
-                                      self.dilation)
-            ind = _Indice(tbl, out_indices, coords.index, coords.shape)
+            index_in, ks, st, pd, dl = x.index(), self.kernel_size, self.stride, self.padding, self.dilation
+            ind = _Indice(None, out_indices, coords.index, coords.shape,
+                          build=lambda: ops.rulebook_sparse(out_indices, index_in, ks, st, pd, dl))
+            ind.index_in = index_in             # for the grouped builder (ops.rulebook_sparse_grouped)
         if self.indice_key is not None:
             x.indice_dict[self.indice_key] = ind
         return ind
@@ -199,8 +201,12 @@ class SparseConvolution(SparseModule):
             grouped = ind.__dict__.get("grouped")
             if grouped is None:
                 if K == 27 and GROUP_ROWS >= (1 if self.subm else 2):
-                    if self.subm and ind._tbl is None and self.kernel_size == (3, 3, 3):
+                    direct = ind._tbl is None and self.kernel_size == (3, 3, 3)
+                    if direct and self.subm:
                         grouped = ops.rulebook_subm_grouped(ind.out_indices, ind.out_index, self.dilation)
+                    elif direct and "index_in" in ind.__dict__:
+                        grouped = ops.rulebook_sparse_grouped(ind.out_indices, ind.index_in, self.stride, self.padding,
+                                                              self.dilation)
                     else:
                         grouped = ops.table_group_rows(ind.tbl, n_out)
                 else:

@@ -170,3 +170,20 @@ def test_grouped_submanifold_builder_equals_group_rows_of_the_scan_order_table()
     a_tbl, a_perm, a_masks = ops.table_group_rows(ops.rulebook_subm(coors, index, 3), n)
     b_tbl, b_perm, b_masks = ops.rulebook_subm_grouped(coors, index)
     assert torch.equal(a_perm[:n], b_perm[:n]) and torch.equal(a_tbl[:, :n], b_tbl[:, :n]) and torch.equal(a_masks, b_masks)
+
+
+def test_grouped_strided_builder_equals_group_rows_of_the_scan_order_table():
+    """s2d_rulebook_sparse_grouped == s2d_rulebook_sparse + s2d_table_group_rows (stride 2 pad 1, and pad (0,1,1))."""
+    from sparse2dense_b200 import synth
+    from sparse2dense_b200.hotpath import concat_clouds
+    pts, offs = concat_clouds([synth.lidar_scene(41), synth.small_scene(42)])
+    vb = ops.voxelize(pts.cuda(), offs, synth.WAYMO_VOXEL, synth.WAYMO_RANGE, 5, 150000, want_voxels=False, mean_channels=5)
+    n = vb.n
+    coors, shape = vb.coors_buffer[:n], (41, 1504, 1504)
+    index = ops.build_grid_index(coors, 2, shape)
+    for pad in (1, (0, 1, 1)):
+        sc = ops.sparse_out_coords(coors, n, 2, shape, 3, 2, pad)
+        oc, m = sc.coors, sc.coors.shape[0]
+        a_tbl, a_perm, a_masks = ops.table_group_rows(ops.rulebook_sparse(oc, index, 3, 2, pad), m)
+        b_tbl, b_perm, b_masks = ops.rulebook_sparse_grouped(oc, index, 2, pad)
+        assert torch.equal(a_perm[:m], b_perm[:m]) and torch.equal(a_tbl[:, :m], b_tbl[:, :m]) and torch.equal(a_masks, b_masks)
