@@ -208,6 +208,15 @@ typedef struct s2d_conv_params {
   int in_split_ld, out_split_ld;
 } s2d_conv_params;
 int s2d_conv_fwd(const s2d_conv_params* params, void* stream);
+/* Dense-grid form of s2d_conv_fwd for a regular map [B, H, W] of split rows (stride 1, k x k kernel, padding `pad`; the
+ * Conv2d layers of det3d/models/necks/rpn.py and bbox_heads/center_head.py): no neighbour table -- the 128 rows a 16 x 8-pixel
+ * tile needs for a kernel offset are ONE 4-D TMA box (cp.async.bulk.tensor, zero fill outside the map = the padding).
+ * params: precision = S2D_PRECISION_BF16X2, in_split / in_split_ld = the map, n_in = B*H*W, tbl = NULL, K = k*k,
+ * n_out = s2d_grid2d_tile_rows_count(B, H, W) (tile-order rows), out_rows = s2d_grid2d_tile_rows(...) (tile-order row ->
+ * pixel row, -1 outside the map); everything else as for s2d_conv_fwd. */
+int s2d_grid2d_tile_rows_count(int B, int H, int W);
+int s2d_grid2d_tile_rows(int B, int H, int W, int* rows, void* stream);
+int s2d_conv_fwd_grid(const s2d_conv_params* params, int B, int H, int W, int k, int pad, void* stream);
 /* fp32 rows [n_rows, C] (row stride in_ld floats) -> split rows (row stride out_ld words); C == 16 or C % 32 == 0. */
 int s2d_rows_split(const float* in, long long n_rows, int C, int in_ld, void* out, int out_ld, void* stream);
 /* tile_masks[t] = OR over the rows r of tile t (128 rows) and the offsets k < K (<= 31) of (tbl[k][r] >= 0) << k. */

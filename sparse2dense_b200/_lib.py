@@ -40,6 +40,9 @@ SIGNATURES = {
     "s2d_spconv_pack_weights": (_i, [_vp, _i, _i, _i, _i, _vp, _vp]),
     "s2d_conv_fwd": (_i, [_vp, _vp]),
     "s2d_rows_split": (_i, [_vp, ctypes.c_longlong, _i, _i, _vp, _i, _vp]),
+    "s2d_grid2d_tile_rows_count": (_i, [_i, _i, _i]),
+    "s2d_grid2d_tile_rows": (_i, [_i, _i, _i, _vp, _vp]),
+    "s2d_conv_fwd_grid": (_i, [_vp, _i, _i, _i, _i, _i, _vp]),
     "s2d_table_tile_masks": (_i, [_vp, _i, _i, _i, _vp, _vp]),
     "s2d_grid2d_table": (_i, [_i, _i, _i, _i, _i, _i, _i, _vp, _i, _vp]),
     "s2d_grid2d_tconv_table": (_i, [_i, _i, _i, _i, _i, _i, _i, _i, _vp, _i, _vp, _vp]),

@@ -30,6 +30,8 @@
 //   warp 9      MMA issuer: one thread, six tcgen05.mma.kind::f16 per step (M = 128, N = COUT, K = 16), tcgen05.commit
 //               releases the rings / publishes the accumulators.  A single in-order issuer sees every mbarrier phase,
 //               so the dynamic step list needs no phase-aliasing rules.
+#include <string.h>
+
 #include "grouping.cuh"
 #include "tc_ptx.cuh"
 
@@ -108,10 +110,23 @@ struct B2Args {
   const int* out_rows;
   int in_ld, out_ld, res_ld, split_ld, tbl_stride, n_out, K, nchunk, kps, ksteps, act, res_after_act;
   int n_tiles, n_groups;     // 128-row tiles; groups of T consecutive tiles
+  // dense-grid (TMA) mode: the input is a regular [B, H, W] map, a tile is kGridTH x kGridTW pixels, the gathered tile of a
+  // kernel offset is ONE 4-D tensor-map box (zero fill outside the map = the convolution's padding)
+  int grid_tiles_x, grid_tiles_y, grid_kw, grid_pad;
   long long* prof;   // optional [gridDim.x][16] cycle counters (tools/microbench_bf2.py --prof), null in production
   int dbg;   // ablation switches (tools/microbench_bf2.py): 1 no gather, 2 no MMA, 4 no weight copies, 8 no stores, 16 all rows
              // missing, 64 no index loads, 128 no epilogue
 };
+
+constexpr int kGridTW = 16, kGridTH = 8;   // pixels of a dense-grid tile (16 x 8 = 128 rows)
+
+// 4-D tiled TMA load: box (32 words, kGridTW, kGridTH, 1) at (c, x, y, b) -> 128 swizzled 128 B rows at dst, completing on bar
+__device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* map, int c, int x, int y, int b, uint32_t bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4, %5}], [%6];" ::"r"(dst),
+      "l"(map), "r"(c), "r"(x), "r"(y), "r"(b), "r"(bar)
+      : "memory");
+}
 
 __device__ __forceinline__ float b2_act(float y, int act) {
   if (act == S2D_ACT_RELU) return fmaxf(y, 0.f);
@@ -134,9 +149,9 @@ __device__ __forceinline__ void split_pair(float a, float b, uint32_t& hi, uint3
 // the per-slot barriers); the epilogue warps drain a group's accumulators from one TMEM buffer while the next group
 // is gathered and multiplied into the other.
 //   block entry = kk | live-tile nibble << 5 | chunk << 9
-template <int COUT, int T, int S>
+template <int COUT, int T, int S, bool TMA>
 __global__ void __launch_bounds__(B2Cfg<COUT, T, S>::THREADS, B2Cfg<COUT, T, S>::CTAS_PER_SM)
-conv_bf2_kernel(const __grid_constant__ B2Args A) {
+conv_bf2_kernel(const __grid_constant__ B2Args A, const __grid_constant__ CUtensorMap in_map) {
   using Cfg = B2Cfg<COUT, T, S>;
   constexpr int kB2Stages = S, kB2ProducerWarps = S, kB2UtilWarp = Cfg::UTIL_WARP, kB2MmaWarp0 = Cfg::MMA_WARP0;
   constexpr int B_STAGE = Cfg::B_STAGE, NB = Cfg::NB, SB = Cfg::SB;
@@ -177,7 +192,7 @@ conv_bf2_kernel(const __grid_constant__ B2Args A) {
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(smem_u32(bar_list_full + s), 1);                  // utility warp, after writing the list
-      mbar_init(smem_u32(bar_list_empty + s), kB2ProducerWarps + T);   // producer + MMA warps done reading it
+      mbar_init(smem_u32(bar_list_empty + s), (TMA ? 1 : kB2ProducerWarps) + T);   // producer(s) + MMA warps done reading it
       mbar_init(smem_u32(bar_acc_full + s), T);                   // every MMA warp after its last MMA of the group
       mbar_init(smem_u32(bar_acc_empty + s), Cfg::EPI_WARPS);     // the epilogue warps
     }
@@ -191,7 +206,51 @@ conv_bf2_kernel(const __grid_constant__ B2Args A) {
   const uint32_t lists0 = smem_u32(lists);
   const bool prof = A.prof != nullptr;
 
-  if (warp < kB2ProducerWarps) {
+  if (TMA && warp < kB2ProducerWarps) {
+    // ===================== dense-grid producer: ONE thread issues a TMA box per (block, live tile) =====================
+    // The regular structure of a BEV map needs no neighbour table: the 128 rows a tile gathers for kernel offset (ky, kx)
+    // are the kGridTH x kGridTW box shifted by the offset, and everything outside the map is zero-filled by the TMA unit.
+    if (warp == 0 && lane == 0) {
+      uint32_t ph = (1u << kB2Stages) - 1u;                  // phase bit per stage; first use of every stage: free
+      const int tiles_img = A.grid_tiles_x * A.grid_tiles_y;
+      int gblk = 0, j = 0;
+#pragma unroll 1
+      for (int g = (int)blockIdx.x; g < n_groups; g += gstep, ++j) {
+        const int buf = j & 1;
+        mbar_wait(smem_u32(bar_list_full + buf), (uint32_t)(j >> 1) & 1u);
+        const int nblocks = (int)s_nblocks[buf];
+        const uint32_t list0 = lists0 + (uint32_t)buf * (kB2ListCap * 2);
+        int bx[T], by[T], bb[T];
+#pragma unroll
+        for (int t = 0; t < T; ++t) {
+          const int tile = g * T + t;
+          bb[t] = tile / tiles_img;
+          const int r = tile - bb[t] * tiles_img;
+          by[t] = (r / A.grid_tiles_x) * kGridTH - A.grid_pad;
+          bx[t] = (r % A.grid_tiles_x) * kGridTW - A.grid_pad;
+        }
+#pragma unroll 1
+        for (int ib = 0; ib < nblocks; ++ib) {
+          const uint32_t e = lds_u16(list0 + 2u * (uint32_t)ib);
+          const int kk = (int)(e & 31u), chunk = (int)(e >> 9);
+          const int ky = kk / A.grid_kw, kx = kk - ky * A.grid_kw;
+          const int slot = (gblk + ib) & (NB - 1);
+#pragma unroll
+          for (int t = 0; t < T; ++t) {
+            if (!((e >> (5 + t)) & 1u)) continue;
+            const int stage = slot * T + t;
+            mbar_wait(smem_u32(bar_a_empty + stage), (ph >> stage) & 1u);
+            ph ^= 1u << stage;
+            const uint32_t bar = smem_u32(bar_a_full + stage);
+            mbar_arrive_expect_tx(bar, kB2AStage);
+            tma_load_4d(smem_u32(a_ring) + (uint32_t)stage * kB2AStage, &in_map, chunk * 32, bx[t] + kx, by[t] + ky, bb[t], bar);
+          }
+        }
+        gblk += nblocks;
+        mbar_arrive(smem_u32(bar_list_empty + buf));
+      }
+    }
+  } else if (warp < kB2ProducerWarps) {
     // ===================== producers: warp w owns stage w = (slot w / T, tile w % T) =====================
     // A warp's iteration is a serial chain of ~100 dependent instructions plus the latency of its own copies, so whole
     // 128-row tiles are dealt over the warps: eight gathers are in flight and one mbarrier arrival publishes a stage.
@@ -361,7 +420,7 @@ conv_bf2_kernel(const __grid_constant__ B2Args A) {
       const int row_end = min(n_out, (g + 1) * T * kBM);
       auto prefetch_idx = [&](int ib) {
         const int pt = lane >> 3, ps = (lane >> 2) & 1, pl = lane & 3;
-        if (ib >= nblocks || pt >= T || ps >= kps || (A.dbg & 64)) return;
+        if (TMA || ib >= nblocks || pt >= T || ps >= kps || (A.dbg & 64)) return;
         const uint32_t e = lds_u16(list0 + 2u * (uint32_t)ib);
         if ((e >> 9) != 0u || !((e >> (5 + pt)) & 1u)) return;      // all chunks of an offset use the same indices
         const int k = (int)(e & 31u) * kps + ps;
@@ -534,7 +593,7 @@ conv_bf2_kernel(const __grid_constant__ B2Args A) {
             const int orow = __shfl_sync(0xffffffffu, orow_l, r);
             const int row = tile0 + t * kBM + g4 * 32 + r;
             float4 v = lds128(stg + (uint32_t)r * kB2EpiRow + 16u * pp);
-            if (row < row_end && !(A.dbg & 8)) {
+            if (row < row_end && orow >= 0 && !(A.dbg & 8)) {
               v.x = v.x * sc.x + sh.x; v.y = v.y * sc.y + sh.y; v.z = v.z * sc.z + sh.z; v.w = v.w * sc.w + sh.w;
               float4 rr = make_float4(0.f, 0.f, 0.f, 0.f);
               if (A.residual) rr = __ldg(reinterpret_cast<const float4*>(A.residual + (size_t)orow * A.res_ld + cblk + c0) + pp);
@@ -703,12 +762,13 @@ static int b2_cout_block(int Cout) {
 }
 bool bf2_supported(int Cin, int Cout) { return (Cin == 16 || (Cin >= 32 && Cin % 32 == 0)) && b2_cout_block(Cout) != 0; }
 
-template <int COUT, int T, int S>
-static int launch_b2(const B2Args& a, int Cout, cudaStream_t st) {
+template <int COUT, int T, int S, bool TMA>
+static int launch_b2(const B2Args& a, const CUtensorMap& map, int Cout, cudaStream_t st) {
   using Cfg = B2Cfg<COUT, T, S>;
   static bool configured = false;
   if (!configured) {
-    S2D_CUDA(cudaFuncSetAttribute(conv_bf2_kernel<COUT, T, S>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
+    S2D_CUDA(cudaFuncSetAttribute(conv_bf2_kernel<COUT, T, S, TMA>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  Cfg::SMEM_BYTES));
     configured = true;
   }
   B2Args b = a;
@@ -723,13 +783,45 @@ static int launch_b2(const B2Args& a, int Cout, cudaStream_t st) {
   if (gx < 1) gx = 1;
   if (gx > b.n_groups) gx = b.n_groups;
   const dim3 grid(gx, gy);
-  conv_bf2_kernel<COUT, T, S><<<grid, Cfg::THREADS, Cfg::SMEM_BYTES, st>>>(b);
+  conv_bf2_kernel<COUT, T, S, TMA><<<grid, Cfg::THREADS, Cfg::SMEM_BYTES, st>>>(b, map);
   S2D_LAUNCH_CHECK();
   count_launches(1);
   return S2D_OK;
 }
 
-int conv_fwd_bf2(const s2d_conv_params& p, cudaStream_t st) {
+// 4-D tensor map over a regular map of split rows [B, H, W, ld words]: box = 32 words x kGridTW x kGridTH x 1, 128B swizzle,
+// zeros outside (the convolution's padding and the ragged last tiles).
+static int make_grid_map(const void* base, int ld_words, int C, int B, int H, int W, CUtensorMap* map) {
+  const cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)B};
+  const cuuint64_t strides[3] = {(cuuint64_t)ld_words * 4, (cuuint64_t)ld_words * 4 * W, (cuuint64_t)ld_words * 4 * W * H};
+  const cuuint32_t box[4] = {32u, (cuuint32_t)kGridTW, (cuuint32_t)kGridTH, 1u};
+  const cuuint32_t estr[4] = {1u, 1u, 1u, 1u};
+  typedef CUresult (*EncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                               const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                               CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+  static EncodeFn encode = nullptr;
+  if (!encode) {             // resolved at run time: the library must load on a machine without a driver (build / ABI checks)
+    void* fn = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    S2D_CUDA(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &q));
+    S2D_REQUIRE(fn && q == cudaDriverEntryPointSuccess, "s2d_conv_fwd_grid: cuTensorMapEncodeTiled not available in this driver");
+    encode = reinterpret_cast<EncodeFn>(fn);
+  }
+  const CUresult r = encode(map, CU_TENSOR_MAP_DATA_TYPE_UINT32, 4, const_cast<void*>(base), dims, strides, box, estr,
+                            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("s2d_conv_fwd_grid: cuTensorMapEncodeTiled failed (%d) for base=%p ld=%d C=%d B=%d H=%d W=%d", (int)r, base, ld_words,
+              C, B, H, W);
+    return S2D_ERR_CUDA;
+  }
+  return S2D_OK;
+}
+
+// grid_k > 0: dense-grid (TMA) mode on a [grid_b, grid_h, grid_w] map with a grid_k x grid_k kernel and padding grid_pad
+static int conv_fwd_bf2_impl(const s2d_conv_params& p, int grid_b, int grid_h, int grid_w, int grid_k, int grid_pad,
+                             cudaStream_t st) {
+  const bool tma = grid_k > 0;
   if (!bf2_supported(p.Cin, p.Cout)) {
     set_error("s2d_conv_fwd: no bf16x2 kernel for Cin=%d Cout=%d (need Cin == 16 or Cin %% 32 == 0, Cout %% 16 == 0)", p.Cin,
               p.Cout);
@@ -741,7 +833,7 @@ int conv_fwd_bf2(const s2d_conv_params& p, cudaStream_t st) {
               "s2d_conv_fwd(bf16x2): split rows must be 16 B aligned with a row stride that is a multiple of 4 words");
   S2D_REQUIRE(!p.out || p.out_ld % 4 == 0, "s2d_conv_fwd: row strides must be multiples of 4 floats");
   S2D_REQUIRE(!p.residual || p.res_ld % 4 == 0, "s2d_conv_fwd: row strides must be multiples of 4 floats");
-  S2D_REQUIRE(p.tbl_stride % 4 == 0 && (reinterpret_cast<uintptr_t>(p.tbl) & 15) == 0,
+  S2D_REQUIRE(tma || (p.tbl_stride % 4 == 0 && (reinterpret_cast<uintptr_t>(p.tbl) & 15) == 0),
               "s2d_conv_fwd(bf16x2): the neighbour table must be 16 B aligned with tbl_stride %% 4 == 0 (got %d)", p.tbl_stride);
   S2D_REQUIRE((unsigned long long)p.n_in * (unsigned long long)p.in_split_ld * 4ull < (1ull << 36),
               "s2d_conv_fwd: input tensor larger than 64 GiB (32-bit gather offsets in 16 B units)");
@@ -760,13 +852,41 @@ int conv_fwd_bf2(const s2d_conv_params& p, cudaStream_t st) {
   a.res_after_act = p.res_after_act;
   a.dbg = g_b2_dbg;
   a.prof = g_b2_prof;
+  a.grid_tiles_x = a.grid_tiles_y = a.grid_kw = a.grid_pad = 0;
+  CUtensorMap map;
+  memset(&map, 0, sizeof(map));
+  if (tma) {
+    S2D_REQUIRE(p.Cin % 32 == 0 && p.K == grid_k * grid_k && p.out_rows && !p.tile_masks,
+                "s2d_conv_fwd_grid: needs Cin %% 32 == 0, K = k*k, out_rows (s2d_grid2d_tile_rows) and no tile masks");
+    a.grid_tiles_x = div_up(grid_w, kGridTW);
+    a.grid_tiles_y = div_up(grid_h, kGridTH);
+    a.grid_kw = grid_k;
+    a.grid_pad = grid_pad;
+    S2D_REQUIRE(p.n_out == grid_b * a.grid_tiles_x * a.grid_tiles_y * kBM, "s2d_conv_fwd_grid: n_out must be tiles x 128");
+    const int rc = make_grid_map(p.in_split, p.in_split_ld, p.Cin, grid_b, grid_h, grid_w, &map);
+    if (rc != S2D_OK) return rc;
+    if (cb == 128) return launch_b2<128, 2, 8, true>(a, map, p.Cout, st);
+    if (cb == 64) return launch_b2<64, 4, 8, true>(a, map, p.Cout, st);
+    if (cb == 32) return launch_b2<32, 4, 8, true>(a, map, p.Cout, st);
+    return launch_b2<16, 4, 8, true>(a, map, p.Cout, st);
+  }
   const int v = g_b2_variant;
   // variant 0: production choice; 1: T = 2.  (Two CTAs per SM with half the stage ring each, S = 4, measured no faster: the
   // kernel is bound by shared-memory bandwidth and the tensor pipe, which both CTAs share, not by barrier latency.)
-  if (cb == 128) return launch_b2<128, 2, 8>(a, p.Cout, st);
-  if (cb == 64) return v == 1 ? launch_b2<64, 2, 8>(a, p.Cout, st) : launch_b2<64, 4, 8>(a, p.Cout, st);
-  if (cb == 32) return v == 1 ? launch_b2<32, 2, 8>(a, p.Cout, st) : launch_b2<32, 4, 8>(a, p.Cout, st);
-  return v == 1 ? launch_b2<16, 2, 8>(a, p.Cout, st) : launch_b2<16, 4, 8>(a, p.Cout, st);
+  if (cb == 128) return launch_b2<128, 2, 8, false>(a, map, p.Cout, st);
+  if (cb == 64) return v == 1 ? launch_b2<64, 2, 8, false>(a, map, p.Cout, st) : launch_b2<64, 4, 8, false>(a, map, p.Cout, st);
+  if (cb == 32) return v == 1 ? launch_b2<32, 2, 8, false>(a, map, p.Cout, st) : launch_b2<32, 4, 8, false>(a, map, p.Cout, st);
+  return v == 1 ? launch_b2<16, 2, 8, false>(a, map, p.Cout, st) : launch_b2<16, 4, 8, false>(a, map, p.Cout, st);
+}
+
+int conv_fwd_bf2(const s2d_conv_params& p, cudaStream_t st) { return conv_fwd_bf2_impl(p, 0, 0, 0, 0, 0, st); }
+
+// out_rows of the dense-grid mode: tile-order row -> pixel row (b * H + y) * W + x, or -1 outside the map
+__global__ void __launch_bounds__(128) grid_tile_rows_kernel(int B, int H, int W, int tiles_x, int tiles_y, int* __restrict__ rows) {
+  const int tile = blockIdx.x, r = threadIdx.x;
+  const int b = tile / (tiles_x * tiles_y), rem = tile - b * tiles_x * tiles_y;
+  const int y = (rem / tiles_x) * kGridTH + r / kGridTW, x = (rem % tiles_x) * kGridTW + r % kGridTW;
+  rows[(size_t)tile * kBM + r] = (y < H && x < W) ? (b * H + y) * W + x : -1;
 }
 
 int pack_weights_bf2(const float* W, int K, int Cin, int Cout, void* packed, cudaStream_t st) {
@@ -825,6 +945,29 @@ extern "C" int s2d_table_group_rows(const int* tbl, int tbl_stride, int K, int n
   S2D_LAUNCH_CHECK();
   count_launches(4);
   return S2D_OK;
+}
+
+extern "C" int s2d_grid2d_tile_rows_count(int B, int H, int W) {
+  return (B < 1 || H < 1 || W < 1) ? 0 : B * div_up(H, kGridTH) * div_up(W, kGridTW) * kBM;
+}
+
+extern "C" int s2d_grid2d_tile_rows(int B, int H, int W, int* rows, void* stream) {
+  S2D_REQUIRE(B >= 1 && H >= 1 && W >= 1 && rows, "s2d_grid2d_tile_rows: bad argument");
+  const int tx = div_up(W, kGridTW), ty = div_up(H, kGridTH);
+  grid_tile_rows_kernel<<<B * tx * ty, 128, 0, static_cast<cudaStream_t>(stream)>>>(B, H, W, tx, ty, rows);
+  S2D_LAUNCH_CHECK();
+  count_launches(1);
+  return S2D_OK;
+}
+
+extern "C" int s2d_conv_fwd_grid(const s2d_conv_params* params, int B, int H, int W, int k, int pad, void* stream) {
+  S2D_REQUIRE(params, "s2d_conv_fwd_grid: null params");
+  const s2d_conv_params& p = *params;
+  S2D_REQUIRE(p.precision == S2D_PRECISION_BF16X2, "s2d_conv_fwd_grid: only S2D_PRECISION_BF16X2");
+  S2D_REQUIRE(B >= 1 && H >= 1 && W >= 1 && k >= 1 && k * k <= 27 && pad >= 0 && p.n_in == B * H * W,
+              "s2d_conv_fwd_grid: bad grid (B=%d H=%d W=%d k=%d pad=%d n_in=%d)", B, H, W, k, pad, p.n_in);
+  S2D_REQUIRE(p.act >= S2D_ACT_NONE && p.act <= S2D_ACT_GELU && p.weights, "s2d_conv_fwd_grid: bad argument");
+  return conv_fwd_bf2_impl(p, B, H, W, k, pad, static_cast<cudaStream_t>(stream));
 }
 
 extern "C" int s2d_rows_split(const float* in, long long n_rows, int C, int in_ld, void* out, int out_ld, void* stream) {

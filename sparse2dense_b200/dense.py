@@ -139,8 +139,12 @@ def _twin_slice(out, cout):
     return twin[r0:r0 + out.shape[0], c0:c0 + cout], base
 
 
+GRID_TMA = int(__import__("os").environ.get("S2D_GRID_TMA", "1"))     # 0: table-driven gathers for the regular grids too (A-B)
+
+
 def conv_rows(x, weight_kio, tbl, n_out, scale=None, shift=None, act=ACT_NONE, residual=None, res_after_act=False,
-              out=None, out_rows=None, precision=ops.PRECISION_TF32X3, packed=None, out_split=None, want_split=True):
+              out=None, out_rows=None, precision=ops.PRECISION_TF32X3, packed=None, out_split=None, want_split=True,
+              grid=None):
     """One gather-GEMM launch.  x / out / residual: 2-D views with stride(1) == 1; weight_kio: [K,Cin,Cout].
     ``packed``: a weight image for ``ops.effective_precision(precision, ...)`` or a dict precision -> image.
     With the BF16-pair kernel the input is read in split-row form (the producer's twin when ``x`` carries one, else
@@ -176,8 +180,15 @@ def conv_rows(x, weight_kio, tbl, n_out, scale=None, shift=None, act=ACT_NONE, r
             out_split = torch.empty((out.shape[0], cout), dtype=torch.int32, device=x.device)
     else:
         out_split = None
-    ops.conv_launch(x, w, tbl, n_out, cin, cout, K, scale, shift, act, residual, res_after_act, out, out_rows, prec, xs,
-                    out_split)
+    if grid is not None and GRID_TMA and prec == ops.PRECISION_BF16X2 and out_rows is None and cin % 32 == 0 and \
+            x.shape[0] == grid[0] * grid[1] * grid[2]:
+        # stride-1 Conv2d on a regular map: TMA boxes instead of the neighbour table (s2d_conv_fwd_grid)
+        rows, n_tile_rows = ops.grid_tile_rows(x.device, grid[0], grid[1], grid[2])
+        ops.conv_launch(x, w, None, n_tile_rows, cin, cout, K, scale, shift, act, residual, res_after_act, out, rows, prec, xs,
+                        out_split, grid=grid)
+    else:
+        ops.conv_launch(x, w, tbl, n_out, cin, cout, K, scale, shift, act, residual, res_after_act, out, out_rows, prec, xs,
+                        out_split)
     if out_split is not None and fresh:
         ops.set_split(out, out_split)
     return out
@@ -289,8 +300,11 @@ class DenseOps:
         tbl, Ho, Wo = conv_table(x.device, B, H, W, k, s, pad)
         kio, packed = self._conv_weights(name, conv)
         scale, shift = self._affine(name, conv, bn)
+        # stride-1 3x3 layers: TMA boxes instead of the neighbour table (3-7 % faster: no table reads, one issuing thread);
+        # 1x1 layers stay on the table path (the 16 x 8-pixel tiles pad the map edges: 4 % more rows, measured 5-10 % slower)
+        grid = (B, H, W, k, pad) if (s == 1 and k == 3 and pad == 1 and conv.dilation[0] == 1) else None
         y = conv_rows(x, kio, tbl, B * Ho * Wo, scale, shift, act, residual, res_after_act, out, None,
-                      self.precision, packed)
+                      self.precision, packed, grid=grid)
         return y, Ho, Wo
 
     def tconv(self, name, x, B, H, W, conv, bn=None, act=ACT_NONE, out=None):

@@ -402,8 +402,10 @@ def effective_precision(precision, cin, cout, tbl):
 
 def conv_launch(x, w_arg, tbl, n_out, cin, cout, k, scale=None, shift=None, act=0, residual=None, res_after_act=False,
                 out=None, out_rows=None, precision=PRECISION_FP32, x_split=None, out_split=None, tile_masks=None,
-                kind="dense"):
-    """One ``s2d_conv_fwd`` call.  x / out / residual / x_split / out_split: 2-D row views with stride(1) == 1 (or None)."""
+                kind="dense", grid=None):
+    """One ``s2d_conv_fwd`` call.  x / out / residual / x_split / out_split: 2-D row views with stride(1) == 1 (or None).
+    ``grid = (B, H, W, k, pad)``: the dense-grid form ``s2d_conv_fwd_grid`` (TMA boxes instead of a neighbour table;
+    ``tbl`` is None, ``n_out`` / ``out_rows`` come from ``grid_tile_rows``)."""
     p = _lib.ConvParams()
     p.in_, p.weights, p.tbl = _ptr(x), _ptr(w_arg), _ptr(tbl)
     p.scale, p.shift, p.residual = _ptr(scale), _ptr(shift), _ptr(residual)
@@ -411,7 +413,7 @@ def conv_launch(x, w_arg, tbl, n_out, cin, cout, k, scale=None, shift=None, act=
     p.in_ld = 0 if x is None else x.stride(0)
     p.out_ld = 0 if out is None else out.stride(0)
     p.res_ld = 0 if residual is None else residual.stride(0)
-    p.tbl_stride, p.K = tbl.stride(0), k
+    p.tbl_stride, p.K = (0 if tbl is None else tbl.stride(0)), k
     p.n_in = (x if x is not None else x_split).shape[0]
     p.n_out, p.Cin, p.Cout = n_out, cin, cout
     p.act, p.res_after_act, p.precision = int(act), int(bool(res_after_act)), int(precision)
@@ -422,10 +424,32 @@ def conv_launch(x, w_arg, tbl, n_out, cin, cout, k, scale=None, shift=None, act=
     if KERNEL_EVENTS is not None:
         ev = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
         ev[0].record()
-    _lib.check(_lib.load().s2d_conv_fwd(_lib.ctypes.byref(p), _stream()), "s2d_conv_fwd")
+    if grid is not None:
+        B, H, W, ksz, pad = grid
+        _lib.check(_lib.load().s2d_conv_fwd_grid(_lib.ctypes.byref(p), B, H, W, ksz, pad, _stream()), "s2d_conv_fwd_grid")
+    else:
+        _lib.check(_lib.load().s2d_conv_fwd(_lib.ctypes.byref(p), _stream()), "s2d_conv_fwd")
     if ev is not None:
         ev[1].record()
-        KERNEL_EVENTS.append(((cin, cout, k, residual is not None, p.n_in, n_out, int(precision), kind), ev[0], ev[1]))
+        n_rows = n_out if grid is None else grid[0] * grid[1] * grid[2]       # real output rows (tile order pads the edges)
+        KERNEL_EVENTS.append(((cin, cout, k, residual is not None, p.n_in, n_rows, int(precision), kind), ev[0], ev[1]))
+
+
+_GRID_ROWS = {}
+
+
+def grid_tile_rows(device, B, H, W):
+    """(out_rows i32 [n_tiles * 128], n_tile_rows) of the dense-grid conv: tile-order row -> pixel row, -1 outside the map
+    (cached per shape and device)."""
+    key = (str(device), B, H, W)
+    hit = _GRID_ROWS.get(key)
+    if hit is None:
+        lib = _lib.load()
+        n = lib.s2d_grid2d_tile_rows_count(B, H, W)
+        rows = torch.empty((n,), dtype=torch.int32, device=device)
+        _lib.check(lib.s2d_grid2d_tile_rows(B, H, W, _ptr(rows), _stream()), "s2d_grid2d_tile_rows")
+        hit = _GRID_ROWS[key] = (rows, n)
+    return hit
 
 
 def spconv_fwd(feats, weight, tbl, n_out, scale=None, shift=None, residual=None, relu=False,

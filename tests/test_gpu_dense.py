@@ -149,3 +149,23 @@ def test_plain_rpn_forward_vs_torch():
         ref = torch.cat(ups, 1)
         got = neck.cuda()(x.cuda())
     assert rel_err(got.cpu().numpy(), ref.numpy()) < 1e-3
+
+
+@pytest.mark.parametrize("B,H,W,cin,cout", [(2, 47, 47, 256, 256), (1, 188, 188, 128, 128), (3, 20, 33, 64, 320), (2, 9, 5, 512, 64),
+                                            (1, 16, 8, 32, 16)])
+def test_dense_grid_tma_conv_equals_table_conv_bitwise(B, H, W, cin, cout):
+    """s2d_conv_fwd_grid (TMA boxes, 16 x 8-pixel tiles, zero fill = padding, ragged edge tiles) writes exactly the bits of the
+    table-driven launch: every output row accumulates the same (chunk, offset) blocks in the same order."""
+    torch.manual_seed(B * 1000 + H)
+    n = B * H * W
+    x = torch.relu(torch.randn(n, cin, device="cuda"))
+    w = torch.randn(9, cin, cout, device="cuda") / (9 * cin) ** 0.5
+    sc, sh = torch.rand(cout, device="cuda") + 0.5, torch.randn(cout, device="cuda")
+    res = torch.randn(n, cout, device="cuda")
+    tbl, Ho, Wo = dense.conv_table(torch.device("cuda"), B, H, W, 3, 1, 1)
+    for r, act in ((None, dense.ACT_RELU), (res, dense.ACT_GELU)):
+        a = dense.conv_rows(x, w, tbl, n, sc, sh, act, r, False, precision=ops.PRECISION_BF16X2)
+        b = dense.conv_rows(x, w, tbl, n, sc, sh, act, r, False, precision=ops.PRECISION_BF16X2, grid=(B, H, W, 3, 1))
+        assert torch.equal(a, b)
+        if cout % 32 == 0:
+            assert torch.equal(ops.get_split(a), ops.get_split(b))
