@@ -99,3 +99,45 @@ def test_multi_group_head_forward_and_predict_on_gpu():
             ok = (np.abs(got_b[:, :2] - bx[i, :2]).max(1) < 1e-3) & (got_l == lb[i]) & (np.abs(got_s - sc[i]) < 1e-4)
             hit += bool(ok.any())
         assert hit >= 0.98 * len(sc), (hit, len(sc))
+
+
+@pytest.mark.gpu
+def test_second_detector_runs_end_to_end_with_anchors():
+    """The SECOND student of configs/waymo/voxelnet/waymo_second_3x_distill_interval_5.py (KD_VoxelNet: SpMiddleResNetFHD ->
+    S2D_RPN -> MultiGroupHead) built through the registry, one small scene, anchors as AssignTarget would provide them."""
+    import logging
+    from sparse2dense_b200 import ops
+    from sparse2dense_b200.hotpath import concat_clouds
+    cfg = dict(type="KD_VoxelNet", pretrained=None, reader=dict(type="VoxelFeatureExtractorV3", num_input_features=5),
+               backbone=dict(type="SpMiddleResNetFHD", num_input_features=5, ds_factor=8),
+               neck=dict(type="S2D_RPN", layer_nums=[5, 5], ds_layer_strides=[1, 2], ds_num_filters=[128, 256],
+                         us_layer_strides=[1, 2], us_num_filters=[256, 256], num_input_features=256,
+                         logger=logging.getLogger("RPN")),
+               bbox_head=dict(type="MultiGroupHead", mode="3d", in_channels=512, tasks=TASKS, weights=[1],
+                              box_coder=A.build_box_coder(dict(type="ground_box3d_coder", n_dim=7, linear_dim=False,
+                                                               encode_angle_vector=False)),
+                              loss_aux=dict(type="WeightedSoftmaxClassificationLoss"), direction_offset=0.0))
+    model = registry.build_detector(cfg, train_cfg=None, test_cfg=TEST_CFG)
+    model.backbone.load_state_dict({k: torch.as_tensor(v) for k, v in synth.backbone_state(0).items()}, strict=False)
+    for i, m in enumerate((model.neck, model.bbox_head)):
+        m.load_state_dict({k: torch.as_tensor(v) for k, v in synth.random_module_state(m, 51 + i).items()}, strict=False)
+    model = model.cuda().eval()
+    model.set_precision(ops.PRECISION_AUTO)
+    clouds = [synth.small_scene(61), synth.small_scene(62)]
+    pts, offs = concat_clouds(clouds)
+    vb = ops.voxelize(pts.cuda(), offs, synth.WAYMO_VOXEL, synth.WAYMO_RANGE, 5, 150000, want_voxels=True)
+    counts = np.diff(vb.offsets_host())
+    anchors = A.task_anchors(ASSIGNER, [1, 188, 188])
+    example = dict(voxels=vb.voxels, coordinates=vb.coors, num_points=vb.num_points, num_voxels=torch.as_tensor(counts),
+                   shape=[np.array([1504, 1504, 40])] * 2, metadata=[{"token": "a"}, {"token": "b"}],
+                   anchors=[torch.from_numpy(a)[None].repeat(2, 1, 1).cuda() for a in anchors])
+    before = ops.kernel_launches()
+    with torch.no_grad():
+        out = model(example, return_loss=False)
+    assert ops.kernel_launches() - before > 100 and len(out) == 2
+    for b in range(2):
+        n = out[b]["box3d_lidar"].shape[0]
+        assert out[b]["box3d_lidar"].shape == (n, 7) and out[b]["scores"].shape == (n,) and n <= 500
+        assert out[b]["metadata"]["token"] == "ab"[b]
+        if n:
+            assert float(out[b]["scores"].min()) >= 0.3 and int(out[b]["label_preds"].max()) <= 2
