@@ -211,3 +211,28 @@ def test_unmodified_reference_waymo_configs_load_and_build():
         assert n >= 1, f
         built += n
     assert built >= 27, built              # 22 files, five of them with a teacher and a student dict
+
+
+def test_twin_slice_maps_a_column_view_onto_the_same_columns_of_the_twin():
+    """dense.rows_with_twin / _twin_slice (host logic of the concat buffers): a column-slice view of the buffer resolves to the
+    same rows / columns of the split twin; unaligned or foreign views resolve to nothing; commit_twin publishes only when
+    every expected launch wrote its slice."""
+    from sparse2dense_b200 import dense, ops
+    buf = dense.rows_with_twin(10, 128, "cpu")
+    view = buf[:, 64:128]
+    tw, base = dense._twin_slice(view, 64)
+    assert base is buf and tw.shape == (10, 64) and tw.data_ptr() == buf._s2d_twin[:, 64:].data_ptr()
+    rows = buf[3:7, 32:64]
+    tw, _ = dense._twin_slice(rows, 32)
+    assert tw.data_ptr() == buf._s2d_twin[3:7, 32:64].data_ptr() and tw.shape == (4, 32)
+    assert dense._twin_slice(buf[:, 16:48], 32)[0] is None               # not on a 32-channel boundary
+    assert dense._twin_slice(torch.empty(10, 64), 64) == (None, None)    # no twin attached
+    dense.commit_twin(buf, 2)
+    assert ops.get_split(buf) is None                                    # nothing written yet
+    buf._s2d_twin_state[0] = 2
+    dense.commit_twin(buf, 2)
+    assert ops.get_split(buf) is buf._s2d_twin
+    other = dense.rows_with_twin(4, 64, "cpu")
+    other._s2d_twin_state[:] = [2, False]                                # one launch wrote fp32 only
+    dense.commit_twin(other, 2)
+    assert ops.get_split(other) is None
