@@ -51,3 +51,27 @@ extern "C" int s2d_export_i32(const int* src, int n, int* dst_host_mapped, void*
 extern "C" unsigned long long s2d_kernel_launches(void) { return s2d::g_launches.load(); }
 extern "C" int s2d_version(void) { return 100; }
 extern "C" const char* s2d_last_error(void) { return s2d::g_err; }
+
+// fp32 FFMA microbenchmark (tools/measure_peaks.py; not part of the public header): every thread runs `iters` rounds of 16
+// independent FMAs, 2 * 16 * iters * threads flops in total.  The denominator for the kernels that still run on CUDA cores.
+namespace s2d {
+__global__ void __launch_bounds__(256) ffma_peak_kernel(int iters, float* __restrict__ sink) {
+  float a[16];
+#pragma unroll
+  for (int i = 0; i < 16; ++i) a[i] = (float)(threadIdx.x + i) * 1e-3f;
+  const float m = 1.0000001f, c = 1e-9f;
+  for (int it = 0; it < iters; ++it) {
+#pragma unroll
+    for (int i = 0; i < 16; ++i) a[i] = fmaf(a[i], m, c);
+  }
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < 16; ++i) s += a[i];
+  if (s == 12345.678f) sink[0] = s;            // never true: keeps the loop alive
+}
+}  // namespace s2d
+extern "C" long long s2d_debug_ffma(int iters, float* sink, void* stream) {
+  const int blocks = s2d::kNumSMs * 16;
+  s2d::ffma_peak_kernel<<<blocks, 256, 0, static_cast<cudaStream_t>(stream)>>>(iters, sink);
+  return 2LL * 16 * iters * blocks * 256;       // flops of the launch
+}
