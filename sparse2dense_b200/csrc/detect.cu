@@ -76,15 +76,49 @@ __global__ void __launch_bounds__(1024) topk_sort_kernel(const unsigned long lon
     return tot;
   };
 
-  // the K-th largest key (keys are unique: the cell index is part of the key); 1 = "every valid key"
+  // the K-th largest key (keys are unique: the cell index is part of the key); 1 = "every valid key".
+  // Radix select, one byte per pass from the top: histogram of the byte among the keys that match the prefix found so far
+  // (warp-aggregated shared-memory atomics: the high bytes of a score take few distinct values), then walk the bins from 255
+  // down to the one that contains the pre_max-th largest key.  8 passes over the keys (the first version tested one BIT per
+  // pass: 65 passes, 0.6 ms for the 219 k cells of a pillar map).
   unsigned long long thr = 1ull;
   const int n_valid = block_count_ge(1ull);
   if (n_valid > pre_max) {
-    thr = 0ull;
-    for (int bit = 63; bit >= 0; --bit) {
-      const unsigned long long cand = thr | (1ull << bit);
-      if (block_count_ge(cand) >= pre_max) thr = cand;     // block-uniform
+    __shared__ int s_hist[256];
+    __shared__ int s_pick[2];
+    unsigned long long prefix = 0ull, mask = 0ull;
+    int remaining = pre_max;
+    for (int shift = 56; shift >= 0; shift -= 8) {
+      for (int i = tid; i < 256; i += 1024) s_hist[i] = 0;
+      __syncthreads();
+      for (int i0 = 0; i0 < cells; i0 += 1024) {
+        const int i = i0 + tid;
+        const unsigned long long v = i < cells ? k[i] : 0ull;
+        const bool in = i < cells && (v & mask) == prefix;
+        const unsigned digit = (unsigned)(v >> shift) & 255u;
+        const unsigned act = __ballot_sync(0xffffffffu, in);
+        if (in) {
+          const unsigned peers = __match_any_sync(act, digit);
+          if ((tid & 31) == __ffs(peers) - 1) atomicAdd(&s_hist[digit], __popc(peers));
+        }
+      }
+      __syncthreads();
+      if (tid == 0) {
+        int cum = 0, b = 255;
+        for (; b > 0; --b) {
+          if (cum + s_hist[b] >= remaining) break;
+          cum += s_hist[b];
+        }
+        s_pick[0] = b;
+        s_pick[1] = remaining - cum;                       // rank of the wanted key inside bin b
+      }
+      __syncthreads();
+      prefix |= (unsigned long long)s_pick[0] << shift;
+      mask |= 255ull << shift;
+      remaining = s_pick[1];
+      __syncthreads();
     }
+    thr = prefix;
   }
   const int n_sel = n_valid > pre_max ? pre_max : n_valid;
   for (int i = tid; i < kNmsMaxBoxes; i += 1024) s_keys[i] = 0ull;
