@@ -66,7 +66,16 @@ __global__ void __launch_bounds__(1024) topk_sort_kernel(const unsigned long lon
 
   auto block_count_ge = [&](unsigned long long thr) {
     int c = 0;
-    for (int i = tid; i < cells; i += 1024) c += (k[i] >= thr) ? 1 : 0;
+    for (int i0 = 0; i0 < cells; i0 += 8 * 1024) {               // eight independent loads in flight per thread: the loop is
+      unsigned long long v[8];                                   // latency bound (one CTA per sample), not bandwidth bound
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        const int i = i0 + u * 1024 + tid;
+        v[u] = i < cells ? __ldg(k + i) : 0ull;
+      }
+#pragma unroll
+      for (int u = 0; u < 8; ++u) c += (v[u] >= thr && v[u] != 0ull) ? 1 : 0;
+    }
     for (int d = 16; d > 0; d >>= 1) c += __shfl_xor_sync(0xffffffffu, c, d);
     __syncthreads();
     if ((tid & 31) == 0) s_red[tid >> 5] = c;
@@ -91,15 +100,22 @@ __global__ void __launch_bounds__(1024) topk_sort_kernel(const unsigned long lon
     for (int shift = 56; shift >= 0; shift -= 8) {
       for (int i = tid; i < 256; i += 1024) s_hist[i] = 0;
       __syncthreads();
-      for (int i0 = 0; i0 < cells; i0 += 1024) {
-        const int i = i0 + tid;
-        const unsigned long long v = i < cells ? k[i] : 0ull;
-        const bool in = i < cells && (v & mask) == prefix;
-        const unsigned digit = (unsigned)(v >> shift) & 255u;
-        const unsigned act = __ballot_sync(0xffffffffu, in);
-        if (in) {
-          const unsigned peers = __match_any_sync(act, digit);
-          if ((tid & 31) == __ffs(peers) - 1) atomicAdd(&s_hist[digit], __popc(peers));
+      for (int i0 = 0; i0 < cells; i0 += 8 * 1024) {
+        unsigned long long v[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+          const int i = i0 + u * 1024 + tid;
+          v[u] = i < cells ? __ldg(k + i) : 0ull;                // 0 never matches a non-zero prefix; with prefix 0 it only
+        }                                                        // lands in bins below the wanted one (n_valid > pre_max)
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+          const bool in = i0 + u * 1024 + tid < cells && (v[u] & mask) == prefix;
+          const unsigned digit = (unsigned)(v[u] >> shift) & 255u;
+          const unsigned act = __ballot_sync(0xffffffffu, in);
+          if (in) {
+            const unsigned peers = __match_any_sync(act, digit);
+            if ((tid & 31) == __ffs(peers) - 1) atomicAdd(&s_hist[digit], __popc(peers));
+          }
         }
       }
       __syncthreads();
@@ -124,9 +140,16 @@ __global__ void __launch_bounds__(1024) topk_sort_kernel(const unsigned long lon
   for (int i = tid; i < kNmsMaxBoxes; i += 1024) s_keys[i] = 0ull;
   if (tid == 0) s_cnt = 0;
   __syncthreads();
-  for (int i = tid; i < cells; i += 1024) {
-    const unsigned long long v = k[i];
-    if (v >= thr && v != 0ull) s_keys[atomicAdd(&s_cnt, 1)] = v;
+  for (int i0 = 0; i0 < cells; i0 += 8 * 1024) {
+    unsigned long long v[8];
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+      const int i = i0 + u * 1024 + tid;
+      v[u] = i < cells ? __ldg(k + i) : 0ull;
+    }
+#pragma unroll
+    for (int u = 0; u < 8; ++u)
+      if (v[u] >= thr && v[u] != 0ull) s_keys[atomicAdd(&s_cnt, 1)] = v[u];
   }
   __syncthreads();
   // bitonic sort, descending (zeros sink to the end)
