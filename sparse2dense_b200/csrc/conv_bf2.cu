@@ -16,20 +16,26 @@
 // operand tile, and the tensor core reads A and B from shared memory (SS mode).  No register ever holds an operand.
 // BF16 MMAs run at twice the TF32 rate, so the three products cost 1.5 TF32 passes (TF32x3 cost 3, TF32+BF16C 2).
 //
-// Executed work is cut by skipping (tile, kernel offset) pairs in which no row of the 128-row tile has a neighbour:
-// the rulebook builders emit one 27-bit liveness mask per tile (rows are ordered by their neighbour pattern, see
-// rulebook.cu), and all warp roles walk the same compacted step list.
+// Executed work is cut by skipping (tile, kernel offset) pairs in which no row of the 128-row tile has a neighbour: the
+// rulebook rows are GROUPED by neighbour pattern (see "Row grouping" below; the launch scatters through out_rows, results are
+// bit-identical), the builders emit one 27-bit liveness mask per tile, and all warp roles walk the same compacted block list
+// (chunk-major: the offsets of one 32-channel chunk back to back, so gathered pieces are re-read from L2).
 //
-//   warps 0-7   producers: warp w gathers rows [16w, 16w+16) of every step (cp.async 16 B, zero-fill for a missing
-//               neighbour); the stage's mbarrier is armed with cp.async.mbarrier.arrive.noinc, so it completes when the
-//               copies of all 256 lanes have landed and the producers never wait for their own data (the CUTLASS sm100
-//               cp.async mainloop synchronises cp.async -> UMMA the same way); afterwards the same warps run the epilogue (tcgen05.ld -> BN affine / residual / activation
-//               -> fp32 row and, optionally, the split row the next layer gathers from).
-//   warp 8      weight tiles: one cp.async.bulk per live (offset step, channel chunk); owns TMEM alloc and builds the
-//               step list.
-//   warp 9      MMA issuer: one thread, six tcgen05.mma.kind::f16 per step (M = 128, N = COUT, K = 16), tcgen05.commit
-//               releases the rings / publishes the accumulators.  A single in-order issuer sees every mbarrier phase,
-//               so the dynamic step list needs no phase-aliasing rules.
+//   warps 0-7   producers: warp w fills stage w (one whole 128-row x 128 B tile per block: cp.async 16 B per lane straight
+//               into the 128B-swizzled operand tile, zero-fill for a missing neighbour), waits for its own copies, fences
+//               them to the async proxy and arrives on the stage's mbarrier.
+//               Dense-grid mode (template flag TMA, s2d_conv_fwd_grid): one thread issues a 4-D TMA box per (block, tile)
+//               instead -- a regular BEV map needs no neighbour table, the padding is the TMA zero fill.
+//   warp 8      utility: block lists (double buffered), one cp.async.bulk per weight tile, L2 prefetch of table lines; owns
+//               the TMEM allocation.
+//   warps 9..   MMA issuers, one per tile of the group: six tcgen05.mma.kind::f16 per block (M = 128, N = COUT, K = 16),
+//               tcgen05.commit releases the rings / publishes the accumulators.
+//   last 8      epilogue warps (two per TMEM lane quarter) on the second accumulator buffer: tcgen05.ld -> BN affine /
+//               residual / ReLU / GELU -> fp32 row and split row, staged through shared memory for whole-row stores.
+//
+// What bounds it: shared-memory bandwidth -- per block the six SS-mode MMAs read the A tile 6 x 4 KB and the
+// weight slices 6 x COUT x 32 B while tile and weights are written into the same memory; neither two CTAs per SM nor TMA
+// instead of LDGSTS changed the time.
 #include <string.h>
 
 #include "grouping.cuh"
