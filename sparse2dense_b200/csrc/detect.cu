@@ -82,6 +82,7 @@ __global__ void __launch_bounds__(1024) topk_sort_kernel(const unsigned long lon
     __syncthreads();
     int tot = 0;
     for (int w = 0; w < 32; ++w) tot += s_red[w];
+    __syncthreads();                                     // nobody reuses shared memory before every thread has its total
     return tot;
   };
 
