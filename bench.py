@@ -457,13 +457,14 @@ def rooflines(wl, raw, steps, world, dev):
         if kind == "sparse":
             if (cin, cout, K) not in pairs_cache:
                 pairs_cache[(cin, cout, K)] = count_pairs_for(wl.path, wl.pts_dev, wl.offs, (cin, cout, K))
-            pairs = pairs_cache[(cin, cout, K)]
+            pairs, live_rows = pairs_cache[(cin, cout, K)]
             # compulsory bytes per launch: in rows + out rows + weights (+ residual on the launches that have one) + the
             # neighbour table once per indice_key (shared by 4 SubM launches); activations counted as fp32 (4 B / channel:
             # the split row is 2 x bf16 = 4 B as well)
             bytes_launch = (n_in * cin + n_out * cout + K * cin * cout + res_frac * n_out * cout) * 4 + n_out * K * 4 / 4
         else:
             pairs = n_out * K                                  # dense grid: every neighbour exists up to the border
+            live_rows = None
             bytes_launch = (n_in * cin + n_out * cout + K * cin * cout + res_frac * n_out * cout) * 4
         flops = 2.0 * pairs * cin * cout
         tfl = flops / (avg_ms * 1e-3) / 1e12
@@ -473,7 +474,8 @@ def rooflines(wl, raw, steps, world, dev):
         return dict(kernel=f"conv {cin}->{cout} K={K} ({kind}, {n_out} rows; precision {eff})", avg_launch_ms=avg_ms,
                     launches_per_step=g["n"] / steps, share_of_step=(g["ms"] / dev_ms) if world == 1 else None,
                     algorithmic_flops=flops, algorithmic_bytes=bytes_launch, pairs=pairs,
-                    executed_over_algorithmic_rows=n_out * K / max(pairs, 1), tflops=tfl, gbs=gbs)
+                    executed_over_algorithmic_rows=(live_rows if live_rows is not None else n_out * K) / max(pairs, 1),
+                    tflops=tfl, gbs=gbs)
 
     def pick(kind):
         ks = [k for k in groups if k[3] == kind]
@@ -510,7 +512,8 @@ def rooflines(wl, raw, steps, world, dev):
             d = describe(k, groups[k])
             table[f"{k[0]}->{k[1]} K={k[2]}"] = {"avg_launch_ms": round(d["avg_launch_ms"], 4), "launches_per_step": d["launches_per_step"],
                                                 "hbm_frac": round(d["gbs"] / pk["hbm"], 4), "tensor_frac": round(d["tflops"] / tf32_peak, 4),
-                                                "gbs": round(d["gbs"], 1), "tflops": round(d["tflops"], 1)}
+                                                "gbs": round(d["gbs"], 1), "tflops": round(d["tflops"], 1),
+                                                "executed_over_algorithmic_rows": round(d["executed_over_algorithmic_rows"], 2)}
         out["sparse_layers"] = table
     if de is not None:
         dense = tensor_obj(de[1], de[0])
@@ -528,7 +531,9 @@ def rooflines(wl, raw, steps, world, dev):
 
 
 def count_pairs_for(path, pts_dev, offs, shape_key):
-    """Rulebook pair count P of the sparse layer group (Cin,Cout,K) on this rank's batch (untimed)."""
+    """(rulebook pair count P, rows the tile kernel executes = 128 x live (tile, offset) pairs of the grouped rulebook) of the
+    sparse layer group (Cin,Cout,K) on this rank's batch (untimed)."""
+    import torch
     from sparse2dense_b200 import ops, spconv
     cin, cout, K = shape_key
     bb = path.backbone
@@ -539,25 +544,31 @@ def count_pairs_for(path, pts_dev, offs, shape_key):
     stages = [(x.indices, x.index(), None)]
     for sc in plan:
         stages.append((sc.coors, sc.index, sc))
+
+    def live(masks):
+        m = masks.to(torch.int64) & 0x7FFFFFF
+        bits = sum(((m >> b) & 1) for b in range(27))
+        return int(bits.sum().item()) * 128
+
     chans = [16, 32, 64, 128]
-    if K == 27 and cin == cout and cin in chans:                       # SubM group of stage s
-        s = chans.index(cin)
-        _, pairs = ops.rulebook_subm(stages[s][0], stages[s][1], 3, count_pairs=True)
-        return int(pairs.item())
     downs = {(16, 32): 1, (32, 64): 2, (64, 128): 3}
     if (cin, cout) in downs and K == 27:
         s = downs[(cin, cout)]
         m = [bb.conv2[0], bb.conv3[0], bb.conv4[0]][s - 1]
-        _, pairs = ops.rulebook_sparse(stages[s][0], stages[s - 1][1], m.kernel_size, m.stride, m.padding,
-                                       count_pairs=True)
-        return int(pairs.item())
+        _, pairs = ops.rulebook_sparse(stages[s][0], stages[s - 1][1], m.kernel_size, m.stride, m.padding, count_pairs=True)
+        masks = ops.rulebook_sparse_grouped(stages[s][0], stages[s - 1][1], m.stride, m.padding)[2] if spconv.GROUP_ROWS >= 2 \
+            else ops.table_tile_masks(ops.rulebook_sparse(stages[s][0], stages[s - 1][1], m.kernel_size, m.stride, m.padding),
+                                      stages[s][0].shape[0])
+        return int(pairs.item()), live(masks)
     if K == 3:
         m = bb.extra_conv[0]
-        _, pairs = ops.rulebook_sparse(stages[4][0], stages[3][1], m.kernel_size, m.stride, m.padding,
-                                       count_pairs=True)
-        return int(pairs.item())
-    _, pairs = ops.rulebook_subm(stages[0][0], stages[0][1], 3, count_pairs=True)
-    return int(pairs.item())
+        tbl, pairs = ops.rulebook_sparse(stages[4][0], stages[3][1], m.kernel_size, m.stride, m.padding, count_pairs=True)
+        return int(pairs.item()), live(ops.table_tile_masks(tbl, stages[4][0].shape[0]))
+    s = chans.index(cout) if (K == 27 and cout in chans and cin in (cout, 5)) else 0     # SubM group of stage s (5->16: stage 0)
+    tbl, pairs = ops.rulebook_subm(stages[s][0], stages[s][1], 3, count_pairs=True)
+    masks = ops.rulebook_subm_grouped(stages[s][0], stages[s][1])[2] if spconv.GROUP_ROWS >= 1 else \
+        ops.table_tile_masks(tbl, stages[s][0].shape[0])
+    return int(pairs.item()), live(masks)
 
 
 def run_gpu(args):
