@@ -71,19 +71,21 @@ __device__ __forceinline__ void sts32(uint32_t addr, int v) {
 // group: one weight tile and up to T gathered tiles (one per tile of the group that has a neighbour at that offset).
 // The eight gathered-tile stages form NB = 8 / T block slots; stage (slot, t) = slot * T + t always belongs to tile t, so
 // producer warp w = stage w and MMA warp t = tile t see every phase of "their" barriers whatever the masks skip.
-template <int COUT, int T_, int S_>
+template <int COUT, int T_, int S_, bool SWAP_ = false>
 struct B2Cfg {
   static constexpr int T = T_;
   static constexpr int S = S_;
+  static constexpr bool SWAP = SWAP_;                          // operands swapped: D[cout, rows of both tiles] (see the MMA warps)
+  static constexpr int MW = SWAP ? 2 : T;                      // MMA warps (swapped: two issuers that alternate blocks)
   static constexpr int CTAS_PER_SM = S == 4 ? 2 : 1;
   static constexpr int NB = S / T;                             // gathered-tile slots per tile (stage = slot * T + t)
   static constexpr int SB = S == 4 ? (COUT >= 64 ? 2 : 4) : (COUT >= 128 ? 3 : 4);   // weight-tile ring
   static constexpr int UTIL_WARP = S;
   static constexpr int MMA_WARP0 = S + 1;
   static constexpr int EPI_WARPS = 8;                          // two per TMEM lane quarter: they split the (tile, column chunk) items
-  static constexpr int WARPS = MMA_WARP0 + T + EPI_WARPS;
+  static constexpr int WARPS = MMA_WARP0 + MW + EPI_WARPS;
   static constexpr int THREADS = 32 * WARPS;
-  static constexpr int EPI_WARP0 = MMA_WARP0 + T;
+  static constexpr int EPI_WARP0 = MMA_WARP0 + MW;
   static constexpr int B_STAGE = COUT * 128;                   // COUT rows x [w1 (64 B) | w2 (64 B)]
   static constexpr int ACC_STRIDE = COUT < 32 ? 32 : COUT;
   static constexpr int ACC_BUF = T * ACC_STRIDE;               // one accumulator set (T tiles)
@@ -95,12 +97,13 @@ struct B2Cfg {
   static constexpr int BAR_BYTES = 512;
   static constexpr int SMEM_BYTES = S * kB2AStage + SB * B_STAGE + LIST_BYTES + EPI_BYTES + S * 1024 + BAR_BYTES + 1024;
   static_assert(T == 2 || T == 4, "tiles per group");
+  static_assert(!SWAP || (COUT == 128 && T == 2), "swapped operands: M = COUT = 128, N = 2 tiles x 128 rows");
   static_assert((S == 4 || S == 8) && NB >= 1 && (NB & (NB - 1)) == 0, "stage ring");
   static_assert(ACC_COLS * CTAS_PER_SM <= 512, "TMEM budget");
   static_assert(TMEM_COLS * CTAS_PER_SM <= 512, "TMEM budget");
   static_assert((SMEM_BYTES + 1024) * CTAS_PER_SM <= 227 * 1024, "shared memory budget");
   static_assert(COUT % 16 == 0 && COUT >= 16 && COUT <= 128, "UMMA N constraint for M = 128");
-  static_assert(2 * S + 2 * SB + 8 <= BAR_BYTES / 8 - 2, "barrier block");
+  static_assert(2 * S + 2 * SB + 10 <= BAR_BYTES / 8 - 2, "barrier block");
 };
 
 struct B2Args {
@@ -155,10 +158,11 @@ __device__ __forceinline__ void split_pair(float a, float b, uint32_t& hi, uint3
 // the per-slot barriers); the epilogue warps drain a group's accumulators from one TMEM buffer while the next group
 // is gathered and multiplied into the other.
 //   block entry = kk | live-tile nibble << 5 | chunk << 9
-template <int COUT, int T, int S, bool TMA>
-__global__ void __launch_bounds__(B2Cfg<COUT, T, S>::THREADS, B2Cfg<COUT, T, S>::CTAS_PER_SM)
+template <int COUT, int T, int S, bool TMA, bool SWAP>
+__global__ void __launch_bounds__(B2Cfg<COUT, T, S, SWAP>::THREADS, B2Cfg<COUT, T, S, SWAP>::CTAS_PER_SM)
 conv_bf2_kernel(const __grid_constant__ B2Args A, const __grid_constant__ CUtensorMap in_map) {
-  using Cfg = B2Cfg<COUT, T, S>;
+  using Cfg = B2Cfg<COUT, T, S, SWAP>;
+  constexpr int MW = Cfg::MW;
   constexpr int kB2Stages = S, kB2ProducerWarps = S, kB2UtilWarp = Cfg::UTIL_WARP, kB2MmaWarp0 = Cfg::MMA_WARP0;
   constexpr int B_STAGE = Cfg::B_STAGE, NB = Cfg::NB, SB = Cfg::SB;
   const int NCHUNK = A.nchunk, K = A.K, KS = A.ksteps, kps = A.kps, n_out = A.n_out;
@@ -181,7 +185,8 @@ conv_bf2_kernel(const __grid_constant__ B2Args A, const __grid_constant__ CUtens
   uint64_t* bar_list_empty = bar_list_full + 2;                  // [2]
   uint64_t* bar_acc_full = bar_list_empty + 2;                   // [2]
   uint64_t* bar_acc_empty = bar_acc_full + 2;                    // [2]
-  uint32_t* s_tmem = reinterpret_cast<uint32_t*>(bar_acc_empty + 2);
+  uint64_t* bar_turn = bar_acc_empty + 2;                        // [2]  swapped operands: issuer p may issue its next block
+  uint32_t* s_tmem = reinterpret_cast<uint32_t*>(bar_turn + 2);
   uint32_t* s_nblocks = s_tmem + 1;                              // [2]
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -194,13 +199,14 @@ conv_bf2_kernel(const __grid_constant__ B2Args A, const __grid_constant__ CUtens
     }
     for (int s = 0; s < SB; ++s) {
       mbar_init(smem_u32(bar_b_full + s), 1);                     // arrive.expect_tx of the loader
-      mbar_init(smem_u32(bar_b_empty + s), T);                    // every MMA warp: commit (or plain arrival if its tile is dead)
+      mbar_init(smem_u32(bar_b_empty + s), SWAP ? 1 : T);         // every MMA warp: commit (or plain arrival if its tile is dead)
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(smem_u32(bar_list_full + s), 1);                  // utility warp, after writing the list
-      mbar_init(smem_u32(bar_list_empty + s), (TMA ? 1 : kB2ProducerWarps) + T);   // producer(s) + MMA warps done reading it
-      mbar_init(smem_u32(bar_acc_full + s), T);                   // every MMA warp after its last MMA of the group
+      mbar_init(smem_u32(bar_list_empty + s), (TMA ? 1 : kB2ProducerWarps) + MW);  // producer(s) + MMA warps done reading it
+      mbar_init(smem_u32(bar_acc_full + s), MW);                  // every MMA warp after its last MMA of the group
       mbar_init(smem_u32(bar_acc_empty + s), Cfg::EPI_WARPS);     // the epilogue warps
+      mbar_init(smem_u32(bar_turn + s), 1);
     }
     fence_barrier_init();
   }
@@ -459,9 +465,120 @@ conv_bf2_kernel(const __grid_constant__ B2Args A, const __grid_constant__ CUtens
     // One issuing thread needs ~500-700 clk per step for six tcgen05.mma and a commit (measured), more than the gather;
     // with a warp per tile the T accumulators advance in parallel.  Warp-uniform control flow and values (the entry is
     // broadcast with a shuffle) keep descriptors and barrier addresses in uniform registers; one elected lane issues.
+    constexpr uint32_t desc_hi = 64u | (1u << 14) | (2u << 29);   // SBO = 1024 B, version 1, SWIZZLE_128B
+    if constexpr (SWAP) {
+      // ---- swapped operands (COUT = 128, T = 2): D[cout, row] = W^T x X^T, two warps issue ALTERNATE blocks ----
+      // Measured (tools/mma_probe.cu, tools/sync_probe.cu): SS-mode MMAs of M = 128, K = 16 run at their floor of N / 2 clk
+      // (64 clk at N = 128 even under shared-memory write traffic); the tensor pipe queues only ~1.5 MMAs behind the one
+      // executing, so every clock beyond ~170 that the issuing warp spends between two blocks (barrier waits, list entry,
+      // commits, and the ~140 clk before the uniform registers of an issued UTCHMMA may be rewritten) is a clock the pipe
+      // idles: with one issuer per tile the Cout = 128 kernels sat at 60-70 % tensor activity.  Here the WEIGHT tile is the
+      // M = 128 operand and the gathered tiles of both tiles of the group ONE N = 256 operand (stages (slot, 0) and (slot, 1)
+      // are adjacent: 256 rows x 128 B), a block is six 128 clk MMAs, and two warps take turns: while one issues block i, the
+      // other waits for the operands of block i + 1 and builds its descriptors, then only needs the `turn` hand-off (~80 clk).
+      // The turn barrier also fixes the order in which the MMAs reach the pipe, so sums are reproducible.  The accumulator is
+      // transposed (TMEM lane = output channel, column = row of the group); the epilogue transposes it back while staging.
+      const int p = warp - kB2MmaWarp0;                           // this warp issues the blocks with (gblk + ib) & 1 == p
+      constexpr uint32_t idesc2 = make_idesc_bf16(COUT, 2 * kBM), idesc1 = make_idesc_bf16(COUT, kBM);
+      const uint32_t a_lo0 = ((smem_u32(a_ring) >> 4) & 0x3FFF) | (1u << 16);
+      const uint32_t b_lo0 = ((smem_u32(b_ring) >> 4) & 0x3FFF) | (1u << 16);
+      const uint32_t bar_a_full0 = smem_u32(bar_a_full), bar_a_empty0 = smem_u32(bar_a_empty);
+      const uint32_t bar_b_full0 = smem_u32(bar_b_full), bar_b_empty0 = smem_u32(bar_b_empty);
+      const uint32_t bar_my_turn = smem_u32(bar_turn + p), bar_other_turn = smem_u32(bar_turn + (p ^ 1));
+      const bool leader = elect_one();
+      const uint64_t hi64 = (uint64_t)desc_hi << 32;
+      // six MMAs: (weight slice, activation slice) pairs, small terms first (same pairs as the unswapped issue below)
+      auto issue6 = [&](uint32_t d, uint32_t w_lo, uint32_t x_lo, uint32_t idesc, uint32_t acc) {
+        if (kps == 1) {
+          umma_bf16_ss(d, hi64 | (w_lo + 0u), hi64 | (x_lo + 4u), idesc, acc);
+          umma_bf16_ss(d, hi64 | (w_lo + 2u), hi64 | (x_lo + 6u), idesc, 1u);
+          umma_bf16_ss(d, hi64 | (w_lo + 4u), hi64 | (x_lo + 0u), idesc, 1u);
+          umma_bf16_ss(d, hi64 | (w_lo + 6u), hi64 | (x_lo + 2u), idesc, 1u);
+          umma_bf16_ss(d, hi64 | (w_lo + 0u), hi64 | (x_lo + 0u), idesc, 1u);
+          umma_bf16_ss(d, hi64 | (w_lo + 2u), hi64 | (x_lo + 2u), idesc, 1u);
+        } else {
+          umma_bf16_ss(d, hi64 | (w_lo + 0u), hi64 | (x_lo + 2u), idesc, acc);
+          umma_bf16_ss(d, hi64 | (w_lo + 2u), hi64 | (x_lo + 0u), idesc, 1u);
+          umma_bf16_ss(d, hi64 | (w_lo + 4u), hi64 | (x_lo + 6u), idesc, 1u);
+          umma_bf16_ss(d, hi64 | (w_lo + 6u), hi64 | (x_lo + 4u), idesc, 1u);
+          umma_bf16_ss(d, hi64 | (w_lo + 0u), hi64 | (x_lo + 0u), idesc, 1u);
+          umma_bf16_ss(d, hi64 | (w_lo + 4u), hi64 | (x_lo + 4u), idesc, 1u);
+        }
+      };
+      uint32_t a_ph = 0;                                          // phase bit per stage (this warp's slots only)
+      uint32_t turn = 0;                                          // blocks this warp has issued
+      int gblk = 0, j = 0;
+      long long mw_a = 0, mw_b = 0, mw_acc = 0, mw_list = 0, m_steps = 0;
+      const long long m_t0 = prof ? clock64() : 0;
+      for (int g = (int)blockIdx.x; g < n_groups; g += gstep, ++j) {
+        const int buf = j & 1;
+        long long c0 = prof ? clock64() : 0;
+        mbar_wait(smem_u32(bar_list_full + buf), (uint32_t)(j >> 1) & 1u);
+        if (prof) { const long long c1 = clock64(); mw_list += c1 - c0; c0 = c1; }
+        mbar_wait(smem_u32(bar_acc_empty + buf), ((uint32_t)(j >> 1) & 1u) ^ 1u);
+        if (prof) mw_acc += clock64() - c0;
+        tc_fence_after();
+        const int nblocks = __shfl_sync(0xffffffffu, (int)s_nblocks[buf], 0);
+        const uint32_t list0 = lists0 + (uint32_t)buf * (kB2ListCap * 2);
+        const uint32_t d0 = tmem_base + (uint32_t)(buf * Cfg::ACC_BUF);
+        uint32_t accm = 0;                                        // bit t: tile t's columns hold a partial sum (both warps track it)
+        bool issued = false;
+        uint32_t e_next = lds_u16(list0);
+#pragma unroll 1
+        for (int ib = 0; ib < nblocks; ++ib) {
+          const uint32_t e = __shfl_sync(0xffffffffu, e_next, 0);
+          e_next = lds_u16(list0 + 2u * (uint32_t)min(ib + 1, nblocks - 1));
+          const int gb = gblk + ib;
+          const uint32_t nib = (e >> 5) & 3u;
+          if ((gb & 1) == p) {
+            const int slot = gb & (NB - 1), bslot = gb % SB;
+            c0 = prof ? clock64() : 0;
+            mbar_wait(bar_b_full0 + 8 * bslot, (uint32_t)(gb / SB) & 1u);
+            if (prof) { const long long c1 = clock64(); mw_b += c1 - c0; c0 = c1; }
+            const int stage0 = slot * 2;
+            if (nib & 1u) { mbar_wait(bar_a_full0 + 8 * stage0, (a_ph >> stage0) & 1u); a_ph ^= 1u << stage0; }
+            if (nib & 2u) { mbar_wait(bar_a_full0 + 8 * (stage0 + 1), (a_ph >> (stage0 + 1)) & 1u); a_ph ^= 2u << stage0; }
+            if (prof) { mw_a += clock64() - c0; ++m_steps; }
+            const uint32_t x_lo = a_lo0 + (uint32_t)stage0 * (kB2AStage >> 4);
+            const uint32_t w_lo = b_lo0 + (uint32_t)bslot * (B_STAGE >> 4);
+            mbar_wait(bar_my_turn, (turn & 1u) ^ (uint32_t)(p ^ 1));     // the other warp has issued the block before this one
+            ++turn;
+            tc_fence_after();
+            if (leader) {
+              if (!(A.dbg & 2)) {
+                if (nib == 3u && (accm == 0u || accm == 3u)) {
+                  issue6(d0, w_lo, x_lo, idesc2, accm ? 1u : 0u);
+                } else {
+                  if (nib & 1u) issue6(d0, w_lo, x_lo, idesc1, accm & 1u);
+                  if (nib & 2u) issue6(d0 + (uint32_t)kBM, w_lo, x_lo + (uint32_t)(kB2AStage >> 4), idesc1, (accm >> 1) & 1u);
+                }
+              }
+              mbar_arrive(bar_other_turn);
+              if (nib & 1u) umma_commit(bar_a_empty0 + 8 * stage0);
+              if (nib & 2u) umma_commit(bar_a_empty0 + 8 * (stage0 + 1));
+              if (nib) umma_commit(bar_b_empty0 + 8 * bslot);
+              else mbar_arrive(bar_b_empty0 + 8 * bslot);
+            }
+            issued = issued || nib != 0u;
+            __syncwarp();
+          }
+          accm |= nib;
+        }
+        gblk += nblocks;
+        if (leader) {
+          if (issued) umma_commit(smem_u32(bar_acc_full + buf));    // this warp's MMAs of the group are complete
+          else mbar_arrive(smem_u32(bar_acc_full + buf));
+          mbar_arrive(smem_u32(bar_list_empty + buf));
+        }
+        __syncwarp();
+      }
+      if (prof && p == 0 && lane == 0) {
+        long long* po = A.prof + (size_t)blockIdx.x * 16;
+        po[5] = clock64() - m_t0; po[6] = mw_a; po[7] = mw_b; po[8] = mw_acc; po[9] = mw_list; po[10] = m_steps;
+      }
+    } else {
     const int t = warp - kB2MmaWarp0;
     constexpr uint32_t idesc = make_idesc_bf16(kBM, COUT);
-    constexpr uint32_t desc_hi = 64u | (1u << 14) | (2u << 29);   // SBO = 1024 B, version 1, SWIZZLE_128B
     const uint32_t a_lo0 = ((smem_u32(a_ring) >> 4) & 0x3FFF) | (1u << 16);
     const uint32_t b_lo0 = ((smem_u32(b_ring) >> 4) & 0x3FFF) | (1u << 16);
     const uint32_t bar_a_full0 = smem_u32(bar_a_full), bar_a_empty0 = smem_u32(bar_a_empty);
@@ -548,6 +665,7 @@ conv_bf2_kernel(const __grid_constant__ B2Args A, const __grid_constant__ CUtens
       long long* po = A.prof + (size_t)blockIdx.x * 16;
       po[5] = clock64() - m_t0; po[6] = mw_a; po[7] = mw_b; po[8] = mw_acc; po[9] = mw_list; po[10] = m_steps;
     }
+    }
   } else {
     // ===================== epilogue warps: TMEM -> staged rows -> coalesced BN / residual / activation / stores ==========
     // A warp reads the accumulator rows of its TMEM lane quarter (lane = row), stages 32 (16) channels per row in shared
@@ -574,7 +692,59 @@ conv_bf2_kernel(const __grid_constant__ B2Args A, const __grid_constant__ CUtens
       const int row_end = min(n_out, tile0 + T * kBM);
       mbar_wait(smem_u32(bar_acc_full + buf), (uint32_t)(j >> 1) & 1u);
       tc_fence_after();
+      // staged 32 rows x EPC channels of this warp -> affine / residual / activation -> whole-row stores.
+      //   rbase: first of the 32 rows inside the group, c0: first channel of the staged piece, orow_l: lane r's output row
+      auto store_staged = [&](int rbase, int c0, int orow_l) {
+        float4 sc = make_float4(1.f, 1.f, 1.f, 1.f), sh = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (scale) sc = __ldg(reinterpret_cast<const float4*>(scale + c0) + pp);
+        if (shift) sh = __ldg(reinterpret_cast<const float4*>(shift + c0) + pp);
+#pragma unroll
+        for (int jj = 0; jj < PPR; ++jj) {
+          const int r = pr + RPI * jj;
+          const int orow = __shfl_sync(0xffffffffu, orow_l, r);
+          const int row = tile0 + rbase + r;
+          float4 v = lds128(stg + (uint32_t)r * kB2EpiRow + 16u * pp);
+          if (row < row_end && orow >= 0 && !(A.dbg & 8)) {
+            v.x = v.x * sc.x + sh.x; v.y = v.y * sc.y + sh.y; v.z = v.z * sc.z + sh.z; v.w = v.w * sc.w + sh.w;
+            float4 rr = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (A.residual) rr = __ldg(reinterpret_cast<const float4*>(A.residual + (size_t)orow * A.res_ld + cblk + c0) + pp);
+            if (!res_after) { v.x += rr.x; v.y += rr.y; v.z += rr.z; v.w += rr.w; }
+            v.x = b2_act(v.x, act); v.y = b2_act(v.y, act); v.z = b2_act(v.z, act); v.w = b2_act(v.w, act);
+            if (res_after) { v.x += rr.x; v.y += rr.y; v.z += rr.z; v.w += rr.w; }
+            if (A.out) reinterpret_cast<float4*>(A.out + (size_t)orow * A.out_ld + cblk + c0)[pp] = v;
+            if (A.out_split) {
+              // split row: per chunk of EPC channels [EPC/2 words hi | EPC/2 words lo]; this lane owns channels 4pp..4pp+3
+              uint32_t h0, l0, h1, l1;
+              split_pair(v.x, v.y, h0, l0);
+              split_pair(v.z, v.w, h1, l1);
+              uint32_t* dst = A.out_split + (size_t)orow * A.split_ld + cblk + c0;
+              *reinterpret_cast<uint2*>(dst + 2 * pp) = make_uint2(h0, h1);
+              *reinterpret_cast<uint2*>(dst + EPC / 2 + 2 * pp) = make_uint2(l0, l1);
+            }
+          }
+        }
+      };
       int item = 0;
+      if constexpr (SWAP) {
+        // transposed accumulator: this warp's TMEM lane quarter = output channels 32 g4 .. 32 g4 + 31, a column = a row of the
+        // group.  An item = 32 rows: lane c reads its channel of 32 consecutive rows and writes them down a staging column.
+        const int c0 = g4 * 32;
+#pragma unroll 1
+        for (int rb = 0; rb < Tr * kBM; rb += 32) {
+          if (A.dbg & 128) break;
+          if ((item++ & 1) != half) continue;
+          if (tile0 + rb >= row_end) break;
+          const int row_l = tile0 + rb + lane;
+          const int orow_l = (row_l < row_end && A.out_rows) ? __ldg(A.out_rows + row_l) : row_l;
+          uint32_t acc[32];
+          tmem_ld<32>(tmem_base + ((uint32_t)(g4 * 32) << 16) + (uint32_t)(buf * Cfg::ACC_BUF + rb), acc);
+#pragma unroll
+          for (int q = 0; q < 32; ++q) sts32(stg + (uint32_t)q * kB2EpiRow + 4u * lane, (int)acc[q]);
+          __syncwarp();
+          store_staged(rb, c0, orow_l);
+          __syncwarp();
+        }
+      } else {
 #pragma unroll 1
       for (int t = 0; t < Tr; ++t) {
         if (A.dbg & 128) break;
@@ -590,36 +760,10 @@ conv_bf2_kernel(const __grid_constant__ B2Args A, const __grid_constant__ CUtens
             sts128(stg + (uint32_t)lane * kB2EpiRow + 16u * q, __uint_as_float(acc[4 * q]), __uint_as_float(acc[4 * q + 1]),
                    __uint_as_float(acc[4 * q + 2]), __uint_as_float(acc[4 * q + 3]));
           __syncwarp();
-          float4 sc = make_float4(1.f, 1.f, 1.f, 1.f), sh = make_float4(0.f, 0.f, 0.f, 0.f);
-          if (scale) sc = __ldg(reinterpret_cast<const float4*>(scale + c0) + pp);
-          if (shift) sh = __ldg(reinterpret_cast<const float4*>(shift + c0) + pp);
-#pragma unroll
-          for (int jj = 0; jj < PPR; ++jj) {
-            const int r = pr + RPI * jj;
-            const int orow = __shfl_sync(0xffffffffu, orow_l, r);
-            const int row = tile0 + t * kBM + g4 * 32 + r;
-            float4 v = lds128(stg + (uint32_t)r * kB2EpiRow + 16u * pp);
-            if (row < row_end && orow >= 0 && !(A.dbg & 8)) {
-              v.x = v.x * sc.x + sh.x; v.y = v.y * sc.y + sh.y; v.z = v.z * sc.z + sh.z; v.w = v.w * sc.w + sh.w;
-              float4 rr = make_float4(0.f, 0.f, 0.f, 0.f);
-              if (A.residual) rr = __ldg(reinterpret_cast<const float4*>(A.residual + (size_t)orow * A.res_ld + cblk + c0) + pp);
-              if (!res_after) { v.x += rr.x; v.y += rr.y; v.z += rr.z; v.w += rr.w; }
-              v.x = b2_act(v.x, act); v.y = b2_act(v.y, act); v.z = b2_act(v.z, act); v.w = b2_act(v.w, act);
-              if (res_after) { v.x += rr.x; v.y += rr.y; v.z += rr.z; v.w += rr.w; }
-              if (A.out) reinterpret_cast<float4*>(A.out + (size_t)orow * A.out_ld + cblk + c0)[pp] = v;
-              if (A.out_split) {
-                // split row: per chunk of EPC channels [EPC/2 words hi | EPC/2 words lo]; this lane owns channels 4pp..4pp+3
-                uint32_t h0, l0, h1, l1;
-                split_pair(v.x, v.y, h0, l0);
-                split_pair(v.z, v.w, h1, l1);
-                uint32_t* dst = A.out_split + (size_t)orow * A.split_ld + cblk + c0;
-                *reinterpret_cast<uint2*>(dst + 2 * pp) = make_uint2(h0, h1);
-                *reinterpret_cast<uint2*>(dst + EPC / 2 + 2 * pp) = make_uint2(l0, l1);
-              }
-            }
-          }
+          store_staged(t * kBM + g4 * 32, c0, orow_l);
           __syncwarp();                                             // staged rows are consumed before the next chunk lands
         }
+      }
       }
       tc_fence_before();
       __syncwarp();
@@ -768,12 +912,12 @@ static int b2_cout_block(int Cout) {
 }
 bool bf2_supported(int Cin, int Cout) { return (Cin == 16 || (Cin >= 32 && Cin % 32 == 0)) && b2_cout_block(Cout) != 0; }
 
-template <int COUT, int T, int S, bool TMA>
+template <int COUT, int T, int S, bool TMA, bool SWAP = false>
 static int launch_b2(const B2Args& a, const CUtensorMap& map, int Cout, cudaStream_t st) {
-  using Cfg = B2Cfg<COUT, T, S>;
+  using Cfg = B2Cfg<COUT, T, S, SWAP>;
   static bool configured = false;
   if (!configured) {
-    S2D_CUDA(cudaFuncSetAttribute(conv_bf2_kernel<COUT, T, S, TMA>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    S2D_CUDA(cudaFuncSetAttribute(conv_bf2_kernel<COUT, T, S, TMA, SWAP>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                   Cfg::SMEM_BYTES));
     configured = true;
   }
@@ -789,7 +933,7 @@ static int launch_b2(const B2Args& a, const CUtensorMap& map, int Cout, cudaStre
   if (gx < 1) gx = 1;
   if (gx > b.n_groups) gx = b.n_groups;
   const dim3 grid(gx, gy);
-  conv_bf2_kernel<COUT, T, S, TMA><<<grid, Cfg::THREADS, Cfg::SMEM_BYTES, st>>>(b, map);
+  conv_bf2_kernel<COUT, T, S, TMA, SWAP><<<grid, Cfg::THREADS, Cfg::SMEM_BYTES, st>>>(b, map);
   S2D_LAUNCH_CHECK();
   count_launches(1);
   return S2D_OK;
@@ -871,7 +1015,7 @@ static int conv_fwd_bf2_impl(const s2d_conv_params& p, int grid_b, int grid_h, i
     S2D_REQUIRE(p.n_out == grid_b * a.grid_tiles_x * a.grid_tiles_y * kBM, "s2d_conv_fwd_grid: n_out must be tiles x 128");
     const int rc = make_grid_map(p.in_split, p.in_split_ld, p.Cin, grid_b, grid_h, grid_w, &map);
     if (rc != S2D_OK) return rc;
-    if (cb == 128) return launch_b2<128, 2, 8, true>(a, map, p.Cout, st);
+    if (cb == 128) return g_b2_variant == 2 ? launch_b2<128, 2, 8, true>(a, map, p.Cout, st) : launch_b2<128, 2, 8, true, true>(a, map, p.Cout, st);
     if (cb == 64) return launch_b2<64, 4, 8, true>(a, map, p.Cout, st);
     if (cb == 32) return launch_b2<32, 4, 8, true>(a, map, p.Cout, st);
     return launch_b2<16, 4, 8, true>(a, map, p.Cout, st);
@@ -879,7 +1023,8 @@ static int conv_fwd_bf2_impl(const s2d_conv_params& p, int grid_b, int grid_h, i
   const int v = g_b2_variant;
   // variant 0: production choice; 1: T = 2.  (Two CTAs per SM with half the stage ring each, S = 4, measured no faster: the
   // kernel is bound by shared-memory bandwidth and the tensor pipe, which both CTAs share, not by barrier latency.)
-  if (cb == 128) return launch_b2<128, 2, 8, false>(a, map, p.Cout, st);
+  // 128 output channels: swapped operands (variant 2: the unswapped kernel, for A/B timing)
+  if (cb == 128) return v == 2 ? launch_b2<128, 2, 8, false>(a, map, p.Cout, st) : launch_b2<128, 2, 8, false, true>(a, map, p.Cout, st);
   if (cb == 64) return v == 1 ? launch_b2<64, 2, 8, false>(a, map, p.Cout, st) : launch_b2<64, 4, 8, false>(a, map, p.Cout, st);
   if (cb == 32) return v == 1 ? launch_b2<32, 2, 8, false>(a, map, p.Cout, st) : launch_b2<32, 4, 8, false>(a, map, p.Cout, st);
   return v == 1 ? launch_b2<16, 2, 8, false>(a, map, p.Cout, st) : launch_b2<16, 4, 8, false>(a, map, p.Cout, st);

@@ -93,25 +93,30 @@ def main():
         if args.prof:
             lib = ctypes.CDLL(_lib.LIB_PATH)
             lib.s2d_debug_bf2_prof.argtypes = [ctypes.c_void_p]
-            for fl in (0, 227):
+            for pv, fl in [(v, f) for v in [int(s) for s in args.variants.split(",")] for f in (0, 227)]:
                 buf = torch.zeros(148 * 16, dtype=torch.int64, device="cuda")
+                setv(pv)
                 setf(fl)
                 lib.s2d_debug_bf2_prof(buf.data_ptr())
                 ops.spconv_fwd(feats, w, tbl, n, precision=ops.PRECISION_BF16X2, packed=pk, out=out)
                 torch.cuda.synchronize()
                 lib.s2d_debug_bf2_prof(None)
                 setf(0)
+                setv(0)
                 m = buf.view(148, 16).double().mean(0).tolist()
-                print(f"   prof {c:3d} flags {fl}: producer0 total {m[0]:.0f} clk: wait_empty {m[1]:.0f} wait_data {m[2]:.0f} wait_list {m[3]:.0f} over {m[4]:.0f} steps "
+                print(f"   prof {c:3d} variant {pv} flags {fl}: producer0 total {m[0]:.0f} clk: wait_empty {m[1]:.0f} wait_data {m[2]:.0f} wait_list {m[3]:.0f} over {m[4]:.0f} steps "
                       f"| mma total {m[5]:.0f}: wait_a {m[6]:.0f} wait_b {m[7]:.0f} wait_acc {m[8]:.0f} wait_list {m[9]:.0f} over {m[10]:.0f} steps", flush=True)
         if args.ablate:
-            line = f"   ablate {c:3d}:"
-            for fl in [int(v) for v in args.ablate.split(",")]:
-                setf(fl)
-                t = timeit(lambda: ops.spconv_fwd(feats, w, tbl, n, precision=ops.PRECISION_BF16X2, packed=pk, out=out), flush, args.reps)
-                line += f" f{fl}={t:.3f}"
-            setf(0)
-            print(line, flush=True)
+            for av in [int(s) for s in args.variants.split(",")]:
+                setv(av)
+                line = f"   ablate {c:3d} variant {av}:"
+                for fl in [int(v) for v in args.ablate.split(",")]:
+                    setf(fl)
+                    t = timeit(lambda: ops.spconv_fwd(feats, w, tbl, n, precision=ops.PRECISION_BF16X2, packed=pk, out=out), flush, args.reps)
+                    line += f" f{fl}={t:.3f}"
+                setf(0)
+                setv(0)
+                print(line, flush=True)
     if args.dense:
         from sparse2dense_b200 import dense
         B = args.batch
