@@ -38,6 +38,8 @@
 // instead of LDGSTS changed the time.
 #include <string.h>
 
+#include <atomic>
+
 #include "grouping.cuh"
 #include "tc_ptx.cuh"
 
@@ -122,6 +124,8 @@ struct B2Args {
   // dense-grid (TMA) mode: the input is a regular [B, H, W] map, a tile is kGridTH x kGridTW pixels, the gathered tile of a
   // kernel offset is ONE 4-D tensor-map box (zero fill outside the map = the convolution's padding)
   int grid_tiles_x, grid_tiles_y, grid_kw, grid_pad;
+  int g4;                // gather through TMA (tile::gather4, four 128 B rows per instruction) instead of cp.async; kps == 1 only
+  unsigned int* sched;   // dynamic group scheduler: [gridDim.y] next-group counters + CTA exit counter at [15]; null = static
   long long* prof;   // optional [gridDim.x][16] cycle counters (tools/microbench_bf2.py --prof), null in production
   int dbg;   // ablation switches (tools/microbench_bf2.py): 1 no gather, 2 no MMA, 4 no weight copies, 8 no stores, 16 all rows
              // missing, 64 no index loads, 128 no epilogue
@@ -188,6 +192,7 @@ conv_bf2_kernel(const __grid_constant__ B2Args A, const __grid_constant__ CUtens
   uint64_t* bar_turn = bar_acc_empty + 2;                        // [2]  swapped operands: issuer p may issue its next block
   uint32_t* s_tmem = reinterpret_cast<uint32_t*>(bar_turn + 2);
   uint32_t* s_nblocks = s_tmem + 1;                              // [2]
+  volatile int* s_group = reinterpret_cast<volatile int*>(s_nblocks + 2);   // [2] tile group of the list buffer, -1 = no more work
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   if ((int)blockIdx.x >= n_groups) return;
@@ -203,7 +208,7 @@ conv_bf2_kernel(const __grid_constant__ B2Args A, const __grid_constant__ CUtens
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(smem_u32(bar_list_full + s), 1);                  // utility warp, after writing the list
-      mbar_init(smem_u32(bar_list_empty + s), (TMA ? 1 : kB2ProducerWarps) + MW);  // producer(s) + MMA warps done reading it
+      mbar_init(smem_u32(bar_list_empty + s), (TMA ? 1 : kB2ProducerWarps) + MW + Cfg::EPI_WARPS);   // every reader of the list / group id
       mbar_init(smem_u32(bar_acc_full + s), MW);                  // every MMA warp after its last MMA of the group
       mbar_init(smem_u32(bar_acc_empty + s), Cfg::EPI_WARPS);     // the epilogue warps
       mbar_init(smem_u32(bar_turn + s), 1);
@@ -227,9 +232,11 @@ conv_bf2_kernel(const __grid_constant__ B2Args A, const __grid_constant__ CUtens
       const int tiles_img = A.grid_tiles_x * A.grid_tiles_y;
       int gblk = 0, j = 0;
 #pragma unroll 1
-      for (int g = (int)blockIdx.x; g < n_groups; g += gstep, ++j) {
+      for (;; ++j) {
         const int buf = j & 1;
         mbar_wait(smem_u32(bar_list_full + buf), (uint32_t)(j >> 1) & 1u);
+        const int g = s_group[buf];
+        if (g < 0) break;
         const int nblocks = (int)s_nblocks[buf];
         const uint32_t list0 = lists0 + (uint32_t)buf * (kB2ListCap * 2);
         int bx[T], by[T], bb[T];
@@ -287,11 +294,13 @@ conv_bf2_kernel(const __grid_constant__ B2Args A, const __grid_constant__ CUtens
     long long pw_empty = 0, pw_data = 0, pw_list = 0, p_steps = 0;
     const long long p_t0 = prof ? clock64() : 0;
 #pragma unroll 1
-    for (int g = (int)blockIdx.x; g < n_groups; g += gstep, ++j) {
+    for (;; ++j) {
       const int buf = j & 1;
       long long c0 = prof ? clock64() : 0;
       mbar_wait(smem_u32(bar_list_full + buf), (uint32_t)(j >> 1) & 1u);
       if (prof) pw_list += clock64() - c0;
+      const int g = s_group[buf];
+      if (g < 0) break;
       const int nblocks = (int)s_nblocks[buf];
       const uint32_t list0 = lists0 + (uint32_t)buf * (kB2ListCap * 2);
       const int tile0 = (g * T + my_t) * kBM;                // first row of this warp's tile
@@ -319,7 +328,7 @@ conv_bf2_kernel(const __grid_constant__ B2Args A, const __grid_constant__ CUtens
 #pragma unroll 1
       for (; ib < nblocks; ib += NB) {
         const bool live = (e >> (5 + my_t)) & 1u;
-        if (live) {
+        if (live && !A.g4) {
           // indices -> scratch, transposed so that the copies of row residue o read four consecutive r with one LDS.128
           sts32(scr + 4u * lane, qa.x); sts32(scr + 128u + 4u * lane, qa.y);
           sts32(scr + 256u + 4u * lane, qa.z); sts32(scr + 384u + 4u * lane, qa.w);
@@ -338,7 +347,18 @@ conv_bf2_kernel(const __grid_constant__ B2Args A, const __grid_constant__ CUtens
           if (kps == 2) qb_n = load_idx(e_n, 1);
         }
         __syncwarp();
-        if (live) {
+        if (live && A.g4) {
+          // TMA gather: lane l moves rows 4l .. 4l + 3 of the tile (its qa) with ONE gather4; a negative row is zero filled;
+          // the stage's barrier counts the bytes, so the warp neither waits for the data nor fences it
+          c0 = prof ? clock64() : 0;
+          mbar_wait(bar_empty, phase);
+          if (prof) { pw_empty += clock64() - c0; ++p_steps; }
+          phase ^= 1;
+          if (lane == 0) mbar_arrive_expect_tx(bar_full, (A.dbg & 1) ? 0u : (uint32_t)kB2AStage);
+          __syncwarp();
+          if (!(A.dbg & 1))
+            tma_gather4(a_stage + (uint32_t)lane * 512u, &in_map, (int)(e >> 9) * 32, qa.x, qa.y, qa.z, qa.w, bar_full);
+        } else if (live) {
           c0 = prof ? clock64() : 0;
           mbar_wait(bar_empty, phase);                         // the MMAs that read the stage's previous tile are done
           if (prof) { pw_empty += clock64() - c0; ++p_steps; }
@@ -378,9 +398,25 @@ conv_bf2_kernel(const __grid_constant__ B2Args A, const __grid_constant__ CUtens
     // ===================== utility warp: block lists, weight tiles, index prefetch =====================
     // Block list of a group: lane = offset step kk; entries ordered (kk, chunk); offsets at which no tile of the group has
     // a neighbour are skipped.  entry = kk | live-tile nibble << 5 | chunk << 9
-    auto build_list = [&](int g, int jj) {
+    // Group of list jj: static (CTA b takes b, b + grid, ...) or, with a scheduler, the next group nobody has taken -- the
+    // grouped rulebooks order their rows by DEscending number of live offset triples (grouping.cuh), so the groups come
+    // heaviest first and the CTAs finish within one light group of each other (a 27-offset group of 128 channels is up to
+    // 108 blocks = 55 us, a sixth of the whole launch: with the static round robin the slowest CTA set the time).
+    auto build_list = [&](int jj) {
       const int buf = jj & 1;
       mbar_wait(smem_u32(bar_list_empty + buf), ((uint32_t)(jj >> 1) & 1u) ^ 1u);
+      int g = (int)blockIdx.x + jj * gstep;
+      if (A.sched) {
+        if (lane == 0) g = (int)atomicAdd(A.sched + blockIdx.y, 1u);
+        g = __shfl_sync(0xffffffffu, g, 0);
+      }
+      if (g >= n_groups) {
+        if (lane == 0) { s_group[buf] = -1; s_nblocks[buf] = 0; }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(smem_u32(bar_list_full + buf));
+        return;
+      }
+      if (lane == 0) s_group[buf] = g;
       const int tile_first = g * T;
       const int Tr = min(T, A.n_tiles - tile_first);
       uint16_t* blocks = reinterpret_cast<uint16_t*>(lists) + buf * kB2ListCap;
@@ -422,11 +458,13 @@ conv_bf2_kernel(const __grid_constant__ B2Args A, const __grid_constant__ CUtens
     const int tbl_stride = A.tbl_stride;
     int gblk = 0;
     int j = 0;
-    build_list((int)blockIdx.x, 0);
+    build_list(0);
 #pragma unroll 1
-    for (int g = (int)blockIdx.x; g < n_groups; g += gstep, ++j) {
-      if (g + gstep < n_groups) build_list(g + gstep, j + 1);
+    for (;; ++j) {
       const int buf = j & 1;
+      const int g = s_group[buf];
+      if (g < 0) break;
+      build_list(j + 1);
       const int nblocks = (int)s_nblocks[buf];
       const uint32_t list0 = lists0 + (uint32_t)buf * (kB2ListCap * 2);
       const int row_end = min(n_out, (g + 1) * T * kBM);
@@ -510,11 +548,12 @@ conv_bf2_kernel(const __grid_constant__ B2Args A, const __grid_constant__ CUtens
       int gblk = 0, j = 0;
       long long mw_a = 0, mw_b = 0, mw_acc = 0, mw_list = 0, m_steps = 0;
       const long long m_t0 = prof ? clock64() : 0;
-      for (int g = (int)blockIdx.x; g < n_groups; g += gstep, ++j) {
+      for (;; ++j) {
         const int buf = j & 1;
         long long c0 = prof ? clock64() : 0;
         mbar_wait(smem_u32(bar_list_full + buf), (uint32_t)(j >> 1) & 1u);
         if (prof) { const long long c1 = clock64(); mw_list += c1 - c0; c0 = c1; }
+        if (s_group[buf] < 0) break;
         mbar_wait(smem_u32(bar_acc_empty + buf), ((uint32_t)(j >> 1) & 1u) ^ 1u);
         if (prof) mw_acc += clock64() - c0;
         tc_fence_after();
@@ -594,11 +633,12 @@ conv_bf2_kernel(const __grid_constant__ B2Args A, const __grid_constant__ CUtens
     int j = 0;
     long long mw_a = 0, mw_b = 0, mw_acc = 0, mw_list = 0, m_steps = 0;
     const long long m_t0 = prof ? clock64() : 0;
-    for (int g = (int)blockIdx.x; g < n_groups; g += gstep, ++j) {
+    for (;; ++j) {
       const int buf = j & 1;
       long long c0 = prof ? clock64() : 0;
       mbar_wait(smem_u32(bar_list_full + buf), (uint32_t)(j >> 1) & 1u);
       if (prof) { const long long c1 = clock64(); mw_list += c1 - c0; c0 = c1; }
+      if (s_group[buf] < 0) break;
       mbar_wait(smem_u32(bar_acc_empty + buf), ((uint32_t)(j >> 1) & 1u) ^ 1u);   // the epilogue has drained this accumulator set
       if (prof) mw_acc += clock64() - c0;
       tc_fence_after();
@@ -684,8 +724,13 @@ conv_bf2_kernel(const __grid_constant__ B2Args A, const __grid_constant__ CUtens
     const int pr = lane / PPR, pp = lane % PPR;
     int j = 0;
 #pragma unroll 1
-    for (int g = (int)blockIdx.x; g < n_groups; g += gstep, ++j) {
+    for (;; ++j) {
       const int buf = j & 1;
+      mbar_wait(smem_u32(bar_list_full + buf), (uint32_t)(j >> 1) & 1u);
+      const int g = s_group[buf];
+      __syncwarp();
+      if (lane == 0) mbar_arrive(smem_u32(bar_list_empty + buf));   // the group id has been read (the list itself is not used here)
+      if (g < 0) break;
       const int tile_first = g * T;
       const int Tr = min(T, A.n_tiles - tile_first);
       const int tile0 = tile_first * kBM;
@@ -774,6 +819,11 @@ conv_bf2_kernel(const __grid_constant__ B2Args A, const __grid_constant__ CUtens
   tc_fence_before();
   __syncthreads();
   if (warp == kB2UtilWarp) tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
+  if (A.sched && tid == 0) {                                     // the last CTA to leave rearms the scheduler slot
+    __threadfence();
+    if (atomicAdd(A.sched + 15, 1u) == gridDim.x * gridDim.y - 1u)
+      for (int i = 0; i < 16; ++i) A.sched[i] = 0u;
+  }
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -903,6 +953,11 @@ __global__ void __launch_bounds__(128) group_permute_table_kernel(const int* __r
   if (threadIdx.x == 0) masks[blockIdx.x] = (int)s_mask;
 }
 
+// dynamic group scheduler slots: [next group per blockIdx.y (<= 8) ... | CTAs that have left at [15]]; zero at load, rearmed
+// by the last CTA of the launch that used the slot; consecutive launches rotate over the slots so that launches running
+// concurrently on different streams never share one
+constexpr int kB2SchedSlots = 256;
+__device__ unsigned int g_b2_sched[kB2SchedSlots][16];
 static int g_b2_variant = 0;
 static int g_b2_dbg = 0;
 static long long* g_b2_prof = nullptr;
@@ -933,6 +988,13 @@ static int launch_b2(const B2Args& a, const CUtensorMap& map, int Cout, cudaStre
   if (gx < 1) gx = 1;
   if (gx > b.n_groups) gx = b.n_groups;
   const dim3 grid(gx, gy);
+  b.sched = nullptr;
+  if (a.tile_masks && gy <= 8 && !(g_b2_variant & 4)) {   // masked (grouped) launches: groups differ in cost -> dynamic scheduler
+    static unsigned int* slots = nullptr;
+    static std::atomic<unsigned> next{0};
+    if (!slots) S2D_CUDA(cudaGetSymbolAddress(reinterpret_cast<void**>(&slots), g_b2_sched));
+    b.sched = slots + (size_t)(next.fetch_add(1) % kB2SchedSlots) * 16;
+  }
   conv_bf2_kernel<COUT, T, S, TMA, SWAP><<<grid, Cfg::THREADS, Cfg::SMEM_BYTES, st>>>(b, map);
   S2D_LAUNCH_CHECK();
   count_launches(1);
@@ -963,6 +1025,30 @@ static int make_grid_map(const void* base, int ld_words, int C, int B, int H, in
   if (r != CUDA_SUCCESS) {
     set_error("s2d_conv_fwd_grid: cuTensorMapEncodeTiled failed (%d) for base=%p ld=%d C=%d B=%d H=%d W=%d", (int)r, base, ld_words,
               C, B, H, W);
+    return S2D_ERR_CUDA;
+  }
+  return S2D_OK;
+}
+
+// 2-D tensor map over split rows [n rows, ld words]: box = 32 words x 1 row, 128B swizzle, zero fill outside -- what
+// tile::gather4 needs (four such rows per instruction, a negative row index reads as zeros)
+static int make_rows_map(const void* base, int ld_words, int C, int n, CUtensorMap* map) {
+  const cuuint64_t dims[2] = {(cuuint64_t)C, (cuuint64_t)(n > 0 ? n : 1)};
+  const cuuint64_t strides[1] = {(cuuint64_t)ld_words * 4};
+  const cuuint32_t box[2] = {32u, 1u};
+  const cuuint32_t estr[2] = {1u, 1u};
+  typedef CUresult (*EncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                               const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                               CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+  void* fn = nullptr;
+  cudaDriverEntryPointQueryResult q;
+  S2D_CUDA(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &q));
+  S2D_REQUIRE(fn && q == cudaDriverEntryPointSuccess, "s2d_conv_fwd: cuTensorMapEncodeTiled not available in this driver");
+  const CUresult r = reinterpret_cast<EncodeFn>(fn)(map, CU_TENSOR_MAP_DATA_TYPE_UINT32, 2, const_cast<void*>(base), dims, strides,
+                                                    box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                                                    CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("s2d_conv_fwd: cuTensorMapEncodeTiled failed (%d) for rows map base=%p ld=%d C=%d n=%d", (int)r, base, ld_words, C, n);
     return S2D_ERR_CUDA;
   }
   return S2D_OK;
@@ -1003,6 +1089,7 @@ static int conv_fwd_bf2_impl(const s2d_conv_params& p, int grid_b, int grid_h, i
   a.dbg = g_b2_dbg;
   a.prof = g_b2_prof;
   a.grid_tiles_x = a.grid_tiles_y = a.grid_kw = a.grid_pad = 0;
+  a.g4 = 0;
   CUtensorMap map;
   memset(&map, 0, sizeof(map));
   if (tma) {
@@ -1015,19 +1102,29 @@ static int conv_fwd_bf2_impl(const s2d_conv_params& p, int grid_b, int grid_h, i
     S2D_REQUIRE(p.n_out == grid_b * a.grid_tiles_x * a.grid_tiles_y * kBM, "s2d_conv_fwd_grid: n_out must be tiles x 128");
     const int rc = make_grid_map(p.in_split, p.in_split_ld, p.Cin, grid_b, grid_h, grid_w, &map);
     if (rc != S2D_OK) return rc;
-    if (cb == 128) return g_b2_variant == 2 ? launch_b2<128, 2, 8, true>(a, map, p.Cout, st) : launch_b2<128, 2, 8, true, true>(a, map, p.Cout, st);
+    if (cb == 128) return (g_b2_variant & 3) == 2 ? launch_b2<128, 2, 8, true>(a, map, p.Cout, st) : launch_b2<128, 2, 8, true, true>(a, map, p.Cout, st);
     if (cb == 64) return launch_b2<64, 4, 8, true>(a, map, p.Cout, st);
     if (cb == 32) return launch_b2<32, 4, 8, true>(a, map, p.Cout, st);
     return launch_b2<16, 4, 8, true>(a, map, p.Cout, st);
   }
   const int v = g_b2_variant;
+  a.g4 = 0;
+  if ((v & 8) && a.kps == 1) {        // experimental: TMA gather4 producers
+    const int rc = make_rows_map(p.in_split, p.in_split_ld, p.Cin, p.n_in, &map);
+    if (rc != S2D_OK) return rc;
+    a.g4 = 1;
+  }
   // variant 0: production choice; 1: T = 2.  (Two CTAs per SM with half the stage ring each, S = 4, measured no faster: the
   // kernel is bound by shared-memory bandwidth and the tensor pipe, which both CTAs share, not by barrier latency.)
-  // 128 output channels: swapped operands (variant 2: the unswapped kernel, for A/B timing)
-  if (cb == 128) return v == 2 ? launch_b2<128, 2, 8, false>(a, map, p.Cout, st) : launch_b2<128, 2, 8, false, true>(a, map, p.Cout, st);
-  if (cb == 64) return v == 1 ? launch_b2<64, 2, 8, false>(a, map, p.Cout, st) : launch_b2<64, 4, 8, false>(a, map, p.Cout, st);
-  if (cb == 32) return v == 1 ? launch_b2<32, 2, 8, false>(a, map, p.Cout, st) : launch_b2<32, 4, 8, false>(a, map, p.Cout, st);
-  return v == 1 ? launch_b2<16, 2, 8, false>(a, map, p.Cout, st) : launch_b2<16, 4, 8, false>(a, map, p.Cout, st);
+  // 128 output channels: swapped operands (variant 2: the unswapped kernel, for A/B timing).  With only a few blocks per
+  // group (1x1 layers) the kernel is bound by its epilogue, and the unswapped one (8 x STS.128 per item instead of 32 x
+  // STS.32) is the faster of the two there.
+  if (cb == 128)
+    return ((v & 3) == 2 || a.ksteps * a.nchunk < 16) ? launch_b2<128, 2, 8, false>(a, map, p.Cout, st)
+                                                       : launch_b2<128, 2, 8, false, true>(a, map, p.Cout, st);
+  if (cb == 64) return (v & 3) == 1 ? launch_b2<64, 2, 8, false>(a, map, p.Cout, st) : launch_b2<64, 4, 8, false>(a, map, p.Cout, st);
+  if (cb == 32) return (v & 3) == 1 ? launch_b2<32, 2, 8, false>(a, map, p.Cout, st) : launch_b2<32, 4, 8, false>(a, map, p.Cout, st);
+  return (v & 3) == 1 ? launch_b2<16, 2, 8, false>(a, map, p.Cout, st) : launch_b2<16, 4, 8, false>(a, map, p.Cout, st);
 }
 
 int conv_fwd_bf2(const s2d_conv_params& p, cudaStream_t st) { return conv_fwd_bf2_impl(p, 0, 0, 0, 0, 0, st); }
@@ -1087,14 +1184,14 @@ extern "C" int s2d_table_group_rows(const int* tbl, int tbl_stride, int K, int n
   const int nblk = div_up(n_rows, kGrpRows);
   int* counts = static_cast<int*>(workspace);
   int* tails = counts + (size_t)nblk * kGrpBuckets;
-  unsigned short* keys = reinterpret_cast<unsigned short*>(tails + 2 * kGrpBuckets);
+  unsigned short* keys = reinterpret_cast<unsigned short*>(tails + kGrpSegs * kGrpBuckets);
   group_keys_hist_kernel<<<nblk, kGrpRows, 0, st>>>(tbl, tbl_stride, K, n_rows, keys, counts);
-  group_scan_kernel<<<1, 1024, 0, st>>>(counts, nblk, tails);
+  group_scan(counts, nblk, tails, st);
   group_scatter_kernel<<<nblk, kGrpRows, 0, st>>>(keys, n_rows, nblk, counts, tails, perm);
   group_permute_table_kernel<<<div_up(n_rows, 128), 128, 0, st>>>(tbl, tbl_stride, K, n_rows, perm, tbl_out, out_stride,
                                                                    tile_masks);
   S2D_LAUNCH_CHECK();
-  count_launches(4);
+  count_launches(5);
   return S2D_OK;
 }
 

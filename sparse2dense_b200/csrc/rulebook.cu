@@ -438,14 +438,14 @@ static int build_grouped(const int* coors, int n_rows, int batch, const int* sha
   const int nblk = div_up(n_rows, kGrpRows);
   int* counts = static_cast<int*>(workspace);
   int* tails = counts + (size_t)nblk * kGrpBuckets;
-  unsigned short* keys = reinterpret_cast<unsigned short*>(tails + 2 * kGrpBuckets);
+  unsigned short* keys = reinterpret_cast<unsigned short*>(tails + kGrpSegs * kGrpBuckets);
   const int4* c4 = reinterpret_cast<const int4*>(coors);
   subm_keys_hist_kernel<<<nblk, kGrpRows, 0, st>>>(c4, n_rows, S, C, I.view(), keys, counts);
-  group_scan_kernel<<<1, 1024, 0, st>>>(counts, nblk, tails);
+  group_scan(counts, nblk, tails, st);
   group_scatter_kernel<<<nblk, kGrpRows, 0, st>>>(keys, n_rows, nblk, counts, tails, perm);
   subm_table_grouped_kernel<<<div_up(n_rows, 128), 128, 0, st>>>(c4, n_rows, S, C, I.view(), perm, tbl, tbl_stride, tile_masks);
   S2D_LAUNCH_CHECK();
-  count_launches(4);
+  count_launches(5);
   return S2D_OK;
 }
 }  // namespace s2d

@@ -36,6 +36,7 @@ def main():
     ap.add_argument("--dense", action="store_true", help="also time dense 3x3 / 1x1 convs of the neck shapes")
     ap.add_argument("--ablate", default="", help="comma list of ablation flag sets (see conv_bf2.cu B2Args::dbg), timed with variant 0")
     ap.add_argument("--only", type=int, default=0)
+    ap.add_argument("--insitu", action="store_true", help="also time the grouped layer with BN affine + residual + ReLU")
     ap.add_argument("--prof", action="store_true", help="print the in-kernel cycle counters (producer / MMA waits)")
     args = ap.parse_args()
     _lib.load()
@@ -90,6 +91,40 @@ def main():
                                           out_rows=gperm), flush, args.reps)
         line += f" | grouped live={glive:.3f} {t:.3f} ms (bit-equal {bool(torch.equal(o2, o3))}; grouping itself {t_grp:.3f} ms)"
         print(line, flush=True)
+        if True:             # executed blocks of the grouped launch: (offset, chunk) x tile groups of T tiles
+            T = 2 if c == 128 else 4
+            mk = gmasks.cpu().numpy().astype("int64") & 0x7ffffff
+            pad = (-len(mk)) % T
+            mg = np.concatenate([mk, np.zeros(pad, "int64")]).reshape(-1, T)
+            kps = 2 if c == 16 else 1
+            def steps(m):       # live offset steps of a mask (two offsets per step at 16 channels)
+                if kps == 1:
+                    return np.array([bin(int(v)).count("1") for v in m])
+                return np.array([sum(1 for q in range(14) if (int(v) >> (2 * q)) & 3) for v in m])
+            nchunk = max(1, c // 32)
+            union = np.bitwise_or.reduce(mg, axis=1)
+            blocks = steps(union) * nchunk
+            tile_blocks = steps(mk).sum() * nchunk
+            clk = t * 1e-3 * 1.965e9 * 148
+            print(f"   grouped {c:3d}: {len(mg)} groups of {T} tiles, {int(blocks.sum())} blocks ({blocks.min()}..{blocks.max()} per group), "
+                  f"{int(tile_blocks)} live tile-blocks = {tile_blocks / max(1, blocks.sum()):.2f} per block; "
+                  f"{clk / blocks.sum():.0f} clk per block, {clk / tile_blocks:.0f} clk per live tile-block", flush=True)
+        if args.insitu:      # as the layer runs inside a residual block: BN affine + residual + ReLU, grouped rulebook
+            sc, sh, res = torch.rand(c, device="cuda") + 0.5, torch.randn(c, device="cuda"), torch.randn(n, c, device="cuda")
+            line = f"   in-situ {c:3d} (grouped, affine + residual + ReLU):"
+            for v in [int(s) for s in args.variants.split(",")]:
+                setv(v)
+                t = timeit(lambda: ops.spconv_fwd(feats, w, gt, n, scale=sc, shift=sh, residual=res, relu=True,
+                                                  precision=ops.PRECISION_BF16X2, packed=pk, out=out, tile_masks=gmasks,
+                                                  out_rows=gperm), flush, args.reps)
+                t2 = timeit(lambda: ops.spconv_fwd(feats, w, gt, n, scale=sc, shift=sh, relu=True,
+                                                   precision=ops.PRECISION_BF16X2, packed=pk, out=out, tile_masks=gmasks,
+                                                   out_rows=gperm), flush, args.reps)
+                t3 = timeit(lambda: ops.spconv_fwd(feats, w, gt, n, precision=ops.PRECISION_BF16X2, packed=pk, out=out,
+                                                   tile_masks=gmasks, out_rows=gperm, want_split=False), flush, args.reps)
+                line += f" | v{v} {t:.3f} ms, no residual {t2:.3f}, plain without split {t3:.3f}"
+            setv(0)
+            print(line, flush=True)
         if args.prof:
             lib = ctypes.CDLL(_lib.LIB_PATH)
             lib.s2d_debug_bf2_prof.argtypes = [ctypes.c_void_p]
