@@ -73,8 +73,9 @@ __device__ __forceinline__ void sts32(uint32_t addr, int v) {
 // group: one weight tile and up to T gathered tiles (one per tile of the group that has a neighbour at that offset).
 // The eight gathered-tile stages form NB = 8 / T block slots; stage (slot, t) = slot * T + t always belongs to tile t, so
 // producer warp w = stage w and MMA warp t = tile t see every phase of "their" barriers whatever the masks skip.
-template <int COUT, int T_, int S_, bool SWAP_ = false>
+template <int COUT, int T_, int S_, bool SWAP_ = false, int PW_ = 1>
 struct B2Cfg {
+  static constexpr int PW = PW_;                               // producer warps per gathered-tile stage (each fills 128 / PW rows)
   static constexpr int T = T_;
   static constexpr int S = S_;
   static constexpr bool SWAP = SWAP_;                          // operands swapped: D[cout, rows of both tiles] (see the MMA warps)
@@ -82,8 +83,8 @@ struct B2Cfg {
   static constexpr int CTAS_PER_SM = S == 4 ? 2 : 1;
   static constexpr int NB = S / T;                             // gathered-tile slots per tile (stage = slot * T + t)
   static constexpr int SB = S == 4 ? (COUT >= 64 ? 2 : 4) : (COUT >= 128 ? 3 : 4);   // weight-tile ring
-  static constexpr int UTIL_WARP = S;
-  static constexpr int MMA_WARP0 = S + 1;
+  static constexpr int UTIL_WARP = S * PW;
+  static constexpr int MMA_WARP0 = S * PW + 1;
   static constexpr int EPI_WARPS = 8;                          // two per TMEM lane quarter: they split the (tile, column chunk) items
   static constexpr int WARPS = MMA_WARP0 + MW + EPI_WARPS;
   static constexpr int THREADS = 32 * WARPS;
@@ -99,6 +100,7 @@ struct B2Cfg {
   static constexpr int BAR_BYTES = 512;
   static constexpr int SMEM_BYTES = S * kB2AStage + SB * B_STAGE + LIST_BYTES + EPI_BYTES + S * 1024 + BAR_BYTES + 1024;
   static_assert(T == 2 || T == 4, "tiles per group");
+  static_assert(PW == 1 || PW == 2, "producer warps per stage");
   static_assert(!SWAP || (COUT == 128 && T == 2), "swapped operands: M = COUT = 128, N = 2 tiles x 128 rows");
   static_assert((S == 4 || S == 8) && NB >= 1 && (NB & (NB - 1)) == 0, "stage ring");
   static_assert(ACC_COLS * CTAS_PER_SM <= 512, "TMEM budget");
@@ -162,12 +164,12 @@ __device__ __forceinline__ void split_pair(float a, float b, uint32_t& hi, uint3
 // the per-slot barriers); the epilogue warps drain a group's accumulators from one TMEM buffer while the next group
 // is gathered and multiplied into the other.
 //   block entry = kk | live-tile nibble << 5 | chunk << 9
-template <int COUT, int T, int S, bool TMA, bool SWAP>
-__global__ void __launch_bounds__(B2Cfg<COUT, T, S, SWAP>::THREADS, B2Cfg<COUT, T, S, SWAP>::CTAS_PER_SM)
+template <int COUT, int T, int S, bool TMA, bool SWAP, int PW>
+__global__ void __launch_bounds__(B2Cfg<COUT, T, S, SWAP, PW>::THREADS, B2Cfg<COUT, T, S, SWAP, PW>::CTAS_PER_SM)
 conv_bf2_kernel(const __grid_constant__ B2Args A, const __grid_constant__ CUtensorMap in_map) {
-  using Cfg = B2Cfg<COUT, T, S, SWAP>;
+  using Cfg = B2Cfg<COUT, T, S, SWAP, PW>;
   constexpr int MW = Cfg::MW;
-  constexpr int kB2Stages = S, kB2ProducerWarps = S, kB2UtilWarp = Cfg::UTIL_WARP, kB2MmaWarp0 = Cfg::MMA_WARP0;
+  constexpr int kB2Stages = S, kB2ProducerWarps = S * PW, kB2UtilWarp = Cfg::UTIL_WARP, kB2MmaWarp0 = Cfg::MMA_WARP0;
   constexpr int B_STAGE = Cfg::B_STAGE, NB = Cfg::NB, SB = Cfg::SB;
   const int NCHUNK = A.nchunk, K = A.K, KS = A.ksteps, kps = A.kps, n_out = A.n_out;
   const int cblk = blockIdx.y * COUT;
@@ -180,7 +182,7 @@ conv_bf2_kernel(const __grid_constant__ B2Args A, const __grid_constant__ CUtens
   uint8_t* lists = b_ring + SB * B_STAGE;                        // 2 x kB2ListCap u16 block entries
   uint8_t* epi = lists + Cfg::LIST_BYTES;                        // 8 warps x [32 rows x 144 B]
   uint8_t* idx_scratch = epi + Cfg::EPI_BYTES;                   // 8 producer warps x 1 KB
-  uint64_t* bars = reinterpret_cast<uint64_t*>(idx_scratch + kB2ProducerWarps * 1024);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(idx_scratch + kB2Stages * 1024);
   uint64_t* bar_a_full = bars;                                   // [8]  producer warp -> MMA warp of the stage's tile
   uint64_t* bar_a_empty = bar_a_full + kB2Stages;                // [8]  MMA warp of the tile -> producer warp of the stage
   uint64_t* bar_b_full = bar_a_empty + kB2Stages;                // [SB] weight tile landed
@@ -199,7 +201,7 @@ conv_bf2_kernel(const __grid_constant__ B2Args A, const __grid_constant__ CUtens
 
   if (warp == kB2MmaWarp0 && lane == 0) {
     for (int s = 0; s < kB2Stages; ++s) {
-      mbar_init(smem_u32(bar_a_full + s), 1);                     // the producer warp that owns the stage
+      mbar_init(smem_u32(bar_a_full + s), TMA ? 1 : PW);          // the producer warp(s) that own the stage
       mbar_init(smem_u32(bar_a_empty + s), 1);                    // tcgen05.commit of the MMA warp that owns the tile
     }
     for (int s = 0; s < SB; ++s) {
@@ -274,7 +276,11 @@ conv_bf2_kernel(const __grid_constant__ B2Args A, const __grid_constant__ CUtens
     // A warp's iteration is a serial chain of ~100 dependent instructions plus the latency of its own copies, so whole
     // 128-row tiles are dealt over the warps: eight gathers are in flight and one mbarrier arrival publishes a stage.
     //   lane = (o = lane >> 3, c8 = lane & 7): copy r (0..31) moves piece c8 of row 4r + o.
-    const int my_slot = warp / T, my_t = warp % T;
+    // With PW = 2 two warps share a stage, each gathering 64 of its rows: the fill of a stage (issue of the copies + their
+    // latency) is the long leg of the stage's cycle fill -> MMA -> empty, and that cycle, not a bandwidth, set the pace.
+    constexpr int R = 32 / PW;                               // copies per lane: rows hbase + 4r + o, r = 0..R-1
+    const int my_stage = warp / PW, hbase = (warp % PW) * (kBM / PW);
+    const int my_slot = my_stage / T, my_t = my_stage % T;
     const int o = lane >> 3, c8 = lane & 7;
     const int sub = kps == 2 ? (c8 >> 2) : 0;                // Cin = 16: pieces 0-3 come from offset 2kk, 4-7 from 2kk + 1
     const uint32_t piece = (uint32_t)(kps == 2 ? (c8 & 3) : c8) * 16u;
@@ -282,12 +288,12 @@ conv_bf2_kernel(const __grid_constant__ B2Args A, const __grid_constant__ CUtens
     const uint32_t row_units = (uint32_t)A.in_ld >> 2;       // row stride in 16 B units (32-bit offsets reach 64 GiB)
     const int* tbl = A.tbl;
     const int tbl_stride = A.tbl_stride;
-    const uint32_t a_stage = smem_u32(a_ring) + (uint32_t)warp * kB2AStage;
-    const uint32_t bar_full = smem_u32(bar_a_full + warp), bar_empty = smem_u32(bar_a_empty + warp);
+    const uint32_t a_stage = smem_u32(a_ring) + (uint32_t)my_stage * kB2AStage + (uint32_t)hbase * 128u;
+    const uint32_t bar_full = smem_u32(bar_a_full + my_stage), bar_empty = smem_u32(bar_a_empty + my_stage);
     uint32_t phase = 1;                                      // first use of the stage: free
-    // index scratch of this warp: [2 offsets][4 row residues o][32 copies r] -> idx of row 4r + o, read back as int4 over r
-    const uint32_t scr = smem_u32(idx_scratch) + (uint32_t)warp * 1024u;
-    const uint32_t scr_rd = scr + (uint32_t)sub * 512u + (uint32_t)o * 128u;
+    // index scratch of this warp: [2 offsets][4 row residues o][R copies r] -> idx of row hbase + 4r + o, read back as int4 over r
+    const uint32_t scr = smem_u32(idx_scratch) + (uint32_t)warp * (1024u / PW);
+    const uint32_t scr_rd = scr + (uint32_t)sub * (16u * R) + (uint32_t)o * (4u * R);
     const uint32_t dst_lane = (uint32_t)o * 128u;            // row 4r + o: byte (4r + o) * 128, swizzle ((4r + o) & 7) ^ c8
     int gblk = 0;                                            // blocks of this CTA before the current group
     int j = 0;
@@ -309,8 +315,8 @@ conv_bf2_kernel(const __grid_constant__ B2Args A, const __grid_constant__ CUtens
       auto load_idx = [&](uint32_t e, int s2) -> int4 {
         int4 v = make_int4(-1, -1, -1, -1);
         const int k = (int)(e & 31u) * kps + s2;
-        const int row0 = tile0 + 4 * lane;
-        if (((e >> (5 + my_t)) & 1u) && k < K && row0 < row_end && !(A.dbg & 64)) {
+        const int row0 = tile0 + hbase + 4 * lane;
+        if (lane < R && ((e >> (5 + my_t)) & 1u) && k < K && row0 < row_end && !(A.dbg & 64)) {
           v = __ldg(reinterpret_cast<const int4*>(tbl + (size_t)k * tbl_stride + row0));
           const int lim = row_end - row0;
           if (lim < 4) { if (lim < 2) v.y = -1; if (lim < 3) v.z = -1; v.w = -1; }
@@ -330,11 +336,13 @@ conv_bf2_kernel(const __grid_constant__ B2Args A, const __grid_constant__ CUtens
         const bool live = (e >> (5 + my_t)) & 1u;
         if (live && !A.g4) {
           // indices -> scratch, transposed so that the copies of row residue o read four consecutive r with one LDS.128
-          sts32(scr + 4u * lane, qa.x); sts32(scr + 128u + 4u * lane, qa.y);
-          sts32(scr + 256u + 4u * lane, qa.z); sts32(scr + 384u + 4u * lane, qa.w);
-          if (kps == 2) {
-            sts32(scr + 512u + 4u * lane, qb.x); sts32(scr + 640u + 4u * lane, qb.y);
-            sts32(scr + 768u + 4u * lane, qb.z); sts32(scr + 896u + 4u * lane, qb.w);
+          if (lane < R) {
+            sts32(scr + 4u * lane, qa.x); sts32(scr + 4u * R + 4u * lane, qa.y);
+            sts32(scr + 8u * R + 4u * lane, qa.z); sts32(scr + 12u * R + 4u * lane, qa.w);
+            if (kps == 2) {
+              sts32(scr + 16u * R + 4u * lane, qb.x); sts32(scr + 20u * R + 4u * lane, qb.y);
+              sts32(scr + 24u * R + 4u * lane, qb.z); sts32(scr + 28u * R + 4u * lane, qb.w);
+            }
           }
         }
         const uint32_t cunits = (kps == 2 ? 0u : (e >> 9) * 8u) + (piece >> 4);
@@ -347,7 +355,7 @@ conv_bf2_kernel(const __grid_constant__ B2Args A, const __grid_constant__ CUtens
           if (kps == 2) qb_n = load_idx(e_n, 1);
         }
         __syncwarp();
-        if (live && A.g4) {
+        if (PW == 1 && live && A.g4) {
           // TMA gather: lane l moves rows 4l .. 4l + 3 of the tile (its qa) with ONE gather4; a negative row is zero filled;
           // the stage's barrier counts the bytes, so the warp neither waits for the data nor fences it
           c0 = prof ? clock64() : 0;
@@ -364,7 +372,7 @@ conv_bf2_kernel(const __grid_constant__ B2Args A, const __grid_constant__ CUtens
           if (prof) { pw_empty += clock64() - c0; ++p_steps; }
           phase ^= 1;
 #pragma unroll
-          for (int q = 0; q < 8; ++q) {
+          for (int q = 0; q < R / 4; ++q) {
             if (A.dbg & 1) break;
             const int4 ii = lds128i(scr_rd + 16u * q);
             const int idx[4] = {ii.x, ii.y, ii.z, ii.w};
@@ -967,12 +975,12 @@ static int b2_cout_block(int Cout) {
 }
 bool bf2_supported(int Cin, int Cout) { return (Cin == 16 || (Cin >= 32 && Cin % 32 == 0)) && b2_cout_block(Cout) != 0; }
 
-template <int COUT, int T, int S, bool TMA, bool SWAP = false>
+template <int COUT, int T, int S, bool TMA, bool SWAP = false, int PW = 1>
 static int launch_b2(const B2Args& a, const CUtensorMap& map, int Cout, cudaStream_t st) {
-  using Cfg = B2Cfg<COUT, T, S, SWAP>;
+  using Cfg = B2Cfg<COUT, T, S, SWAP, PW>;
   static bool configured = false;
   if (!configured) {
-    S2D_CUDA(cudaFuncSetAttribute(conv_bf2_kernel<COUT, T, S, TMA, SWAP>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    S2D_CUDA(cudaFuncSetAttribute(conv_bf2_kernel<COUT, T, S, TMA, SWAP, PW>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                   Cfg::SMEM_BYTES));
     configured = true;
   }
@@ -995,7 +1003,7 @@ static int launch_b2(const B2Args& a, const CUtensorMap& map, int Cout, cudaStre
     if (!slots) S2D_CUDA(cudaGetSymbolAddress(reinterpret_cast<void**>(&slots), g_b2_sched));
     b.sched = slots + (size_t)(next.fetch_add(1) % kB2SchedSlots) * 16;
   }
-  conv_bf2_kernel<COUT, T, S, TMA, SWAP><<<grid, Cfg::THREADS, Cfg::SMEM_BYTES, st>>>(b, map);
+  conv_bf2_kernel<COUT, T, S, TMA, SWAP, PW><<<grid, Cfg::THREADS, Cfg::SMEM_BYTES, st>>>(b, map);
   S2D_LAUNCH_CHECK();
   count_launches(1);
   return S2D_OK;
@@ -1119,9 +1127,13 @@ static int conv_fwd_bf2_impl(const s2d_conv_params& p, int grid_b, int grid_h, i
   // 128 output channels: swapped operands (variant 2: the unswapped kernel, for A/B timing).  With only a few blocks per
   // group (1x1 layers) the kernel is bound by its epilogue, and the unswapped one (8 x STS.128 per item instead of 32 x
   // STS.32) is the faster of the two there.
-  if (cb == 128)
-    return ((v & 3) == 2 || a.ksteps * a.nchunk < 16) ? launch_b2<128, 2, 8, false>(a, map, p.Cout, st)
-                                                       : launch_b2<128, 2, 8, false, true>(a, map, p.Cout, st);
+  if (cb == 128) {
+    if ((v & 3) == 2 || a.ksteps * a.nchunk < 16) return launch_b2<128, 2, 8, false>(a, map, p.Cout, st);
+    // variant 16: two producer warps per stage -- measured no faster (0.390 ms either way on the 128 -> 128 layer): the
+    // gather is bound by what the SM can pull from L2 for a map of this size, not by the fill latency of a stage
+    if ((v & 16) && !a.g4) return launch_b2<128, 2, 8, false, true, 2>(a, map, p.Cout, st);
+    return launch_b2<128, 2, 8, false, true>(a, map, p.Cout, st);
+  }
   if (cb == 64) return (v & 3) == 1 ? launch_b2<64, 2, 8, false>(a, map, p.Cout, st) : launch_b2<64, 4, 8, false>(a, map, p.Cout, st);
   if (cb == 32) return (v & 3) == 1 ? launch_b2<32, 2, 8, false>(a, map, p.Cout, st) : launch_b2<32, 4, 8, false>(a, map, p.Cout, st);
   return (v & 3) == 1 ? launch_b2<16, 2, 8, false>(a, map, p.Cout, st) : launch_b2<16, 4, 8, false>(a, map, p.Cout, st);
