@@ -28,14 +28,20 @@
 //               instead -- a regular BEV map needs no neighbour table, the padding is the TMA zero fill.
 //   warp 8      utility: block lists (double buffered), one cp.async.bulk per weight tile, L2 prefetch of table lines; owns
 //               the TMEM allocation.
-//   warps 9..   MMA issuers, one per tile of the group: six tcgen05.mma.kind::f16 per block (M = 128, N = COUT, K = 16),
-//               tcgen05.commit releases the rings / publishes the accumulators.
+//   warps 9..   MMA issuers.  Cout <= 64 (and 1x1 layers): one per tile of the group, six tcgen05.mma.kind::f16 per block
+//               (M = 128, N = COUT, K = 16).  Cout = 128: operands SWAPPED -- the weight tile is the M = 128 operand, the
+//               gathered tiles of both tiles of the group one N = 256 operand, the accumulator is transposed -- and two
+//               warps that issue ALTERNATE blocks (see there).  tcgen05.commit releases the rings / publishes the accumulators.
 //   last 8      epilogue warps (two per TMEM lane quarter) on the second accumulator buffer: tcgen05.ld -> BN affine /
 //               residual / ReLU / GELU -> fp32 row and split row, staged through shared memory for whole-row stores.
 //
-// What bounds it: shared-memory bandwidth -- per block the six SS-mode MMAs read the A tile 6 x 4 KB and the
-// weight slices 6 x COUT x 32 B while tile and weights are written into the same memory; neither two CTAs per SM nor TMA
-// instead of LDGSTS changed the time.
+// Tile groups are handed out dynamically for masked launches (heaviest neighbour patterns first, grouping.cuh), statically
+// otherwise.
+//
+// What bounds it (measured with tools/mma_probe.cu / sync_probe.cu / l2_probe.cu): the tensor pipe queues only
+// ~1.5 MMAs, so the per-block overhead of the issuing warp used to idle it (fixed for Cout = 128 by the alternating
+// issuers); what remains is the stream of gathered rows and weight tiles from L2 into the SM (~50 B/clk/SM for maps of
+// 100-240 MB), 27 re-reads of every input row.
 #include <string.h>
 
 #include <atomic>
@@ -291,6 +297,11 @@ conv_bf2_kernel(const __grid_constant__ B2Args A, const __grid_constant__ CUtens
     const uint32_t a_stage = smem_u32(a_ring) + (uint32_t)my_stage * kB2AStage + (uint32_t)hbase * 128u;
     const uint32_t bar_full = smem_u32(bar_a_full + my_stage), bar_empty = smem_u32(bar_a_empty + my_stage);
     uint32_t phase = 1;                                      // first use of the stage: free
+    // the gathered map is re-read once per kernel offset: ask L2 to keep it (the read-once table and residual and the
+    // written-once fp32 output are streamed with evict-first)
+    uint64_t keep_policy;
+    if (A.dbg & 256) asm volatile("createpolicy.fractional.L2::evict_normal.b64 %0, 1.0;" : "=l"(keep_policy));
+    else asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(keep_policy));
     // index scratch of this warp: [2 offsets][4 row residues o][R copies r] -> idx of row hbase + 4r + o, read back as int4 over r
     const uint32_t scr = smem_u32(idx_scratch) + (uint32_t)warp * (1024u / PW);
     const uint32_t scr_rd = scr + (uint32_t)sub * (16u * R) + (uint32_t)o * (4u * R);
@@ -317,7 +328,8 @@ conv_bf2_kernel(const __grid_constant__ B2Args A, const __grid_constant__ CUtens
         const int k = (int)(e & 31u) * kps + s2;
         const int row0 = tile0 + hbase + 4 * lane;
         if (lane < R && ((e >> (5 + my_t)) & 1u) && k < K && row0 < row_end && !(A.dbg & 64)) {
-          v = __ldg(reinterpret_cast<const int4*>(tbl + (size_t)k * tbl_stride + row0));
+          if (A.dbg & 512) v = __ldg(reinterpret_cast<const int4*>(tbl + (size_t)k * tbl_stride + row0));
+          else v = __ldcs(reinterpret_cast<const int4*>(tbl + (size_t)k * tbl_stride + row0));   // read once: evict first
           const int lim = row_end - row0;
           if (lim < 4) { if (lim < 2) v.y = -1; if (lim < 3) v.z = -1; v.w = -1; }
         }
@@ -381,7 +393,7 @@ conv_bf2_kernel(const __grid_constant__ B2Args A, const __grid_constant__ CUtens
               const int r = 4 * q + rr;                        // row 4r + o; (4r + o) & 7 = 4 (r & 1) + o
               const uint32_t dst = a_stage + (uint32_t)r * 512u + dst_lane + (uint32_t)((c8 ^ (4 * (r & 1) + o)) << 4);
               const uint32_t off = (uint32_t)max(idx[rr], 0) * row_units + cunits;
-              cp_async16_zfill(dst, in_bytes + ((size_t)off << 4), (idx[rr] >= 0 && !(A.dbg & 16)) ? 16u : 0u);
+              cp_async16_zfill_hint(dst, in_bytes + ((size_t)off << 4), (idx[rr] >= 0 && !(A.dbg & 16)) ? 16u : 0u, keep_policy);
             }
           }
           cp_async_commit();
@@ -760,11 +772,12 @@ conv_bf2_kernel(const __grid_constant__ B2Args A, const __grid_constant__ CUtens
           if (row < row_end && orow >= 0 && !(A.dbg & 8)) {
             v.x = v.x * sc.x + sh.x; v.y = v.y * sc.y + sh.y; v.z = v.z * sc.z + sh.z; v.w = v.w * sc.w + sh.w;
             float4 rr = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (A.residual) rr = __ldg(reinterpret_cast<const float4*>(A.residual + (size_t)orow * A.res_ld + cblk + c0) + pp);
+            // read-once / written-once streams must not push the gathered map out of L2: evict-first loads and stores
+            if (A.residual) rr = __ldcs(reinterpret_cast<const float4*>(A.residual + (size_t)orow * A.res_ld + cblk + c0) + pp);
             if (!res_after) { v.x += rr.x; v.y += rr.y; v.z += rr.z; v.w += rr.w; }
             v.x = b2_act(v.x, act); v.y = b2_act(v.y, act); v.z = b2_act(v.z, act); v.w = b2_act(v.w, act);
             if (res_after) { v.x += rr.x; v.y += rr.y; v.z += rr.z; v.w += rr.w; }
-            if (A.out) reinterpret_cast<float4*>(A.out + (size_t)orow * A.out_ld + cblk + c0)[pp] = v;
+            if (A.out) __stcs(reinterpret_cast<float4*>(A.out + (size_t)orow * A.out_ld + cblk + c0) + pp, v);
             if (A.out_split) {
               // split row: per chunk of EPC channels [EPC/2 words hi | EPC/2 words lo]; this lane owns channels 4pp..4pp+3
               uint32_t h0, l0, h1, l1;

@@ -155,6 +155,10 @@ __device__ __forceinline__ void tmem_ld(uint32_t taddr, uint32_t (&v)[N]) {
 __device__ __forceinline__ void cp_async16_zfill(uint32_t dst, const void* src, uint32_t src_bytes) {
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(src_bytes) : "memory");
 }
+__device__ __forceinline__ void cp_async16_zfill_hint(uint32_t dst, const void* src, uint32_t src_bytes, uint64_t policy) {
+  asm volatile("cp.async.cg.shared.global.L2::cache_hint [%0], [%1], 16, %2, %3;" ::"r"(dst), "l"(src), "r"(src_bytes), "l"(policy)
+               : "memory");
+}
 // arrive on `bar` once all cp.async issued so far by this thread have completed (counts against the barrier's expected arrivals)
 __device__ __forceinline__ void cp_async_mbar_arrive_noinc(uint32_t bar) {
   asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(bar) : "memory");

@@ -125,6 +125,15 @@ def main():
                 line += f" | v{v} {t:.3f} ms, no residual {t2:.3f}, plain without split {t3:.3f}"
             setv(0)
             print(line, flush=True)
+            line = f"   in-situ {c:3d} cache-policy flags (affine + residual + ReLU):"
+            for fl in (0, 256, 512, 768):
+                setf(fl)
+                t = timeit(lambda: ops.spconv_fwd(feats, w, gt, n, scale=sc, shift=sh, residual=res, relu=True,
+                                                  precision=ops.PRECISION_BF16X2, packed=pk, out=out, tile_masks=gmasks,
+                                                  out_rows=gperm), flush, max(args.reps, 15))
+                line += f" f{fl}={t:.4f}"
+            setf(0)
+            print(line, flush=True)
         if args.prof:
             lib = ctypes.CDLL(_lib.LIB_PATH)
             lib.s2d_debug_bf2_prof.argtypes = [ctypes.c_void_p]
