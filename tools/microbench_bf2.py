@@ -134,6 +134,18 @@ def main():
                 line += f" f{fl}={t:.4f}"
             setf(0)
             print(line, flush=True)
+        if args.prof:          # grouped launch: who waits for whom
+            lib = ctypes.CDLL(_lib.LIB_PATH)
+            lib.s2d_debug_bf2_prof.argtypes = [ctypes.c_void_p]
+            buf = torch.zeros(148 * 16, dtype=torch.int64, device="cuda")
+            lib.s2d_debug_bf2_prof(buf.data_ptr())
+            ops.spconv_fwd(feats, w, gt, n, precision=ops.PRECISION_BF16X2, packed=pk, out=out, tile_masks=gmasks, out_rows=gperm)
+            torch.cuda.synchronize()
+            lib.s2d_debug_bf2_prof(None)
+            m = buf.view(148, 16).double().mean(0).tolist()
+            mx = buf.view(148, 16).double().max(0).values.tolist()
+            print(f"   prof {c:3d} GROUPED: producer0 total {m[0]:.0f} clk (max {mx[0]:.0f}): wait_empty {m[1]:.0f} wait_data {m[2]:.0f} wait_list {m[3]:.0f} over {m[4]:.0f} steps "
+                  f"| mma0 total {m[5]:.0f}: wait_a {m[6]:.0f} wait_b {m[7]:.0f} wait_acc {m[8]:.0f} wait_list {m[9]:.0f} over {m[10]:.0f} steps", flush=True)
         if args.prof:
             lib = ctypes.CDLL(_lib.LIB_PATH)
             lib.s2d_debug_bf2_prof.argtypes = [ctypes.c_void_p]
