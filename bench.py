@@ -489,6 +489,29 @@ def rooflines(wl, raw, steps, world, dev):
     peak_note = ("tensor peak = dense TF32 GEMM 8192^3 measured live with cuBLAS (%.1f TFLOP/s; bf16 burst / 2 from %s = %.1f); "
                  "hbm peak from %s" % (tf32_peak, pk["source"], pk["bf16"] / 2.0, pk["source"]))
 
+    def l2_stream(d, key):
+        """What the gather-GEMM pulls from L2 into the SMs per launch -- the stream that binds conv_bf2: every real
+        (row, offset) pair reads Cin x 4 B of split rows, every executed block one [128-channel x 128 B] weight tile shared by
+        the tiles of a group (2 tiles at 128 output channels, else 4) -- against the L2 -> SM rate measured by tools/l2_probe.cu."""
+        cin, cout, K, kind, n_out = key
+        try:
+            with open(os.path.join(ROOT, "profiles", "r2_l2_probe.json")) as f:
+                probe = json.load(f)
+        except Exception:
+            probe = {"l2_to_sm_tbs_resident": 20.3, "l2_to_sm_tbs_large_working_set": 14.5, "source": "fallback constants"}
+        cb = 128 if cout % 128 == 0 else 64 if cout % 64 == 0 else 32 if cout % 32 == 0 else 16
+        tiles_per_group = 2 if cb == 128 else 4
+        chunk_k = 2 if cin == 16 else 1                       # two offsets share a 128 B row at 16 channels
+        executed_rows = d["executed_over_algorithmic_rows"] * d["pairs"]
+        tile_blocks = executed_rows / 128.0 * max(1, cin // 32) / chunk_k
+        weight_bytes = tile_blocks / tiles_per_group * cb * 128.0 * (cout // cb)
+        gather_bytes = d["pairs"] * cin * 4.0
+        tbs = (gather_bytes + weight_bytes) / (d["avg_launch_ms"] * 1e-3) / 1e12
+        return {"achieved_tbs": tbs, "peak_tbs": probe["l2_to_sm_tbs_resident"], "frac": tbs / probe["l2_to_sm_tbs_resident"],
+                "peak_tbs_large_working_set": probe["l2_to_sm_tbs_large_working_set"],
+                "gather_bytes_per_launch": gather_bytes, "weight_tile_bytes_per_launch": weight_bytes,
+                "source": probe.get("source", "")}
+
     def tensor_obj(d, key):
         cin, cout, K, kind, n_out = key
         return {"bound": "tensor", "achieved": d["tflops"], "peak": tf32_peak, "unit": "TFLOP/s", "frac": d["tflops"] / tf32_peak,
@@ -497,7 +520,8 @@ def rooflines(wl, raw, steps, world, dev):
                 "share_of_step": d["share_of_step"], "algorithmic_flops_per_launch": d["algorithmic_flops"],
                 "algorithmic_bytes_per_launch": d["algorithmic_bytes"],
                 "executed_over_algorithmic_rows": d["executed_over_algorithmic_rows"],
-                "hbm": {"achieved_gbs": d["gbs"], "peak_gbs": pk["hbm"], "frac": d["gbs"] / pk["hbm"]}}
+                "hbm": {"achieved_gbs": d["gbs"], "peak_gbs": pk["hbm"], "frac": d["gbs"] / pk["hbm"]},
+                "l2_stream": l2_stream(d, key)}
 
     if sp is not None:
         out = tensor_obj(sp[1], sp[0])
