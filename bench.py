@@ -512,6 +512,17 @@ def rooflines(wl, raw, steps, world, dev):
                 "gather_bytes_per_launch": gather_bytes, "weight_tile_bytes_per_launch": weight_bytes,
                 "source": probe.get("source", "")}
 
+    def executed_bf16(d, key):
+        """The MMAs the kernel really issues: three kind::f16 (BF16) MMAs per product over the EXECUTED rows (whole 128-row tiles
+        of live (tile, offset) pairs), against the dense BF16 GEMM rate of MEASURED_PEAKS.json.  `frac` here says how busy the
+        tensor cores are; `roofline.frac` above charges the 1.5 TF32-pass cost of the fp32-level product and the dead rows of
+        live tiles to the kernel."""
+        cin, cout, K, kind, n_out = key
+        fl = 3.0 * 2.0 * d["executed_over_algorithmic_rows"] * d["pairs"] * cin * cout
+        tfl = fl / (d["avg_launch_ms"] * 1e-3) / 1e12
+        return {"achieved_tflops": tfl, "peak_tflops": pk["bf16"], "frac": tfl / pk["bf16"],
+                "note": "3 BF16 MMAs per product x executed rows; peak = dense bf16 GEMM (burst) from " + pk["source"]}
+
     def tensor_obj(d, key):
         cin, cout, K, kind, n_out = key
         return {"bound": "tensor", "achieved": d["tflops"], "peak": tf32_peak, "unit": "TFLOP/s", "frac": d["tflops"] / tf32_peak,
@@ -521,7 +532,7 @@ def rooflines(wl, raw, steps, world, dev):
                 "algorithmic_bytes_per_launch": d["algorithmic_bytes"],
                 "executed_over_algorithmic_rows": d["executed_over_algorithmic_rows"],
                 "hbm": {"achieved_gbs": d["gbs"], "peak_gbs": pk["hbm"], "frac": d["gbs"] / pk["hbm"]},
-                "l2_stream": l2_stream(d, key)}
+                "l2_stream": l2_stream(d, key), "executed_bf16": executed_bf16(d, key)}
 
     if sp is not None:
         out = tensor_obj(sp[1], sp[0])
