@@ -88,7 +88,11 @@ struct B2Cfg {
   static constexpr int MW = SWAP ? 2 : T;                      // MMA warps (swapped: two issuers that alternate blocks)
   static constexpr int CTAS_PER_SM = S == 4 ? 2 : 1;
   static constexpr int NB = S / T;                             // gathered-tile slots per tile (stage = slot * T + t)
-  static constexpr int SB = S == 4 ? (COUT >= 64 ? 2 : 4) : (COUT >= 128 ? 3 : 4);   // weight-tile ring
+  // weight-tile ring.  Swapped operands: FOUR stages -- the issuing warps waited 17 % of their time for weight tiles with
+  // three (two blocks of look-ahead do not always cover a 16 KB bulk copy under load); the epilogue stages 16 instead of 32
+  // rows per item there, which pays for the extra stage
+  static constexpr int SB = S == 4 ? (COUT >= 64 ? 2 : 4) : (COUT >= 128 ? (SWAP ? 4 : 3) : 4);
+  static constexpr int EPI_ROWS = SWAP ? 16 : 32;              // rows staged at a time per epilogue warp
   static constexpr int UTIL_WARP = S * PW;
   static constexpr int MMA_WARP0 = S * PW + 1;
   static constexpr int EPI_WARPS = 8;                          // two per TMEM lane quarter: they split the (tile, column chunk) items
@@ -102,7 +106,7 @@ struct B2Cfg {
   static constexpr int TMEM_COLS = ACC_COLS <= 32 ? 32 : ACC_COLS <= 64 ? 64 : ACC_COLS <= 128 ? 128 : ACC_COLS <= 256 ? 256 : 512;
   static constexpr int EPC = COUT < 32 ? COUT : 32;
   static constexpr int LIST_BYTES = 2 * kB2ListCap * 2;
-  static constexpr int EPI_BYTES = EPI_WARPS * 32 * kB2EpiRow;
+  static constexpr int EPI_BYTES = EPI_WARPS * EPI_ROWS * kB2EpiRow;
   static constexpr int BAR_BYTES = 512;
   static constexpr int SMEM_BYTES = S * kB2AStage + SB * B_STAGE + LIST_BYTES + EPI_BYTES + S * 1024 + BAR_BYTES + 1024;
   static_assert(T == 2 || T == 4, "tiles per group");
@@ -734,7 +738,7 @@ conv_bf2_kernel(const __grid_constant__ B2Args A, const __grid_constant__ CUtens
     // 1x1 layers of the neck were epilogue-bound (256->256 at 188 x 188: 585 us against 180 us for the same shape with ReLU).
     const int g4 = warp & 3;
     const int half = (warp - Cfg::EPI_WARP0) >> 2;                  // which of the quarter's two warps
-    const uint32_t stg = smem_u32(epi) + (uint32_t)(warp - Cfg::EPI_WARP0) * (32 * kB2EpiRow);
+    const uint32_t stg = smem_u32(epi) + (uint32_t)(warp - Cfg::EPI_WARP0) * (Cfg::EPI_ROWS * kB2EpiRow);
     const float* __restrict__ scale = A.scale ? A.scale + cblk : nullptr;
     const float* __restrict__ shift = A.shift ? A.shift + cblk : nullptr;
     const int act = A.act, res_after = A.res_after_act;
@@ -759,14 +763,15 @@ conv_bf2_kernel(const __grid_constant__ B2Args A, const __grid_constant__ CUtens
       tc_fence_after();
       // staged 32 rows x EPC channels of this warp -> affine / residual / activation -> whole-row stores.
       //   rbase: first of the 32 rows inside the group, c0: first channel of the staged piece, orow_l: lane r's output row
-      auto store_staged = [&](int rbase, int c0, int orow_l) {
+      auto store_staged = [&](int rbase, int c0, int orow_l, int lane0, int iters) {
         float4 sc = make_float4(1.f, 1.f, 1.f, 1.f), sh = make_float4(0.f, 0.f, 0.f, 0.f);
         if (scale) sc = __ldg(reinterpret_cast<const float4*>(scale + c0) + pp);
         if (shift) sh = __ldg(reinterpret_cast<const float4*>(shift + c0) + pp);
 #pragma unroll
         for (int jj = 0; jj < PPR; ++jj) {
+          if (jj >= iters) break;
           const int r = pr + RPI * jj;
-          const int orow = __shfl_sync(0xffffffffu, orow_l, r);
+          const int orow = __shfl_sync(0xffffffffu, orow_l, lane0 + r);
           const int row = tile0 + rbase + r;
           float4 v = lds128(stg + (uint32_t)r * kB2EpiRow + 16u * pp);
           if (row < row_end && orow >= 0 && !(A.dbg & 8)) {
@@ -802,13 +807,16 @@ conv_bf2_kernel(const __grid_constant__ B2Args A, const __grid_constant__ CUtens
           if (tile0 + rb >= row_end) break;
           const int row_l = tile0 + rb + lane;
           const int orow_l = (row_l < row_end && A.out_rows) ? __ldg(A.out_rows + row_l) : row_l;
-          uint32_t acc[32];
-          tmem_ld<32>(tmem_base + ((uint32_t)(g4 * 32) << 16) + (uint32_t)(buf * Cfg::ACC_BUF + rb), acc);
+#pragma unroll 1
+          for (int h = 0; h < 2; ++h) {                              // 16 rows at a time (Cfg::EPI_ROWS)
+            uint32_t acc[16];
+            tmem_ld<16>(tmem_base + ((uint32_t)(g4 * 32) << 16) + (uint32_t)(buf * Cfg::ACC_BUF + rb + 16 * h), acc);
 #pragma unroll
-          for (int q = 0; q < 32; ++q) sts32(stg + (uint32_t)q * kB2EpiRow + 4u * lane, (int)acc[q]);
-          __syncwarp();
-          store_staged(rb, c0, orow_l);
-          __syncwarp();
+            for (int q = 0; q < 16; ++q) sts32(stg + (uint32_t)q * kB2EpiRow + 4u * lane, (int)acc[q]);
+            __syncwarp();
+            store_staged(rb + 16 * h, c0, orow_l, 16 * h, PPR / 2);
+            __syncwarp();
+          }
         }
       } else {
 #pragma unroll 1
@@ -826,7 +834,7 @@ conv_bf2_kernel(const __grid_constant__ B2Args A, const __grid_constant__ CUtens
             sts128(stg + (uint32_t)lane * kB2EpiRow + 16u * q, __uint_as_float(acc[4 * q]), __uint_as_float(acc[4 * q + 1]),
                    __uint_as_float(acc[4 * q + 2]), __uint_as_float(acc[4 * q + 3]));
           __syncwarp();
-          store_staged(t * kBM + g4 * 32, c0, orow_l);
+          store_staged(t * kBM + g4 * 32, c0, orow_l, 0, PPR);
           __syncwarp();                                             // staged rows are consumed before the next chunk lands
         }
       }
