@@ -187,3 +187,39 @@ def test_grouped_strided_builder_equals_group_rows_of_the_scan_order_table():
         a_tbl, a_perm, a_masks = ops.table_group_rows(ops.rulebook_sparse(oc, index, 3, 2, pad), m)
         b_tbl, b_perm, b_masks = ops.rulebook_sparse_grouped(oc, index, 2, pad)
         assert torch.equal(a_perm[:m], b_perm[:m]) and torch.equal(a_tbl[:, :m], b_tbl[:, :m]) and torch.equal(a_masks, b_masks)
+
+
+def _set_variant(v):
+    import ctypes
+    from sparse2dense_b200 import _lib
+    _lib.load()
+    ctypes.CDLL(_lib.LIB_PATH).s2d_debug_bf2_variant(int(v))
+
+
+@pytest.mark.parametrize("cin,cout,n", [(128, 128, 562), (64, 128, 1300), (128, 256, 3001)])
+def test_swapped_operand_kernel_variants_agree(cin, cout, n):
+    """128 output channels run with swapped operands and two alternating issuer warps (conv_bf2.cu).  On a grouped rulebook
+    whose tiles differ in their live offsets (so that one tile of a group starts accumulating before the other), with an ODD
+    number of tiles (562 rows = 4 tiles + 50 rows: the last group has one tile) and with two output-channel blocks: the result
+    matches the fp64 oracle, is bit-identical between the dynamic tile-group scheduler and the static round robin (variant 4),
+    and agrees with the unswapped kernel (variant 2) to the per-layer tolerance."""
+    shape, batch, coors, feats, w = make_case(cin, cout, n, 11 * cin + cout + n)
+    rt, _ = R.rulebook_subm(coors, shape, 3)
+    ref = R.spconv_fwd(feats, w, rt, wide=True)
+    c = torch.from_numpy(coors).cuda()
+    tbl = ops.rulebook_subm(c, ops.build_grid_index(c, batch, shape), 3)
+    gt, perm, masks = ops.table_group_rows(tbl, n)
+    assert len(set(int(m) for m in masks.cpu().tolist())) > 1            # tiles with different live offsets
+    x, wt = torch.from_numpy(feats).cuda(), torch.from_numpy(w).cuda()
+    pk = ops.pack_weights_tf32(wt, ops.PRECISION_BF16X2)
+    outs = {}
+    try:
+        for v in (0, 4, 2):
+            _set_variant(v)
+            outs[v] = ops.spconv_fwd(x, wt, gt, n, precision=ops.PRECISION_BF16X2, packed=pk, tile_masks=masks,
+                                     out_rows=perm).cpu().numpy()
+    finally:
+        _set_variant(0)
+    assert rel_err(outs[0], ref) < TOL
+    np.testing.assert_array_equal(outs[0], outs[4])
+    assert rel_err(outs[2], outs[0]) < TOL
