@@ -248,8 +248,13 @@ __global__ void __launch_bounds__(kWtThreads, 1) wgrad_tc_kernel(const __grid_co
       }
     }
   } else {
-    // ===================== MMA issue (one lane) =====================
-    if (lane == 0) {
+    // ===================== MMA issue (one elected lane, warp-uniform control flow) =====================
+    // The whole warp walks the loop and only the issue is predicated: every descriptor is a warp-uniform value, so ptxas
+    // keeps it in uniform registers.  (Issuing from inside `if (lane == 0)` made it wrap each UTCHMMA in an R2UR waterfall
+    // loop that reuses the same uniform registers and therefore waits ~140 clk for the previous MMA to release them:
+    // tools/mma_probe.cu.)
+    {
+      const bool leader = elect_one();
       const uint32_t idesc = make_idesc_bf16(kBM, 64 * nb) | (1u << 15) | (1u << 16);       // A and B MN-major
       const int mbs = (na + 1) / 2;
 #pragma unroll 1
@@ -258,18 +263,32 @@ __global__ void __launch_bounds__(kWtThreads, 1) wgrad_tc_kernel(const __grid_co
         mbar_wait(smem_u32(bar_full + s), (uint32_t)(j / S) & 1u);
         tc_fence_after();
         const uint32_t stage = smem0 + (uint32_t)s * Cfg::STAGE;
-        for (int mb = 0; mb < mbs; ++mb) {
-          const uint32_t lbo_a = (2 * mb + 1 < na) ? (uint32_t)kWtChunk : 0u;   // a lone chunk is mirrored into lanes 64-127
+        // all descriptors first, then the MMAs back to back in one predicated block (distinct uniform registers: an MMA
+        // holds its descriptor registers for ~140 clk after issue, rewriting them would wait that long)
+        uint64_t da[Cfg::MB][kWtRows / 16], dbb[kWtRows / 16];
 #pragma unroll
-          for (int ks = 0; ks < kWtRows / 16; ++ks) {
-            const uint64_t da = wt_desc(stage + (uint32_t)(2 * mb) * kWtChunk + (uint32_t)ks * 2048u, lbo_a, 1024u);
-            const uint64_t dbb = wt_desc(stage + (uint32_t)NA * kWtChunk + (uint32_t)ks * 2048u, (uint32_t)kWtChunk, 1024u);
-            wt_mma(tmem_base + (uint32_t)(mb * 64 * NB), da, dbb, idesc, (j > 0 || ks > 0) ? 1u : 0u);
+        for (int ks = 0; ks < kWtRows / 16; ++ks) {
+          dbb[ks] = wt_desc(stage + (uint32_t)NA * kWtChunk + (uint32_t)ks * 2048u, (uint32_t)kWtChunk, 1024u);
+#pragma unroll
+          for (int mb = 0; mb < Cfg::MB; ++mb) {
+            const uint32_t lbo_a = (2 * mb + 1 < na) ? (uint32_t)kWtChunk : 0u;   // a lone chunk is mirrored into lanes 64-127
+            da[mb][ks] = wt_desc(stage + (uint32_t)(2 * mb) * kWtChunk + (uint32_t)ks * 2048u, lbo_a, 1024u);
           }
         }
-        umma_commit(smem_u32(bar_empty + s));
+        if (leader) {
+#pragma unroll
+          for (int mb = 0; mb < Cfg::MB; ++mb) {
+            if (mb < mbs) {
+#pragma unroll
+              for (int ks = 0; ks < kWtRows / 16; ++ks)
+                wt_mma(tmem_base + (uint32_t)(mb * 64 * NB), da[mb][ks], dbb[ks], idesc, (j > 0 || ks > 0) ? 1u : 0u);
+            }
+          }
+          umma_commit(smem_u32(bar_empty + s));
+        }
+        __syncwarp();
       }
-      if (n_slabs > 0) umma_commit(smem_u32(bar_acc));
+      if (n_slabs > 0 && leader) umma_commit(smem_u32(bar_acc));
     }
     __syncwarp();
   }

@@ -36,6 +36,7 @@ def main():
     ap.add_argument("--dense", action="store_true", help="also time dense 3x3 / 1x1 convs of the neck shapes")
     ap.add_argument("--ablate", default="", help="comma list of ablation flag sets (see conv_bf2.cu B2Args::dbg), timed with variant 0")
     ap.add_argument("--only", type=int, default=0)
+    ap.add_argument("--wgrad", action="store_true", help="also time the tensor-core weight gradient of each layer")
     ap.add_argument("--insitu", action="store_true", help="also time the grouped layer with BN affine + residual + ReLU")
     ap.add_argument("--prof", action="store_true", help="print the in-kernel cycle counters (producer / MMA waits)")
     args = ap.parse_args()
@@ -109,6 +110,13 @@ def main():
             print(f"   grouped {c:3d}: {len(mg)} groups of {T} tiles, {int(blocks.sum())} blocks ({blocks.min()}..{blocks.max()} per group), "
                   f"{int(tile_blocks)} live tile-blocks = {tile_blocks / max(1, blocks.sum()):.2f} per block; "
                   f"{clk / blocks.sum():.0f} clk per block, {clk / tile_blocks:.0f} clk per live tile-block", flush=True)
+        if args.wgrad and c >= 32:       # tensor-core weight gradient of the same layer (wgrad_tc.cu)
+            from sparse2dense_b200 import autograd as AG
+            dy = torch.randn(n, c, device="cuda")
+            ops.rows_split(dy, cache=True)
+            ops.rows_split(feats, cache=True)
+            t_w = timeit(lambda: AG.conv_wgrad(feats, dy, tbl, n), flush, args.reps)
+            print(f"   wgrad {c:3d}x{c:3d} K=27 rows {n}: {t_w:.3f} ms", flush=True)
         if args.insitu:      # as the layer runs inside a residual block: BN affine + residual + ReLU, grouped rulebook
             sc, sh, res = torch.rand(c, device="cuda") + 0.5, torch.randn(c, device="cuda"), torch.randn(n, c, device="cuda")
             line = f"   in-situ {c:3d} (grouped, affine + residual + ReLU):"
