@@ -401,6 +401,17 @@ conv_bf2_kernel(const __grid_constant__ B2Args A, const __grid_constant__ CUtens
             }
           }
           cp_async_commit();
+          // While these copies fly: pull the rows of this warp's NEXT block into L2 (its indices were requested before the
+          // copies were issued).  A stage is published when its slowest row has landed, and with 20-25 % of the sectors
+          // coming from DRAM nearly every stage has such a row; the next block's copies then find all their lines in L2.
+          if (kps == 1 && !(A.dbg & 1024) && ((e_n >> (5 + my_t)) & 1u)) {
+            const uint32_t cu = (e_n >> 9) * 8u;
+            const int pi[4] = {qa_n.x, qa_n.y, qa_n.z, qa_n.w};
+#pragma unroll
+            for (int rr = 0; rr < 4; ++rr)
+              if (pi[rr] >= 0)
+                asm volatile("prefetch.global.L2 [%0];" ::"l"(in_bytes + ((size_t)((uint32_t)pi[rr] * row_units + cu) << 4)));
+          }
           c0 = prof ? clock64() : 0;
           cp_async_wait<0>();                                  // this lane's pieces have landed ...
           if (prof) pw_data += clock64() - c0;

@@ -134,7 +134,7 @@ def main():
             setv(0)
             print(line, flush=True)
             line = f"   in-situ {c:3d} cache-policy flags (affine + residual + ReLU):"
-            for fl in (0, 256, 512, 768):
+            for fl in (0, 256, 512, 768, 1024):
                 setf(fl)
                 t = timeit(lambda: ops.spconv_fwd(feats, w, gt, n, scale=sc, shift=sh, residual=res, relu=True,
                                                   precision=ops.PRECISION_BF16X2, packed=pk, out=out, tile_masks=gmasks,
