@@ -998,6 +998,13 @@ __global__ void __launch_bounds__(128) group_permute_table_kernel(const int* __r
 // concurrently on different streams never share one
 constexpr int kB2SchedSlots = 256;
 __device__ unsigned int g_b2_sched[kB2SchedSlots][16];
+// next slot, shared by every instantiation of the kernel (one rotation for the whole library)
+static unsigned int* b2_sched_slot() {
+  static unsigned int* slots = nullptr;
+  static std::atomic<unsigned> next{0};
+  if (!slots && cudaGetSymbolAddress(reinterpret_cast<void**>(&slots), g_b2_sched) != cudaSuccess) return nullptr;
+  return slots + (size_t)(next.fetch_add(1) % kB2SchedSlots) * 16;
+}
 static int g_b2_variant = 0;
 static int g_b2_dbg = 0;
 static long long* g_b2_prof = nullptr;
@@ -1030,10 +1037,8 @@ static int launch_b2(const B2Args& a, const CUtensorMap& map, int Cout, cudaStre
   const dim3 grid(gx, gy);
   b.sched = nullptr;
   if (a.tile_masks && gy <= 8 && !(g_b2_variant & 4)) {   // masked (grouped) launches: groups differ in cost -> dynamic scheduler
-    static unsigned int* slots = nullptr;
-    static std::atomic<unsigned> next{0};
-    if (!slots) S2D_CUDA(cudaGetSymbolAddress(reinterpret_cast<void**>(&slots), g_b2_sched));
-    b.sched = slots + (size_t)(next.fetch_add(1) % kB2SchedSlots) * 16;
+    b.sched = b2_sched_slot();
+    S2D_REQUIRE(b.sched, "s2d_conv_fwd(bf16x2): cannot resolve the scheduler slots");
   }
   conv_bf2_kernel<COUT, T, S, TMA, SWAP, PW><<<grid, Cfg::THREADS, Cfg::SMEM_BYTES, st>>>(b, map);
   S2D_LAUNCH_CHECK();
