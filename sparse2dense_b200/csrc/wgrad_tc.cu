@@ -139,15 +139,30 @@ __global__ void __launch_bounds__(kWtThreads, 1) wgrad_tc_kernel(const __grid_co
         }
       }
     };
-    int ia[RQ][4], id[RQ];
-    indices(0, ia, id);
+    // Index loads run TWO stages ahead of their use and the table lines are pulled into L2 eight stages ahead: with one
+    // stage of look-ahead the gather threads spent 30 % of their samples waiting for the indices of the stage they were
+    // about to copy (ncu source page: long-scoreboard stall on the first use of the index registers) -- the table is
+    // streamed once per launch and offset, so every one of those loads went to DRAM.
+    constexpr int kIdxAhead = 8;
+    auto prefetch_table = [&](int slab) {
+      if (slab >= n_slabs || (tid & 7) != 0) return;           // one lane per row group; 32 rows x 4 B = one 128 B line per tap
+      const int i = row0 + slab * kWtRows;
+      if (rg < ntaps) asm volatile("prefetch.global.L2 [%0];" ::"l"(tk + (size_t)rg * A.tbl_stride + i));
+      if (rg == 4 && A.d_rows) asm volatile("prefetch.global.L2 [%0];" ::"l"(A.d_rows + i));
+    };
+    // three index register sets rotate by NAME over a loop unrolled by three (a copy "cur = next" at the end of an
+    // iteration would be the first use of the loaded registers and stall right there)
+    int ia0[RQ][4], id0[RQ], ia1[RQ][4], id1[RQ], ia2[RQ][4], id2[RQ];
+    for (int pj = 0; pj < kIdxAhead; ++pj) prefetch_table(pj);
+    indices(0, ia0, id0);
+    indices(1, ia1, id1);
     const bool multi = A.tpc > 1;                            // several kernel offsets per CTA: chunk c -> offset c / cpt
-#pragma unroll 1
-    for (int j = 0; j < n_slabs; ++j) {
+    // one stage: copies of slab j from the indices (ia, id); the indices of slab j + 2 go into (la, ld)
+    auto stage_step = [&](int j, int (&ia)[RQ][4], int (&id)[RQ], int (&la)[RQ][4], int (&ld)[RQ]) {
       const int s = j % S;
       if (j >= S) mbar_wait(smem_u32(bar_empty + s), (uint32_t)((j / S) - 1) & 1u);
-      int ia_n[RQ][4], id_n[RQ];
-      if (j + 1 < n_slabs) indices(j + 1, ia_n, id_n);       // next stage's index loads fly under this stage's copies
+      prefetch_table(j + kIdxAhead);
+      indices(j + 2, la, ld);                                // (past the end: all -1, no loads)
       const uint32_t stage = smem0 + (uint32_t)s * Cfg::STAGE;
 #pragma unroll
       for (int q = 0; q < RQ; ++q) {
@@ -170,18 +185,16 @@ __global__ void __launch_bounds__(kWtThreads, 1) wgrad_tc_kernel(const __grid_co
       }
       cp_async_commit();
       if (j >= kWtLag) {
-        cp_async_wait<kWtLag>();                             // the copies of stage j - 2 have landed ...
+        cp_async_wait<kWtLag>();                             // the copies of stage j - 3 have landed ...
         fence_proxy_async();                                 // ... and are visible to the tensor core (async proxy)
         mbar_arrive(smem_u32(bar_full + (j - kWtLag) % S));
       }
-      if (j + 1 < n_slabs) {
-#pragma unroll
-        for (int q = 0; q < RQ; ++q) {
-#pragma unroll
-          for (int t = 0; t < 4; ++t) ia[q][t] = ia_n[q][t];
-          id[q] = id_n[q];
-        }
-      }
+    };
+#pragma unroll 1
+    for (int j = 0; j < n_slabs; j += 3) {
+      stage_step(j, ia0, id0, ia2, id2);
+      if (j + 1 < n_slabs) stage_step(j + 1, ia1, id1, ia0, id0);
+      if (j + 2 < n_slabs) stage_step(j + 2, ia2, id2, ia1, id1);
     }
     // drain: publish the last (up to kWtLag) stages in order
     if (n_slabs >= 3) {
