@@ -16,11 +16,12 @@
 // ever converted or transposed in registers: the gather is cp.async straight into the operand tile.
 //
 //   CTA = (row chunk, kernel offset k, block of <= 4 G-chunks x <= 4 D-chunks) -> 128 x 128 channels of dW[k] for its rows
-//   warps 0-3  gather 64-row stages (two threads per row; up to 64 x 16 B cp.async per stage and thread), publish a
-//              stage two stages later (cp.async.wait_group 2 -> fence.proxy.async -> mbarrier), then run the epilogue:
-//              tcgen05.ld, quadrant sums (hi/lo lanes live in different warps: exchanged through shared memory), partial
-//              result of the chunk to the workspace
-//   warp 4     TMEM allocation; one lane issues (na + 1) / 2 x 4 MMAs (M = 128, N = 64 nb, K = 16 rows) per stage and
+//   warps 0-7  gather 32-row stages (eight lanes per 128 B row, one row per thread: up to 8 x 16 B cp.async per stage and
+//              thread), indices loaded two stages ahead, table lines prefetched into L2; a stage is published three
+//              stages after it was issued (cp.async.wait_group 3 -> fence.proxy.async -> mbarrier).  Warps 0-3 then run the
+//              epilogue: tcgen05.ld, quadrant sums (hi/lo lanes live in different warps: exchanged through shared memory),
+//              partial result of the chunk to the workspace
+//   warp 8     TMEM allocation; one elected lane issues (na + 1) / 2 x 2 MMAs (M = 128, N = 64 nb, K = 16 rows) per stage and
 //              releases it with tcgen05.commit
 // Row chunks bound the length of one TMEM accumulation (the tensor core truncates when it aligns addends) and
 // fill the GPU; their partial results are summed in a fixed order (deterministic).
@@ -35,7 +36,12 @@ constexpr int kWtChunk = kWtRows * 128;    // bytes of one 32-channel chunk of a
 // S - kWtLag stages ahead of the tensor core.  (First version: 64-row stages, S = 3, lag 2 -> one stage of slack, i.e. MMA,
 // issue and barrier round trip fully serialised: 4.1 k clk per 64 rows against 1 k clk of MMA time.)
 constexpr int kWtLag = 3;
-constexpr int kWtThreads = 160;
+// Eight gather warps (one row per thread and stage) + the MMA warp.  With four (two rows per thread) the gather warps were
+// bound by their own instruction stream -- 64-bit address arithmetic for 16 copies per thread and stage: ncu showed them
+// issuing or in fixed-latency dependency stalls ~75 % of the time -- while shared memory held room for more copies in flight.
+constexpr int kWtGatherWarps = 8;
+constexpr int kWtRowGroups = kWtGatherWarps * 4;          // row groups of a stage: eight lanes copy one 128 B row
+constexpr int kWtThreads = 32 * (kWtGatherWarps + 1);
 
 struct WtArgs {
   const uint32_t* g;
@@ -99,10 +105,10 @@ __global__ void __launch_bounds__(kWtThreads, 1) wgrad_tc_kernel(const __grid_co
   const int n_slabs = row_end > row0 ? (row_end - row0 + kWtRows - 1) / kWtRows : 0;
   const uint32_t smem0 = smem_u32(smem);
 
-  if (warp == 4) {
+  if (warp == kWtGatherWarps) {
     if (lane == 0) {
       for (int s = 0; s < S; ++s) {
-        mbar_init(smem_u32(bar_full + s), 128);             // every gather thread, once its copies have landed
+        mbar_init(smem_u32(bar_full + s), 32 * kWtGatherWarps);   // every gather thread, once its copies have landed
         mbar_init(smem_u32(bar_empty + s), 1);              // tcgen05.commit of the MMAs that read the stage
       }
       mbar_init(smem_u32(bar_acc), 1);
@@ -116,12 +122,12 @@ __global__ void __launch_bounds__(kWtThreads, 1) wgrad_tc_kernel(const __grid_co
   tc_fence_after();
   const uint32_t tmem_base = *s_tmem;
 
-  if (warp < 4) {
+  if (warp < kWtGatherWarps) {
     // ===================== gather: thread = (16 B piece of a 128 B chunk row, row group); four rows per thread ==========
     // Eight lanes copy one whole 128 B row of a chunk, so a warp instruction moves four full rows (the first version gave
     // a thread half a row: 32 half-used sectors per instruction, and the kernel ran at 10 B/clk/SM).
-    constexpr int RQ = kWtRows / 16;                         // rows per thread and stage
-    const int piece = tid & 7, rg = tid >> 3;                // rows rg, rg + 16 of the stage
+    constexpr int RQ = kWtRows / kWtRowGroups;               // rows per thread and stage
+    const int piece = tid & 7, rg = tid >> 3;                // row rg of the stage
     const char* gb = reinterpret_cast<const char*>(A.g) + (size_t)a0 * 128 + piece * 16;
     const char* db = reinterpret_cast<const char*>(A.d) + (size_t)b0 * 128 + piece * 16;
     const size_t g_row = (size_t)A.g_ld * 4, d_row = (size_t)A.d_ld * 4;
@@ -129,7 +135,7 @@ __global__ void __launch_bounds__(kWtThreads, 1) wgrad_tc_kernel(const __grid_co
     auto indices = [&](int slab, int (&ia)[RQ][4], int (&id)[RQ]) {
 #pragma unroll
       for (int q = 0; q < RQ; ++q) {
-        const int i = row0 + slab * kWtRows + q * 16 + rg;
+        const int i = row0 + slab * kWtRows + q * kWtRowGroups + rg;
         ia[q][0] = ia[q][1] = ia[q][2] = ia[q][3] = id[q] = -1;
         if (i < row_end) {
 #pragma unroll
@@ -166,7 +172,7 @@ __global__ void __launch_bounds__(kWtThreads, 1) wgrad_tc_kernel(const __grid_co
       const uint32_t stage = smem0 + (uint32_t)s * Cfg::STAGE;
 #pragma unroll
       for (int q = 0; q < RQ; ++q) {
-        const int r = q * 16 + rg;
+        const int r = q * kWtRowGroups + rg;
         const uint32_t dst = stage + (uint32_t)r * 128u + (uint32_t)((piece ^ (r & 7)) << 4);
 #pragma unroll
         for (int c = 0; c < NA; ++c) {
@@ -213,7 +219,8 @@ __global__ void __launch_bounds__(kWtThreads, 1) wgrad_tc_kernel(const __grid_co
       mbar_arrive(smem_u32(bar_full + (n_slabs - 1) % S));
     }
 
-    // ===================== epilogue: quadrant sums -> partial[chunk][k][a][b] =====================
+    // ===================== epilogue (warps 0-3, one per TMEM lane quarter): quadrant sums -> partial[chunk][k][a][b] =========
+    if (warp < 4) {
     if (n_slabs > 0) {
       mbar_wait(smem_u32(bar_acc), 0u);
       tc_fence_after();
@@ -259,6 +266,7 @@ __global__ void __launch_bounds__(kWtThreads, 1) wgrad_tc_kernel(const __grid_co
         }
         wt_bar_sync();
       }
+    }
     }
   } else {
     // ===================== MMA issue (one elected lane, warp-uniform control flow) =====================
@@ -308,7 +316,7 @@ __global__ void __launch_bounds__(kWtThreads, 1) wgrad_tc_kernel(const __grid_co
 
   tc_fence_before();
   __syncthreads();
-  if (warp == 4) tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
+  if (warp == kWtGatherWarps) tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
 }
 
 __global__ void wt_reduce_kernel(const float* __restrict__ partial, int n_chunks, long long n_elem, int accumulate,
