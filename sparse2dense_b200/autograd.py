@@ -23,9 +23,14 @@ def _ptr(t):
 class Table:
     """A k-major neighbour table with its lazily built transpose (for the data gradient)."""
 
-    def __init__(self, tbl, n_in, n_out, symmetric=False, out_rows=None):
+    def __init__(self, tbl, n_in, n_out, symmetric=False, out_rows=None, grouped=None):
         self.tbl, self.n_in, self.n_out, self.symmetric, self.out_rows = tbl, int(n_in), int(n_out), symmetric, out_rows
         self._inv = None
+        # (table in grouped row order, perm, tile masks) of a 27-offset sparse rulebook (conv_bf2.cu "Row grouping"): the
+        # forward -- and for a submanifold table, which is its own transpose with the taps reversed, the data gradient --
+        # skip the (tile, offset) blocks without neighbours, with bit-identical results.  The scan-order ``tbl`` stays for
+        # the weight gradient.
+        self.grouped = grouped
 
     def transposed(self):
         """inv[k][j] = i  <=>  tbl[k][i] = j.  A SubM table is its own transpose with the taps reversed."""
@@ -78,7 +83,7 @@ def _pad_channels(c, is_input):
     return -(-c // 16) * 16
 
 
-def conv_rows_tc(x, w, tbl, n_out, precision, out_rows=None, n_total=None):
+def conv_rows_tc(x, w, tbl, n_out, precision, out_rows=None, n_total=None, grouped=None):
     """conv_rows that keeps small-channel layers (the 3-channel generators of the PCR branch, the 1..3-channel head
     convolutions and their data gradients) on the tensor-core kernel by zero-padding the channel counts, when there is
     enough work per row to pay for the padded traffic; otherwise the exact-shape kernel.  With ``out_rows`` the result
@@ -97,10 +102,17 @@ def conv_rows_tc(x, w, tbl, n_out, precision, out_rows=None, n_total=None):
             wp[:, :cin, :cout] = w
             w = wp
     cout_eff = w.shape[2]
+    tile_masks = None
+    if grouped is not None and out_rows is None and \
+            ops.effective_precision(precision, x.shape[1], cout_eff, grouped[0]) == ops.PRECISION_BF16X2:
+        # ``grouped`` = (tbl in grouped row order, perm, tile masks) of the same rulebook: the BF16-pair kernel skips the
+        # (tile, offset) blocks without neighbours and scatters through perm -- bit-identical to the plain launch
+        tbl, out_rows, tile_masks = grouped
+        n_total = n_out
     out = None
     if out_rows is not None:
         out = torch.empty((n_total, cout_eff), dtype=torch.float32, device=x.device)
-    y = conv_rows(x, w.contiguous(), tbl, n_out, out=out, out_rows=out_rows, precision=precision)
+    y = conv_rows(x, w.contiguous(), tbl, n_out, out=out, out_rows=out_rows, precision=precision, tile_masks=tile_masks)
     return y if cout_eff == cout else y[:, :cout]
 
 
@@ -135,7 +147,7 @@ class GatherConv(torch.autograd.Function):
         w = w.contiguous()
         ctx.save_for_backward(x, w)
         ctx.table, ctx.precision = table, precision
-        return conv_rows_tc(x, w, table.tbl, table.n_out, precision)
+        return conv_rows_tc(x, w, table.tbl, table.n_out, precision, grouped=table.grouped)
 
     @staticmethod
     def backward(ctx, dy):
@@ -147,7 +159,7 @@ class GatherConv(torch.autograd.Function):
             wt = w.transpose(1, 2).contiguous()                       # [K, Cout, Cin]
             if t.symmetric:
                 wt = torch.flip(wt, dims=[0])
-                dx = conv_rows_tc(dy, wt, t.tbl, t.n_in, ctx.precision)
+                dx = conv_rows_tc(dy, wt, t.tbl, t.n_in, ctx.precision, grouped=t.grouped)   # same table, taps of W reversed
             else:
                 dx = conv_rows_tc(dy, wt, t.transposed(), t.n_in, ctx.precision)
         if ctx.needs_input_grad[1]:

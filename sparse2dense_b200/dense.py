@@ -144,7 +144,7 @@ GRID_TMA = int(__import__("os").environ.get("S2D_GRID_TMA", "1"))     # 0: table
 
 def conv_rows(x, weight_kio, tbl, n_out, scale=None, shift=None, act=ACT_NONE, residual=None, res_after_act=False,
               out=None, out_rows=None, precision=ops.PRECISION_TF32X3, packed=None, out_split=None, want_split=True,
-              grid=None):
+              grid=None, tile_masks=None):
     """One gather-GEMM launch.  x / out / residual: 2-D views with stride(1) == 1; weight_kio: [K,Cin,Cout].
     ``packed``: a weight image for ``ops.effective_precision(precision, ...)`` or a dict precision -> image.
     With the BF16-pair kernel the input is read in split-row form (the producer's twin when ``x`` carries one, else
@@ -187,8 +187,9 @@ def conv_rows(x, weight_kio, tbl, n_out, scale=None, shift=None, act=ACT_NONE, r
         ops.conv_launch(x, w, None, n_tile_rows, cin, cout, K, scale, shift, act, residual, res_after_act, out, rows, prec, xs,
                         out_split, grid=grid)
     else:
+        assert tile_masks is None or prec == ops.PRECISION_BF16X2, "tile masks need the BF16-pair kernel"
         ops.conv_launch(x, w, tbl, n_out, cin, cout, K, scale, shift, act, residual, res_after_act, out, out_rows, prec, xs,
-                        out_split)
+                        out_split, tile_masks)
     if out_split is not None and fresh:
         ops.set_split(out, out_split)
     return out

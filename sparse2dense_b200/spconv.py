@@ -227,9 +227,15 @@ class SparseConvolution(SparseModule):
         -> ReLU, each with its backward in libs2d_b200.so (autograd.py)."""
         from . import autograd as AG
         table = ind.__dict__.get("table")
-        if table is None:
-            table = ind.table = AG.Table(ind.tbl, x.features.shape[0], ind.out_indices.shape[0], symmetric=self.subm)
         K = self.kernel_size[0] * self.kernel_size[1] * self.kernel_size[2]
+        if table is None:
+            n_out = ind.out_indices.shape[0]
+            grouped = ind.__dict__.get("grouped")
+            if grouped is not None and grouped[1] is None:
+                grouped = None                              # masks of an ungrouped table: not what the training path wants
+            if grouped is None and K == 27 and n_out > 0 and GROUP_ROWS >= (1 if self.subm else 2):
+                grouped = ops.table_group_rows(ind.tbl, n_out)
+            table = ind.table = AG.Table(ind.tbl, x.features.shape[0], n_out, symmetric=self.subm, grouped=grouped)
         w = self.weight.view(K, self.in_channels, self.out_channels)
         y = AG.GatherConv.apply(x.features, w, table, self.precision)
         act = 1 if relu else 0
