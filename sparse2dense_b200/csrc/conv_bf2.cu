@@ -140,7 +140,8 @@ struct B2Args {
   unsigned int* sched;   // dynamic group scheduler: [gridDim.y] next-group counters + CTA exit counter at [15]; null = static
   long long* prof;   // optional [gridDim.x][16] cycle counters (tools/microbench_bf2.py --prof), null in production
   int dbg;   // ablation switches (tools/microbench_bf2.py): 1 no gather, 2 no MMA, 4 no weight copies, 8 no stores, 16 all rows
-             // missing, 64 no index loads, 128 no epilogue
+             // missing, 64 no index loads, 128 no epilogue, 256 no evict-last hint on the gathers, 512 plain (not evict-first)
+             // table loads, 1024 no L2 prefetch of the next block's rows
 };
 
 constexpr int kGridTW = 16, kGridTH = 8;   // pixels of a dense-grid tile (16 x 8 = 128 rows)
@@ -1202,7 +1203,9 @@ int pack_weights_bf2(const float* W, int K, int Cin, int Cout, void* packed, cud
 
 using namespace s2d;
 
-// which (tiles per CTA, A stages, B stages) instantiation conv_fwd_bf2 launches (tuning aid; not part of the public header)
+// which instantiation conv_fwd_bf2 launches (tuning aid; not part of the public header): low two bits 1 = two tiles per group
+// for Cout <= 64, 2 = the unswapped kernel for Cout = 128; bit 4 = static round robin instead of the dynamic group scheduler;
+// bit 8 = TMA gather4 producers (experiment, 2x slower); bit 16 = two producer warps per stage at Cout = 128 (no gain)
 extern "C" void s2d_debug_bf2_variant(int v) { g_b2_variant = v; }
 extern "C" void s2d_debug_bf2_flags(int f) { g_b2_dbg = f; }
 extern "C" void s2d_debug_bf2_prof(long long* p) { g_b2_prof = p; }
