@@ -202,10 +202,10 @@ conv_bf2_kernel(const __grid_constant__ B2Args A, const __grid_constant__ CUtens
   uint64_t* bar_list_empty = bar_list_full + 2;                  // [2]
   uint64_t* bar_acc_full = bar_list_empty + 2;                   // [2]
   uint64_t* bar_acc_empty = bar_acc_full + 2;                    // [2]
-  uint64_t* bar_turn = bar_acc_empty + 2;                        // [2]  swapped operands: issuer p may issue its next block
-  uint32_t* s_tmem = reinterpret_cast<uint32_t*>(bar_turn + 2);
+  uint32_t* s_tmem = reinterpret_cast<uint32_t*>(bar_acc_empty + 2);
   uint32_t* s_nblocks = s_tmem + 1;                              // [2]
   volatile int* s_group = reinterpret_cast<volatile int*>(s_nblocks + 2);   // [2] tile group of the list buffer, -1 = no more work
+  volatile uint32_t* s_turn = reinterpret_cast<volatile uint32_t*>(s_nblocks + 4);   // swapped operands: next block that may issue
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   if ((int)blockIdx.x >= n_groups) return;
@@ -224,8 +224,8 @@ conv_bf2_kernel(const __grid_constant__ B2Args A, const __grid_constant__ CUtens
       mbar_init(smem_u32(bar_list_empty + s), (TMA ? 1 : kB2ProducerWarps) + MW + Cfg::EPI_WARPS);   // every reader of the list / group id
       mbar_init(smem_u32(bar_acc_full + s), MW);                  // every MMA warp after its last MMA of the group
       mbar_init(smem_u32(bar_acc_empty + s), Cfg::EPI_WARPS);     // the epilogue warps
-      mbar_init(smem_u32(bar_turn + s), 1);
     }
+    *s_turn = 0u;
     fence_barrier_init();
   }
   if (warp == kB2UtilWarp) tmem_alloc(smem_u32(s_tmem), Cfg::TMEM_COLS);
@@ -549,8 +549,9 @@ conv_bf2_kernel(const __grid_constant__ B2Args A, const __grid_constant__ CUtens
       // idles: with one issuer per tile the Cout = 128 kernels sat at 60-70 % tensor activity.  Here the WEIGHT tile is the
       // M = 128 operand and the gathered tiles of both tiles of the group ONE N = 256 operand (stages (slot, 0) and (slot, 1)
       // are adjacent: 256 rows x 128 B), a block is six 128 clk MMAs, and two warps take turns: while one issues block i, the
-      // other waits for the operands of block i + 1 and builds its descriptors, then only needs the `turn` hand-off (~80 clk).
-      // The turn barrier also fixes the order in which the MMAs reach the pipe, so sums are reproducible.  The accumulator is
+      // other waits for the operands of block i + 1 and builds its descriptors, then only needs the `turn` hand-off (a block
+      // counter in shared memory that the waiting warp polls).  The turn also fixes the order in which the MMAs reach the
+      // pipe, so sums are reproducible.  The accumulator is
       // transposed (TMEM lane = output channel, column = row of the group); the epilogue transposes it back while staging.
       const int p = warp - kB2MmaWarp0;                           // this warp issues the blocks with (gblk + ib) & 1 == p
       constexpr uint32_t idesc2 = make_idesc_bf16(COUT, 2 * kBM), idesc1 = make_idesc_bf16(COUT, kBM);
@@ -558,7 +559,6 @@ conv_bf2_kernel(const __grid_constant__ B2Args A, const __grid_constant__ CUtens
       const uint32_t b_lo0 = ((smem_u32(b_ring) >> 4) & 0x3FFF) | (1u << 16);
       const uint32_t bar_a_full0 = smem_u32(bar_a_full), bar_a_empty0 = smem_u32(bar_a_empty);
       const uint32_t bar_b_full0 = smem_u32(bar_b_full), bar_b_empty0 = smem_u32(bar_b_empty);
-      const uint32_t bar_my_turn = smem_u32(bar_turn + p), bar_other_turn = smem_u32(bar_turn + (p ^ 1));
       const bool leader = elect_one();
       const uint64_t hi64 = (uint64_t)desc_hi << 32;
       // six MMAs: (weight slice, activation slice) pairs, small terms first (same pairs as the unswapped issue below)
@@ -580,7 +580,6 @@ conv_bf2_kernel(const __grid_constant__ B2Args A, const __grid_constant__ CUtens
         }
       };
       uint32_t a_ph = 0;                                          // phase bit per stage (this warp's slots only)
-      uint32_t turn = 0;                                          // blocks this warp has issued
       int gblk = 0, j = 0;
       long long mw_a = 0, mw_b = 0, mw_acc = 0, mw_list = 0, m_steps = 0;
       const long long m_t0 = prof ? clock64() : 0;
@@ -616,8 +615,10 @@ conv_bf2_kernel(const __grid_constant__ B2Args A, const __grid_constant__ CUtens
             if (prof) { mw_a += clock64() - c0; ++m_steps; }
             const uint32_t x_lo = a_lo0 + (uint32_t)stage0 * (kB2AStage >> 4);
             const uint32_t w_lo = b_lo0 + (uint32_t)bslot * (B_STAGE >> 4);
-            mbar_wait(bar_my_turn, (turn & 1u) ^ (uint32_t)(p ^ 1));     // the other warp has issued the block before this one
-            ++turn;
+            // the turn: block gb may issue once every block before it has (a counter in shared memory, polled; the
+            // hand-off is a plain store after the last UTCHMMA of a block -- shorter than an mbarrier round trip)
+            for (uint32_t spin = 0; *s_turn != (uint32_t)gb; ++spin)
+              if (spin > (1u << 26)) __trap();                   // bounded: a protocol bug must not hang the GPU
             tc_fence_after();
             if (leader) {
               if (!(A.dbg & 2)) {
@@ -628,7 +629,7 @@ conv_bf2_kernel(const __grid_constant__ B2Args A, const __grid_constant__ CUtens
                   if (nib & 2u) issue6(d0 + (uint32_t)kBM, w_lo, x_lo + (uint32_t)(kB2AStage >> 4), idesc1, (accm >> 1) & 1u);
                 }
               }
-              mbar_arrive(bar_other_turn);
+              *s_turn = (uint32_t)gb + 1u;
               if (nib & 1u) umma_commit(bar_a_empty0 + 8 * stage0);
               if (nib & 2u) umma_commit(bar_a_empty0 + 8 * (stage0 + 1));
               if (nib) umma_commit(bar_b_empty0 + 8 * bslot);

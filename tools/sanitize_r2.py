@@ -7,6 +7,11 @@ sys.path.insert(0, '/root/repo')
 from sparse2dense_b200 import autograd as AG, dense, ops, synth
 from sparse2dense_b200.hotpath import concat_clouds
 
+import ctypes, os
+from sparse2dense_b200 import _lib
+if os.environ.get("S2D_BF2_VARIANT"):            # e.g. 2: the unswapped kernel for 128 output channels (A/B under the tool)
+    _lib.load()
+    ctypes.CDLL(_lib.LIB_PATH).s2d_debug_bf2_variant(int(os.environ["S2D_BF2_VARIANT"]))
 pts, offs = concat_clouds([synth.small_scene(5), synth.small_scene(6)])
 vb = ops.voxelize(pts.cuda(), offs, synth.WAYMO_VOXEL, synth.WAYMO_RANGE, 5, 150000, want_voxels=False, mean_channels=5)
 n = vb.n
